@@ -1,0 +1,898 @@
+/* md_oracle.c — CPU restatement (fp64, FMA-free) of HOOMD-blue v4.8.2's pair-force step.
+ * TEST INFRASTRUCTURE ONLY (see md_oracle.h). Parity pinning: tests/test_oracle_golden.py checks this
+ * file against the reference's own golden vectors (true_pair_list.json, forces_and_energies.json,
+ * Philox KATs, Seed/Counter KATs) and against outputs of the reference itself run in the build
+ * container (tests/golden npz files, made by tests/golden/make_golden.py).
+ *
+ * Written from the algorithm description in SURVEY.md §8 / Appendix A; citations are to
+ * /root/reference paths. Nothing here is copied from the reference sources.
+ */
+#include "md_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------------------------------------------------------------- box ---- */
+
+void orc_box_set(orc_box* b, double Lx, double Ly, double Lz)
+    {
+    /* hoomd/BoxDim.h:183-200: hi = L/2, lo = -hi, Linv = 1/L */
+    double L[3] = {Lx, Ly, Lz};
+    for (int d = 0; d < 3; d++)
+        {
+        b->L[d] = L[d];
+        b->hi[d] = L[d] / 2.0;
+        b->lo[d] = -b->hi[d];
+        b->Linv[d] = (L[d] == 0.0) ? 0.0 : 1.0 / L[d];
+        b->periodic[d] = 1;
+        }
+    }
+
+void orc_make_fraction(const orc_box* b, const double p[3], const double gw[3], double f[3])
+    {
+    /* hoomd/BoxDim.h:276-284 with zero tilt: ((p-lo)*Linv + gf) / (1 + 2 gf), gf = gw / L */
+    for (int d = 0; d < 3; d++)
+        {
+        double delta = p[d] - b->lo[d];
+        double gf = gw ? gw[d] / b->L[d] : 0.0;
+        f[d] = (delta * b->Linv[d] + gf) / (1.0 + 2.0 * gf);
+        }
+    }
+
+void orc_min_image(const orc_box* b, double w[3])
+    {
+    /* hoomd/BoxDim.h:343-389. z: one +-L shift; y, x: int(w*Linv + 0.5) multiples of L. */
+    if (b->periodic[2])
+        {
+        if (w[2] >= b->hi[2])
+            w[2] -= b->L[2];
+        else if (w[2] < b->lo[2])
+            w[2] += b->L[2];
+        }
+    for (int d = 1; d >= 0; d--)
+        {
+        if (!b->periodic[d])
+            continue;
+        if (w[d] >= b->hi[d])
+            {
+            int i = (int)(w[d] * b->Linv[d] + 0.5);
+            w[d] -= (double)i * b->L[d];
+            }
+        else if (w[d] < b->lo[d])
+            {
+            int i = (int)(-w[d] * b->Linv[d] + 0.5);
+            w[d] += (double)i * b->L[d];
+            }
+        }
+    }
+
+void orc_wrap(const orc_box* b, double w[3], int img[3])
+    {
+    /* hoomd/BoxDim.h:407-474, flags = 0, zero tilt: x then y then z; >= hi -> -L, < lo -> +L */
+    for (int d = 0; d < 3; d++)
+        {
+        if (!b->periodic[d])
+            continue;
+        if (w[d] >= b->hi[d])
+            {
+            w[d] -= b->L[d];
+            img[d]++;
+            }
+        else if (w[d] < b->lo[d])
+            {
+            w[d] += b->L[d];
+            img[d]--;
+            }
+        }
+    }
+
+/* ---------------------------------------------------------- cell list ---- */
+
+void orc_cell_dims(const orc_box* b, double width, const double gw[3], uint32_t dim[3])
+    {
+    /* hoomd/CellList.cc:83-131 (m_multiple = 1) */
+    for (int d = 0; d < 3; d++)
+        {
+        double g = gw ? gw[d] : 0.0;
+        dim[d] = (uint32_t)((b->L[d] + 2.0 * g) / width);
+        if (dim[d] == 0)
+            dim[d] = 1;
+        }
+    }
+
+uint32_t orc_cell_adj_width(const uint32_t dim[3])
+    {
+    /* hoomd/CellList.cc:252-273, radius 1 */
+    uint32_t w = 1;
+    for (int d = 0; d < 3; d++)
+        w *= (dim[d] > 3) ? 3 : dim[d];
+    return w;
+    }
+
+static int cmp_u32(const void* a, const void* b)
+    {
+    uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return (x > y) - (x < y);
+    }
+
+void orc_cell_adj(const uint32_t dim[3], uint32_t* adj)
+    {
+    /* hoomd/CellList.cc:346-402: the 27 periodic-wrapped neighbours, sorted, de-duplicated */
+    const uint32_t width = orc_cell_adj_width(dim);
+    const int mx = (int)dim[0], my = (int)dim[1], mz = (int)dim[2];
+    for (int k = 0; k < mz; k++)
+        for (int j = 0; j < my; j++)
+            for (int i = 0; i < mx; i++)
+                {
+                uint32_t tmp[27];
+                int n = 0;
+                for (int nk = k - 1; nk <= k + 1; nk++)
+                    for (int nj = j - 1; nj <= j + 1; nj++)
+                        for (int ni = i - 1; ni <= i + 1; ni++)
+                            {
+                            int wi = ni % mx, wj = nj % my, wk = nk % mz;
+                            if (wi < 0)
+                                wi += mx;
+                            if (wj < 0)
+                                wj += my;
+                            if (wk < 0)
+                                wk += mz;
+                            tmp[n++] = (uint32_t)((wk * my + wj) * mx + wi);
+                            }
+                qsort(tmp, 27, sizeof(uint32_t), cmp_u32);
+                int m = 0;
+                for (int q = 0; q < 27; q++)
+                    if (q == 0 || tmp[q] != tmp[q - 1])
+                        tmp[m++] = tmp[q];
+                uint32_t cell = (uint32_t)((k * my + j) * mx + i);
+                for (int q = 0; q < m && q < (int)width; q++)
+                    adj[(size_t)cell * width + q] = tmp[q];
+                }
+    }
+
+static int bin_of(const orc_box* b, const uint32_t dim[3], const double gw[3], const double p[3],
+                  int ijk[3], double f[3])
+    {
+    /* hoomd/CellList.cc:455-470 and hoomd/md/NeighborListBinned.cc:107-121 */
+    orc_make_fraction(b, p, gw, f);
+    for (int d = 0; d < 3; d++)
+        {
+        ijk[d] = (int)(f[d] * dim[d]);
+        if (ijk[d] == (int)dim[d] && b->periodic[d])
+            ijk[d] = 0;
+        }
+    return (ijk[2] * (int)dim[1] + ijk[1]) * (int)dim[0] + ijk[0];
+    }
+
+int orc_cell_list(const orc_box* b, const uint32_t dim[3], const double gw[3], const double* pos,
+                  uint32_t n_local, uint32_t n_total, uint32_t Nmax, uint32_t* cell_size,
+                  uint32_t* cell_idx, uint32_t conditions[3])
+    {
+    /* hoomd/CellList.cc:404-547 */
+    const size_t Nc = (size_t)dim[0] * dim[1] * dim[2];
+    memset(cell_size, 0, sizeof(uint32_t) * Nc);
+    conditions[0] = conditions[1] = conditions[2] = 0;
+    for (uint32_t n = 0; n < n_total; n++)
+        {
+        const double* p = pos + 3 * (size_t)n;
+        if (isnan(p[0]) || isnan(p[1]) || isnan(p[2]))
+            {
+            conditions[1] = n + 1;
+            continue;
+            }
+        int ijk[3];
+        double f[3];
+        int bin = bin_of(b, dim, gw, p, ijk, f);
+        int out = 0;
+        for (int d = 0; d < 3; d++)
+            if (f[d] < -0.00001 || f[d] >= 1.00001 || ijk[d] < 0 || ijk[d] >= (int)dim[d])
+                out = 1;
+        if (out)
+            {
+            if (n < n_local)
+                conditions[2] = n + 1;
+            continue;
+            }
+        uint32_t offset = cell_size[bin];
+        if (offset < Nmax)
+            cell_idx[(size_t)bin * Nmax + offset] = n;
+        else if (offset + 1 > conditions[0])
+            conditions[0] = offset + 1;
+        cell_size[bin]++;
+        }
+    return (conditions[0] || conditions[1] || conditions[2]) ? 1 : 0;
+    }
+
+/* --------------------------------------------------------- neighbour list ---- */
+
+void orc_r_listsq(const double* r_cut, uint32_t nt, double r_buff, double* r_listsq,
+                  double* rcut_max, double* rcut_max_max)
+    {
+    /* hoomd/md/NeighborList.cc:490-512 */
+    double mm = 0.0;
+    for (uint32_t i = 0; i < nt; i++)
+        {
+        double mi = 0.0;
+        for (uint32_t j = 0; j < nt; j++)
+            {
+            double rc = r_cut[j * nt + i];
+            if (rc > mi)
+                mi = rc;
+            double r_list = (rc > 0.0) ? rc + r_buff : 0.0;
+            r_listsq[j * nt + i] = r_list * r_list;
+            }
+        if (rcut_max)
+            rcut_max[i] = mi;
+        if (mi > mm)
+            mm = mi;
+        }
+    if (rcut_max_max)
+        *rcut_max_max = mm;
+    }
+
+static inline double dist_sq(const orc_box* b, const double* pi, const double* pj)
+    {
+    /* dx = pi - pj; minImage; dot = x*x + y*y + z*z left to right
+     * (hoomd/md/NeighborListBinned.cc:139-143, hoomd/VectorMath.h dot) */
+    double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
+    orc_min_image(b, dx);
+    return dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    }
+
+uint32_t* orc_nlist_binned(const orc_box* b, const double* pos, const uint32_t* type,
+                           uint32_t n_local, uint32_t n_total, const double* r_cut, uint32_t nt,
+                           double r_buff, int full, const double gw[3], uint32_t* n_neigh,
+                           uint64_t* head, uint64_t* total, uint32_t dim_out[3])
+    {
+    double* r_listsq = (double*)malloc(sizeof(double) * nt * nt);
+    double rmaxmax;
+    orc_r_listsq(r_cut, nt, r_buff, r_listsq, NULL, &rmaxmax);
+
+    /* hoomd/md/NeighborListBinned.cc:39-45: nominal width = max r_cut + buffer */
+    uint32_t dim[3];
+    orc_cell_dims(b, rmaxmax + r_buff, gw, dim);
+    if (dim_out)
+        memcpy(dim_out, dim, sizeof(dim));
+    const size_t Nc = (size_t)dim[0] * dim[1] * dim[2];
+    const uint32_t aw = orc_cell_adj_width(dim);
+    uint32_t* adj = (uint32_t*)malloc(sizeof(uint32_t) * Nc * aw);
+    orc_cell_adj(dim, adj);
+
+    /* cell list with the overflow/regrow loop of hoomd/CellList.cc:186-198 */
+    uint32_t Nmax = (uint32_t)ceil((double)n_total / (double)Nc);
+    if (Nmax == 0)
+        Nmax = 1;
+    uint32_t* cell_size = (uint32_t*)malloc(sizeof(uint32_t) * Nc);
+    uint32_t* cell_idx = NULL;
+    for (;;)
+        {
+        cell_idx = (uint32_t*)realloc(cell_idx, sizeof(uint32_t) * Nc * Nmax);
+        uint32_t cond[3];
+        orc_cell_list(b, dim, gw, pos, n_local, n_total, Nmax, cell_size, cell_idx, cond);
+        if (cond[0] > Nmax)
+            {
+            Nmax = cond[0];
+            continue;
+            }
+        break;
+        }
+
+    uint32_t* nlist = NULL;
+    /* pass 0 counts (stands in for the Nmax overflow/retry loop, hoomd/md/NeighborList.cc:411-427),
+       pass 1 fills */
+    for (int pass = 0; pass < 2; pass++)
+        {
+        for (uint32_t i = 0; i < n_local; i++)
+            {
+            const double* pi = pos + 3 * (size_t)i;
+            const uint32_t ti = type[i];
+            int ijk[3];
+            double f[3];
+            int my_cell = bin_of(b, dim, gw, pi, ijk, f);
+            uint32_t cnt = 0;
+            for (uint32_t a = 0; a < aw; a++)
+                {
+                uint32_t nc = adj[(size_t)my_cell * aw + a];
+                uint32_t sz = cell_size[nc];
+                for (uint32_t o = 0; o < sz; o++)
+                    {
+                    uint32_t j = cell_idx[(size_t)nc * Nmax + o];
+                    uint32_t tp = type[j] * nt + ti; /* Index2D(ti,tj) = tj*nt + ti */
+                    if (j == i || r_cut[tp] <= 0.0)
+                        continue;
+                    double drsq = dist_sq(b, pi, pos + 3 * (size_t)j);
+                    if (drsq <= r_listsq[tp] && (full || i < j))
+                        {
+                        if (pass)
+                            nlist[head[i] + cnt] = j;
+                        cnt++;
+                        }
+                    }
+                }
+            if (!pass)
+                n_neigh[i] = cnt;
+            }
+        if (!pass)
+            {
+            uint64_t s = 0;
+            for (uint32_t i = 0; i < n_local; i++)
+                {
+                head[i] = s;
+                s += n_neigh[i];
+                }
+            *total = s;
+            nlist = (uint32_t*)malloc(sizeof(uint32_t) * (s ? s : 1));
+            }
+        }
+    free(cell_idx);
+    free(cell_size);
+    free(adj);
+    free(r_listsq);
+    return nlist;
+    }
+
+uint32_t* orc_nlist_brute(const orc_box* b, const double* pos, const uint32_t* type, uint32_t n_local,
+                          uint32_t n_total, const double* r_cut, uint32_t nt, double r_buff, int full,
+                          uint32_t* n_neigh, uint64_t* head, uint64_t* total)
+    {
+    double* r_listsq = (double*)malloc(sizeof(double) * nt * nt);
+    orc_r_listsq(r_cut, nt, r_buff, r_listsq, NULL, NULL);
+    uint32_t* nlist = NULL;
+    for (int pass = 0; pass < 2; pass++)
+        {
+        for (uint32_t i = 0; i < n_local; i++)
+            {
+            uint32_t cnt = 0;
+            for (uint32_t j = 0; j < n_total; j++)
+                {
+                uint32_t tp = type[j] * nt + type[i];
+                if (j == i || r_cut[tp] <= 0.0)
+                    continue;
+                double drsq = dist_sq(b, pos + 3 * (size_t)i, pos + 3 * (size_t)j);
+                if (drsq <= r_listsq[tp] && (full || i < j))
+                    {
+                    if (pass)
+                        nlist[head[i] + cnt] = j;
+                    cnt++;
+                    }
+                }
+            if (!pass)
+                n_neigh[i] = cnt;
+            }
+        if (!pass)
+            {
+            uint64_t s = 0;
+            for (uint32_t i = 0; i < n_local; i++)
+                {
+                head[i] = s;
+                s += n_neigh[i];
+                }
+            *total = s;
+            nlist = (uint32_t*)malloc(sizeof(uint32_t) * (s ? s : 1));
+            }
+        }
+    free(r_listsq);
+    return nlist;
+    }
+
+void orc_free(void* p)
+    {
+    free(p);
+    }
+
+int orc_distance_check(const orc_box* b, const double* pos, const double* last_pos,
+                       const uint32_t* type, uint32_t n, const double* rcut_max, double r_buff)
+    {
+    /* hoomd/md/NeighborList.cc:1244-1269 with lambda = (1,1,1), lambda_min = 1 */
+    for (uint32_t i = 0; i < n; i++)
+        {
+        double old_rmin = rcut_max[type[i]];
+        double rmax = old_rmin + r_buff;
+        double delta_max = (rmax * 1.0 - old_rmin) / 2.0;
+        double maxsq = (delta_max > 0) ? delta_max * delta_max : 0;
+        double dx[3];
+        for (int d = 0; d < 3; d++)
+            dx[d] = pos[3 * (size_t)i + d] - 1.0 * last_pos[3 * (size_t)i + d];
+        orc_min_image(b, dx);
+        if (dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2] >= maxsq)
+            return 1;
+        }
+    return 0;
+    }
+
+/* -------------------------------------------------------------- potentials ---- */
+
+int orc_eval_lj(double rsq, double rcutsq, double epsilon, double sigma, int energy_shift,
+                double* force_divr, double* pair_eng)
+    {
+    /* params: hoomd/md/EvaluatorPairLJ.h:119-140; evaluation :162-211 */
+    double sigma_6 = sigma * sigma * sigma * sigma * sigma * sigma;
+    double epsilon_x_4 = 4.0 * epsilon;
+    double lj1 = epsilon_x_4 * sigma_6 * sigma_6;
+    double lj2 = epsilon_x_4 * sigma_6;
+    if (rsq < rcutsq && lj1 != 0)
+        {
+        double r2inv = 1.0 / rsq;
+        double r6inv = r2inv * r2inv * r2inv;
+        *force_divr = r2inv * r6inv * (12.0 * lj1 * r6inv - 6.0 * lj2);
+        *pair_eng = r6inv * (lj1 * r6inv - lj2);
+        if (energy_shift)
+            {
+            double rcut2inv = 1.0 / rcutsq;
+            double rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+            *pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
+            }
+        return 1;
+        }
+    return 0;
+    }
+
+int orc_eval_dpd_conservative(double rsq, double rcutsq, double A, double* force_divr,
+                              double* pair_eng)
+    {
+    /* hoomd/md/EvaluatorPairDPDThermoDPD.h:186-203 */
+    if (rsq < rcutsq)
+        {
+        double rinv = 1.0 / sqrt(rsq);
+        double r = 1.0 / rinv;
+        double rcutinv = 1.0 / sqrt(rcutsq);
+        double rcut = 1.0 / rcutinv;
+        *force_divr = A * (rinv - rcutinv);
+        *pair_eng = A * (rcut - r) - (1.0 / 2.0) * A * rcutinv * (rcutsq - rsq);
+        return 1;
+        }
+    return 0;
+    }
+
+static void accumulate_pair(double* force, double* virial, uint32_t N, uint32_t i, uint32_t j,
+                            const double dx[3], double fdivr, double fdivr_virial, double eng,
+                            int third_law_j, int compute_virial, double acc[10])
+    {
+    /* hoomd/md/PotentialPair.h:739-772: acc = {fx,fy,fz,pe,vxx,vxy,vxz,vyy,vyz,vzz} of i */
+    double f2 = fdivr_virial * 0.5;
+    acc[0] += dx[0] * fdivr;
+    acc[1] += dx[1] * fdivr;
+    acc[2] += dx[2] * fdivr;
+    acc[3] += eng * 0.5;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (compute_virial)
+        {
+        v[0] = f2 * dx[0] * dx[0];
+        v[1] = f2 * dx[0] * dx[1];
+        v[2] = f2 * dx[0] * dx[2];
+        v[3] = f2 * dx[1] * dx[1];
+        v[4] = f2 * dx[1] * dx[2];
+        v[5] = f2 * dx[2] * dx[2];
+        for (int l = 0; l < 6; l++)
+            acc[4 + l] += v[l];
+        }
+    if (third_law_j)
+        {
+        force[4 * (size_t)j + 0] -= dx[0] * fdivr;
+        force[4 * (size_t)j + 1] -= dx[1] * fdivr;
+        force[4 * (size_t)j + 2] -= dx[2] * fdivr;
+        force[4 * (size_t)j + 3] += eng * 0.5;
+        if (compute_virial)
+            for (int l = 0; l < 6; l++)
+                virial[(size_t)l * N + j] += v[l];
+        }
+    (void)i;
+    }
+
+void orc_pair_lj(const orc_box* b, const double* pos, const uint32_t* type, uint32_t N,
+                 const uint32_t* n_neigh, const uint64_t* head, const uint32_t* nlist, int half,
+                 const double* params, const double* r_cut, const double* r_on, uint32_t nt,
+                 int shift_mode, int compute_virial, double* force, double* virial)
+    {
+    /* hoomd/md/PotentialPair.h:587-794 */
+    memset(force, 0, sizeof(double) * 4 * (size_t)N);
+    memset(virial, 0, sizeof(double) * 6 * (size_t)N);
+    for (uint32_t i = 0; i < N; i++)
+        {
+        const double* pi = pos + 3 * (size_t)i;
+        double acc[10] = {0};
+        for (uint32_t k = 0; k < n_neigh[i]; k++)
+            {
+            uint32_t j = nlist[head[i] + k];
+            const double* pj = pos + 3 * (size_t)j;
+            double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
+            orc_min_image(b, dx);
+            double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+            uint32_t tp = type[j] * nt + type[i];
+            double rcutsq = r_cut[tp] * r_cut[tp]; /* hoomd/md/PotentialPair.h:498 */
+            double ronsq = 0.0;
+            if (shift_mode == 2)
+                ronsq = r_on[tp] * r_on[tp];
+            int energy_shift = (shift_mode == 1) || (shift_mode == 2 && ronsq > rcutsq);
+            double fdivr = 0.0, eng = 0.0;
+            if (!orc_eval_lj(rsq, rcutsq, params[2 * tp], params[2 * tp + 1], energy_shift, &fdivr,
+                             &eng))
+                continue;
+            if (shift_mode == 2 && rsq >= ronsq && rsq < rcutsq)
+                {
+                /* hoomd/md/PotentialPair.h:711-737 */
+                double old_eng = eng, old_f = fdivr;
+                double denom_inv = 1.0 / ((rcutsq - ronsq) * (rcutsq - ronsq) * (rcutsq - ronsq));
+                double m = rsq - rcutsq;
+                double s = m * m * (rcutsq + 2.0 * rsq - 3.0 * ronsq) * denom_inv;
+                double ds = 12.0 * (rsq - ronsq) * m * denom_inv;
+                eng = old_eng * s;
+                fdivr = s * old_f - ds * old_eng;
+                }
+            accumulate_pair(force, virial, N, i, j, dx, fdivr, fdivr, eng, half && j < N,
+                            compute_virial, acc);
+            }
+        for (int c = 0; c < 4; c++)
+            force[4 * (size_t)i + c] += acc[c];
+        if (compute_virial)
+            for (int l = 0; l < 6; l++)
+                virial[(size_t)l * N + i] += acc[4 + l];
+        }
+    }
+
+double orc_lj_tail_correction(const double* params, const double* r_cut, uint32_t nt,
+                              const uint32_t* n_per_type, double volume, double* virial_diag)
+    {
+    /* hoomd/md/PotentialPair.h:283-337 with hoomd/md/EvaluatorPairLJ.h:213-248 */
+    double e = 0.0, w = 0.0;
+    for (uint32_t ti = 0; ti < nt; ti++)
+        {
+        double rho_i = n_per_type[ti] / volume;
+        for (uint32_t tj = 0; tj < nt; tj++)
+            {
+            double rho_j = n_per_type[tj] / volume;
+            uint32_t tp = tj * nt + ti;
+            double eps = params[2 * tp], sig = params[2 * tp + 1];
+            double s6 = sig * sig * sig * sig * sig * sig;
+            double lj1 = 4.0 * eps * s6 * s6, lj2 = 4.0 * eps * s6;
+            double rcutsq = r_cut[tp] * r_cut[tp];
+            double ie = 0.0, ip = 0.0;
+            if (rcutsq != 0)
+                {
+                double rc3inv = 1.0 / pow(rcutsq, 1.5);
+                double rc9inv = rc3inv * rc3inv * rc3inv;
+                ie = lj1 / 9.0 * rc9inv - lj2 / 3.0 * rc3inv;
+                ip = lj1 * 4.0 / 3.0 * rc9inv - lj2 * 2.0 * rc3inv;
+                }
+            e += 2.0 * n_per_type[ti] * M_PI * rho_j * ie;
+            double dp = 4.0 / 6.0 * rho_i * rho_j * M_PI * ip;
+            w += 3 * volume * dp / 3.0;
+            }
+        }
+    if (virial_diag)
+        *virial_diag = w;
+    return e;
+    }
+
+/* ---------------------------------------------------------------------- RNG ---- */
+
+void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+    {
+    /* Philox4x32-10, Salmon/Moraes/Dror/Shaw SC'11 (random123 philox.h): multipliers
+       0xD2511F53 / 0xCD9E8D57, Weyl key increments 0x9E3779B9 / 0xBB67AE85 */
+    uint32_t c[4] = {ctr_in[0], ctr_in[1], ctr_in[2], ctr_in[3]};
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; r++)
+        {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0;
+        c[1] = n1;
+        c[2] = n2;
+        c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+        }
+    memcpy(out, c, sizeof(c));
+    }
+
+void orc_seed_key(uint8_t id, uint64_t timestep, uint16_t seed, uint32_t key[2])
+    {
+    /* hoomd/RandomNumbers.h:153-158 */
+    key[0] = (uint32_t)id << 24 | (uint32_t)seed << 8
+             | (uint32_t)((timestep & 0x000000ff00000000ull) >> 32);
+    key[1] = (uint32_t)(timestep & 0x00000000ffffffffull);
+    }
+
+typedef struct
+    {
+    uint32_t key[2], ctr[4];
+    } orc_rng;
+
+static void rng_init(orc_rng* g, uint8_t id, uint64_t timestep, uint16_t seed, uint32_t a,
+                     uint32_t b, uint32_t c, uint16_t d)
+    {
+    /* hoomd/RandomNumbers.h:185-187: ctr = {d<<16, c, b, a} */
+    orc_seed_key(id, timestep, seed, g->key);
+    g->ctr[0] = (uint32_t)d << 16;
+    g->ctr[1] = c;
+    g->ctr[2] = b;
+    g->ctr[3] = a;
+    }
+
+static void rng_next(orc_rng* g, uint32_t u[4])
+    {
+    /* hoomd/RandomNumbers.h:264-270 */
+    orc_philox4x32_10(g->ctr, g->key, u);
+    g->ctr[0] += 1;
+    }
+
+static double u01_u64(uint64_t in)
+    {
+    /* hoomd/RandomNumbers.h:63-74: in * 2^-64 + 2^-65 */
+    const double factor = 1.0 / (18446744073709551615.0 + 1.0);
+    const double halffactor = 0.5 * factor;
+    return (double)in * factor + halffactor;
+    }
+
+static double uneg11_u64(uint64_t in)
+    {
+    /* hoomd/RandomNumbers.h:76-87: int64(in) * 2^-63 + 2^-64 */
+    const double factor = 1.0 / (9223372036854775807.0 + 1.0);
+    const double halffactor = 0.5 * factor;
+    return (double)(int64_t)in * factor + halffactor;
+    }
+
+static double rng_canonical(orc_rng* g)
+    {
+    uint32_t u[4];
+    rng_next(g, u);
+    return u01_u64((uint64_t)u[0] << 32 | u[1]);
+    }
+
+static double rng_normal(orc_rng* g)
+    {
+    /* hoomd/RandomNumbers.h:361-374 (Box-Muller, sigma 1, mu 0); CPU sincospi = sincos(M_PI*x)
+       hoomd/HOOMDMath.h:330-339 */
+    uint32_t u[4];
+    rng_next(g, u);
+    uint64_t u0 = (uint64_t)u[0] << 32 | u[1], u1 = (uint64_t)u[2] << 32 | u[3];
+    double a = M_PI * uneg11_u64(u0);
+    double x = sin(a);
+    double r = sqrt(-2.0 * log(u01_u64(u1)));
+    x *= r;
+    return x * 1.0 + 0.0;
+    }
+
+static double rng_gamma(orc_rng* g, double alpha_in, double bparam)
+    {
+    /* hoomd/RandomNumbers.h:461-505 (Marsaglia-Tsang) */
+    double alpha = alpha_in;
+    if (alpha_in < 1.0)
+        alpha += 1.0;
+    double d = alpha - (1. / 3.);
+    double c = (1.0 / sqrt(d)) / 3.;
+    double v;
+    for (;;)
+        {
+        double x;
+        do
+            {
+            x = rng_normal(g);
+            v = 1.0 + c * x;
+            } while (v <= 0.);
+        v = v * v * v;
+        const double x2 = x * x;
+        double u = rng_canonical(g);
+        if (u < 1.0 - 0.0331 * x2 * x2)
+            break;
+        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v)))
+            break;
+        }
+    v *= d * bparam;
+    if (alpha_in < 1.0)
+        v *= pow(rng_canonical(g), 1.0 / alpha_in);
+    return v;
+    }
+
+double orc_dpd_alpha(uint16_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep)
+    {
+    /* hoomd/md/EvaluatorPairDPDThermoDPD.h:237-254; id 22 = hoomd/RNGIdentifiers.h
+       EvaluatorPairDPDThermo; Counter(min, max) */
+    uint32_t oi = tag_i, oj = tag_j;
+    if (tag_i > tag_j)
+        {
+        oi = tag_j;
+        oj = tag_i;
+        }
+    orc_rng g;
+    rng_init(&g, 22, timestep, seed, oi, oj, 0, 0);
+    /* UniformDistribution(-1,1): a + width*u, hoomd/RandomNumbers.h:325-335 */
+    return -1.0 + 2.0 * rng_canonical(&g);
+    }
+
+void orc_pair_dpd(const orc_box* b, const double* pos, const double* vel, const uint32_t* type,
+                  const uint32_t* tag, uint32_t N, const uint32_t* n_neigh, const uint64_t* head,
+                  const uint32_t* nlist, int half, const double* params, const double* r_cut,
+                  uint32_t nt, uint16_t seed, uint64_t timestep, double dt, double kT, double* force,
+                  double* virial)
+    {
+    /* hoomd/md/PotentialPairDPDThermo.h:102-268. Virial is accumulated unconditionally there. */
+    memset(force, 0, sizeof(double) * 4 * (size_t)N);
+    memset(virial, 0, sizeof(double) * 6 * (size_t)N);
+    for (uint32_t i = 0; i < N; i++)
+        {
+        const double* pi = pos + 3 * (size_t)i;
+        const double* vi = vel + 3 * (size_t)i;
+        double acc[10] = {0};
+        for (uint32_t k = 0; k < n_neigh[i]; k++)
+            {
+            uint32_t j = nlist[head[i] + k];
+            const double* pj = pos + 3 * (size_t)j;
+            const double* vj = vel + 3 * (size_t)j;
+            double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
+            double dv[3] = {vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2]};
+            orc_min_image(b, dx);
+            double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+            double rdotv = dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2];
+            uint32_t tp = type[j] * nt + type[i];
+            double rcutsq = r_cut[tp] * r_cut[tp];
+            double A = params[2 * tp], gamma = params[2 * tp + 1];
+            if (!(rsq < rcutsq))
+                continue;
+            /* hoomd/md/EvaluatorPairDPDThermoDPD.h:222-277 */
+            double rinv = 1.0 / sqrt(rsq);
+            double r = 1.0 / rinv;
+            double rcutinv = 1.0 / sqrt(rcutsq);
+            double rcut = 1.0 / rcutinv;
+            double alpha = orc_dpd_alpha(seed, tag[i], tag[j], timestep);
+            double fdivr = A * (rinv - rcutinv);
+            double fcons = fdivr;
+            fdivr -= gamma * rdotv * (rinv - rcutinv) * (rinv - rcutinv);
+            fdivr += (1.0 / sqrt(dt / (kT * gamma * 6.0))) * (rinv - rcutinv) * alpha;
+            double eng = A * (rcut - r) - (1.0 / 2.0) * A * rcutinv * (rcutsq - rsq);
+            /* third-law update has no j < N guard here (PotentialPairDPDThermo.h:238) */
+            accumulate_pair(force, virial, N, i, j, dx, fdivr, fcons, eng, half && j < N, 1, acc);
+            }
+        for (int c = 0; c < 4; c++)
+            force[4 * (size_t)i + c] += acc[c];
+        for (int l = 0; l < 6; l++)
+            virial[(size_t)l * N + i] += acc[4 + l];
+        }
+    }
+
+/* ---------------------------------------------------------------- integration ---- */
+
+void orc_step_one(const orc_box* b, double* pos, double* vel, const double* accel, int* image,
+                  uint32_t n, double dt, double rescale)
+    {
+    /* hoomd/md/TwoStepConstantVolume.cc:33-79: v += 1/2 a dt; v *= s; r += dt v; then wrap */
+    for (uint32_t j = 0; j < n; j++)
+        for (int d = 0; d < 3; d++)
+            {
+            double v = vel[3 * (size_t)j + d] + (1.0 / 2.0) * accel[3 * (size_t)j + d] * dt;
+            v *= rescale;
+            pos[3 * (size_t)j + d] += dt * v;
+            vel[3 * (size_t)j + d] = v;
+            }
+    for (uint32_t j = 0; j < n; j++)
+        orc_wrap(b, pos + 3 * (size_t)j, image + 3 * (size_t)j);
+    }
+
+void orc_step_two(double* vel, double* accel, const double* mass, const double* force4, uint32_t n,
+                  double dt, double rescale)
+    {
+    /* hoomd/md/TwoStepConstantVolume.cc:234-260: a = F * (1/m); v *= s; v += 1/2 dt a */
+    for (uint32_t j = 0; j < n; j++)
+        {
+        double minv = 1.0 / mass[j];
+        for (int d = 0; d < 3; d++)
+            {
+            double a = force4[4 * (size_t)j + d] * minv;
+            double v = vel[3 * (size_t)j + d] * rescale;
+            v += (1.0 / 2.0) * dt * a;
+            vel[3 * (size_t)j + d] = v;
+            accel[3 * (size_t)j + d] = a;
+            }
+        }
+    }
+
+double orc_kinetic_energy(const double* vel, const double* mass, uint32_t n)
+    {
+    /* hoomd/md/ComputeThermo.cc:139-153 */
+    double ke = 0.0;
+    for (uint32_t j = 0; j < n; j++)
+        ke += mass[j]
+              * (vel[3 * (size_t)j] * vel[3 * (size_t)j] + vel[3 * (size_t)j + 1] * vel[3 * (size_t)j + 1]
+                 + vel[3 * (size_t)j + 2] * vel[3 * (size_t)j + 2]);
+    return ke * 0.5;
+    }
+
+double orc_bussi_factor(double K, double dof, double dt, double kT, double tau, uint64_t timestep,
+                        uint16_t seed, uint32_t first_tag)
+    {
+    /* hoomd/md/Thermostat.h:357-447; id 45 = BussiThermostat (hoomd/RNGIdentifiers.h);
+       RandomGenerator(Seed, Counter(instance_id)) */
+    if (dt == 0.0 || dof == 0)
+        return 1.0;
+    orc_rng g;
+    rng_init(&g, 45, timestep, seed, first_tag, 0, 0, 0);
+    double decay = 0.0;
+    if (tau != 0.0)
+        decay = exp(-dt / tau);
+    double rn = rng_normal(&g);
+    double r_gamma = 0.0;
+    if (dof > 1.0)
+        r_gamma = 2.0 * rng_gamma(&g, (dof - 1.0) / 2.0, 1.0);
+    double v = kT / 2.0 / K;
+    double term1 = v * (1.0 - decay) * (r_gamma + rn * rn);
+    double term2 = 2.0 * rn * sqrt(v * (1.0 - decay) * decay);
+    return sqrt(decay + term1 + term2);
+    }
+
+/* ----------------------------------------------------------------- step loop ---- */
+
+int orc_run(const orc_box* b, orc_run_cfg* cfg, double* pos, double* vel, double* accel, int* image,
+            const double* mass, const uint32_t* type, const uint32_t* tag, const double* params,
+            const double* r_cut, uint64_t nsteps, double* force_out, double* n_neigh_mean)
+    {
+    /* hoomd/md/IntegratorTwoStep.cc:51-123 (update) and :226-281 (prepRun): forces at the current
+       timestep first (accelerations are taken as given), then per step: step one, forces at t+1,
+       step two. Half neighbour list as hoomd.device.CPU selects (hoomd/md/pair/pair.py:135-142).
+       Rebuild policy hoomd/md/NeighborList.cc:1325-1418 with rebuild_check_delay=1, check_dist. */
+    const uint32_t N = cfg->n, nt = cfg->ntypes;
+    double* force = (double*)malloc(sizeof(double) * 4 * (size_t)N);
+    double* virial = (double*)malloc(sizeof(double) * 6 * (size_t)N);
+    double* last_pos = (double*)malloc(sizeof(double) * 3 * (size_t)N);
+    uint32_t* n_neigh = (uint32_t*)malloc(sizeof(uint32_t) * N);
+    uint64_t* head = (uint64_t*)malloc(sizeof(uint64_t) * N);
+    double* rcut_max = (double*)malloc(sizeof(double) * nt);
+    double* r_listsq = (double*)malloc(sizeof(double) * nt * nt);
+    orc_r_listsq(r_cut, nt, cfg->r_buff, r_listsq, rcut_max, NULL);
+    uint32_t* nlist = NULL;
+    uint64_t total = 0;
+    int builds = 0, have_list = 0;
+    double nn_acc = 0.0;
+    const double dof = 3.0 * N - 3.0; /* hoomd/md/IntegratorTwoStep.cc:154-189 (3D, momentum conserved) */
+
+    for (uint64_t s = 0; s <= nsteps; s++)
+        {
+        const uint64_t t_force = cfg->timestep + s; /* forces evaluated at this timestep */
+        if (s > 0)
+            {
+            double scale = 1.0;
+            if (cfg->thermostat == 1)
+                scale = orc_bussi_factor(orc_kinetic_energy(vel, mass, N), dof, cfg->dt, cfg->kT,
+                                         cfg->tau, t_force - 1, cfg->seed, tag[0]);
+            orc_step_one(b, pos, vel, accel, image, N, cfg->dt, scale);
+            }
+        int rebuild = !have_list || cfg->r_buff < 1e-6
+                      || orc_distance_check(b, pos, last_pos, type, N, rcut_max, cfg->r_buff);
+        if (rebuild)
+            {
+            orc_free(nlist);
+            nlist = orc_nlist_binned(b, pos, type, N, N, r_cut, nt, cfg->r_buff, 0, NULL, n_neigh,
+                                     head, &total, NULL);
+            memcpy(last_pos, pos, sizeof(double) * 3 * (size_t)N);
+            have_list = 1;
+            builds++;
+            nn_acc += (double)total / N;
+            }
+        if (cfg->potential == 1)
+            orc_pair_dpd(b, pos, vel, type, tag, N, n_neigh, head, nlist, 1, params, r_cut, nt,
+                         cfg->seed, t_force, cfg->dt, cfg->kT, force, virial);
+        else
+            orc_pair_lj(b, pos, type, N, n_neigh, head, nlist, 1, params, r_cut, r_cut, nt,
+                        cfg->shift_mode, 0, force, virial);
+        if (s > 0)
+            orc_step_two(vel, accel, mass, force, N, cfg->dt, 1.0);
+        }
+    cfg->timestep += nsteps;
+    if (force_out)
+        memcpy(force_out, force, sizeof(double) * 4 * (size_t)N);
+    if (n_neigh_mean)
+        *n_neigh_mean = builds ? nn_acc / builds : 0.0;
+    orc_free(nlist);
+    free(force);
+    free(virial);
+    free(last_pos);
+    free(n_neigh);
+    free(head);
+    free(rcut_max);
+    free(r_listsq);
+    return builds;
+    }

@@ -1,0 +1,273 @@
+"""Pins the CPU oracle (oracle/md_oracle.c) against (a) the reference's own golden vectors for this
+path and (b) outputs of the reference itself (HOOMD-blue v4.8.2 CPU build, fp64) committed under
+tests/golden/ by tests/golden/make_golden.py.  CPU only.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def refvec(golden_dir):
+    with open(os.path.join(golden_dir, "ref_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_philox_kat(oracle, refvec):
+    # hoomd/extern/random123/tests/kat_vectors:27-29
+    assert len(refvec["philox4x32_10"]) == 3
+    for kat in refvec["philox4x32_10"]:
+        out = oracle.philox4x32_10([int(x, 16) for x in kat["ctr"]], [int(x, 16) for x in kat["key"]])
+        assert [f"{x:08x}" for x in out] == kat["out"]
+
+
+def test_seed_key_kat(oracle, refvec):
+    # hoomd/test/random_numbers_test.cc:456-462
+    k = refvec["seed_kat"]
+    key = oracle.seed_key(k["id"], int(k["timestep"], 16), int(k["seed"], 16))
+    assert list(key) == [int(x, 16) for x in k["key"]]
+
+
+def test_true_pair_list(oracle, refvec):
+    # hoomd/md/pytest/test_nlist.py:221-222,353-372 with hoomd/conftest.py:203-262 (n=7, a=1),
+    # r_cut 1.1, buffer 0
+    n = 7
+    r = np.arange(-n / 2, n / 2)
+    x, y, z = np.meshgrid(r, r, r)
+    pos = (np.vstack((x.flatten(), y.flatten(), z.flatten())).T + 0.5) * 1.0
+    box = oracle.make_box([7.0, 7.0, 7.0])
+    truth = set(frozenset(p) for p in refvec["true_pair_list"])
+    assert len(truth) == 1029
+    for full in (True, False):
+        for brute in (False, True):
+            nn, head, nl, dim = oracle.nlist(box, pos, np.zeros(len(pos), np.uint32), [1.1], 0.0,
+                                             full=full, brute=brute)
+            pairs = oracle.pair_set(nn, head, nl)
+            assert len(pairs) == 1029
+            assert set(frozenset((int(a), int(b))) for a, b in pairs) == truth
+            if full:
+                assert nn.sum() == 2 * 1029
+            if not brute:
+                assert dim == (6, 6, 6)
+
+
+def test_forces_and_energies_json(oracle, refvec):
+    # hoomd/md/pytest/test_potential.py:994-1051: r = 0.75 and 1.5, r_cut 2.5, rtol 5e-6
+    fe = refvec["forces_and_energies"]
+    for p, F, E in zip(fe["LJ"]["params"], fe["LJ"]["forces"], fe["LJ"]["energies"]):
+        for d, f_ref, e_ref in zip((0.75, 1.5), F, E):
+            ok, fdivr, eng = oracle.eval_lj(d * d, 2.5 * 2.5, p["epsilon"], p["sigma"])
+            assert ok
+            assert np.isclose(-d * fdivr, f_ref, rtol=5e-6, atol=1e-6 if f_ref == 0 else 0)
+            assert np.isclose(eng, e_ref, rtol=5e-6, atol=1e-6 if e_ref == 0 else 0)
+    dc = fe["DPDConservative"]
+    for p, F, E in zip(dc["params"], dc["forces"], dc["energies"]):
+        for d, f_ref, e_ref in zip((0.75, 1.5), F, E):
+            ok, fdivr, eng = oracle.eval_dpd_conservative(d * d, 2.5 * 2.5, p["A"])
+            assert ok
+            assert np.isclose(-d * fdivr, f_ref, rtol=5e-6)
+            assert np.isclose(eng, e_ref, rtol=5e-6)
+
+
+def test_lj_shift_and_cutoff(oracle):
+    # hoomd/md/pytest/test_potential.py:780 (energy shifting): E_shift(r) = E(r) - E(r_cut)
+    ok, f0, e0 = oracle.eval_lj(1.2 ** 2, 2.5 ** 2, 1.0, 1.0, energy_shift=False)
+    ok, f1, e1 = oracle.eval_lj(1.2 ** 2, 2.5 ** 2, 1.0, 1.0, energy_shift=True)
+    _, _, ec = oracle.eval_lj(2.5 ** 2 * (1 - 1e-15), 2.5 ** 2, 1.0, 1.0)
+    assert f0 == f1 and np.isclose(e1, e0 - ec, rtol=1e-12)
+    assert not oracle.eval_lj(2.5 ** 2, 2.5 ** 2, 1.0, 1.0)[0]       # rsq < rcutsq is strict
+    assert not oracle.eval_lj(1.0, 2.5 ** 2, 0.0, 1.0)[0]            # lj1 == 0 gate
+
+
+def _type_params(pdict, names, cols):
+    nt = len(names)
+    out = np.zeros((nt, nt, cols))
+    for (a, b), v in pdict.items():
+        i, j = names.index(a), names.index(b)
+        out[i, j] = out[j, i] = v
+    return out.reshape(nt * nt, cols)
+
+
+def _check_frame(oracle, g, prefix, params, r_cut, buffer, shift_mode, r_on=None):
+    box = oracle.make_box(g["L"].astype(np.float64))
+    pos = g["pos"].astype(np.float64)
+    types = g["typeid"]
+    for full in (False, True):
+        nn, head, nl, dim = oracle.nlist(box, pos, types, r_cut, buffer, full=full)
+        pairs = oracle.pair_set(nn, head, nl)
+        assert pairs.shape == g[f"{prefix}_pairs"].shape
+        assert np.array_equal(pairs, g[f"{prefix}_pairs"])          # bit-exact pair set
+        assert tuple(g[f"{prefix}_dims"]) == dim
+        force, virial = oracle.pair_lj(box, pos, types, nn, head, nl, params, r_cut, r_on=r_on,
+                                       half=not full, shift_mode=shift_mode)
+        # half list: same summation order as the reference -> near bit-level agreement
+        tol = 1e-13 if not full else 1e-11
+        scale = np.abs(g[f"{prefix}_force"]).max()
+        assert np.abs(force[:, :3] - g[f"{prefix}_force"]).max() <= tol * scale
+        assert np.allclose(force[:, 3], g[f"{prefix}_energy"], rtol=1e-10, atol=1e-10)
+        assert np.allclose(virial.T, g[f"{prefix}_virial"], rtol=1e-9, atol=1e-9)
+        assert np.isclose(force[:, 3].sum(), float(g[f"{prefix}_total_energy"]), rtol=1e-12)
+
+
+def test_lj_2k_frame_vs_reference(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "lj_2k.npz"))
+    params = np.array([[1.0, 1.0]])
+    _check_frame(oracle, g, "none", params, [2.5], 0.4, 0)
+    _check_frame(oracle, g, "shift", params, [2.5], 0.4, 1)
+    _check_frame(oracle, g, "xplor", params, [2.5], 0.4, 2, r_on=[2.0])
+
+
+def test_ka_2k_frame_vs_reference(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ka_2k.npz"))
+    names = ["A", "B"]
+    params = _type_params({("A", "A"): (1.0, 1.0), ("A", "B"): (1.5, 0.8), ("B", "B"): (0.5, 0.88)},
+                          names, 2)
+    r_cut = _type_params({("A", "A"): 2.5, ("A", "B"): 2.0, ("B", "B"): 2.2}, names, 1).ravel()
+    _check_frame(oracle, g, "shift", params, r_cut, 0.3, 1)
+
+
+def test_dpd_3k_vs_reference(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dpd_3k.npz"))
+    box = oracle.make_box(g["L"].astype(np.float64))
+    pos = g["pos"].astype(np.float64)
+    vel = g["vel"].astype(np.float64)
+    N = len(pos)
+    types = g["typeid"]
+    tags = np.arange(N, dtype=np.uint32)
+    params = np.array([[float(g["A"]), float(g["gamma"])]])
+    for full in (False, True):
+        nn, head, nl, _ = oracle.nlist(box, pos, types, [1.0], 0.4, full=full)
+        assert np.array_equal(oracle.pair_set(nn, head, nl), g["pairs"])
+        for n, ts in enumerate(g["timesteps"]):
+            force, virial = oracle.pair_dpd(box, pos, vel, types, tags, nn, head, nl, params, [1.0],
+                                            int(g["seed"]), int(ts), float(g["dt"]), float(g["kT"]),
+                                            half=not full)
+            scale = np.abs(g[f"force_{n}"]).max()
+            # random + drag forces included: pins the Philox key/counter layout and u01 mapping
+            assert np.abs(force[:, :3] - g[f"force_{n}"]).max() <= 1e-11 * scale
+            assert np.allclose(force[:, 3], g[f"energy_{n}"], rtol=1e-10, atol=1e-12)
+            assert np.allclose(virial.T, g[f"virial_{n}"], rtol=1e-9, atol=1e-10)
+    # the three timesteps must give different random forces
+    assert not np.allclose(g["force_0"], g["force_1"])
+
+
+def _run_traj(oracle, g, thermostat, nsteps=20):
+    box = oracle.make_box(g["L"].astype(np.float64))
+    pos = g["pos"].astype(np.float64).copy()
+    vel = g["vel"].astype(np.float64).copy()
+    img = g["image"].astype(np.int32).copy()
+    N = len(pos)
+    mass = np.ones(N)
+    types = g["typeid"]
+    tags = np.arange(N, dtype=np.uint32)
+    params = np.array([[1.0, 1.0]])
+    # prepRun: accel = F/m at t0 (hoomd/md/IntegratorTwoStep.cc:262-275)
+    nn, head, nl, _ = oracle.nlist(box, pos, types, [2.5], 0.4, full=False)
+    f0, _ = oracle.pair_lj(box, pos, types, nn, head, nl, params, [2.5], half=True)
+    accel = np.ascontiguousarray(f0[:, :3] / mass[:, None])
+    r = oracle.run(box, pos, vel, accel, img, mass, types, tags, params, [2.5], nsteps, 0.005, 0.4,
+                   thermostat=thermostat, kT=1.5, tau=0.0, seed=11)  # Bussi default tau=0 (hoomd/md/methods/thermostats.py:319)
+    return pos, vel, img, r
+
+
+def test_nve_trajectory_vs_reference(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "lj_2k.npz"))
+    pos, vel, img, r = _run_traj(oracle, g, None)
+    assert np.abs(pos - g["nve_pos"]).max() < 1e-10
+    assert np.abs(vel - g["nve_vel"]).max() < 1e-10
+    assert np.array_equal(img, g["nve_image"])
+    assert 1 <= r["builds"] <= 5    # (hoomd resets num_builds on every run() call: not comparable)
+    ke = oracle.kinetic_energy(vel, np.ones(len(vel)))
+    assert np.isclose(ke, g["nve_ke"][-1], rtol=1e-11)
+    assert np.isclose(r["force"][:, 3].sum(), g["nve_pe"][-1], rtol=1e-11)
+
+
+def test_bussi_trajectory_vs_reference(oracle, golden_dir):
+    # pins the Bussi rescale factor incl. HOOMD's Normal/Gamma draws (hoomd/md/Thermostat.h:357-447)
+    g = np.load(os.path.join(golden_dir, "lj_2k.npz"))
+    pos, vel, img, r = _run_traj(oracle, g, "bussi")
+    assert np.abs(pos - g["bussi_pos"]).max() < 1e-9
+    assert np.abs(vel - g["bussi_vel"]).max() < 1e-9
+    ke = oracle.kinetic_energy(vel, np.ones(len(vel)))
+    assert np.isclose(ke, g["bussi_ke"][-1], rtol=1e-10)
+    assert not np.allclose(g["bussi_vel"], g["nve_vel"], atol=1e-6)
+
+
+def test_c1_64k_vs_reference(oracle, golden_dir):
+    path = os.path.join(golden_dir, "c1_64k.npz")
+    if not os.path.exists(path):
+        pytest.skip("c1_64k.npz not generated")
+    g = np.load(path)
+    box = oracle.make_box(g["L"].astype(np.float64))
+    pos = g["pos"].astype(np.float64)
+    types = np.zeros(len(pos), np.uint32)
+    nn, head, nl, dim = oracle.nlist(box, pos, types, [2.5], 0.4, full=False)
+    pairs = oracle.pair_set(nn, head, nl)
+    assert len(pairs) == int(g["n_pairs"])
+    assert hashlib.sha256(pairs.tobytes()).hexdigest() == str(g["pairs_sha256"])
+    assert tuple(g["dims"]) == dim
+    force, virial = oracle.pair_lj(box, pos, types, nn, head, nl, np.array([[1.0, 1.0]]), [2.5],
+                                   half=True)
+    assert np.abs(force[:, :3] - g["force"]).max() <= 1e-12 * np.abs(g["force"]).max()
+    assert np.isclose(force[:, 3].sum(), float(g["total_energy"]), rtol=1e-12)
+    assert np.allclose(virial.sum(axis=1), g["virial_sum"], rtol=1e-10)
+
+
+def test_cell_list_restatement(oracle):
+    # hoomd/test/test_cell_list.cc:33-148 (dimensions), :155-238 (adjacency), :245-505 (small system)
+    box = oracle.make_box([10.0, 10.0, 10.0])
+    assert oracle.cell_dims(box, 1.0) == (10, 10, 10)
+    assert oracle.cell_dims(box, 3.0) == (3, 3, 3)
+    assert oracle.cell_dims(box, 30.0) == (1, 1, 1)
+    adj = oracle.cell_adj((5, 5, 5))
+    assert adj.shape == (125, 27)
+    assert np.all(np.diff(adj.astype(np.int64), axis=1) > 0)          # sorted, unique
+    # cell (0,0,0): neighbours wrap to index 4 in every direction
+    want = sorted((k % 5 * 5 + j % 5) * 5 + i % 5 for k in (-1, 0, 1) for j in (-1, 0, 1)
+                  for i in (-1, 0, 1))
+    assert list(adj[0]) == want
+    assert oracle.cell_adj((2, 2, 2)).shape == (8, 8)                # de-duplicated rows
+    pos = np.array([[-4.9, -4.9, -4.9], [4.9, 4.9, 4.9], [0.0, 0.0, 0.0], [0.1, 0.1, 0.1]])
+    size, idx, cond = oracle.cell_list(box, (3, 3, 3), pos, 4)
+    assert cond == (0, 0, 0)
+    assert size[0] == 1 and size[26] == 1 and size[13] == 2
+    assert list(idx[13][:2]) == [2, 3]                               # ascending particle index
+    _, _, cond = oracle.cell_list(box, (3, 3, 3), np.array([[np.nan, 0, 0]]), 4)
+    assert cond[1] == 1                                              # NaN position flagged
+    _, _, cond = oracle.cell_list(box, (3, 3, 3), np.array([[5.1, 0, 0]]), 4)
+    assert cond[2] == 1                                              # out of box flagged
+    _, _, cond = oracle.cell_list(box, (3, 3, 3), np.zeros((6, 3)), 4)
+    assert cond[0] == 6                                              # overflow reports needed Nmax
+
+
+def test_min_image_and_wrap(oracle):
+    # hoomd/md/test/test_neighborlist.cc:33-326 exercises pairs across each periodic face
+    box = oracle.make_box([20.0, 40.0, 60.0])
+    d = oracle.min_image(box, np.array([[19.0, -39.0, 59.0], [10.0, 20.0, 30.0],
+                                        [-10.0, -20.0, -30.0], [9.9, 0, 0]]))
+    assert np.allclose(d[0], [-1.0, 1.0, -1.0])
+    assert np.allclose(d[1], [-10.0, -20.0, -30.0])                  # >= hi wraps
+    assert np.allclose(d[2], [-10.0, -20.0, -30.0])                  # == lo stays
+    assert np.allclose(d[3], [9.9, 0, 0])
+    pos = np.array([[10.0, -20.5, 30.0]])
+    vel = np.zeros((1, 3))
+    acc = np.zeros((1, 3))
+    img = np.zeros((1, 3), dtype=np.int32)
+    oracle.step_one(box, pos, vel, acc, img, 0.005)
+    assert np.allclose(pos, [[-10.0, 19.5, -30.0]]) and img.tolist() == [[1, -1, 1]]
+
+
+def test_distance_check(oracle):
+    box = oracle.make_box([10.0, 10.0, 10.0])
+    last = np.zeros((2, 3))
+    pos = np.array([[0.0, 0.0, 0.0], [0.19, 0.0, 0.0]])
+    t = np.zeros(2, np.uint32)
+    assert not oracle.distance_check(box, pos, last, t, [2.5], 0.4)
+    pos[1, 0] = 0.2000001
+    assert oracle.distance_check(box, pos, last, t, [2.5], 0.4)     # >= (buffer/2)^2
+    pos[1] = [4.95, 0, 0]
+    last[1] = [-4.95, 0, 0]
+    assert not oracle.distance_check(box, pos, last, t, [2.5], 0.4)  # min image of displacement
