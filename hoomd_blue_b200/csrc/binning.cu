@@ -1,0 +1,174 @@
+// binning.cu — deterministic cell binning by key sort (no atomics) and the physical re-ordering of
+// the particle arrays into cell order.
+//
+// Replaces CellList::computeCellList (hoomd/CellList.cc:404-547), gpu_compute_cell_list_kernel
+// (hoomd/CellListGPU.cu:42-171, atomicInc slots) and the optional thrust sort that makes it
+// deterministic (hoomd/CellListGPU.cu:439-565). Because the particles themselves are permuted into
+// cell order at every rebuild, this also subsumes SFCPackTuner (hoomd/SFCPackTuner.cc:81-117): the
+// sorted order is a space-filling order with x-rows of cells contiguous in memory, and the "cell
+// list" is just cell_start[] into the particle arrays (no Nc x Nmax padded xyzf copy).
+#include "common.cuh"
+#include "kernels.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace hb2
+    {
+// One thread per particle: cell id with the reference's rule in fp64.
+// f = (p - lo) * Linv (hoomd/BoxDim.h:276-284, zero tilt, no ghost width);
+// ib = (int)(f * dim), ib == dim -> 0 when periodic (hoomd/CellList.cc:455-470).
+__global__ void __launch_bounds__(256)
+    bin_kernel(const float4* __restrict__ pos, uint32_t N, BoxD box, uint3 dim,
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+               uint32_t* __restrict__ conditions)
+    {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    float4 p = pos[i];
+    uint32_t key = 0;
+    if (isnan(p.x) || isnan(p.y) || isnan(p.z))
+        {
+        atomicMax(&conditions[1], i + 1);
+        }
+    else
+        {
+        double f[3];
+        f[0] = __dmul_rn(__dadd_rn((double)p.x, -box.lo[0]), box.Linv[0]);
+        f[1] = __dmul_rn(__dadd_rn((double)p.y, -box.lo[1]), box.Linv[1]);
+        f[2] = __dmul_rn(__dadd_rn((double)p.z, -box.lo[2]), box.Linv[2]);
+        const uint32_t dm[3] = {dim.x, dim.y, dim.z};
+        int ib[3];
+        bool out = false;
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            ib[d] = (int)__dmul_rn(f[d], (double)dm[d]);
+            if (ib[d] == (int)dm[d])
+                ib[d] = 0;
+            if (f[d] < -0.00001 || f[d] >= 1.00001 || ib[d] < 0 || ib[d] >= (int)dm[d])
+                out = true;
+            }
+        if (out)
+            atomicMax(&conditions[2], i + 1);
+        else
+            key = ((uint32_t)ib[2] * dim.y + (uint32_t)ib[1]) * dim.x + (uint32_t)ib[0];
+        }
+    keys[i] = key;
+    vals[i] = i;
+    }
+
+// cell_start from the sorted keys: slot k starts every cell in (key[k-1], key[k]].
+__global__ void __launch_bounds__(256)
+    cell_start_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t N, uint32_t Nc,
+                      uint32_t* __restrict__ cell_start)
+    {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > N)
+        return;
+    uint32_t lo = (k == 0) ? 0u : keys_sorted[k - 1] + 1u;
+    uint32_t hi = (k == N) ? Nc : keys_sorted[k];
+    if (k == 0)
+        lo = 0;
+    for (uint32_t c = lo; c <= hi && c <= Nc; c++)
+        cell_start[c] = k;
+    }
+
+// Gather every per-particle array into cell order; refresh rtag.
+__global__ void __launch_bounds__(256)
+    reorder_kernel(const uint32_t* __restrict__ order, uint32_t N, const float4* __restrict__ pos_in,
+                   const float4* __restrict__ vel_in, const int* __restrict__ img_in,
+                   const uint32_t* __restrict__ tag_in, const float4* __restrict__ force_in,
+                   float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+                   int* __restrict__ img_out, uint32_t* __restrict__ tag_out,
+                   float4* __restrict__ force_out, uint32_t* __restrict__ rtag)
+    {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N)
+        return;
+    uint32_t o = order[k];
+    pos_out[k] = pos_in[o];
+    vel_out[k] = vel_in[o];
+    img_out[3 * k + 0] = img_in[3 * o + 0];
+    img_out[3 * k + 1] = img_in[3 * o + 1];
+    img_out[3 * k + 2] = img_in[3 * o + 2];
+    uint32_t t = tag_in[o];
+    tag_out[k] = t;
+    if (force_in)
+        force_out[k] = force_in[o];
+    rtag[t] = k;
+    }
+
+static inline int key_bits(uint32_t Nc)
+    {
+    int b = 1;
+    while (b < 32 && (1ull << b) < (unsigned long long)Nc)
+        b++;
+    return b;
+    }
+
+size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc)
+    {
+    size_t sort_bytes = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k, v, (int)N, 0, key_bits(Nc));
+    sort_bytes = (sort_bytes + 255) & ~size_t(255);
+    size_t arr = ((size_t)N * sizeof(uint32_t) + 255) & ~size_t(255);
+    return sort_bytes + 3 * arr; // keys, keys_alt, vals_alt (+ the caller's order[] as vals)
+    }
+
+hb2_status compute_cell_order(const float4* d_pos, uint32_t N, const hb2_box& box, uint3 dim,
+                              uint32_t* d_order, uint32_t* d_cell_start, uint32_t* d_conditions,
+                              void* d_tmp, size_t tmp_bytes, cudaStream_t stream)
+    {
+    const uint32_t Nc = dim.x * dim.y * dim.z;
+    if (tmp_bytes < cell_order_tmp_bytes(N, Nc))
+        {
+        set_error("compute_cell_order: scratch buffer too small");
+        return HB2_ERR_INVALID;
+        }
+    size_t arr = ((size_t)N * sizeof(uint32_t) + 255) & ~size_t(255);
+    char* base = (char*)d_tmp;
+    uint32_t* keys = (uint32_t*)base;
+    uint32_t* keys_alt = (uint32_t*)(base + arr);
+    uint32_t* vals_alt = (uint32_t*)(base + 2 * arr);
+    void* sort_tmp = base + 3 * arr;
+    size_t sort_bytes = tmp_bytes - 3 * arr;
+
+    if (N > 0)
+        {
+        bin_kernel<<<(N + 255) / 256, 256, 0, stream>>>(d_pos, N, boxd(box), dim, keys, d_order,
+                                                        d_conditions);
+        HB2_CHECK_LAUNCH("bin_kernel");
+        cub::DoubleBuffer<uint32_t> k(keys, keys_alt), v(d_order, vals_alt);
+        HB2_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k, v, (int)N, 0, key_bits(Nc),
+                                                 stream));
+        count_launch(3);
+        if (v.Current() != d_order)
+            HB2_CUDA(cudaMemcpyAsync(d_order, v.Current(), (size_t)N * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToDevice, stream));
+        cell_start_kernel<<<(N + 1 + 255) / 256, 256, 0, stream>>>(k.Current(), N, Nc, d_cell_start);
+        HB2_CHECK_LAUNCH("cell_start_kernel");
+        }
+    else
+        {
+        HB2_CUDA(cudaMemsetAsync(d_cell_start, 0, sizeof(uint32_t) * ((size_t)Nc + 1), stream));
+        }
+    return HB2_OK;
+    }
+
+hb2_status reorder_particles(const uint32_t* d_order, uint32_t N, const float4* pos_in,
+                             const float4* vel_in, const int* img_in, const uint32_t* tag_in,
+                             const float4* force_in, float4* pos_out, float4* vel_out, int* img_out,
+                             uint32_t* tag_out, float4* force_out, uint32_t* rtag,
+                             cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    reorder_kernel<<<(N + 255) / 256, 256, 0, stream>>>(d_order, N, pos_in, vel_in, img_in, tag_in,
+                                                        force_in, pos_out, vel_out, img_out, tag_out,
+                                                        force_out, rtag);
+    HB2_CHECK_LAUNCH("reorder_kernel");
+    return HB2_OK;
+    }
+
+    } // namespace hb2

@@ -1,0 +1,1507 @@
+// engine.cu — host side of the path in C++: particle state resident in HBM, the neighbour list
+// object, the pair force object and the two-step integrator, exported through the C ABI of
+// include/hoomd_b200.h (layer 2).  Mirrors, for this path only:
+//   ParticleData            hoomd/ParticleData.h:1285-1334
+//   NeighborList(+Binned)   hoomd/md/NeighborList.cc:363-435 (compute), :452-529 (r_list),
+//                           :535-561 (box check), :1325-1418 (needsUpdating), :1601-1617 (overflow)
+//   PotentialPair           hoomd/md/PotentialPair.h:369-371, :467-580, :587-794
+//   IntegratorTwoStep       hoomd/md/IntegratorTwoStep.cc:51-123 (update), :226-281 (prepRun)
+//   TwoStepConstantVolume   hoomd/md/TwoStepConstantVolume.cc
+#include "common.cuh"
+#include "evaluators.cuh"
+#include "kernels.cuh"
+#include "pair_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace hb2
+    {
+static thread_local std::string t_error;
+uint64_t g_launches = 0;
+
+void set_error(const std::string& msg)
+    {
+    t_error = msg;
+    }
+hb2_status cuda_fail(cudaError_t e, const char* what)
+    {
+    t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return HB2_ERR_CUDA;
+    }
+
+template<class T> static hb2_status dev_alloc(T** p, size_t n)
+    {
+    *p = nullptr;
+    if (n == 0)
+        n = 1;
+    HB2_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    return HB2_OK;
+    }
+template<class T> static void dev_free(T*& p)
+    {
+    if (p)
+        cudaFree(p);
+    p = nullptr;
+    }
+    } // namespace hb2
+
+using namespace hb2;
+
+#define HB2_TRY(expr)              \
+    do                             \
+        {                          \
+        hb2_status _s = (expr);    \
+        if (_s != HB2_OK)          \
+            return _s;             \
+        } while (0)
+
+// =================================================================================================
+struct hb2_system
+    {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t ntypes = 1;
+    uint32_t seed = 0;
+    hb2_box box;
+    bool has_box = false;
+    uint32_t N = 0;
+    uint64_t timestep = 0;
+    uint64_t* d_timestep = nullptr;
+    bool compute_virial = false;
+
+    // particle arrays, double buffered: every nlist rebuild gathers them into cell order
+    float4* pos[2] = {nullptr, nullptr};
+    float4* vel[2] = {nullptr, nullptr};
+    int* image[2] = {nullptr, nullptr};
+    uint32_t* tag[2] = {nullptr, nullptr};
+    uint32_t* rtag = nullptr;
+    int cur = 0;
+    uint64_t order_epoch = 0; // bumped whenever the particle order changes
+
+    // reduction scratch
+    double* d_partial = nullptr;
+    uint32_t* d_ticket = nullptr;
+    double* d_sums = nullptr; // [0] KE, [1..7] PE + virial, [8] rescale factor
+
+    std::vector<hb2_nlist*> nlists;
+    std::vector<hb2_pair*> pairs;
+
+    hb2_status set_timestep(uint64_t t)
+        {
+        timestep = t;
+        HB2_CUDA(cudaMemcpyAsync(d_timestep, &timestep, sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                 stream));
+        HB2_CUDA(cudaStreamSynchronize(stream));
+        return HB2_OK;
+        }
+    };
+
+struct hb2_nlist
+    {
+    hb2_system* sys = nullptr;
+    double buffer = 0.4;
+    uint32_t rebuild_check_delay = 1;
+    bool check_dist = true;
+
+    std::vector<hb2_pair*> consumers;
+    std::vector<double> r_cut, r_listsq, rcut_max;
+    double rcut_max_max = 0.0, r_list_min = 0.0;
+    bool params_dirty = true;
+
+    uint3 dim = {0, 0, 0};
+    uint32_t cell_cap = 0;
+    uint32_t* d_cell_start = nullptr;
+    uint32_t* d_order = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    double* d_r_listsq = nullptr;
+
+    uint32_t* d_nlist = nullptr;
+    uint32_t pitch = 0;
+    size_t nlist_cap = 0;
+    uint32_t* d_n_neigh = nullptr;
+    float4* d_last_pos = nullptr;
+    uint32_t cap_N = 0;
+    uint32_t* d_conditions = nullptr; // [0] max n_neigh, [1] nan idx+1, [2] oob idx+1, [3] rebuild flag
+    uint32_t* h_conditions = nullptr; // pinned mirror
+
+    bool force_update = true;
+    bool has_list = false;
+    uint64_t num_builds = 0;
+    uint64_t last_update_step = 0;
+    uint64_t shortest_rebuild = ~0ull;
+    uint32_t max_neigh = 0;
+
+    hb2_status update_r_list();
+    hb2_status ensure_capacity();
+    hb2_status rebuild(uint64_t timestep);
+    hb2_status compute(uint64_t timestep, bool flag_known, bool flag_value);
+    float maxshift() const
+        {
+        // hoomd/md/NeighborList.cc:1244-1260 with a fixed box (lambda = 1): (r_max - r_min)/2
+        return (float)(buffer / 2.0);
+        }
+    };
+
+struct hb2_pair
+    {
+    hb2_system* sys = nullptr;
+    hb2_nlist* nl = nullptr;
+    hb2_evaluator ev = HB2_EVAL_LJ;
+    hb2_shift_mode mode = HB2_SHIFT_NONE;
+    std::vector<double> user; // ntypes^2 x 2 user parameters
+    std::vector<uint8_t> have_params;
+    std::vector<double> r_cut, r_on;
+    std::vector<float> packed, rcutsq, ronsq;
+    float* d_params = nullptr;
+    float* d_rcutsq = nullptr;
+    float* d_ronsq = nullptr;
+    bool params_dirty = true;
+    double kT = 1.0;
+    double dt = 0.005;
+    uint32_t tpp = 8;
+    bool tail_correction = false;
+
+    float4* d_force = nullptr;
+    float* d_virial = nullptr;
+    uint32_t cap_N = 0;
+    bool virial_valid = false;
+    bool computed = false;
+    uint64_t computed_step = 0, computed_epoch = 0;
+
+    hb2_status upload_params();
+    hb2_status compute(uint64_t timestep, bool flag_known = false, bool flag_value = false);
+    };
+
+struct hb2_integrator
+    {
+    hb2_system* sys = nullptr;
+    double dt = 0.005;
+    std::vector<hb2_pair*> forces;
+    int thermostat = 0;
+    double kT = 1.0, tau = 0.0;
+    bool prepared = false;
+    uint64_t prepared_epoch = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    };
+
+// =================================================================================================
+// system
+// =================================================================================================
+extern "C" const char* hb2_last_error(void)
+    {
+    return t_error.c_str();
+    }
+extern "C" int hb2_abi_version(void)
+    {
+    return HB2_ABI_VERSION;
+    }
+extern "C" uint64_t hb2_launch_count(void)
+    {
+    return g_launches;
+    }
+
+extern "C" hb2_status hb2_box_make(hb2_box* box, double Lx, double Ly, double Lz)
+    {
+    if (!box || !(Lx > 0) || !(Ly > 0) || !(Lz > 0))
+        {
+        set_error("hb2_box_make: box lengths must be positive");
+        return HB2_ERR_INVALID;
+        }
+    const double L[3] = {Lx, Ly, Lz};
+    for (int d = 0; d < 3; d++)
+        {
+        // hoomd/BoxDim.h:183-200
+        box->L[d] = L[d];
+        box->hi[d] = L[d] / 2.0;
+        box->lo[d] = -box->hi[d];
+        box->Linv[d] = 1.0 / L[d];
+        box->Lf[d] = (float)box->L[d];
+        box->hif[d] = (float)box->hi[d];
+        box->lof[d] = (float)box->lo[d];
+        box->Linvf[d] = (float)box->Linv[d];
+        box->periodic[d] = 1;
+        }
+    box->_pad = 0;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_system_create(hb2_system** out, int device, uint32_t ntypes, uint32_t seed)
+    {
+    if (!out || ntypes == 0)
+        {
+        set_error("hb2_system_create: bad arguments");
+        return HB2_ERR_INVALID;
+        }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        {
+        cudaGetLastError();
+        set_error("hb2_system_create: no CUDA device is visible and this library has no CPU path");
+        return HB2_ERR_NO_DEVICE;
+        }
+    if (device < 0 || device >= ndev)
+        {
+        set_error("hb2_system_create: device ordinal out of range");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(device));
+    hb2_system* s = new hb2_system();
+    s->device = device;
+    s->ntypes = ntypes;
+    s->seed = seed & 0xffffu;
+    hb2_status st = HB2_OK;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+        st = HB2_ERR_CUDA;
+    if (st == HB2_OK)
+        st = dev_alloc(&s->d_timestep, 1);
+    if (st == HB2_OK)
+        st = dev_alloc(&s->d_ticket, 4);
+    if (st == HB2_OK)
+        st = dev_alloc(&s->d_sums, 16);
+    if (st == HB2_OK)
+        {
+        cudaMemsetAsync(s->d_ticket, 0, 4 * sizeof(uint32_t), s->stream);
+        cudaMemsetAsync(s->d_sums, 0, 16 * sizeof(double), s->stream);
+        st = s->set_timestep(0);
+        }
+    if (st != HB2_OK)
+        {
+        delete s;
+        return st;
+        }
+    *out = s;
+    return HB2_OK;
+    }
+
+extern "C" void hb2_system_destroy(hb2_system* s)
+    {
+    if (!s)
+        return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    for (int b = 0; b < 2; b++)
+        {
+        dev_free(s->pos[b]);
+        dev_free(s->vel[b]);
+        dev_free(s->image[b]);
+        dev_free(s->tag[b]);
+        }
+    dev_free(s->rtag);
+    dev_free(s->d_timestep);
+    dev_free(s->d_partial);
+    dev_free(s->d_ticket);
+    dev_free(s->d_sums);
+    cudaStreamDestroy(s->stream);
+    delete s;
+    }
+
+extern "C" hb2_status hb2_system_set_box(hb2_system* s, double Lx, double Ly, double Lz, double xy,
+                                         double xz, double yz)
+    {
+    if (!s)
+        return HB2_ERR_INVALID;
+    if (xy != 0.0 || xz != 0.0 || yz != 0.0)
+        {
+        set_error("hb2_system_set_box: triclinic boxes are outside this path's scope (tilt must be 0)");
+        return HB2_ERR_INVALID;
+        }
+    HB2_TRY(hb2_box_make(&s->box, Lx, Ly, Lz));
+    s->has_box = true;
+    for (auto* nl : s->nlists)
+        {
+        nl->force_update = true;
+        nl->params_dirty = true;
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const float* pos3,
+                                               const float* vel3, const float* mass,
+                                               const uint32_t* typeid_, const int32_t* image3)
+    {
+    if (!s || !pos3)
+        {
+        set_error("hb2_system_set_particles: positions are required");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    if (N != s->N || !s->pos[0])
+        {
+        for (int b = 0; b < 2; b++)
+            {
+            dev_free(s->pos[b]);
+            dev_free(s->vel[b]);
+            dev_free(s->image[b]);
+            dev_free(s->tag[b]);
+            HB2_TRY(dev_alloc(&s->pos[b], N));
+            HB2_TRY(dev_alloc(&s->vel[b], N));
+            HB2_TRY(dev_alloc(&s->image[b], 3 * (size_t)N));
+            HB2_TRY(dev_alloc(&s->tag[b], N));
+            }
+        dev_free(s->rtag);
+        HB2_TRY(dev_alloc(&s->rtag, N));
+        dev_free(s->d_partial);
+        HB2_TRY(dev_alloc(&s->d_partial, 8 * (size_t)(reduce_blocks(N) + 1)));
+        s->N = N;
+        }
+    std::vector<float4> hp(N), hv(N);
+    std::vector<int> hi(3 * (size_t)N, 0);
+    std::vector<uint32_t> ht(N);
+    for (uint32_t i = 0; i < N; i++)
+        {
+        const uint32_t t = typeid_ ? typeid_[i] : 0u;
+        if (t >= s->ntypes)
+            {
+            set_error("hb2_system_set_particles: type id out of range");
+            return HB2_ERR_INVALID;
+            }
+        float tw;
+        memcpy(&tw, &t, 4);
+        hp[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], tw);
+        hv[i] = make_float4(vel3 ? vel3[3 * i] : 0.f, vel3 ? vel3[3 * i + 1] : 0.f,
+                            vel3 ? vel3[3 * i + 2] : 0.f, mass ? mass[i] : 1.0f);
+        ht[i] = i;
+        }
+    if (image3)
+        memcpy(hi.data(), image3, sizeof(int) * 3 * (size_t)N);
+    s->cur = 0;
+    HB2_CUDA(cudaMemcpyAsync(s->pos[0], hp.data(), sizeof(float4) * N, cudaMemcpyHostToDevice,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(s->vel[0], hv.data(), sizeof(float4) * N, cudaMemcpyHostToDevice,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(s->image[0], hi.data(), sizeof(int) * 3 * (size_t)N,
+                             cudaMemcpyHostToDevice, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(s->tag[0], ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(s->rtag, ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice,
+                             s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    s->order_epoch++;
+    for (auto* nl : s->nlists)
+        {
+        nl->force_update = true;
+        nl->has_list = false;
+        }
+    for (auto* p : s->pairs)
+        p->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_system_get_particles(hb2_system* s, float* pos3, float* vel3, float* mass,
+                                               uint32_t* typeid_, int32_t* image3)
+    {
+    if (!s)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(s->device));
+    const uint32_t N = s->N;
+    std::vector<float4> hp(N), hv(N);
+    std::vector<int> hi(3 * (size_t)N);
+    std::vector<uint32_t> ht(N);
+    const int c = s->cur;
+    HB2_CUDA(cudaMemcpyAsync(hp.data(), s->pos[c], sizeof(float4) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(hv.data(), s->vel[c], sizeof(float4) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(hi.data(), s->image[c], sizeof(int) * 3 * (size_t)N,
+                             cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(ht.data(), s->tag[c], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t k = 0; k < N; k++)
+        {
+        const uint32_t t = ht[k];
+        if (pos3)
+            {
+            pos3[3 * t] = hp[k].x;
+            pos3[3 * t + 1] = hp[k].y;
+            pos3[3 * t + 2] = hp[k].z;
+            }
+        if (typeid_)
+            memcpy(&typeid_[t], &hp[k].w, 4);
+        if (vel3)
+            {
+            vel3[3 * t] = hv[k].x;
+            vel3[3 * t + 1] = hv[k].y;
+            vel3[3 * t + 2] = hv[k].z;
+            }
+        if (mass)
+            mass[t] = hv[k].w;
+        if (image3)
+            {
+            image3[3 * t] = hi[3 * k];
+            image3[3 * t + 1] = hi[3 * k + 1];
+            image3[3 * t + 2] = hi[3 * k + 2];
+            }
+        }
+    return HB2_OK;
+    }
+
+extern "C" uint32_t hb2_system_n(const hb2_system* s)
+    {
+    return s ? s->N : 0;
+    }
+extern "C" uint64_t hb2_system_timestep(const hb2_system* s)
+    {
+    return s ? s->timestep : 0;
+    }
+extern "C" hb2_status hb2_system_set_timestep(hb2_system* s, uint64_t t)
+    {
+    if (!s)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(s->device));
+    return s->set_timestep(t);
+    }
+extern "C" hb2_status hb2_system_set_compute_virial(hb2_system* s, int on)
+    {
+    if (!s)
+        return HB2_ERR_INVALID;
+    if (s->compute_virial != (on != 0))
+        for (auto* p : s->pairs)
+            p->computed = false; // flags changed -> recompute (hoomd/ForceCompute.cc:562-574)
+    s->compute_virial = on != 0;
+    return HB2_OK;
+    }
+extern "C" hb2_status hb2_system_synchronize(hb2_system* s)
+    {
+    if (!s)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    return HB2_OK;
+    }
+
+// =================================================================================================
+// neighbour list
+// =================================================================================================
+hb2_status hb2_nlist::update_r_list()
+    {
+    // hoomd/md/NeighborList.cc:452-529: r_cut = max over consumers; r_listsq = (r_cut + buff)^2 or 0
+    const uint32_t nt = sys->ntypes;
+    r_cut.assign((size_t)nt * nt, 0.0);
+    for (auto* p : consumers)
+        for (size_t q = 0; q < r_cut.size(); q++)
+            r_cut[q] = std::max(r_cut[q], p->r_cut[q]);
+    r_listsq.assign((size_t)nt * nt, 0.0);
+    rcut_max.assign(nt, 0.0);
+    rcut_max_max = 0.0;
+    r_list_min = 0.0;
+    for (uint32_t i = 0; i < nt; i++)
+        {
+        double mi = 0.0;
+        for (uint32_t j = 0; j < nt; j++)
+            {
+            const double rc = r_cut[(size_t)j * nt + i];
+            mi = std::max(mi, rc);
+            const double r_list = (rc > 0.0) ? rc + buffer : 0.0;
+            r_listsq[(size_t)j * nt + i] = r_list * r_list;
+            if (r_list > 0.0 && (r_list_min == 0.0 || r_list < r_list_min))
+                r_list_min = r_list;
+            }
+        rcut_max[i] = mi;
+        rcut_max_max = std::max(rcut_max_max, mi);
+        }
+    if (!d_r_listsq)
+        HB2_TRY(dev_alloc(&d_r_listsq, (size_t)nt * nt));
+    HB2_CUDA(cudaMemcpyAsync(d_r_listsq, r_listsq.data(), sizeof(double) * nt * nt,
+                             cudaMemcpyHostToDevice, sys->stream));
+    HB2_CUDA(cudaStreamSynchronize(sys->stream));
+    params_dirty = false;
+    return HB2_OK;
+    }
+
+hb2_status hb2_nlist::ensure_capacity()
+    {
+    const uint32_t N = sys->N;
+    // cell grid: dim = floor(L / (max r_cut + buffer)), at least 1 (hoomd/CellList.cc:83-131 with
+    // the nominal width of hoomd/md/NeighborListBinned.cc:39-45)
+    const double width = rcut_max_max + buffer;
+    uint32_t d[3];
+    for (int k = 0; k < 3; k++)
+        {
+        d[k] = (uint32_t)(sys->box.L[k] / width);
+        if (d[k] == 0)
+            d[k] = 1;
+        }
+    dim = make_uint3(d[0], d[1], d[2]);
+    const uint64_t Nc64 = (uint64_t)d[0] * d[1] * d[2];
+    if (Nc64 >= (1ull << 31))
+        {
+        set_error("nlist: cell grid too large");
+        return HB2_ERR_INVALID;
+        }
+    const uint32_t Nc = (uint32_t)Nc64;
+    if (Nc + 1 > cell_cap)
+        {
+        dev_free(d_cell_start);
+        HB2_TRY(dev_alloc(&d_cell_start, (size_t)Nc + 1));
+        cell_cap = Nc + 1;
+        }
+    const size_t need_tmp = cell_order_tmp_bytes(N, Nc);
+    if (need_tmp > tmp_bytes)
+        {
+        if (d_tmp)
+            cudaFree(d_tmp);
+        d_tmp = nullptr;
+        HB2_CUDA(cudaMalloc(&d_tmp, need_tmp));
+        tmp_bytes = need_tmp;
+        }
+    if (N > cap_N)
+        {
+        dev_free(d_order);
+        dev_free(d_n_neigh);
+        dev_free(d_last_pos);
+        HB2_TRY(dev_alloc(&d_order, N));
+        HB2_TRY(dev_alloc(&d_n_neigh, N));
+        HB2_TRY(dev_alloc(&d_last_pos, N));
+        cap_N = N;
+        }
+    if (pitch == 0)
+        {
+        // first guess from the mean density; grows on overflow like hoomd/md/NeighborList.cc:1601-1617
+        const double vol = sys->box.L[0] * sys->box.L[1] * sys->box.L[2];
+        const double rl = rcut_max_max + buffer;
+        const double est = (double)N / vol * 4.18879020478639 * rl * rl * rl;
+        pitch = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 16.0), (double)std::max(N, 8u));
+        pitch = (pitch + 7u) & ~7u;
+        }
+    if ((size_t)N * pitch > nlist_cap)
+        {
+        dev_free(d_nlist);
+        HB2_TRY(dev_alloc(&d_nlist, (size_t)N * pitch));
+        nlist_cap = (size_t)N * pitch;
+        }
+    return HB2_OK;
+    }
+
+hb2_status hb2_nlist::rebuild(uint64_t timestep)
+    {
+    hb2_system* s = sys;
+    if (!s->has_box || s->N == 0 || !s->pos[0])
+        {
+        set_error("nlist: the system has no box or no particles");
+        return HB2_ERR_INVALID;
+        }
+    if (params_dirty)
+        HB2_TRY(update_r_list());
+    // hoomd/md/NeighborList.cc:535-561
+    const double rmax = rcut_max_max + buffer;
+    for (int d = 0; d < 3; d++)
+        if (s->box.L[d] <= rmax * 2.0)
+            {
+            set_error("nlist: Simulation box is too small, the neighbor list is searching beyond "
+                      "the minimum image: rmax=" + std::to_string(rmax));
+            return HB2_ERR_BOX_TOO_SMALL;
+            }
+    HB2_TRY(ensure_capacity());
+    const uint32_t N = s->N;
+    cudaStream_t st = s->stream;
+
+    HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
+    const int c = s->cur, o = 1 - c;
+    HB2_TRY(compute_cell_order(s->pos[c], N, s->box, dim, d_order, d_cell_start, d_conditions, d_tmp,
+                               tmp_bytes, st));
+    HB2_TRY(reorder_particles(d_order, N, s->pos[c], s->vel[c], s->image[c], s->tag[c], nullptr,
+                              s->pos[o], s->vel[o], s->image[o], s->tag[o], nullptr, s->rtag, st));
+    s->cur = o;
+    s->order_epoch++;
+
+    for (;;)
+        {
+        NlistBuildArgs a;
+        a.pos = s->pos[s->cur];
+        a.N = N;
+        a.dim = dim;
+        a.cell_start = d_cell_start;
+        a.r_listsq = d_r_listsq;
+        a.ntypes = s->ntypes;
+        a.r_listsq_single = r_listsq[0];
+        a.r_list_min = r_list_min;
+        a.Lmax = (float)std::max(s->box.L[0], std::max(s->box.L[1], s->box.L[2]));
+        a.nlist = d_nlist;
+        a.pitch = pitch;
+        a.n_neigh = d_n_neigh;
+        a.last_pos = d_last_pos;
+        a.conditions = d_conditions;
+        HB2_TRY(launch_nlist_build(a, s->box, st));
+        HB2_CUDA(cudaMemcpyAsync(h_conditions, d_conditions, 4 * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, st));
+        HB2_CUDA(cudaStreamSynchronize(st));
+        if (h_conditions[1])
+            {
+            set_error("Particle with index " + std::to_string(h_conditions[1] - 1)
+                      + " has NaN for its position.");
+            return HB2_ERR_NAN_POSITION;
+            }
+        if (h_conditions[2])
+            {
+            set_error("Particle with index " + std::to_string(h_conditions[2] - 1)
+                      + " is no longer in the simulation box.");
+            return HB2_ERR_OUT_OF_BOX;
+            }
+        max_neigh = h_conditions[0];
+        if (max_neigh <= pitch)
+            break;
+        // overflow: regrow to a multiple of 8 with headroom and rebuild
+        // (hoomd/md/NeighborList.cc:411-427, :1601-1617)
+        pitch = ((uint32_t)(max_neigh * 1.125) + 8u + 7u) & ~7u;
+        if ((size_t)N * pitch > nlist_cap)
+            {
+            dev_free(d_nlist);
+            HB2_TRY(dev_alloc(&d_nlist, (size_t)N * pitch));
+            nlist_cap = (size_t)N * pitch;
+            }
+        HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
+        }
+    if (has_list && timestep > last_update_step)
+        shortest_rebuild = std::min<uint64_t>(shortest_rebuild, timestep - last_update_step);
+    has_list = true;
+    force_update = false;
+    num_builds++;
+    last_update_step = timestep;
+    return HB2_OK;
+    }
+
+hb2_status hb2_nlist::compute(uint64_t timestep, bool flag_known, bool flag_value)
+    {
+    // hoomd/md/NeighborList.cc:363-435 + needsUpdating :1325-1418
+    if (params_dirty)
+        {
+        HB2_TRY(update_r_list());
+        force_update = true;
+        }
+    bool need = force_update || !has_list;
+    if (!need)
+        {
+        if (buffer < 1e-6)
+            need = true;
+        else if (timestep >= last_update_step + rebuild_check_delay)
+            {
+            if (!check_dist)
+                need = true;
+            else if (flag_known)
+                need = flag_value;
+            else
+                {
+                // standalone distance check against last_pos (positions may have been set outside)
+                need = true;
+                }
+            }
+        }
+    if (need)
+        return rebuild(timestep);
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_create(hb2_nlist** out, hb2_system* s, double buffer,
+                                       uint32_t rebuild_check_delay, int check_dist)
+    {
+    if (!out || !s || buffer < 0)
+        {
+        set_error("hb2_nlist_create: bad arguments");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    hb2_nlist* nl = new hb2_nlist();
+    nl->sys = s;
+    nl->buffer = buffer;
+    nl->rebuild_check_delay = rebuild_check_delay;
+    nl->check_dist = check_dist != 0;
+    hb2_status st = dev_alloc(&nl->d_conditions, 4);
+    if (st == HB2_OK && cudaMallocHost((void**)&nl->h_conditions, 4 * sizeof(uint32_t)) != cudaSuccess)
+        st = cuda_fail(cudaGetLastError(), "cudaMallocHost");
+    if (st != HB2_OK)
+        {
+        delete nl;
+        return st;
+        }
+    cudaMemsetAsync(nl->d_conditions, 0, 4 * sizeof(uint32_t), s->stream);
+    s->nlists.push_back(nl);
+    *out = nl;
+    return HB2_OK;
+    }
+
+extern "C" void hb2_nlist_destroy(hb2_nlist* nl)
+    {
+    if (!nl)
+        return;
+    hb2_system* s = nl->sys;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    s->nlists.erase(std::remove(s->nlists.begin(), s->nlists.end(), nl), s->nlists.end());
+    dev_free(nl->d_cell_start);
+    dev_free(nl->d_order);
+    if (nl->d_tmp)
+        cudaFree(nl->d_tmp);
+    dev_free(nl->d_r_listsq);
+    dev_free(nl->d_nlist);
+    dev_free(nl->d_n_neigh);
+    dev_free(nl->d_last_pos);
+    dev_free(nl->d_conditions);
+    if (nl->h_conditions)
+        cudaFreeHost(nl->h_conditions);
+    delete nl;
+    }
+
+extern "C" hb2_status hb2_nlist_set_buffer(hb2_nlist* nl, double buffer)
+    {
+    if (!nl || buffer < 0)
+        return HB2_ERR_INVALID;
+    nl->buffer = buffer;
+    nl->params_dirty = true;
+    nl->force_update = true;
+    nl->pitch = 0; // re-estimate
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_compute(hb2_nlist* nl)
+    {
+    if (!nl)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(nl->sys->device));
+    nl->force_update = true;
+    return nl->compute(nl->sys->timestep, false, false);
+    }
+extern "C" uint64_t hb2_nlist_num_builds(const hb2_nlist* nl)
+    {
+    return nl ? nl->num_builds : 0;
+    }
+extern "C" uint64_t hb2_nlist_shortest_rebuild(const hb2_nlist* nl)
+    {
+    return nl ? (nl->shortest_rebuild == ~0ull ? 0 : nl->shortest_rebuild) : 0;
+    }
+extern "C" hb2_status hb2_nlist_dimensions(const hb2_nlist* nl, uint32_t dim[3])
+    {
+    if (!nl || !dim)
+        return HB2_ERR_INVALID;
+    dim[0] = nl->dim.x;
+    dim[1] = nl->dim.y;
+    dim[2] = nl->dim.z;
+    return HB2_OK;
+    }
+
+static hb2_status nlist_download(hb2_nlist* nl, std::vector<uint32_t>& n_neigh,
+                                 std::vector<uint32_t>& list, std::vector<uint32_t>& tag)
+    {
+    hb2_system* s = nl->sys;
+    if (!nl->has_list)
+        {
+        set_error("nlist: no neighbour list has been built yet");
+        return HB2_ERR_INVALID;
+        }
+    const uint32_t N = s->N;
+    n_neigh.resize(N);
+    tag.resize(N);
+    list.resize((size_t)N * nl->pitch);
+    HB2_CUDA(cudaMemcpyAsync(n_neigh.data(), nl->d_n_neigh, sizeof(uint32_t) * N,
+                             cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(tag.data(), s->tag[s->cur], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(list.data(), nl->d_nlist, sizeof(uint32_t) * (size_t)N * nl->pitch,
+                             cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_pair_count(hb2_nlist* nl, uint64_t* n_pairs)
+    {
+    if (!nl || !n_pairs)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(nl->sys->device));
+    if (!nl->has_list)
+        {
+        set_error("nlist: no neighbour list has been built yet");
+        return HB2_ERR_INVALID;
+        }
+    std::vector<uint32_t> nn(nl->sys->N);
+    HB2_CUDA(cudaMemcpyAsync(nn.data(), nl->d_n_neigh, sizeof(uint32_t) * nn.size(),
+                             cudaMemcpyDeviceToHost, nl->sys->stream));
+    HB2_CUDA(cudaStreamSynchronize(nl->sys->stream));
+    uint64_t t = 0;
+    for (uint32_t v : nn)
+        t += v;
+    *n_pairs = t / 2; // full list: every unordered pair is stored twice
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_pair_list(hb2_nlist* nl, uint32_t* pairs, uint64_t cap,
+                                          uint64_t* n_pairs)
+    {
+    if (!nl || !pairs || !n_pairs)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(nl->sys->device));
+    std::vector<uint32_t> nn, list, tag;
+    HB2_TRY(nlist_download(nl, nn, list, tag));
+    uint64_t n = 0;
+    const uint32_t N = nl->sys->N;
+    for (uint32_t i = 0; i < N; i++)
+        for (uint32_t k = 0; k < nn[i]; k++)
+            {
+            const uint32_t j = list[(size_t)i * nl->pitch + k];
+            if (i < j) // half-list view: each unordered pair once (hoomd/md/NeighborList.cc:1814-1828)
+                {
+                if (n < cap)
+                    {
+                    pairs[2 * n] = tag[i];
+                    pairs[2 * n + 1] = tag[j];
+                    }
+                n++;
+                }
+            }
+    *n_pairs = n;
+    if (n > cap)
+        {
+        set_error("hb2_nlist_pair_list: output buffer too small");
+        return HB2_ERR_INVALID;
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_stats(hb2_nlist* nl, double* mean_neigh, uint32_t* max_neigh,
+                                      uint32_t* pitch)
+    {
+    if (!nl)
+        return HB2_ERR_INVALID;
+    uint64_t np = 0;
+    HB2_TRY(hb2_nlist_pair_count(nl, &np));
+    if (mean_neigh)
+        *mean_neigh = nl->sys->N ? 2.0 * (double)np / nl->sys->N : 0.0;
+    if (max_neigh)
+        *max_neigh = nl->max_neigh;
+    if (pitch)
+        *pitch = nl->pitch;
+    return HB2_OK;
+    }
+
+// =================================================================================================
+// pair force
+// =================================================================================================
+static unsigned n_user_params(hb2_evaluator ev)
+    {
+    switch (ev)
+        {
+    case HB2_EVAL_LJ:
+        return EvaluatorPairLJ::n_user_params;
+    case HB2_EVAL_DPD:
+        return EvaluatorPairDPDThermoDPD::n_user_params;
+    case HB2_EVAL_DPD_CONSERVATIVE:
+        return 1;
+    case HB2_EVAL_EXAMPLE:
+        return EvaluatorPairExample::n_user_params;
+        }
+    return 0;
+    }
+
+extern "C" hb2_status hb2_pack_params(hb2_evaluator ev, const double* user, uint32_t n_user,
+                                      float packed[2])
+    {
+    if (!user || !packed || n_user < n_user_params(ev))
+        {
+        set_error("hb2_pack_params: not enough user parameters for this evaluator");
+        return HB2_ERR_INVALID;
+        }
+    switch (ev)
+        {
+    case HB2_EVAL_LJ:
+        {
+        EvaluatorPairLJ::param_type p;
+        EvaluatorPairLJ::pack(user, p);
+        memcpy(packed, &p, sizeof(p));
+        return HB2_OK;
+        }
+    case HB2_EVAL_DPD:
+        {
+        EvaluatorPairDPDThermoDPD::param_type p;
+        EvaluatorPairDPDThermoDPD::pack(user, p);
+        memcpy(packed, &p, sizeof(p));
+        return HB2_OK;
+        }
+    case HB2_EVAL_DPD_CONSERVATIVE:
+        packed[0] = (float)user[0];
+        packed[1] = 0.f;
+        return HB2_OK;
+    case HB2_EVAL_EXAMPLE:
+        {
+        EvaluatorPairExample::param_type p;
+        EvaluatorPairExample::pack(user, p);
+        memcpy(packed, &p, sizeof(p));
+        return HB2_OK;
+        }
+        }
+    set_error("hb2_pack_params: unknown evaluator");
+    return HB2_ERR_INVALID;
+    }
+
+namespace hb2
+    {
+hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,
+                              const hb2_box& box, cudaStream_t stream)
+    {
+    switch (ev)
+        {
+    case HB2_EVAL_LJ:
+        return pair_forces_lj(mode, a, box, stream);
+    case HB2_EVAL_DPD:
+        return pair_forces_dpd(mode, a, box, stream);
+    case HB2_EVAL_DPD_CONSERVATIVE:
+        return pair_forces_dpd_conservative(mode, a, box, stream);
+    case HB2_EVAL_EXAMPLE:
+        return pair_forces_example(mode, a, box, stream);
+        }
+    set_error("pair forces: unknown evaluator");
+    return HB2_ERR_INVALID;
+    }
+    } // namespace hb2
+
+hb2_status hb2_pair::upload_params()
+    {
+    const uint32_t nt = sys->ntypes;
+    const size_t nt2 = (size_t)nt * nt;
+    packed.assign(2 * nt2, 0.f);
+    rcutsq.assign(nt2, 0.f);
+    ronsq.assign(nt2, 0.f);
+    for (size_t q = 0; q < nt2; q++)
+        {
+        if (!have_params[q])
+            {
+            set_error("pair: parameters are not set for every type pair");
+            return HB2_ERR_INVALID;
+            }
+        HB2_TRY(hb2_pack_params(ev, &user[2 * q], 2, &packed[2 * q]));
+        rcutsq[q] = (float)(r_cut[q] * r_cut[q]); // hoomd/md/PotentialPair.h:498
+        ronsq[q] = (float)(r_on[q] * r_on[q]);
+        }
+    if (!d_params)
+        {
+        HB2_TRY(dev_alloc(&d_params, 2 * nt2));
+        HB2_TRY(dev_alloc(&d_rcutsq, nt2));
+        HB2_TRY(dev_alloc(&d_ronsq, nt2));
+        }
+    cudaStream_t st = sys->stream;
+    HB2_CUDA(cudaMemcpyAsync(d_params, packed.data(), sizeof(float) * 2 * nt2, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(d_rcutsq, rcutsq.data(), sizeof(float) * nt2, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(d_ronsq, ronsq.data(), sizeof(float) * nt2, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    params_dirty = false;
+    return HB2_OK;
+    }
+
+hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value)
+    {
+    hb2_system* s = sys;
+    if (params_dirty)
+        HB2_TRY(upload_params());
+    HB2_TRY(nl->compute(timestep, flag_known, flag_value));
+    const uint32_t N = s->N;
+    if (N > cap_N)
+        {
+        dev_free(d_force);
+        dev_free(d_virial);
+        HB2_TRY(dev_alloc(&d_force, N));
+        HB2_TRY(dev_alloc(&d_virial, 6 * (size_t)N));
+        cap_N = N;
+        }
+    PairArgs a;
+    a.pos = s->pos[s->cur];
+    a.vel = s->vel[s->cur];
+    a.tag = s->tag[s->cur];
+    a.N = N;
+    a.n_neigh = nl->d_n_neigh;
+    a.nlist = nl->d_nlist;
+    a.pitch = nl->pitch;
+    a.params = d_params;
+    a.rcutsq = d_rcutsq;
+    a.ronsq = d_ronsq;
+    a.params0[0] = packed[0];
+    a.params0[1] = packed[1];
+    a.rcutsq0 = rcutsq[0];
+    a.ronsq0 = ronsq[0];
+    a.ntypes = s->ntypes;
+    a.force = d_force;
+    a.virial = s->compute_virial ? d_virial : nullptr;
+    a.virial_pitch = N;
+    a.seed = s->seed;
+    a.d_timestep = nullptr;
+    a.timestep = timestep;
+    a.dt = (float)dt;
+    a.kT = (float)kT;
+    a.tpp = tpp;
+    HB2_TRY(launch_pair_forces(ev, mode, a, s->box, s->stream));
+    virial_valid = s->compute_virial;
+    computed = true;
+    computed_step = timestep;
+    computed_epoch = s->order_epoch;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_create(hb2_pair** out, hb2_system* s, hb2_nlist* nl, hb2_evaluator ev,
+                                      hb2_shift_mode mode)
+    {
+    if (!out || !s || !nl || nl->sys != s)
+        {
+        set_error("hb2_pair_create: bad arguments");
+        return HB2_ERR_INVALID;
+        }
+    hb2_pair* p = new hb2_pair();
+    p->sys = s;
+    p->nl = nl;
+    p->ev = ev;
+    p->mode = mode;
+    const size_t nt2 = (size_t)s->ntypes * s->ntypes;
+    p->user.assign(2 * nt2, 0.0);
+    p->have_params.assign(nt2, 0);
+    p->r_cut.assign(nt2, 0.0);
+    p->r_on.assign(nt2, 0.0);
+    nl->consumers.push_back(p); // addRCutMatrix, hoomd/md/PotentialPair.h:369-371
+    nl->params_dirty = true;
+    s->pairs.push_back(p);
+    *out = p;
+    return HB2_OK;
+    }
+
+extern "C" void hb2_pair_destroy(hb2_pair* p)
+    {
+    if (!p)
+        return;
+    hb2_system* s = p->sys;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    auto& c = p->nl->consumers;
+    c.erase(std::remove(c.begin(), c.end(), p), c.end());
+    p->nl->params_dirty = true;
+    s->pairs.erase(std::remove(s->pairs.begin(), s->pairs.end(), p), s->pairs.end());
+    dev_free(p->d_params);
+    dev_free(p->d_rcutsq);
+    dev_free(p->d_ronsq);
+    dev_free(p->d_force);
+    dev_free(p->d_virial);
+    delete p;
+    }
+
+static bool pair_index(hb2_pair* p, uint32_t ti, uint32_t tj, size_t& a, size_t& b)
+    {
+    const uint32_t nt = p->sys->ntypes;
+    if (ti >= nt || tj >= nt)
+        {
+        set_error("pair: type index out of range");
+        return false;
+        }
+    a = (size_t)tj * nt + ti;
+    b = (size_t)ti * nt + tj;
+    return true;
+    }
+
+extern "C" hb2_status hb2_pair_set_params(hb2_pair* p, uint32_t ti, uint32_t tj,
+                                          const double* user_params, uint32_t n_user)
+    {
+    size_t a, b;
+    if (!p || !user_params || !pair_index(p, ti, tj, a, b))
+        return HB2_ERR_INVALID;
+    if (n_user < n_user_params(p->ev) || n_user > 2)
+        {
+        set_error("hb2_pair_set_params: wrong number of parameters for this evaluator");
+        return HB2_ERR_INVALID;
+        }
+    for (size_t q : {a, b})
+        {
+        p->user[2 * q] = user_params[0];
+        p->user[2 * q + 1] = n_user > 1 ? user_params[1] : 0.0;
+        p->have_params[q] = 1;
+        }
+    p->params_dirty = true;
+    p->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_set_r_cut(hb2_pair* p, uint32_t ti, uint32_t tj, double r_cut)
+    {
+    size_t a, b;
+    if (!p || !pair_index(p, ti, tj, a, b))
+        return HB2_ERR_INVALID;
+    p->r_cut[a] = p->r_cut[b] = r_cut;
+    p->params_dirty = true;
+    p->computed = false;
+    p->nl->params_dirty = true; // notifyRCutMatrixChange
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_set_r_on(hb2_pair* p, uint32_t ti, uint32_t tj, double r_on)
+    {
+    size_t a, b;
+    if (!p || !pair_index(p, ti, tj, a, b))
+        return HB2_ERR_INVALID;
+    p->r_on[a] = p->r_on[b] = r_on;
+    p->params_dirty = true;
+    p->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_set_kT(hb2_pair* p, double kT)
+    {
+    if (!p)
+        return HB2_ERR_INVALID;
+    p->kT = kT;
+    p->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_set_threads_per_particle(hb2_pair* p, uint32_t tpp)
+    {
+    if (!p || tpp == 0 || tpp > 32 || (tpp & (tpp - 1)))
+        {
+        set_error("threads_per_particle must be a power of two in [1, 32]");
+        return HB2_ERR_INVALID;
+        }
+    p->tpp = tpp;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_compute(hb2_pair* p, uint64_t timestep)
+    {
+    if (!p)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(p->sys->device));
+    return p->compute(timestep);
+    }
+
+static hb2_status pair_ensure(hb2_pair* p)
+    {
+    // recompute when the particle order changed or nothing was computed yet
+    // (hoomd/ForceCompute.cc:562-574: "sorted / new timestep / flags changed")
+    if (!p->computed || p->computed_epoch != p->sys->order_epoch
+        || (p->sys->compute_virial && !p->virial_valid))
+        return p->compute(p->sys->timestep);
+    return HB2_OK;
+    }
+
+static hb2_status pair_download(hb2_pair* p, std::vector<float4>& f, std::vector<float>* vir,
+                                std::vector<uint32_t>& tag)
+    {
+    hb2_system* s = p->sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_TRY(pair_ensure(p));
+    const uint32_t N = s->N;
+    f.resize(N);
+    tag.resize(N);
+    HB2_CUDA(cudaMemcpyAsync(f.data(), p->d_force, sizeof(float4) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(tag.data(), s->tag[s->cur], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    if (vir)
+        {
+        vir->resize(6 * (size_t)N);
+        HB2_CUDA(cudaMemcpyAsync(vir->data(), p->d_virial, sizeof(float) * 6 * (size_t)N,
+                                 cudaMemcpyDeviceToHost, s->stream));
+        }
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_get_forces(hb2_pair* p, double* forces3)
+    {
+    if (!p || !forces3)
+        return HB2_ERR_INVALID;
+    std::vector<float4> f;
+    std::vector<uint32_t> tag;
+    HB2_TRY(pair_download(p, f, nullptr, tag));
+    for (size_t k = 0; k < f.size(); k++)
+        {
+        forces3[3 * (size_t)tag[k]] = f[k].x;
+        forces3[3 * (size_t)tag[k] + 1] = f[k].y;
+        forces3[3 * (size_t)tag[k] + 2] = f[k].z;
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_get_energies(hb2_pair* p, double* energies)
+    {
+    if (!p || !energies)
+        return HB2_ERR_INVALID;
+    std::vector<float4> f;
+    std::vector<uint32_t> tag;
+    HB2_TRY(pair_download(p, f, nullptr, tag));
+    for (size_t k = 0; k < f.size(); k++)
+        energies[tag[k]] = f[k].w;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_get_virials(hb2_pair* p, double* virials6)
+    {
+    if (!p || !virials6)
+        return HB2_ERR_INVALID;
+    if (!p->sys->compute_virial)
+        {
+        set_error("virials are not computed unless the pressure flag is set "
+                  "(always_compute_pressure)");
+        return HB2_ERR_INVALID;
+        }
+    std::vector<float4> f;
+    std::vector<float> v;
+    std::vector<uint32_t> tag;
+    HB2_TRY(pair_download(p, f, &v, tag));
+    const size_t N = f.size();
+    for (size_t k = 0; k < N; k++)
+        for (int q = 0; q < 6; q++)
+            virials6[6 * (size_t)tag[k] + q] = v[q * N + k];
+    return HB2_OK;
+    }
+
+static hb2_status sums7(hb2_pair* p, double out[7])
+    {
+    hb2_system* s = p->sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_TRY(pair_ensure(p));
+    HB2_TRY(launch_reduce_energy(p->d_force, p->virial_valid ? p->d_virial : nullptr, s->N, s->N,
+                                 s->d_partial, s->d_ticket + 1, s->d_sums + 1, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(out, s->d_sums + 1, 7 * sizeof(double), cudaMemcpyDeviceToHost,
+                             s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    return HB2_OK;
+    }
+
+static void tail_correction(hb2_pair* p, double& e, double& w)
+    {
+    // hoomd/md/PotentialPair.h:283-337 with hoomd/md/EvaluatorPairLJ.h:213-248
+    e = 0.0;
+    w = 0.0;
+    if (!p->tail_correction || p->ev != HB2_EVAL_LJ)
+        return;
+    hb2_system* s = p->sys;
+    const uint32_t nt = s->ntypes;
+    std::vector<float4> hp(s->N);
+    cudaMemcpyAsync(hp.data(), s->pos[s->cur], sizeof(float4) * s->N, cudaMemcpyDeviceToHost, s->stream);
+    cudaStreamSynchronize(s->stream);
+    std::vector<uint32_t> n_per_type(nt, 0);
+    for (auto& q : hp)
+        {
+        uint32_t t;
+        memcpy(&t, &q.w, 4);
+        n_per_type[t]++;
+        }
+    const double volume = s->box.L[0] * s->box.L[1] * s->box.L[2];
+    const double pi = 3.14159265358979323846;
+    for (uint32_t ti = 0; ti < nt; ti++)
+        {
+        const double rho_i = n_per_type[ti] / volume;
+        for (uint32_t tj = 0; tj < nt; tj++)
+            {
+            const double rho_j = n_per_type[tj] / volume;
+            const size_t tp = (size_t)tj * nt + ti;
+            const double eps = p->user[2 * tp], sig = p->user[2 * tp + 1];
+            const double s6 = sig * sig * sig * sig * sig * sig;
+            const double lj1 = 4.0 * eps * s6 * s6, lj2 = 4.0 * eps * s6;
+            const double rcutsq = p->r_cut[tp] * p->r_cut[tp];
+            double ie = 0.0, ip = 0.0;
+            if (rcutsq != 0)
+                {
+                const double rc3inv = 1.0 / pow(rcutsq, 1.5);
+                const double rc9inv = rc3inv * rc3inv * rc3inv;
+                ie = lj1 / 9.0 * rc9inv - lj2 / 3.0 * rc3inv;
+                ip = lj1 * 4.0 / 3.0 * rc9inv - lj2 * 2.0 * rc3inv;
+                }
+            e += 2.0 * n_per_type[ti] * pi * rho_j * ie;
+            const double dp = 4.0 / 6.0 * rho_i * rho_j * pi * ip;
+            w += 3 * volume * dp / 3.0;
+            }
+        }
+    }
+
+extern "C" hb2_status hb2_pair_get_energy(hb2_pair* p, double* energy)
+    {
+    if (!p || !energy)
+        return HB2_ERR_INVALID;
+    double v[7];
+    HB2_TRY(sums7(p, v));
+    double e, w;
+    tail_correction(p, e, w);
+    *energy = v[0] + e; // hoomd/ForceCompute.cc:213-234: sum + external energy
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_set_tail_correction(hb2_pair* p, int on)
+    {
+    if (!p)
+        return HB2_ERR_INVALID;
+    if (on && p->ev != HB2_EVAL_LJ)
+        {
+        set_error("tail_correction is only available for the LJ evaluator");
+        return HB2_ERR_INVALID;
+        }
+    p->tail_correction = on != 0;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_get_additional(hb2_pair* p, double* energy, double virial6[6])
+    {
+    if (!p)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(p->sys->device));
+    double e, w;
+    tail_correction(p, e, w);
+    if (energy)
+        *energy = e;
+    if (virial6)
+        {
+        for (int q = 0; q < 6; q++)
+            virial6[q] = 0.0;
+        virial6[0] = virial6[3] = virial6[5] = w / 3.0 * 1.0; // diagonal share (PotentialPair.h:330-337)
+        }
+    return HB2_OK;
+    }
+
+// =================================================================================================
+// integrator
+// =================================================================================================
+extern "C" hb2_status hb2_integrator_create(hb2_integrator** out, hb2_system* s, double dt)
+    {
+    if (!out || !s)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(s->device));
+    hb2_integrator* it = new hb2_integrator();
+    it->sys = s;
+    it->dt = dt;
+    cudaEventCreate(&it->ev0);
+    cudaEventCreate(&it->ev1);
+    *out = it;
+    return HB2_OK;
+    }
+
+extern "C" void hb2_integrator_destroy(hb2_integrator* it)
+    {
+    if (!it)
+        return;
+    cudaSetDevice(it->sys->device);
+    cudaEventDestroy(it->ev0);
+    cudaEventDestroy(it->ev1);
+    delete it;
+    }
+
+extern "C" hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p)
+    {
+    if (!it || !p || p->sys != it->sys)
+        return HB2_ERR_INVALID;
+    if (!it->forces.empty())
+        {
+        set_error("integrator: this path carries exactly one pair force (net force aliases it, "
+                  "hoomd/Integrator.cc:166-246 with one ForceCompute)");
+        return HB2_ERR_INVALID;
+        }
+    it->forces.push_back(p);
+    it->prepared = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat,
+                                                         double kT, double tau)
+    {
+    if (!it || (thermostat != 0 && thermostat != 1))
+        return HB2_ERR_INVALID;
+    it->thermostat = thermostat;
+    it->kT = kT;
+    it->tau = tau;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
+    {
+    if (!it || it->forces.empty())
+        {
+        set_error("integrator: no force attached");
+        return HB2_ERR_INVALID;
+        }
+    hb2_system* s = it->sys;
+    hb2_pair* pf = it->forces[0];
+    hb2_nlist* nl = pf->nl;
+    HB2_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    pf->dt = it->dt;
+    const uint32_t N = s->N;
+    double* d_ke = s->d_sums;
+    double* d_rescale = s->d_sums + 8;
+    // translational degrees of freedom of filter All, momentum conserving, 3D
+    // (hoomd/md/IntegratorTwoStep.cc:154-189)
+    const double dof = 3.0 * N - 3.0;
+
+    HB2_CUDA(cudaEventRecord(it->ev0, st));
+    // prepRun (hoomd/md/IntegratorTwoStep.cc:226-281): net force at the current timestep
+    if (!it->prepared || !pf->computed || pf->computed_epoch != s->order_epoch
+        || pf->computed_step != s->timestep)
+        {
+        HB2_TRY(pf->compute(s->timestep));
+        it->prepared = true;
+        }
+    if (it->thermostat == 1)
+        HB2_TRY(launch_kinetic(s->vel[s->cur], N, s->d_partial, s->d_ticket, d_ke, st));
+
+    for (uint64_t step = 0; step < nsteps; step++)
+        {
+        const uint64_t t = s->timestep;
+        const double* rescale = nullptr;
+        if (it->thermostat == 1)
+            {
+            HB2_CUDA(cudaMemcpyAsync(s->d_timestep, &s->timestep, sizeof(uint64_t),
+                                     cudaMemcpyHostToDevice, st));
+            HB2_TRY(launch_bussi(d_ke, dof, it->dt, it->kT, it->tau, s->d_timestep, s->seed, 0u,
+                                 d_rescale, st));
+            rescale = d_rescale;
+            }
+        const bool check = nl->has_list && nl->check_dist;
+        HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], pf->d_force, s->image[s->cur], N,
+                                s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
+                                nl->maxshift(), nl->d_conditions + 3, st));
+        bool flag = false;
+        if (check)
+            {
+            // the one host read per step of the reference's loop (hoomd/md/NeighborListGPU.cc:78-82)
+            HB2_CUDA(cudaMemcpyAsync(nl->h_conditions + 3, nl->d_conditions + 3, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, st));
+            HB2_CUDA(cudaStreamSynchronize(st));
+            flag = nl->h_conditions[3] != 0;
+            }
+        HB2_TRY(pf->compute(t + 1, check, flag));
+        HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, N, (float)it->dt, nullptr, s->d_partial,
+                                s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st));
+        s->timestep = t + 1;
+        }
+    HB2_CUDA(cudaMemcpyAsync(s->d_timestep, &s->timestep, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaEventRecord(it->ev1, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    HB2_CUDA(cudaEventElapsedTime(&it->last_ms, it->ev0, it->ev1));
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic, double* potential,
+                                            double virial6[6])
+    {
+    if (!it || it->forces.empty())
+        return HB2_ERR_INVALID;
+    hb2_system* s = it->sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    double v[7];
+    HB2_TRY(sums7(it->forces[0], v));
+    double ke = 0.0;
+    HB2_TRY(launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket + 2, s->d_sums + 9,
+                           s->stream));
+    HB2_CUDA(cudaMemcpyAsync(&ke, s->d_sums + 9, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    if (kinetic)
+        *kinetic = ke;
+    if (potential)
+        *potential = v[0];
+    if (virial6)
+        for (int q = 0; q < 6; q++)
+            virial6[q] = v[1 + q];
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_last_run_ms(hb2_integrator* it, float* ms)
+    {
+    if (!it || !ms)
+        return HB2_ERR_INVALID;
+    *ms = it->last_ms;
+    return HB2_OK;
+    }

@@ -1,0 +1,217 @@
+// evaluators.cuh — pair evaluators with the interface of the reference's pair_plugin template
+// (example_plugins/pair_plugin/EvaluatorPairExample.h:33-160; canonical doc
+// hoomd/md/EvaluatorPairLJ.h:34-80): nested param_type, ctor (rsq, rcutsq, params),
+// evalForceAndEnergy(force_divr, pair_eng, energy_shift), static getName(). A user evaluator written
+// for the reference compiles against pair_kernel.cuh by adding one .cu that instantiates
+// hb2::pair_dispatch<Evaluator> (see pair_example.cu and INTEGRATION.md).
+//
+// Arithmetic is fp32 (Scalar = float, the HOOMD_LONGREAL_SIZE=32 layout). Host-side `pack` is the
+// param_type(pybind11::dict) constructor restated over a plain array of user parameters.
+#pragma once
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace hb2
+    {
+typedef float Scalar;
+
+// ---------------------------------------------------------------------------------------------
+// Lennard-Jones (hoomd/md/EvaluatorPairLJ.h:95-270)
+// ---------------------------------------------------------------------------------------------
+class EvaluatorPairLJ
+    {
+    public:
+    struct param_type
+        {
+        Scalar lj1; // 4 eps sigma^12
+        Scalar lj2; // 4 eps sigma^6
+        };
+    static constexpr bool needs_thermo = false;
+    static constexpr unsigned n_user_params = 2; // {epsilon, sigma}
+
+    // hoomd/md/EvaluatorPairLJ.h:119-140: sigma_6 = sigma^6, epsilon_x_4 = 4 eps (fp64 on the host)
+    static void pack(const double* user, param_type& p)
+        {
+        const double eps = user[0], sigma = user[1];
+        const double s6 = sigma * sigma * sigma * sigma * sigma * sigma;
+        p.lj1 = (Scalar)(4.0 * eps * s6 * s6);
+        p.lj2 = (Scalar)(4.0 * eps * s6);
+        }
+
+    HB2_DEVICE EvaluatorPairLJ(Scalar _rsq, Scalar _rcutsq, const param_type& _params)
+        : rsq(_rsq), rcutsq(_rcutsq), lj1(_params.lj1), lj2(_params.lj2)
+        {
+        }
+
+    // hoomd/md/EvaluatorPairLJ.h:162-211
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && lj1 != 0)
+            {
+            const Scalar r2inv = __frcp_rn(rsq);
+            const Scalar r6inv = r2inv * r2inv * r2inv;
+            force_divr = r2inv * r6inv * (Scalar(12.0) * lj1 * r6inv - Scalar(6.0) * lj2);
+            pair_eng = r6inv * (lj1 * r6inv - lj2);
+            if (energy_shift)
+                {
+                const Scalar rcut2inv = __frcp_rn(rcutsq);
+                const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+                pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "lj";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, lj1, lj2;
+    };
+
+// ---------------------------------------------------------------------------------------------
+// The pair_plugin example potential V = k/2 (sigma - r)^2
+// (example_plugins/pair_plugin/EvaluatorPairExample.h:94-127)
+// ---------------------------------------------------------------------------------------------
+class EvaluatorPairExample
+    {
+    public:
+    struct param_type
+        {
+        Scalar k;
+        Scalar sigma;
+        };
+    static constexpr bool needs_thermo = false;
+    static constexpr unsigned n_user_params = 2; // {k, sigma}
+    static void pack(const double* user, param_type& p)
+        {
+        p.k = (Scalar)user[0];
+        p.sigma = (Scalar)user[1];
+        }
+    HB2_DEVICE EvaluatorPairExample(Scalar _rsq, Scalar _rcutsq, const param_type& _params)
+        : rsq(_rsq), rcutsq(_rcutsq), k(_params.k), sigma(_params.sigma)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar r = sqrtf(rsq);
+            const Scalar rinv = Scalar(1.0) / r;
+            const Scalar overlap = sigma - r;
+            force_divr = k * overlap * rinv;
+            pair_eng = Scalar(0.5) * k * overlap * overlap;
+            if (energy_shift)
+                {
+                const Scalar rcut = sqrtf(rcutsq);
+                const Scalar cut_overlap = sigma - rcut;
+                pair_eng -= Scalar(0.5) * k * cut_overlap * cut_overlap;
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "example_pair";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, k, sigma;
+    };
+
+// ---------------------------------------------------------------------------------------------
+// DPD (hoomd/md/EvaluatorPairDPDThermoDPD.h:144-277). evalForceAndEnergy is the conservative part
+// (:186-203); evalForceEnergyThermo adds drag and the per-pair Philox random force (:222-277).
+// ---------------------------------------------------------------------------------------------
+class EvaluatorPairDPDThermoDPD
+    {
+    public:
+    struct param_type
+        {
+        Scalar A;
+        Scalar gamma;
+        };
+    static constexpr bool needs_thermo = true;
+    static constexpr unsigned n_user_params = 2; // {A, gamma}
+    static void pack(const double* user, param_type& p)
+        {
+        p.A = (Scalar)user[0];
+        p.gamma = (Scalar)user[1];
+        }
+    HB2_DEVICE EvaluatorPairDPDThermoDPD(Scalar _rsq, Scalar _rcutsq, const param_type& _params)
+        : rsq(_rsq), rcutsq(_rcutsq), a(_params.A), gamma(_params.gamma)
+        {
+        }
+    HB2_DEVICE void set_seed_ij_timestep(uint16_t seed, uint32_t i, uint32_t j, uint64_t timestep)
+        {
+        m_seed = seed;
+        m_i = i;
+        m_j = j;
+        m_timestep = timestep;
+        }
+    HB2_DEVICE void setDeltaT(Scalar dt)
+        {
+        m_deltaT = dt;
+        }
+    HB2_DEVICE void setRDotV(Scalar dot)
+        {
+        m_dot = dot;
+        }
+    HB2_DEVICE void setT(Scalar Temp)
+        {
+        m_T = Temp;
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar rinv = rsqrtf(rsq);
+            const Scalar r = Scalar(1.0) / rinv;
+            const Scalar rcutinv = rsqrtf(rcutsq);
+            const Scalar rcut = Scalar(1.0) / rcutinv;
+            force_divr = a * (rinv - rcutinv);
+            pair_eng = a * (rcut - r) - Scalar(0.5) * a * rcutinv * (rcutsq - rsq);
+            return true;
+            }
+        return false;
+        }
+    HB2_DEVICE bool evalForceEnergyThermo(Scalar& force_divr, Scalar& force_divr_cons,
+                                          Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar rinv = rsqrtf(rsq);
+            const Scalar r = Scalar(1.0) / rinv;
+            const Scalar rcutinv = rsqrtf(rcutsq);
+            const Scalar rcut = Scalar(1.0) / rcutinv;
+            const Scalar w = rinv - rcutinv;
+            // uniform in (-1,1) from the pair's Philox draw; the top 32 bits carry every bit an
+            // fp32 alpha can hold (the fp64 reference uses 64)
+            uint32_t w0, w1;
+            dpd_pair_bits(m_seed, m_i, m_j, m_timestep, w0, w1);
+            const Scalar alpha = fmaf((Scalar)w0, 4.656612873077393e-10f, -1.0f + 2.3283064e-10f);
+            force_divr = a * w;
+            force_divr_cons = force_divr;
+            force_divr -= gamma * m_dot * w * w;
+            force_divr += rsqrtf(m_deltaT / (m_T * gamma * Scalar(6.0))) * w * alpha;
+            pair_eng = a * (rcut - r) - Scalar(0.5) * a * rcutinv * (rcutsq - rsq);
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "dpd";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, a, gamma;
+    uint16_t m_seed;
+    uint32_t m_i, m_j;
+    uint64_t m_timestep;
+    Scalar m_deltaT, m_dot, m_T;
+    };
+    } // namespace hb2

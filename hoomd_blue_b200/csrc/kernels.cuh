@@ -1,0 +1,93 @@
+// kernels.cuh — internal launcher interface shared by the C-ABI layers (capi.cu, engine.cu).
+#pragma once
+#include "common.cuh"
+
+namespace hb2
+    {
+// ---- binning.cu
+size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc);
+hb2_status compute_cell_order(const float4* d_pos, uint32_t N, const hb2_box& box, uint3 dim,
+                              uint32_t* d_order, uint32_t* d_cell_start, uint32_t* d_conditions,
+                              void* d_tmp, size_t tmp_bytes, cudaStream_t stream);
+hb2_status reorder_particles(const uint32_t* d_order, uint32_t N, const float4* pos_in,
+                             const float4* vel_in, const int* img_in, const uint32_t* tag_in,
+                             const float4* force_in, float4* pos_out, float4* vel_out, int* img_out,
+                             uint32_t* tag_out, float4* force_out, uint32_t* rtag,
+                             cudaStream_t stream);
+
+// ---- nlist.cu
+struct NlistBuildArgs
+    {
+    const float4* pos;          // cell-ordered positions, N_local first-class rows
+    uint32_t N;                 // particles that get a row
+    uint3 dim;                  // cell grid
+    const uint32_t* cell_start; // Nc + 1
+    const double* r_listsq;     // ntypes^2 doubles (device), tj*ntypes+ti
+    uint32_t ntypes;
+    double r_listsq_single;     // copy of r_listsq[0] for the one-type fast path
+    double r_list_min;          // smallest positive r_list (sets the fp32 guard band)
+    float Lmax;                 // longest box edge (sets the fp32 guard band)
+    uint32_t* nlist;
+    uint32_t pitch;
+    uint32_t* n_neigh;
+    float4* last_pos;           // may be null
+    uint32_t* conditions;       // [0] <- max n_neigh
+    };
+hb2_status launch_nlist_build(const NlistBuildArgs& a, const hb2_box& box, cudaStream_t stream);
+
+// ---- pair.cu
+struct PairArgs
+    {
+    const float4* pos;
+    const float4* vel;   // DPD only
+    const uint32_t* tag; // DPD only
+    uint32_t N;
+    const uint32_t* n_neigh;
+    const uint32_t* nlist;
+    uint32_t pitch;
+    const float* params; // ntypes^2 x 2 floats (packed by the evaluator's param_type)
+    const float* rcutsq; // ntypes^2
+    const float* ronsq;  // ntypes^2
+    // host copies of entry [0] for the one-type fast path (passed in the constant bank)
+    float params0[2];
+    float rcutsq0, ronsq0;
+    uint32_t ntypes;
+    float4* force;
+    float* virial; // 6 x virial_pitch or null
+    size_t virial_pitch;
+    uint32_t seed;
+    const uint64_t* d_timestep; // device timestep (graph-replay safe) or null -> timestep
+    uint64_t timestep;
+    float dt, kT;
+    uint32_t tpp;
+    };
+hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,
+                              const hb2_box& box, cudaStream_t stream);
+
+// ---- integrate.cu
+hb2_status launch_step_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
+                           const hb2_box& box, float dt, const double* d_rescale,
+                           const float4* last_pos, float maxshift, uint32_t* d_flag,
+                           cudaStream_t stream);
+// d_ke_partial: >= step_two_blocks(N) doubles of scratch; d_ke_out: 1 double (deterministic sum).
+uint32_t step_two_blocks(uint32_t N);
+hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
+                           const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
+                           double* d_ke_out, cudaStream_t stream);
+hb2_status launch_kinetic(const float4* vel, uint32_t N, double* d_partial, uint32_t* d_ticket,
+                          double* d_ke_out, cudaStream_t stream);
+// Bussi factor on device (hoomd/md/Thermostat.h:357-447): *d_rescale <- factor for the step-one of
+// timestep *d_timestep; reads *d_ke.
+hb2_status launch_bussi(const double* d_ke, double dof, double dt, double kT, double tau,
+                        const uint64_t* d_timestep, uint32_t seed, uint32_t first_tag,
+                        double* d_rescale, cudaStream_t stream);
+hb2_status launch_advance_timestep(uint64_t* d_timestep, cudaStream_t stream);
+// sum of force.w (potential energy), deterministic; and 6 virial sums
+hb2_status launch_reduce_energy(const float4* force, const float* virial, size_t virial_pitch,
+                                uint32_t N, double* d_partial, uint32_t* d_ticket, double* d_out7,
+                                cudaStream_t stream);
+uint32_t reduce_blocks(uint32_t N);
+
+double bussi_factor_host(double K, double dof, double dt, double kT, double tau, uint64_t timestep,
+                         uint32_t seed, uint32_t first_tag);
+    } // namespace hb2

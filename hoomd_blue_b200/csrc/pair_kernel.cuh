@@ -1,0 +1,303 @@
+// pair_kernel.cuh — PotentialPair<Evaluator> force / energy / virial pass over a full neighbour list.
+//
+// Replaces PotentialPair<ev>::computeForces (hoomd/md/PotentialPair.h:587-794) and
+// gpu_compute_pair_forces_shared_kernel (hoomd/md/PotentialPairGPU.cuh:146-404), and the DPD
+// variants (hoomd/md/PotentialPairDPDThermo.h:102-268, hoomd/md/PotentialPairDPDThermoGPU.cuh:148-330).
+//
+// TPP lanes share one particle: they stride over its neighbour row (coalesced u32 loads — rows are
+// pitch-aligned and ascending in j, and the particles are in cell order, so the float4 position
+// gathers of adjacent lanes fall into a handful of 128-byte lines), evaluate the pair in fp32,
+// and combine with __shfl_xor. Owner-computes on a full list: no atomics, fixed reduction tree,
+// bitwise reproducible. Each visit adds E/2 and (F/r) dx_a dx_b / 2 to the visiting particle only
+// (hoomd/md/PotentialPairGPU.cuh:365-370, hoomd/md/PotentialPair.h:739-752).
+#pragma once
+#include "common.cuh"
+#include "evaluators.cuh"
+#include "kernels.cuh"
+
+namespace hb2
+    {
+constexpr int PAIR_BLOCK = 128;
+constexpr int PAIR_MAX_TYPES_SMEM = 16; // ntypes^2 <= 256 entries staged in shared memory
+
+template<class Ev> struct PairKArgs
+    {
+    const float4* pos;
+    const float4* vel;
+    const uint32_t* tag;
+    uint32_t N;
+    const uint32_t* n_neigh;
+    const uint32_t* nlist;
+    uint32_t pitch;
+    const typename Ev::param_type* params;
+    const float* rcutsq;
+    const float* ronsq;
+    typename Ev::param_type param0;
+    float rcutsq0, ronsq0;
+    uint32_t ntypes;
+    float4* force;
+    float* virial;
+    size_t virial_pitch;
+    uint32_t seed;
+    const uint64_t* d_timestep;
+    uint64_t timestep;
+    float dt, kT;
+    int energy_shift;
+    BoxF box;
+    };
+
+template<class Ev, bool XPLOR, bool VIRIAL, int TPP, bool ONETYPE>
+__global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<Ev> a)
+    {
+    typedef typename Ev::param_type param_type;
+    __shared__ param_type s_params[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
+    __shared__ float s_rcutsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
+    __shared__ float s_ronsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
+    if (!ONETYPE)
+        {
+        const uint32_t nt2 = a.ntypes * a.ntypes;
+        for (uint32_t t = threadIdx.x; t < nt2; t += blockDim.x)
+            {
+            s_params[t] = a.params[t];
+            s_rcutsq[t] = a.rcutsq[t];
+            s_ronsq[t] = a.ronsq[t];
+            }
+        __syncthreads();
+        }
+
+    const uint32_t gid = blockIdx.x * PAIR_BLOCK + threadIdx.x;
+    const uint32_t i = gid / TPP;
+    const uint32_t sub = gid % TPP;
+    const bool active = i < a.N;
+
+    float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+    float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
+
+    if (active)
+        {
+        const float4 pi = __ldg(a.pos + i);
+        const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
+        const uint32_t n = __ldg(a.n_neigh + i);
+        const uint32_t* __restrict__ row = a.nlist + (size_t)i * a.pitch;
+        const float Lx = a.box.L[0], Ly = a.box.L[1], Lz = a.box.L[2];
+        const float hx = a.box.hi[0], hy = a.box.hi[1], hz = a.box.hi[2];
+
+        float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t tagi = 0;
+        uint64_t timestep = 0;
+        if (Ev::needs_thermo)
+            {
+            vi = __ldg(a.vel + i);
+            tagi = __ldg(a.tag + i);
+            timestep = a.d_timestep ? *a.d_timestep : a.timestep;
+            }
+
+#pragma unroll 2
+        for (uint32_t k = sub; k < n; k += TPP)
+            {
+            const uint32_t j = __ldg(row + k);
+            const float4 pj = __ldg(a.pos + j);
+            const float dx = min_image_f(pi.x - pj.x, Lx, hx);
+            const float dy = min_image_f(pi.y - pj.y, Ly, hy);
+            const float dz = min_image_f(pi.z - pj.z, Lz, hz);
+            const float rsq = dx * dx + dy * dy + dz * dz;
+
+            float rcutsq = a.rcutsq0, ronsq = a.ronsq0;
+            const param_type* prm = &a.param0;
+            if (!ONETYPE)
+                {
+                // Index2D(ntypes)(ti, tj) = tj * ntypes + ti (hoomd/Index1D.h:53)
+                const uint32_t tp = __float_as_uint(pj.w) * a.ntypes + ti;
+                rcutsq = s_rcutsq[tp];
+                ronsq = s_ronsq[tp];
+                prm = &s_params[tp];
+                }
+            bool energy_shift = a.energy_shift != 0;
+            if (XPLOR)
+                energy_shift = ronsq > rcutsq; // hoomd/md/PotentialPair.h:697-700
+
+            float force_divr = 0.f, force_divr_cons = 0.f, pair_eng = 0.f;
+            Ev eval(rsq, rcutsq, *prm);
+            bool evaluated;
+            if constexpr (Ev::needs_thermo)
+                {
+                const float4 vj = __ldg(a.vel + j);
+                const uint32_t tagj = __ldg(a.tag + j);
+                const float rdotv = dx * (vi.x - vj.x) + dy * (vi.y - vj.y) + dz * (vi.z - vj.z);
+                eval.set_seed_ij_timestep((uint16_t)a.seed, tagi, tagj, timestep);
+                eval.setDeltaT(a.dt);
+                eval.setRDotV(rdotv);
+                eval.setT(a.kT);
+                evaluated = eval.evalForceEnergyThermo(force_divr, force_divr_cons, pair_eng,
+                                                       energy_shift);
+                }
+            else
+                {
+                evaluated = eval.evalForceAndEnergy(force_divr, pair_eng, energy_shift);
+                force_divr_cons = force_divr;
+                }
+            if (evaluated)
+                {
+                if (XPLOR)
+                    {
+                    // hoomd/md/PotentialPair.h:711-737
+                    if (rsq >= ronsq && rsq < rcutsq)
+                        {
+                        const float old_eng = pair_eng, old_f = force_divr;
+                        const float d = rcutsq - ronsq;
+                        const float denom_inv = 1.0f / (d * d * d);
+                        const float m = rsq - rcutsq;
+                        const float s = m * m * (rcutsq + 2.0f * rsq - 3.0f * ronsq) * denom_inv;
+                        const float ds = 12.0f * (rsq - ronsq) * m * denom_inv;
+                        pair_eng = old_eng * s;
+                        force_divr = s * old_f - ds * old_eng;
+                        force_divr_cons = force_divr;
+                        }
+                    }
+                fx += dx * force_divr;
+                fy += dy * force_divr;
+                fz += dz * force_divr;
+                pe += pair_eng * 0.5f;
+                if (VIRIAL)
+                    {
+                    const float f2 = 0.5f * force_divr_cons;
+                    vxx += f2 * dx * dx;
+                    vxy += f2 * dx * dy;
+                    vxz += f2 * dx * dz;
+                    vyy += f2 * dy * dy;
+                    vyz += f2 * dy * dz;
+                    vzz += f2 * dz * dz;
+                    }
+                }
+            }
+        }
+
+    // combine the TPP lanes of a particle (fixed butterfly -> reproducible)
+#pragma unroll
+    for (int off = TPP >> 1; off > 0; off >>= 1)
+        {
+        fx += __shfl_xor_sync(0xffffffffu, fx, off);
+        fy += __shfl_xor_sync(0xffffffffu, fy, off);
+        fz += __shfl_xor_sync(0xffffffffu, fz, off);
+        pe += __shfl_xor_sync(0xffffffffu, pe, off);
+        if (VIRIAL)
+            {
+            vxx += __shfl_xor_sync(0xffffffffu, vxx, off);
+            vxy += __shfl_xor_sync(0xffffffffu, vxy, off);
+            vxz += __shfl_xor_sync(0xffffffffu, vxz, off);
+            vyy += __shfl_xor_sync(0xffffffffu, vyy, off);
+            vyz += __shfl_xor_sync(0xffffffffu, vyz, off);
+            vzz += __shfl_xor_sync(0xffffffffu, vzz, off);
+            }
+        }
+    if (active && sub == 0)
+        {
+        a.force[i] = make_float4(fx, fy, fz, pe);
+        if (VIRIAL)
+            {
+            a.virial[0 * a.virial_pitch + i] = vxx;
+            a.virial[1 * a.virial_pitch + i] = vxy;
+            a.virial[2 * a.virial_pitch + i] = vxz;
+            a.virial[3 * a.virial_pitch + i] = vyy;
+            a.virial[4 * a.virial_pitch + i] = vyz;
+            a.virial[5 * a.virial_pitch + i] = vzz;
+            }
+        }
+    }
+
+template<class Ev, bool XPLOR, bool VIRIAL, int TPP>
+hb2_status pair_launch_tpp(const PairKArgs<Ev>& k, cudaStream_t stream)
+    {
+    const uint64_t threads = (uint64_t)k.N * TPP;
+    const uint32_t blocks = (uint32_t)((threads + PAIR_BLOCK - 1) / PAIR_BLOCK);
+    if (k.ntypes == 1)
+        pair_force_kernel<Ev, XPLOR, VIRIAL, TPP, true><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
+    else
+        pair_force_kernel<Ev, XPLOR, VIRIAL, TPP, false><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
+    HB2_CHECK_LAUNCH("pair_force_kernel");
+    return HB2_OK;
+    }
+
+template<class Ev, bool XPLOR, bool VIRIAL>
+hb2_status pair_launch(const PairKArgs<Ev>& k, uint32_t tpp, cudaStream_t stream)
+    {
+    switch (tpp)
+        {
+    case 1:
+        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 1>(k, stream);
+    case 2:
+        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 2>(k, stream);
+    case 4:
+        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 4>(k, stream);
+    case 8:
+        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 8>(k, stream);
+    case 16:
+        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 16>(k, stream);
+    case 32:
+        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 32>(k, stream);
+    default:
+        set_error("threads_per_particle must be a power of two in [1, 32]");
+        return HB2_ERR_INVALID;
+        }
+    }
+
+// The one entry point an evaluator's .cu instantiates (the counterpart of the reference's
+// `template hipError_t gpu_compute_pair_forces<Evaluator>(...)`,
+// example_plugins/pair_plugin/PotentialPairExampleGPUKernel.cu:13-15).
+template<class Ev>
+hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& box,
+                         cudaStream_t stream)
+    {
+    static_assert(sizeof(typename Ev::param_type) == 2 * sizeof(float),
+                  "packed param_type is two floats on this ABI");
+    if (a.N == 0)
+        return HB2_OK;
+    if (a.ntypes > PAIR_MAX_TYPES_SMEM)
+        {
+        set_error("pair forces: at most 16 particle types are supported");
+        return HB2_ERR_INVALID;
+        }
+    PairKArgs<Ev> k;
+    k.pos = a.pos;
+    k.vel = a.vel;
+    k.tag = a.tag;
+    k.N = a.N;
+    k.n_neigh = a.n_neigh;
+    k.nlist = a.nlist;
+    k.pitch = a.pitch;
+    k.params = reinterpret_cast<const typename Ev::param_type*>(a.params);
+    k.rcutsq = a.rcutsq;
+    k.ronsq = a.ronsq;
+    memcpy(&k.param0, a.params0, sizeof(k.param0));
+    k.rcutsq0 = a.rcutsq0;
+    k.ronsq0 = a.ronsq0;
+    k.ntypes = a.ntypes;
+    k.force = a.force;
+    k.virial = a.virial;
+    k.virial_pitch = a.virial_pitch;
+    k.seed = a.seed;
+    k.d_timestep = a.d_timestep;
+    k.timestep = a.timestep;
+    k.dt = a.dt;
+    k.kT = a.kT;
+    k.energy_shift = (mode == HB2_SHIFT_SHIFT);
+    k.box = boxf(box);
+    if (Ev::needs_thermo && (!a.vel || !a.tag))
+        {
+        set_error("pair forces: this evaluator needs velocities and tags");
+        return HB2_ERR_INVALID;
+        }
+    const bool virial = a.virial != nullptr;
+    if (mode == HB2_SHIFT_XPLOR)
+        return virial ? pair_launch<Ev, true, true>(k, a.tpp, stream)
+                      : pair_launch<Ev, true, false>(k, a.tpp, stream);
+    return virial ? pair_launch<Ev, false, true>(k, a.tpp, stream)
+                  : pair_launch<Ev, false, false>(k, a.tpp, stream);
+    }
+
+// per-evaluator translation units
+hb2_status pair_forces_lj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_dpd(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_example(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_dpd_conservative(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+    } // namespace hb2

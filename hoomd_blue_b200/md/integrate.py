@@ -1,0 +1,65 @@
+"""hoomd.md.Integrator for this path (hoomd/md/integrate.py:128-293)."""
+import ctypes as C
+
+from .. import _lib
+from .._lib import check
+from .methods import ConstantVolume, Bussi
+
+
+class Integrator:
+    """hoomd.md.Integrator(dt, forces=[pair], methods=[ConstantVolume(...)]). Constraints, rigid
+    bodies, half-step hooks and integrate_rotational_dof are outside this path."""
+
+    def __init__(self, dt, integrate_rotational_dof=False, forces=None, constraints=None,
+                 methods=None, rigid=None, half_step_hook=None):
+        if integrate_rotational_dof or constraints or rigid or half_step_hook:
+            raise NotImplementedError("only translational ConstantVolume integration is on this path")
+        self.dt = float(dt)
+        self.forces = list(forces or [])
+        self.methods = list(methods or [])
+        self._h = None
+        self._sim = None
+
+    def _attach(self, sim):
+        if self._h is not None:
+            return
+        if len(self.forces) != 1:
+            raise NotImplementedError("this path carries exactly one pair force")
+        if len(self.methods) != 1 or not isinstance(self.methods[0], ConstantVolume):
+            raise NotImplementedError("this path integrates with one ConstantVolume method")
+        L = _lib.lib()
+        h = C.c_void_p()
+        check(L.hb2_integrator_create(C.byref(h), sim.state._h, self.dt))
+        self._h = h
+        self._sim = sim
+        f = self.forces[0]
+        f._attach(sim)
+        check(L.hb2_integrator_add_force(h, f._h))
+        th = self.methods[0].thermostat
+        if isinstance(th, Bussi):
+            check(L.hb2_integrator_set_constant_volume(h, 1, th.kT, th.tau))
+        else:
+            check(L.hb2_integrator_set_constant_volume(h, 0, 0.0, 0.0))
+
+    def _detach(self):
+        if self._h is not None:
+            _lib.lib().hb2_integrator_destroy(self._h)
+            self._h = None
+        for f in self.forces:
+            f._detach()
+            f.nlist._detach()
+
+    def _run(self, steps):
+        check(_lib.lib().hb2_integrator_run(self._h, steps))
+
+    def _last_run_ms(self):
+        ms = C.c_float(0)
+        check(_lib.lib().hb2_integrator_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def _thermo(self):
+        ke = C.c_double(0)
+        pe = C.c_double(0)
+        v = (C.c_double * 6)()
+        check(_lib.lib().hb2_integrator_thermo(self._h, C.byref(ke), C.byref(pe), v))
+        return ke.value, pe.value, list(v)

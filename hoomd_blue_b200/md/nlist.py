@@ -1,0 +1,102 @@
+"""hoomd.md.nlist for this path (hoomd/md/nlist.py:87-418): Cell."""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import check, ptr
+
+
+class NeighborList:
+    """Base class (hoomd/md/nlist.py:87-323)."""
+
+    def __init__(self, buffer, exclusions, rebuild_check_delay, check_dist, mesh, default_r_cut):
+        if exclusions not in ((), None) and tuple(exclusions) != ("bond",):
+            raise NotImplementedError("exclusions other than the default are outside this path")
+        if mesh is not None:
+            raise NotImplementedError("mesh neighbour lists are outside this path")
+        self.buffer = float(buffer)
+        self.exclusions = tuple(exclusions or ())
+        self.rebuild_check_delay = int(rebuild_check_delay)
+        self.check_dist = bool(check_dist)
+        self.default_r_cut = float(default_r_cut)
+        self._h = None
+        self._sim = None
+
+    @property
+    def _attached(self):
+        return self._h is not None
+
+    def _attach(self, sim):
+        if self._h is not None:
+            if self._sim is not sim:
+                raise RuntimeError("nlist is attached to another simulation")
+            return
+        h = C.c_void_p()
+        check(_lib.lib().hb2_nlist_create(C.byref(h), sim.state._h, self.buffer,
+                                          self.rebuild_check_delay, int(self.check_dist)))
+        self._h = h
+        self._sim = sim
+
+    def _detach(self):
+        if self._h is not None:
+            _lib.lib().hb2_nlist_destroy(self._h)
+            self._h = None
+            self._sim = None
+
+    def _need(self):
+        if self._h is None:
+            raise RuntimeError("nlist is not attached (run the simulation first)")  # DataAccessError
+
+    @property
+    def pair_list(self):
+        """(n, 2) uint32 tag pairs, each unordered pair once (hoomd/md/nlist.py:293-305)."""
+        self._need()
+        L = _lib.lib()
+        n = C.c_uint64(0)
+        check(L.hb2_nlist_pair_count(self._h, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 2), dtype=np.uint32)
+        check(L.hb2_nlist_pair_list(self._h, ptr(out, C.c_uint32), out.shape[0], C.byref(n)))
+        return out[:n.value]
+
+    local_pair_list = pair_list
+
+    @property
+    def num_builds(self):
+        self._need()
+        return int(_lib.lib().hb2_nlist_num_builds(self._h))
+
+    @property
+    def shortest_rebuild(self):
+        self._need()
+        return int(_lib.lib().hb2_nlist_shortest_rebuild(self._h))
+
+    def _stats(self):
+        self._need()
+        mean = C.c_double(0)
+        mx = C.c_uint32(0)
+        pitch = C.c_uint32(0)
+        check(_lib.lib().hb2_nlist_stats(self._h, C.byref(mean), C.byref(mx), C.byref(pitch)))
+        return dict(mean_neighbors=mean.value, max_neighbors=mx.value, pitch=pitch.value)
+
+
+class Cell(NeighborList):
+    """hoomd.md.nlist.Cell (hoomd/md/nlist.py:326-418). `deterministic` is accepted and always
+    honoured: binning is a key sort and rows are written in ascending particle index."""
+
+    def __init__(self, buffer, exclusions=("bond",), rebuild_check_delay=1, check_dist=True,
+                 deterministic=False, mesh=None, default_r_cut=0.0):
+        super().__init__(buffer, exclusions, rebuild_check_delay, check_dist, mesh, default_r_cut)
+        self.deterministic = bool(deterministic)
+
+    @property
+    def dimensions(self):
+        self._need()
+        d = (C.c_uint32 * 3)()
+        check(_lib.lib().hb2_nlist_dimensions(self._h, d))
+        return tuple(int(x) for x in d)
+
+    @property
+    def allocated_particles_per_cell(self):
+        # the cell list is an offset table into the cell-ordered particle arrays: nothing is padded
+        return 0

@@ -1,0 +1,196 @@
+"""hoomd.md.pair for this path (hoomd/md/pair/pair.py): Pair base, LJ, DPD, DPDConservative and the
+pair_plugin example potential (example_plugins/pair_plugin/pair.py)."""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import check, ptr
+from .typeparam import TypePairDict
+
+
+def _nonneg(v):
+    v = float(v)
+    if v < 0:
+        raise ValueError("expected a non-negative real")
+    return v
+
+
+class Force:
+    """hoomd.md.force.Force properties (hoomd/md/force.py:77-156), tag-ordered."""
+
+    _h = None
+    _sim = None
+
+    def _need(self):
+        if self._h is None:
+            raise RuntimeError("force is not attached (run the simulation first)")
+
+    @property
+    def forces(self):
+        self._need()
+        out = np.zeros((self._sim.state.N_particles, 3), dtype=np.float64)
+        check(_lib.lib().hb2_pair_get_forces(self._h, ptr(out, C.c_double)))
+        return out
+
+    @property
+    def energies(self):
+        self._need()
+        out = np.zeros(self._sim.state.N_particles, dtype=np.float64)
+        check(_lib.lib().hb2_pair_get_energies(self._h, ptr(out, C.c_double)))
+        return out
+
+    @property
+    def virials(self):
+        """(N, 6) or None when the pressure flag is off (hoomd/ForceCompute.cc:491-496)."""
+        self._need()
+        if not self._sim.always_compute_pressure:
+            return None
+        out = np.zeros((self._sim.state.N_particles, 6), dtype=np.float64)
+        check(_lib.lib().hb2_pair_get_virials(self._h, ptr(out, C.c_double)))
+        return out
+
+    @property
+    def energy(self):
+        self._need()
+        e = C.c_double(0)
+        check(_lib.lib().hb2_pair_get_energy(self._h, C.byref(e)))
+        return e.value
+
+    @property
+    def additional_energy(self):
+        self._need()
+        e = C.c_double(0)
+        v = (C.c_double * 6)()
+        check(_lib.lib().hb2_pair_get_additional(self._h, C.byref(e), v))
+        return e.value
+
+    @property
+    def additional_virial(self):
+        self._need()
+        e = C.c_double(0)
+        v = (C.c_double * 6)()
+        check(_lib.lib().hb2_pair_get_additional(self._h, C.byref(e), v))
+        return np.array(list(v))
+
+
+class Pair(Force):
+    """hoomd.md.pair.Pair(nlist, default_r_cut=None, default_r_on=0., mode='none')."""
+
+    _accepted_modes = ("none", "shift", "xplor")
+    _evaluator = None  # name in _lib.EVAL
+    _param_keys = ()
+
+    def __init__(self, nlist, default_r_cut=None, default_r_on=0.0, mode="none"):
+        if mode not in self._accepted_modes:
+            raise ValueError(f"mode must be one of {self._accepted_modes}")
+        self.nlist = nlist
+        self.mode = mode
+        self.r_cut = TypePairDict("r_cut", _nonneg, None if default_r_cut is None else default_r_cut)
+        self.r_on = TypePairDict("r_on", _nonneg, default_r_on)
+        self.params = TypePairDict("params", self._validate_params)
+        self.r_cut._on_change = self.r_on._on_change = self.params._on_change = self._sync
+        self._tpp = None
+
+    def _validate_params(self, v):
+        missing = [k for k in self._param_keys if k not in v]
+        if missing:
+            raise ValueError(f"missing parameters {missing}")
+        return {k: float(v[k]) for k in self._param_keys}
+
+    # --- attach: create the C++ object and push every type-pair parameter
+    # (hoomd/md/pair/pair.py:126-144)
+    def _attach(self, sim):
+        if self._h is not None:
+            return
+        self.nlist._attach(sim)
+        h = C.c_void_p()
+        check(_lib.lib().hb2_pair_create(C.byref(h), sim.state._h, self.nlist._h,
+                                         _lib.EVAL[self._evaluator], _lib.SHIFT[self.mode]))
+        self._h = h
+        self._sim = sim
+        self._sync()
+        self._attach_extra()
+
+    def _attach_extra(self):
+        pass
+
+    def _detach(self):
+        if self._h is not None:
+            _lib.lib().hb2_pair_destroy(self._h)
+            self._h = None
+            self._sim = None
+
+    def _sync(self):
+        if self._h is None:
+            return
+        L = _lib.lib()
+        types = self._sim.state.particle_types
+        for i, a in enumerate(types):
+            for j, b in enumerate(types):
+                if j < i:
+                    continue
+                p = self.params[(a, b)]
+                arr = (C.c_double * len(self._param_keys))(*[p[k] for k in self._param_keys])
+                check(L.hb2_pair_set_params(self._h, i, j, arr, len(self._param_keys)))
+                check(L.hb2_pair_set_r_cut(self._h, i, j, self.r_cut[(a, b)]))
+                check(L.hb2_pair_set_r_on(self._h, i, j, self.r_on[(a, b)]))
+        if self._tpp:
+            check(L.hb2_pair_set_threads_per_particle(self._h, self._tpp))
+
+    @property
+    def kernel_parameters(self):
+        """Autotuner knob of the reference (block size, threads per particle); here tpp only."""
+        return {"threads_per_particle": self._tpp or 8}
+
+    def set_threads_per_particle(self, tpp):
+        self._tpp = int(tpp)
+        if self._h is not None:
+            check(_lib.lib().hb2_pair_set_threads_per_particle(self._h, self._tpp))
+
+
+class LJ(Pair):
+    """hoomd.md.pair.LJ(nlist, default_r_cut=None, default_r_on=0., mode='none',
+    tail_correction=False); params {epsilon, sigma} (hoomd/md/pair/pair.py:163-260)."""
+    _evaluator = "lj"
+    _param_keys = ("epsilon", "sigma")
+
+    def __init__(self, nlist, default_r_cut=None, default_r_on=0.0, mode="none",
+                 tail_correction=False):
+        super().__init__(nlist, default_r_cut, default_r_on, mode)
+        self.tail_correction = bool(tail_correction)
+
+    def _attach_extra(self):
+        check(_lib.lib().hb2_pair_set_tail_correction(self._h, int(self.tail_correction)))
+
+
+class DPD(Pair):
+    """hoomd.md.pair.DPD(nlist, kT, default_r_cut=None); params {A, gamma}
+    (hoomd/md/pair/pair.py:676-779). mode is fixed to 'none'."""
+    _accepted_modes = ("none",)
+    _evaluator = "dpd"
+    _param_keys = ("A", "gamma")
+
+    def __init__(self, nlist, kT, default_r_cut=None):
+        super().__init__(nlist, default_r_cut, 0.0, "none")
+        self.kT = float(kT)
+
+    def _attach_extra(self):
+        check(_lib.lib().hb2_pair_set_kT(self._h, self.kT))
+
+
+class DPDConservative(Pair):
+    """hoomd.md.pair.DPDConservative(nlist, default_r_cut=None); params {A}."""
+    _accepted_modes = ("none",)
+    _evaluator = "dpd_conservative"
+    _param_keys = ("A",)
+
+    def __init__(self, nlist, default_r_cut=None):
+        super().__init__(nlist, default_r_cut, 0.0, "none")
+
+
+class ExamplePair(Pair):
+    """The pair_plugin potential (example_plugins/pair_plugin/pair.py): params {k, sigma},
+    modes none/shift/xplor."""
+    _evaluator = "example_pair"
+    _param_keys = ("k", "sigma")

@@ -1,0 +1,244 @@
+"""Simulation / State / Snapshot / Operations for the pair-force path.
+
+Mirrors hoomd/simulation.py:33-562 (Simulation: create_state_from_snapshot / _gsd, run, timestep,
+tps, walltime, always_compute_pressure), hoomd/snapshot.py (Snapshot.configuration / .particles),
+hoomd/state.py (State.get_snapshot, N_particles, box, particle_types) and hoomd/operations.py
+(Operations.integrator) — only the members a pair-force simulation touches.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+
+class _Configuration:
+
+    def __init__(self):
+        self.box = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]  # Lx, Ly, Lz, xy, xz, yz
+        self.dimensions = 3
+        self.step = 0
+
+
+class _Particles:
+    """hoomd.Snapshot.particles: setting N (re)allocates zeroed arrays (hoomd/snapshot.py)."""
+
+    def __init__(self):
+        self.types = ["A"]
+        self._N = 0
+        self._alloc(0)
+
+    def _alloc(self, n):
+        self.position = np.zeros((n, 3), dtype=np.float32)
+        self.velocity = np.zeros((n, 3), dtype=np.float32)
+        self.image = np.zeros((n, 3), dtype=np.int32)
+        self.typeid = np.zeros(n, dtype=np.uint32)
+        self.mass = np.ones(n, dtype=np.float32)
+
+    @property
+    def N(self):
+        return self._N
+
+    @N.setter
+    def N(self, n):
+        self._N = int(n)
+        self._alloc(self._N)
+
+
+class Snapshot:
+
+    def __init__(self, communicator=None):
+        self.configuration = _Configuration()
+        self.particles = _Particles()
+        self.communicator = communicator
+
+    @classmethod
+    def from_arrays(cls, box, position, velocity=None, typeid=None, types=("A",), image=None,
+                    mass=None):
+        s = cls()
+        L = list(np.asarray(box, dtype=np.float64).reshape(-1))
+        s.configuration.box = (L + [0.0] * 6)[:6] if len(L) >= 3 else [L[0]] * 3 + [0.0] * 3
+        n = len(position)
+        s.particles.N = n
+        s.particles.types = list(types)
+        s.particles.position[:] = position
+        if velocity is not None:
+            s.particles.velocity[:] = velocity
+        if typeid is not None:
+            s.particles.typeid[:] = typeid
+        if image is not None:
+            s.particles.image[:] = image
+        if mass is not None:
+            s.particles.mass[:] = mass
+        return s
+
+
+class _BoxView:
+
+    def __init__(self, box6):
+        self.Lx, self.Ly, self.Lz, self.xy, self.xz, self.yz = [float(v) for v in box6]
+
+    @property
+    def L(self):
+        return np.array([self.Lx, self.Ly, self.Lz])
+
+    @property
+    def volume(self):
+        return self.Lx * self.Ly * self.Lz
+
+
+class State:
+    """Particle state resident in HBM (hb2_system)."""
+
+    def __init__(self, simulation, snapshot):
+        L = _lib.lib()
+        self._simulation = simulation
+        self._types = list(snapshot.particles.types)
+        self._box = [float(v) for v in snapshot.configuration.box]
+        h = C.c_void_p()
+        check(L.hb2_system_create(C.byref(h), simulation.device.gpu_id, len(self._types),
+                                  simulation.seed & 0xFFFF))
+        self._h = h
+        check(L.hb2_system_set_box(h, *self._box))
+        self.set_snapshot(snapshot)
+
+    def set_snapshot(self, snapshot):
+        L = _lib.lib()
+        p = snapshot.particles
+        pos = np.ascontiguousarray(p.position, dtype=np.float32)
+        vel = np.ascontiguousarray(p.velocity, dtype=np.float32)
+        mass = np.ascontiguousarray(p.mass, dtype=np.float32)
+        tid = np.ascontiguousarray(p.typeid, dtype=np.uint32)
+        img = np.ascontiguousarray(p.image, dtype=np.int32)
+        check(L.hb2_system_set_particles(self._h, pos.shape[0], ptr(pos, C.c_float),
+                                         ptr(vel, C.c_float), ptr(mass, C.c_float),
+                                         ptr(tid, C.c_uint32), ptr(img, C.c_int32)))
+
+    def get_snapshot(self):
+        L = _lib.lib()
+        n = self.N_particles
+        s = Snapshot()
+        s.configuration.box = list(self._box)
+        s.particles.N = n
+        s.particles.types = list(self._types)
+        p = s.particles
+        check(L.hb2_system_get_particles(self._h, ptr(p.position, C.c_float),
+                                         ptr(p.velocity, C.c_float), ptr(p.mass, C.c_float),
+                                         ptr(p.typeid, C.c_uint32), ptr(p.image, C.c_int32)))
+        return s
+
+    @property
+    def N_particles(self):
+        return int(_lib.lib().hb2_system_n(self._h))
+
+    @property
+    def particle_types(self):
+        return list(self._types)
+
+    @property
+    def box(self):
+        return _BoxView(self._box)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().hb2_system_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Operations:
+    """hoomd.Operations restricted to `integrator` (hoomd/operations.py:32)."""
+
+    def __init__(self, simulation):
+        self._simulation = simulation
+        self._integrator = None
+
+    @property
+    def integrator(self):
+        return self._integrator
+
+    @integrator.setter
+    def integrator(self, op):
+        if self._integrator is not None and self._integrator is not op:
+            self._integrator._detach()
+        self._integrator = op
+
+
+class Simulation:
+
+    def __init__(self, device, seed=None):
+        from .device import GPU
+        if not isinstance(device, GPU):
+            raise TypeError("device must be hoomd_blue_b200.device.GPU")
+        self.device = device
+        self.seed = 0 if seed is None else int(seed)
+        self.state = None
+        self.operations = Operations(self)
+        self._always_compute_pressure = False
+        self._initial_timestep = 0
+        self._tps = 0.0
+        self._walltime = 0.0
+        self._last_device_ms = 0.0
+
+    # --- state creation (hoomd/simulation.py:188-301)
+    def create_state_from_snapshot(self, snapshot, domain_decomposition=(None, None, None)):
+        if self.state is not None:
+            raise RuntimeError("Cannot initialize more than once\n")
+        self.state = State(self, snapshot)
+        check(_lib.lib().hb2_system_set_timestep(self.state._h, self._initial_timestep))
+        if self._always_compute_pressure:
+            check(_lib.lib().hb2_system_set_compute_virial(self.state._h, 1))
+
+    def create_state_from_gsd(self, filename, frame=-1, domain_decomposition=(None, None, None)):
+        from . import gsd_io
+        snap, step = gsd_io.read_frame(filename, frame)
+        if self.state is None and self._initial_timestep == 0:
+            self._initial_timestep = step
+        self.create_state_from_snapshot(snap)
+
+    @property
+    def timestep(self):
+        if self.state is None:
+            return self._initial_timestep
+        return int(_lib.lib().hb2_system_timestep(self.state._h))
+
+    @timestep.setter
+    def timestep(self, step):
+        if self.state is not None:
+            raise RuntimeError("State must not be set to change timestep.")  # simulation.py:99-105
+        self._initial_timestep = int(step)
+
+    @property
+    def always_compute_pressure(self):
+        return self._always_compute_pressure
+
+    @always_compute_pressure.setter
+    def always_compute_pressure(self, value):
+        self._always_compute_pressure = bool(value)
+        if self.state is not None:
+            check(_lib.lib().hb2_system_set_compute_virial(self.state._h, int(bool(value))))
+
+    @property
+    def tps(self):
+        return self._tps
+
+    @property
+    def walltime(self):
+        return self._walltime
+
+    def run(self, steps, write_at_start=False):
+        if self.state is None:
+            raise RuntimeError("Cannot run before state is set.")
+        integ = self.operations.integrator
+        if integ is None:
+            raise RuntimeError("No integrator is set")
+        integ._attach(self)
+        t0 = time.perf_counter()
+        integ._run(int(steps))
+        self._walltime = time.perf_counter() - t0
+        self._tps = steps / self._walltime if self._walltime > 0 else 0.0
+        self._last_device_ms = integ._last_run_ms()

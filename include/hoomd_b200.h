@@ -1,0 +1,250 @@
+/* hoomd_b200.h — C ABI of the B200-native short-range MD pair-force step.
+ *
+ * This is the drop-in boundary for the path BASELINE.json:north_star names: cell binning ->
+ * neighbour-list build -> PotentialPair<Evaluator> force/energy/virial -> ConstantVolume half steps.
+ * Plain pointers and sizes only; no C++/torch types cross this boundary; no exceptions either: every
+ * entry point returns an hb2_status and hb2_last_error() holds the message for the calling thread.
+ *
+ * Two layers:
+ *   (1) hb2_gpu_*      stateless kernel drivers over caller-owned DEVICE arrays. They replace the
+ *                      reference's GPU driver functions one for one (cited per function) and are what
+ *                      a HOOMD `...GPU` class would call from computeForces/buildNlist/integrateStep*.
+ *   (2) hb2_system_* … opaque-handle engine over HOST buffers (ParticleData + NeighborList +
+ *                      ForceCompute + IntegratorTwoStep in one place, state resident in HBM). The
+ *                      Python operator surface (hoomd_blue_b200/) binds this layer with ctypes.
+ *
+ * Citations are to /root/reference (HOOMD-blue v4.8.2) file:line.
+ * Precision contract: particle state is fp32 (HOOMD_LONGREAL_SIZE=32 layout: Scalar4 = float4),
+ * neighbour-list membership is decided in fp64 with the CPU build's operation order (bit-exact pair
+ * set), per-particle sums are fp32, global sums fp64.
+ * Scope: 3D orthorhombic periodic boxes (tilt factors must be 0).
+ */
+#ifndef HOOMD_B200_H
+#define HOOMD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define HB2_ABI_VERSION 1
+
+typedef enum
+    {
+    HB2_OK = 0,
+    HB2_ERR_INVALID = 1,        /* bad argument / wrong state (std::invalid_argument in the reference) */
+    HB2_ERR_CUDA = 2,           /* CUDA runtime error (CHECK_CUDA_ERROR, hoomd/md/PotentialPairGPU.h:163) */
+    HB2_ERR_NAN_POSITION = 3,   /* hoomd/CellList.cc:575-590 "Particle with unique tag ... has NaN" */
+    HB2_ERR_OUT_OF_BOX = 4,     /* hoomd/CellList.cc:592-604 "is no longer in the simulation box" */
+    HB2_ERR_BOX_TOO_SMALL = 5,  /* hoomd/md/NeighborList.cc:544-560 "box too small for r_cut+buffer" */
+    HB2_ERR_NLIST_OVERFLOW = 6, /* hoomd/md/NeighborList.cc:1601-1617 (reference regrows; see below) */
+    HB2_ERR_NO_DEVICE = 7,      /* no CUDA device: there is NO CPU fallback in this library */
+    HB2_ERR_COMM = 8            /* NCCL error on the domain-decomposed path */
+    } hb2_status;
+
+const char* hb2_last_error(void);
+int hb2_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t hb2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ *
+ * POD box (replaces BoxDim in kernel signatures; hoomd/BoxDim.h:183-200: hi = L/2, lo = -hi).
+ * The fp64 copy feeds the bit-exact membership test and the binning, the fp32 copy the hot loops.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct
+    {
+    double L[3], lo[3], hi[3], Linv[3];
+    float Lf[3], lof[3], hif[3], Linvf[3];
+    int32_t periodic[3];
+    int32_t _pad;
+    } hb2_box;
+
+hb2_status hb2_box_make(hb2_box* box, double Lx, double Ly, double Lz);
+
+/* Evaluators compiled into the library (the pair_plugin template adds more, see
+ * hoomd_blue_b200/csrc/evaluators.cuh and INTEGRATION.md). */
+typedef enum
+    {
+    HB2_EVAL_LJ = 0,  /* hoomd/md/EvaluatorPairLJ.h:95-270; params {epsilon, sigma} */
+    HB2_EVAL_DPD = 1, /* hoomd/md/EvaluatorPairDPDThermoDPD.h:144-277; params {A, gamma} (+kT, seed) */
+    HB2_EVAL_DPD_CONSERVATIVE = 2, /* same header :186-203; params {A} */
+    HB2_EVAL_EXAMPLE = 3 /* example_plugins/pair_plugin/EvaluatorPairExample.h; params {k, sigma} */
+    } hb2_evaluator;
+
+/* hoomd/md/PotentialPair.h:104-109 */
+typedef enum
+    {
+    HB2_SHIFT_NONE = 0,
+    HB2_SHIFT_SHIFT = 1,
+    HB2_SHIFT_XPLOR = 2
+    } hb2_shift_mode;
+
+/* ========================================================================================== *
+ * Layer 1: stateless kernel drivers (device pointers, caller's stream).
+ * `stream` is a cudaStream_t passed as void*.
+ * ========================================================================================== */
+
+/* Replaces gpu_compute_cell_list (hoomd/CellListGPU.cu:173-194) + the deterministic sort pass
+ * (:439-565). Bins N particles with the reference's rule (hoomd/CellList.cc:455-470, fp64
+ * makeFraction hoomd/BoxDim.h:276-284) on a dim[0] x dim[1] x dim[2] grid, then key-sorts (cell,
+ * index) — no atomics, order is deterministic. Outputs: order[k] = old index of the k-th particle in
+ * cell order, cell_start[Nc+1] = first sorted slot of each cell. conditions[3] = {0, nan idx+1,
+ * out-of-box idx+1} as hoomd/CellList.cc:549-607. tmp/tmp_bytes: scratch; call with tmp = NULL to
+ * get the size. */
+hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N, const hb2_box* box,
+                                      const uint32_t dim[3], uint32_t* d_order,
+                                      uint32_t* d_cell_start, uint32_t* d_conditions, void* d_tmp,
+                                      size_t* tmp_bytes, void* stream);
+
+/* Replaces gpu_compute_nlist_binned (hoomd/md/NeighborListGPUBinned.cu:756-824) for particles that
+ * are already in cell order (d_pos4 sorted so that cell c owns [cell_start[c], cell_start[c+1])).
+ * Membership rule hoomd/md/NeighborListBinned.cc:144-157: j != i, r_cut(ti,tj) > 0,
+ * |minImage(pi - pj)|^2 <= (r_cut(ti,tj) + r_buff)^2 decided in fp64. Full list, row i at
+ * d_nlist[i * pitch], ascending j. d_r_listsq: ntypes^2 doubles indexed tj*ntypes+ti
+ * (hoomd/md/NeighborList.cc:505-506). d_conditions[0] receives max(n_neigh) (overflow if > pitch).
+ * Also writes d_last_pos4 = d_pos4 (hoomd/md/NeighborList.cc:1293-1311). */
+hb2_status hb2_gpu_compute_nlist_binned(const float* d_pos4, uint32_t N, uint32_t N_total,
+                                        const hb2_box* box, const uint32_t dim[3],
+                                        const uint32_t* d_cell_start, const double* d_r_listsq,
+                                        uint32_t ntypes, uint32_t* d_nlist, uint32_t pitch,
+                                        uint32_t* d_n_neigh, float* d_last_pos4,
+                                        uint32_t* d_conditions, void* stream);
+
+/* Replaces gpu_compute_pair_forces<evaluator> (hoomd/md/PotentialPairGPU.cuh:579-656; args
+ * pair_args_t :44-98). d_params: ntypes^2 x 2 floats of evaluator-packed parameters
+ * (hb2_pack_params), d_rcutsq / d_ronsq: ntypes^2 floats, all indexed tj*ntypes+ti. d_force4 =
+ * (fx,fy,fz,pe) per particle, d_virial = 6 x virial_pitch floats (xx,xy,xz,yy,yz,zz) or NULL
+ * (pressure flag off, hoomd/md/PotentialPair.h:739-752). DPD-only inputs may be NULL otherwise. */
+hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const float* d_pos4,
+                                       const float* d_vel4, const uint32_t* d_tag, uint32_t N,
+                                       const hb2_box* box, const uint32_t* d_n_neigh,
+                                       const uint32_t* d_nlist, uint32_t pitch,
+                                       const float* d_params, const float* d_rcutsq,
+                                       const float* d_ronsq, uint32_t ntypes, float* d_force4,
+                                       float* d_virial, size_t virial_pitch, uint32_t seed,
+                                       uint64_t timestep, float dt, float kT,
+                                       uint32_t threads_per_particle, void* stream);
+
+/* Host helper: user parameters -> packed evaluator parameters (the param_type constructor of the
+ * evaluator, e.g. hoomd/md/EvaluatorPairLJ.h:119-140: lj1 = 4 eps sigma^12, lj2 = 4 eps sigma^6). */
+hb2_status hb2_pack_params(hb2_evaluator ev, const double* user_params, uint32_t n_user,
+                           float packed[2]);
+
+/* Replace gpu_nvt_rescale_step_one / _step_two (hoomd/md/TwoStepConstantVolumeGPU.cu:102-114,
+ * :215-223; arithmetic hoomd/md/TwoStepConstantVolume.cc:33-79, :234-260). Step one also performs
+ * the neighbour-list distance check against d_last_pos4 (hoomd/md/NeighborList.cc:1244-1269,
+ * replacing gpu_nlist_needs_update_check_new, hoomd/md/NeighborListGPU.cu:42-84): *d_flag is set to 1
+ * when any particle moved >= maxshift. d_rescale: device scalar (thermostat factor) or NULL = 1. */
+hb2_status hb2_gpu_nve_step_one(float* d_pos4, float* d_vel4, const float* d_force4,
+                                int32_t* d_image3, uint32_t N, const hb2_box* box, float dt,
+                                const double* d_rescale, const float* d_last_pos4, float maxshift,
+                                uint32_t* d_flag, void* stream);
+hb2_status hb2_gpu_nve_step_two(float* d_vel4, const float* d_force4, uint32_t N, float dt,
+                                const double* d_rescale, double* d_ke_out, void* stream);
+
+/* ========================================================================================== *
+ * Layer 2: engine with opaque handles (state resident in HBM; host buffers in/out).
+ * ========================================================================================== */
+typedef struct hb2_system hb2_system;         /* ~ SystemDefinition + ParticleData (hoomd/ParticleData.h:1285) */
+typedef struct hb2_nlist hb2_nlist;           /* ~ NeighborListGPUBinned (hoomd/md/NeighborList.h:121) */
+typedef struct hb2_pair hb2_pair;             /* ~ PotentialPairGPU<evaluator> (hoomd/md/PotentialPairGPU.h:89) */
+typedef struct hb2_integrator hb2_integrator; /* ~ IntegratorTwoStep + TwoStepConstantVolume */
+
+/* device: CUDA ordinal. ntypes: number of particle types. seed: hoomd.Simulation(seed) (16 bit used,
+ * hoomd/RandomNumbers.h:136-171). */
+hb2_status hb2_system_create(hb2_system** out, int device, uint32_t ntypes, uint32_t seed);
+void hb2_system_destroy(hb2_system* sys);
+hb2_status hb2_system_set_box(hb2_system* sys, double Lx, double Ly, double Lz, double xy, double xz,
+                              double yz);
+/* Snapshot in (hoomd/Snapshot / GSD frame layout): N x 3 float positions and velocities, N masses,
+ * N type ids, N x 3 images (may be NULL = 0), tags are 0..N-1 in array order. */
+hb2_status hb2_system_set_particles(hb2_system* sys, uint32_t N, const float* pos3, const float* vel3,
+                                    const float* mass, const uint32_t* typeid_,
+                                    const int32_t* image3);
+/* Snapshot out, tag order. Any pointer may be NULL. */
+hb2_status hb2_system_get_particles(hb2_system* sys, float* pos3, float* vel3, float* mass,
+                                    uint32_t* typeid_, int32_t* image3);
+uint32_t hb2_system_n(const hb2_system* sys);
+uint64_t hb2_system_timestep(const hb2_system* sys);
+hb2_status hb2_system_set_timestep(hb2_system* sys, uint64_t timestep);
+/* hoomd.Simulation.always_compute_pressure (hoomd/simulation.py:447-483): virials are only computed
+ * when set (PDataFlags pressure_tensor, hoomd/ParticleData.h:70-84). */
+hb2_status hb2_system_set_compute_virial(hb2_system* sys, int on);
+hb2_status hb2_system_synchronize(hb2_system* sys);
+
+/* hoomd.md.nlist.Cell(buffer, rebuild_check_delay, check_dist, deterministic) hoomd/md/nlist.py:375 */
+hb2_status hb2_nlist_create(hb2_nlist** out, hb2_system* sys, double buffer,
+                            uint32_t rebuild_check_delay, int check_dist);
+void hb2_nlist_destroy(hb2_nlist* nl);
+hb2_status hb2_nlist_set_buffer(hb2_nlist* nl, double buffer);
+/* Force a (re)build now at the current positions (NeighborList::compute with m_force_update,
+ * hoomd/md/NeighborList.cc:363-435). */
+hb2_status hb2_nlist_compute(hb2_nlist* nl);
+uint64_t hb2_nlist_num_builds(const hb2_nlist* nl);       /* hoomd/md/nlist.py:307 */
+uint64_t hb2_nlist_shortest_rebuild(const hb2_nlist* nl); /* hoomd/md/nlist.py:315 */
+hb2_status hb2_nlist_dimensions(const hb2_nlist* nl, uint32_t dim[3]); /* hoomd/md/nlist.py:399 */
+/* Number of (i<j) pairs currently listed and the pairs themselves as tags, like
+ * NeighborList::getPairListPython in half mode (hoomd/md/NeighborList.cc:1787-1942): each unordered
+ * pair once. pairs: n x 2 uint32 host buffer of capacity cap pairs. */
+hb2_status hb2_nlist_pair_count(hb2_nlist* nl, uint64_t* n_pairs);
+hb2_status hb2_nlist_pair_list(hb2_nlist* nl, uint32_t* pairs, uint64_t cap, uint64_t* n_pairs);
+/* Mean / max full neighbours per particle at the last build. */
+hb2_status hb2_nlist_stats(hb2_nlist* nl, double* mean_neigh, uint32_t* max_neigh,
+                           uint32_t* pitch);
+
+/* hoomd.md.pair.LJ / DPD / plugin pair (hoomd/md/pair/pair.py:163,676); registers its r_cut matrix
+ * with the nlist (hoomd/md/PotentialPair.h:369-371). */
+hb2_status hb2_pair_create(hb2_pair** out, hb2_system* sys, hb2_nlist* nl, hb2_evaluator ev,
+                           hb2_shift_mode mode);
+void hb2_pair_destroy(hb2_pair* p);
+/* setParams / setRCut / setROn for the unordered type pair (ti,tj) (hoomd/md/PotentialPair.h:467-580).
+ * user_params: evaluator's user parameters in declaration order, e.g. LJ {epsilon, sigma}. */
+hb2_status hb2_pair_set_params(hb2_pair* p, uint32_t ti, uint32_t tj, const double* user_params,
+                               uint32_t n_user);
+hb2_status hb2_pair_set_r_cut(hb2_pair* p, uint32_t ti, uint32_t tj, double r_cut);
+hb2_status hb2_pair_set_r_on(hb2_pair* p, uint32_t ti, uint32_t tj, double r_on);
+hb2_status hb2_pair_set_kT(hb2_pair* p, double kT); /* DPD thermostat temperature */
+hb2_status hb2_pair_set_threads_per_particle(hb2_pair* p, uint32_t tpp); /* Autotuner<2> knob */
+/* ForceCompute::compute(timestep) (hoomd/ForceCompute.cc:562-574): builds the nlist if needed. */
+hb2_status hb2_pair_compute(hb2_pair* p, uint64_t timestep);
+/* Tag-ordered results (hoomd/md/force.py:77-156): forces N x 3, energies N, virials N x 6 (error
+ * HB2_ERR_INVALID if the pressure flag was off), total energy. */
+hb2_status hb2_pair_get_forces(hb2_pair* p, double* forces3);
+hb2_status hb2_pair_get_energies(hb2_pair* p, double* energies);
+hb2_status hb2_pair_get_virials(hb2_pair* p, double* virials6);
+hb2_status hb2_pair_get_energy(hb2_pair* p, double* energy);
+/* hoomd/md/PotentialPair.h:255-341 (LJ only): isotropic tail correction -> additional energy and
+ * the diagonal virial term; off by default. */
+hb2_status hb2_pair_set_tail_correction(hb2_pair* p, int on);
+hb2_status hb2_pair_get_additional(hb2_pair* p, double* energy, double virial6[6]);
+
+/* hoomd.md.Integrator(dt, forces=[pair], methods=[ConstantVolume(filter=All, thermostat)])
+ * hoomd/md/integrate.py:267-293, hoomd/md/methods/methods.py:145-175. */
+hb2_status hb2_integrator_create(hb2_integrator** out, hb2_system* sys, double dt);
+void hb2_integrator_destroy(hb2_integrator* it);
+hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p);
+/* thermostat: 0 none (NVE), 1 Bussi(kT, tau) (hoomd/md/Thermostat.h:337-447; tau = 0 is allowed). */
+hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat, double kT,
+                                              double tau);
+/* System::run(nsteps) (hoomd/System.cc:80-181) restricted to this path: prepRun on the first call
+ * (hoomd/md/IntegratorTwoStep.cc:226-281), then per step: step one -> nlist check/rebuild -> forces
+ * -> step two. No host synchronisation inside the loop. */
+hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps);
+/* ComputeThermo quantities of the current state (hoomd/md/ComputeThermo.cc:76-…): kinetic energy,
+ * potential energy, and the 6 virial sums (virial valid only with the pressure flag). */
+hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic, double* potential,
+                                 double virial6[6]);
+/* Device time (ms, CUDA events) spent in the last hb2_integrator_run, and per-phase kernel counts. */
+hb2_status hb2_integrator_last_run_ms(hb2_integrator* it, float* ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOOMD_B200_H */
