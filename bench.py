@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — LJ particle-timesteps/s of the B200 pair-force step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one MD timestep (step one -> nlist check/rebuild -> pair forces -> step two) of the LJ
+liquid of BASELINE.json configs[1]: N = 1,048,576 (FCC 64^3 cells melted to a liquid), rho = 0.9,
+kT = 1.5, r_cut = 2.5, buffer = 0.4, Cell nlist + ConstantVolume with the Bussi thermostat, dt = 0.005.
+Inputs are synthetic (seeded lattice + Maxwell velocities, equilibrated on the device before timing).
+
+Prints ONE JSON line (see the task contract): value = particle-steps/s with the state resident in HBM;
+e2e = the same metric through the public API with HOST snapshots in and out inside the timed region;
+roofline = the pair-force kernel against the measured HBM peak; cpu_baseline = the CPU oracle port
+timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO, KT, RCUT, BUFFER, DT = 0.9, 1.5, 2.5, 0.4, 0.005
+METRIC = "LJ particle-timesteps/s"
+UNIT = "particle-steps/s"
+
+
+def fcc_liquid(ncell, seed=1):
+    a = (4.0 / RHO) ** (1.0 / 3.0)
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) + 0.25
+    g = np.arange(ncell)
+    cells = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 1, 3)
+    L = np.float32(ncell * a)
+    pos = ((cells + base[None]) * a).reshape(-1, 3) - float(L) / 2
+    pos = pos.astype(np.float32)
+    rng = np.random.default_rng(seed)
+    vel = rng.normal(0, np.sqrt(KT), size=pos.shape).astype(np.float32)
+    vel -= vel.mean(axis=0, dtype=np.float64).astype(np.float32)
+    return pos, vel, L
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_sim(hoomd, pos, vel, L, device_id=0, seed=1, thermostat=True):
+    sim = hoomd.Simulation(device=hoomd.device.GPU(gpu_id=device_id), seed=seed)
+    sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays([L, L, L, 0, 0, 0], pos, vel))
+    cell = hoomd.md.nlist.Cell(buffer=BUFFER)
+    lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=RCUT)
+    lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+    th = hoomd.md.methods.thermostats.Bussi(kT=KT) if thermostat else None
+    cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All(), thermostat=th)
+    sim.operations.integrator = hoomd.md.Integrator(dt=DT, methods=[cv], forces=[lj])
+    return sim, cell, lj
+
+
+def oracle_run(snapshot_pos, snapshot_vel, L, nsteps, seed=1):
+    """The CPU oracle port on one core (half list, like hoomd.device.CPU). Returns seconds, builds."""
+    from oracle import md_oracle as orc
+    N = len(snapshot_pos)
+    box = orc.make_box([float(L)] * 3)
+    pos = snapshot_pos.astype(np.float64).copy()
+    vel = snapshot_vel.astype(np.float64).copy()
+    accel = np.zeros_like(pos)
+    image = np.zeros((N, 3), dtype=np.int32)
+    mass = np.ones(N)
+    types = np.zeros(N, dtype=np.uint32)
+    tags = np.arange(N, dtype=np.uint32)
+    # one untimed step-0 call warms the accelerations (prepRun) and page-faults the arrays
+    orc.run(box, pos, vel, accel, image, mass, types, tags, [[1.0, 1.0]], [RCUT], 0, DT, BUFFER,
+            thermostat="bussi", kT=KT, tau=0.0, seed=seed)
+    t0 = time.perf_counter()
+    r = orc.run(box, pos, vel, accel, image, mass, types, tags, [[1.0, 1.0]], [RCUT], nsteps, DT,
+                BUFFER, thermostat="bussi", kT=KT, tau=0.0, seed=seed)
+    return time.perf_counter() - t0, r["builds"]
+
+
+def c1_sample():
+    """The reference-generated equilibrated C1 liquid (N=64,000, same rho/kT as the benchmark state):
+    the bounded CPU sample."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "c1_64k.npz"))
+    return fx["pos"], fx["vel"], fx["L"][0]
+
+
+def cpu_baseline(pos, vel, L, nsteps, replicas):
+    """`replicas` independent single-core oracle runs concurrently (HOOMD's MD CPU path is
+    single-threaded per rank and no MPI exists here: SURVEY.md §8(d)); aggregate throughput."""
+    out = [None] * replicas
+
+    def work(i):
+        out[i] = oracle_run(pos, vel, L, nsteps)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(replicas)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    # each replica times its own steps; the aggregate uses the slowest replica's clock
+    slowest = max(o[0] for o in out)
+    return replicas * nsteps * len(pos) / slowest, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import md_oracle as orc
+    orc.lib()
+    cores = os.cpu_count() or 1
+    # bounded sample of the same workload: a 64^3-cell FCC liquid is 1,048,576 particles; the oracle
+    # does ~5e5 particle-steps/s/core, so the sample is the same state advanced a few steps
+    pos, vel, L = c1_sample()
+    nsteps = max(1, min(args.steps, int(os.environ.get("HB2_REF_STEPS", "100"))))
+    # the oracle's untimed step-0 call (prepRun) is its warm-up
+    value, wall = cpu_baseline(pos, vel, L, nsteps, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": nsteps, "warmup": 1, "ms_per_step": 1e3 * len(pos) * cores / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"LJ liquid N={len(pos)} rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4 Bussi "
+                               "(CPU oracle port of the reference's half-list path)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} independent single-core replicas x {nsteps} steps of the "
+                                   f"N={len(pos)} equilibrated liquid of configs[0] (same rho, kT, "
+                                   "r_cut, buffer as the 1M workload; no MPI in this image: "
+                                   f"throughput-equivalent, not strong-scaled; {wall:.1f} s wall)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import hoomd_blue_b200 as hoomd
+    from hoomd_blue_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ncell = int(os.environ.get("HB2_BENCH_NCELL", "64"))
+    pos, vel, L = fcc_liquid(ncell, seed=1 + rank)
+    N = len(pos)
+    sim, cell, lj = build_sim(hoomd, pos, vel, L, device_id=local, seed=1 + rank)
+    tpp = int(os.environ.get("HB2_TPP", "0"))
+    if tpp:
+        lj.set_threads_per_particle(tpp)
+    # melt the lattice and equilibrate (untimed)
+    sim.run(int(os.environ.get("HB2_BENCH_EQUIL", "2000")))
+    stats = cell._stats()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim.run(args.warmup)
+    L0 = _lib.lib().hb2_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    sim.run(args.steps)
+    ms = sim._last_device_ms
+    barrier()
+    clocks = sampler.stop()
+    launches = int(_lib.lib().hb2_launch_count() - L0)
+    builds = cell.num_builds
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host snapshot in -> run(S) -> host snapshot + energy out, all inside the timed region
+    S = int(os.environ.get("HB2_E2E_BLOCK", "100"))
+    calls = max(1, min(5, args.steps // S if args.steps >= S else 1))
+    snap = sim.state.get_snapshot()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        sim.state.set_snapshot(snap)
+        sim.run(S)
+        snap = sim.state.get_snapshot()
+        e = lj.energy
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * S * calls / float(t.item())
+    h2d = N * (12 + 12 + 4 + 4 + 12)
+    d2h = N * (12 + 12 + 4 + 4 + 12) + 8
+
+    line = None
+    if rank == 0:
+        hbm, peak_src = peaks()
+        nbar, k = stats["mean_neighbors"], args.steps / max(builds, 1)
+        bytes_step = (4 * nbar + 44) + 168 + 32 + (4 * nbar + 168) / k
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LJ liquid N={N} per GPU rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4, Cell "
+                                   "nlist + ConstantVolume/Bussi, dt=0.005 (BASELINE.json configs[1])",
+                       "l2": "working set (nlist %.0f MB + state) exceeds the 126 MB L2; no flush"
+                             % (N * stats["pitch"] * 4 / 1e6),
+                       "mean_neighbors": nbar, "steps_per_rebuild": k, "nlist_builds": builds,
+                       "threads_per_particle": tpp or 8},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / S,
+                    "d2h_bytes_per_step": d2h / S, "steps_per_call": S, "calls": calls,
+                    "what": "state.set_snapshot(host) + sim.run(S) + state.get_snapshot() + energy"},
+            "gpu_launches": launches,
+            "roofline_step": {"bound": "hbm", "achieved": bytes_step * value / world / 1e9,
+                              "peak": hbm, "unit": "GB/s",
+                              "frac": bytes_step * value / world / 1e9 / hbm,
+                              "bytes_per_particle_step": bytes_step, "peak_source": peak_src},
+        }
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        if os.environ.get("HB2_BENCH_CPU", "1") != "0" and world == 1:
+            cores = os.cpu_count() or 1
+            nst = int(os.environ.get("HB2_REF_STEPS", "100"))
+            cp, cv, cL = c1_sample()
+            v, wall = cpu_baseline(cp, cv, cL, nst, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{cores} independent single-core oracle replicas x "
+                                              f"{nst} steps of the N={len(cp)} equilibrated liquid of "
+                                              f"configs[0] (same rho, kT, r_cut, buffer; {wall:.1f} s "
+                                              "wall)"}
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -51,7 +51,7 @@ def _declare(L):
     L.hb2_gpu_compute_pair_forces.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, C.c_uint32,
                                               C.POINTER(Box), _vp, _vp, C.c_uint32, _vp, _vp, _vp,
                                               C.c_uint32, _vp, _vp, C.c_size_t, C.c_uint32,
-                                              C.c_uint64, C.c_float, C.c_float, C.c_uint32, _vp]
+                                              C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_uint32, _vp]
     L.hb2_gpu_nve_step_one.argtypes = [_vp, _vp, _vp, _vp, C.c_uint32, C.POINTER(Box), C.c_float,
                                        _vp, _vp, C.c_float, _vp, _vp]
     L.hb2_gpu_nve_step_two.argtypes = [_vp, _vp, C.c_uint32, C.c_float, _vp, _vp, _vp]

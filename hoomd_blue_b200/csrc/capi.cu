@@ -93,6 +93,7 @@ extern "C" hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mo
                                                   float* d_force4, float* d_virial,
                                                   size_t virial_pitch, uint32_t seed,
                                                   uint64_t timestep, float dt, float kT,
+                                                  float face_margin,
                                                   uint32_t threads_per_particle, void* stream)
     {
     if (!d_pos4 || !box || !d_n_neigh || !d_nlist || !d_params || !d_rcutsq || !d_ronsq || !d_force4
@@ -130,6 +131,7 @@ extern "C" hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mo
     a.timestep = timestep;
     a.dt = dt;
     a.kT = kT;
+    a.face_margin = face_margin;
     a.tpp = threads_per_particle ? threads_per_particle : 8;
     return launch_pair_forces(ev, mode, a, *box, (cudaStream_t)stream);
     }

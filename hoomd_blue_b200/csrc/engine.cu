@@ -1029,6 +1029,7 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
     a.timestep = timestep;
     a.dt = (float)dt;
     a.kT = (float)kT;
+    a.face_margin = (float)(nl->rcut_max_max + 2.0 * nl->buffer) * 1.0001f;
     a.tpp = tpp;
     HB2_TRY(launch_pair_forces(ev, mode, a, s->box, s->stream));
     virial_valid = s->compute_virial;
@@ -1426,6 +1427,10 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     // (hoomd/md/IntegratorTwoStep.cc:154-189)
     const double dof = 3.0 * N - 3.0;
 
+    // System::run resets the per-run statistics of every compute (hoomd/System.cc:103-110 ->
+    // NeighborList::resetStats, hoomd/md/NeighborList.cc:1420-1427): num_builds counts this run only
+    nl->num_builds = 0;
+    nl->shortest_rebuild = ~0ull;
     HB2_CUDA(cudaEventRecord(it->ev0, st));
     // prepRun (hoomd/md/IntegratorTwoStep.cc:226-281): net force at the current timestep
     if (!it->prepared || !pf->computed || pf->computed_epoch != s->order_epoch

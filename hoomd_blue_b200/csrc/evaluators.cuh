@@ -15,6 +15,15 @@ namespace hb2
     {
 typedef float Scalar;
 
+// 1/x to ~0.5 ulp: MUFU.RCP (1 ulp) plus one Newton step in FMA form.
+HB2_DEVICE float rcp_refined(float x)
+    {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float e = fmaf(-x, y, 1.0f);
+    return fmaf(y, e, y);
+    }
+
 // ---------------------------------------------------------------------------------------------
 // Lennard-Jones (hoomd/md/EvaluatorPairLJ.h:95-270)
 // ---------------------------------------------------------------------------------------------
@@ -48,13 +57,13 @@ class EvaluatorPairLJ
         {
         if (rsq < rcutsq && lj1 != 0)
             {
-            const Scalar r2inv = __frcp_rn(rsq);
+            const Scalar r2inv = rcp_refined(rsq);
             const Scalar r6inv = r2inv * r2inv * r2inv;
             force_divr = r2inv * r6inv * (Scalar(12.0) * lj1 * r6inv - Scalar(6.0) * lj2);
             pair_eng = r6inv * (lj1 * r6inv - lj2);
             if (energy_shift)
                 {
-                const Scalar rcut2inv = __frcp_rn(rcutsq);
+                const Scalar rcut2inv = rcp_refined(rcutsq);
                 const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
                 pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
                 }

@@ -59,6 +59,7 @@ struct PairArgs
     const uint64_t* d_timestep; // device timestep (graph-replay safe) or null -> timestep
     uint64_t timestep;
     float dt, kT;
+    float face_margin; // r_list_max + buffer (distance from a face beyond which no image shift occurs)
     uint32_t tpp;
     };
 hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,

@@ -43,7 +43,9 @@ template<class Ev> struct PairKArgs
     uint64_t timestep;
     float dt, kT;
     int energy_shift;
+    float face_margin; // r_list_max + buffer: farther than this from every face => no image shifts
     BoxF box;
+    BoxD boxd;
     };
 
 template<class Ev, bool XPLOR, bool VIRIAL, int TPP, bool ONETYPE>
@@ -73,14 +75,31 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
     float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
     float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
 
+    // Image handling without per-pair fp32 cancellation error: a particle farther than
+    // r_list + buffer from every face has all its listed neighbours in the same image, so the plain
+    // difference pi - pj is the minimum image (and is exact or correctly rounded). A warp that holds
+    // only such particles runs the shift-free loop. Otherwise the particle carries pi - L and pi + L
+    // as unevaluated (hi, lo) float pairs (from fp64), and a pair across a face uses
+    // (hi - pj) + lo: the first difference is exact (Sterbenz), so dx is correctly rounded instead
+    // of carrying half an ulp of L.
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool near_face = false;
     if (active)
         {
-        const float4 pi = __ldg(a.pos + i);
+        pi = __ldg(a.pos + i);
+        // a non-positive margin disables the shortcut (every particle takes the shifting loop)
+        const float m = a.face_margin > 0.f ? a.face_margin : 3.0e38f;
+        near_face = (pi.x >= a.box.hi[0] - m) || (pi.x < a.box.lo[0] + m)
+                    || (pi.y >= a.box.hi[1] - m) || (pi.y < a.box.lo[1] + m)
+                    || (pi.z >= a.box.hi[2] - m) || (pi.z < a.box.lo[2] + m);
+        }
+    const bool warp_shift = __any_sync(0xffffffffu, near_face);
+
+    if (active)
+        {
         const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
         const uint32_t n = __ldg(a.n_neigh + i);
         const uint32_t* __restrict__ row = a.nlist + (size_t)i * a.pitch;
-        const float Lx = a.box.L[0], Ly = a.box.L[1], Lz = a.box.L[2];
-        const float hx = a.box.hi[0], hy = a.box.hi[1], hz = a.box.hi[2];
 
         float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t tagi = 0;
@@ -92,14 +111,9 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
             timestep = a.d_timestep ? *a.d_timestep : a.timestep;
             }
 
-#pragma unroll 2
-        for (uint32_t k = sub; k < n; k += TPP)
-            {
-            const uint32_t j = __ldg(row + k);
-            const float4 pj = __ldg(a.pos + j);
-            const float dx = min_image_f(pi.x - pj.x, Lx, hx);
-            const float dy = min_image_f(pi.y - pj.y, Ly, hy);
-            const float dz = min_image_f(pi.z - pj.z, Lz, hz);
+        auto pair_body = [&](const uint32_t j, const float4 pj, const float dx, const float dy,
+                             const float dz)
+        {
             const float rsq = dx * dx + dy * dy + dz * dz;
 
             float rcutsq = a.rcutsq0, ronsq = a.ronsq0;
@@ -168,6 +182,53 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
                     vyz += f2 * dy * dz;
                     vzz += f2 * dz * dz;
                     }
+                }
+        };
+
+        if (!warp_shift)
+            {
+#pragma unroll 2
+            for (uint32_t k = sub; k < n; k += TPP)
+                {
+                const uint32_t j = __ldg(row + k);
+                const float4 pj = __ldg(a.pos + j);
+                pair_body(j, pj, pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                }
+            }
+        else
+            {
+            // (hi, lo) of pi - L and pi + L per component
+            float mh[3], ml[3], ph[3], pl[3];
+            const float pc[3] = {pi.x, pi.y, pi.z};
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                {
+                const double m = (double)pc[c] - a.boxd.L[c];
+                const double p = (double)pc[c] + a.boxd.L[c];
+                mh[c] = (float)m;
+                ml[c] = (float)(m - (double)mh[c]);
+                ph[c] = (float)p;
+                pl[c] = (float)(p - (double)ph[c]);
+                }
+            const float hx = a.box.hi[0], hy = a.box.hi[1], hz = a.box.hi[2];
+#pragma unroll 2
+            for (uint32_t k = sub; k < n; k += TPP)
+                {
+                const uint32_t j = __ldg(row + k);
+                const float4 pj = __ldg(a.pos + j);
+                float d[3];
+                const float qc[3] = {pj.x, pj.y, pj.z};
+                const float hc[3] = {hx, hy, hz};
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    {
+                    const float d0 = pc[c] - qc[c];
+                    const bool um = d0 >= hc[c], up = d0 < -hc[c];
+                    const float h = um ? mh[c] : (up ? ph[c] : pc[c]);
+                    const float l = um ? ml[c] : (up ? pl[c] : 0.0f);
+                    d[c] = (h - qc[c]) + l;
+                    }
+                pair_body(j, pj, d[0], d[1], d[2]);
                 }
             }
         }
@@ -282,6 +343,8 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.kT = a.kT;
     k.energy_shift = (mode == HB2_SHIFT_SHIFT);
     k.box = boxf(box);
+    k.boxd = boxd(box);
+    k.face_margin = a.face_margin;
     if (Ev::needs_thermo && (!a.vel || !a.tag))
         {
         set_error("pair forces: this evaluator needs velocities and tags");

@@ -118,7 +118,9 @@ hb2_status hb2_gpu_compute_nlist_binned(const float* d_pos4, uint32_t N, uint32_
  * pair_args_t :44-98). d_params: ntypes^2 x 2 floats of evaluator-packed parameters
  * (hb2_pack_params), d_rcutsq / d_ronsq: ntypes^2 floats, all indexed tj*ntypes+ti. d_force4 =
  * (fx,fy,fz,pe) per particle, d_virial = 6 x virial_pitch floats (xx,xy,xz,yy,yz,zz) or NULL
- * (pressure flag off, hoomd/md/PotentialPair.h:739-752). DPD-only inputs may be NULL otherwise. */
+ * (pressure flag off, hoomd/md/PotentialPair.h:739-752). DPD-only inputs may be NULL otherwise.
+ * face_margin: a particle farther than this from every box face is guaranteed to have all listed
+ * neighbours in its own periodic image (pass r_cut_max + 2 * buffer; <= 0 disables the shortcut). */
 hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const float* d_pos4,
                                        const float* d_vel4, const uint32_t* d_tag, uint32_t N,
                                        const hb2_box* box, const uint32_t* d_n_neigh,
@@ -126,7 +128,7 @@ hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, co
                                        const float* d_params, const float* d_rcutsq,
                                        const float* d_ronsq, uint32_t ntypes, float* d_force4,
                                        float* d_virial, size_t virial_pitch, uint32_t seed,
-                                       uint64_t timestep, float dt, float kT,
+                                       uint64_t timestep, float dt, float kT, float face_margin,
                                        uint32_t threads_per_particle, void* stream);
 
 /* Host helper: user parameters -> packed evaluator parameters (the param_type constructor of the

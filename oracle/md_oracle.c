@@ -39,7 +39,7 @@ void orc_make_fraction(const orc_box* b, const double p[3], const double gw[3], 
         }
     }
 
-void orc_min_image(const orc_box* b, double w[3])
+static inline void min_image_inl(const orc_box* b, double w[3])
     {
     /* hoomd/BoxDim.h:343-389. z: one +-L shift; y, x: int(w*Linv + 0.5) multiples of L. */
     if (b->periodic[2])
@@ -64,6 +64,11 @@ void orc_min_image(const orc_box* b, double w[3])
             w[d] += (double)i * b->L[d];
             }
         }
+    }
+
+void orc_min_image(const orc_box* b, double w[3])
+    {
+    min_image_inl(b, w);
     }
 
 void orc_wrap(const orc_box* b, double w[3], int img[3])
@@ -235,7 +240,7 @@ static inline double dist_sq(const orc_box* b, const double* pi, const double* p
     /* dx = pi - pj; minImage; dot = x*x + y*y + z*z left to right
      * (hoomd/md/NeighborListBinned.cc:139-143, hoomd/VectorMath.h dot) */
     double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
-    orc_min_image(b, dx);
+    min_image_inl(b, dx);
     return dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
     }
 
@@ -277,53 +282,57 @@ uint32_t* orc_nlist_binned(const orc_box* b, const double* pos, const uint32_t* 
         break;
         }
 
-    uint32_t* nlist = NULL;
-    /* pass 0 counts (stands in for the Nmax overflow/retry loop, hoomd/md/NeighborList.cc:411-427),
-       pass 1 fills */
-    for (int pass = 0; pass < 2; pass++)
+    /* Cell contents as contiguous (x, y, z) beside the index, as the reference's xyzf array
+       (hoomd/CellList.cc:513-521): the inner loop streams them instead of gathering pos[j]. */
+    double* cell_xyz = (double*)malloc(sizeof(double) * 3 * Nc * Nmax);
+    for (size_t c = 0; c < Nc; c++)
+        for (uint32_t o = 0; o < cell_size[c]; o++)
+            {
+            const uint32_t j = cell_idx[c * Nmax + o];
+            memcpy(cell_xyz + 3 * (c * Nmax + o), pos + 3 * (size_t)j, sizeof(double) * 3);
+            }
+
+    /* One pass appending rows in particle order: head[i] is the running total, so no count pass is
+       needed; the buffer doubles on overflow (stands in for the Nmax overflow/retry loop of
+       hoomd/md/NeighborList.cc:411-427 — same rows, same order). */
+    uint64_t cap = (uint64_t)n_local * 64 + 1024, s_tot = 0;
+    uint32_t* nlist = (uint32_t*)malloc(sizeof(uint32_t) * cap);
+    for (uint32_t i = 0; i < n_local; i++)
         {
-        for (uint32_t i = 0; i < n_local; i++)
+        const double* pi = pos + 3 * (size_t)i;
+        const uint32_t ti = type[i];
+        int ijk[3];
+        double f[3];
+        int my_cell = bin_of(b, dim, gw, pi, ijk, f);
+        uint32_t cnt = 0;
+        head[i] = s_tot;
+        for (uint32_t a = 0; a < aw; a++)
             {
-            const double* pi = pos + 3 * (size_t)i;
-            const uint32_t ti = type[i];
-            int ijk[3];
-            double f[3];
-            int my_cell = bin_of(b, dim, gw, pi, ijk, f);
-            uint32_t cnt = 0;
-            for (uint32_t a = 0; a < aw; a++)
+            const uint32_t nc = adj[(size_t)my_cell * aw + a];
+            const uint32_t sz = cell_size[nc];
+            if (s_tot + cnt + sz > cap)
                 {
-                uint32_t nc = adj[(size_t)my_cell * aw + a];
-                uint32_t sz = cell_size[nc];
-                for (uint32_t o = 0; o < sz; o++)
-                    {
-                    uint32_t j = cell_idx[(size_t)nc * Nmax + o];
-                    uint32_t tp = type[j] * nt + ti; /* Index2D(ti,tj) = tj*nt + ti */
-                    if (j == i || r_cut[tp] <= 0.0)
-                        continue;
-                    double drsq = dist_sq(b, pi, pos + 3 * (size_t)j);
-                    if (drsq <= r_listsq[tp] && (full || i < j))
-                        {
-                        if (pass)
-                            nlist[head[i] + cnt] = j;
-                        cnt++;
-                        }
-                    }
+                cap = 2 * cap + sz;
+                nlist = (uint32_t*)realloc(nlist, sizeof(uint32_t) * cap);
                 }
-            if (!pass)
-                n_neigh[i] = cnt;
-            }
-        if (!pass)
-            {
-            uint64_t s = 0;
-            for (uint32_t i = 0; i < n_local; i++)
+            const uint32_t* idx = cell_idx + (size_t)nc * Nmax;
+            const double* xyz = cell_xyz + 3 * (size_t)nc * Nmax;
+            for (uint32_t o = 0; o < sz; o++)
                 {
-                head[i] = s;
-                s += n_neigh[i];
+                const uint32_t j = idx[o];
+                const uint32_t tp = type[j] * nt + ti; /* Index2D(ti,tj) = tj*nt + ti */
+                if (j == i || r_cut[tp] <= 0.0)
+                    continue;
+                const double drsq = dist_sq(b, pi, xyz + 3 * (size_t)o);
+                if (drsq <= r_listsq[tp] && (full || i < j))
+                    nlist[s_tot + cnt++] = j;
                 }
-            *total = s;
-            nlist = (uint32_t*)malloc(sizeof(uint32_t) * (s ? s : 1));
             }
+        n_neigh[i] = cnt;
+        s_tot += cnt;
         }
+    *total = s_tot;
+    free(cell_xyz);
     free(cell_idx);
     free(cell_size);
     free(adj);
@@ -393,7 +402,7 @@ int orc_distance_check(const orc_box* b, const double* pos, const double* last_p
         double dx[3];
         for (int d = 0; d < 3; d++)
             dx[d] = pos[3 * (size_t)i + d] - 1.0 * last_pos[3 * (size_t)i + d];
-        orc_min_image(b, dx);
+        min_image_inl(b, dx);
         if (dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2] >= maxsq)
             return 1;
         }
@@ -496,7 +505,7 @@ void orc_pair_lj(const orc_box* b, const double* pos, const uint32_t* type, uint
             uint32_t j = nlist[head[i] + k];
             const double* pj = pos + 3 * (size_t)j;
             double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
-            orc_min_image(b, dx);
+            min_image_inl(b, dx);
             double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
             uint32_t tp = type[j] * nt + type[i];
             double rcutsq = r_cut[tp] * r_cut[tp]; /* hoomd/md/PotentialPair.h:498 */
@@ -726,7 +735,7 @@ void orc_pair_dpd(const orc_box* b, const double* pos, const double* vel, const 
             const double* vj = vel + 3 * (size_t)j;
             double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
             double dv[3] = {vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2]};
-            orc_min_image(b, dx);
+            min_image_inl(b, dx);
             double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
             double rdotv = dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2];
             uint32_t tp = type[j] * nt + type[i];

@@ -1,0 +1,349 @@
+"""GPU parity tests: the CUDA path (through the C ABI / operator surface) against the committed
+reference fixtures (tests/golden, made by the reference itself) and against the CPU oracle on seeded
+inputs. Bars (BASELINE.json north_star): neighbour-pair set bit-exact; per-particle force within 1e-5
+relative (norm-wise, floored at the rms force); total energy and virial within 1e-6 relative.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-5
+TOTAL_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def hoomd():
+    import hoomd_blue_b200 as h
+    return h
+
+
+def canon_pairs(pl):
+    pl = np.asarray(pl, dtype=np.uint32).reshape(-1, 2)
+    lo, hi = pl.min(axis=1), pl.max(axis=1)
+    key = np.unique(lo.astype(np.uint64) << np.uint64(32) | hi.astype(np.uint64))
+    return np.stack([(key >> np.uint64(32)).astype(np.uint32),
+                     (key & np.uint64(0xFFFFFFFF)).astype(np.uint32)], axis=1)
+
+
+def force_err(f, f_ref):
+    """max over particles of |f - f_ref| / max(|f_ref|, rms|f_ref|)"""
+    n_ref = np.linalg.norm(f_ref, axis=1)
+    floor = np.sqrt(np.mean(n_ref ** 2))
+    return np.max(np.linalg.norm(f - f_ref, axis=1) / np.maximum(n_ref, floor))
+
+
+def make_sim(hoomd, L, pos, vel=None, typeid=None, types=("A",), image=None, seed=1, timestep=None):
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=seed)
+    if timestep:
+        sim.timestep = timestep
+    snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel, typeid, types, image)
+    sim.create_state_from_snapshot(snap)
+    return sim
+
+
+def lj_sim(hoomd, fx, params, r_cut, buffer, mode, r_on=None, types=("A",), seed=1, thermostat=None,
+           dt=0.005, tpp=None):
+    sim = make_sim(hoomd, fx["L"], fx["pos"], fx["vel"], fx["typeid"] if "typeid" in fx else None,
+                   types, fx["image"] if "image" in fx else None, seed)
+    sim.always_compute_pressure = True
+    cell = hoomd.md.nlist.Cell(buffer=buffer)
+    lj = hoomd.md.pair.LJ(nlist=cell, mode=mode)
+    for (a, b), (eps, sig) in params.items():
+        lj.params[(a, b)] = dict(epsilon=eps, sigma=sig)
+        lj.r_cut[(a, b)] = r_cut[(a, b)]
+        if r_on is not None:
+            lj.r_on[(a, b)] = r_on[(a, b)]
+    if tpp:
+        lj.set_threads_per_particle(tpp)
+    cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All(), thermostat=thermostat)
+    sim.operations.integrator = hoomd.md.Integrator(dt=dt, methods=[cv], forces=[lj])
+    return sim, cell, lj
+
+
+def check_forces(lj, fx, prefix):
+    f = lj.forces
+    assert force_err(f, fx[f"{prefix}force"]) <= FORCE_RTOL
+    e_tot = float(fx[f"{prefix}total_energy"])
+    assert abs(lj.energy - e_tot) <= TOTAL_RTOL * abs(e_tot)
+    # per-particle energies: absolute error relative to the rms energy
+    e = lj.energies
+    e_ref = fx[f"{prefix}energy"]
+    assert np.max(np.abs(e - e_ref)) <= 1e-5 * np.sqrt(np.mean(e_ref ** 2))
+    v = lj.virials
+    v_ref = fx[f"{prefix}virial"]
+    vs, vs_ref = v.sum(axis=0), v_ref.sum(axis=0)
+    # the diagonal sums carry the pressure; off-diagonals average to ~0, so compare against the
+    # diagonal scale
+    scale = np.max(np.abs(vs_ref[[0, 3, 5]]))
+    assert np.max(np.abs(vs[[0, 3, 5]] - vs_ref[[0, 3, 5]])) <= TOTAL_RTOL * scale
+    assert np.max(np.abs(vs - vs_ref)) <= 1e-5 * scale
+    assert np.max(np.abs(v - v_ref)) <= 1e-5 * np.sqrt(np.mean(v_ref ** 2)) * 10
+
+
+# ---------------------------------------------------------------- reference golden vectors ----
+def test_true_pair_list(hoomd, golden_dir):
+    """hoomd/md/pytest/test_nlist.py:221-222,353-372 with hoomd/conftest.py:203-262."""
+    with open(os.path.join(golden_dir, "ref_vectors.json")) as f:
+        truth = set(frozenset(p) for p in json.load(f)["true_pair_list"])
+    n = 7
+    r = np.arange(-n / 2, n / 2)
+    x, y, z = np.meshgrid(r, r, r)
+    pos = (np.vstack((x.flatten(), y.flatten(), z.flatten())).T + 0.5) * 1.0
+    fx = dict(L=[7.0, 7.0, 7.0], pos=pos.astype(np.float32), vel=np.zeros_like(pos, dtype=np.float32))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 1.1}, 0.0, "none")
+    sim.run(0)
+    pairs = cell.pair_list
+    assert len(pairs) == 1029
+    assert set(frozenset((int(a), int(b))) for a, b in pairs) == truth
+    assert cell.dimensions == (6, 6, 6)
+    assert cell.num_builds == 1
+
+
+def test_forces_and_energies_json(hoomd, golden_dir):
+    """hoomd/md/pytest/test_potential.py:952-1051: two particles at r = 0.75 and 1.5, rtol 5e-6."""
+    with open(os.path.join(golden_dir, "ref_vectors.json")) as f:
+        fe = json.load(f)["forces_and_energies"]
+    for name, cls_name, keys in (("LJ", "LJ", ("epsilon", "sigma")),
+                                 ("DPDConservative", "DPDConservative", ("A",))):
+        tab = fe[name]
+        for p, F, E in zip(tab["params"], tab["forces"], tab["energies"]):
+            for d, f_ref, e_ref in zip((0.75, 1.5), F, E):
+                pos = np.array([[0, 0, 0.1], [0, 0, 0.1 + d]], dtype=np.float32)
+                sim = make_sim(hoomd, [20.0, 20.0, 20.0], pos, np.zeros_like(pos))
+                cell = hoomd.md.nlist.Cell(buffer=0.4)
+                cls = getattr(hoomd.md.pair, cls_name)
+                pot = cls(nlist=cell, default_r_cut=2.5)
+                pot.params[("A", "A")] = {k: p[k] for k in keys}
+                cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+                sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[cv], forces=[pot])
+                sim.run(0)
+                d32 = float(pos[1, 2]) - float(pos[0, 2])  # the fp32 separation actually simulated
+                f = pot.forces
+                # the table holds the force on particle 0 along r_hat = +z
+                # (test_potential.py:1044-1048: sim_forces[0] == forces[i] * r)
+                assert abs(d32 - d) < 1e-6
+                assert np.isclose(f[0, 2], f_ref, rtol=2e-5, atol=1e-6 if f_ref == 0 else 0), (name, p, d)
+                assert np.isclose(f[1, 2], -f_ref, rtol=2e-5, atol=1e-6 if f_ref == 0 else 0)
+                assert np.isclose(pot.energy, e_ref, rtol=2e-5, atol=1e-6 if e_ref == 0 else 0)
+
+
+@pytest.mark.parametrize("mode", ["none", "shift", "xplor"])
+def test_lj_2k(hoomd, golden_dir, mode):
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    r_on = {("A", "A"): 2.0} if mode == "xplor" else None
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, mode, r_on)
+    sim.run(0)
+    assert np.array_equal(canon_pairs(cell.pair_list), fx[f"{mode}_pairs"])
+    assert cell.dimensions == tuple(int(d) for d in fx[f"{mode}_dims"])
+    check_forces(lj, fx, f"{mode}_")
+
+
+@pytest.mark.parametrize("tpp", [1, 2, 4, 8, 16, 32])
+def test_lj_2k_threads_per_particle(hoomd, golden_dir, tpp):
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none",
+                           tpp=tpp)
+    sim.run(0)
+    check_forces(lj, fx, "none_")
+
+
+KA_PARAMS = {("A", "A"): (1.0, 1.0), ("A", "B"): (1.5, 0.8), ("B", "B"): (0.5, 0.88)}
+KA_RC = {("A", "A"): 2.5, ("A", "B"): 2.0, ("B", "B"): 2.2}
+
+
+def test_ka_2k(hoomd, golden_dir):
+    """Kob-Andersen 80:20: per-type-pair parameters and r_cut, mode shift."""
+    fx = dict(np.load(os.path.join(golden_dir, "ka_2k.npz")))
+    sim, cell, lj = lj_sim(hoomd, fx, KA_PARAMS, KA_RC, 0.3, "shift", types=("A", "B"))
+    sim.run(0)
+    assert np.array_equal(canon_pairs(cell.pair_list), fx["shift_pairs"])
+    check_forces(lj, fx, "shift_")
+
+
+def test_dpd_3k(hoomd, golden_dir):
+    """DPD with the per-pair Philox draw at three timesteps (one beyond 2^32)."""
+    fx = dict(np.load(os.path.join(golden_dir, "dpd_3k.npz")))
+    for n, ts in enumerate(fx["timesteps"]):
+        sim = make_sim(hoomd, fx["L"], fx["pos"], fx["vel"], seed=int(fx["seed"]), timestep=int(ts))
+        sim.always_compute_pressure = True
+        cell = hoomd.md.nlist.Cell(buffer=float(fx["buffer"]))
+        dpd = hoomd.md.pair.DPD(nlist=cell, kT=float(fx["kT"]), default_r_cut=float(fx["r_cut"]))
+        dpd.params[("A", "A")] = dict(A=float(fx["A"]), gamma=float(fx["gamma"]))
+        cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+        sim.operations.integrator = hoomd.md.Integrator(dt=float(fx["dt"]), methods=[cv],
+                                                        forces=[dpd])
+        sim.run(0)
+        if n == 0:
+            assert np.array_equal(canon_pairs(cell.pair_list), fx["pairs"])
+        assert force_err(dpd.forces, fx[f"force_{n}"]) <= FORCE_RTOL
+        e_ref = fx[f"energy_{n}"]
+        assert abs(dpd.energy - e_ref.sum()) <= TOTAL_RTOL * abs(e_ref.sum())
+        vs, vs_ref = dpd.virials.sum(axis=0), fx[f"virial_{n}"].sum(axis=0)
+        scale = np.max(np.abs(vs_ref[[0, 3, 5]]))
+        assert np.max(np.abs(vs[[0, 3, 5]] - vs_ref[[0, 3, 5]])) <= TOTAL_RTOL * scale
+
+
+def test_c1_64k(hoomd, golden_dir):
+    """BASELINE.json configs[0]: LJ liquid N=64,000 — pair set by sha256, forces, totals."""
+    fx = dict(np.load(os.path.join(golden_dir, "c1_64k.npz")))
+    fx["typeid"] = np.zeros(len(fx["pos"]), dtype=np.uint32)
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none")
+    sim.run(0)
+    pairs = canon_pairs(cell.pair_list)
+    assert len(pairs) == int(fx["n_pairs"])
+    assert np.array_equal(pairs[:64], fx["pairs_head"])
+    assert hashlib.sha256(pairs.tobytes()).hexdigest() == str(fx["pairs_sha256"])
+    assert cell.dimensions == tuple(int(d) for d in fx["dims"])
+    assert force_err(lj.forces, fx["force"]) <= FORCE_RTOL
+    e_tot = float(fx["total_energy"])
+    assert abs(lj.energy - e_tot) <= TOTAL_RTOL * abs(e_tot)
+    vs, vs_ref = lj.virials.sum(axis=0), fx["virial_sum"]
+    scale = np.max(np.abs(vs_ref[[0, 3, 5]]))
+    assert np.max(np.abs(vs[[0, 3, 5]] - vs_ref[[0, 3, 5]])) <= TOTAL_RTOL * scale
+
+
+# ------------------------------------------------------------------------- trajectories ----
+def test_nve_trajectory_lj_2k(hoomd, golden_dir):
+    """20 NVE steps against the reference's fp64 trajectory: fp32 state tracks it to ~1e-4, energy
+    is conserved as well as the reference conserves it."""
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none",
+                           seed=11)
+    thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+    thermo._attach(sim)
+    sim.run(0)
+    ke, pe = [thermo.kinetic_energy], [thermo.potential_energy]
+    for _ in range(20):
+        sim.run(1)
+        ke.append(thermo.kinetic_energy)
+        pe.append(thermo.potential_energy)
+    ke, pe = np.array(ke), np.array(pe)
+    assert sim.timestep == 20
+    assert np.allclose(ke, fx["nve_ke"], rtol=2e-5)
+    assert np.allclose(pe, fx["nve_pe"], rtol=2e-5)
+    e, e_ref = ke + pe, fx["nve_ke"] + fx["nve_pe"]
+    assert np.max(np.abs(e - e[0])) <= 2.0 * np.max(np.abs(e_ref - e_ref[0])) + 1e-6 * abs(e_ref[0])
+    s = sim.state.get_snapshot()
+    L = fx["L"].astype(np.float64)
+    d = s.particles.position.astype(np.float64) - fx["nve_pos"]
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 2e-4
+    assert np.max(np.abs(s.particles.velocity - fx["nve_vel"])) < 2e-3
+    unwrapped = s.particles.position + s.particles.image * L
+    unwrapped_ref = fx["nve_pos"] + fx["nve_image"] * L
+    assert np.max(np.abs(unwrapped - unwrapped_ref)) < 2e-4
+    assert cell.num_builds == int(fx["nve_builds"])
+
+
+def test_bussi_trajectory_lj_2k(hoomd, golden_dir):
+    """20 steps with the Bussi thermostat: the rescale factor is a function of (KE, timestep, seed)
+    only, so the kinetic-energy trace must follow the reference's."""
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    th = hoomd.md.methods.thermostats.Bussi(kT=1.5)
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none",
+                           seed=11, thermostat=th)
+    thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+    thermo._attach(sim)
+    sim.run(0)
+    ke = [thermo.kinetic_energy]
+    for _ in range(20):
+        sim.run(1)
+        ke.append(thermo.kinetic_energy)
+    assert np.allclose(np.array(ke), fx["bussi_ke"], rtol=5e-5)
+    s = sim.state.get_snapshot()
+    L = fx["L"].astype(np.float64)
+    d = s.particles.position.astype(np.float64) - fx["bussi_pos"]
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 2e-4
+
+
+def test_dpd_trajectory(hoomd, golden_dir):
+    fx = dict(np.load(os.path.join(golden_dir, "dpd_3k.npz")))
+    sim = make_sim(hoomd, fx["L"], fx["pos"], fx["vel"], seed=int(fx["seed"]))
+    cell = hoomd.md.nlist.Cell(buffer=float(fx["buffer"]))
+    dpd = hoomd.md.pair.DPD(nlist=cell, kT=float(fx["kT"]), default_r_cut=float(fx["r_cut"]))
+    dpd.params[("A", "A")] = dict(A=float(fx["A"]), gamma=float(fx["gamma"]))
+    cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+    sim.operations.integrator = hoomd.md.Integrator(dt=float(fx["dt"]), methods=[cv], forces=[dpd])
+    sim.run(10)
+    s = sim.state.get_snapshot()
+    L = fx["L"].astype(np.float64)
+    d = s.particles.position.astype(np.float64) - fx["traj_pos"]
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 1e-4
+    assert np.max(np.abs(s.particles.velocity - fx["traj_vel"])) < 2e-3
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs ----
+def random_liquid(n_side, rho, seed, jitter=0.1):
+    rng = np.random.default_rng(seed)
+    N = n_side ** 3
+    L = np.float32((N / rho) ** (1 / 3))
+    g = (np.arange(n_side) + 0.5) * (float(L) / n_side) - float(L) / 2
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    pos = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    pos += rng.uniform(-jitter, jitter, size=pos.shape)
+    pos = pos.astype(np.float32)
+    Lf = float(L)
+    pos[pos >= Lf / 2] -= L
+    pos[pos < -Lf / 2] += L
+    pos = np.clip(pos, -Lf / 2, np.nextafter(np.float32(Lf / 2), np.float32(0)))
+    vel = rng.normal(0, 1.0, size=pos.shape).astype(np.float32)
+    return pos, vel, np.array([L, L, L], dtype=np.float32)
+
+
+@pytest.mark.parametrize("n_side,rho", [(30, 0.9), (20, 0.4), (48, 0.9)])
+def test_oracle_random_liquid(hoomd, oracle, n_side, rho):
+    pos, vel, L = random_liquid(n_side, rho, seed=n_side)
+    fx = dict(L=L, pos=pos, vel=vel)
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "shift")
+    sim.run(0)
+    box = oracle.make_box([float(v) for v in L])
+    types = np.zeros(len(pos), dtype=np.uint32)
+    nn, head, nl, dim = oracle.nlist(box, pos, types, [2.5], 0.4, full=True)
+    assert np.array_equal(canon_pairs(cell.pair_list), oracle.pair_set(nn, head, nl))
+    assert cell.dimensions == dim
+    f_ref, v_ref = oracle.pair_lj(box, pos, types, nn, head, nl, [[1.0, 1.0]], [2.5], shift_mode=1)
+    assert force_err(lj.forces, f_ref[:, :3]) <= FORCE_RTOL
+    e_ref = f_ref[:, 3].sum()
+    assert abs(lj.energy - e_ref) <= TOTAL_RTOL * abs(e_ref)
+    vs, vs_ref = lj.virials.sum(axis=0), v_ref.sum(axis=1)
+    scale = np.max(np.abs(vs_ref[[0, 3, 5]]))
+    assert np.max(np.abs(vs[[0, 3, 5]] - vs_ref[[0, 3, 5]])) <= TOTAL_RTOL * scale
+
+
+def test_edge_cases(hoomd):
+    """box too small, NaN position, particle out of the box, empty cells / sparse gas."""
+    pos = np.array([[0, 0, 0], [1, 0, 0]], dtype=np.float32)
+    fx = dict(L=[5.0, 5.0, 5.0], pos=pos, vel=np.zeros_like(pos))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none")
+    with pytest.raises(RuntimeError, match="too small"):
+        sim.run(0)
+    bad = pos.copy()
+    bad[1, 0] = np.nan
+    fx = dict(L=[20.0, 20.0, 20.0], pos=bad, vel=np.zeros_like(pos))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none")
+    with pytest.raises(RuntimeError, match="NaN"):
+        sim.run(0)
+    bad = pos.copy()
+    bad[1, 0] = 11.0
+    fx = dict(L=[20.0, 20.0, 20.0], pos=bad, vel=np.zeros_like(pos))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none")
+    with pytest.raises(RuntimeError, match="no longer in the simulation box"):
+        sim.run(0)
+    # two particles across the periodic face, far fewer particles than cells
+    p2 = np.array([[9.9, 0, 0], [-9.9, 0, 0], [0, 5, 5]], dtype=np.float32)
+    fx = dict(L=[20.0, 20.0, 20.0], pos=p2, vel=np.zeros_like(p2))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none")
+    sim.run(0)
+    assert [sorted(p) for p in cell.pair_list.tolist()] == [[0, 1]]
+    f = lj.forces
+    assert np.allclose(f[0], -f[1]) and np.allclose(f[2], 0) and f[0, 0] != 0
+    assert lj.virials is not None
+    sim.always_compute_pressure = False
+    assert lj.virials is None
