@@ -53,6 +53,20 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def roofline_pair(prof, nbar, N, hbm, peak_src):
+    t = prof["force_ms"] / max(prof["force_launches"], 1) * 1e-3
+    alg = (4.0 * nbar + 44.0) * N
+    traffic = None
+    summ = os.path.join(ROOT, "profiles", "pair_force_summary.json")
+    if os.path.exists(summ):
+        with open(summ) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    return {"kernel": "pair_force_kernel<EvaluatorPairLJ>", "bound": "hbm",
+            "achieved": alg / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / t / 1e9 / hbm,
+            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3,
+            "peak_source": peak_src}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled during the timed region."""
 
@@ -240,6 +254,16 @@ def run_ours(args):
     ms = float(t.item())
     value = world * N * args.steps / (ms * 1e-3)
 
+    # ---- per-phase device times of the same loop (separate, event-instrumented run: the events
+    # would perturb the timed region above)
+    integ = sim.operations.integrator
+    P = max(20, min(args.steps, 300))
+    integ._set_profiling(True)
+    sim.run(P)
+    prof = integ._profile()
+    integ._set_profiling(False)
+    pstats = cell._stats()
+
     # ---- e2e: host snapshot in -> run(S) -> host snapshot + energy out, all inside the timed region
     S = int(os.environ.get("HB2_E2E_BLOCK", "100"))
     calls = max(1, min(5, args.steps // S if args.steps >= S else 1))
@@ -280,6 +304,14 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h / S, "steps_per_call": S, "calls": calls,
                     "what": "state.set_snapshot(host) + sim.run(S) + state.get_snapshot() + energy"},
             "gpu_launches": launches,
+            # dominant kernel: pair_force_kernel. Algorithmic bytes per launch = (4 nbar + 44) N
+            # (neighbour row + own position + count + head + force write)
+            "roofline": roofline_pair(prof, pstats["mean_neighbors"], N, hbm, peak_src),
+            "phases": {"force_ms_per_step": prof["force_ms"] / max(prof["force_launches"], 1),
+                       "nlist_ms_per_build": prof["nlist_ms"] / max(prof["builds"], 1),
+                       "nlist_ms_per_step": prof["nlist_ms"] / max(prof["steps"], 1),
+                       "integrate_ms_per_step": prof["integrate_ms"] / max(prof["steps"], 1),
+                       "profiled_steps": prof["steps"], "profiled_builds": prof["builds"]},
             "roofline_step": {"bound": "hbm", "achieved": bytes_step * value / world / 1e9,
                               "peak": hbm, "unit": "GB/s",
                               "frac": bytes_step * value / world / 1e9 / hbm,

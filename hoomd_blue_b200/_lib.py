@@ -105,6 +105,8 @@ def _declare(L):
     L.hb2_integrator_run.argtypes = [_vp, C.c_uint64]
     L.hb2_integrator_thermo.argtypes = [_vp, _f64p, _f64p, _f64p]
     L.hb2_integrator_last_run_ms.argtypes = [_vp, _f32p]
+    L.hb2_integrator_set_profiling.argtypes = [_vp, C.c_int]
+    L.hb2_integrator_get_profile.argtypes = [_vp, _f64p, C.POINTER(C.c_uint64)]
 
 
 def lib():

@@ -13,6 +13,18 @@
 
 namespace hb2
     {
+// Sub-cell resolution of the sort key: particles of one cell are ordered along a 4x4x4 Morton curve,
+// so that 8 consecutive particles (one 128-byte line of float4 positions) form a compact blob and the
+// force kernel's position gathers share lines (DESIGN.md "gather locality").
+constexpr int SUB_BITS = 6;
+
+HB2_DEVICE uint32_t morton2x3(uint32_t x, uint32_t y, uint32_t z)
+    {
+    // interleave three 2-bit coordinates: z1 y1 x1 z0 y0 x0
+    return (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3)
+           | ((z & 2u) << 4);
+    }
+
 // One thread per particle: cell id with the reference's rule in fp64.
 // f = (p - lo) * Linv (hoomd/BoxDim.h:276-284, zero tilt, no ghost width);
 // ib = (int)(f * dim), ib == dim -> 0 when periodic (hoomd/CellList.cc:455-470).
@@ -38,26 +50,36 @@ __global__ void __launch_bounds__(256)
         f[2] = __dmul_rn(__dadd_rn((double)p.z, -box.lo[2]), box.Linv[2]);
         const uint32_t dm[3] = {dim.x, dim.y, dim.z};
         int ib[3];
+        uint32_t sb[3];
         bool out = false;
 #pragma unroll
         for (int d = 0; d < 3; d++)
             {
-            ib[d] = (int)__dmul_rn(f[d], (double)dm[d]);
+            const double fc = __dmul_rn(f[d], (double)dm[d]);
+            ib[d] = (int)fc;
+            // position inside the cell in quarters (ordering only; never decides membership)
+            const int q = (int)((fc - (double)ib[d]) * 4.0);
+            sb[d] = (uint32_t)min(max(q, 0), 3);
             if (ib[d] == (int)dm[d])
+                {
                 ib[d] = 0;
+                sb[d] = 0;
+                }
             if (f[d] < -0.00001 || f[d] >= 1.00001 || ib[d] < 0 || ib[d] >= (int)dm[d])
                 out = true;
             }
         if (out)
             atomicMax(&conditions[2], i + 1);
         else
-            key = ((uint32_t)ib[2] * dim.y + (uint32_t)ib[1]) * dim.x + (uint32_t)ib[0];
+            key = ((((uint32_t)ib[2] * dim.y + (uint32_t)ib[1]) * dim.x + (uint32_t)ib[0]) << SUB_BITS)
+                  | morton2x3(sb[0], sb[1], sb[2]);
         }
     keys[i] = key;
     vals[i] = i;
     }
 
-// cell_start from the sorted keys: slot k starts every cell in (key[k-1], key[k]].
+// cell_start from the sorted keys (cell = key >> SUB_BITS): slot k starts every cell in
+// (cell[k-1], cell[k]].
 __global__ void __launch_bounds__(256)
     cell_start_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t N, uint32_t Nc,
                       uint32_t* __restrict__ cell_start)
@@ -65,8 +87,8 @@ __global__ void __launch_bounds__(256)
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > N)
         return;
-    uint32_t lo = (k == 0) ? 0u : keys_sorted[k - 1] + 1u;
-    uint32_t hi = (k == N) ? Nc : keys_sorted[k];
+    uint32_t lo = (k == 0) ? 0u : (keys_sorted[k - 1] >> SUB_BITS) + 1u;
+    uint32_t hi = (k == N) ? Nc : (keys_sorted[k] >> SUB_BITS);
     if (k == 0)
         lo = 0;
     for (uint32_t c = lo; c <= hi && c <= Nc; c++)
@@ -103,7 +125,7 @@ static inline int key_bits(uint32_t Nc)
     int b = 1;
     while (b < 32 && (1ull << b) < (unsigned long long)Nc)
         b++;
-    return b;
+    return b + SUB_BITS;
     }
 
 size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc)

@@ -41,7 +41,7 @@ extern "C" hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N
                               (cudaStream_t)stream);
     }
 
-extern "C" hb2_status hb2_gpu_compute_nlist_binned(const float* d_pos4, uint32_t N, uint32_t N_total,
+extern "C" hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_total,
                                                    const hb2_box* box, const uint32_t dim[3],
                                                    const uint32_t* d_cell_start,
                                                    const double* d_r_listsq, uint32_t ntypes,
@@ -55,7 +55,15 @@ extern "C" hb2_status hb2_gpu_compute_nlist_binned(const float* d_pos4, uint32_t
         set_error("hb2_gpu_compute_nlist_binned: null argument");
         return HB2_ERR_INVALID;
         }
-    (void)N_total;
+    if (pitch % 32u != 0)
+        {
+        set_error("hb2_gpu_compute_nlist_binned: pitch must be a multiple of 32");
+        return HB2_ERR_INVALID;
+        }
+    // the far-away dummy particle that pads the rows lives at index N_total
+    const float4 far_pos = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
+    HB2_CUDA(cudaMemcpyAsync((float4*)d_pos4 + N_total, &far_pos, sizeof(float4), cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
     // the guard band and the one-type fast path need the host copy of the r_list^2 matrix
     std::vector<double> h((size_t)ntypes * ntypes);
     HB2_CUDA(cudaMemcpyAsync(h.data(), d_r_listsq, sizeof(double) * h.size(), cudaMemcpyDeviceToHost,
@@ -80,6 +88,7 @@ extern "C" hb2_status hb2_gpu_compute_nlist_binned(const float* d_pos4, uint32_t
     a.n_neigh = d_n_neigh;
     a.last_pos = (float4*)d_last_pos4;
     a.conditions = d_conditions;
+    a.dummy_index = N_total;
     return launch_nlist_build(a, *box, (cudaStream_t)stream);
     }
 

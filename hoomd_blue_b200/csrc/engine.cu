@@ -88,6 +88,7 @@ struct hb2_system
 
     std::vector<hb2_nlist*> nlists;
     std::vector<hb2_pair*> pairs;
+    cudaEvent_t mid_event = nullptr; // recorded between the nlist update and the force launch
 
     hb2_status set_timestep(uint64_t t)
         {
@@ -187,6 +188,23 @@ struct hb2_integrator
     uint64_t prepared_epoch = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
+    // optional per-phase device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    std::vector<size_t> marks; // five events per step: a b c d e
+    double phase_ms[3] = {0, 0, 0}; // integrate, nlist, force
+    uint64_t phase_n[3] = {0, 0, 0};
+    cudaEvent_t next_event()
+        {
+        if (pool_used == pool.size())
+            {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+            }
+        return pool[pool_used++];
+        }
     };
 
 // =================================================================================================
@@ -338,10 +356,11 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
             dev_free(s->vel[b]);
             dev_free(s->image[b]);
             dev_free(s->tag[b]);
-            HB2_TRY(dev_alloc(&s->pos[b], N));
-            HB2_TRY(dev_alloc(&s->vel[b], N));
+            // one extra slot: the far-away dummy particle that pads neighbour-list rows
+            HB2_TRY(dev_alloc(&s->pos[b], (size_t)N + 1));
+            HB2_TRY(dev_alloc(&s->vel[b], (size_t)N + 1));
             HB2_TRY(dev_alloc(&s->image[b], 3 * (size_t)N));
-            HB2_TRY(dev_alloc(&s->tag[b], N));
+            HB2_TRY(dev_alloc(&s->tag[b], (size_t)N + 1));
             }
         dev_free(s->rtag);
         HB2_TRY(dev_alloc(&s->rtag, N));
@@ -380,6 +399,15 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
                              s->stream));
     HB2_CUDA(cudaMemcpyAsync(s->rtag, ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice,
                              s->stream));
+    const float4 far_pos = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
+    const float4 far_vel = make_float4(0.f, 0.f, 0.f, 1.f);
+    const uint32_t far_tag = 0xffffffffu;
+    for (int b = 0; b < 2; b++)
+        {
+        HB2_CUDA(cudaMemcpyAsync(s->pos[b] + N, &far_pos, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+        HB2_CUDA(cudaMemcpyAsync(s->vel[b] + N, &far_vel, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+        HB2_CUDA(cudaMemcpyAsync(s->tag[b] + N, &far_tag, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        }
     HB2_CUDA(cudaStreamSynchronize(s->stream));
     s->order_epoch++;
     for (auto* nl : s->nlists)
@@ -529,7 +557,7 @@ hb2_status hb2_nlist::ensure_capacity()
         }
     dim = make_uint3(d[0], d[1], d[2]);
     const uint64_t Nc64 = (uint64_t)d[0] * d[1] * d[2];
-    if (Nc64 >= (1ull << 31))
+    if (Nc64 >= (1ull << 25)) // the sort key holds the cell id above 6 sub-cell bits
         {
         set_error("nlist: cell grid too large");
         return HB2_ERR_INVALID;
@@ -567,7 +595,7 @@ hb2_status hb2_nlist::ensure_capacity()
         const double rl = rcut_max_max + buffer;
         const double est = (double)N / vol * 4.18879020478639 * rl * rl * rl;
         pitch = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 16.0), (double)std::max(N, 8u));
-        pitch = (pitch + 7u) & ~7u;
+        pitch = (pitch + 31u) & ~31u; // rows are padded to whole 32-entry chunks
         }
     if ((size_t)N * pitch > nlist_cap)
         {
@@ -627,6 +655,7 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
         a.n_neigh = d_n_neigh;
         a.last_pos = d_last_pos;
         a.conditions = d_conditions;
+        a.dummy_index = N;
         HB2_TRY(launch_nlist_build(a, s->box, st));
         HB2_CUDA(cudaMemcpyAsync(h_conditions, d_conditions, 4 * sizeof(uint32_t),
                                  cudaMemcpyDeviceToHost, st));
@@ -648,7 +677,7 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
             break;
         // overflow: regrow to a multiple of 8 with headroom and rebuild
         // (hoomd/md/NeighborList.cc:411-427, :1601-1617)
-        pitch = ((uint32_t)(max_neigh * 1.125) + 8u + 7u) & ~7u;
+        pitch = ((uint32_t)(max_neigh * 1.125) + 8u + 31u) & ~31u;
         if ((size_t)N * pitch > nlist_cap)
             {
             dev_free(d_nlist);
@@ -1031,6 +1060,8 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
     a.kT = (float)kT;
     a.face_margin = (float)(nl->rcut_max_max + 2.0 * nl->buffer) * 1.0001f;
     a.tpp = tpp;
+    if (s->mid_event)
+        HB2_CUDA(cudaEventRecord(s->mid_event, s->stream));
     HB2_TRY(launch_pair_forces(ev, mode, a, s->box, s->stream));
     virial_valid = s->compute_virial;
     computed = true;
@@ -1152,9 +1183,9 @@ extern "C" hb2_status hb2_pair_set_kT(hb2_pair* p, double kT)
 
 extern "C" hb2_status hb2_pair_set_threads_per_particle(hb2_pair* p, uint32_t tpp)
     {
-    if (!p || tpp == 0 || tpp > 32 || (tpp & (tpp - 1)))
+    if (!p || (tpp != 4 && tpp != 8 && tpp != 16 && tpp != 32))
         {
-        set_error("threads_per_particle must be a power of two in [1, 32]");
+        set_error("threads_per_particle must be 4, 8, 16 or 32");
         return HB2_ERR_INVALID;
         }
     p->tpp = tpp;
@@ -1378,6 +1409,8 @@ extern "C" void hb2_integrator_destroy(hb2_integrator* it)
     cudaSetDevice(it->sys->device);
     cudaEventDestroy(it->ev0);
     cudaEventDestroy(it->ev1);
+    for (auto e : it->pool)
+        cudaEventDestroy(e);
     delete it;
     }
 
@@ -1442,10 +1475,22 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     if (it->thermostat == 1)
         HB2_TRY(launch_kinetic(s->vel[s->cur], N, s->d_partial, s->d_ticket, d_ke, st));
 
+    it->pool_used = 0;
+    it->marks.clear();
     for (uint64_t step = 0; step < nsteps; step++)
         {
         const uint64_t t = s->timestep;
         const double* rescale = nullptr;
+        cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (it->profiling)
+            {
+            for (int q = 0; q < 5; q++)
+                {
+                it->marks.push_back(it->pool_used);
+                pe[q] = it->next_event();
+                }
+            HB2_CUDA(cudaEventRecord(pe[0], st));
+            }
         if (it->thermostat == 1)
             {
             HB2_CUDA(cudaMemcpyAsync(s->d_timestep, &s->timestep, sizeof(uint64_t),
@@ -1467,15 +1512,73 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             HB2_CUDA(cudaStreamSynchronize(st));
             flag = nl->h_conditions[3] != 0;
             }
-        HB2_TRY(pf->compute(t + 1, check, flag));
+        if (it->profiling)
+            {
+            HB2_CUDA(cudaEventRecord(pe[1], st));
+            s->mid_event = pe[2];
+            }
+        const uint64_t builds_before = nl->num_builds;
+        hb2_status cst = pf->compute(t + 1, check, flag);
+        s->mid_event = nullptr;
+        HB2_TRY(cst);
+        if (it->profiling)
+            {
+            HB2_CUDA(cudaEventRecord(pe[3], st));
+            it->phase_n[1] += nl->num_builds - builds_before;
+            }
         HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, N, (float)it->dt, nullptr, s->d_partial,
                                 s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st));
+        if (it->profiling)
+            HB2_CUDA(cudaEventRecord(pe[4], st));
         s->timestep = t + 1;
         }
     HB2_CUDA(cudaMemcpyAsync(s->d_timestep, &s->timestep, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaEventRecord(it->ev1, st));
     HB2_CUDA(cudaStreamSynchronize(st));
     HB2_CUDA(cudaEventElapsedTime(&it->last_ms, it->ev0, it->ev1));
+    if (it->profiling)
+        {
+        for (size_t k = 0; k + 4 < it->marks.size() + 0 && k < it->marks.size(); k += 5)
+            {
+            cudaEvent_t* e = &it->pool[it->marks[k]];
+            float ab, bc, cd, de;
+            HB2_CUDA(cudaEventElapsedTime(&ab, e[0], e[1]));
+            HB2_CUDA(cudaEventElapsedTime(&bc, e[1], e[2]));
+            HB2_CUDA(cudaEventElapsedTime(&cd, e[2], e[3]));
+            HB2_CUDA(cudaEventElapsedTime(&de, e[3], e[4]));
+            it->phase_ms[0] += ab + de;
+            it->phase_ms[1] += bc;
+            it->phase_ms[2] += cd;
+            it->phase_n[0] += 1;
+            it->phase_n[2] += 1;
+            }
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_set_profiling(hb2_integrator* it, int on)
+    {
+    if (!it)
+        return HB2_ERR_INVALID;
+    it->profiling = on != 0;
+    for (int q = 0; q < 3; q++)
+        {
+        it->phase_ms[q] = 0;
+        it->phase_n[q] = 0;
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_get_profile(hb2_integrator* it, double phase_ms[3],
+                                                 uint64_t phase_n[3])
+    {
+    if (!it || !phase_ms || !phase_n)
+        return HB2_ERR_INVALID;
+    for (int q = 0; q < 3; q++)
+        {
+        phase_ms[q] = it->phase_ms[q];
+        phase_n[q] = it->phase_n[q];
+        }
     return HB2_OK;
     }
 

@@ -7,6 +7,10 @@
 //
 // Arithmetic is fp32 (Scalar = float, the HOOMD_LONGREAL_SIZE=32 layout). Host-side `pack` is the
 // param_type(pybind11::dict) constructor restated over a plain array of user parameters.
+//
+// The built-in evaluators are written branch-free (compute, then select on the cut-off test): in a
+// liquid nearly every warp has a lane inside the cut-off, so a branch only adds divergence
+// bookkeeping; the kernel discards the values of a pair that returns false.
 #pragma once
 #include "common.cuh"
 #include "rng.cuh"
@@ -22,6 +26,14 @@ HB2_DEVICE float rcp_refined(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     const float e = fmaf(-x, y, 1.0f);
     return fmaf(y, e, y);
+    }
+// 1/sqrt(x) to ~0.5 ulp: MUFU.RSQ plus one Newton step.
+HB2_DEVICE float rsqrt_refined(float x)
+    {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float e = fmaf(-x * y, y, 1.0f);
+    return fmaf(0.5f * y, e, y);
     }
 
 // ---------------------------------------------------------------------------------------------
@@ -55,21 +67,18 @@ class EvaluatorPairLJ
     // hoomd/md/EvaluatorPairLJ.h:162-211
     HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
         {
-        if (rsq < rcutsq && lj1 != 0)
+        const bool within = rsq < rcutsq && lj1 != 0;
+        const Scalar r2inv = rcp_refined(rsq);
+        const Scalar r6inv = r2inv * r2inv * r2inv;
+        force_divr = r2inv * r6inv * (Scalar(12.0) * lj1 * r6inv - Scalar(6.0) * lj2);
+        pair_eng = r6inv * (lj1 * r6inv - lj2);
+        if (energy_shift)
             {
-            const Scalar r2inv = rcp_refined(rsq);
-            const Scalar r6inv = r2inv * r2inv * r2inv;
-            force_divr = r2inv * r6inv * (Scalar(12.0) * lj1 * r6inv - Scalar(6.0) * lj2);
-            pair_eng = r6inv * (lj1 * r6inv - lj2);
-            if (energy_shift)
-                {
-                const Scalar rcut2inv = rcp_refined(rcutsq);
-                const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
-                pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
-                }
-            return true;
+            const Scalar rcut2inv = rcp_refined(rcutsq);
+            const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+            pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
             }
-        return false;
+        return within;
         }
     static const char* getName()
         {
@@ -82,7 +91,8 @@ class EvaluatorPairLJ
 
 // ---------------------------------------------------------------------------------------------
 // The pair_plugin example potential V = k/2 (sigma - r)^2
-// (example_plugins/pair_plugin/EvaluatorPairExample.h:94-127)
+// (example_plugins/pair_plugin/EvaluatorPairExample.h:94-127) — kept in the reference's branchy form
+// to show that an unmodified user evaluator works.
 // ---------------------------------------------------------------------------------------------
 class EvaluatorPairExample
     {
@@ -175,37 +185,37 @@ class EvaluatorPairDPDThermoDPD
         }
     HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
         {
-        if (rsq < rcutsq)
-            {
-            const Scalar rinv = rsqrtf(rsq);
-            const Scalar r = Scalar(1.0) / rinv;
-            const Scalar rcutinv = rsqrtf(rcutsq);
-            const Scalar rcut = Scalar(1.0) / rcutinv;
-            force_divr = a * (rinv - rcutinv);
-            pair_eng = a * (rcut - r) - Scalar(0.5) * a * rcutinv * (rcutsq - rsq);
-            return true;
-            }
-        return false;
+        const bool within = rsq < rcutsq;
+        const Scalar rinv = rsqrt_refined(rsq);
+        const Scalar r = rsq * rinv;
+        const Scalar rcutinv = rsqrt_refined(rcutsq);
+        const Scalar rcut = rcutsq * rcutinv;
+        force_divr = a * (rinv - rcutinv);
+        pair_eng = a * (rcut - r) - Scalar(0.5) * a * rcutinv * (rcutsq - rsq);
+        return within;
         }
     HB2_DEVICE bool evalForceEnergyThermo(Scalar& force_divr, Scalar& force_divr_cons,
                                           Scalar& pair_eng, bool energy_shift)
         {
+        // Unlike the LJ case most listed DPD neighbours are OUTSIDE the cut-off (r_cut = 1,
+        // r_list = 1.4: 64 % of the list) and the Philox draw is 40+ integer instructions, so this
+        // one keeps the branch.
         if (rsq < rcutsq)
             {
-            const Scalar rinv = rsqrtf(rsq);
-            const Scalar r = Scalar(1.0) / rinv;
-            const Scalar rcutinv = rsqrtf(rcutsq);
-            const Scalar rcut = Scalar(1.0) / rcutinv;
+            const Scalar rinv = rsqrt_refined(rsq);
+            const Scalar r = rsq * rinv;
+            const Scalar rcutinv = rsqrt_refined(rcutsq);
+            const Scalar rcut = rcutsq * rcutinv;
             const Scalar w = rinv - rcutinv;
             // uniform in (-1,1) from the pair's Philox draw; the top 32 bits carry every bit an
             // fp32 alpha can hold (the fp64 reference uses 64)
             uint32_t w0, w1;
             dpd_pair_bits(m_seed, m_i, m_j, m_timestep, w0, w1);
-            const Scalar alpha = fmaf((Scalar)w0, 4.656612873077393e-10f, -1.0f + 2.3283064e-10f);
+            const Scalar alpha = fmaf((Scalar)w0, 4.656612873077393e-10f, -1.0f);
             force_divr = a * w;
             force_divr_cons = force_divr;
             force_divr -= gamma * m_dot * w * w;
-            force_divr += rsqrtf(m_deltaT / (m_T * gamma * Scalar(6.0))) * w * alpha;
+            force_divr += rsqrt_refined(m_deltaT / (m_T * gamma * Scalar(6.0))) * w * alpha;
             pair_eng = a * (rcut - r) - Scalar(0.5) * a * rcutinv * (rcutsq - rsq);
             return true;
             }

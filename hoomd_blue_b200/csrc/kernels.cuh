@@ -32,6 +32,7 @@ struct NlistBuildArgs
     uint32_t* n_neigh;
     float4* last_pos;           // may be null
     uint32_t* conditions;       // [0] <- max n_neigh
+    uint32_t dummy_index;       // index of the far-away padding particle (pos[N_total])
     };
 hb2_status launch_nlist_build(const NlistBuildArgs& a, const hb2_box& box, cudaStream_t stream);
 

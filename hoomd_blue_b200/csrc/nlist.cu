@@ -3,29 +3,34 @@
 // Replaces NeighborListBinned::buildNlist (hoomd/md/NeighborListBinned.cc:36-179) and
 // gpu_compute_nlist_binned_kernel (hoomd/md/NeighborListGPUBinned.cu:56-298).
 //
-// One warp owns one home cell. It stages the contents of the <= 27 stencil cells (ascending cell id,
-// the order hoomd/CellList.cc:393-400 sorts cell_adj into) as one concatenated candidate array in
-// shared memory with coalesced float4 loads — x-adjacent cells are contiguous in the cell-ordered
-// particle array, so the stencil is at most 9 long runs. Then, for each home particle, the 32 lanes
-// sweep the candidates 32 at a time: fp32 distance with a guard band, the few borderline candidates
-// are re-decided in fp64 with the CPU build's exact operation order (bit-exact membership), and
-// ballot/popc compaction appends the hits to the particle's row in ascending j. No atomics on the
-// data path; the row order is deterministic.
+// One warp owns one home cell.
+//  1. Stencil: lane l < 27 resolves its stencil cell (ascending cell id, the order
+//     hoomd/CellList.cc:393-400 sorts cell_adj into), reads that cell's [start, end) from cell_start
+//     and its periodic image shift; a warp scan lays the cells out back to back.
+//  2. Staging: the cells' float4 positions are copied into shared memory with coalesced loads,
+//     already shifted into the home cell's image (no minimum-image arithmetic in the sweep) and with
+//     the particle index in .w; the tail is padded with far-away dummies up to 32*C candidates.
+//  3. Sweep: lane l owns candidates [l*C, l*C + C) (C odd => conflict-free LDS.128). For TWO home
+//     particles at a time it tests its C candidates in fp32 against a guard band and records hits and
+//     borderline cases as bits of per-lane registers — no ballot, no store inside the sweep.
+//  4. Borderline candidates (a few per million) are re-decided in fp64 with the CPU build's exact
+//     operation order, which makes the pair set bit-exact with the reference.
+//  5. Compaction: one warp scan of popc(hits) per home particle, then every lane appends its own
+//     hits: rows come out in ascending particle index, deterministically, without atomics.
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace hb2
     {
-constexpr int NL_WARPS = 4;  // warps (home cells) per block
-constexpr int NL_CAP = 768;  // staged candidates per warp per round
-constexpr int NL_MAXRUNS = 27;
+constexpr int NL_WARPS = 4;     // warps (home cells) per block
+constexpr int NL_CMAX = 23;     // candidates per lane per round (odd)
+constexpr int NL_CAP = 32 * NL_CMAX;
+constexpr float NL_FAR = 1.0e18f;
 
 struct NlWarpSmem
     {
-    float4 cand[NL_CAP];            // x, y, z, particle index (bits)
-    uint32_t runs[NL_MAXRUNS][2];   // [start, end) particle ranges, ascending
-    uint8_t type[NL_CAP];           // candidate type (MULTITYPE only)
-    uint8_t pad[8];
+    float4 cand[NL_CAP]; // x, y, z (image-shifted), particle index (bits)
+    uint8_t type[NL_CAP];
     };
 
 struct NlConst
@@ -35,54 +40,117 @@ struct NlConst
     float band; // relative guard band of the fp32 distance test
     };
 
-// sorted, de-duplicated periodic neighbours {c-1, c, c+1} of coordinate c on a ring of size dim
-HB2_DEVICE int ring3(int c, int dim, int out[3])
+// k-th (ascending) member of the sorted, de-duplicated periodic neighbourhood {c-1, c, c+1} of
+// coordinate c on a ring of size dim, and the image shift (in units of L) that brings that cell next
+// to c. Returns the neighbourhood size.
+HB2_DEVICE int ring3(int c, int dim, int k, int& coord, int& shift)
     {
+    shift = 0;
     if (dim == 1)
         {
-        out[0] = 0;
+        coord = 0;
         return 1;
         }
     if (dim == 2)
         {
-        out[0] = 0;
-        out[1] = 1;
+        coord = k & 1;
         return 2;
         }
     if (c == 0)
         {
-        out[0] = 0;
-        out[1] = 1;
-        out[2] = dim - 1;
+        coord = (k == 2) ? dim - 1 : k;
+        shift = (k == 2) ? -1 : 0;
         }
     else if (c == dim - 1)
         {
-        out[0] = 0;
-        out[1] = dim - 2;
-        out[2] = dim - 1;
+        coord = (k == 0) ? 0 : dim - 3 + k;
+        shift = (k == 0) ? 1 : 0;
         }
     else
-        {
-        out[0] = c - 1;
-        out[1] = c;
-        out[2] = c + 1;
-        }
+        coord = c - 1 + k;
     return 3;
     }
 
-template<bool MULTITYPE>
+// position of the q-th (0-based) set bit of m (m < 2^24 and popc(m) > q): binary search on popc
+HB2_DEVICE uint32_t nth_set_bit(uint32_t m, uint32_t q)
+    {
+    uint32_t t = 0, c;
+    c = __popc(m & 0xFFFu);
+    if (q >= c)
+        {
+        q -= c;
+        t = 12;
+        m >>= 12;
+        }
+    c = __popc(m & 0x3Fu);
+    if (q >= c)
+        {
+        q -= c;
+        t += 6;
+        m >>= 6;
+        }
+    c = __popc(m & 0x7u);
+    if (q >= c)
+        {
+        q -= c;
+        t += 3;
+        m >>= 3;
+        }
+    c = m & 1u;
+    if (q >= c)
+        {
+        q -= c;
+        t += 1;
+        m >>= 1;
+        }
+    c = m & 1u;
+    if (q >= c)
+        t += 1;
+    return t;
+    }
+
+HB2_DEVICE uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total)
+    {
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+        {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off)
+            incl += t;
+        }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+    }
+
+// MULTITYPE: per-type-pair r_list; SMALLDIM: some grid dimension < 3, so a stencil cell can hold
+// both images of a neighbour and the sweep applies the minimum image itself.
+template<bool MULTITYPE, bool SMALLDIM>
 __global__ void __launch_bounds__(NL_WARPS * 32)
     nlist_build_kernel(const float4* __restrict__ pos, uint32_t N, uint3 dim,
                        const uint32_t* __restrict__ cell_start,
                        const double* __restrict__ r_listsq, uint32_t ntypes, double r_listsq_single,
                        NlConst cst, uint32_t* __restrict__ nlist, uint32_t pitch,
                        uint32_t* __restrict__ n_neigh, float4* __restrict__ last_pos,
-                       uint32_t* __restrict__ conditions)
+                       uint32_t* __restrict__ conditions, uint32_t dummy_index)
     {
     extern __shared__ __align__(16) unsigned char s_raw[];
     NlWarpSmem& sm = reinterpret_cast<NlWarpSmem*>(s_raw)[threadIdx.x >> 5];
+    // per-type-pair (lo, hi) thresholds of the fp32 test, after the per-warp regions
+    float2* s_thr = reinterpret_cast<float2*>(s_raw + sizeof(NlWarpSmem) * NL_WARPS);
 
     const int lane = threadIdx.x & 31;
+    const float band = cst.band;
+    if (MULTITYPE)
+        {
+        for (uint32_t t = threadIdx.x; t < ntypes * ntypes; t += blockDim.x)
+            {
+            const float rl2 = (float)r_listsq[t];
+            s_thr[t] = make_float2(rl2 * (1.0f - band), rl2 * (1.0f + band));
+            }
+        __syncthreads();
+        }
+
     const uint32_t Nc = dim.x * dim.y * dim.z;
     const uint32_t cell = blockIdx.x * NL_WARPS + (threadIdx.x >> 5);
     if (cell >= Nc)
@@ -92,131 +160,275 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
     if (h0 >= hend)
         return;
 
-    // --- the stencil as ascending [start,end) runs; x-neighbours merge when contiguous
-    int nruns = 0;
-    if (lane == 0)
+    // ---- 1. stencil cells, one per lane, ascending cell id
+    const int cx = cell % dim.x, cy = (cell / dim.x) % dim.y, cz = cell / (dim.x * dim.y);
+    int dummy_c, dummy_s;
+    const int cnx = ring3(cx, dim.x, 0, dummy_c, dummy_s);
+    const int cny = ring3(cy, dim.y, 0, dummy_c, dummy_s);
+    const int cnz = ring3(cz, dim.z, 0, dummy_c, dummy_s);
+    const int ncells = cnx * cny * cnz;
+    uint32_t c_start = 0, c_cnt = 0;
+    float shx = 0.f, shy = 0.f, shz = 0.f;
+    bool is_home = false;
+    if (lane < ncells)
         {
-        const int cx = cell % dim.x, cy = (cell / dim.x) % dim.y, cz = cell / (dim.x * dim.y);
-        int nx[3], ny[3], nz[3];
-        const int cnx = ring3(cx, dim.x, nx), cny = ring3(cy, dim.y, ny),
-                  cnz = ring3(cz, dim.z, nz);
-        for (int a = 0; a < cnz; a++)
-            for (int b = 0; b < cny; b++)
-                {
-                const uint32_t row = ((uint32_t)nz[a] * dim.y + (uint32_t)ny[b]) * dim.x;
-                for (int c = 0; c < cnx; c++)
-                    {
-                    const uint32_t s = cell_start[row + nx[c]], e = cell_start[row + nx[c] + 1];
-                    if (e <= s)
-                        continue;
-                    if (nruns > 0 && sm.runs[nruns - 1][1] == s)
-                        sm.runs[nruns - 1][1] = e; // contiguous with the previous run
-                    else
-                        {
-                        sm.runs[nruns][0] = s;
-                        sm.runs[nruns][1] = e;
-                        nruns++;
-                        }
-                    }
-                }
+        const int kx = lane % cnx, ky = (lane / cnx) % cny, kz = lane / (cnx * cny);
+        int nx, ny, nz, sx, sy, sz;
+        ring3(cx, dim.x, kx, nx, sx);
+        ring3(cy, dim.y, ky, ny, sy);
+        ring3(cz, dim.z, kz, nz, sz);
+        const uint32_t cid = ((uint32_t)nz * dim.y + (uint32_t)ny) * dim.x + (uint32_t)nx;
+        c_start = __ldg(cell_start + cid);
+        c_cnt = __ldg(cell_start + cid + 1) - c_start;
+        shx = (float)sx * cst.bf.L[0];
+        shy = (float)sy * cst.bf.L[1];
+        shz = (float)sz * cst.bf.L[2];
+        is_home = (cid == cell);
         }
-    nruns = __shfl_sync(0xffffffffu, nruns, 0);
-    __syncwarp();
+    uint32_t T;
+    const uint32_t c_off = warp_excl_scan(c_cnt, lane, T);
+    const uint32_t home_off = __shfl_sync(0xffffffffu, c_off, __ffs(__ballot_sync(0xffffffffu, is_home)) - 1);
 
-    const float band = cst.band;
     const float rl2_1 = (float)r_listsq_single;
     const float rl2_lo1 = rl2_1 * (1.0f - band), rl2_hi1 = rl2_1 * (1.0f + band);
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const float Lx = cst.bf.L[0], Ly = cst.bf.L[1], Lz = cst.bf.L[2];
     const float hx = cst.bf.hi[0], hy = cst.bf.hi[1], hz = cst.bf.hi[2];
 
-    int run = 0;
-    uint32_t run_off = 0; // progress inside runs[run]
-    bool first_round = true;
     uint32_t max_n = 0;
-    while (run < nruns)
+    // ---- rounds of at most NL_CAP staged candidates (one round unless the stencil is very full)
+    for (uint32_t r0 = 0; r0 < T; r0 += NL_CAP)
         {
-        // ---- stage up to NL_CAP candidates (coalesced float4 loads of contiguous runs)
-        uint32_t ncand = 0;
-        while (run < nruns && ncand < NL_CAP)
+        const uint32_t r1 = min(T, r0 + NL_CAP);
+        const uint32_t ncand = r1 - r0;
+        // ---- 2. staging (cells intersecting [r0, r1)): batches of 9 cells so that nine independent
+        // coalesced loads are in flight per lane before the first shared-memory store
+        auto stage = [&](uint32_t q, uint32_t j, float4 p, float sx, float sy, float sz)
+        {
+            if (MULTITYPE)
+                sm.type[q - r0] = (uint8_t)__float_as_uint(p.w);
+            if (!SMALLDIM)
+                {
+                p.x += sx;
+                p.y += sy;
+                p.z += sz;
+                }
+            p.w = __uint_as_float(j);
+            sm.cand[q - r0] = p;
+        };
+        for (int c0 = 0; c0 < ncells; c0 += 9)
             {
-            const uint32_t s = sm.runs[run][0] + run_off, e = sm.runs[run][1];
-            const uint32_t take = min(e - s, (uint32_t)NL_CAP - ncand);
-            for (uint32_t k = lane; k < take; k += 32)
+            float4 v[9];
+            bool ok[9];
+#pragma unroll
+            for (int u = 0; u < 9; u++)
                 {
-                float4 p = __ldg(pos + s + k);
-                if (MULTITYPE)
-                    sm.type[ncand + k] = (uint8_t)__float_as_uint(p.w);
-                p.w = __uint_as_float(s + k);
-                sm.cand[ncand + k] = p;
+                const int c = min(c0 + u, 31);
+                const uint32_t s = __shfl_sync(0xffffffffu, c_start, c);
+                const uint32_t cnt = __shfl_sync(0xffffffffu, c_cnt, c);
+                const uint32_t q = __shfl_sync(0xffffffffu, c_off, c) + lane;
+                ok[u] = (c0 + u < ncells) && ((uint32_t)lane < cnt) && q >= r0 && q < r1;
+                v[u] = ok[u] ? __ldg(pos + s + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            ncand += take;
-            if (s + take == e)
+#pragma unroll
+            for (int u = 0; u < 9; u++)
                 {
-                run++;
-                run_off = 0;
+                const int c = min(c0 + u, 31);
+                const uint32_t s = __shfl_sync(0xffffffffu, c_start, c);
+                const uint32_t cnt = __shfl_sync(0xffffffffu, c_cnt, c);
+                const uint32_t off = __shfl_sync(0xffffffffu, c_off, c);
+                const float sx = __shfl_sync(0xffffffffu, shx, c);
+                const float sy = __shfl_sync(0xffffffffu, shy, c);
+                const float sz = __shfl_sync(0xffffffffu, shz, c);
+                if (ok[u])
+                    stage(off + lane, s + lane, v[u], sx, sy, sz);
+                if (c0 + u < ncells && cnt > 32) // crowded cell: the rest, one load at a time
+                    for (uint32_t k = 32 + lane; k < cnt; k += 32)
+                        if (off + k >= r0 && off + k < r1)
+                            stage(off + k, s + k, __ldg(pos + s + k), sx, sy, sz);
                 }
-            else
-                run_off += take;
+            }
+        // lane-blocked ownership: C candidates per lane, C odd (bank-conflict-free float4 reads)
+        const uint32_t C = ((ncand + 31) >> 5) | 1u;
+        for (uint32_t q = ncand + lane; q < 32 * C; q += 32)
+            {
+            sm.cand[q] = make_float4(NL_FAR, NL_FAR, NL_FAR, __uint_as_float(0xffffffffu));
+            if (MULTITYPE)
+                sm.type[q] = 0;
             }
         __syncwarp();
+        const float4* __restrict__ mine = sm.cand + lane * C;
+        const uint8_t* __restrict__ mine_t = sm.type + lane * C;
 
-        // ---- every home particle sweeps the staged candidates
-        for (uint32_t i = h0; i < hend; i++)
+        // ---- 3./4./5. two home particles per sweep
+        for (uint32_t ia = h0; ia < hend; ia += 2)
             {
-            const float4 pi = __ldg(pos + i);
-            const uint32_t ti = MULTITYPE ? __float_as_uint(pi.w) : 0u;
-            uint32_t n = first_round ? 0u : n_neigh[i];
-            uint32_t* __restrict__ row = nlist + (size_t)i * pitch;
-            for (uint32_t k0 = 0; k0 < ncand; k0 += 32)
+            const bool has_b = ia + 1 < hend;
+            const uint32_t ib = has_b ? ia + 1 : ia;
+            // the home cell is part of its own stencil with zero shift: read the home particles
+            // from shared memory when this round staged them (no global latency in the loop)
+            const uint32_t ka = home_off + (ia - h0), kb = home_off + (ib - h0);
+            const bool sa = ka >= r0 && ka < r1, sb = kb >= r0 && kb < r1;
+            const float4 pa = sa ? sm.cand[ka - r0] : __ldg(pos + ia);
+            const float4 pb = sb ? sm.cand[kb - r0] : __ldg(pos + ib);
+            uint32_t ta = 0u, tb = 0u;
+            if (MULTITYPE)
                 {
-                const uint32_t k = k0 + lane;
-                bool hit = false;
-                uint32_t j = 0;
-                if (k < ncand)
-                    {
-                    const float4 c = sm.cand[k];
-                    j = __float_as_uint(c.w);
-                    const float dx = min_image_f(pi.x - c.x, Lx, hx);
-                    const float dy = min_image_f(pi.y - c.y, Ly, hy);
-                    const float dz = min_image_f(pi.z - c.z, Lz, hz);
-                    const float rsq = dx * dx + dy * dy + dz * dz;
-                    float lo = rl2_lo1, hi = rl2_hi1;
-                    uint32_t tp = 0;
-                    if (MULTITYPE)
-                        {
-                        tp = (uint32_t)sm.type[k] * ntypes + ti;
-                        const float rl2 = (float)r_listsq[tp];
-                        lo = rl2 * (1.0f - band);
-                        hi = rl2 * (1.0f + band);
-                        }
-                    if (rsq <= hi && hi > 0.0f && j != i)
-                        {
-                        if (rsq < lo)
-                            hit = true;
-                        else
-                            {
-                            // borderline: decide exactly as the fp64 CPU build does
-                            float4 pj = c;
-                            const double rl2d = MULTITYPE ? r_listsq[tp] : r_listsq_single;
-                            hit = dist_sq_exact(cst.bd, pi, pj) <= rl2d;
-                            }
-                        }
-                    }
-                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                if (hit)
-                    {
-                    const uint32_t slot = n + __popc(mask & lt_mask);
-                    if (slot < pitch)
-                        row[slot] = j;
-                    }
-                n += __popc(mask);
+                ta = sa ? (uint32_t)sm.type[ka - r0] : __float_as_uint(pa.w);
+                tb = sb ? (uint32_t)sm.type[kb - r0] : __float_as_uint(pb.w);
                 }
+
+            // Distances are non-negative floats, so their bit patterns order like integers: the sign
+            // bit of (bits(r) - bits(threshold)) is the comparison result, and a funnel shift pushes it
+            // into the per-lane mask — two integer instructions per test, no predicates, no branches.
+            // (The masks come out bit-reversed: candidate t lands in bit C-1-t; fixed up after the loop.)
+            uint32_t in_a = 0, in_b = 0, cd_a = 0, cd_b = 0;
+            int lo_a = __float_as_int(rl2_lo1), hi_a = __float_as_int(rl2_hi1) + 1;
+            int lo_b = lo_a, hi_b = hi_a;
+#pragma unroll 4
+            for (uint32_t t = 0; t < C; t++)
+                {
+                const float4 c = mine[t];
+                float ax = pa.x - c.x, ay = pa.y - c.y, az = pa.z - c.z;
+                float bx = pb.x - c.x, by = pb.y - c.y, bz = pb.z - c.z;
+                if (SMALLDIM)
+                    {
+                    ax = min_image_f(ax, Lx, hx);
+                    ay = min_image_f(ay, Ly, hy);
+                    az = min_image_f(az, Lz, hz);
+                    bx = min_image_f(bx, Lx, hx);
+                    by = min_image_f(by, Ly, hy);
+                    bz = min_image_f(bz, Lz, hz);
+                    }
+                const int ra = __float_as_int(ax * ax + ay * ay + az * az);
+                const int rb = __float_as_int(bx * bx + by * by + bz * bz);
+                if (MULTITYPE)
+                    {
+                    const uint32_t tc = mine_t[t];
+                    const float2 tha = s_thr[tc * ntypes + ta], thb = s_thr[tc * ntypes + tb];
+                    lo_a = __float_as_int(tha.x);
+                    hi_a = __float_as_int(tha.y) + 1;
+                    lo_b = __float_as_int(thb.x);
+                    hi_b = __float_as_int(thb.y) + 1;
+                    }
+                in_a = __funnelshift_l((uint32_t)(ra - lo_a), in_a, 1); // r <  lo : certainly inside
+                cd_a = __funnelshift_l((uint32_t)(ra - hi_a), cd_a, 1); // r <= hi : candidate
+                in_b = __funnelshift_l((uint32_t)(rb - lo_b), in_b, 1);
+                cd_b = __funnelshift_l((uint32_t)(rb - hi_b), cd_b, 1);
+                }
+            uint32_t hit_a = __brev(in_a) >> (32u - C), hit_b = __brev(in_b) >> (32u - C);
+            uint32_t may_a = (__brev(cd_a) >> (32u - C)) & ~hit_a;
+            uint32_t may_b = (__brev(cd_b) >> (32u - C)) & ~hit_b;
+            // a particle is not its own neighbour (hoomd/md/NeighborListBinned.cc:144)
+            if (sa)
+                {
+                const uint32_t ks = ka - r0;
+                if (ks / C == (uint32_t)lane)
+                    {
+                    hit_a &= ~(1u << (ks % C));
+                    may_a &= ~(1u << (ks % C));
+                    }
+                }
+            if (sb)
+                {
+                const uint32_t ks = kb - r0;
+                if (ks / C == (uint32_t)lane)
+                    {
+                    hit_b &= ~(1u << (ks % C));
+                    may_b &= ~(1u << (ks % C));
+                    }
+                }
+            // ---- 4. borderline: decide exactly as the fp64 CPU build does
+            if (__any_sync(0xffffffffu, (may_a | may_b) != 0u))
+                {
+                while (may_a)
+                    {
+                    const uint32_t t = __ffs(may_a) - 1;
+                    may_a &= may_a - 1;
+                    const uint32_t j = __float_as_uint(mine[t].w);
+                    if (j == 0xffffffffu)
+                        continue;
+                    const float4 pj = __ldg(pos + j);
+                    const double rl2d = MULTITYPE ? r_listsq[__float_as_uint(pj.w) * ntypes + ta]
+                                                  : r_listsq_single;
+                    if (rl2d > 0.0 && dist_sq_exact(cst.bd, pa, pj) <= rl2d)
+                        hit_a |= 1u << t;
+                    }
+                while (may_b)
+                    {
+                    const uint32_t t = __ffs(may_b) - 1;
+                    may_b &= may_b - 1;
+                    const uint32_t j = __float_as_uint(mine[t].w);
+                    if (j == 0xffffffffu)
+                        continue;
+                    const float4 pj = __ldg(pos + j);
+                    const double rl2d = MULTITYPE ? r_listsq[__float_as_uint(pj.w) * ntypes + tb]
+                                                  : r_listsq_single;
+                    if (rl2d > 0.0 && dist_sq_exact(cst.bd, pb, pj) <= rl2d)
+                        hit_b |= 1u << t;
+                    }
+                }
+            if (!has_b)
+                hit_b = 0;
+
+            // ---- 5. compaction, output-parallel: lane l of pass p writes row slot 32 p + l. It finds
+            // the lane that owns that slot by binary search over the exclusive scan of the per-lane
+            // hit counts (shuffles), fetches that lane's hit mask and picks the right set bit. Every
+            // pass is one fully coalesced 128-byte store, ascending candidate order == ascending
+            // particle index, and slots past the last hit are filled with the dummy particle's index
+            // so that rows are padded to a multiple of 32 for the force kernel.
+            uint32_t tot_a, tot_b;
+            const uint32_t off_a = warp_excl_scan(__popc(hit_a), lane, tot_a);
+            const uint32_t off_b = warp_excl_scan(__popc(hit_b), lane, tot_b);
+            uint32_t base_a = 0, base_b = 0;
+            if (r0 > 0)
+                {
+                base_a = n_neigh[ia];
+                base_b = n_neigh[ib];
+                }
+            const bool last_round = (r1 == T);
+            auto emit = [&](const uint32_t hit, const uint32_t off, const uint32_t tot,
+                            const uint32_t base, uint32_t* __restrict__ rowp)
+            {
+                // slots [base, base + tot) receive this round's hits; on the last round the tail of
+                // the final 32-slot group receives the dummy index
+                const uint32_t end = last_round ? ((base + tot + 31u) & ~31u) : base + tot;
+                for (uint32_t s0 = base & ~31u; s0 < end; s0 += 32)
+                    {
+                    const uint32_t slot = s0 + lane;
+                    const uint32_t r = slot - base; // rank of the hit this slot wants (if any)
+                    // source lane: the last lane whose exclusive offset is <= r
+                    uint32_t src = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1)
+                        {
+                        const uint32_t probe = __shfl_sync(0xffffffffu, off, (src + step) & 31);
+                        if (probe <= r)
+                            src += step;
+                        }
+                    const uint32_t m = __shfl_sync(0xffffffffu, hit, src);
+                    const uint32_t o = __shfl_sync(0xffffffffu, off, src);
+                    uint32_t val = dummy_index;
+                    const bool have = slot >= base && r < tot;
+                    if (have)
+                        {
+                        const uint32_t t = nth_set_bit(m, r - o);
+                        val = __float_as_uint(sm.cand[src * C + t].w);
+                        }
+                    if (slot >= base && slot < end && slot < pitch)
+                        rowp[slot] = val;
+                    }
+            };
+            emit(hit_a, off_a, tot_a, base_a, nlist + (size_t)ia * pitch);
+            if (has_b)
+                emit(hit_b, off_b, tot_b, base_b, nlist + (size_t)ib * pitch);
             if (lane == 0)
-                n_neigh[i] = n;
-            max_n = max(max_n, n);
+                {
+                n_neigh[ia] = base_a + tot_a;
+                if (has_b)
+                    n_neigh[ib] = base_b + tot_b;
+                }
+            max_n = max(max_n, max(base_a + tot_a, base_b + tot_b));
             }
-        first_round = false;
         __syncwarp();
         }
 
@@ -227,57 +439,55 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
         atomicMax(&conditions[0], max_n);
     }
 
+template<bool MT, bool SD>
+static hb2_status launch_variant(const NlistBuildArgs& a, const NlConst& cst, cudaStream_t stream)
+    {
+    const uint32_t Nc = a.dim.x * a.dim.y * a.dim.z;
+    const uint32_t blocks = (Nc + NL_WARPS - 1) / NL_WARPS;
+    const size_t smem = sizeof(NlWarpSmem) * NL_WARPS + sizeof(float2) * (MT ? a.ntypes * a.ntypes : 1);
+    static bool attr = false;
+    static size_t attr_smem = 0;
+    if (!attr || smem > attr_smem)
+        {
+        HB2_CUDA(cudaFuncSetAttribute(nlist_build_kernel<MT, SD>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+        attr_smem = smem;
+        }
+    nlist_build_kernel<MT, SD><<<blocks, NL_WARPS * 32, smem, stream>>>(
+        a.pos, a.N, a.dim, a.cell_start, a.r_listsq, a.ntypes, a.r_listsq_single, cst, a.nlist,
+        a.pitch, a.n_neigh, a.last_pos, a.conditions, a.dummy_index);
+    HB2_CHECK_LAUNCH("nlist_build_kernel");
+    return HB2_OK;
+    }
+
 hb2_status launch_nlist_build(const NlistBuildArgs& a, const hb2_box& box, cudaStream_t stream)
     {
     if (a.N == 0)
         return HB2_OK;
-    if (a.ntypes > 255)
+    if (a.ntypes > 64)
         {
-        set_error("nlist build: at most 255 particle types are supported");
+        set_error("nlist build: at most 64 particle types are supported");
         return HB2_ERR_INVALID;
         }
     NlConst cst;
     cst.bf = boxf(box);
     cst.bd = boxd(box);
-    // fp32 error model of rsq (DESIGN.md "guard band"): |d| carries <= 2^-23 Lmax absolute error,
-    // so rsq carries <= 2 sqrt(3) r 2^-23 Lmax + 2^-22 rsq; the band is twice that, relative to the
-    // smallest r_list^2 in use.
+    // fp32 error model of rsq (DESIGN.md "guard band"): each component of the separation carries at
+    // most 2^-23 Lmax absolute error (one rounding of a difference of magnitude <= Lmax, one of the
+    // image shift), so rsq carries <= 2 sqrt(3) r 2^-23 Lmax + 2^-22 rsq. The band is twice that,
+    // relative to the smallest r_list in use.
     const double rl_min = a.r_list_min > 0 ? a.r_list_min : 1.0;
     double band = 2.0 * (2.0 * 1.7320508 * ldexp(1.0, -23) * (double)a.Lmax / rl_min + ldexp(1.0, -22));
     if (band > 0.25)
         band = 0.25;
     cst.band = (float)band;
 
-    const uint32_t Nc = a.dim.x * a.dim.y * a.dim.z;
-    const uint32_t blocks = (Nc + NL_WARPS - 1) / NL_WARPS;
-    const size_t smem = sizeof(NlWarpSmem) * NL_WARPS;
+    const bool small = a.dim.x < 3 || a.dim.y < 3 || a.dim.z < 3;
     if (a.ntypes > 1)
-        {
-        static bool attr = false;
-        if (!attr)
-            {
-            HB2_CUDA(cudaFuncSetAttribute(nlist_build_kernel<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-            }
-        nlist_build_kernel<true><<<blocks, NL_WARPS * 32, smem, stream>>>(
-            a.pos, a.N, a.dim, a.cell_start, a.r_listsq, a.ntypes, a.r_listsq_single, cst, a.nlist,
-            a.pitch, a.n_neigh, a.last_pos, a.conditions);
-        }
-    else
-        {
-        static bool attr = false;
-        if (!attr)
-            {
-            HB2_CUDA(cudaFuncSetAttribute(nlist_build_kernel<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-            }
-        nlist_build_kernel<false><<<blocks, NL_WARPS * 32, smem, stream>>>(
-            a.pos, a.N, a.dim, a.cell_start, a.r_listsq, a.ntypes, a.r_listsq_single, cst, a.nlist,
-            a.pitch, a.n_neigh, a.last_pos, a.conditions);
-        }
-    HB2_CHECK_LAUNCH("nlist_build_kernel");
-    return HB2_OK;
+        return small ? launch_variant<true, true>(a, cst, stream)
+                     : launch_variant<true, false>(a, cst, stream);
+    return small ? launch_variant<false, true>(a, cst, stream)
+                 : launch_variant<false, false>(a, cst, stream);
     }
     } // namespace hb2

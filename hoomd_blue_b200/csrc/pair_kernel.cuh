@@ -4,11 +4,19 @@
 // gpu_compute_pair_forces_shared_kernel (hoomd/md/PotentialPairGPU.cuh:146-404), and the DPD
 // variants (hoomd/md/PotentialPairDPDThermo.h:102-268, hoomd/md/PotentialPairDPDThermoGPU.cuh:148-330).
 //
-// TPP lanes share one particle: they stride over its neighbour row (coalesced u32 loads — rows are
-// pitch-aligned and ascending in j, and the particles are in cell order, so the float4 position
-// gathers of adjacent lanes fall into a handful of 128-byte lines), evaluate the pair in fp32,
-// and combine with __shfl_xor. Owner-computes on a full list: no atomics, fixed reduction tree,
-// bitwise reproducible. Each visit adds E/2 and (F/r) dx_a dx_b / 2 to the visiting particle only
+// Layout contract with the build kernel (nlist.cu): row i starts at nlist + i * pitch, pitch is a
+// multiple of 32, entries are ascending in j and the row is padded to a multiple of 32 with the index
+// of a far-away dummy particle (pos[N_total]), so the loop has no tail handling and never tests
+// k < n_neigh.
+//
+// TPP lanes share one particle. One loop iteration consumes a 32-entry chunk of the row: for
+// u = 0 .. 32/TPP-1 lane `sub` takes entry u*TPP + sub. The index loads of the TPP lanes are one
+// coalesced 4*TPP-byte segment, and — because rows are ascending and the particles are in cell order —
+// the TPP position gathers issued by one instruction fall on TPP nearly consecutive particles, i.e. on
+// one or two 128-byte lines. All 32/TPP index loads, then all gathers, are issued before the first
+// pair is evaluated (memory-level parallelism), and the next chunk's indices are prefetched.
+// Owner-computes on a full list: no atomics, fixed __shfl_xor reduction tree, bitwise reproducible.
+// Each visit adds E/2 and (F/r) dx_a dx_b / 2 to the visiting particle only
 // (hoomd/md/PotentialPairGPU.cuh:365-370, hoomd/md/PotentialPair.h:739-752).
 #pragma once
 #include "common.cuh"
@@ -42,16 +50,17 @@ template<class Ev> struct PairKArgs
     const uint64_t* d_timestep;
     uint64_t timestep;
     float dt, kT;
-    int energy_shift;
     float face_margin; // r_list_max + buffer: farther than this from every face => no image shifts
     BoxF box;
     BoxD boxd;
     };
 
-template<class Ev, bool XPLOR, bool VIRIAL, int TPP, bool ONETYPE>
+// MODE: 0 none, 1 shift, 2 xplor (hoomd/md/PotentialPair.h:104-109)
+template<class Ev, int MODE, bool VIRIAL, int TPP, bool ONETYPE>
 __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<Ev> a)
     {
     typedef typename Ev::param_type param_type;
+    constexpr int U = 32 / TPP; // entries per lane per 32-entry chunk
     __shared__ param_type s_params[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_rcutsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_ronsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
@@ -99,7 +108,8 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
         {
         const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
         const uint32_t n = __ldg(a.n_neigh + i);
-        const uint32_t* __restrict__ row = a.nlist + (size_t)i * a.pitch;
+        const uint32_t* __restrict__ row = a.nlist + (size_t)i * a.pitch + sub;
+        const uint32_t nchunks = (n + 31u) >> 5;
 
         float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t tagi = 0;
@@ -126,8 +136,8 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
                 ronsq = s_ronsq[tp];
                 prm = &s_params[tp];
                 }
-            bool energy_shift = a.energy_shift != 0;
-            if (XPLOR)
+            bool energy_shift = (MODE == 1);
+            if (MODE == 2)
                 energy_shift = ronsq > rcutsq; // hoomd/md/PotentialPair.h:697-700
 
             float force_divr = 0.f, force_divr_cons = 0.f, pair_eng = 0.f;
@@ -150,56 +160,47 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
                 evaluated = eval.evalForceAndEnergy(force_divr, pair_eng, energy_shift);
                 force_divr_cons = force_divr;
                 }
-            if (evaluated)
+            if (MODE == 2)
                 {
-                if (XPLOR)
+                // hoomd/md/PotentialPair.h:711-737
+                if (evaluated && rsq >= ronsq && rsq < rcutsq)
                     {
-                    // hoomd/md/PotentialPair.h:711-737
-                    if (rsq >= ronsq && rsq < rcutsq)
-                        {
-                        const float old_eng = pair_eng, old_f = force_divr;
-                        const float d = rcutsq - ronsq;
-                        const float denom_inv = 1.0f / (d * d * d);
-                        const float m = rsq - rcutsq;
-                        const float s = m * m * (rcutsq + 2.0f * rsq - 3.0f * ronsq) * denom_inv;
-                        const float ds = 12.0f * (rsq - ronsq) * m * denom_inv;
-                        pair_eng = old_eng * s;
-                        force_divr = s * old_f - ds * old_eng;
-                        force_divr_cons = force_divr;
-                        }
+                    const float old_eng = pair_eng, old_f = force_divr;
+                    const float d = rcutsq - ronsq;
+                    const float denom_inv = 1.0f / (d * d * d);
+                    const float m = rsq - rcutsq;
+                    const float s = m * m * (rcutsq + 2.0f * rsq - 3.0f * ronsq) * denom_inv;
+                    const float ds = 12.0f * (rsq - ronsq) * m * denom_inv;
+                    pair_eng = old_eng * s;
+                    force_divr = s * old_f - ds * old_eng;
+                    force_divr_cons = force_divr;
                     }
-                fx += dx * force_divr;
-                fy += dy * force_divr;
-                fz += dz * force_divr;
-                pe += pair_eng * 0.5f;
-                if (VIRIAL)
-                    {
-                    const float f2 = 0.5f * force_divr_cons;
-                    vxx += f2 * dx * dx;
-                    vxy += f2 * dx * dy;
-                    vxz += f2 * dx * dz;
-                    vyy += f2 * dy * dy;
-                    vyz += f2 * dy * dz;
-                    vzz += f2 * dz * dz;
-                    }
+                }
+            // branch-free accumulation: a pair beyond the cut-off (or the row padding) adds zeros
+            force_divr = evaluated ? force_divr : 0.f;
+            pair_eng = evaluated ? pair_eng : 0.f;
+            fx += dx * force_divr;
+            fy += dy * force_divr;
+            fz += dz * force_divr;
+            pe += pair_eng * 0.5f;
+            if (VIRIAL)
+                {
+                const float f2 = evaluated ? 0.5f * force_divr_cons : 0.f;
+                vxx += f2 * dx * dx;
+                vxy += f2 * dx * dy;
+                vxz += f2 * dx * dz;
+                vyy += f2 * dy * dy;
+                vyz += f2 * dy * dz;
+                vzz += f2 * dz * dz;
                 }
         };
 
-        if (!warp_shift)
+        // (hi, lo) of pi - L and pi + L per component (only the face-shifting loop uses them)
+        float mh[3], ml[3], ph[3], pl[3];
+        const float pc[3] = {pi.x, pi.y, pi.z};
+        const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
+        if (warp_shift)
             {
-#pragma unroll 2
-            for (uint32_t k = sub; k < n; k += TPP)
-                {
-                const uint32_t j = __ldg(row + k);
-                const float4 pj = __ldg(a.pos + j);
-                pair_body(j, pj, pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                }
-            }
-        else
-            {
-            // (hi, lo) of pi - L and pi + L per component
-            float mh[3], ml[3], ph[3], pl[3];
-            const float pc[3] = {pi.x, pi.y, pi.z};
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 {
@@ -210,25 +211,55 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
                 ph[c] = (float)p;
                 pl[c] = (float)(p - (double)ph[c]);
                 }
-            const float hx = a.box.hi[0], hy = a.box.hi[1], hz = a.box.hi[2];
-#pragma unroll 2
-            for (uint32_t k = sub; k < n; k += TPP)
-                {
-                const uint32_t j = __ldg(row + k);
-                const float4 pj = __ldg(a.pos + j);
-                float d[3];
-                const float qc[3] = {pj.x, pj.y, pj.z};
-                const float hc[3] = {hx, hy, hz};
+            }
+
+        uint32_t jn[U];
+        if (nchunks > 0)
+            {
 #pragma unroll
-                for (int c = 0; c < 3; c++)
+            for (int u = 0; u < U; u++)
+                jn[u] = __ldg(row + u * TPP);
+            }
+        for (uint32_t c = 0; c < nchunks; c++)
+            {
+            uint32_t j[U];
+            float4 pj[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                j[u] = jn[u];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                pj[u] = __ldg(a.pos + j[u]);
+            if (c + 1 < nchunks)
+                {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    jn[u] = __ldg(row + (c + 1) * 32 + u * TPP);
+                }
+            if (!warp_shift)
+                {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    pair_body(j[u], pj[u], pi.x - pj[u].x, pi.y - pj[u].y, pi.z - pj[u].z);
+                }
+            else
+                {
+#pragma unroll
+                for (int u = 0; u < U; u++)
                     {
-                    const float d0 = pc[c] - qc[c];
-                    const bool um = d0 >= hc[c], up = d0 < -hc[c];
-                    const float h = um ? mh[c] : (up ? ph[c] : pc[c]);
-                    const float l = um ? ml[c] : (up ? pl[c] : 0.0f);
-                    d[c] = (h - qc[c]) + l;
+                    float d[3];
+                    const float qc[3] = {pj[u].x, pj[u].y, pj[u].z};
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        {
+                        const float d0 = pc[q] - qc[q];
+                        const bool um = d0 >= hc[q], up = d0 < -hc[q];
+                        const float h = um ? mh[q] : (up ? ph[q] : pc[q]);
+                        const float l = um ? ml[q] : (up ? pl[q] : 0.0f);
+                        d[q] = (h - qc[q]) + l;
+                        }
+                    pair_body(j[u], pj[u], d[0], d[1], d[2]);
                     }
-                pair_body(j, pj, d[0], d[1], d[2]);
                 }
             }
         }
@@ -266,40 +297,43 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
         }
     }
 
-template<class Ev, bool XPLOR, bool VIRIAL, int TPP>
+template<class Ev, int MODE, bool VIRIAL, int TPP>
 hb2_status pair_launch_tpp(const PairKArgs<Ev>& k, cudaStream_t stream)
     {
     const uint64_t threads = (uint64_t)k.N * TPP;
     const uint32_t blocks = (uint32_t)((threads + PAIR_BLOCK - 1) / PAIR_BLOCK);
     if (k.ntypes == 1)
-        pair_force_kernel<Ev, XPLOR, VIRIAL, TPP, true><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
+        pair_force_kernel<Ev, MODE, VIRIAL, TPP, true><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
     else
-        pair_force_kernel<Ev, XPLOR, VIRIAL, TPP, false><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
+        pair_force_kernel<Ev, MODE, VIRIAL, TPP, false><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
     HB2_CHECK_LAUNCH("pair_force_kernel");
     return HB2_OK;
     }
 
-template<class Ev, bool XPLOR, bool VIRIAL>
+template<class Ev, int MODE, bool VIRIAL>
 hb2_status pair_launch(const PairKArgs<Ev>& k, uint32_t tpp, cudaStream_t stream)
     {
     switch (tpp)
         {
-    case 1:
-        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 1>(k, stream);
-    case 2:
-        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 2>(k, stream);
     case 4:
-        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 4>(k, stream);
+        return pair_launch_tpp<Ev, MODE, VIRIAL, 4>(k, stream);
     case 8:
-        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 8>(k, stream);
+        return pair_launch_tpp<Ev, MODE, VIRIAL, 8>(k, stream);
     case 16:
-        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 16>(k, stream);
+        return pair_launch_tpp<Ev, MODE, VIRIAL, 16>(k, stream);
     case 32:
-        return pair_launch_tpp<Ev, XPLOR, VIRIAL, 32>(k, stream);
+        return pair_launch_tpp<Ev, MODE, VIRIAL, 32>(k, stream);
     default:
-        set_error("threads_per_particle must be a power of two in [1, 32]");
+        set_error("threads_per_particle must be 4, 8, 16 or 32");
         return HB2_ERR_INVALID;
         }
+    }
+
+template<class Ev, int MODE>
+hb2_status pair_launch_mode(const PairKArgs<Ev>& k, bool virial, uint32_t tpp, cudaStream_t stream)
+    {
+    return virial ? pair_launch<Ev, MODE, true>(k, tpp, stream)
+                  : pair_launch<Ev, MODE, false>(k, tpp, stream);
     }
 
 // The one entry point an evaluator's .cu instantiates (the counterpart of the reference's
@@ -316,6 +350,11 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     if (a.ntypes > PAIR_MAX_TYPES_SMEM)
         {
         set_error("pair forces: at most 16 particle types are supported");
+        return HB2_ERR_INVALID;
+        }
+    if (a.pitch % 32u != 0)
+        {
+        set_error("pair forces: the neighbour-list pitch must be a multiple of 32");
         return HB2_ERR_INVALID;
         }
     PairKArgs<Ev> k;
@@ -341,7 +380,6 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.timestep = a.timestep;
     k.dt = a.dt;
     k.kT = a.kT;
-    k.energy_shift = (mode == HB2_SHIFT_SHIFT);
     k.box = boxf(box);
     k.boxd = boxd(box);
     k.face_margin = a.face_margin;
@@ -351,11 +389,17 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
         return HB2_ERR_INVALID;
         }
     const bool virial = a.virial != nullptr;
-    if (mode == HB2_SHIFT_XPLOR)
-        return virial ? pair_launch<Ev, true, true>(k, a.tpp, stream)
-                      : pair_launch<Ev, true, false>(k, a.tpp, stream);
-    return virial ? pair_launch<Ev, false, true>(k, a.tpp, stream)
-                  : pair_launch<Ev, false, false>(k, a.tpp, stream);
+    switch (mode)
+        {
+    case HB2_SHIFT_NONE:
+        return pair_launch_mode<Ev, 0>(k, virial, a.tpp, stream);
+    case HB2_SHIFT_SHIFT:
+        return pair_launch_mode<Ev, 1>(k, virial, a.tpp, stream);
+    case HB2_SHIFT_XPLOR:
+        return pair_launch_mode<Ev, 2>(k, virial, a.tpp, stream);
+        }
+    set_error("pair forces: unknown shift mode");
+    return HB2_ERR_INVALID;
     }
 
 // per-evaluator translation units

@@ -57,6 +57,18 @@ class Integrator:
         check(_lib.lib().hb2_integrator_last_run_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def _set_profiling(self, on):
+        check(_lib.lib().hb2_integrator_set_profiling(self._h, int(bool(on))))
+
+    def _profile(self):
+        """dict(integrate_ms, nlist_ms, force_ms, steps, builds, force_launches) since profiling
+        was switched on."""
+        ms = (C.c_double * 3)()
+        n = (C.c_uint64 * 3)()
+        check(_lib.lib().hb2_integrator_get_profile(self._h, ms, n))
+        return dict(integrate_ms=ms[0], nlist_ms=ms[1], force_ms=ms[2], steps=int(n[0]),
+                    builds=int(n[1]), force_launches=int(n[2]))
+
     def _thermo(self):
         ke = C.c_double(0)
         pe = C.c_double(0)

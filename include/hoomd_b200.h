@@ -106,8 +106,11 @@ hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N, const hb2
  * |minImage(pi - pj)|^2 <= (r_cut(ti,tj) + r_buff)^2 decided in fp64. Full list, row i at
  * d_nlist[i * pitch], ascending j. d_r_listsq: ntypes^2 doubles indexed tj*ntypes+ti
  * (hoomd/md/NeighborList.cc:505-506). d_conditions[0] receives max(n_neigh) (overflow if > pitch).
- * Also writes d_last_pos4 = d_pos4 (hoomd/md/NeighborList.cc:1293-1311). */
-hb2_status hb2_gpu_compute_nlist_binned(const float* d_pos4, uint32_t N, uint32_t N_total,
+ * Also writes d_last_pos4 = d_pos4 (hoomd/md/NeighborList.cc:1293-1311).
+ * Row padding: pitch must be a multiple of 32 and every row is padded to a multiple of 32 entries
+ * with the index N_total of a far-away dummy particle, which this call writes to d_pos4[N_total]
+ * (so d_pos4 — and d_vel4 / d_tag for DPD — need N_total + 1 entries); the force driver relies on it. */
+hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_total,
                                         const hb2_box* box, const uint32_t dim[3],
                                         const uint32_t* d_cell_start, const double* d_r_listsq,
                                         uint32_t ntypes, uint32_t* d_nlist, uint32_t pitch,
@@ -242,6 +245,13 @@ hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic, double* po
                                  double virial6[6]);
 /* Device time (ms, CUDA events) spent in the last hb2_integrator_run, and per-phase kernel counts. */
 hb2_status hb2_integrator_last_run_ms(hb2_integrator* it, float* ms);
+/* Per-phase device timing of the following runs (CUDA events on the launching stream, the
+ * counterpart of the reference's Autotuner event sampling, hoomd/Autotuner.h:509-511): phase 0 =
+ * integrate (step one + thermostat + step two), 1 = neighbour list (binning, sort, reorder, build and
+ * the rebuild-flag read-back), 2 = pair-force kernel. phase_n = steps, builds, force launches.
+ * Profiling adds five event records per step; leave it off for throughput measurements. */
+hb2_status hb2_integrator_set_profiling(hb2_integrator* it, int on);
+hb2_status hb2_integrator_get_profile(hb2_integrator* it, double phase_ms[3], uint64_t phase_n[3]);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -10,7 +10,7 @@ for name in ("lj_2k", "c1_64k"):
     fx = dict(np.load(os.path.join(G, name + ".npz")))
     fx["typeid"] = np.zeros(len(fx["pos"]), dtype=np.uint32)
     pre = "none_" if name == "lj_2k" else ""
-    for tpp in (1, 4, 8, 32):
+    for tpp in (4, 8, 32):
         sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none", tpp=tpp)
         sim.run(0)
         f = lj.forces; fr = fx[pre + "force"]

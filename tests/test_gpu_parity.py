@@ -143,7 +143,7 @@ def test_lj_2k(hoomd, golden_dir, mode):
     check_forces(lj, fx, f"{mode}_")
 
 
-@pytest.mark.parametrize("tpp", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("tpp", [4, 8, 16, 32])
 def test_lj_2k_threads_per_particle(hoomd, golden_dir, tpp):
     fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
     sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none",
