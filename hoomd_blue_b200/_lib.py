@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhoomd_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("HB2_LIB", "libhoomd_b200.so"))
 
 # every symbol include/hoomd_b200.h declares (tests check the exports against the header)
 (OK, ERR_INVALID, ERR_CUDA, ERR_NAN_POSITION, ERR_OUT_OF_BOX, ERR_BOX_TOO_SMALL, ERR_NLIST_OVERFLOW,

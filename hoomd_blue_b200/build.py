@@ -10,14 +10,18 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libhoomd_b200.so")
+# HB2_VARIANT / HB2_EXTRA_FLAGS build an experiment library beside the product one (kernel tuning:
+# `HB2_VARIANT=mb10 HB2_EXTRA_FLAGS=-DPAIR_MIN_BLOCKS=10 python -m hoomd_blue_b200.build`, loaded with
+# HB2_LIB=libhoomd_b200_mb10.so)
+_VAR = os.environ.get("HB2_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _VAR if _VAR else ""))
+LIB = os.path.join(HERE, "libhoomd_b200" + ("_" + _VAR if _VAR else "") + ".so")
 SOURCES = ["engine.cu", "capi.cu", "binning.cu", "nlist.cu", "integrate.cu", "pair_lj.cu",
            "pair_dpd.cu", "pair_example.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v"]
+         "-Xptxas", "-v"] + os.environ.get("HB2_EXTRA_FLAGS", "").split()
 
 
 def _headers():

@@ -9,12 +9,15 @@
 // of a far-away dummy particle (pos[N_total]), so the loop has no tail handling and never tests
 // k < n_neigh.
 //
-// TPP lanes share one particle. One loop iteration consumes a 32-entry chunk of the row: for
-// u = 0 .. 32/TPP-1 lane `sub` takes entry u*TPP + sub. The index loads of the TPP lanes are one
-// coalesced 4*TPP-byte segment, and — because rows are ascending and the particles are in cell order —
-// the TPP position gathers issued by one instruction fall on TPP nearly consecutive particles, i.e. on
-// one or two 128-byte lines. All 32/TPP index loads, then all gathers, are issued before the first
-// pair is evaluated (memory-level parallelism), and the next chunk's indices are prefetched.
+// TPP lanes share one particle. The rows of a warp's particles are staged in shared memory by one
+// bulk copy (cp.async.bulk, TMA 1D) per row completing on a per-warp mbarrier: the streaming read of
+// the list bypasses the LSU wavefront queue that the position gathers saturate (ncu r01: 79 % of the
+// L1 data pipe, a quarter of it index loads) and its DRAM latency is paid once per warp.
+// One loop iteration consumes a 32-entry chunk of the row: for u = 0 .. 32/TPP-1 lane `sub` takes
+// entry u*TPP + sub (a conflict-free 32-bit shared load), and — because rows are ascending and the
+// particles are in cell order — the TPP position gathers issued by one instruction fall on TPP nearly
+// consecutive particles, i.e. on one or two 128-byte lines. All 32/TPP gathers are issued before the
+// first pair is evaluated (memory-level parallelism).
 // Owner-computes on a full list: no atomics, fixed __shfl_xor reduction tree, bitwise reproducible.
 // Each visit adds E/2 and (F/r) dx_a dx_b / 2 to the visiting particle only
 // (hoomd/md/PotentialPairGPU.cuh:365-370, hoomd/md/PotentialPair.h:739-752).
@@ -22,11 +25,58 @@
 #include "common.cuh"
 #include "evaluators.cuh"
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace hb2
     {
 constexpr int PAIR_BLOCK = 128;
 constexpr int PAIR_MAX_TYPES_SMEM = 16; // ntypes^2 <= 256 entries staged in shared memory
+constexpr int PAIR_STAGE_MAX = 8;       // 32-entry chunks of a row staged in shared memory per pass
+// 10 resident blocks per SM (<= 51 registers): measured best of {unbounded 56 regs, 10, 12} on B200
+#ifndef PAIR_MIN_BLOCKS
+#define PAIR_MIN_BLOCKS 10
+#endif
+#define PAIR_BOUNDS __launch_bounds__(PAIR_BLOCK, PAIR_MIN_BLOCKS)
+constexpr int PAIR_ROW_PAD = 8;         // words of padding per staged row (bank spread across rows)
+
+// ---- bulk-copy (TMA 1D) row staging: one cp.async.bulk per neighbour-list row, completion on a
+// per-warp mbarrier. The row never passes through registers or the LSU wavefront queue, and the DRAM
+// latency of the list is paid once per warp instead of once per 32-entry chunk.
+HB2_DEVICE uint32_t smem_addr(const void* p)
+    {
+    return (uint32_t)__cvta_generic_to_shared(p);
+    }
+HB2_DEVICE void mbar_init(uint64_t* bar, uint32_t count)
+    {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+HB2_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+    {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+    }
+HB2_DEVICE void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+    {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+    }
+HB2_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity)
+    {
+    uint32_t done;
+    do
+        {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+        } while (!done);
+    }
 
 template<class Ev> struct PairKArgs
     {
@@ -51,19 +101,27 @@ template<class Ev> struct PairKArgs
     uint64_t timestep;
     float dt, kT;
     float face_margin; // r_list_max + buffer: farther than this from every face => no image shifts
+    uint32_t stage;    // chunks of a row staged per pass (<= PAIR_STAGE_MAX)
     BoxF box;
     BoxD boxd;
     };
 
 // MODE: 0 none, 1 shift, 2 xplor (hoomd/md/PotentialPair.h:104-109)
 template<class Ev, int MODE, bool VIRIAL, int TPP, bool ONETYPE>
-__global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<Ev> a)
+__global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
     {
     typedef typename Ev::param_type param_type;
     constexpr int U = 32 / TPP; // entries per lane per 32-entry chunk
     __shared__ param_type s_params[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_rcutsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_ronsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
+    __shared__ __align__(8) uint64_t s_bar[PAIR_BLOCK / 32];
+    extern __shared__ __align__(128) uint32_t s_rows[]; // PAIR_BLOCK / TPP rows of stage*32 + pad
+    const int lane = threadIdx.x & 31;
+    uint64_t* bar = &s_bar[threadIdx.x >> 5];
+    if (lane == 0)
+        mbar_init(bar, 1);
+    __syncwarp();
     if (!ONETYPE)
         {
         const uint32_t nt2 = a.ntypes * a.ntypes;
@@ -104,138 +162,151 @@ __global__ void __launch_bounds__(PAIR_BLOCK) pair_force_kernel(const PairKArgs<
         }
     const bool warp_shift = __any_sync(0xffffffffu, near_face);
 
-    if (active)
+    // ---- per-particle set-up (inactive lanes of the last warp carry n = 0 and only take part in the
+    // warp-wide staging protocol)
+    const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
+    const uint32_t n = active ? __ldg(a.n_neigh + i) : 0u;
+    const uint32_t nchunks = (n + 31u) >> 5;
+    float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t tagi = 0;
+    uint64_t timestep = 0;
+    if (Ev::needs_thermo && active)
         {
-        const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
-        const uint32_t n = __ldg(a.n_neigh + i);
-        const uint32_t* __restrict__ row = a.nlist + (size_t)i * a.pitch + sub;
-        const uint32_t nchunks = (n + 31u) >> 5;
+        vi = __ldg(a.vel + i);
+        tagi = __ldg(a.tag + i);
+        timestep = a.d_timestep ? *a.d_timestep : a.timestep;
+        }
 
-        float4 vi = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t tagi = 0;
-        uint64_t timestep = 0;
-        if (Ev::needs_thermo)
+    auto pair_body = [&](const uint32_t j, const float4 pj, const float dx, const float dy,
+                         const float dz)
+    {
+        const float rsq = dx * dx + dy * dy + dz * dz;
+
+        float rcutsq = a.rcutsq0, ronsq = a.ronsq0;
+        const param_type* prm = &a.param0;
+        if (!ONETYPE)
             {
-            vi = __ldg(a.vel + i);
-            tagi = __ldg(a.tag + i);
-            timestep = a.d_timestep ? *a.d_timestep : a.timestep;
+            // Index2D(ntypes)(ti, tj) = tj * ntypes + ti (hoomd/Index1D.h:53)
+            const uint32_t tp = __float_as_uint(pj.w) * a.ntypes + ti;
+            rcutsq = s_rcutsq[tp];
+            ronsq = s_ronsq[tp];
+            prm = &s_params[tp];
             }
+        bool energy_shift = (MODE == 1);
+        if (MODE == 2)
+            energy_shift = ronsq > rcutsq; // hoomd/md/PotentialPair.h:697-700
 
-        auto pair_body = [&](const uint32_t j, const float4 pj, const float dx, const float dy,
-                             const float dz)
-        {
-            const float rsq = dx * dx + dy * dy + dz * dz;
-
-            float rcutsq = a.rcutsq0, ronsq = a.ronsq0;
-            const param_type* prm = &a.param0;
-            if (!ONETYPE)
+        float force_divr = 0.f, force_divr_cons = 0.f, pair_eng = 0.f;
+        Ev eval(rsq, rcutsq, *prm);
+        bool evaluated;
+        if constexpr (Ev::needs_thermo)
+            {
+            const float4 vj = __ldg(a.vel + j);
+            const uint32_t tagj = __ldg(a.tag + j);
+            const float rdotv = dx * (vi.x - vj.x) + dy * (vi.y - vj.y) + dz * (vi.z - vj.z);
+            eval.set_seed_ij_timestep((uint16_t)a.seed, tagi, tagj, timestep);
+            eval.setDeltaT(a.dt);
+            eval.setRDotV(rdotv);
+            eval.setT(a.kT);
+            evaluated = eval.evalForceEnergyThermo(force_divr, force_divr_cons, pair_eng,
+                                                   energy_shift);
+            }
+        else
+            {
+            evaluated = eval.evalForceAndEnergy(force_divr, pair_eng, energy_shift);
+            force_divr_cons = force_divr;
+            }
+        if (MODE == 2)
+            {
+            // hoomd/md/PotentialPair.h:711-737
+            if (evaluated && rsq >= ronsq && rsq < rcutsq)
                 {
-                // Index2D(ntypes)(ti, tj) = tj * ntypes + ti (hoomd/Index1D.h:53)
-                const uint32_t tp = __float_as_uint(pj.w) * a.ntypes + ti;
-                rcutsq = s_rcutsq[tp];
-                ronsq = s_ronsq[tp];
-                prm = &s_params[tp];
-                }
-            bool energy_shift = (MODE == 1);
-            if (MODE == 2)
-                energy_shift = ronsq > rcutsq; // hoomd/md/PotentialPair.h:697-700
-
-            float force_divr = 0.f, force_divr_cons = 0.f, pair_eng = 0.f;
-            Ev eval(rsq, rcutsq, *prm);
-            bool evaluated;
-            if constexpr (Ev::needs_thermo)
-                {
-                const float4 vj = __ldg(a.vel + j);
-                const uint32_t tagj = __ldg(a.tag + j);
-                const float rdotv = dx * (vi.x - vj.x) + dy * (vi.y - vj.y) + dz * (vi.z - vj.z);
-                eval.set_seed_ij_timestep((uint16_t)a.seed, tagi, tagj, timestep);
-                eval.setDeltaT(a.dt);
-                eval.setRDotV(rdotv);
-                eval.setT(a.kT);
-                evaluated = eval.evalForceEnergyThermo(force_divr, force_divr_cons, pair_eng,
-                                                       energy_shift);
-                }
-            else
-                {
-                evaluated = eval.evalForceAndEnergy(force_divr, pair_eng, energy_shift);
+                const float old_eng = pair_eng, old_f = force_divr;
+                const float d = rcutsq - ronsq;
+                const float denom_inv = 1.0f / (d * d * d);
+                const float m = rsq - rcutsq;
+                const float s = m * m * (rcutsq + 2.0f * rsq - 3.0f * ronsq) * denom_inv;
+                const float ds = 12.0f * (rsq - ronsq) * m * denom_inv;
+                pair_eng = old_eng * s;
+                force_divr = s * old_f - ds * old_eng;
                 force_divr_cons = force_divr;
                 }
-            if (MODE == 2)
-                {
-                // hoomd/md/PotentialPair.h:711-737
-                if (evaluated && rsq >= ronsq && rsq < rcutsq)
-                    {
-                    const float old_eng = pair_eng, old_f = force_divr;
-                    const float d = rcutsq - ronsq;
-                    const float denom_inv = 1.0f / (d * d * d);
-                    const float m = rsq - rcutsq;
-                    const float s = m * m * (rcutsq + 2.0f * rsq - 3.0f * ronsq) * denom_inv;
-                    const float ds = 12.0f * (rsq - ronsq) * m * denom_inv;
-                    pair_eng = old_eng * s;
-                    force_divr = s * old_f - ds * old_eng;
-                    force_divr_cons = force_divr;
-                    }
-                }
-            // branch-free accumulation: a pair beyond the cut-off (or the row padding) adds zeros
-            force_divr = evaluated ? force_divr : 0.f;
-            pair_eng = evaluated ? pair_eng : 0.f;
-            fx += dx * force_divr;
-            fy += dy * force_divr;
-            fz += dz * force_divr;
-            pe += pair_eng * 0.5f;
-            if (VIRIAL)
-                {
-                const float f2 = evaluated ? 0.5f * force_divr_cons : 0.f;
-                vxx += f2 * dx * dx;
-                vxy += f2 * dx * dy;
-                vxz += f2 * dx * dz;
-                vyy += f2 * dy * dy;
-                vyz += f2 * dy * dz;
-                vzz += f2 * dz * dz;
-                }
-        };
-
-        // (hi, lo) of pi - L and pi + L per component (only the face-shifting loop uses them)
-        float mh[3], ml[3], ph[3], pl[3];
-        const float pc[3] = {pi.x, pi.y, pi.z};
-        const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
-        if (warp_shift)
-            {
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                {
-                const double m = (double)pc[c] - a.boxd.L[c];
-                const double p = (double)pc[c] + a.boxd.L[c];
-                mh[c] = (float)m;
-                ml[c] = (float)(m - (double)mh[c]);
-                ph[c] = (float)p;
-                pl[c] = (float)(p - (double)ph[c]);
-                }
             }
-
-        uint32_t jn[U];
-        if (nchunks > 0)
+        // branch-free accumulation: a pair beyond the cut-off (or the row padding) adds zeros
+        force_divr = evaluated ? force_divr : 0.f;
+        pair_eng = evaluated ? pair_eng : 0.f;
+        fx += dx * force_divr;
+        fy += dy * force_divr;
+        fz += dz * force_divr;
+        pe += pair_eng * 0.5f;
+        if (VIRIAL)
             {
-#pragma unroll
-            for (int u = 0; u < U; u++)
-                jn[u] = __ldg(row + u * TPP);
+            const float f2 = evaluated ? 0.5f * force_divr_cons : 0.f;
+            vxx += f2 * dx * dx;
+            vxy += f2 * dx * dy;
+            vxz += f2 * dx * dz;
+            vyy += f2 * dy * dy;
+            vyz += f2 * dy * dz;
+            vzz += f2 * dz * dz;
             }
-        for (uint32_t c = 0; c < nchunks; c++)
+    };
+
+    // (hi, lo) of pi - L and pi + L per component (only the face-shifting loop uses them)
+    float mh[3], ml[3], ph[3], pl[3];
+    const float pc[3] = {pi.x, pi.y, pi.z};
+    const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
+    if (warp_shift)
+        {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            {
+            const double m = (double)pc[c] - a.boxd.L[c];
+            const double p = (double)pc[c] + a.boxd.L[c];
+            mh[c] = (float)m;
+            ml[c] = (float)(m - (double)mh[c]);
+            ph[c] = (float)p;
+            pl[c] = (float)(p - (double)ph[c]);
+            }
+        }
+
+    // ---- staged sweep over the row. Pass p brings chunks [p*stage, (p+1)*stage) of every row of the
+    // warp into shared memory with one bulk copy per row; lanes then read their indices with
+    // conflict-free 32-bit shared loads (row stride = stage*32 + 8 words).
+    const uint32_t stage = a.stage;
+    const uint32_t row_words = stage * 32u + PAIR_ROW_PAD;
+    uint32_t* __restrict__ myrow = s_rows + (threadIdx.x / TPP) * row_words;
+    const uint32_t* __restrict__ grow = a.nlist + (size_t)i * a.pitch;
+    const uint32_t nch_warp = __reduce_max_sync(0xffffffffu, nchunks);
+    uint32_t parity = 0;
+    for (uint32_t c0 = 0; c0 < nch_warp; c0 += stage)
+        {
+        const uint32_t cnt = nchunks > c0 ? min(nchunks - c0, stage) : 0u;
+        const uint32_t bytes = cnt * 128u;
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, sub == 0 ? bytes : 0u);
+        if (c0 > 0)
+            {
+            // every lane is done reading the previous pass before the async proxy overwrites it
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+        if (lane == 0)
+            mbar_expect_tx(bar, tot);
+        __syncwarp();
+        if (sub == 0 && bytes)
+            bulk_copy_g2s(myrow, grow + c0 * 32u, bytes, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        for (uint32_t c = 0; c < cnt; c++)
             {
             uint32_t j[U];
             float4 pj[U];
 #pragma unroll
             for (int u = 0; u < U; u++)
-                j[u] = jn[u];
+                j[u] = myrow[c * 32u + u * TPP + sub];
 #pragma unroll
             for (int u = 0; u < U; u++)
                 pj[u] = __ldg(a.pos + j[u]);
-            if (c + 1 < nchunks)
-                {
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    jn[u] = __ldg(row + (c + 1) * 32 + u * TPP);
-                }
             if (!warp_shift)
                 {
 #pragma unroll
@@ -302,10 +373,12 @@ hb2_status pair_launch_tpp(const PairKArgs<Ev>& k, cudaStream_t stream)
     {
     const uint64_t threads = (uint64_t)k.N * TPP;
     const uint32_t blocks = (uint32_t)((threads + PAIR_BLOCK - 1) / PAIR_BLOCK);
+    // staged rows: PAIR_BLOCK / TPP rows of (stage * 32 + pad) words; at most 33 KB (TPP = 4)
+    const size_t smem = (size_t)(PAIR_BLOCK / TPP) * (k.stage * 32u + PAIR_ROW_PAD) * sizeof(uint32_t);
     if (k.ntypes == 1)
-        pair_force_kernel<Ev, MODE, VIRIAL, TPP, true><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
+        pair_force_kernel<Ev, MODE, VIRIAL, TPP, true><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
     else
-        pair_force_kernel<Ev, MODE, VIRIAL, TPP, false><<<blocks, PAIR_BLOCK, 0, stream>>>(k);
+        pair_force_kernel<Ev, MODE, VIRIAL, TPP, false><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
     HB2_CHECK_LAUNCH("pair_force_kernel");
     return HB2_OK;
     }
@@ -383,6 +456,7 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.box = boxf(box);
     k.boxd = boxd(box);
     k.face_margin = a.face_margin;
+    k.stage = std::min<uint32_t>(std::max<uint32_t>(a.pitch / 32u, 1u), PAIR_STAGE_MAX);
     if (Ev::needs_thermo && (!a.vel || !a.tag))
         {
         set_error("pair forces: this evaluator needs velocities and tags");
