@@ -36,7 +36,9 @@ constexpr int PAIR_STAGE_MAX = 8;       // 32-entry chunks of a row staged in sh
 #ifndef PAIR_MIN_BLOCKS
 #define PAIR_MIN_BLOCKS 10
 #endif
-#define PAIR_BOUNDS __launch_bounds__(PAIR_BLOCK, PAIR_MIN_BLOCKS)
+// (the virial / thermostatted / multi-type instantiations carry more state: 8 blocks, 64 registers)
+#define PAIR_BOUNDS \
+    __launch_bounds__(PAIR_BLOCK, (VIRIAL || Ev::needs_thermo || !ONETYPE || TPP < 8) ? 8 : PAIR_MIN_BLOCKS)
 constexpr int PAIR_ROW_PAD = 8;         // words of padding per staged row (bank spread across rows)
 
 // ---- bulk-copy (TMA 1D) row staging: one cp.async.bulk per neighbour-list row, completion on a
