@@ -44,10 +44,10 @@ def _declare(L):
     L.hb2_pack_params.argtypes = [C.c_int, _f64p, C.c_uint32, _f32p]
     # layer 1
     L.hb2_gpu_compute_cell_order.argtypes = [_vp, C.c_uint32, C.POINTER(Box), _u32p, _vp, _vp, _vp,
-                                             _vp, C.POINTER(C.c_size_t), _vp]
+                                             _vp, _vp, C.POINTER(C.c_size_t), _vp]
     L.hb2_gpu_compute_nlist_binned.argtypes = [_vp, C.c_uint32, C.c_uint32, C.POINTER(Box), _u32p,
-                                               _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp,
-                                               _vp]
+                                               _vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp,
+                                               _vp, _vp]
     L.hb2_gpu_compute_pair_forces.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, C.c_uint32,
                                               C.POINTER(Box), _vp, _vp, C.c_uint32, _vp, _vp, _vp,
                                               C.c_uint32, _vp, _vp, C.c_size_t, C.c_uint32,
@@ -64,6 +64,20 @@ def _declare(L):
     L.hb2_system_get_particles.argtypes = [_vp, _f32p, _f32p, _f32p, _u32p, _i32p]
     L.hb2_system_n.argtypes = [_vp]
     L.hb2_system_n.restype = C.c_uint32
+    L.hb2_comm_unique_id.argtypes = [_vp]
+    L.hb2_system_set_domain.argtypes = [_vp, _u32p, C.c_uint32, C.c_uint32, _vp]
+    L.hb2_domain_find_decomposition.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_double, _u32p]
+    L.hb2_domain_place.argtypes = [C.POINTER(Box), _u32p, _f32p, C.c_uint32, _u32p]
+    L.hb2_domain_ghost_mask.argtypes = [C.POINTER(Box), _u32p, _u32p, C.c_double, _f32p, C.c_uint32,
+                                        C.POINTER(C.c_uint8)]
+    L.hb2_system_set_particles_tagged.argtypes = [_vp, C.c_uint32, C.c_uint64, _u32p, _f32p, _f32p,
+                                                  _f32p, _u32p, _i32p]
+    L.hb2_system_get_local.argtypes = [_vp, _u32p, _f32p, _f32p, _f32p, _u32p, _i32p]
+    L.hb2_system_n_global.argtypes = [_vp]
+    L.hb2_system_n_global.restype = C.c_uint64
+    L.hb2_system_n_ghost.argtypes = [_vp]
+    L.hb2_system_n_ghost.restype = C.c_uint32
+    L.hb2_pair_get_local.argtypes = [_vp, _u32p, _f64p, _f64p, _f64p]
     L.hb2_system_timestep.argtypes = [_vp]
     L.hb2_system_timestep.restype = C.c_uint64
     L.hb2_system_set_timestep.argtypes = [_vp, C.c_uint64]

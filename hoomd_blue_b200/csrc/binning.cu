@@ -9,6 +9,7 @@
 // list" is just cell_start[] into the particle arrays (no Nc x Nmax padded xyzf copy).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "comm.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace hb2
@@ -28,8 +29,12 @@ HB2_DEVICE uint32_t morton2x3(uint32_t x, uint32_t y, uint32_t z)
 // One thread per particle: cell id with the reference's rule in fp64.
 // f = (p - lo) * Linv (hoomd/BoxDim.h:276-284, zero tilt, no ghost width);
 // ib = (int)(f * dim), ib == dim -> 0 when periodic (hoomd/CellList.cc:455-470).
+// Along a decomposed dimension (geom.n > 1) the grid is local: g = domain_g(f) in units of the
+// sub-domain width, interior cells 1..dimi from floor(g * dimi), cell 0 / dimi+1 for the ghost layers
+// below / above. Ghost particles (index >= N_owned) carry bit 31 of the key so that the sort keeps
+// owned particles in [0, N_owned) and ghosts behind them, both in cell order.
 __global__ void __launch_bounds__(256)
-    bin_kernel(const float4* __restrict__ pos, uint32_t N, BoxD box, uint3 dim,
+    bin_kernel(const float4* __restrict__ pos, uint32_t N, uint32_t N_owned, BoxD box, DomainGeom geom,
                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                uint32_t* __restrict__ conditions)
     {
@@ -48,51 +53,87 @@ __global__ void __launch_bounds__(256)
         f[0] = __dmul_rn(__dadd_rn((double)p.x, -box.lo[0]), box.Linv[0]);
         f[1] = __dmul_rn(__dadd_rn((double)p.y, -box.lo[1]), box.Linv[1]);
         f[2] = __dmul_rn(__dadd_rn((double)p.z, -box.lo[2]), box.Linv[2]);
-        const uint32_t dm[3] = {dim.x, dim.y, dim.z};
         int ib[3];
         uint32_t sb[3];
         bool out = false;
 #pragma unroll
         for (int d = 0; d < 3; d++)
             {
-            const double fc = __dmul_rn(f[d], (double)dm[d]);
-            ib[d] = (int)fc;
-            // position inside the cell in quarters (ordering only; never decides membership)
-            const int q = (int)((fc - (double)ib[d]) * 4.0);
-            sb[d] = (uint32_t)min(max(q, 0), 3);
-            if (ib[d] == (int)dm[d])
-                {
-                ib[d] = 0;
-                sb[d] = 0;
-                }
-            if (f[d] < -0.00001 || f[d] >= 1.00001 || ib[d] < 0 || ib[d] >= (int)dm[d])
+            const int dm = (int)geom.dimi[d];
+            if (f[d] < -0.00001 || f[d] >= 1.00001)
                 out = true;
+            if (geom.n[d] == 1)
+                {
+                const double fc = __dmul_rn(f[d], (double)dm);
+                ib[d] = (int)fc;
+                // position inside the cell in quarters (ordering only; never decides membership)
+                const int q = (int)((fc - (double)ib[d]) * 4.0);
+                sb[d] = (uint32_t)min(max(q, 0), 3);
+                if (ib[d] == dm)
+                    {
+                    ib[d] = 0;
+                    sb[d] = 0;
+                    }
+                if (ib[d] < 0 || ib[d] >= dm)
+                    out = true;
+                }
+            else
+                {
+                const double g = domain_g(f[d], geom.n[d], geom.coord[d]);
+                const double fc = g * (double)dm;
+                int cell, q;
+                if (g >= 1.0)
+                    {
+                    cell = dm + 1;
+                    q = (int)((fc - (double)dm) * 4.0);
+                    }
+                else if (g < 0.0)
+                    {
+                    cell = 0;
+                    q = (int)((fc + 1.0) * 4.0);
+                    }
+                else
+                    {
+                    const int c0 = min((int)fc, dm - 1);
+                    cell = c0 + 1;
+                    q = (int)((fc - (double)c0) * 4.0);
+                    }
+                ib[d] = cell;
+                sb[d] = (uint32_t)min(max(q, 0), 3);
+                // an owned particle must lie inside its domain (migration runs before binning)
+                if (i < N_owned && (g < 0.0 || g >= 1.0))
+                    out = true;
+                }
             }
         if (out)
             atomicMax(&conditions[2], i + 1);
         else
-            key = ((((uint32_t)ib[2] * dim.y + (uint32_t)ib[1]) * dim.x + (uint32_t)ib[0]) << SUB_BITS)
+            key = ((((uint32_t)ib[2] * geom.dimt[1] + (uint32_t)ib[1]) * geom.dimt[0] + (uint32_t)ib[0])
+                   << SUB_BITS)
                   | morton2x3(sb[0], sb[1], sb[2]);
         }
+    if (i >= N_owned)
+        key |= 0x80000000u;
     keys[i] = key;
     vals[i] = i;
     }
 
-// cell_start from the sorted keys (cell = key >> SUB_BITS): slot k starts every cell in
-// (cell[k-1], cell[k]].
+// [cell_start, cell_end) from the sorted keys (cell = key bits 6..30): slot k opens its cell when the
+// previous slot holds another cell (or the other side of the owned / ghost split) and closes the
+// previous one. Both arrays are zeroed first, so empty cells read as [0, 0).
 __global__ void __launch_bounds__(256)
-    cell_start_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t N, uint32_t Nc,
-                      uint32_t* __restrict__ cell_start)
+    cell_range_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t N,
+                      uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end)
     {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > N)
+    if (k >= N)
         return;
-    uint32_t lo = (k == 0) ? 0u : (keys_sorted[k - 1] >> SUB_BITS) + 1u;
-    uint32_t hi = (k == N) ? Nc : (keys_sorted[k] >> SUB_BITS);
-    if (k == 0)
-        lo = 0;
-    for (uint32_t c = lo; c <= hi && c <= Nc; c++)
-        cell_start[c] = k;
+    const uint32_t key = keys_sorted[k] >> SUB_BITS;
+    const uint32_t cell = key & ((1u << (31 - SUB_BITS)) - 1u);
+    if (k == 0 || (keys_sorted[k - 1] >> SUB_BITS) != key)
+        cell_start[cell] = k;
+    if (k == N - 1 || (keys_sorted[k + 1] >> SUB_BITS) != key)
+        cell_end[cell] = k + 1;
     }
 
 // Gather every per-particle array into cell order; refresh rtag.
@@ -117,11 +158,14 @@ __global__ void __launch_bounds__(256)
     tag_out[k] = t;
     if (force_in)
         force_out[k] = force_in[o];
-    rtag[t] = k;
+    if (rtag)
+        rtag[t] = k;
     }
 
-static inline int key_bits(uint32_t Nc)
+static inline int key_bits(uint32_t Nc, bool ghosts)
     {
+    if (ghosts)
+        return 32; // bit 31 splits owned / ghost particles
     int b = 1;
     while (b < 32 && (1ull << b) < (unsigned long long)Nc)
         b++;
@@ -132,17 +176,18 @@ size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc)
     {
     size_t sort_bytes = 0;
     cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k, v, (int)N, 0, key_bits(Nc));
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k, v, (int)N, 0, 32);
     sort_bytes = (sort_bytes + 255) & ~size_t(255);
     size_t arr = ((size_t)N * sizeof(uint32_t) + 255) & ~size_t(255);
     return sort_bytes + 3 * arr; // keys, keys_alt, vals_alt (+ the caller's order[] as vals)
     }
 
-hb2_status compute_cell_order(const float4* d_pos, uint32_t N, const hb2_box& box, uint3 dim,
-                              uint32_t* d_order, uint32_t* d_cell_start, uint32_t* d_conditions,
-                              void* d_tmp, size_t tmp_bytes, cudaStream_t stream)
+hb2_status compute_cell_order(const float4* d_pos, uint32_t N, uint32_t N_owned, const hb2_box& box,
+                              const DomainGeom& geom, uint32_t* d_order, uint32_t* d_cell_start,
+                              uint32_t* d_cell_end, uint32_t* d_conditions, void* d_tmp,
+                              size_t tmp_bytes, cudaStream_t stream)
     {
-    const uint32_t Nc = dim.x * dim.y * dim.z;
+    const uint32_t Nc = geom.dimt[0] * geom.dimt[1] * geom.dimt[2];
     if (tmp_bytes < cell_order_tmp_bytes(N, Nc))
         {
         set_error("compute_cell_order: scratch buffer too small");
@@ -156,24 +201,23 @@ hb2_status compute_cell_order(const float4* d_pos, uint32_t N, const hb2_box& bo
     void* sort_tmp = base + 3 * arr;
     size_t sort_bytes = tmp_bytes - 3 * arr;
 
+    HB2_CUDA(cudaMemsetAsync(d_cell_start, 0, sizeof(uint32_t) * (size_t)Nc, stream));
+    HB2_CUDA(cudaMemsetAsync(d_cell_end, 0, sizeof(uint32_t) * (size_t)Nc, stream));
     if (N > 0)
         {
-        bin_kernel<<<(N + 255) / 256, 256, 0, stream>>>(d_pos, N, boxd(box), dim, keys, d_order,
-                                                        d_conditions);
+        bin_kernel<<<(N + 255) / 256, 256, 0, stream>>>(d_pos, N, N_owned, boxd(box), geom, keys,
+                                                        d_order, d_conditions);
         HB2_CHECK_LAUNCH("bin_kernel");
         cub::DoubleBuffer<uint32_t> k(keys, keys_alt), v(d_order, vals_alt);
-        HB2_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k, v, (int)N, 0, key_bits(Nc),
-                                                 stream));
+        HB2_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k, v, (int)N, 0,
+                                                 key_bits(Nc, N_owned < N), stream));
         count_launch(3);
         if (v.Current() != d_order)
             HB2_CUDA(cudaMemcpyAsync(d_order, v.Current(), (size_t)N * sizeof(uint32_t),
                                      cudaMemcpyDeviceToDevice, stream));
-        cell_start_kernel<<<(N + 1 + 255) / 256, 256, 0, stream>>>(k.Current(), N, Nc, d_cell_start);
-        HB2_CHECK_LAUNCH("cell_start_kernel");
-        }
-    else
-        {
-        HB2_CUDA(cudaMemsetAsync(d_cell_start, 0, sizeof(uint32_t) * ((size_t)Nc + 1), stream));
+        cell_range_kernel<<<(N + 255) / 256, 256, 0, stream>>>(k.Current(), N, d_cell_start,
+                                                               d_cell_end);
+        HB2_CHECK_LAUNCH("cell_range_kernel");
         }
     return HB2_OK;
     }

@@ -12,8 +12,9 @@ using namespace hb2;
 
 extern "C" hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N, const hb2_box* box,
                                                  const uint32_t dim[3], uint32_t* d_order,
-                                                 uint32_t* d_cell_start, uint32_t* d_conditions,
-                                                 void* d_tmp, size_t* tmp_bytes, void* stream)
+                                                 uint32_t* d_cell_start, uint32_t* d_cell_end,
+                                                 uint32_t* d_conditions, void* d_tmp,
+                                                 size_t* tmp_bytes, void* stream)
     {
     if (!box || !dim || !tmp_bytes)
         {
@@ -31,25 +32,26 @@ extern "C" hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N
         *tmp_bytes = cell_order_tmp_bytes(N, (uint32_t)Nc);
         return HB2_OK;
         }
-    if (!d_pos4 || !d_order || !d_cell_start || !d_conditions)
+    if (!d_pos4 || !d_order || !d_cell_start || !d_cell_end || !d_conditions)
         {
         set_error("hb2_gpu_compute_cell_order: null device pointer");
         return HB2_ERR_INVALID;
         }
-    return compute_cell_order((const float4*)d_pos4, N, *box, make_uint3(dim[0], dim[1], dim[2]),
-                              d_order, d_cell_start, d_conditions, d_tmp, *tmp_bytes,
+    return compute_cell_order((const float4*)d_pos4, N, N, *box, periodic_geom(dim), d_order,
+                              d_cell_start, d_cell_end, d_conditions, d_tmp, *tmp_bytes,
                               (cudaStream_t)stream);
     }
 
 extern "C" hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_total,
                                                    const hb2_box* box, const uint32_t dim[3],
                                                    const uint32_t* d_cell_start,
+                                                   const uint32_t* d_cell_end,
                                                    const double* d_r_listsq, uint32_t ntypes,
                                                    uint32_t* d_nlist, uint32_t pitch,
                                                    uint32_t* d_n_neigh, float* d_last_pos4,
                                                    uint32_t* d_conditions, void* stream)
     {
-    if (!d_pos4 || !box || !dim || !d_cell_start || !d_r_listsq || !d_nlist || !d_n_neigh
+    if (!d_pos4 || !box || !dim || !d_cell_start || !d_cell_end || !d_r_listsq || !d_nlist || !d_n_neigh
         || !d_conditions || ntypes == 0)
         {
         set_error("hb2_gpu_compute_nlist_binned: null argument");
@@ -76,8 +78,9 @@ extern "C" hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, ui
     NlistBuildArgs a;
     a.pos = (const float4*)d_pos4;
     a.N = N;
-    a.dim = make_uint3(dim[0], dim[1], dim[2]);
+    a.geom = periodic_geom(dim);
     a.cell_start = d_cell_start;
+    a.cell_end = d_cell_end;
     a.r_listsq = d_r_listsq;
     a.ntypes = ntypes;
     a.r_listsq_single = h[0];

@@ -11,11 +11,7 @@
 #include "evaluators.cuh"
 #include "kernels.cuh"
 #include "pair_kernel.cuh"
-
-#include <algorithm>
-#include <cmath>
-#include <cstring>
-#include <vector>
+#include "engine.cuh"
 
 namespace hb2
     {
@@ -32,180 +28,8 @@ hb2_status cuda_fail(cudaError_t e, const char* what)
     return HB2_ERR_CUDA;
     }
 
-template<class T> static hb2_status dev_alloc(T** p, size_t n)
-    {
-    *p = nullptr;
-    if (n == 0)
-        n = 1;
-    HB2_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
-    return HB2_OK;
-    }
-template<class T> static void dev_free(T*& p)
-    {
-    if (p)
-        cudaFree(p);
-    p = nullptr;
-    }
     } // namespace hb2
 
-using namespace hb2;
-
-#define HB2_TRY(expr)              \
-    do                             \
-        {                          \
-        hb2_status _s = (expr);    \
-        if (_s != HB2_OK)          \
-            return _s;             \
-        } while (0)
-
-// =================================================================================================
-struct hb2_system
-    {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    uint32_t ntypes = 1;
-    uint32_t seed = 0;
-    hb2_box box;
-    bool has_box = false;
-    uint32_t N = 0;
-    uint64_t timestep = 0;
-    uint64_t* d_timestep = nullptr;
-    bool compute_virial = false;
-
-    // particle arrays, double buffered: every nlist rebuild gathers them into cell order
-    float4* pos[2] = {nullptr, nullptr};
-    float4* vel[2] = {nullptr, nullptr};
-    int* image[2] = {nullptr, nullptr};
-    uint32_t* tag[2] = {nullptr, nullptr};
-    uint32_t* rtag = nullptr;
-    int cur = 0;
-    uint64_t order_epoch = 0; // bumped whenever the particle order changes
-
-    // reduction scratch
-    double* d_partial = nullptr;
-    uint32_t* d_ticket = nullptr;
-    double* d_sums = nullptr; // [0] KE, [1..7] PE + virial, [8] rescale factor
-
-    std::vector<hb2_nlist*> nlists;
-    std::vector<hb2_pair*> pairs;
-    cudaEvent_t mid_event = nullptr; // recorded between the nlist update and the force launch
-
-    hb2_status set_timestep(uint64_t t)
-        {
-        timestep = t;
-        HB2_CUDA(cudaMemcpyAsync(d_timestep, &timestep, sizeof(uint64_t), cudaMemcpyHostToDevice,
-                                 stream));
-        HB2_CUDA(cudaStreamSynchronize(stream));
-        return HB2_OK;
-        }
-    };
-
-struct hb2_nlist
-    {
-    hb2_system* sys = nullptr;
-    double buffer = 0.4;
-    uint32_t rebuild_check_delay = 1;
-    bool check_dist = true;
-
-    std::vector<hb2_pair*> consumers;
-    std::vector<double> r_cut, r_listsq, rcut_max;
-    double rcut_max_max = 0.0, r_list_min = 0.0;
-    bool params_dirty = true;
-
-    uint3 dim = {0, 0, 0};
-    uint32_t cell_cap = 0;
-    uint32_t* d_cell_start = nullptr;
-    uint32_t* d_order = nullptr;
-    void* d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    double* d_r_listsq = nullptr;
-
-    uint32_t* d_nlist = nullptr;
-    uint32_t pitch = 0;
-    size_t nlist_cap = 0;
-    uint32_t* d_n_neigh = nullptr;
-    float4* d_last_pos = nullptr;
-    uint32_t cap_N = 0;
-    uint32_t* d_conditions = nullptr; // [0] max n_neigh, [1] nan idx+1, [2] oob idx+1, [3] rebuild flag
-    uint32_t* h_conditions = nullptr; // pinned mirror
-
-    bool force_update = true;
-    bool has_list = false;
-    uint64_t num_builds = 0;
-    uint64_t last_update_step = 0;
-    uint64_t shortest_rebuild = ~0ull;
-    uint32_t max_neigh = 0;
-
-    hb2_status update_r_list();
-    hb2_status ensure_capacity();
-    hb2_status rebuild(uint64_t timestep);
-    hb2_status compute(uint64_t timestep, bool flag_known, bool flag_value);
-    float maxshift() const
-        {
-        // hoomd/md/NeighborList.cc:1244-1260 with a fixed box (lambda = 1): (r_max - r_min)/2
-        return (float)(buffer / 2.0);
-        }
-    };
-
-struct hb2_pair
-    {
-    hb2_system* sys = nullptr;
-    hb2_nlist* nl = nullptr;
-    hb2_evaluator ev = HB2_EVAL_LJ;
-    hb2_shift_mode mode = HB2_SHIFT_NONE;
-    std::vector<double> user; // ntypes^2 x 2 user parameters
-    std::vector<uint8_t> have_params;
-    std::vector<double> r_cut, r_on;
-    std::vector<float> packed, rcutsq, ronsq;
-    float* d_params = nullptr;
-    float* d_rcutsq = nullptr;
-    float* d_ronsq = nullptr;
-    bool params_dirty = true;
-    double kT = 1.0;
-    double dt = 0.005;
-    uint32_t tpp = 8;
-    bool tail_correction = false;
-
-    float4* d_force = nullptr;
-    float* d_virial = nullptr;
-    uint32_t cap_N = 0;
-    bool virial_valid = false;
-    bool computed = false;
-    uint64_t computed_step = 0, computed_epoch = 0;
-
-    hb2_status upload_params();
-    hb2_status compute(uint64_t timestep, bool flag_known = false, bool flag_value = false);
-    };
-
-struct hb2_integrator
-    {
-    hb2_system* sys = nullptr;
-    double dt = 0.005;
-    std::vector<hb2_pair*> forces;
-    int thermostat = 0;
-    double kT = 1.0, tau = 0.0;
-    bool prepared = false;
-    uint64_t prepared_epoch = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = 0.f;
-    // optional per-phase device timing (CUDA events on the launching stream)
-    bool profiling = false;
-    std::vector<cudaEvent_t> pool;
-    size_t pool_used = 0;
-    std::vector<size_t> marks; // five events per step: a b c d e
-    double phase_ms[3] = {0, 0, 0}; // integrate, nlist, force
-    uint64_t phase_n[3] = {0, 0, 0};
-    cudaEvent_t next_event()
-        {
-        if (pool_used == pool.size())
-            {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
-            pool.push_back(e);
-            }
-        return pool[pool_used++];
-        }
-    };
 
 // =================================================================================================
 // system
@@ -302,6 +126,7 @@ extern "C" void hb2_system_destroy(hb2_system* s)
         return;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
+    domain_destroy(s);
     for (int b = 0; b < 2; b++)
         {
         dev_free(s->pos[b]);
@@ -338,40 +163,68 @@ extern "C" hb2_status hb2_system_set_box(hb2_system* s, double Lx, double Ly, do
     return HB2_OK;
     }
 
-extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const float* pos3,
-                                               const float* vel3, const float* mass,
-                                               const uint32_t* typeid_, const int32_t* image3)
+// (Re)allocates every per-particle array of the system for `cap` slots.
+static hb2_status system_allocate(hb2_system* s, uint32_t cap, bool with_rtag, uint64_t n_tags)
+    {
+    for (int b = 0; b < 2; b++)
+        {
+        dev_free(s->pos[b]);
+        dev_free(s->vel[b]);
+        dev_free(s->image[b]);
+        dev_free(s->tag[b]);
+        HB2_TRY(dev_alloc(&s->pos[b], (size_t)cap));
+        HB2_TRY(dev_alloc(&s->vel[b], (size_t)cap));
+        HB2_TRY(dev_alloc(&s->image[b], 3 * (size_t)cap));
+        HB2_TRY(dev_alloc(&s->tag[b], (size_t)cap));
+        }
+    dev_free(s->rtag);
+    if (with_rtag)
+        HB2_TRY(dev_alloc(&s->rtag, n_tags));
+    dev_free(s->d_partial);
+    HB2_TRY(dev_alloc(&s->d_partial, 8 * (size_t)(reduce_blocks(cap) + 1)));
+    s->cap = cap;
+    return HB2_OK;
+    }
+
+// the far-away dummy particle that pads neighbour-list rows lives right behind the last ghost
+static hb2_status system_place_dummy(hb2_system* s)
+    {
+    // static: the sources must outlive the asynchronous copies
+    static const float4 far_pos = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
+    static const float4 far_vel = make_float4(0.f, 0.f, 0.f, 1.f);
+    static const uint32_t far_tag = 0xffffffffu;
+    const size_t at = (size_t)s->N + s->Ng;
+    const int b = s->cur;
+    HB2_CUDA(cudaMemcpyAsync(s->pos[b] + at, &far_pos, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(s->vel[b] + at, &far_vel, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(s->tag[b] + at, &far_tag, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    return HB2_OK;
+    }
+
+// Common body of set_particles / set_particles_tagged. With a domain decomposition only the
+// particles this rank owns are kept (hoomd/ParticleData.cc initializeFromSnapshot scatters the
+// snapshot with DomainDecomposition::placeParticle in the same way).
+static hb2_status system_set(hb2_system* s, uint32_t n_in, uint64_t N_global, const uint32_t* tag,
+                             const float* pos3, const float* vel3, const float* mass,
+                             const uint32_t* typeid_, const int32_t* image3)
     {
     if (!s || !pos3)
         {
         set_error("hb2_system_set_particles: positions are required");
         return HB2_ERR_INVALID;
         }
-    HB2_CUDA(cudaSetDevice(s->device));
-    if (N != s->N || !s->pos[0])
+    if (!s->has_box)
         {
-        for (int b = 0; b < 2; b++)
-            {
-            dev_free(s->pos[b]);
-            dev_free(s->vel[b]);
-            dev_free(s->image[b]);
-            dev_free(s->tag[b]);
-            // one extra slot: the far-away dummy particle that pads neighbour-list rows
-            HB2_TRY(dev_alloc(&s->pos[b], (size_t)N + 1));
-            HB2_TRY(dev_alloc(&s->vel[b], (size_t)N + 1));
-            HB2_TRY(dev_alloc(&s->image[b], 3 * (size_t)N));
-            HB2_TRY(dev_alloc(&s->tag[b], (size_t)N + 1));
-            }
-        dev_free(s->rtag);
-        HB2_TRY(dev_alloc(&s->rtag, N));
-        dev_free(s->d_partial);
-        HB2_TRY(dev_alloc(&s->d_partial, 8 * (size_t)(reduce_blocks(N) + 1)));
-        s->N = N;
+        set_error("hb2_system_set_particles: set the box first");
+        return HB2_ERR_INVALID;
         }
-    std::vector<float4> hp(N), hv(N);
-    std::vector<int> hi(3 * (size_t)N, 0);
-    std::vector<uint32_t> ht(N);
-    for (uint32_t i = 0; i < N; i++)
+    HB2_CUDA(cudaSetDevice(s->device));
+    Domain& D = s->dom;
+    std::vector<float4> hp, hv;
+    std::vector<int> hi;
+    std::vector<uint32_t> ht;
+    hp.reserve(D.active ? n_in / D.nranks + 16 : n_in);
+    for (uint32_t i = 0; i < n_in; i++)
         {
         const uint32_t t = typeid_ ? typeid_[i] : 0u;
         if (t >= s->ntypes)
@@ -379,36 +232,57 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
             set_error("hb2_system_set_particles: type id out of range");
             return HB2_ERR_INVALID;
             }
+        if (D.active)
+            {
+            bool mine = true;
+            for (int d = 0; d < 3 && mine; d++)
+                {
+                if (D.grid[d] == 1)
+                    continue;
+                const double f = ((double)pos3[3 * (size_t)i + d] - s->box.lo[d]) * s->box.Linv[d];
+                const double g = domain_g(f, D.grid[d], D.coord[d]);
+                mine = (g >= 0.0 && g < 1.0);
+                }
+            if (!mine)
+                continue;
+            }
         float tw;
         memcpy(&tw, &t, 4);
-        hp[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], tw);
-        hv[i] = make_float4(vel3 ? vel3[3 * i] : 0.f, vel3 ? vel3[3 * i + 1] : 0.f,
-                            vel3 ? vel3[3 * i + 2] : 0.f, mass ? mass[i] : 1.0f);
-        ht[i] = i;
+        hp.push_back(make_float4(pos3[3 * (size_t)i], pos3[3 * (size_t)i + 1], pos3[3 * (size_t)i + 2], tw));
+        hv.push_back(make_float4(vel3 ? vel3[3 * (size_t)i] : 0.f, vel3 ? vel3[3 * (size_t)i + 1] : 0.f,
+                                 vel3 ? vel3[3 * (size_t)i + 2] : 0.f, mass ? mass[i] : 1.0f));
+        for (int d = 0; d < 3; d++)
+            hi.push_back(image3 ? image3[3 * (size_t)i + d] : 0);
+        ht.push_back(tag ? tag[i] : i);
         }
-    if (image3)
-        memcpy(hi.data(), image3, sizeof(int) * 3 * (size_t)N);
-    s->cur = 0;
-    HB2_CUDA(cudaMemcpyAsync(s->pos[0], hp.data(), sizeof(float4) * N, cudaMemcpyHostToDevice,
-                             s->stream));
-    HB2_CUDA(cudaMemcpyAsync(s->vel[0], hv.data(), sizeof(float4) * N, cudaMemcpyHostToDevice,
-                             s->stream));
-    HB2_CUDA(cudaMemcpyAsync(s->image[0], hi.data(), sizeof(int) * 3 * (size_t)N,
-                             cudaMemcpyHostToDevice, s->stream));
-    HB2_CUDA(cudaMemcpyAsync(s->tag[0], ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice,
-                             s->stream));
-    HB2_CUDA(cudaMemcpyAsync(s->rtag, ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice,
-                             s->stream));
-    const float4 far_pos = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
-    const float4 far_vel = make_float4(0.f, 0.f, 0.f, 1.f);
-    const uint32_t far_tag = 0xffffffffu;
-    for (int b = 0; b < 2; b++)
+    const uint32_t N = (uint32_t)hp.size();
+    uint32_t need = N + 1;
+    if (D.active)
         {
-        HB2_CUDA(cudaMemcpyAsync(s->pos[b] + N, &far_pos, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
-        HB2_CUDA(cudaMemcpyAsync(s->vel[b] + N, &far_vel, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
-        HB2_CUDA(cudaMemcpyAsync(s->tag[b] + N, &far_tag, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        // room for density fluctuations, migration and the ghost layer (estimated from the mean
+        // density with a generous margin; exceeding it is reported, not silently truncated)
+        const double n0 = (double)N_global / D.nranks;
+        double shell = 1.0;
+        for (int d = 0; d < 3; d++)
+            if (D.grid[d] > 1)
+                shell *= 1.0 + 2.0 * std::min(0.5, 4.0 / (s->box.L[d] / D.grid[d]));
+        need = (uint32_t)std::min<double>(4.0e9, 1.3 * n0 * shell + 1.2 * N + 4096.0);
         }
-    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    if (need > s->cap || !s->pos[0])
+        HB2_TRY(system_allocate(s, need, !D.active, N_global));
+    s->N = N;
+    s->Ng = 0;
+    s->cur = 0;
+    D.N_global = N_global;
+    cudaStream_t st = s->stream;
+    HB2_CUDA(cudaMemcpyAsync(s->pos[0], hp.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(s->vel[0], hv.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(s->image[0], hi.data(), sizeof(int) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(s->tag[0], ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+    if (s->rtag)
+        HB2_CUDA(cudaMemcpyAsync(s->rtag, ht.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    HB2_TRY(system_place_dummy(s));
     s->order_epoch++;
     for (auto* nl : s->nlists)
         {
@@ -420,11 +294,103 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
     return HB2_OK;
     }
 
+extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const float* pos3,
+                                               const float* vel3, const float* mass,
+                                               const uint32_t* typeid_, const int32_t* image3)
+    {
+    return system_set(s, N, N, nullptr, pos3, vel3, mass, typeid_, image3);
+    }
+
+extern "C" hb2_status hb2_system_set_particles_tagged(hb2_system* s, uint32_t n, uint64_t N_global,
+                                                      const uint32_t* tag, const float* pos3,
+                                                      const float* vel3, const float* mass,
+                                                      const uint32_t* typeid_, const int32_t* image3)
+    {
+    if (!tag || N_global > 0xfffffffeull)
+        {
+        set_error("hb2_system_set_particles_tagged: tags are required and must fit 32 bits");
+        return HB2_ERR_INVALID;
+        }
+    return system_set(s, n, N_global, tag, pos3, vel3, mass, typeid_, image3);
+    }
+
+extern "C" hb2_status hb2_system_set_domain(hb2_system* s, const uint32_t grid[3], uint32_t rank,
+                                            uint32_t nranks, const void* nccl_unique_id)
+    {
+    if (!s || !grid || !nccl_unique_id)
+        return HB2_ERR_INVALID;
+    if (s->N || s->dom.active)
+        {
+        set_error("hb2_system_set_domain: must be called once, before particles are set");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    if (nranks == 1)
+        return HB2_OK;
+    return domain_setup(s, grid, (int)rank, (int)nranks, nccl_unique_id);
+    }
+
+extern "C" hb2_status hb2_system_get_local(hb2_system* s, uint32_t* tag, float* pos3, float* vel3,
+                                           float* mass, uint32_t* typeid_, int32_t* image3)
+    {
+    if (!s)
+        return HB2_ERR_INVALID;
+    HB2_CUDA(cudaSetDevice(s->device));
+    const uint32_t N = s->N;
+    std::vector<float4> hp(N), hv(N);
+    std::vector<int> hi(3 * (size_t)N);
+    const int c = s->cur;
+    cudaStream_t st = s->stream;
+    HB2_CUDA(cudaMemcpyAsync(hp.data(), s->pos[c], sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaMemcpyAsync(hv.data(), s->vel[c], sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaMemcpyAsync(hi.data(), s->image[c], sizeof(int) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
+    if (tag)
+        HB2_CUDA(cudaMemcpyAsync(tag, s->tag[c], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t k = 0; k < N; k++)
+        {
+        if (pos3)
+            {
+            pos3[3 * (size_t)k] = hp[k].x;
+            pos3[3 * (size_t)k + 1] = hp[k].y;
+            pos3[3 * (size_t)k + 2] = hp[k].z;
+            }
+        if (typeid_)
+            memcpy(&typeid_[k], &hp[k].w, 4);
+        if (vel3)
+            {
+            vel3[3 * (size_t)k] = hv[k].x;
+            vel3[3 * (size_t)k + 1] = hv[k].y;
+            vel3[3 * (size_t)k + 2] = hv[k].z;
+            }
+        if (mass)
+            mass[k] = hv[k].w;
+        if (image3)
+            memcpy(&image3[3 * (size_t)k], &hi[3 * (size_t)k], 3 * sizeof(int));
+        }
+    return HB2_OK;
+    }
+
+extern "C" uint64_t hb2_system_n_global(const hb2_system* s)
+    {
+    return s ? (s->dom.active ? s->dom.N_global : s->N) : 0;
+    }
+extern "C" uint32_t hb2_system_n_ghost(const hb2_system* s)
+    {
+    return s ? s->Ng : 0;
+    }
+
 extern "C" hb2_status hb2_system_get_particles(hb2_system* s, float* pos3, float* vel3, float* mass,
                                                uint32_t* typeid_, int32_t* image3)
     {
     if (!s)
         return HB2_ERR_INVALID;
+    if (s->dom.active)
+        {
+        set_error("hb2_system_get_particles: the system is domain decomposed; use "
+                  "hb2_system_get_local and gather by tag");
+        return HB2_ERR_INVALID;
+        }
     HB2_CUDA(cudaSetDevice(s->device));
     const uint32_t N = s->N;
     std::vector<float4> hp(N), hv(N);
@@ -544,32 +510,41 @@ hb2_status hb2_nlist::update_r_list()
 
 hb2_status hb2_nlist::ensure_capacity()
     {
-    const uint32_t N = sys->N;
-    // cell grid: dim = floor(L / (max r_cut + buffer)), at least 1 (hoomd/CellList.cc:83-131 with
-    // the nominal width of hoomd/md/NeighborListBinned.cc:39-45)
+    const uint32_t cap = sys->cap;
+    const Domain& D = sys->dom;
+    // cell grid: dim = floor(width / (max r_cut + buffer)), at least 1 (hoomd/CellList.cc:83-131 with
+    // the nominal width of hoomd/md/NeighborListBinned.cc:39-45); along a decomposed dimension the
+    // width is the sub-domain's and one ghost-cell layer is added on each side (hoomd/CellList.cc
+    // does the same through ghost_width, :95-116)
     const double width = rcut_max_max + buffer;
-    uint32_t d[3];
+    uint64_t Nc64 = 1;
     for (int k = 0; k < 3; k++)
         {
-        d[k] = (uint32_t)(sys->box.L[k] / width);
-        if (d[k] == 0)
-            d[k] = 1;
+        const uint32_t n = D.active ? D.grid[k] : 1u;
+        uint32_t d = (uint32_t)(sys->box.L[k] / (double)n / width);
+        if (d == 0)
+            d = 1;
+        geom.n[k] = n;
+        geom.coord[k] = D.active ? D.coord[k] : 0u;
+        geom.dimi[k] = d;
+        geom.dimt[k] = n > 1 ? d + 2 : d;
+        Nc64 *= geom.dimt[k];
         }
-    dim = make_uint3(d[0], d[1], d[2]);
-    const uint64_t Nc64 = (uint64_t)d[0] * d[1] * d[2];
-    if (Nc64 >= (1ull << 25)) // the sort key holds the cell id above 6 sub-cell bits
+    if (Nc64 >= (1ull << 25)) // the sort key holds the cell id above 6 sub-cell bits, below bit 31
         {
         set_error("nlist: cell grid too large");
         return HB2_ERR_INVALID;
         }
     const uint32_t Nc = (uint32_t)Nc64;
-    if (Nc + 1 > cell_cap)
+    if (Nc > cell_cap)
         {
         dev_free(d_cell_start);
-        HB2_TRY(dev_alloc(&d_cell_start, (size_t)Nc + 1));
-        cell_cap = Nc + 1;
+        dev_free(d_cell_end);
+        HB2_TRY(dev_alloc(&d_cell_start, (size_t)Nc));
+        HB2_TRY(dev_alloc(&d_cell_end, (size_t)Nc));
+        cell_cap = Nc;
         }
-    const size_t need_tmp = cell_order_tmp_bytes(N, Nc);
+    const size_t need_tmp = cell_order_tmp_bytes(cap, Nc);
     if (need_tmp > tmp_bytes)
         {
         if (d_tmp)
@@ -578,30 +553,33 @@ hb2_status hb2_nlist::ensure_capacity()
         HB2_CUDA(cudaMalloc(&d_tmp, need_tmp));
         tmp_bytes = need_tmp;
         }
-    if (N > cap_N)
+    if (cap > cap_N)
         {
         dev_free(d_order);
         dev_free(d_n_neigh);
         dev_free(d_last_pos);
-        HB2_TRY(dev_alloc(&d_order, N));
-        HB2_TRY(dev_alloc(&d_n_neigh, N));
-        HB2_TRY(dev_alloc(&d_last_pos, N));
-        cap_N = N;
+        HB2_TRY(dev_alloc(&d_order, cap));
+        HB2_TRY(dev_alloc(&d_n_neigh, cap));
+        HB2_TRY(dev_alloc(&d_last_pos, cap));
+        cap_N = cap;
         }
     if (pitch == 0)
         {
         // first guess from the mean density; grows on overflow like hoomd/md/NeighborList.cc:1601-1617
         const double vol = sys->box.L[0] * sys->box.L[1] * sys->box.L[2];
         const double rl = rcut_max_max + buffer;
-        const double est = (double)N / vol * 4.18879020478639 * rl * rl * rl;
-        pitch = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 16.0), (double)std::max(N, 8u));
+        const double Ng = D.active ? (double)D.N_global : (double)sys->N;
+        const double est = Ng / vol * 4.18879020478639 * rl * rl * rl;
+        pitch = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 16.0), std::max(Ng, 8.0));
         pitch = (pitch + 31u) & ~31u; // rows are padded to whole 32-entry chunks
         }
-    if ((size_t)N * pitch > nlist_cap)
+    // rows exist for owned particles only; leave room for the owned count to drift between builds
+    const size_t rows = D.active ? std::min<size_t>(cap, (size_t)(sys->N * 1.1) + 1024) : sys->N;
+    if (rows * pitch > nlist_cap)
         {
         dev_free(d_nlist);
-        HB2_TRY(dev_alloc(&d_nlist, (size_t)N * pitch));
-        nlist_cap = (size_t)N * pitch;
+        HB2_TRY(dev_alloc(&d_nlist, rows * pitch));
+        nlist_cap = rows * pitch;
         }
     return HB2_OK;
     }
@@ -609,7 +587,7 @@ hb2_status hb2_nlist::ensure_capacity()
 hb2_status hb2_nlist::rebuild(uint64_t timestep)
     {
     hb2_system* s = sys;
-    if (!s->has_box || s->N == 0 || !s->pos[0])
+    if (!s->has_box || !s->pos[0] || (s->N == 0 && !s->dom.active))
         {
         set_error("nlist: the system has no box or no particles");
         return HB2_ERR_INVALID;
@@ -625,26 +603,36 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
                       "the minimum image: rmax=" + std::to_string(rmax));
             return HB2_ERR_BOX_TOO_SMALL;
             }
-    HB2_TRY(ensure_capacity());
-    const uint32_t N = s->N;
     cudaStream_t st = s->stream;
+    if (s->dom.active)
+        {
+        // hoomd/Communicator.cc:1510-1570: migrate, then rebuild the ghost layer, on rebuild steps
+        HB2_TRY(domain_migrate(s));
+        HB2_TRY(domain_exchange_ghosts(s, rmax));
+        }
+    HB2_TRY(ensure_capacity());
+    const uint32_t N = s->N, Ntot = s->N + s->Ng;
 
     HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
     const int c = s->cur, o = 1 - c;
-    HB2_TRY(compute_cell_order(s->pos[c], N, s->box, dim, d_order, d_cell_start, d_conditions, d_tmp,
-                               tmp_bytes, st));
-    HB2_TRY(reorder_particles(d_order, N, s->pos[c], s->vel[c], s->image[c], s->tag[c], nullptr,
+    HB2_TRY(compute_cell_order(s->pos[c], Ntot, N, s->box, geom, d_order, d_cell_start, d_cell_end,
+                               d_conditions, d_tmp, tmp_bytes, st));
+    HB2_TRY(reorder_particles(d_order, Ntot, s->pos[c], s->vel[c], s->image[c], s->tag[c], nullptr,
                               s->pos[o], s->vel[o], s->image[o], s->tag[o], nullptr, s->rtag, st));
     s->cur = o;
     s->order_epoch++;
+    if (s->dom.active)
+        HB2_TRY(domain_remap(s, d_order, Ntot));
+    HB2_TRY(system_place_dummy(s));
 
     for (;;)
         {
         NlistBuildArgs a;
         a.pos = s->pos[s->cur];
         a.N = N;
-        a.dim = dim;
+        a.geom = geom;
         a.cell_start = d_cell_start;
+        a.cell_end = d_cell_end;
         a.r_listsq = d_r_listsq;
         a.ntypes = s->ntypes;
         a.r_listsq_single = r_listsq[0];
@@ -655,8 +643,10 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
         a.n_neigh = d_n_neigh;
         a.last_pos = d_last_pos;
         a.conditions = d_conditions;
-        a.dummy_index = N;
+        a.dummy_index = Ntot;
         HB2_TRY(launch_nlist_build(a, s->box, st));
+        if (s->dom.active) // every rank must take the same branch below
+            HB2_TRY(domain_allreduce_max_u32(s, d_conditions, 3));
         HB2_CUDA(cudaMemcpyAsync(h_conditions, d_conditions, 4 * sizeof(uint32_t),
                                  cudaMemcpyDeviceToHost, st));
         HB2_CUDA(cudaStreamSynchronize(st));
@@ -678,12 +668,8 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
         // overflow: regrow to a multiple of 8 with headroom and rebuild
         // (hoomd/md/NeighborList.cc:411-427, :1601-1617)
         pitch = ((uint32_t)(max_neigh * 1.125) + 8u + 31u) & ~31u;
-        if ((size_t)N * pitch > nlist_cap)
-            {
-            dev_free(d_nlist);
-            HB2_TRY(dev_alloc(&d_nlist, (size_t)N * pitch));
-            nlist_cap = (size_t)N * pitch;
-            }
+        nlist_cap = 0;
+        HB2_TRY(ensure_capacity());
         HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
         }
     if (has_list && timestep > last_update_step)
@@ -763,6 +749,7 @@ extern "C" void hb2_nlist_destroy(hb2_nlist* nl)
     cudaStreamSynchronize(s->stream);
     s->nlists.erase(std::remove(s->nlists.begin(), s->nlists.end(), nl), s->nlists.end());
     dev_free(nl->d_cell_start);
+    dev_free(nl->d_cell_end);
     dev_free(nl->d_order);
     if (nl->d_tmp)
         cudaFree(nl->d_tmp);
@@ -807,9 +794,8 @@ extern "C" hb2_status hb2_nlist_dimensions(const hb2_nlist* nl, uint32_t dim[3])
     {
     if (!nl || !dim)
         return HB2_ERR_INVALID;
-    dim[0] = nl->dim.x;
-    dim[1] = nl->dim.y;
-    dim[2] = nl->dim.z;
+    for (int d = 0; d < 3; d++)
+        dim[d] = nl->geom.dimi[d];
     return HB2_OK;
     }
 
@@ -824,12 +810,12 @@ static hb2_status nlist_download(hb2_nlist* nl, std::vector<uint32_t>& n_neigh,
         }
     const uint32_t N = s->N;
     n_neigh.resize(N);
-    tag.resize(N);
+    tag.resize((size_t)N + s->Ng);
     list.resize((size_t)N * nl->pitch);
     HB2_CUDA(cudaMemcpyAsync(n_neigh.data(), nl->d_n_neigh, sizeof(uint32_t) * N,
                              cudaMemcpyDeviceToHost, s->stream));
-    HB2_CUDA(cudaMemcpyAsync(tag.data(), s->tag[s->cur], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost,
-                             s->stream));
+    HB2_CUDA(cudaMemcpyAsync(tag.data(), s->tag[s->cur], sizeof(uint32_t) * tag.size(),
+                             cudaMemcpyDeviceToHost, s->stream));
     HB2_CUDA(cudaMemcpyAsync(list.data(), nl->d_nlist, sizeof(uint32_t) * (size_t)N * nl->pitch,
                              cudaMemcpyDeviceToHost, s->stream));
     HB2_CUDA(cudaStreamSynchronize(s->stream));
@@ -854,6 +840,8 @@ extern "C" hb2_status hb2_nlist_pair_count(hb2_nlist* nl, uint64_t* n_pairs)
     for (uint32_t v : nn)
         t += v;
     *n_pairs = t / 2; // full list: every unordered pair is stored twice
+    if (nl->sys->dom.active)
+        *n_pairs = t; // upper bound: pairs with a ghost are stored once on each of the two owners
     return HB2_OK;
     }
 
@@ -871,7 +859,9 @@ extern "C" hb2_status hb2_nlist_pair_list(hb2_nlist* nl, uint32_t* pairs, uint64
         for (uint32_t k = 0; k < nn[i]; k++)
             {
             const uint32_t j = list[(size_t)i * nl->pitch + k];
-            if (i < j) // half-list view: each unordered pair once (hoomd/md/NeighborList.cc:1814-1828)
+            // half-list view: each unordered pair once (hoomd/md/NeighborList.cc:1814-1828). A pair
+            // with a ghost is also listed by the ghost's owner: the smaller tag keeps it.
+            if (j < N ? i < j : tag[i] < tag[j])
                 {
                 if (n < cap)
                     {
@@ -897,6 +887,8 @@ extern "C" hb2_status hb2_nlist_stats(hb2_nlist* nl, double* mean_neigh, uint32_
         return HB2_ERR_INVALID;
     uint64_t np = 0;
     HB2_TRY(hb2_nlist_pair_count(nl, &np));
+    if (nl->sys->dom.active)
+        np /= 2;
     if (mean_neigh)
         *mean_neigh = nl->sys->N ? 2.0 * (double)np / nl->sys->N : 0.0;
     if (max_neigh)
@@ -1024,15 +1016,28 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
     hb2_system* s = sys;
     if (params_dirty)
         HB2_TRY(upload_params());
+    const uint64_t builds_before = nl->num_builds;
     HB2_TRY(nl->compute(timestep, flag_known, flag_value));
+    if (s->dom.active)
+        {
+        // DPD reads the velocities of its neighbours (hoomd/md/PotentialPairDPDThermo.h:274-286
+        // requests the ghost velocity flag for the same reason)
+        if (ev == HB2_EVAL_DPD && !s->dom.need_vel)
+            s->dom.need_vel = true;
+        // a rebuild has just exchanged the ghost layer; otherwise refresh it
+        // (Communicator::beginUpdateGhosts, hoomd/Communicator.cc:2630)
+        if (nl->num_builds == builds_before)
+            HB2_TRY(domain_update_ghosts(s));
+        }
     const uint32_t N = s->N;
-    if (N > cap_N)
+    if (s->cap > cap_N)
         {
         dev_free(d_force);
         dev_free(d_virial);
-        HB2_TRY(dev_alloc(&d_force, N));
-        HB2_TRY(dev_alloc(&d_virial, 6 * (size_t)N));
-        cap_N = N;
+        HB2_TRY(dev_alloc(&d_force, s->cap));
+        HB2_TRY(dev_alloc(&d_virial, 6 * (size_t)s->cap));
+        cap_N = s->cap;
+        computed = false;
         }
     PairArgs a;
     a.pos = s->pos[s->cur];
@@ -1052,7 +1057,7 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
     a.ntypes = s->ntypes;
     a.force = d_force;
     a.virial = s->compute_virial ? d_virial : nullptr;
-    a.virial_pitch = N;
+    a.virial_pitch = cap_N;
     a.seed = s->seed;
     a.d_timestep = nullptr;
     a.timestep = timestep;
@@ -1225,8 +1230,8 @@ static hb2_status pair_download(hb2_pair* p, std::vector<float4>& f, std::vector
                              s->stream));
     if (vir)
         {
-        vir->resize(6 * (size_t)N);
-        HB2_CUDA(cudaMemcpyAsync(vir->data(), p->d_virial, sizeof(float) * 6 * (size_t)N,
+        vir->resize(6 * (size_t)p->cap_N);
+        HB2_CUDA(cudaMemcpyAsync(vir->data(), p->d_virial, sizeof(float) * 6 * (size_t)p->cap_N,
                                  cudaMemcpyDeviceToHost, s->stream));
         }
     HB2_CUDA(cudaStreamSynchronize(s->stream));
@@ -1237,6 +1242,11 @@ extern "C" hb2_status hb2_pair_get_forces(hb2_pair* p, double* forces3)
     {
     if (!p || !forces3)
         return HB2_ERR_INVALID;
+    if (p->sys->dom.active)
+        {
+        set_error("the system is domain decomposed: use hb2_pair_get_local and gather by tag");
+        return HB2_ERR_INVALID;
+        }
     std::vector<float4> f;
     std::vector<uint32_t> tag;
     HB2_TRY(pair_download(p, f, nullptr, tag));
@@ -1253,6 +1263,11 @@ extern "C" hb2_status hb2_pair_get_energies(hb2_pair* p, double* energies)
     {
     if (!p || !energies)
         return HB2_ERR_INVALID;
+    if (p->sys->dom.active)
+        {
+        set_error("the system is domain decomposed: use hb2_pair_get_local and gather by tag");
+        return HB2_ERR_INVALID;
+        }
     std::vector<float4> f;
     std::vector<uint32_t> tag;
     HB2_TRY(pair_download(p, f, nullptr, tag));
@@ -1265,6 +1280,11 @@ extern "C" hb2_status hb2_pair_get_virials(hb2_pair* p, double* virials6)
     {
     if (!p || !virials6)
         return HB2_ERR_INVALID;
+    if (p->sys->dom.active)
+        {
+        set_error("the system is domain decomposed: use hb2_pair_get_local and gather by tag");
+        return HB2_ERR_INVALID;
+        }
     if (!p->sys->compute_virial)
         {
         set_error("virials are not computed unless the pressure flag is set "
@@ -1278,7 +1298,41 @@ extern "C" hb2_status hb2_pair_get_virials(hb2_pair* p, double* virials6)
     const size_t N = f.size();
     for (size_t k = 0; k < N; k++)
         for (int q = 0; q < 6; q++)
-            virials6[6 * (size_t)tag[k] + q] = v[q * N + k];
+            virials6[6 * (size_t)tag[k] + q] = v[q * (size_t)p->cap_N + k];
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_get_local(hb2_pair* p, uint32_t* tag_out, double* forces3,
+                                         double* energies, double* virials6)
+    {
+    if (!p)
+        return HB2_ERR_INVALID;
+    if (virials6 && !p->sys->compute_virial)
+        {
+        set_error("virials are not computed unless the pressure flag is set "
+                  "(always_compute_pressure)");
+        return HB2_ERR_INVALID;
+        }
+    std::vector<float4> f;
+    std::vector<float> v;
+    std::vector<uint32_t> tag;
+    HB2_TRY(pair_download(p, f, virials6 ? &v : nullptr, tag));
+    for (size_t k = 0; k < f.size(); k++)
+        {
+        if (tag_out)
+            tag_out[k] = tag[k];
+        if (forces3)
+            {
+            forces3[3 * k] = f[k].x;
+            forces3[3 * k + 1] = f[k].y;
+            forces3[3 * k + 2] = f[k].z;
+            }
+        if (energies)
+            energies[k] = f[k].w;
+        if (virials6)
+            for (int q = 0; q < 6; q++)
+                virials6[6 * k + q] = v[q * (size_t)p->cap_N + k];
+        }
     return HB2_OK;
     }
 
@@ -1287,8 +1341,10 @@ static hb2_status sums7(hb2_pair* p, double out[7])
     hb2_system* s = p->sys;
     HB2_CUDA(cudaSetDevice(s->device));
     HB2_TRY(pair_ensure(p));
-    HB2_TRY(launch_reduce_energy(p->d_force, p->virial_valid ? p->d_virial : nullptr, s->N, s->N,
+    HB2_TRY(launch_reduce_energy(p->d_force, p->virial_valid ? p->d_virial : nullptr, p->cap_N, s->N,
                                  s->d_partial, s->d_ticket + 1, s->d_sums + 1, s->stream));
+    if (s->dom.active) // collective: every rank asks for the same quantity (as with MPI in the reference)
+        HB2_TRY(domain_allreduce_sum_f64(s, s->d_sums + 1, 7));
     HB2_CUDA(cudaMemcpyAsync(out, s->d_sums + 1, 7 * sizeof(double), cudaMemcpyDeviceToHost,
                              s->stream));
     HB2_CUDA(cudaStreamSynchronize(s->stream));
@@ -1361,6 +1417,11 @@ extern "C" hb2_status hb2_pair_set_tail_correction(hb2_pair* p, int on)
     if (on && p->ev != HB2_EVAL_LJ)
         {
         set_error("tail_correction is only available for the LJ evaluator");
+        return HB2_ERR_INVALID;
+        }
+    if (on && p->sys->dom.active)
+        {
+        set_error("tail_correction is not available with a domain decomposition on this path");
         return HB2_ERR_INVALID;
         }
     p->tail_correction = on != 0;
@@ -1453,12 +1514,11 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     HB2_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
     pf->dt = it->dt;
-    const uint32_t N = s->N;
     double* d_ke = s->d_sums;
     double* d_rescale = s->d_sums + 8;
     // translational degrees of freedom of filter All, momentum conserving, 3D
     // (hoomd/md/IntegratorTwoStep.cc:154-189)
-    const double dof = 3.0 * N - 3.0;
+    const double dof = 3.0 * (double)(s->dom.active ? s->dom.N_global : s->N) - 3.0;
 
     // System::run resets the per-run statistics of every compute (hoomd/System.cc:103-110 ->
     // NeighborList::resetStats, hoomd/md/NeighborList.cc:1420-1427): num_builds counts this run only
@@ -1473,7 +1533,11 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         it->prepared = true;
         }
     if (it->thermostat == 1)
-        HB2_TRY(launch_kinetic(s->vel[s->cur], N, s->d_partial, s->d_ticket, d_ke, st));
+        {
+        HB2_TRY(launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket, d_ke, st));
+        if (s->dom.active)
+            HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
+        }
 
     it->pool_used = 0;
     it->marks.clear();
@@ -1500,12 +1564,15 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             rescale = d_rescale;
             }
         const bool check = nl->has_list && nl->check_dist;
-        HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], pf->d_force, s->image[s->cur], N,
+        HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], pf->d_force, s->image[s->cur], s->N,
                                 s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
                                 nl->maxshift(), nl->d_conditions + 3, st));
         bool flag = false;
         if (check)
             {
+            // all ranks rebuild on the same step (hoomd/md/NeighborList.cc:1271-1285)
+            if (s->dom.active)
+                HB2_TRY(domain_allreduce_max_u32(s, nl->d_conditions + 3, 1));
             // the one host read per step of the reference's loop (hoomd/md/NeighborListGPU.cc:78-82)
             HB2_CUDA(cudaMemcpyAsync(nl->h_conditions + 3, nl->d_conditions + 3, sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, st));
@@ -1526,8 +1593,10 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             HB2_CUDA(cudaEventRecord(pe[3], st));
             it->phase_n[1] += nl->num_builds - builds_before;
             }
-        HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, N, (float)it->dt, nullptr, s->d_partial,
+        HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
                                 s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st));
+        if (it->thermostat == 1 && s->dom.active)
+            HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
         if (it->profiling)
             HB2_CUDA(cudaEventRecord(pe[4], st));
         s->timestep = t + 1;
@@ -1594,6 +1663,8 @@ extern "C" hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic,
     double ke = 0.0;
     HB2_TRY(launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket + 2, s->d_sums + 9,
                            s->stream));
+    if (s->dom.active)
+        HB2_TRY(domain_allreduce_sum_f64(s, s->d_sums + 9, 1));
     HB2_CUDA(cudaMemcpyAsync(&ke, s->d_sums + 9, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     HB2_CUDA(cudaStreamSynchronize(s->stream));
     if (kinetic)

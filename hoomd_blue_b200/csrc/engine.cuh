@@ -1,0 +1,194 @@
+// engine.cuh — the engine's host-side objects (shared by engine.cu and comm.cu). See engine.cu for
+// the reference classes each one mirrors.
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+#include "comm.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace hb2
+    {
+template<class T> inline hb2_status dev_alloc(T** p, size_t n)
+    {
+    *p = nullptr;
+    if (n == 0)
+        n = 1;
+    HB2_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    return HB2_OK;
+    }
+template<class T> inline void dev_free(T*& p)
+    {
+    if (p)
+        cudaFree(p);
+    p = nullptr;
+    }
+    } // namespace hb2
+
+using namespace hb2;
+
+#define HB2_TRY(expr)              \
+    do                             \
+        {                          \
+        hb2_status _s = (expr);    \
+        if (_s != HB2_OK)          \
+            return _s;             \
+        } while (0)
+
+// =================================================================================================
+struct hb2_system
+    {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t ntypes = 1;
+    uint32_t seed = 0;
+    hb2_box box;
+    bool has_box = false;
+    uint32_t N = 0;   // owned particles, indices [0, N)
+    uint32_t Ng = 0;  // ghost particles of the domain decomposition, indices [N, N + Ng)
+    uint32_t cap = 0; // capacity of every per-particle array (N + Ng + 1 <= cap; the slot after the
+                      // last ghost holds the far-away dummy that pads neighbour-list rows)
+    Domain dom;
+    uint64_t timestep = 0;
+    uint64_t* d_timestep = nullptr;
+    bool compute_virial = false;
+
+    // particle arrays, double buffered: every nlist rebuild gathers them into cell order
+    float4* pos[2] = {nullptr, nullptr};
+    float4* vel[2] = {nullptr, nullptr};
+    int* image[2] = {nullptr, nullptr};
+    uint32_t* tag[2] = {nullptr, nullptr};
+    uint32_t* rtag = nullptr;
+    int cur = 0;
+    uint64_t order_epoch = 0; // bumped whenever the particle order changes
+
+    // reduction scratch
+    double* d_partial = nullptr;
+    uint32_t* d_ticket = nullptr;
+    double* d_sums = nullptr; // [0] KE, [1..7] PE + virial, [8] rescale factor
+
+    std::vector<hb2_nlist*> nlists;
+    std::vector<hb2_pair*> pairs;
+    cudaEvent_t mid_event = nullptr; // recorded between the nlist update and the force launch
+
+    hb2_status set_timestep(uint64_t t)
+        {
+        timestep = t;
+        HB2_CUDA(cudaMemcpyAsync(d_timestep, &timestep, sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                 stream));
+        HB2_CUDA(cudaStreamSynchronize(stream));
+        return HB2_OK;
+        }
+    };
+
+struct hb2_nlist
+    {
+    hb2_system* sys = nullptr;
+    double buffer = 0.4;
+    uint32_t rebuild_check_delay = 1;
+    bool check_dist = true;
+
+    std::vector<hb2_pair*> consumers;
+    std::vector<double> r_cut, r_listsq, rcut_max;
+    double rcut_max_max = 0.0, r_list_min = 0.0;
+    bool params_dirty = true;
+
+    DomainGeom geom;  // cell grid of the last build (dimi = dimensions reported to Python)
+    uint32_t cell_cap = 0;
+    uint32_t* d_cell_start = nullptr;
+    uint32_t* d_cell_end = nullptr;
+    uint32_t* d_order = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    double* d_r_listsq = nullptr;
+
+    uint32_t* d_nlist = nullptr;
+    uint32_t pitch = 0;
+    size_t nlist_cap = 0;
+    uint32_t* d_n_neigh = nullptr;
+    float4* d_last_pos = nullptr;
+    uint32_t cap_N = 0;
+    uint32_t* d_conditions = nullptr; // [0] max n_neigh, [1] nan idx+1, [2] oob idx+1, [3] rebuild flag
+    uint32_t* h_conditions = nullptr; // pinned mirror
+
+    bool force_update = true;
+    bool has_list = false;
+    uint64_t num_builds = 0;
+    uint64_t last_update_step = 0;
+    uint64_t shortest_rebuild = ~0ull;
+    uint32_t max_neigh = 0;
+
+    hb2_status update_r_list();
+    hb2_status ensure_capacity();
+    hb2_status rebuild(uint64_t timestep);
+    hb2_status compute(uint64_t timestep, bool flag_known, bool flag_value);
+    float maxshift() const
+        {
+        // hoomd/md/NeighborList.cc:1244-1260 with a fixed box (lambda = 1): (r_max - r_min)/2
+        return (float)(buffer / 2.0);
+        }
+    };
+
+struct hb2_pair
+    {
+    hb2_system* sys = nullptr;
+    hb2_nlist* nl = nullptr;
+    hb2_evaluator ev = HB2_EVAL_LJ;
+    hb2_shift_mode mode = HB2_SHIFT_NONE;
+    std::vector<double> user; // ntypes^2 x 2 user parameters
+    std::vector<uint8_t> have_params;
+    std::vector<double> r_cut, r_on;
+    std::vector<float> packed, rcutsq, ronsq;
+    float* d_params = nullptr;
+    float* d_rcutsq = nullptr;
+    float* d_ronsq = nullptr;
+    bool params_dirty = true;
+    double kT = 1.0;
+    double dt = 0.005;
+    uint32_t tpp = 8;
+    bool tail_correction = false;
+
+    float4* d_force = nullptr;
+    float* d_virial = nullptr;
+    uint32_t cap_N = 0;
+    bool virial_valid = false;
+    bool computed = false;
+    uint64_t computed_step = 0, computed_epoch = 0;
+
+    hb2_status upload_params();
+    hb2_status compute(uint64_t timestep, bool flag_known = false, bool flag_value = false);
+    };
+
+struct hb2_integrator
+    {
+    hb2_system* sys = nullptr;
+    double dt = 0.005;
+    std::vector<hb2_pair*> forces;
+    int thermostat = 0;
+    double kT = 1.0, tau = 0.0;
+    bool prepared = false;
+    uint64_t prepared_epoch = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    // optional per-phase device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    std::vector<size_t> marks; // five events per step: a b c d e
+    double phase_ms[3] = {0, 0, 0}; // integrate, nlist, force
+    uint64_t phase_n[3] = {0, 0, 0};
+    cudaEvent_t next_event()
+        {
+        if (pool_used == pool.size())
+            {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+            }
+        return pool[pool_used++];
+        }
+    };
+

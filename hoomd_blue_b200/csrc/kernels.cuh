@@ -1,14 +1,18 @@
 // kernels.cuh — internal launcher interface shared by the C-ABI layers (capi.cu, engine.cu).
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 
 namespace hb2
     {
 // ---- binning.cu
 size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc);
-hb2_status compute_cell_order(const float4* d_pos, uint32_t N, const hb2_box& box, uint3 dim,
-                              uint32_t* d_order, uint32_t* d_cell_start, uint32_t* d_conditions,
-                              void* d_tmp, size_t tmp_bytes, cudaStream_t stream);
+// N particles of which the first N_owned are owned (the rest are ghosts of a domain decomposition);
+// geom.n = {1,1,1} is the single-GPU periodic grid. d_cell_start / d_cell_end: Nc entries each.
+hb2_status compute_cell_order(const float4* d_pos, uint32_t N, uint32_t N_owned, const hb2_box& box,
+                              const DomainGeom& geom, uint32_t* d_order, uint32_t* d_cell_start,
+                              uint32_t* d_cell_end, uint32_t* d_conditions, void* d_tmp,
+                              size_t tmp_bytes, cudaStream_t stream);
 hb2_status reorder_particles(const uint32_t* d_order, uint32_t N, const float4* pos_in,
                              const float4* vel_in, const int* img_in, const uint32_t* tag_in,
                              const float4* force_in, float4* pos_out, float4* vel_out, int* img_out,
@@ -20,8 +24,9 @@ struct NlistBuildArgs
     {
     const float4* pos;          // cell-ordered positions, N_local first-class rows
     uint32_t N;                 // particles that get a row
-    uint3 dim;                  // cell grid
-    const uint32_t* cell_start; // Nc + 1
+    DomainGeom geom;            // cell grid (dimt) and decomposition (n = 1: periodic ring)
+    const uint32_t* cell_start; // Nc
+    const uint32_t* cell_end;   // Nc
     const double* r_listsq;     // ntypes^2 doubles (device), tj*ntypes+ti
     uint32_t ntypes;
     double r_listsq_single;     // copy of r_listsq[0] for the one-type fast path

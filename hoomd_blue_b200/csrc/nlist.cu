@@ -109,6 +109,24 @@ HB2_DEVICE uint32_t nth_set_bit(uint32_t m, uint32_t q)
     return t;
     }
 
+// The same along a dimension that may be decomposed over n ranks (this rank at grid coordinate rc):
+// the local grid is then open — interior home cells 1..dim-2 always have both neighbours — and only
+// the ghost-cell layers that lie across the GLOBAL periodic boundary carry an image shift.
+HB2_DEVICE int stencil3(int c, int dim, int n, int rc, int k, int& coord, int& shift)
+    {
+    if (n > 1)
+        {
+        coord = c - 1 + k;
+        shift = 0;
+        if (coord == 0 && rc == 0)
+            shift = -1;
+        else if (coord == dim - 1 && rc == n - 1)
+            shift = 1;
+        return 3;
+        }
+    return ring3(c, dim, k, coord, shift);
+    }
+
 HB2_DEVICE uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total)
     {
     uint32_t incl = v;
@@ -127,8 +145,9 @@ HB2_DEVICE uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total)
 // both images of a neighbour and the sweep applies the minimum image itself.
 template<bool MULTITYPE, bool SMALLDIM>
 __global__ void __launch_bounds__(NL_WARPS * 32)
-    nlist_build_kernel(const float4* __restrict__ pos, uint32_t N, uint3 dim,
+    nlist_build_kernel(const float4* __restrict__ pos, uint32_t N, DomainGeom geom,
                        const uint32_t* __restrict__ cell_start,
+                       const uint32_t* __restrict__ cell_end,
                        const double* __restrict__ r_listsq, uint32_t ntypes, double r_listsq_single,
                        NlConst cst, uint32_t* __restrict__ nlist, uint32_t pitch,
                        uint32_t* __restrict__ n_neigh, float4* __restrict__ last_pos,
@@ -151,21 +170,23 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
         __syncthreads();
         }
 
+    const uint3 dim = make_uint3(geom.dimt[0], geom.dimt[1], geom.dimt[2]);
     const uint32_t Nc = dim.x * dim.y * dim.z;
     const uint32_t cell = blockIdx.x * NL_WARPS + (threadIdx.x >> 5);
     if (cell >= Nc)
         return;
+    // owned particles occupy [0, N) in cell order; ghost-layer cells start at or beyond N
     const uint32_t h0 = cell_start[cell];
-    const uint32_t hend = min(cell_start[cell + 1], N);
+    const uint32_t hend = min(cell_end[cell], N);
     if (h0 >= hend)
         return;
 
     // ---- 1. stencil cells, one per lane, ascending cell id
     const int cx = cell % dim.x, cy = (cell / dim.x) % dim.y, cz = cell / (dim.x * dim.y);
     int dummy_c, dummy_s;
-    const int cnx = ring3(cx, dim.x, 0, dummy_c, dummy_s);
-    const int cny = ring3(cy, dim.y, 0, dummy_c, dummy_s);
-    const int cnz = ring3(cz, dim.z, 0, dummy_c, dummy_s);
+    const int cnx = stencil3(cx, dim.x, geom.n[0], geom.coord[0], 0, dummy_c, dummy_s);
+    const int cny = stencil3(cy, dim.y, geom.n[1], geom.coord[1], 0, dummy_c, dummy_s);
+    const int cnz = stencil3(cz, dim.z, geom.n[2], geom.coord[2], 0, dummy_c, dummy_s);
     const int ncells = cnx * cny * cnz;
     uint32_t c_start = 0, c_cnt = 0;
     float shx = 0.f, shy = 0.f, shz = 0.f;
@@ -174,12 +195,12 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
         {
         const int kx = lane % cnx, ky = (lane / cnx) % cny, kz = lane / (cnx * cny);
         int nx, ny, nz, sx, sy, sz;
-        ring3(cx, dim.x, kx, nx, sx);
-        ring3(cy, dim.y, ky, ny, sy);
-        ring3(cz, dim.z, kz, nz, sz);
+        stencil3(cx, dim.x, geom.n[0], geom.coord[0], kx, nx, sx);
+        stencil3(cy, dim.y, geom.n[1], geom.coord[1], ky, ny, sy);
+        stencil3(cz, dim.z, geom.n[2], geom.coord[2], kz, nz, sz);
         const uint32_t cid = ((uint32_t)nz * dim.y + (uint32_t)ny) * dim.x + (uint32_t)nx;
         c_start = __ldg(cell_start + cid);
-        c_cnt = __ldg(cell_start + cid + 1) - c_start;
+        c_cnt = __ldg(cell_end + cid) - c_start;
         shx = (float)sx * cst.bf.L[0];
         shy = (float)sy * cst.bf.L[1];
         shz = (float)sz * cst.bf.L[2];
@@ -442,7 +463,7 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
 template<bool MT, bool SD>
 static hb2_status launch_variant(const NlistBuildArgs& a, const NlConst& cst, cudaStream_t stream)
     {
-    const uint32_t Nc = a.dim.x * a.dim.y * a.dim.z;
+    const uint32_t Nc = a.geom.dimt[0] * a.geom.dimt[1] * a.geom.dimt[2];
     const uint32_t blocks = (Nc + NL_WARPS - 1) / NL_WARPS;
     const size_t smem = sizeof(NlWarpSmem) * NL_WARPS + sizeof(float2) * (MT ? a.ntypes * a.ntypes : 1);
     static bool attr = false;
@@ -455,7 +476,7 @@ static hb2_status launch_variant(const NlistBuildArgs& a, const NlConst& cst, cu
         attr_smem = smem;
         }
     nlist_build_kernel<MT, SD><<<blocks, NL_WARPS * 32, smem, stream>>>(
-        a.pos, a.N, a.dim, a.cell_start, a.r_listsq, a.ntypes, a.r_listsq_single, cst, a.nlist,
+        a.pos, a.N, a.geom, a.cell_start, a.cell_end, a.r_listsq, a.ntypes, a.r_listsq_single, cst, a.nlist,
         a.pitch, a.n_neigh, a.last_pos, a.conditions, a.dummy_index);
     HB2_CHECK_LAUNCH("nlist_build_kernel");
     return HB2_OK;
@@ -483,7 +504,10 @@ hb2_status launch_nlist_build(const NlistBuildArgs& a, const hb2_box& box, cudaS
         band = 0.25;
     cst.band = (float)band;
 
-    const bool small = a.dim.x < 3 || a.dim.y < 3 || a.dim.z < 3;
+    // only a periodic ring of fewer than 3 cells can hold two images of one neighbour
+    bool small = false;
+    for (int d = 0; d < 3; d++)
+        small = small || (a.geom.n[d] == 1 && a.geom.dimt[d] < 3);
     if (a.ntypes > 1)
         return small ? launch_variant<true, true>(a, cst, stream)
                      : launch_variant<true, false>(a, cst, stream);

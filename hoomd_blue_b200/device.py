@@ -1,5 +1,6 @@
 """hoomd.device for this path (hoomd/device.py). Only GPU exists: there is no CPU implementation."""
 from . import _lib
+from .communicator import Communicator
 
 
 class Device:
@@ -12,6 +13,10 @@ class GPU(Device):
     def __init__(self, gpu_ids=None, gpu_id=None, **kwargs):
         if gpu_ids is not None and gpu_id is None:
             gpu_id = gpu_ids[0] if hasattr(gpu_ids, "__len__") else gpu_ids
+        self.communicator = kwargs.get("communicator") or Communicator()
+        if gpu_id is None and self.communicator.num_ranks > 1:
+            import os
+            gpu_id = int(os.environ.get("LOCAL_RANK", self.communicator.rank))
         self.gpu_id = int(gpu_id or 0)
         _lib.lib()  # fail loudly now if the CUDA library is not built
 

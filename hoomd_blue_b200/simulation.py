@@ -11,6 +11,7 @@ import time
 import numpy as np
 
 from . import _lib
+from . import communicator as _comm
 from ._lib import check, ptr
 
 
@@ -90,22 +91,76 @@ class _BoxView:
 
 
 class State:
-    """Particle state resident in HBM (hb2_system)."""
+    """Particle state resident in HBM (hb2_system). With more than one rank in the process group the
+    box is split into a 3D grid of domains (hoomd/state.py domain_decomposition,
+    hoomd/DomainDecomposition.cc) and this object holds one domain."""
 
-    def __init__(self, simulation, snapshot):
+    def __init__(self, simulation, snapshot, domain_decomposition=(None, None, None), local=None):
         L = _lib.lib()
         self._simulation = simulation
-        self._types = list(snapshot.particles.types)
-        self._box = [float(v) for v in snapshot.configuration.box]
+        comm = simulation.device.communicator
+        snapshot_types, box = None, None
+        if snapshot is not None and (comm.rank == 0 or snapshot.particles.N > 0):
+            snapshot_types, box = list(snapshot.particles.types), list(snapshot.configuration.box)
+        if comm.num_ranks > 1:
+            snapshot_types, box = _comm.broadcast_object((snapshot_types, box))
+        self._types = snapshot_types
+        self._box = [float(v) for v in box]
         h = C.c_void_p()
         check(L.hb2_system_create(C.byref(h), simulation.device.gpu_id, len(self._types),
                                   simulation.seed & 0xFFFF))
         self._h = h
         check(L.hb2_system_set_box(h, *self._box))
-        self.set_snapshot(snapshot)
+        self._grid = (1, 1, 1)
+        if comm.num_ranks > 1:
+            grid = (C.c_uint32 * 3)()
+            if all(g is not None for g in domain_decomposition):
+                for k in range(3):
+                    grid[k] = int(domain_decomposition[k])
+            else:
+                check(L.hb2_domain_find_decomposition(comm.num_ranks, *self._box[:3], grid))
+            uid = (C.c_uint8 * 128)()
+            if comm.rank == 0:
+                check(L.hb2_comm_unique_id(uid))
+            raw = _comm.broadcast_object(bytes(uid))
+            uid = (C.c_uint8 * 128).from_buffer_copy(raw)
+            check(L.hb2_system_set_domain(h, grid, comm.rank, comm.num_ranks, uid))
+            self._grid = tuple(int(g) for g in grid)
+        if local is not None:
+            self._set_tagged(*local)
+        else:
+            self.set_snapshot(snapshot)
+
+    @property
+    def domain_decomposition(self):
+        return self._grid
+
+    def _set_tagged(self, n_global, tag, pos, vel, typeid=None, mass=None, image=None):
+        L = _lib.lib()
+        n = len(pos)
+        tag = np.ascontiguousarray(tag, dtype=np.uint32)
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        vel = np.ascontiguousarray(vel, dtype=np.float32)
+        tid = np.ascontiguousarray(typeid if typeid is not None else np.zeros(n), dtype=np.uint32)
+        mass = np.ascontiguousarray(mass if mass is not None else np.ones(n), dtype=np.float32)
+        img = np.ascontiguousarray(image if image is not None else np.zeros((n, 3)), dtype=np.int32)
+        check(L.hb2_system_set_particles_tagged(self._h, n, int(n_global), ptr(tag, C.c_uint32),
+                                                ptr(pos, C.c_float), ptr(vel, C.c_float),
+                                                ptr(mass, C.c_float), ptr(tid, C.c_uint32),
+                                                ptr(img, C.c_int32)))
 
     def set_snapshot(self, snapshot):
         L = _lib.lib()
+        comm = self._simulation.device.communicator
+        if comm.num_ranks > 1:
+            # the reference scatters rank 0's snapshot (hoomd/ParticleData.cc initializeFromSnapshot);
+            # here every rank receives it and the engine keeps the particles it owns
+            p = snapshot.particles if comm.rank == 0 else None
+            data = _comm.broadcast_object(
+                None if p is None else (p.position, p.velocity, p.typeid, p.mass, p.image))
+            pos, vel, tid, mass, img = data
+            self._set_tagged(len(pos), np.arange(len(pos), dtype=np.uint32), pos, vel, tid, mass, img)
+            return
         p = snapshot.particles
         pos = np.ascontiguousarray(p.position, dtype=np.float32)
         vel = np.ascontiguousarray(p.velocity, dtype=np.float32)
@@ -116,6 +171,20 @@ class State:
                                          ptr(vel, C.c_float), ptr(mass, C.c_float),
                                          ptr(tid, C.c_uint32), ptr(img, C.c_int32)))
 
+    def _get_local(self):
+        L = _lib.lib()
+        n = int(L.hb2_system_n(self._h))
+        tag = np.zeros(n, dtype=np.uint32)
+        pos = np.zeros((n, 3), dtype=np.float32)
+        vel = np.zeros((n, 3), dtype=np.float32)
+        mass = np.zeros(n, dtype=np.float32)
+        tid = np.zeros(n, dtype=np.uint32)
+        img = np.zeros((n, 3), dtype=np.int32)
+        check(L.hb2_system_get_local(self._h, ptr(tag, C.c_uint32), ptr(pos, C.c_float),
+                                     ptr(vel, C.c_float), ptr(mass, C.c_float), ptr(tid, C.c_uint32),
+                                     ptr(img, C.c_int32)))
+        return tag, pos, vel, mass, tid, img
+
     def get_snapshot(self):
         L = _lib.lib()
         n = self.N_particles
@@ -124,6 +193,16 @@ class State:
         s.particles.N = n
         s.particles.types = list(self._types)
         p = s.particles
+        if self._simulation.device.communicator.num_ranks > 1:
+            # gathered by tag (hoomd/ParticleData.cc takeSnapshot does the same with MPI gathers;
+            # here every rank receives the global snapshot)
+            tag, pos, vel, mass, tid, img = self._get_local()
+            p.position[:] = _comm.gather_by_tag(n, tag, pos)
+            p.velocity[:] = _comm.gather_by_tag(n, tag, vel)
+            p.mass[:] = _comm.gather_by_tag(n, tag, mass)
+            p.typeid[:] = _comm.gather_by_tag(n, tag, tid)
+            p.image[:] = _comm.gather_by_tag(n, tag, img)
+            return s
         check(L.hb2_system_get_particles(self._h, ptr(p.position, C.c_float),
                                          ptr(p.velocity, C.c_float), ptr(p.mass, C.c_float),
                                          ptr(p.typeid, C.c_uint32), ptr(p.image, C.c_int32)))
@@ -131,7 +210,16 @@ class State:
 
     @property
     def N_particles(self):
+        """Global particle count (hoomd/state.py:N_particles)."""
+        return int(_lib.lib().hb2_system_n_global(self._h))
+
+    @property
+    def _N_local(self):
         return int(_lib.lib().hb2_system_n(self._h))
+
+    @property
+    def _N_ghost(self):
+        return int(_lib.lib().hb2_system_n_ghost(self._h))
 
     @property
     def particle_types(self):
@@ -188,7 +276,23 @@ class Simulation:
     def create_state_from_snapshot(self, snapshot, domain_decomposition=(None, None, None)):
         if self.state is not None:
             raise RuntimeError("Cannot initialize more than once\n")
-        self.state = State(self, snapshot)
+        self.state = State(self, snapshot, domain_decomposition)
+        check(_lib.lib().hb2_system_set_timestep(self.state._h, self._initial_timestep))
+        if self._always_compute_pressure:
+            check(_lib.lib().hb2_system_set_compute_virial(self.state._h, 1))
+
+    def _create_state_from_local(self, box, types, n_global, tag, position, velocity, typeid=None,
+                                 mass=None, image=None, domain_decomposition=(None, None, None)):
+        """Every rank passes its own share of a large system (any superset of what it owns; the
+        engine keeps the owned particles). Not in the reference's API: its snapshots always
+        originate on rank 0, which does not scale to the 64 M-particle configuration."""
+        if self.state is not None:
+            raise RuntimeError("Cannot initialize more than once\n")
+        snap = Snapshot()
+        snap.configuration.box = [float(v) for v in box]
+        snap.particles.types = list(types)
+        self.state = State(self, snap, domain_decomposition,
+                           local=(n_global, tag, position, velocity, typeid, mass, image))
         check(_lib.lib().hb2_system_set_timestep(self.state._h, self._initial_timestep))
         if self._always_compute_pressure:
             check(_lib.lib().hb2_system_set_compute_virial(self.state._h, 1))

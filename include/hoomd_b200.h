@@ -92,16 +92,17 @@ typedef enum
  * (:439-565). Bins N particles with the reference's rule (hoomd/CellList.cc:455-470, fp64
  * makeFraction hoomd/BoxDim.h:276-284) on a dim[0] x dim[1] x dim[2] grid, then key-sorts (cell,
  * index) — no atomics, order is deterministic. Outputs: order[k] = old index of the k-th particle in
- * cell order, cell_start[Nc+1] = first sorted slot of each cell. conditions[3] = {0, nan idx+1,
- * out-of-box idx+1} as hoomd/CellList.cc:549-607. tmp/tmp_bytes: scratch; call with tmp = NULL to
- * get the size. */
+ * cell order; cell c owns sorted slots [cell_start[c], cell_end[c]) (Nc entries each, an empty cell
+ * reads [0, 0)). conditions[3] = {0, nan idx+1, out-of-box idx+1} as hoomd/CellList.cc:549-607.
+ * tmp/tmp_bytes: scratch; call with tmp = NULL to get the size. */
 hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N, const hb2_box* box,
                                       const uint32_t dim[3], uint32_t* d_order,
-                                      uint32_t* d_cell_start, uint32_t* d_conditions, void* d_tmp,
-                                      size_t* tmp_bytes, void* stream);
+                                      uint32_t* d_cell_start, uint32_t* d_cell_end,
+                                      uint32_t* d_conditions, void* d_tmp, size_t* tmp_bytes,
+                                      void* stream);
 
 /* Replaces gpu_compute_nlist_binned (hoomd/md/NeighborListGPUBinned.cu:756-824) for particles that
- * are already in cell order (d_pos4 sorted so that cell c owns [cell_start[c], cell_start[c+1])).
+ * are already in cell order (d_pos4 sorted so that cell c owns [cell_start[c], cell_end[c])).
  * Membership rule hoomd/md/NeighborListBinned.cc:144-157: j != i, r_cut(ti,tj) > 0,
  * |minImage(pi - pj)|^2 <= (r_cut(ti,tj) + r_buff)^2 decided in fp64. Full list, row i at
  * d_nlist[i * pitch], ascending j. d_r_listsq: ntypes^2 doubles indexed tj*ntypes+ti
@@ -112,8 +113,9 @@ hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N, const hb2
  * (so d_pos4 — and d_vel4 / d_tag for DPD — need N_total + 1 entries); the force driver relies on it. */
 hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_total,
                                         const hb2_box* box, const uint32_t dim[3],
-                                        const uint32_t* d_cell_start, const double* d_r_listsq,
-                                        uint32_t ntypes, uint32_t* d_nlist, uint32_t pitch,
+                                        const uint32_t* d_cell_start, const uint32_t* d_cell_end,
+                                        const double* d_r_listsq, uint32_t ntypes,
+                                        uint32_t* d_nlist, uint32_t pitch,
                                         uint32_t* d_n_neigh, float* d_last_pos4,
                                         uint32_t* d_conditions, void* stream);
 
@@ -173,7 +175,40 @@ hb2_status hb2_system_set_particles(hb2_system* sys, uint32_t N, const float* po
 /* Snapshot out, tag order. Any pointer may be NULL. */
 hb2_status hb2_system_get_particles(hb2_system* sys, float* pos3, float* vel3, float* mass,
                                     uint32_t* typeid_, int32_t* image3);
-uint32_t hb2_system_n(const hb2_system* sys);
+uint32_t hb2_system_n(const hb2_system* sys); /* owned particles on this rank */
+
+/* ---- domain decomposition (one process per GPU; replaces DomainDecomposition + Communicator:
+ * hoomd/DomainDecomposition.cc:327-409,604-660, hoomd/Communicator.cc:1510-1570). Bootstrap: rank 0
+ * calls hb2_comm_unique_id and broadcasts the 128 bytes (torch.distributed / MPI / any side channel),
+ * then EVERY rank calls hb2_system_set_domain (collective: ncclCommInitRank) before setting particles.
+ * grid = ranks along x, y, z with grid[0]*grid[1]*grid[2] == nranks; rank = (cz*ny + cy)*nx + cx.
+ * With a domain set, set_particles[_tagged] keeps only the particles this rank owns, every run /
+ * compute / energy call is collective, and per-particle results are read with the *_local getters
+ * (local order, with tags) and gathered by the caller. */
+hb2_status hb2_comm_unique_id(void* out128);
+hb2_status hb2_system_set_domain(hb2_system* sys, const uint32_t grid[3], uint32_t rank,
+                                 uint32_t nranks, const void* nccl_unique_id);
+/* hoomd/DomainDecomposition.cc:327-409 (findDecomposition): the grid with the least interface area. */
+hb2_status hb2_domain_find_decomposition(uint32_t nranks, double Lx, double Ly, double Lz,
+                                         uint32_t grid[3]);
+/* Host helpers (no GPU needed): owner rank of each position (placeParticle,
+ * hoomd/DomainDecomposition.cc:604-660) and the ghost-layer plan of one rank (bit 2d: within r_ghost of
+ * the lower face of dimension d, bit 2d+1: of the upper face; hoomd/CommunicatorGPU.cu:306-357). */
+hb2_status hb2_domain_place(const hb2_box* box, const uint32_t grid[3], const float* pos3, uint32_t n,
+                            uint32_t* rank_out);
+hb2_status hb2_domain_ghost_mask(const hb2_box* box, const uint32_t grid[3], const uint32_t coord[3],
+                                 double r_ghost, const float* pos3, uint32_t n, uint8_t* mask_out);
+/* Candidates with explicit global tags (any subset of the N_global particles; with a domain only the
+ * owned ones are kept), e.g. each rank passing just its own slab of a large lattice. */
+hb2_status hb2_system_set_particles_tagged(hb2_system* sys, uint32_t n, uint64_t N_global,
+                                           const uint32_t* tag, const float* pos3, const float* vel3,
+                                           const float* mass, const uint32_t* typeid_,
+                                           const int32_t* image3);
+/* Owned particles in local (cell) order with their tags; arrays of hb2_system_n entries. */
+hb2_status hb2_system_get_local(hb2_system* sys, uint32_t* tag, float* pos3, float* vel3, float* mass,
+                                uint32_t* typeid_, int32_t* image3);
+uint64_t hb2_system_n_global(const hb2_system* sys);
+uint32_t hb2_system_n_ghost(const hb2_system* sys);
 uint64_t hb2_system_timestep(const hb2_system* sys);
 hb2_status hb2_system_set_timestep(hb2_system* sys, uint64_t timestep);
 /* hoomd.Simulation.always_compute_pressure (hoomd/simulation.py:447-483): virials are only computed
@@ -221,7 +256,11 @@ hb2_status hb2_pair_compute(hb2_pair* p, uint64_t timestep);
 hb2_status hb2_pair_get_forces(hb2_pair* p, double* forces3);
 hb2_status hb2_pair_get_energies(hb2_pair* p, double* energies);
 hb2_status hb2_pair_get_virials(hb2_pair* p, double* virials6);
-hb2_status hb2_pair_get_energy(hb2_pair* p, double* energy);
+hb2_status hb2_pair_get_energy(hb2_pair* p, double* energy); /* global sum (collective) */
+/* Local-order results with tags (any output may be NULL): the domain-decomposed counterpart of the
+ * three getters above, hb2_system_n entries each. */
+hb2_status hb2_pair_get_local(hb2_pair* p, uint32_t* tag, double* forces3, double* energies,
+                              double* virials6);
 /* hoomd/md/PotentialPair.h:255-341 (LJ only): isotropic tail correction -> additional energy and
  * the diagonal virial term; off by default. */
 hb2_status hb2_pair_set_tail_correction(hb2_pair* p, int on);
