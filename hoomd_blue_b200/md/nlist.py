@@ -4,6 +4,7 @@ import ctypes as C
 import numpy as np
 
 from .. import _lib
+from .. import communicator as _comm
 from .._lib import check, ptr
 
 
@@ -49,8 +50,10 @@ class NeighborList:
             raise RuntimeError("nlist is not attached (run the simulation first)")  # DataAccessError
 
     @property
-    def pair_list(self):
-        """(n, 2) uint32 tag pairs, each unordered pair once (hoomd/md/nlist.py:293-305)."""
+    def local_pair_list(self):
+        """Tag pairs listed on this rank; a pair that straddles two domains is reported by the
+        owner of its smaller tag only, so the ranks' lists are disjoint
+        (hoomd/md/nlist.py:270-291)."""
         self._need()
         L = _lib.lib()
         n = C.c_uint64(0)
@@ -59,7 +62,15 @@ class NeighborList:
         check(L.hb2_nlist_pair_list(self._h, ptr(out, C.c_uint32), out.shape[0], C.byref(n)))
         return out[:n.value]
 
-    local_pair_list = pair_list
+    @property
+    def pair_list(self):
+        """(n, 2) uint32 tag pairs, each unordered pair once (hoomd/md/nlist.py:293-305). With a
+        domain decomposition the ranks' lists are concatenated (the reference gathers to rank 0;
+        here every rank receives the list)."""
+        local = self.local_pair_list
+        if self._sim.device.communicator.num_ranks > 1:
+            return np.concatenate(_comm.all_gather_arrays(local), axis=0)
+        return local
 
     @property
     def num_builds(self):

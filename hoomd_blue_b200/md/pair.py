@@ -5,6 +5,7 @@ import ctypes as C
 import numpy as np
 
 from .. import _lib
+from .. import communicator as _comm
 from .._lib import check, ptr
 from .typeparam import TypePairDict
 
@@ -26,9 +27,27 @@ class Force:
         if self._h is None:
             raise RuntimeError("force is not attached (run the simulation first)")
 
+    def _decomposed(self):
+        return self._sim.device.communicator.num_ranks > 1
+
+    def _local(self, want_virial=False):
+        """(tags, forces, energies, virials) of the particles this rank owns."""
+        n = self._sim.state._N_local
+        tag = np.zeros(n, dtype=np.uint32)
+        f = np.zeros((n, 3), dtype=np.float64)
+        e = np.zeros(n, dtype=np.float64)
+        v = np.zeros((n, 6), dtype=np.float64) if want_virial else None
+        check(_lib.lib().hb2_pair_get_local(self._h, ptr(tag, C.c_uint32), ptr(f, C.c_double),
+                                            ptr(e, C.c_double),
+                                            ptr(v, C.c_double) if want_virial else None))
+        return tag, f, e, v
+
     @property
     def forces(self):
         self._need()
+        if self._decomposed():
+            tag, f, _, _ = self._local()
+            return _comm.gather_by_tag(self._sim.state.N_particles, tag, f)
         out = np.zeros((self._sim.state.N_particles, 3), dtype=np.float64)
         check(_lib.lib().hb2_pair_get_forces(self._h, ptr(out, C.c_double)))
         return out
@@ -36,6 +55,9 @@ class Force:
     @property
     def energies(self):
         self._need()
+        if self._decomposed():
+            tag, _, e, _ = self._local()
+            return _comm.gather_by_tag(self._sim.state.N_particles, tag, e)
         out = np.zeros(self._sim.state.N_particles, dtype=np.float64)
         check(_lib.lib().hb2_pair_get_energies(self._h, ptr(out, C.c_double)))
         return out
@@ -46,6 +68,9 @@ class Force:
         self._need()
         if not self._sim.always_compute_pressure:
             return None
+        if self._decomposed():
+            tag, _, _, v = self._local(want_virial=True)
+            return _comm.gather_by_tag(self._sim.state.N_particles, tag, v)
         out = np.zeros((self._sim.state.N_particles, 6), dtype=np.float64)
         check(_lib.lib().hb2_pair_get_virials(self._h, ptr(out, C.c_double)))
         return out
