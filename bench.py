@@ -116,9 +116,41 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_sim(hoomd, pos, vel, L, device_id=0, seed=1, thermostat=True):
-    sim = hoomd.Simulation(device=hoomd.device.GPU(gpu_id=device_id), seed=seed)
-    sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays([L, L, L, 0, 0, 0], pos, vel))
+def replicated_c1(repl, grid, coord):
+    """BASELINE.json configs[3]: the equilibrated C1 frame (tests/golden/c1_64k.npz, made by the
+    reference) replicated repl = (nx, ny, nz) times like hoomd.State.replicate (hoomd/state.py:580-609).
+    Returns only the replicas that overlap the domain `coord` of `grid` (tags are global)."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "c1_64k.npz"))
+    p0, v0, L0 = fx["pos"].astype(np.float64), fx["vel"], float(fx["L"][0])
+    n0 = len(p0)
+    L = np.array([np.float32(L0 * r) for r in repl], dtype=np.float64)
+    tags, pos, vel = [], [], []
+    for i in range(repl[0]):
+        for j in range(repl[1]):
+            for k in range(repl[2]):
+                idx = (i, j, k)
+                keep = True
+                for d in range(3):
+                    # replica slab [idx, idx+1) * L0 against the domain [coord, coord+1) * L / grid
+                    lo, hi = idx[d] * L0, (idx[d] + 1) * L0
+                    dlo, dhi = coord[d] * L[d] / grid[d], (coord[d] + 1) * L[d] / grid[d]
+                    keep = keep and hi > dlo - 1e-3 and lo < dhi + 1e-3
+                if not keep:
+                    continue
+                shift = (np.array(idx) + 0.5) * L0 - L / 2
+                pos.append((p0 + shift).astype(np.float32))
+                vel.append(v0)
+                r = (i * repl[1] + j) * repl[2] + k
+                tags.append(np.arange(n0, dtype=np.uint32) + np.uint32(r * n0))
+    n_global = n0 * repl[0] * repl[1] * repl[2]
+    pos = np.concatenate(pos)
+    # a replica edge can round onto the box face
+    hi = np.nextafter(np.float32(L / 2), np.float32(0)).astype(np.float32)
+    pos = np.minimum(np.maximum(pos, (-L / 2).astype(np.float32)), hi)
+    return n_global, np.concatenate(tags), pos, np.concatenate(vel), L
+
+
+def attach_ops(hoomd, sim, thermostat=True):
     cell = hoomd.md.nlist.Cell(buffer=BUFFER)
     lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=RCUT)
     lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
@@ -126,6 +158,12 @@ def build_sim(hoomd, pos, vel, L, device_id=0, seed=1, thermostat=True):
     cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All(), thermostat=th)
     sim.operations.integrator = hoomd.md.Integrator(dt=DT, methods=[cv], forces=[lj])
     return sim, cell, lj
+
+
+def build_sim(hoomd, pos, vel, L, device_id=0, seed=1, thermostat=True):
+    sim = hoomd.Simulation(device=hoomd.device.GPU(gpu_id=device_id), seed=seed)
+    sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays([L, L, L, 0, 0, 0], pos, vel))
+    return attach_ops(hoomd, sim, thermostat)
 
 
 def oracle_run(snapshot_pos, snapshot_vel, L, nsteps, seed=1):
@@ -220,16 +258,48 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    ncell = int(os.environ.get("HB2_BENCH_NCELL", "64"))
-    pos, vel, L = fcc_liquid(ncell, seed=1 + rank)
-    N = len(pos)
-    sim, cell, lj = build_sim(hoomd, pos, vel, L, device_id=local, seed=1 + rank)
+    # Workload. 1 GPU: configs[1], the 1,048,576-particle liquid (FCC lattice melted on the device).
+    # N > 1 GPUs: configs[3], the equilibrated 64,000-particle reference frame replicated 10x10x10 =
+    # 64 M particles in ONE box, spatially decomposed over the N GPUs (strong scaling: total work
+    # fixed). HB2_BENCH_REPL=nx,ny,nz overrides the replication (e.g. a per-GPU-fixed series).
+    repl_env = os.environ.get("HB2_BENCH_REPL", "")
+    if world == 1 and not repl_env:
+        ncell = int(os.environ.get("HB2_BENCH_NCELL", "64"))
+        pos, vel, L = fcc_liquid(ncell, seed=1)
+        N = len(pos)
+        sim, cell, lj = build_sim(hoomd, pos, vel, L, device_id=local, seed=1)
+        equil = int(os.environ.get("HB2_BENCH_EQUIL", "2000"))
+        workload = (f"LJ liquid N={N} rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4, Cell nlist + "
+                    "ConstantVolume/Bussi, dt=0.005 (BASELINE.json configs[1])")
+        scaling, grid = "weak", (1, 1, 1)
+    else:
+        repl = tuple(int(x) for x in (repl_env or "10,10,10").split(","))
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "c1_64k.npz"))
+        L0 = float(fx["L"][0])
+        Lbox = [float(np.float32(L0 * r)) for r in repl]
+        g = (__import__("ctypes").c_uint32 * 3)()
+        _lib.check(_lib.lib().hb2_domain_find_decomposition(world, *Lbox, g))
+        grid = tuple(int(x) for x in g)
+        coord = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
+        N, tags, pos, vel, _ = replicated_c1(repl, grid, coord)
+        sim = hoomd.Simulation(device=hoomd.device.GPU(gpu_id=local), seed=1)
+        sim._create_state_from_local(Lbox + [0, 0, 0], ["A"], N, tags, pos, vel,
+                                     domain_decomposition=grid if world > 1 else (None, None, None))
+        del tags, pos, vel
+        sim, cell, lj = attach_ops(hoomd, sim)
+        equil = int(os.environ.get("HB2_BENCH_EQUIL", "50"))
+        workload = (f"LJ liquid N={N} (reference-equilibrated 64,000-particle frame replicated "
+                    f"{repl[0]}x{repl[1]}x{repl[2]}) rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4, Cell nlist + "
+                    f"ConstantVolume/Bussi, dt=0.005, domain decomposition {grid[0]}x{grid[1]}x{grid[2]} "
+                    "with NCCL ghost exchange (BASELINE.json configs[3])")
+        scaling = "strong"
     tpp = int(os.environ.get("HB2_TPP", "0"))
     if tpp:
         lj.set_threads_per_particle(tpp)
-    # melt the lattice and equilibrate (untimed)
-    sim.run(int(os.environ.get("HB2_BENCH_EQUIL", "2000")))
+    # melt / equilibrate (untimed)
+    sim.run(equil)
     stats = cell._stats()
+    n_local, n_ghost = sim.state._N_local, sim.state._N_ghost
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,22 +307,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sim.run(args.warmup)
-    L0 = _lib.lib().hb2_launch_count()
+    L0c = _lib.lib().hb2_launch_count()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     sim.run(args.steps)
-    ms = sim._last_device_ms
+    ms = sim._last_device_ms  # CUDA events on the engine's stream around the K steps
     barrier()
     clocks = sampler.stop()
-    launches = int(_lib.lib().hb2_launch_count() - L0)
+    launches = int(_lib.lib().hb2_launch_count() - L0c)
     builds = cell.num_builds
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * N * args.steps / (ms * 1e-3)
+    ms = max_over_ranks(ms)
+    value = N * args.steps / (ms * 1e-3)
 
     # ---- per-phase device times of the same loop (separate, event-instrumented run: the events
     # would perturb the timed region above)
@@ -264,25 +337,32 @@ def run_ours(args):
     integ._set_profiling(False)
     pstats = cell._stats()
 
-    # ---- e2e: host snapshot in -> run(S) -> host snapshot + energy out, all inside the timed region
+    # ---- e2e: host arrays in -> run(S) -> host arrays + energy out, all inside the timed region,
+    # through the public API (1 GPU: Snapshot in / out; N GPUs: each rank's own particles in / out)
     S = int(os.environ.get("HB2_E2E_BLOCK", "100"))
     calls = max(1, min(5, args.steps // S if args.steps >= S else 1))
-    snap = sim.state.get_snapshot()
+    if world == 1:
+        snap = sim.state.get_snapshot()
+    else:
+        loc = sim.state._get_local()
     barrier()
     t0 = time.perf_counter()
     for _ in range(calls):
-        sim.state.set_snapshot(snap)
-        sim.run(S)
-        snap = sim.state.get_snapshot()
+        if world == 1:
+            sim.state.set_snapshot(snap)
+            sim.run(S)
+            snap = sim.state.get_snapshot()
+        else:
+            tag_, pos_, vel_, mass_, tid_, img_ = loc
+            sim.state._set_tagged(N, tag_, pos_, vel_, tid_, mass_, img_)
+            sim.run(S)
+            loc = sim.state._get_local()
         e = lj.energy
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * S * calls / float(t.item())
-    h2d = N * (12 + 12 + 4 + 4 + 12)
-    d2h = N * (12 + 12 + 4 + 4 + 12) + 8
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = N * S * calls / e2e_s
+    h2d = N * (12 + 12 + 4 + 4 + 12) + (0 if world == 1 else 4 * N)
+    d2h = h2d + 8
 
     line = None
     if rank == 0:
@@ -292,32 +372,39 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"LJ liquid N={N} per GPU rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4, Cell "
-                                   "nlist + ConstantVolume/Bussi, dt=0.005 (BASELINE.json configs[1])",
-                       "l2": "working set (nlist %.0f MB + state) exceeds the 126 MB L2; no flush"
-                             % (N * stats["pitch"] * 4 / 1e6),
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload,
+                       "l2": "working set per GPU (nlist %.0f MB + state) exceeds the 126 MB L2; no flush"
+                             % (n_local * stats["pitch"] * 4 / 1e6),
+                       "particles_per_gpu_rank0": n_local, "ghosts_rank0": n_ghost,
+                       "decomposition": list(grid),
                        "mean_neighbors": nbar, "steps_per_rebuild": k, "nlist_builds": builds,
                        "threads_per_particle": tpp or 8},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / S,
                     "d2h_bytes_per_step": d2h / S, "steps_per_call": S, "calls": calls,
-                    "what": "state.set_snapshot(host) + sim.run(S) + state.get_snapshot() + energy"},
+                    "what": ("state.set_snapshot(host) + sim.run(S) + state.get_snapshot() + energy"
+                             if world == 1 else
+                             "per rank: state._set_tagged(host arrays) + sim.run(S) + "
+                             "state._get_local() + energy (collective)")},
             "gpu_launches": launches,
-            # dominant kernel: pair_force_kernel. Algorithmic bytes per launch = (4 nbar + 44) N
+            # dominant kernel: pair_force_kernel. Algorithmic bytes per launch = (4 nbar + 44) N_local
             # (neighbour row + own position + count + head + force write)
-            "roofline": roofline_pair(prof, pstats["mean_neighbors"], N, hbm, peak_src),
+            "roofline": roofline_pair(prof, pstats["mean_neighbors"], n_local, hbm, peak_src),
             "phases": {"force_ms_per_step": prof["force_ms"] / max(prof["force_launches"], 1),
                        "nlist_ms_per_build": prof["nlist_ms"] / max(prof["builds"], 1),
                        "nlist_ms_per_step": prof["nlist_ms"] / max(prof["steps"], 1),
                        "integrate_ms_per_step": prof["integrate_ms"] / max(prof["steps"], 1),
-                       "profiled_steps": prof["steps"], "profiled_builds": prof["builds"]},
+                       "profiled_steps": prof["steps"], "profiled_builds": prof["builds"],
+                       "note": "rank 0; nlist includes migration + ghost exchange, force includes the "
+                               "per-step ghost refresh" if world > 1 else "single GPU"},
             "roofline_step": {"bound": "hbm", "achieved": bytes_step * value / world / 1e9,
                               "peak": hbm, "unit": "GB/s",
                               "frac": bytes_step * value / world / 1e9 / hbm,
                               "bytes_per_particle_step": bytes_step, "peak_source": peak_src},
         }
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         if os.environ.get("HB2_BENCH_CPU", "1") != "0" and world == 1:

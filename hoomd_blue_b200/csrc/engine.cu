@@ -266,7 +266,7 @@ static hb2_status system_set(hb2_system* s, uint32_t n_in, uint64_t N_global, co
         for (int d = 0; d < 3; d++)
             if (D.grid[d] > 1)
                 shell *= 1.0 + 2.0 * std::min(0.5, 4.0 / (s->box.L[d] / D.grid[d]));
-        need = (uint32_t)std::min<double>(4.0e9, 1.3 * n0 * shell + 1.2 * N + 4096.0);
+        need = (uint32_t)std::min<double>(4.0e9, std::max(1.25 * n0, 1.1 * (double)N) * shell + 4096.0);
         }
     if (need > s->cap || !s->pos[0])
         HB2_TRY(system_allocate(s, need, !D.active, N_global));
