@@ -334,8 +334,15 @@ def run_ours(args):
     integ._set_profiling(True)
     sim.run(P)
     prof = integ._profile()
+    prof_run_ms = max_over_ranks(sim._last_device_ms) / P
     integ._set_profiling(False)
     pstats = cell._stats()
+    if os.environ.get("HB2_BENCH_DEBUG"):
+        for _ in range(3):
+            sim.run(args.steps)
+            if rank == 0:
+                print("debug run ms/step", sim._last_device_ms / args.steps, "builds", cell.num_builds,
+                      file=sys.stderr)
 
     # ---- e2e: host arrays in -> run(S) -> host arrays + energy out, all inside the timed region,
     # through the public API (1 GPU: Snapshot in / out; N GPUs: each rank's own particles in / out)
@@ -396,6 +403,7 @@ def run_ours(args):
                        "nlist_ms_per_step": prof["nlist_ms"] / max(prof["steps"], 1),
                        "integrate_ms_per_step": prof["integrate_ms"] / max(prof["steps"], 1),
                        "profiled_steps": prof["steps"], "profiled_builds": prof["builds"],
+                       "profiled_run_ms_per_step": prof_run_ms,
                        "note": "rank 0; nlist includes migration + ghost exchange, force includes the "
                                "per-step ghost refresh" if world > 1 else "single GPU"},
             "roofline_step": {"bound": "hbm", "achieved": bytes_step * value / world / 1e9,

@@ -573,10 +573,11 @@ hb2_status hb2_nlist::ensure_capacity()
         pitch = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 16.0), std::max(Ng, 8.0));
         pitch = (pitch + 31u) & ~31u; // rows are padded to whole 32-entry chunks
         }
-    // rows exist for owned particles only; leave room for the owned count to drift between builds
-    const size_t rows = D.active ? std::min<size_t>(cap, (size_t)(sys->N * 1.1) + 1024) : sys->N;
-    if (rows * pitch > nlist_cap)
+    // rows exist for owned particles only; allocate with room for the owned count to drift between
+    // builds, and only reallocate when the rows in use no longer fit
+    if ((size_t)sys->N * pitch > nlist_cap)
         {
+        const size_t rows = D.active ? std::min<size_t>(cap, (size_t)(sys->N * 1.1) + 1024) : sys->N;
         dev_free(d_nlist);
         HB2_TRY(dev_alloc(&d_nlist, rows * pitch));
         nlist_cap = rows * pitch;
