@@ -116,12 +116,12 @@ def test_stateless_drivers_against_oracle(oracle):
     v_half = vel4[:, :3] + np.float32(0.5) * dt * f32[:, :3]
     p1 = p0[:, :3] + dt * v_half
     wrapped = np.where(p1 >= np.float32(Lb / 2), p1 - np.float32(Lb), np.where(p1 < np.float32(-Lb / 2), p1 + np.float32(Lb), p1))
-    assert np.allclose(d_vel.cpu().numpy()[:, :3], v_half, rtol=0, atol=2e-6)
+    assert np.allclose(d_vel.cpu().numpy()[:, :3], v_half, rtol=1e-6, atol=1e-5)
     assert np.allclose(d_pos_s.cpu().numpy()[:N, :3], wrapped, rtol=0, atol=1e-5)
     assert int(d_flag.item()) == 0
     d_ke = torch.zeros(1, dtype=torch.float64, device=dev)
     _lib.check(L.hb2_gpu_nve_step_two(_p(d_vel), _p(d_f), N, dt, None, _p(d_ke), None))
     torch.cuda.synchronize()
     v1 = v_half + np.float32(0.5) * dt * f32[:, :3]
-    assert np.allclose(d_vel.cpu().numpy()[:, :3], v1, rtol=0, atol=2e-6)
+    assert np.allclose(d_vel.cpu().numpy()[:, :3], v1, rtol=1e-6, atol=1e-5)
     assert abs(float(d_ke.item()) - 0.5 * (v1.astype(np.float64) ** 2).sum()) <= 1e-6 * float(d_ke.item())
