@@ -162,6 +162,85 @@ __global__ void __launch_bounds__(256)
         rtag[t] = k;
     }
 
+// Snapshot <-> device layout on the device (the host only moves the caller's raw arrays):
+// pack: (pos3, vel3, mass, typeid, image3) in tag order -> pos4 / vel4 / image / tag = index.
+__global__ void __launch_bounds__(256)
+    snapshot_pack_kernel(uint32_t N, const float* __restrict__ pos3, const float* __restrict__ vel3,
+                         const float* __restrict__ mass, const uint32_t* __restrict__ typeid_,
+                         const int* __restrict__ image3, float4* __restrict__ pos,
+                         float4* __restrict__ vel, int* __restrict__ image,
+                         uint32_t* __restrict__ tag, uint32_t* __restrict__ rtag, uint32_t ntypes,
+                         uint32_t* __restrict__ bad_type)
+    {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const uint32_t t = typeid_ ? typeid_[i] : 0u;
+    if (t >= ntypes)
+        atomicMax(bad_type, i + 1);
+    pos[i] = make_float4(pos3[3 * (size_t)i], pos3[3 * (size_t)i + 1], pos3[3 * (size_t)i + 2],
+                         __uint_as_float(t));
+    vel[i] = make_float4(vel3 ? vel3[3 * (size_t)i] : 0.f, vel3 ? vel3[3 * (size_t)i + 1] : 0.f,
+                         vel3 ? vel3[3 * (size_t)i + 2] : 0.f, mass ? mass[i] : 1.0f);
+    image[3 * (size_t)i] = image3 ? image3[3 * (size_t)i] : 0;
+    image[3 * (size_t)i + 1] = image3 ? image3[3 * (size_t)i + 1] : 0;
+    image[3 * (size_t)i + 2] = image3 ? image3[3 * (size_t)i + 2] : 0;
+    tag[i] = i;
+    if (rtag)
+        rtag[i] = i;
+    }
+
+// unpack: particle k (cell order) -> row tag[k] of the tag-ordered raw arrays
+__global__ void __launch_bounds__(256)
+    snapshot_unpack_kernel(uint32_t N, const float4* __restrict__ pos, const float4* __restrict__ vel,
+                           const int* __restrict__ image, const uint32_t* __restrict__ tag,
+                           float* __restrict__ pos3, float* __restrict__ vel3,
+                           float* __restrict__ mass, uint32_t* __restrict__ typeid_,
+                           int* __restrict__ image3)
+    {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N)
+        return;
+    const size_t t = tag[k];
+    const float4 p = pos[k], v = vel[k];
+    pos3[3 * t] = p.x;
+    pos3[3 * t + 1] = p.y;
+    pos3[3 * t + 2] = p.z;
+    typeid_[t] = __float_as_uint(p.w);
+    vel3[3 * t] = v.x;
+    vel3[3 * t + 1] = v.y;
+    vel3[3 * t + 2] = v.z;
+    mass[t] = v.w;
+    image3[3 * t] = image[3 * (size_t)k];
+    image3[3 * t + 1] = image[3 * (size_t)k + 1];
+    image3[3 * t + 2] = image[3 * (size_t)k + 2];
+    }
+
+hb2_status snapshot_pack(uint32_t N, const float* pos3, const float* vel3, const float* mass,
+                         const uint32_t* typeid_, const int* image3, float4* pos, float4* vel,
+                         int* image, uint32_t* tag, uint32_t* rtag, uint32_t ntypes,
+                         uint32_t* bad_type, cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    snapshot_pack_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, pos3, vel3, mass, typeid_, image3, pos,
+                                                              vel, image, tag, rtag, ntypes, bad_type);
+    HB2_CHECK_LAUNCH("snapshot_pack_kernel");
+    return HB2_OK;
+    }
+
+hb2_status snapshot_unpack(uint32_t N, const float4* pos, const float4* vel, const int* image,
+                           const uint32_t* tag, float* pos3, float* vel3, float* mass,
+                           uint32_t* typeid_, int* image3, cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    snapshot_unpack_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, pos, vel, image, tag, pos3, vel3,
+                                                                mass, typeid_, image3);
+    HB2_CHECK_LAUNCH("snapshot_unpack_kernel");
+    return HB2_OK;
+    }
+
 static inline int key_bits(uint32_t Nc, bool ghosts)
     {
     if (ghosts)

@@ -135,6 +135,9 @@ extern "C" void hb2_system_destroy(hb2_system* s)
         dev_free(s->tag[b]);
         }
     dev_free(s->rtag);
+    dev_free(s->d_stage);
+    if (s->h_stage)
+        cudaFreeHost(s->h_stage);
     dev_free(s->d_timestep);
     dev_free(s->d_partial);
     dev_free(s->d_ticket);
@@ -294,11 +297,92 @@ static hb2_status system_set(hb2_system* s, uint32_t n_in, uint64_t N_global, co
     return HB2_OK;
     }
 
+static hb2_status system_stage(hb2_system* s, uint32_t N)
+    {
+    const size_t words = 11 * (size_t)N;
+    if (words <= s->stage_cap)
+        return HB2_OK;
+    dev_free(s->d_stage);
+    if (s->h_stage)
+        cudaFreeHost(s->h_stage);
+    s->h_stage = nullptr;
+    HB2_TRY(dev_alloc(&s->d_stage, words));
+    HB2_CUDA(cudaMallocHost((void**)&s->h_stage, words * sizeof(float)));
+    s->stage_cap = words;
+    return HB2_OK;
+    }
+
 extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const float* pos3,
                                                const float* vel3, const float* mass,
                                                const uint32_t* typeid_, const int32_t* image3)
     {
-    return system_set(s, N, N, nullptr, pos3, vel3, mass, typeid_, image3);
+    if (!s || !pos3)
+        {
+        set_error("hb2_system_set_particles: positions are required");
+        return HB2_ERR_INVALID;
+        }
+    if (s->dom.active)
+        return system_set(s, N, N, nullptr, pos3, vel3, mass, typeid_, image3);
+    // Single GPU: the raw arrays cross PCIe once from a pinned bounce buffer and are packed into the
+    // float4 layout on the device.
+    if (!s->has_box)
+        {
+        set_error("hb2_system_set_particles: set the box first");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    if (N + 1 > s->cap || !s->pos[0])
+        HB2_TRY(system_allocate(s, N + 1, true, N));
+    HB2_TRY(system_stage(s, N));
+    cudaStream_t st = s->stream;
+    const size_t n = N;
+    float* h = s->h_stage;
+    memcpy(h, pos3, 12 * n);
+    if (vel3)
+        memcpy(h + 3 * n, vel3, 12 * n);
+    else
+        memset(h + 3 * n, 0, 12 * n);
+    if (mass)
+        memcpy(h + 6 * n, mass, 4 * n);
+    else
+        std::fill(h + 6 * n, h + 7 * n, 1.0f);
+    if (typeid_)
+        memcpy(h + 7 * n, typeid_, 4 * n);
+    else
+        memset(h + 7 * n, 0, 4 * n);
+    if (image3)
+        memcpy(h + 8 * n, image3, 12 * n);
+    else
+        memset(h + 8 * n, 0, 12 * n);
+    float* d = s->d_stage;
+    HB2_CUDA(cudaMemcpyAsync(d, h, 44 * n, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemsetAsync(s->d_ticket + 3, 0, sizeof(uint32_t), st));
+    s->N = N;
+    s->Ng = 0;
+    s->cur = 0;
+    s->dom.N_global = N;
+    HB2_TRY(snapshot_pack(N, d, d + 3 * n, d + 6 * n, (const uint32_t*)(d + 7 * n),
+                          (const int*)(d + 8 * n), s->pos[0], s->vel[0], s->image[0], s->tag[0],
+                          s->rtag, s->ntypes, s->d_ticket + 3, st));
+    uint32_t bad = 0;
+    HB2_CUDA(cudaMemcpyAsync(&bad, s->d_ticket + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    if (bad)
+        {
+        s->N = 0;
+        set_error("hb2_system_set_particles: type id out of range");
+        return HB2_ERR_INVALID;
+        }
+    HB2_TRY(system_place_dummy(s));
+    s->order_epoch++;
+    for (auto* nl : s->nlists)
+        {
+        nl->force_update = true;
+        nl->has_list = false;
+        }
+    for (auto* p : s->pairs)
+        p->computed = false;
+    return HB2_OK;
     }
 
 extern "C" hb2_status hb2_system_set_particles_tagged(hb2_system* s, uint32_t n, uint64_t N_global,
@@ -393,45 +477,29 @@ extern "C" hb2_status hb2_system_get_particles(hb2_system* s, float* pos3, float
         }
     HB2_CUDA(cudaSetDevice(s->device));
     const uint32_t N = s->N;
-    std::vector<float4> hp(N), hv(N);
-    std::vector<int> hi(3 * (size_t)N);
-    std::vector<uint32_t> ht(N);
+    if (N == 0)
+        return HB2_OK;
+    HB2_TRY(system_stage(s, N));
+    const size_t n = N;
     const int c = s->cur;
-    HB2_CUDA(cudaMemcpyAsync(hp.data(), s->pos[c], sizeof(float4) * N, cudaMemcpyDeviceToHost,
-                             s->stream));
-    HB2_CUDA(cudaMemcpyAsync(hv.data(), s->vel[c], sizeof(float4) * N, cudaMemcpyDeviceToHost,
-                             s->stream));
-    HB2_CUDA(cudaMemcpyAsync(hi.data(), s->image[c], sizeof(int) * 3 * (size_t)N,
-                             cudaMemcpyDeviceToHost, s->stream));
-    HB2_CUDA(cudaMemcpyAsync(ht.data(), s->tag[c], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost,
-                             s->stream));
-    HB2_CUDA(cudaStreamSynchronize(s->stream));
-    for (uint32_t k = 0; k < N; k++)
-        {
-        const uint32_t t = ht[k];
-        if (pos3)
-            {
-            pos3[3 * t] = hp[k].x;
-            pos3[3 * t + 1] = hp[k].y;
-            pos3[3 * t + 2] = hp[k].z;
-            }
-        if (typeid_)
-            memcpy(&typeid_[t], &hp[k].w, 4);
-        if (vel3)
-            {
-            vel3[3 * t] = hv[k].x;
-            vel3[3 * t + 1] = hv[k].y;
-            vel3[3 * t + 2] = hv[k].z;
-            }
-        if (mass)
-            mass[t] = hv[k].w;
-        if (image3)
-            {
-            image3[3 * t] = hi[3 * k];
-            image3[3 * t + 1] = hi[3 * k + 1];
-            image3[3 * t + 2] = hi[3 * k + 2];
-            }
-        }
+    cudaStream_t st = s->stream;
+    float* d = s->d_stage;
+    float* h = s->h_stage;
+    // tag order is restored on the device; one pinned D2H copy brings all five arrays back
+    HB2_TRY(snapshot_unpack(N, s->pos[c], s->vel[c], s->image[c], s->tag[c], d, d + 3 * n, d + 6 * n,
+                            (uint32_t*)(d + 7 * n), (int*)(d + 8 * n), st));
+    HB2_CUDA(cudaMemcpyAsync(h, d, 44 * n, cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    if (pos3)
+        memcpy(pos3, h, 12 * n);
+    if (vel3)
+        memcpy(vel3, h + 3 * n, 12 * n);
+    if (mass)
+        memcpy(mass, h + 6 * n, 4 * n);
+    if (typeid_)
+        memcpy(typeid_, h + 7 * n, 4 * n);
+    if (image3)
+        memcpy(image3, h + 8 * n, 12 * n);
     return HB2_OK;
     }
 

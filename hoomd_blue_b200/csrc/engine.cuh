@@ -62,6 +62,11 @@ struct hb2_system
     int* image[2] = {nullptr, nullptr};
     uint32_t* tag[2] = {nullptr, nullptr};
     uint32_t* rtag = nullptr;
+    // snapshot staging: the caller's raw tag-ordered arrays as they cross PCIe (11 words per particle)
+    // and the pinned bounce buffer behind them
+    float* d_stage = nullptr;
+    float* h_stage = nullptr;
+    size_t stage_cap = 0;
     int cur = 0;
     uint64_t order_epoch = 0; // bumped whenever the particle order changes
 

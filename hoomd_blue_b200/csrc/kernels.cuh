@@ -19,6 +19,15 @@ hb2_status reorder_particles(const uint32_t* d_order, uint32_t N, const float4* 
                              uint32_t* tag_out, float4* force_out, uint32_t* rtag,
                              cudaStream_t stream);
 
+// snapshot (tag-ordered raw arrays, all DEVICE pointers) <-> engine layout
+hb2_status snapshot_pack(uint32_t N, const float* pos3, const float* vel3, const float* mass,
+                         const uint32_t* typeid_, const int* image3, float4* pos, float4* vel,
+                         int* image, uint32_t* tag, uint32_t* rtag, uint32_t ntypes,
+                         uint32_t* bad_type, cudaStream_t stream);
+hb2_status snapshot_unpack(uint32_t N, const float4* pos, const float4* vel, const int* image,
+                           const uint32_t* tag, float* pos3, float* vel3, float* mass,
+                           uint32_t* typeid_, int* image3, cudaStream_t stream);
+
 // ---- nlist.cu
 struct NlistBuildArgs
     {
