@@ -1080,7 +1080,7 @@ hb2_status hb2_pair::upload_params()
     return HB2_OK;
     }
 
-hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value)
+hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value, bool want_energy)
     {
     hb2_system* s = sys;
     if (params_dirty)
@@ -1134,10 +1134,12 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
     a.kT = (float)kT;
     a.face_margin = (float)(nl->rcut_max_max + 2.0 * nl->buffer) * 1.0001f;
     a.tpp = tpp;
+    a.energy = want_energy || energy_every_step || tpp != 8;
     if (s->mid_event)
         HB2_CUDA(cudaEventRecord(s->mid_event, s->stream));
     HB2_TRY(launch_pair_forces(ev, mode, a, s->box, s->stream));
     virial_valid = s->compute_virial;
+    energy_valid = a.energy;
     computed = true;
     computed_step = timestep;
     computed_epoch = s->order_epoch;
@@ -1274,12 +1276,12 @@ extern "C" hb2_status hb2_pair_compute(hb2_pair* p, uint64_t timestep)
     return p->compute(timestep);
     }
 
-static hb2_status pair_ensure(hb2_pair* p)
+static hb2_status pair_ensure(hb2_pair* p, bool need_energy = true)
     {
     // recompute when the particle order changed or nothing was computed yet
     // (hoomd/ForceCompute.cc:562-574: "sorted / new timestep / flags changed")
     if (!p->computed || p->computed_epoch != p->sys->order_epoch
-        || (p->sys->compute_virial && !p->virial_valid))
+        || (p->sys->compute_virial && !p->virial_valid) || (need_energy && !p->energy_valid))
         return p->compute(p->sys->timestep);
     return HB2_OK;
     }
@@ -1654,7 +1656,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             s->mid_event = pe[2];
             }
         const uint64_t builds_before = nl->num_builds;
-        hb2_status cst = pf->compute(t + 1, check, flag);
+        hb2_status cst = pf->compute(t + 1, check, flag, step + 1 == nsteps);
         s->mid_event = nullptr;
         HB2_TRY(cst);
         if (it->profiling)

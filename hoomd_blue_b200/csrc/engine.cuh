@@ -160,11 +160,14 @@ struct hb2_pair
     float* d_virial = nullptr;
     uint32_t cap_N = 0;
     bool virial_valid = false;
+    bool energy_valid = false; // the last force pass also accumulated per-particle energies
+    bool energy_every_step = false;
     bool computed = false;
     uint64_t computed_step = 0, computed_epoch = 0;
 
     hb2_status upload_params();
-    hb2_status compute(uint64_t timestep, bool flag_known = false, bool flag_value = false);
+    hb2_status compute(uint64_t timestep, bool flag_known = false, bool flag_value = false,
+                       bool want_energy = true);
     };
 
 struct hb2_integrator

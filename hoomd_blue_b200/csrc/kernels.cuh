@@ -76,6 +76,7 @@ struct PairArgs
     float dt, kT;
     float face_margin; // r_list_max + buffer (distance from a face beyond which no image shift occurs)
     uint32_t tpp;
+    bool energy = true; // false: skip the per-particle potential energy (force.w = 0)
     };
 hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,
                               const hb2_box& box, cudaStream_t stream);

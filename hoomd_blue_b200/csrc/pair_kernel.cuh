@@ -104,12 +104,16 @@ template<class Ev> struct PairKArgs
     float dt, kT;
     float face_margin; // r_list_max + buffer: farther than this from every face => no image shifts
     uint32_t stage;    // chunks of a row staged per pass (<= PAIR_STAGE_MAX)
+    bool energy;       // accumulate the per-particle potential energy
     BoxF box;
     BoxD boxd;
     };
 
 // MODE: 0 none, 1 shift, 2 xplor (hoomd/md/PotentialPair.h:104-109)
-template<class Ev, int MODE, bool VIRIAL, int TPP, bool ONETYPE>
+// ENERGY = false skips the per-particle potential energy (force.w is written as 0): the engine asks
+// for it only on steps whose energies can be observed (the last step of a run, or lazily when a getter
+// is called), like the reference does for the virial through PDataFlags (hoomd/ParticleData.h:70-84).
+template<class Ev, int MODE, bool VIRIAL, int TPP, bool ONETYPE, bool ENERGY>
 __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
     {
     typedef typename Ev::param_type param_type;
@@ -253,8 +257,10 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
             }
     };
 
-    // (hi, lo) of pi - L and pi + L per component (only the face-shifting loop uses them)
-    float mh[3], ml[3], ph[3], pl[3];
+    // (hi, lo) of the one image shift a neighbour of this particle can need per component: a particle
+    // in the upper half of the box can only see neighbours across the upper face (pi - L), one in the
+    // lower half only across the lower face (pi + L). Only the face-shifting loop uses them.
+    float sh[3], sl[3];
     const float pc[3] = {pi.x, pi.y, pi.z};
     const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
     if (warp_shift)
@@ -262,12 +268,9 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
 #pragma unroll
         for (int c = 0; c < 3; c++)
             {
-            const double m = (double)pc[c] - a.boxd.L[c];
-            const double p = (double)pc[c] + a.boxd.L[c];
-            mh[c] = (float)m;
-            ml[c] = (float)(m - (double)mh[c]);
-            ph[c] = (float)p;
-            pl[c] = (float)(p - (double)ph[c]);
+            const double m = pc[c] >= 0.f ? (double)pc[c] - a.boxd.L[c] : (double)pc[c] + a.boxd.L[c];
+            sh[c] = (float)m;
+            sl[c] = (float)(m - (double)sh[c]);
             }
         }
 
@@ -326,10 +329,8 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
                     for (int q = 0; q < 3; q++)
                         {
                         const float d0 = pc[q] - qc[q];
-                        const bool um = d0 >= hc[q], up = d0 < -hc[q];
-                        const float h = um ? mh[q] : (up ? ph[q] : pc[q]);
-                        const float l = um ? ml[q] : (up ? pl[q] : 0.0f);
-                        d[q] = (h - qc[q]) + l;
+                        const float ds = (sh[q] - qc[q]) + sl[q];
+                        d[q] = fabsf(d0) >= hc[q] ? ds : d0;
                         }
                     pair_body(j[u], pj[u], d[0], d[1], d[2]);
                     }
@@ -377,10 +378,18 @@ hb2_status pair_launch_tpp(const PairKArgs<Ev>& k, cudaStream_t stream)
     const uint32_t blocks = (uint32_t)((threads + PAIR_BLOCK - 1) / PAIR_BLOCK);
     // staged rows: PAIR_BLOCK / TPP rows of (stage * 32 + pad) words; at most 33 KB (TPP = 4)
     const size_t smem = (size_t)(PAIR_BLOCK / TPP) * (k.stage * 32u + PAIR_ROW_PAD) * sizeof(uint32_t);
-    if (k.ntypes == 1)
-        pair_force_kernel<Ev, MODE, VIRIAL, TPP, true><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
+    // the energy-free variant exists for the default TPP only (it is the step loop's kernel)
+    if (TPP == 8 && !k.energy)
+        {
+        if (k.ntypes == 1)
+            pair_force_kernel<Ev, MODE, VIRIAL, TPP, true, (TPP != 8)><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
+        else
+            pair_force_kernel<Ev, MODE, VIRIAL, TPP, false, (TPP != 8)><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
+        }
+    else if (k.ntypes == 1)
+        pair_force_kernel<Ev, MODE, VIRIAL, TPP, true, true><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
     else
-        pair_force_kernel<Ev, MODE, VIRIAL, TPP, false><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
+        pair_force_kernel<Ev, MODE, VIRIAL, TPP, false, true><<<blocks, PAIR_BLOCK, smem, stream>>>(k);
     HB2_CHECK_LAUNCH("pair_force_kernel");
     return HB2_OK;
     }
@@ -458,6 +467,7 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.box = boxf(box);
     k.boxd = boxd(box);
     k.face_margin = a.face_margin;
+    k.energy = a.energy;
     k.stage = std::min<uint32_t>(std::max<uint32_t>(a.pitch / 32u, 1u), PAIR_STAGE_MAX);
     if (Ev::needs_thermo && (!a.vel || !a.tag))
         {
