@@ -23,14 +23,17 @@
 namespace hb2
     {
 constexpr int NL_WARPS = 4;     // warps (home cells) per block
-constexpr int NL_CMAX = 23;     // candidates per lane per round (odd)
+#ifndef NL_CMAX_DEF
+#define NL_CMAX_DEF 21
+#endif
+constexpr int NL_CMAX = NL_CMAX_DEF; // candidates per lane per round (odd); 21 -> 5 blocks per SM
 constexpr int NL_CAP = 32 * NL_CMAX;
 constexpr float NL_FAR = 1.0e18f;
 
-struct NlWarpSmem
+template<bool MULTITYPE> struct NlWarpSmem
     {
     float4 cand[NL_CAP]; // x, y, z (image-shifted), particle index (bits)
-    uint8_t type[NL_CAP];
+    uint8_t type[MULTITYPE ? NL_CAP : 16];
     };
 
 struct NlConst
@@ -154,9 +157,9 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
                        uint32_t* __restrict__ conditions, uint32_t dummy_index)
     {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    NlWarpSmem& sm = reinterpret_cast<NlWarpSmem*>(s_raw)[threadIdx.x >> 5];
+    NlWarpSmem<MULTITYPE>& sm = reinterpret_cast<NlWarpSmem<MULTITYPE>*>(s_raw)[threadIdx.x >> 5];
     // per-type-pair (lo, hi) thresholds of the fp32 test, after the per-warp regions
-    float2* s_thr = reinterpret_cast<float2*>(s_raw + sizeof(NlWarpSmem) * NL_WARPS);
+    float2* s_thr = reinterpret_cast<float2*>(s_raw + sizeof(NlWarpSmem<MULTITYPE>) * NL_WARPS);
 
     const int lane = threadIdx.x & 31;
     const float band = cst.band;
@@ -465,7 +468,7 @@ static hb2_status launch_variant(const NlistBuildArgs& a, const NlConst& cst, cu
     {
     const uint32_t Nc = a.geom.dimt[0] * a.geom.dimt[1] * a.geom.dimt[2];
     const uint32_t blocks = (Nc + NL_WARPS - 1) / NL_WARPS;
-    const size_t smem = sizeof(NlWarpSmem) * NL_WARPS + sizeof(float2) * (MT ? a.ntypes * a.ntypes : 1);
+    const size_t smem = sizeof(NlWarpSmem<MT>) * NL_WARPS + sizeof(float2) * (MT ? a.ntypes * a.ntypes : 1);
     static bool attr = false;
     static size_t attr_smem = 0;
     if (!attr || smem > attr_smem)
