@@ -1628,10 +1628,11 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             }
         if (it->thermostat == 1)
             {
-            HB2_CUDA(cudaMemcpyAsync(s->d_timestep, &s->timestep, sizeof(uint64_t),
-                                     cudaMemcpyHostToDevice, st));
-            HB2_TRY(launch_bussi(d_ke, dof, it->dt, it->kT, it->tau, s->d_timestep, s->seed, 0u,
-                                 d_rescale, st));
+            // the factor of step t comes from the KE left by step t-1: drawn inside step two's
+            // reduction on a single GPU; after the KE all-reduce with a domain decomposition, and for
+            // the first step of a run (KE from prepRun)
+            if (step == 0 || s->dom.active)
+                HB2_TRY(launch_bussi(d_ke, dof, it->dt, it->kT, it->tau, t, s->seed, 0u, d_rescale, st));
             rescale = d_rescale;
             }
         const bool check = nl->has_list && nl->check_dist;
@@ -1664,8 +1665,19 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             HB2_CUDA(cudaEventRecord(pe[3], st));
             it->phase_n[1] += nl->num_builds - builds_before;
             }
+        BussiNext bn;
+        if (it->thermostat == 1 && !s->dom.active && step + 1 < nsteps)
+            {
+            bn.rescale = d_rescale;
+            bn.dof = dof;
+            bn.dt = it->dt;
+            bn.kT = it->kT;
+            bn.tau = it->tau;
+            bn.timestep = t + 1;
+            bn.seed = s->seed;
+            }
         HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
-                                s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st));
+                                s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn));
         if (it->thermostat == 1 && s->dom.active)
             HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
         if (it->profiling)

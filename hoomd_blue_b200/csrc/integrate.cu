@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(INT_BLOCK)
 
 // Deterministic block -> grid fp64 sum: every block writes its partial, the last block to finish
 // (ticket) adds the partials in index order with a fixed tree.
+// Returns true in the one thread that wrote the final sums (so a caller can chain scalar work).
 template<int NV>
-HB2_DEVICE void grid_sum(double (&v)[NV], double* __restrict__ partial, uint32_t* __restrict__ ticket,
+HB2_DEVICE bool grid_sum(double (&v)[NV], double* __restrict__ partial, uint32_t* __restrict__ ticket,
                          double* __restrict__ out)
     {
     __shared__ double s_w[NV][INT_BLOCK / 32];
@@ -152,17 +153,21 @@ HB2_DEVICE void grid_sum(double (&v)[NV], double* __restrict__ partial, uint32_t
                 out[q] = t;
                 }
             *ticket = 0u;
+            return true;
             }
         }
+    return false;
     }
 
 // a = F/m; v *= s; v += 1/2 dt a (hoomd/md/TwoStepConstantVolume.cc:234-260), optionally followed
 // by KE = 1/2 sum m v^2 in fp64 (hoomd/md/ComputeThermo.cc:139-153).
+// When `bussi.rescale` is set, the thread that finishes the KE sum also draws the Bussi factor of the
+// NEXT step (hoomd/md/Thermostat.h:357-447) — no extra launch, no host round trip.
 template<bool KE>
 __global__ void __launch_bounds__(INT_BLOCK)
     step_two_kernel(float4* __restrict__ vel, const float4* __restrict__ force, uint32_t N, float dt,
                     const double* __restrict__ d_rescale, double* __restrict__ partial,
-                    uint32_t* __restrict__ ticket, double* __restrict__ ke_out)
+                    uint32_t* __restrict__ ticket, double* __restrict__ ke_out, BussiNext bussi)
     {
     const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
     double ke[1] = {0.0};
@@ -183,7 +188,12 @@ __global__ void __launch_bounds__(INT_BLOCK)
                        + (double)v.z * (double)v.z);
         }
     if (KE)
-        grid_sum<1>(ke, partial, ticket, ke_out);
+        {
+        const bool fin = grid_sum<1>(ke, partial, ticket, ke_out);
+        if (fin && bussi.rescale)
+            *bussi.rescale = bussi_factor(*ke_out, bussi.dof, bussi.dt, bussi.kT, bussi.tau,
+                                          bussi.timestep, (uint16_t)bussi.seed, bussi.first_tag);
+        }
     }
 
 // KE of the current velocities only (prepRun / thermo queries)
@@ -222,11 +232,11 @@ __global__ void __launch_bounds__(INT_BLOCK)
     }
 
 __global__ void bussi_kernel(const double* __restrict__ d_ke, double dof, double dt, double kT,
-                             double tau, const uint64_t* __restrict__ d_timestep, uint32_t seed,
-                             uint32_t first_tag, double* __restrict__ d_rescale)
+                             double tau, uint64_t timestep, uint32_t seed, uint32_t first_tag,
+                             double* __restrict__ d_rescale)
     {
     if (threadIdx.x == 0 && blockIdx.x == 0)
-        *d_rescale = bussi_factor(*d_ke, dof, dt, kT, tau, *d_timestep, (uint16_t)seed, first_tag);
+        *d_rescale = bussi_factor(*d_ke, dof, dt, kT, tau, timestep, (uint16_t)seed, first_tag);
     }
 
 __global__ void advance_timestep_kernel(uint64_t* d_timestep)
@@ -259,17 +269,20 @@ hb2_status launch_step_one(float4* pos, float4* vel, const float4* force, int* i
 
 hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
                            const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
-                           double* d_ke_out, cudaStream_t stream)
+                           double* d_ke_out, cudaStream_t stream, const BussiNext* bussi)
     {
     if (N == 0)
         return HB2_OK;
     const uint32_t blocks = step_two_blocks(N);
+    BussiNext b;
+    if (bussi)
+        b = *bussi;
     if (d_ke_out)
         step_two_kernel<true><<<blocks, INT_BLOCK, 0, stream>>>(vel, force, N, dt, d_rescale,
-                                                                d_ke_partial, d_ticket, d_ke_out);
+                                                                d_ke_partial, d_ticket, d_ke_out, b);
     else
         step_two_kernel<false><<<blocks, INT_BLOCK, 0, stream>>>(vel, force, N, dt, d_rescale,
-                                                                 nullptr, nullptr, nullptr);
+                                                                 nullptr, nullptr, nullptr, b);
     HB2_CHECK_LAUNCH("step_two_kernel");
     return HB2_OK;
     }
@@ -297,11 +310,10 @@ hb2_status launch_reduce_energy(const float4* force, const float* virial, size_t
     }
 
 hb2_status launch_bussi(const double* d_ke, double dof, double dt, double kT, double tau,
-                        const uint64_t* d_timestep, uint32_t seed, uint32_t first_tag,
-                        double* d_rescale, cudaStream_t stream)
+                        uint64_t timestep, uint32_t seed, uint32_t first_tag, double* d_rescale,
+                        cudaStream_t stream)
     {
-    bussi_kernel<<<1, 32, 0, stream>>>(d_ke, dof, dt, kT, tau, d_timestep, seed, first_tag,
-                                       d_rescale);
+    bussi_kernel<<<1, 32, 0, stream>>>(d_ke, dof, dt, kT, tau, timestep, seed, first_tag, d_rescale);
     HB2_CHECK_LAUNCH("bussi_kernel");
     return HB2_OK;
     }

@@ -86,18 +86,26 @@ hb2_status launch_step_one(float4* pos, float4* vel, const float4* force, int* i
                            const hb2_box& box, float dt, const double* d_rescale,
                            const float4* last_pos, float maxshift, uint32_t* d_flag,
                            cudaStream_t stream);
+// Bussi factor of the next step, drawn by the thread that completes step two's KE sum
+struct BussiNext
+    {
+    double* rescale = nullptr; // null: off
+    double dof = 0, dt = 0, kT = 0, tau = 0;
+    uint64_t timestep = 0; // the step whose step-one will apply the factor
+    uint32_t seed = 0, first_tag = 0;
+    };
 // d_ke_partial: >= step_two_blocks(N) doubles of scratch; d_ke_out: 1 double (deterministic sum).
 uint32_t step_two_blocks(uint32_t N);
 hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
                            const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
-                           double* d_ke_out, cudaStream_t stream);
+                           double* d_ke_out, cudaStream_t stream, const BussiNext* bussi = nullptr);
 hb2_status launch_kinetic(const float4* vel, uint32_t N, double* d_partial, uint32_t* d_ticket,
                           double* d_ke_out, cudaStream_t stream);
 // Bussi factor on device (hoomd/md/Thermostat.h:357-447): *d_rescale <- factor for the step-one of
 // timestep *d_timestep; reads *d_ke.
 hb2_status launch_bussi(const double* d_ke, double dof, double dt, double kT, double tau,
-                        const uint64_t* d_timestep, uint32_t seed, uint32_t first_tag,
-                        double* d_rescale, cudaStream_t stream);
+                        uint64_t timestep, uint32_t seed, uint32_t first_tag, double* d_rescale,
+                        cudaStream_t stream);
 hb2_status launch_advance_timestep(uint64_t* d_timestep, cudaStream_t stream);
 // sum of force.w (potential energy), deterministic; and 6 virial sums
 hb2_status launch_reduce_energy(const float4* force, const float* virial, size_t virial_pitch,
