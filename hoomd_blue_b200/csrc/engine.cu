@@ -97,7 +97,10 @@ extern "C" hb2_status hb2_system_create(hb2_system** out, int device, uint32_t n
     s->ntypes = ntypes;
     s->seed = seed & 0xffffu;
     hb2_status st = HB2_OK;
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&s->flag_ready, cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&s->flag_copied, cudaEventDisableTiming) != cudaSuccess)
         st = HB2_ERR_CUDA;
     if (st == HB2_OK)
         st = dev_alloc(&s->d_timestep, 1);
@@ -143,6 +146,12 @@ extern "C" void hb2_system_destroy(hb2_system* s)
     dev_free(s->d_ticket);
     dev_free(s->d_sums);
     cudaStreamDestroy(s->stream);
+    if (s->side_stream)
+        cudaStreamDestroy(s->side_stream);
+    if (s->flag_ready)
+        cudaEventDestroy(s->flag_ready);
+    if (s->flag_copied)
+        cudaEventDestroy(s->flag_copied);
     delete s;
     }
 
@@ -1098,6 +1107,14 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
         if (nl->num_builds == builds_before)
             HB2_TRY(domain_update_ghosts(s));
         }
+    return launch(timestep, want_energy, nullptr);
+    }
+
+// The force pass over the current list. skip_flag (device word) makes the kernel a no-op when set:
+// the step loop launches it before the host knows whether this step rebuilds (see hb2_integrator_run).
+hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t* skip_flag)
+    {
+    hb2_system* s = sys;
     const uint32_t N = s->N;
     if (s->cap > cap_N)
         {
@@ -1135,6 +1152,7 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
     a.face_margin = (float)(nl->rcut_max_max + 2.0 * nl->buffer) * 1.0001f;
     a.tpp = tpp;
     a.energy = want_energy || energy_every_step || tpp != 8;
+    a.skip_flag = skip_flag;
     if (s->mid_event)
         HB2_CUDA(cudaEventRecord(s->mid_event, s->stream));
     HB2_TRY(launch_pair_forces(ev, mode, a, s->box, s->stream));
@@ -1640,26 +1658,59 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                                 s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
                                 nl->maxshift(), nl->d_conditions + 3, st));
         bool flag = false;
+        const uint64_t builds_before = nl->num_builds;
+        // Speculative force launch. On most steps the list is still valid, so the force pass is
+        // queued right behind step one with the rebuild flag as its skip word, and the flag travels
+        // to the host on a side stream meanwhile: the GPU never idles waiting for the host's
+        // decision. When the flag turns out set, the skipped launch cost ~2 us; rebuild and launch
+        // again. (The reference reads the flag with a blocking copy every step,
+        // hoomd/md/NeighborListGPU.cc:78-82.)
+        const bool speculate = check && !it->profiling && !nl->force_update && !nl->params_dirty
+                               && !pf->params_dirty && nl->buffer >= 1e-6
+                               && t + 1 >= nl->last_update_step + nl->rebuild_check_delay;
         if (check)
             {
             // all ranks rebuild on the same step (hoomd/md/NeighborList.cc:1271-1285)
             if (s->dom.active)
                 HB2_TRY(domain_allreduce_max_u32(s, nl->d_conditions + 3, 1));
-            // the one host read per step of the reference's loop (hoomd/md/NeighborListGPU.cc:78-82)
-            HB2_CUDA(cudaMemcpyAsync(nl->h_conditions + 3, nl->d_conditions + 3, sizeof(uint32_t),
-                                     cudaMemcpyDeviceToHost, st));
-            HB2_CUDA(cudaStreamSynchronize(st));
-            flag = nl->h_conditions[3] != 0;
             }
-        if (it->profiling)
+        if (speculate)
             {
-            HB2_CUDA(cudaEventRecord(pe[1], st));
-            s->mid_event = pe[2];
+            HB2_CUDA(cudaEventRecord(s->flag_ready, st));
+            HB2_CUDA(cudaStreamWaitEvent(s->side_stream, s->flag_ready, 0));
+            HB2_CUDA(cudaMemcpyAsync(nl->h_conditions + 3, nl->d_conditions + 3, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, s->side_stream));
+            HB2_CUDA(cudaEventRecord(s->flag_copied, s->side_stream));
+            if (s->dom.active)
+                HB2_TRY(domain_update_ghosts(s));
+            HB2_TRY(pf->launch(t + 1, step + 1 == nsteps, nl->d_conditions + 3));
+            HB2_CUDA(cudaEventSynchronize(s->flag_copied));
+            flag = nl->h_conditions[3] != 0;
+            if (flag)
+                {
+                HB2_TRY(nl->rebuild(t + 1));
+                HB2_TRY(pf->launch(t + 1, step + 1 == nsteps, nullptr));
+                }
             }
-        const uint64_t builds_before = nl->num_builds;
-        hb2_status cst = pf->compute(t + 1, check, flag, step + 1 == nsteps);
-        s->mid_event = nullptr;
-        HB2_TRY(cst);
+        else
+            {
+            if (check)
+                {
+                // the one host read per step of the reference's loop (hoomd/md/NeighborListGPU.cc:78-82)
+                HB2_CUDA(cudaMemcpyAsync(nl->h_conditions + 3, nl->d_conditions + 3, sizeof(uint32_t),
+                                         cudaMemcpyDeviceToHost, st));
+                HB2_CUDA(cudaStreamSynchronize(st));
+                flag = nl->h_conditions[3] != 0;
+                }
+            if (it->profiling)
+                {
+                HB2_CUDA(cudaEventRecord(pe[1], st));
+                s->mid_event = pe[2];
+                }
+            hb2_status cst = pf->compute(t + 1, check, flag, step + 1 == nsteps);
+            s->mid_event = nullptr;
+            HB2_TRY(cst);
+            }
         if (it->profiling)
             {
             HB2_CUDA(cudaEventRecord(pe[3], st));

@@ -78,6 +78,9 @@ struct hb2_system
     std::vector<hb2_nlist*> nlists;
     std::vector<hb2_pair*> pairs;
     cudaEvent_t mid_event = nullptr; // recorded between the nlist update and the force launch
+    // the rebuild flag travels to the host on a side stream while the speculative force pass runs
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t flag_ready = nullptr, flag_copied = nullptr;
 
     hb2_status set_timestep(uint64_t t)
         {
@@ -168,6 +171,7 @@ struct hb2_pair
     hb2_status upload_params();
     hb2_status compute(uint64_t timestep, bool flag_known = false, bool flag_value = false,
                        bool want_energy = true);
+    hb2_status launch(uint64_t timestep, bool want_energy, const uint32_t* skip_flag);
     };
 
 struct hb2_integrator

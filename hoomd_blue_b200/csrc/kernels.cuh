@@ -77,6 +77,7 @@ struct PairArgs
     float face_margin; // r_list_max + buffer (distance from a face beyond which no image shift occurs)
     uint32_t tpp;
     bool energy = true; // false: skip the per-particle potential energy (force.w = 0)
+    const uint32_t* skip_flag = nullptr; // device word; non-zero => the launch does nothing
     };
 hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,
                               const hb2_box& box, cudaStream_t stream);

@@ -105,6 +105,7 @@ template<class Ev> struct PairKArgs
     float face_margin; // r_list_max + buffer: farther than this from every face => no image shifts
     uint32_t stage;    // chunks of a row staged per pass (<= PAIR_STAGE_MAX)
     bool energy;       // accumulate the per-particle potential energy
+    const uint32_t* skip_flag; // non-zero word => return at once (speculative launch, engine.cu)
     BoxF box;
     BoxD boxd;
     };
@@ -118,6 +119,8 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
     {
     typedef typename Ev::param_type param_type;
     constexpr int U = 32 / TPP; // entries per lane per 32-entry chunk
+    if (a.skip_flag && *a.skip_flag)
+        return;
     __shared__ param_type s_params[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_rcutsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_ronsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
@@ -468,6 +471,7 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.boxd = boxd(box);
     k.face_margin = a.face_margin;
     k.energy = a.energy;
+    k.skip_flag = a.skip_flag;
     k.stage = std::min<uint32_t>(std::max<uint32_t>(a.pitch / 32u, 1u), PAIR_STAGE_MAX);
     if (Ev::needs_thermo && (!a.vel || !a.tag))
         {
