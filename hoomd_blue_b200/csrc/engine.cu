@@ -1063,6 +1063,7 @@ hb2_status hb2_pair::upload_params()
     packed.assign(2 * nt2, 0.f);
     rcutsq.assign(nt2, 0.f);
     ronsq.assign(nt2, 0.f);
+    rcutsq_d.assign(nt2, 0.0);
     for (size_t q = 0; q < nt2; q++)
         {
         if (!have_params[q])
@@ -1071,7 +1072,8 @@ hb2_status hb2_pair::upload_params()
             return HB2_ERR_INVALID;
             }
         HB2_TRY(hb2_pack_params(ev, &user[2 * q], 2, &packed[2 * q]));
-        rcutsq[q] = (float)(r_cut[q] * r_cut[q]); // hoomd/md/PotentialPair.h:498
+        rcutsq_d[q] = r_cut[q] * r_cut[q]; // hoomd/md/PotentialPair.h:498
+        rcutsq[q] = (float)rcutsq_d[q];
         ronsq[q] = (float)(r_on[q] * r_on[q]);
         }
     if (!d_params)
@@ -1079,11 +1081,13 @@ hb2_status hb2_pair::upload_params()
         HB2_TRY(dev_alloc(&d_params, 2 * nt2));
         HB2_TRY(dev_alloc(&d_rcutsq, nt2));
         HB2_TRY(dev_alloc(&d_ronsq, nt2));
+        HB2_TRY(dev_alloc(&d_rcutsq_d, nt2));
         }
     cudaStream_t st = sys->stream;
     HB2_CUDA(cudaMemcpyAsync(d_params, packed.data(), sizeof(float) * 2 * nt2, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaMemcpyAsync(d_rcutsq, rcutsq.data(), sizeof(float) * nt2, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaMemcpyAsync(d_ronsq, ronsq.data(), sizeof(float) * nt2, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(d_rcutsq_d, rcutsq_d.data(), sizeof(double) * nt2, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaStreamSynchronize(st));
     params_dirty = false;
     return HB2_OK;
@@ -1140,6 +1144,8 @@ hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t*
     a.params0[1] = packed[1];
     a.rcutsq0 = rcutsq[0];
     a.ronsq0 = ronsq[0];
+    a.rcutsq_d = d_rcutsq_d;
+    a.rcutsq0_d = rcutsq_d[0];
     a.ntypes = s->ntypes;
     a.force = d_force;
     a.virial = s->compute_virial ? d_virial : nullptr;
@@ -1203,6 +1209,7 @@ extern "C" void hb2_pair_destroy(hb2_pair* p)
     dev_free(p->d_params);
     dev_free(p->d_rcutsq);
     dev_free(p->d_ronsq);
+    dev_free(p->d_rcutsq_d);
     dev_free(p->d_force);
     dev_free(p->d_virial);
     delete p;

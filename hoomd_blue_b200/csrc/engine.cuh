@@ -153,6 +153,8 @@ struct hb2_pair
     float* d_params = nullptr;
     float* d_rcutsq = nullptr;
     float* d_ronsq = nullptr;
+    std::vector<double> rcutsq_d;
+    double* d_rcutsq_d = nullptr;
     bool params_dirty = true;
     double kT = 1.0;
     double dt = 0.005;

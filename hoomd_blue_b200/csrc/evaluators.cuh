@@ -85,6 +85,41 @@ class EvaluatorPairLJ
         return "lj";
         }
 
+    // Two pairs per instruction on Blackwell's packed fp32 pipe (FFMA2 / FMUL2 / FADD2, sm_100):
+    // the same arithmetic as evalForceAndEnergy, component-wise on (pair 0, pair 1). Used by the pair
+    // kernel for the one-type, non-xplor instantiations (uniform parameters).
+    static constexpr bool has_packed = true;
+    HB2_DEVICE static void evalPacked(const float2 rsq, const Scalar rcutsq, const param_type& p,
+                                      const bool energy_shift, const bool want_energy,
+                                      float2& force_divr, float2& pair_eng, bool& in0, bool& in1)
+        {
+        const bool on = p.lj1 != 0;
+        in0 = rsq.x < rcutsq && on;
+        in1 = rsq.y < rcutsq && on;
+        float2 y;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(rsq.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(rsq.y));
+        const float2 one = make_float2(1.0f, 1.0f);
+        const float2 e = __ffma2_rn(make_float2(-rsq.x, -rsq.y), y, one);
+        const float2 r2inv = __ffma2_rn(y, e, y);
+        const float2 r6inv = __fmul2_rn(__fmul2_rn(r2inv, r2inv), r2inv);
+        const Scalar a12 = Scalar(12.0) * p.lj1, b6 = Scalar(-6.0) * p.lj2;
+        const float2 t = __ffma2_rn(make_float2(a12, a12), r6inv, make_float2(b6, b6));
+        force_divr = __fmul2_rn(__fmul2_rn(r2inv, r6inv), t);
+        if (want_energy)
+            {
+            const float2 u = __ffma2_rn(make_float2(p.lj1, p.lj1), r6inv, make_float2(-p.lj2, -p.lj2));
+            pair_eng = __fmul2_rn(r6inv, u);
+            if (energy_shift)
+                {
+                const Scalar rcut2inv = rcp_refined(rcutsq);
+                const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+                const Scalar sft = rcut6inv * (p.lj1 * rcut6inv - p.lj2);
+                pair_eng = __fadd2_rn(pair_eng, make_float2(-sft, -sft));
+                }
+            }
+        }
+
     protected:
     Scalar rsq, rcutsq, lj1, lj2;
     };
@@ -97,6 +132,7 @@ class EvaluatorPairLJ
 class EvaluatorPairExample
     {
     public:
+    static constexpr bool has_packed = false;
     struct param_type
         {
         Scalar k;
@@ -148,6 +184,7 @@ class EvaluatorPairExample
 class EvaluatorPairDPDThermoDPD
     {
     public:
+    static constexpr bool has_packed = false;
     struct param_type
         {
         Scalar A;

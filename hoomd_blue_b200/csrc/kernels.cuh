@@ -63,6 +63,11 @@ struct PairArgs
     const float* params; // ntypes^2 x 2 floats (packed by the evaluator's param_type)
     const float* rcutsq; // ntypes^2
     const float* ronsq;  // ntypes^2
+    // r_cut^2 in fp64 (hoomd/md/PotentialPair.h:498 computes it in Scalar = double): decides pairs
+    // whose fp32 rsq lies within rounding of the cut-off exactly as the reference does. Null: the
+    // float values are widened (layer-1 callers that only have floats).
+    const double* rcutsq_d = nullptr;
+    double rcutsq0_d = 0.0;
     // host copies of entry [0] for the one-type fast path (passed in the constant bank)
     float params0[2];
     float rcutsq0, ronsq0;

@@ -32,7 +32,8 @@ namespace hb2
 constexpr int PAIR_BLOCK = 128;
 constexpr int PAIR_MAX_TYPES_SMEM = 16; // ntypes^2 <= 256 entries staged in shared memory
 constexpr int PAIR_STAGE_MAX = 8;       // 32-entry chunks of a row staged in shared memory per pass
-// 10 resident blocks per SM (<= 51 registers): measured best of {unbounded 56 regs, 10, 12} on B200
+// 10 resident blocks per SM (48 registers): with the packed arithmetic the kernel is latency-bound on
+// its gathers and 10 blocks measure 7 % faster than 8 (0.193 vs 0.207 ms at C2)
 #ifndef PAIR_MIN_BLOCKS
 #define PAIR_MIN_BLOCKS 10
 #endif
@@ -94,6 +95,8 @@ template<class Ev> struct PairKArgs
     const float* ronsq;
     typename Ev::param_type param0;
     float rcutsq0, ronsq0;
+    const double* rcutsq_d; // fp64 r_cut^2 per type pair (may be null) and for type pair 0
+    double rcutsq0_d;
     uint32_t ntypes;
     float4* force;
     float* virial;
@@ -150,6 +153,11 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
 
     float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
     float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
+    // Packed path (Blackwell FFMA2/FMUL2/FADD2: two pairs per instruction): one-type, non-xplor,
+    // non-thermostatted evaluators that provide evalPacked. Accumulators hold (even, odd) pair sums.
+    constexpr bool PACKED = Ev::has_packed && ONETYPE && MODE != 2 && !Ev::needs_thermo && (U % 2 == 0);
+    float2 fx2 = make_float2(0.f, 0.f), fy2 = fx2, fz2 = fx2, pe2 = fx2;
+    float2 wxx = fx2, wxy = fx2, wxz = fx2, wyy = fx2, wyz = fx2, wzz = fx2;
 
     // Image handling without per-pair fp32 cancellation error: a particle farther than
     // r_list + buffer from every face has all its listed neighbours in the same image, so the plain
@@ -186,11 +194,28 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
         timestep = a.d_timestep ? *a.d_timestep : a.timestep;
         }
 
-    auto pair_body = [&](const uint32_t j, const float4 pj, const float dx, const float dy,
-                         const float dz)
+    // The cut-off decision of the reference is made in fp64 (rsq < rcutsq with Scalar = double), and
+    // an unshifted LJ pair flipped at the cut-off costs 8e-4 of the rms force. The hot loop stays
+    // branch-free: it decides in fp32 and only notes (two integer instructions per pair) whether any
+    // rsq came within 32 ulp of r_cut^2 — the separations are exact or correctly rounded, so rsq
+    // carries < 2 ulp. Such a pass (about one in 1e5) is then re-walked by `fix_pass`, which decides
+    // the near pairs with the CPU build's exact arithmetic (dist_sq_exact) and adds or removes the
+    // contribution of the pairs where fp32 and the reference disagree.
+    // near_min = min over the pass of (bits(rsq) - bits(r_cut^2) + 32) as unsigned: <= 64 iff some rsq
+    // came within 32 ulp of the cut-off (one VIADDMNMX per pair).
+    uint32_t near_min = 0xffffffffu;
+    auto note_near = [&](const float rsq, const float rcutsq)
     {
-        const float rsq = dx * dx + dy * dy + dz * dz;
+#ifndef PAIR_NO_EXACT
+        near_min = min(near_min, (uint32_t)(__float_as_int(rsq) + (32 - __float_as_int(rcutsq))));
+#endif
+    };
 
+    // one pair; sgn = +1 adds it, -1 removes it (fix_pass). rsq is passed in so that the caller
+    // controls which side of the cut-off the evaluator sees.
+    auto pair_body = [&](const uint32_t j, const float4 pj, const float dx, const float dy,
+                         const float dz, const float rsq, const float sgn)
+    {
         float rcutsq = a.rcutsq0, ronsq = a.ronsq0;
         const param_type* prm = &a.param0;
         if (!ONETYPE)
@@ -242,21 +267,56 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
                 }
             }
         // branch-free accumulation: a pair beyond the cut-off (or the row padding) adds zeros
-        force_divr = evaluated ? force_divr : 0.f;
-        pair_eng = evaluated ? pair_eng : 0.f;
+        force_divr = evaluated ? sgn * force_divr : 0.f;
+        pair_eng = evaluated ? sgn * pair_eng : 0.f;
         fx += dx * force_divr;
         fy += dy * force_divr;
         fz += dz * force_divr;
-        pe += pair_eng * 0.5f;
+        if (ENERGY)
+            pe += pair_eng * 0.5f;
         if (VIRIAL)
             {
-            const float f2 = evaluated ? 0.5f * force_divr_cons : 0.f;
+            const float f2 = evaluated ? 0.5f * sgn * force_divr_cons : 0.f;
             vxx += f2 * dx * dx;
             vxy += f2 * dx * dy;
             vxz += f2 * dx * dz;
             vyy += f2 * dy * dy;
             vyz += f2 * dy * dz;
             vzz += f2 * dz * dz;
+            }
+    };
+
+    // two neighbours at once; dx2 = (dx of pair 0, dx of pair 1) etc.
+    auto pair_body2 = [&](const float2 dx2, const float2 dy2, const float2 dz2)
+    {
+        const float2 rsq = __ffma2_rn(dz2, dz2, __ffma2_rn(dy2, dy2, __fmul2_rn(dx2, dx2)));
+        note_near(rsq.x, a.rcutsq0);
+        note_near(rsq.y, a.rcutsq0);
+        float2 fdr = make_float2(0.f, 0.f), eng = fdr;
+        bool in0 = false, in1 = false;
+        if constexpr (PACKED)
+            Ev::evalPacked(rsq, a.rcutsq0, a.param0, MODE == 1, ENERGY, fdr, eng, in0, in1);
+        fdr.x = in0 ? fdr.x : 0.f;
+        fdr.y = in1 ? fdr.y : 0.f;
+        fx2 = __ffma2_rn(dx2, fdr, fx2);
+        fy2 = __ffma2_rn(dy2, fdr, fy2);
+        fz2 = __ffma2_rn(dz2, fdr, fz2);
+        if (ENERGY)
+            {
+            eng.x = in0 ? eng.x : 0.f;
+            eng.y = in1 ? eng.y : 0.f;
+            pe2 = __ffma2_rn(eng, make_float2(0.5f, 0.5f), pe2);
+            }
+        if (VIRIAL)
+            {
+            const float2 h = __fmul2_rn(fdr, make_float2(0.5f, 0.5f));
+            const float2 hx = __fmul2_rn(h, dx2), hy = __fmul2_rn(h, dy2), hz = __fmul2_rn(h, dz2);
+            wxx = __ffma2_rn(hx, dx2, wxx);
+            wxy = __ffma2_rn(hx, dy2, wxy);
+            wxz = __ffma2_rn(hx, dz2, wxz);
+            wyy = __ffma2_rn(hy, dy2, wyy);
+            wyz = __ffma2_rn(hy, dz2, wyz);
+            wzz = __ffma2_rn(hz, dz2, wzz);
             }
     };
 
@@ -277,6 +337,38 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
             }
         }
 
+    // minimum-image separation pi - pj: the plain difference when no particle of the warp is near a
+    // face, the (hi, lo) form otherwise
+    auto separation_shift = [&](const float4 q, float& dx, float& dy, float& dz)
+    {
+        float d[3];
+        const float qc[3] = {q.x, q.y, q.z};
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            {
+            const float d0 = pc[c] - qc[c];
+            const float ds = (sh[c] - qc[c]) + sl[c];
+            d[c] = fabsf(d0) >= hc[c] ? ds : d0;
+            }
+        dx = d[0];
+        dy = d[1];
+        dz = d[2];
+    };
+    auto separation = [&](const float4 q, float& dx, float& dy, float& dz)
+    {
+        if (!warp_shift)
+            {
+            dx = pi.x - q.x;
+            dy = pi.y - q.y;
+            dz = pi.z - q.z;
+            }
+        else
+            separation_shift(q, dx, dy, dz);
+    };
+    // the one rounding sequence both the hot loop (scalar and packed) and fix_pass use
+    auto rsq_of = [](const float dx, const float dy, const float dz)
+    { return fmaf(dz, dz, fmaf(dy, dy, dx * dx)); };
+
     // ---- staged sweep over the row. Pass p brings chunks [p*stage, (p+1)*stage) of every row of the
     // warp into shared memory with one bulk copy per row; lanes then read their indices with
     // conflict-free 32-bit shared loads (row stride = stage*32 + 8 words).
@@ -285,6 +377,32 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
     uint32_t* __restrict__ myrow = s_rows + (threadIdx.x / TPP) * row_words;
     const uint32_t* __restrict__ grow = a.nlist + (size_t)i * a.pitch;
     const uint32_t nch_warp = __reduce_max_sync(0xffffffffu, nchunks);
+    // rare: re-walk the staged pass, decide the pairs near the cut-off exactly, repair disagreements
+    auto fix_pass = [&](const uint32_t cnt)
+    {
+        for (uint32_t c = 0; c < cnt; c++)
+            for (int u = 0; u < U; u++)
+                {
+                const uint32_t j = myrow[c * 32u + u * TPP + sub];
+                const float4 q = __ldg(a.pos + j);
+                float dx, dy, dz;
+                separation(q, dx, dy, dz);
+                const float rsq = rsq_of(dx, dy, dz);
+                const uint32_t tp = ONETYPE ? 0u : __float_as_uint(q.w) * a.ntypes + ti;
+                const float rcutsq = ONETYPE ? a.rcutsq0 : s_rcutsq[tp];
+                if ((uint32_t)(__float_as_int(rsq) - __float_as_int(rcutsq) + 32) > 64u)
+                    continue;
+                const double rc2 = ONETYPE ? a.rcutsq0_d : (a.rcutsq_d ? a.rcutsq_d[tp] : (double)rcutsq);
+                const bool in_ref = dist_sq_exact(a.boxd, pi, q) < rc2;
+                const bool in_f32 = rsq < rcutsq;
+                if (in_ref == in_f32)
+                    continue;
+                // add the pair just inside the cut-off, or take back what the hot loop added
+                const float below = __uint_as_float(__float_as_uint(rcutsq) - 1u);
+                pair_body(j, q, dx, dy, dz, in_ref ? below : rsq, in_ref ? 1.0f : -1.0f);
+                }
+    };
+
     uint32_t parity = 0;
     for (uint32_t c0 = 0; c0 < nch_warp; c0 += stage)
         {
@@ -315,29 +433,65 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
 #pragma unroll
             for (int u = 0; u < U; u++)
                 pj[u] = __ldg(a.pos + j[u]);
-            if (!warp_shift)
+            // separations of the U neighbours (scalar: each result lands in its own register, so
+            // consecutive pairs form the float2 operands of the packed path without moves)
+            float dxs[U], dys[U], dzs[U];
+            if (!warp_shift) // hoisted: one warp-uniform branch per chunk, not per neighbour
                 {
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    pair_body(j[u], pj[u], pi.x - pj[u].x, pi.y - pj[u].y, pi.z - pj[u].z);
+                    {
+                    dxs[u] = pi.x - pj[u].x;
+                    dys[u] = pi.y - pj[u].y;
+                    dzs[u] = pi.z - pj[u].z;
+                    }
+                }
+            else
+                {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    separation_shift(pj[u], dxs[u], dys[u], dzs[u]);
+                }
+            if constexpr (PACKED)
+                {
+#pragma unroll
+                for (int u = 0; u < U; u += 2)
+                    pair_body2(make_float2(dxs[u], dxs[u + 1]), make_float2(dys[u], dys[u + 1]),
+                               make_float2(dzs[u], dzs[u + 1]));
                 }
             else
                 {
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     {
-                    float d[3];
-                    const float qc[3] = {pj[u].x, pj[u].y, pj[u].z};
-#pragma unroll
-                    for (int q = 0; q < 3; q++)
-                        {
-                        const float d0 = pc[q] - qc[q];
-                        const float ds = (sh[q] - qc[q]) + sl[q];
-                        d[q] = fabsf(d0) >= hc[q] ? ds : d0;
-                        }
-                    pair_body(j[u], pj[u], d[0], d[1], d[2]);
+                    const float rsq = rsq_of(dxs[u], dys[u], dzs[u]);
+                    note_near(rsq, ONETYPE ? a.rcutsq0
+                                           : s_rcutsq[__float_as_uint(pj[u].w) * a.ntypes + ti]);
+                    pair_body(j[u], pj[u], dxs[u], dys[u], dzs[u], rsq, 1.0f);
                     }
                 }
+            }
+        if (near_min <= 64u)
+            fix_pass(cnt);
+        near_min = 0xffffffffu;
+        }
+
+    if constexpr (PACKED)
+        {
+        // fixed order: even-pair sums + odd-pair sums
+        // (the scalar accumulators hold fix_pass's rare corrections)
+        fx += fx2.x + fx2.y;
+        fy += fy2.x + fy2.y;
+        fz += fz2.x + fz2.y;
+        pe += pe2.x + pe2.y;
+        if (VIRIAL)
+            {
+            vxx += wxx.x + wxx.y;
+            vxy += wxy.x + wxy.y;
+            vxz += wxz.x + wxz.y;
+            vyy += wyy.x + wyy.y;
+            vyz += wyz.x + wyz.y;
+            vzz += wzz.x + wzz.y;
             }
         }
 
@@ -458,6 +612,8 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     memcpy(&k.param0, a.params0, sizeof(k.param0));
     k.rcutsq0 = a.rcutsq0;
     k.ronsq0 = a.ronsq0;
+    k.rcutsq_d = a.rcutsq_d;
+    k.rcutsq0_d = a.rcutsq_d ? a.rcutsq0_d : (double)a.rcutsq0;
     k.ntypes = a.ntypes;
     k.force = a.force;
     k.virial = a.virial;

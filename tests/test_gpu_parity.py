@@ -347,3 +347,37 @@ def test_edge_cases(hoomd):
     assert lj.virials is not None
     sim.always_compute_pressure = False
     assert lj.virials is None
+
+
+def test_nve_drift_1e5(hoomd, golden_dir):
+    """NVE energy drift over 1e5 steps (BASELINE.json: "comparable NVE energy drift over 1e5 steps"):
+    the 2,048-particle reference frame, LJ shift, dt = 0.005, against the fp64 CPU oracle's trace
+    (tests/golden/make_drift.py). Trajectories diverge chaotically; the drift statistic is what
+    compares. The oracle's first sample is skipped (its harness starts from zero accelerations)."""
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    ref = np.load(os.path.join(golden_dir, "nve_drift_2k.npz"))
+    N = len(fx["pos"])
+    e_ref = (ref["ke"] + ref["pe"]) / N
+    every = int(ref["every"])
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "shift")
+    sim.run(0)
+    integ = sim.operations.integrator
+    e = []
+    builds = 0
+    for _ in range(len(e_ref) - 1):
+        sim.run(every)
+        builds += cell.num_builds
+        ke, pe, _ = integ._thermo()
+        e.append((ke + pe) / N)
+    e = np.array(e)
+    drift = e[-1] - e[0]
+    drift_ref = e_ref[-1] - e_ref[1]
+    fluct, fluct_ref = np.std(np.diff(e)), np.std(np.diff(e_ref[1:]))
+    print(f"NVE 1e5 steps: drift/N gpu {drift:.2e} ref {drift_ref:.2e}; chunk-to-chunk sigma gpu "
+          f"{fluct:.2e} ref {fluct_ref:.2e}; builds gpu {builds} ref {int(ref['builds'])}")
+    # same short-time energy noise (the integrator and the truncated force are the same) ...
+    assert fluct <= 2.0 * fluct_ref
+    # ... and a long-time drift of the same order as the fp64 reference's (|ref| ~ 5e-4 per particle)
+    assert abs(drift) <= max(5.0 * abs(drift_ref), 3e-3)
+    # same rebuild cadence (identical criterion, different chaotic trajectory)
+    assert abs(builds - int(ref["builds"])) <= 0.02 * int(ref["builds"])
