@@ -349,7 +349,9 @@ def run_ours(args):
     S = int(os.environ.get("HB2_E2E_BLOCK", "100"))
     calls = max(1, min(5, args.steps // S if args.steps >= S else 1))
     if world == 1:
-        snap = sim.state.get_snapshot()
+        # the host copy of the state lives in page-locked memory (contract: inputs come from pinned
+        # host memory), so both directions are plain DMA
+        snap = sim.state.get_snapshot(into=hoomd.Snapshot(pinned=True))
     else:
         loc = sim.state._get_local()
     barrier()
@@ -358,7 +360,7 @@ def run_ours(args):
         if world == 1:
             sim.state.set_snapshot(snap)
             sim.run(S)
-            snap = sim.state.get_snapshot()
+            snap = sim.state.get_snapshot(into=snap)
         else:
             tag_, pos_, vel_, mass_, tid_, img_ = loc
             sim.state._set_tagged(N, tag_, pos_, vel_, tid_, mass_, img_)
@@ -390,7 +392,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / S,
                     "d2h_bytes_per_step": d2h / S, "steps_per_call": S, "calls": calls,
-                    "what": ("state.set_snapshot(host) + sim.run(S) + state.get_snapshot() + energy"
+                    "what": ("state.set_snapshot(pinned host snapshot) + sim.run(S) + state.get_snapshot() + energy"
                              if world == 1 else
                              "per rank: state._set_tagged(host arrays) + sim.run(S) + "
                              "state._get_local() + energy (collective)")},

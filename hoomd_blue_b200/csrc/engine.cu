@@ -346,25 +346,46 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
     cudaStream_t st = s->stream;
     const size_t n = N;
     float* h = s->h_stage;
-    memcpy(h, pos3, 12 * n);
-    if (vel3)
-        memcpy(h + 3 * n, vel3, 12 * n);
-    else
-        memset(h + 3 * n, 0, 12 * n);
-    if (mass)
-        memcpy(h + 6 * n, mass, 4 * n);
-    else
-        std::fill(h + 6 * n, h + 7 * n, 1.0f);
-    if (typeid_)
-        memcpy(h + 7 * n, typeid_, 4 * n);
-    else
-        memset(h + 7 * n, 0, 4 * n);
-    if (image3)
-        memcpy(h + 8 * n, image3, 12 * n);
-    else
-        memset(h + 8 * n, 0, 12 * n);
     float* d = s->d_stage;
-    HB2_CUDA(cudaMemcpyAsync(d, h, 44 * n, cudaMemcpyHostToDevice, st));
+    // Page-locked caller arrays (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are
+    // DMA'd straight into the staging area; pageable ones go through the pinned bounce buffer.
+    auto pinned = [](const void* p)
+    {
+        if (!p)
+            return true;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+            {
+            cudaGetLastError();
+            return false;
+            }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool direct = pinned(pos3) && pinned(vel3) && pinned(mass) && pinned(typeid_) && pinned(image3);
+    auto put = [&](size_t off_words, const void* src, size_t bytes, int fill) -> hb2_status
+    {
+        if (src && direct)
+            {
+            HB2_CUDA(cudaMemcpyAsync(d + off_words, src, bytes, cudaMemcpyHostToDevice, st));
+            return HB2_OK;
+            }
+        if (src)
+            memcpy(h + off_words, src, bytes);
+        else if (fill == 1)
+            std::fill(h + off_words, h + off_words + bytes / 4, 1.0f);
+        else
+            memset(h + off_words, 0, bytes);
+        if (direct) // a missing array's default still comes from the bounce buffer
+            HB2_CUDA(cudaMemcpyAsync(d + off_words, h + off_words, bytes, cudaMemcpyHostToDevice, st));
+        return HB2_OK;
+    };
+    HB2_TRY(put(0, pos3, 12 * n, 0));
+    HB2_TRY(put(3 * n, vel3, 12 * n, 0));
+    HB2_TRY(put(6 * n, mass, 4 * n, 1));
+    HB2_TRY(put(7 * n, typeid_, 4 * n, 0));
+    HB2_TRY(put(8 * n, image3, 12 * n, 0));
+    if (!direct)
+        HB2_CUDA(cudaMemcpyAsync(d, h, 44 * n, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaMemsetAsync(s->d_ticket + 3, 0, sizeof(uint32_t), st));
     s->N = N;
     s->Ng = 0;
@@ -497,6 +518,34 @@ extern "C" hb2_status hb2_system_get_particles(hb2_system* s, float* pos3, float
     // tag order is restored on the device; one pinned D2H copy brings all five arrays back
     HB2_TRY(snapshot_unpack(N, s->pos[c], s->vel[c], s->image[c], s->tag[c], d, d + 3 * n, d + 6 * n,
                             (uint32_t*)(d + 7 * n), (int*)(d + 8 * n), st));
+    auto pinned = [](const void* p)
+    {
+        if (!p)
+            return true;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+            {
+            cudaGetLastError();
+            return false;
+            }
+        return at.type == cudaMemoryTypeHost;
+    };
+    if (pinned(pos3) && pinned(vel3) && pinned(mass) && pinned(typeid_) && pinned(image3))
+        {
+        // page-locked destinations: DMA straight into the caller's arrays
+        if (pos3)
+            HB2_CUDA(cudaMemcpyAsync(pos3, d, 12 * n, cudaMemcpyDeviceToHost, st));
+        if (vel3)
+            HB2_CUDA(cudaMemcpyAsync(vel3, d + 3 * n, 12 * n, cudaMemcpyDeviceToHost, st));
+        if (mass)
+            HB2_CUDA(cudaMemcpyAsync(mass, d + 6 * n, 4 * n, cudaMemcpyDeviceToHost, st));
+        if (typeid_)
+            HB2_CUDA(cudaMemcpyAsync(typeid_, d + 7 * n, 4 * n, cudaMemcpyDeviceToHost, st));
+        if (image3)
+            HB2_CUDA(cudaMemcpyAsync(image3, d + 8 * n, 12 * n, cudaMemcpyDeviceToHost, st));
+        HB2_CUDA(cudaStreamSynchronize(st));
+        return HB2_OK;
+        }
     HB2_CUDA(cudaMemcpyAsync(h, d, 44 * n, cudaMemcpyDeviceToHost, st));
     HB2_CUDA(cudaStreamSynchronize(st));
     if (pos3)

@@ -26,17 +26,29 @@ class _Configuration:
 class _Particles:
     """hoomd.Snapshot.particles: setting N (re)allocates zeroed arrays (hoomd/snapshot.py)."""
 
-    def __init__(self):
+    def __init__(self, pinned=False):
         self.types = ["A"]
         self._N = 0
+        self._pinned = pinned
         self._alloc(0)
 
+    def _zeros(self, shape, dtype, fill=0):
+        if self._pinned and int(np.prod(shape)) > 0:
+            # page-locked host memory (torch is only the allocator here): the engine DMAs such arrays
+            # directly instead of going through its bounce buffer
+            import torch
+            tdt = {np.float32: torch.float32, np.int32: torch.int32, np.uint32: torch.int32}[dtype]
+            a = torch.empty(shape, dtype=tdt, pin_memory=True).numpy().view(dtype)
+            a[...] = fill
+            return a
+        return np.full(shape, fill, dtype=dtype)
+
     def _alloc(self, n):
-        self.position = np.zeros((n, 3), dtype=np.float32)
-        self.velocity = np.zeros((n, 3), dtype=np.float32)
-        self.image = np.zeros((n, 3), dtype=np.int32)
-        self.typeid = np.zeros(n, dtype=np.uint32)
-        self.mass = np.ones(n, dtype=np.float32)
+        self.position = self._zeros((n, 3), np.float32)
+        self.velocity = self._zeros((n, 3), np.float32)
+        self.image = self._zeros((n, 3), np.int32)
+        self.typeid = self._zeros((n,), np.uint32)
+        self.mass = self._zeros((n,), np.float32, 1)
 
     @property
     def N(self):
@@ -49,10 +61,12 @@ class _Particles:
 
 
 class Snapshot:
+    """hoomd.Snapshot (configuration + particles). pinned=True (not in the reference) allocates the
+    particle arrays in page-locked memory so that set_snapshot / get_snapshot copy by DMA."""
 
-    def __init__(self, communicator=None):
+    def __init__(self, communicator=None, pinned=False):
         self.configuration = _Configuration()
-        self.particles = _Particles()
+        self.particles = _Particles(pinned)
         self.communicator = communicator
 
     @classmethod
@@ -185,12 +199,15 @@ class State:
                                      ptr(img, C.c_int32)))
         return tag, pos, vel, mass, tid, img
 
-    def get_snapshot(self):
+    def get_snapshot(self, into=None):
+        """hoomd.State.get_snapshot. `into` (not in the reference) reuses an existing snapshot's
+        arrays — e.g. a pinned one — instead of allocating."""
         L = _lib.lib()
         n = self.N_particles
-        s = Snapshot()
+        s = into if into is not None else Snapshot()
         s.configuration.box = list(self._box)
-        s.particles.N = n
+        if s.particles.N != n:
+            s.particles.N = n
         s.particles.types = list(self._types)
         p = s.particles
         if self._simulation.device.communicator.num_ranks > 1:

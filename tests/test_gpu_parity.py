@@ -381,3 +381,34 @@ def test_nve_drift_1e5(hoomd, golden_dir):
     assert abs(drift) <= max(5.0 * abs(drift_ref), 3e-3)
     # same rebuild cadence (identical criterion, different chaotic trajectory)
     assert abs(builds - int(ref["builds"])) <= 0.02 * int(ref["builds"])
+
+
+def test_snapshot_roundtrip_pageable_and_pinned(hoomd):
+    """set_snapshot / get_snapshot are exact copies in tag order, through the bounce buffer (pageable
+    arrays) and by direct DMA (page-locked arrays), before and after the particles were re-ordered."""
+    pos, vel, L = random_liquid(16, 0.8, seed=2)
+    N = len(pos)
+    rng = np.random.default_rng(1)
+    img = rng.integers(-3, 4, size=(N, 3)).astype(np.int32)
+    tid = rng.integers(0, 2, size=N).astype(np.uint32)
+    mass = rng.uniform(0.5, 2.0, size=N).astype(np.float32)
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=1)
+    snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel, tid, ("A", "B"), img, mass)
+    sim.create_state_from_snapshot(snap)
+    for pinned in (False, True):
+        out = sim.state.get_snapshot(into=hoomd.Snapshot(pinned=pinned))
+        for a, b in ((out.particles.position, pos), (out.particles.velocity, vel),
+                     (out.particles.image, img), (out.particles.typeid, tid), (out.particles.mass, mass)):
+            assert np.array_equal(a, b)
+        sim.state.set_snapshot(out)
+    cell = hoomd.md.nlist.Cell(buffer=0.4)
+    lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+    for k in (("A", "A"), ("A", "B"), ("B", "B")):
+        lj.params[k] = dict(epsilon=1.0, sigma=1.0)
+    cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.0, methods=[cv], forces=[lj])
+    sim.run(3)  # dt = 0: the cell sort permutes the arrays, positions stay put
+    out = sim.state.get_snapshot(into=hoomd.Snapshot(pinned=True))
+    assert np.array_equal(out.particles.position, pos)
+    assert np.array_equal(out.particles.typeid, tid)
+    assert np.array_equal(out.particles.image, img)
