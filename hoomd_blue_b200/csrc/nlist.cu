@@ -26,6 +26,9 @@ constexpr int NL_WARPS = 4;     // warps (home cells) per block
 #ifndef NL_CMAX_DEF
 #define NL_CMAX_DEF 21
 #endif
+#ifndef NL_MIN_BLOCKS
+#define NL_MIN_BLOCKS 5
+#endif
 constexpr int NL_CMAX = NL_CMAX_DEF; // candidates per lane per round (odd); 21 -> 5 blocks per SM
 constexpr int NL_CAP = 32 * NL_CMAX;
 constexpr float NL_FAR = 1.0e18f;
@@ -147,7 +150,7 @@ HB2_DEVICE uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total)
 // MULTITYPE: per-type-pair r_list; SMALLDIM: some grid dimension < 3, so a stencil cell can hold
 // both images of a neighbour and the sweep applies the minimum image itself.
 template<bool MULTITYPE, bool SMALLDIM>
-__global__ void __launch_bounds__(NL_WARPS * 32)
+__global__ void __launch_bounds__(NL_WARPS * 32, NL_MIN_BLOCKS)
     nlist_build_kernel(const float4* __restrict__ pos, uint32_t N, DomainGeom geom,
                        const uint32_t* __restrict__ cell_start,
                        const uint32_t* __restrict__ cell_end,
@@ -283,170 +286,186 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
         const float4* __restrict__ mine = sm.cand + lane * C;
         const uint8_t* __restrict__ mine_t = sm.type + lane * C;
 
-        // ---- 3./4./5. two home particles per sweep
-        for (uint32_t ia = h0; ia < hend; ia += 2)
+        // ---- 3./4./5. H home particles per sweep: every candidate read from shared memory is tested
+        // against all of them, and their rows are emitted in lock step (H independent dependency
+        // chains: this stage is latency-bound). H = 4 was measured too: same 0.93 ms per build at C2,
+        // the extra registers cancel the extra parallelism.
+        constexpr int H = 2;
+        for (uint32_t i0 = h0; i0 < hend; i0 += H)
             {
-            const bool has_b = ia + 1 < hend;
-            const uint32_t ib = has_b ? ia + 1 : ia;
-            // the home cell is part of its own stencil with zero shift: read the home particles
-            // from shared memory when this round staged them (no global latency in the loop)
-            const uint32_t ka = home_off + (ia - h0), kb = home_off + (ib - h0);
-            const bool sa = ka >= r0 && ka < r1, sb = kb >= r0 && kb < r1;
-            const float4 pa = sa ? sm.cand[ka - r0] : __ldg(pos + ia);
-            const float4 pb = sb ? sm.cand[kb - r0] : __ldg(pos + ib);
-            uint32_t ta = 0u, tb = 0u;
-            if (MULTITYPE)
+            uint32_t ih[H], kh[H], th[H];
+            bool has[H], sh_[H];
+            float4 ph[H];
+#pragma unroll
+            for (int h = 0; h < H; h++)
                 {
-                ta = sa ? (uint32_t)sm.type[ka - r0] : __float_as_uint(pa.w);
-                tb = sb ? (uint32_t)sm.type[kb - r0] : __float_as_uint(pb.w);
+                has[h] = i0 + h < hend;
+                ih[h] = has[h] ? i0 + h : i0;
+                // the home cell is part of its own stencil with zero shift: read the home particles
+                // from shared memory when this round staged them (no global latency in the loop)
+                kh[h] = home_off + (ih[h] - h0);
+                sh_[h] = kh[h] >= r0 && kh[h] < r1;
+                ph[h] = sh_[h] ? sm.cand[kh[h] - r0] : __ldg(pos + ih[h]);
+                th[h] = 0u;
+                if (MULTITYPE)
+                    th[h] = sh_[h] ? (uint32_t)sm.type[kh[h] - r0] : __float_as_uint(ph[h].w);
                 }
 
             // Distances are non-negative floats, so their bit patterns order like integers: the sign
             // bit of (bits(r) - bits(threshold)) is the comparison result, and a funnel shift pushes it
-            // into the per-lane mask — two integer instructions per test, no predicates, no branches.
+            // into the per-lane mask — no predicates, no branches.
             // (The masks come out bit-reversed: candidate t lands in bit C-1-t; fixed up after the loop.)
-            uint32_t in_a = 0, in_b = 0, cd_a = 0, cd_b = 0;
-            int lo_a = __float_as_int(rl2_lo1), hi_a = __float_as_int(rl2_hi1) + 1;
-            int lo_b = lo_a, hi_b = hi_a;
-            uint32_t hit_a, hit_b, may_a, may_b;
+            uint32_t hit[H], may[H];
+            const int lo1 = __float_as_int(rl2_lo1), hi1 = __float_as_int(rl2_hi1) + 1;
             if constexpr (!MULTITYPE && !SMALLDIM)
                 {
-                // One-type fast path. Both home particles ride in the two halves of Blackwell's packed
-                // fp32 instructions (FADD2 / FMUL2 / FFMA2 with the candidate as a broadcast scalar
-                // operand): 6 instead of 12 fp instructions per candidate. The guard band is tracked as
-                // a running unsigned minimum of bits(r) - bits(lo) instead of a second mask (r < lo
-                // wraps to a huge value and drops out), so a test costs three integer instructions.
-                const float2 pxx = make_float2(pa.x, pb.x), pyy = make_float2(pa.y, pb.y),
-                             pzz = make_float2(pa.z, pb.z);
-                uint32_t m_a = 0xffffffffu, m_b = 0xffffffffu;
-#pragma unroll 4
+                // One-type fast path. The home particles ride pairwise in the two halves of Blackwell's
+                // packed fp32 instructions (FADD2 / FMUL2 / FFMA2 with the candidate as a broadcast
+                // scalar operand): 6 instead of 12 fp instructions per candidate and pair. The guard
+                // band is tracked as a running unsigned minimum of bits(r) - bits(lo) instead of a
+                // second mask (r < lo wraps to a huge value and drops out).
+                float2 pxx[H / 2], pyy[H / 2], pzz[H / 2];
+#pragma unroll
+                for (int g = 0; g < H / 2; g++)
+                    {
+                    pxx[g] = make_float2(ph[2 * g].x, ph[2 * g + 1].x);
+                    pyy[g] = make_float2(ph[2 * g].y, ph[2 * g + 1].y);
+                    pzz[g] = make_float2(ph[2 * g].z, ph[2 * g + 1].z);
+                    }
+                uint32_t in[H], mn[H];
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    in[h] = 0u;
+                    mn[h] = 0xffffffffu;
+                    }
+#pragma unroll 2
                 for (uint32_t t = 0; t < C; t++)
                     {
                     const float4 c = mine[t];
-                    const float2 dx = __fadd2_rn(pxx, make_float2(-c.x, -c.x));
-                    const float2 dy = __fadd2_rn(pyy, make_float2(-c.y, -c.y));
-                    const float2 dz = __fadd2_rn(pzz, make_float2(-c.z, -c.z));
-                    const float2 r = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                    const uint32_t ka2 = (uint32_t)(__float_as_int(r.x) - lo_a);
-                    const uint32_t kb2 = (uint32_t)(__float_as_int(r.y) - lo_a);
-                    in_a = __funnelshift_l(ka2, in_a, 1); // r < lo : certainly inside
-                    in_b = __funnelshift_l(kb2, in_b, 1);
-                    m_a = min(m_a, ka2);
-                    m_b = min(m_b, kb2);
+#pragma unroll
+                    for (int g = 0; g < H / 2; g++)
+                        {
+                        const float2 dx = __fadd2_rn(pxx[g], make_float2(-c.x, -c.x));
+                        const float2 dy = __fadd2_rn(pyy[g], make_float2(-c.y, -c.y));
+                        const float2 dz = __fadd2_rn(pzz[g], make_float2(-c.z, -c.z));
+                        const float2 r = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                        const uint32_t k0 = (uint32_t)(__float_as_int(r.x) - lo1);
+                        const uint32_t k1 = (uint32_t)(__float_as_int(r.y) - lo1);
+                        in[2 * g] = __funnelshift_l(k0, in[2 * g], 1); // r < lo : certainly inside
+                        in[2 * g + 1] = __funnelshift_l(k1, in[2 * g + 1], 1);
+                        mn[2 * g] = min(mn[2 * g], k0);
+                        mn[2 * g + 1] = min(mn[2 * g + 1], k1);
+                        }
                     }
-                hit_a = __brev(in_a) >> (32u - C);
-                hit_b = __brev(in_b) >> (32u - C);
-                may_a = 0;
-                may_b = 0;
-                const uint32_t W = (uint32_t)(hi_a - lo_a); // lo <= r <= hi  <=>  k < W
-                if (m_a < W || m_b < W)
+                const uint32_t W = (uint32_t)(hi1 - lo1); // lo <= r <= hi  <=>  k < W
+                bool any_band = false;
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    hit[h] = __brev(in[h]) >> (32u - C);
+                    may[h] = 0;
+                    any_band |= mn[h] < W;
+                    }
+                if (any_band)
                     {
                     // rare: find which candidates sit in the band
                     for (uint32_t t = 0; t < C; t++)
                         {
                         const float4 c = mine[t];
-                        const float ax = pa.x - c.x, ay = pa.y - c.y, az = pa.z - c.z;
-                        const float bx = pb.x - c.x, by = pb.y - c.y, bz = pb.z - c.z;
-                        const uint32_t ka2
-                            = (uint32_t)(__float_as_int(fmaf(az, az, fmaf(ay, ay, ax * ax))) - lo_a);
-                        const uint32_t kb2
-                            = (uint32_t)(__float_as_int(fmaf(bz, bz, fmaf(by, by, bx * bx))) - lo_a);
-                        if (ka2 < W)
-                            may_a |= 1u << t;
-                        if (kb2 < W)
-                            may_b |= 1u << t;
+#pragma unroll
+                        for (int h = 0; h < H; h++)
+                            {
+                            const float ax = ph[h].x - c.x, ay = ph[h].y - c.y, az = ph[h].z - c.z;
+                            const uint32_t k
+                                = (uint32_t)(__float_as_int(fmaf(az, az, fmaf(ay, ay, ax * ax))) - lo1);
+                            if (k < W)
+                                may[h] |= 1u << t;
+                            }
                         }
                     }
                 }
             else
                 {
+                uint32_t in[H], cd[H];
+                int lo[H], hi[H];
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    in[h] = cd[h] = 0u;
+                    lo[h] = lo1;
+                    hi[h] = hi1;
+                    }
 #pragma unroll 4
                 for (uint32_t t = 0; t < C; t++)
                     {
                     const float4 c = mine[t];
-                    float ax = pa.x - c.x, ay = pa.y - c.y, az = pa.z - c.z;
-                    float bx = pb.x - c.x, by = pb.y - c.y, bz = pb.z - c.z;
-                    if (SMALLDIM)
-                        {
-                        ax = min_image_f(ax, Lx, hx);
-                        ay = min_image_f(ay, Ly, hy);
-                        az = min_image_f(az, Lz, hz);
-                        bx = min_image_f(bx, Lx, hx);
-                        by = min_image_f(by, Ly, hy);
-                        bz = min_image_f(bz, Lz, hz);
-                        }
-                    const int ra = __float_as_int(ax * ax + ay * ay + az * az);
-                    const int rb = __float_as_int(bx * bx + by * by + bz * bz);
+                    uint32_t tc = 0;
                     if (MULTITYPE)
+                        tc = mine_t[t];
+#pragma unroll
+                    for (int h = 0; h < H; h++)
                         {
-                        const uint32_t tc = mine_t[t];
-                        const float2 tha = s_thr[tc * ntypes + ta], thb = s_thr[tc * ntypes + tb];
-                        lo_a = __float_as_int(tha.x);
-                        hi_a = __float_as_int(tha.y) + 1;
-                        lo_b = __float_as_int(thb.x);
-                        hi_b = __float_as_int(thb.y) + 1;
+                        float ax = ph[h].x - c.x, ay = ph[h].y - c.y, az = ph[h].z - c.z;
+                        if (SMALLDIM)
+                            {
+                            ax = min_image_f(ax, Lx, hx);
+                            ay = min_image_f(ay, Ly, hy);
+                            az = min_image_f(az, Lz, hz);
+                            }
+                        const int r = __float_as_int(ax * ax + ay * ay + az * az);
+                        if (MULTITYPE)
+                            {
+                            const float2 thr = s_thr[tc * ntypes + th[h]];
+                            lo[h] = __float_as_int(thr.x);
+                            hi[h] = __float_as_int(thr.y) + 1;
+                            }
+                        in[h] = __funnelshift_l((uint32_t)(r - lo[h]), in[h], 1); // r <  lo : inside
+                        cd[h] = __funnelshift_l((uint32_t)(r - hi[h]), cd[h], 1); // r <= hi : candidate
                         }
-                    in_a = __funnelshift_l((uint32_t)(ra - lo_a), in_a, 1); // r <  lo : certainly inside
-                    cd_a = __funnelshift_l((uint32_t)(ra - hi_a), cd_a, 1); // r <= hi : candidate
-                    in_b = __funnelshift_l((uint32_t)(rb - lo_b), in_b, 1);
-                    cd_b = __funnelshift_l((uint32_t)(rb - hi_b), cd_b, 1);
                     }
-                hit_a = __brev(in_a) >> (32u - C);
-                hit_b = __brev(in_b) >> (32u - C);
-                may_a = (__brev(cd_a) >> (32u - C)) & ~hit_a;
-                may_b = (__brev(cd_b) >> (32u - C)) & ~hit_b;
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    hit[h] = __brev(in[h]) >> (32u - C);
+                    may[h] = (__brev(cd[h]) >> (32u - C)) & ~hit[h];
+                    }
                 }
             // a particle is not its own neighbour (hoomd/md/NeighborListBinned.cc:144)
-            if (sa)
+            uint32_t may_any = 0;
+#pragma unroll
+            for (int h = 0; h < H; h++)
                 {
-                const uint32_t ks = ka - r0;
-                if (ks / C == (uint32_t)lane)
+                if (sh_[h])
                     {
-                    hit_a &= ~(1u << (ks % C));
-                    may_a &= ~(1u << (ks % C));
+                    const uint32_t ks = kh[h] - r0;
+                    if (ks / C == (uint32_t)lane)
+                        {
+                        hit[h] &= ~(1u << (ks % C));
+                        may[h] &= ~(1u << (ks % C));
+                        }
                     }
-                }
-            if (sb)
-                {
-                const uint32_t ks = kb - r0;
-                if (ks / C == (uint32_t)lane)
-                    {
-                    hit_b &= ~(1u << (ks % C));
-                    may_b &= ~(1u << (ks % C));
-                    }
+                may_any |= may[h];
                 }
             // ---- 4. borderline: decide exactly as the fp64 CPU build does
-            if (__any_sync(0xffffffffu, (may_a | may_b) != 0u))
+            if (__any_sync(0xffffffffu, may_any != 0u))
                 {
-                while (may_a)
-                    {
-                    const uint32_t t = __ffs(may_a) - 1;
-                    may_a &= may_a - 1;
-                    const uint32_t j = __float_as_uint(mine[t].w);
-                    if (j == 0xffffffffu)
-                        continue;
-                    const float4 pj = __ldg(pos + j);
-                    const double rl2d = MULTITYPE ? r_listsq[__float_as_uint(pj.w) * ntypes + ta]
-                                                  : r_listsq_single;
-                    if (rl2d > 0.0 && dist_sq_exact(cst.bd, pa, pj) <= rl2d)
-                        hit_a |= 1u << t;
-                    }
-                while (may_b)
-                    {
-                    const uint32_t t = __ffs(may_b) - 1;
-                    may_b &= may_b - 1;
-                    const uint32_t j = __float_as_uint(mine[t].w);
-                    if (j == 0xffffffffu)
-                        continue;
-                    const float4 pj = __ldg(pos + j);
-                    const double rl2d = MULTITYPE ? r_listsq[__float_as_uint(pj.w) * ntypes + tb]
-                                                  : r_listsq_single;
-                    if (rl2d > 0.0 && dist_sq_exact(cst.bd, pb, pj) <= rl2d)
-                        hit_b |= 1u << t;
-                    }
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    while (may[h])
+                        {
+                        const uint32_t t = __ffs(may[h]) - 1;
+                        may[h] &= may[h] - 1;
+                        const uint32_t j = __float_as_uint(mine[t].w);
+                        if (j == 0xffffffffu)
+                            continue;
+                        const float4 pj = __ldg(pos + j);
+                        const double rl2d = MULTITYPE ? r_listsq[__float_as_uint(pj.w) * ntypes + th[h]]
+                                                      : r_listsq_single;
+                        if (rl2d > 0.0 && dist_sq_exact(cst.bd, ph[h], pj) <= rl2d)
+                            hit[h] |= 1u << t;
+                        }
                 }
-            if (!has_b)
-                hit_b = 0;
 
             // ---- 5. compaction, output-parallel: lane l of pass p writes row slot 32 p + l. It finds
             // the lane that owns that slot by binary search over the exclusive scan of the per-lane
@@ -454,69 +473,72 @@ __global__ void __launch_bounds__(NL_WARPS * 32)
             // pass is one fully coalesced 128-byte store, ascending candidate order == ascending
             // particle index, and slots past the last hit are filled with the dummy particle's index
             // so that rows are padded to a multiple of 32 for the force kernel.
-            uint32_t tot_a, tot_b;
-            const uint32_t off_a = warp_excl_scan(__popc(hit_a), lane, tot_a);
-            const uint32_t off_b = warp_excl_scan(__popc(hit_b), lane, tot_b);
-            uint32_t base_a = 0, base_b = 0;
-            if (r0 > 0)
-                {
-                base_a = n_neigh[ia];
-                base_b = n_neigh[ib];
-                }
             const bool last_round = (r1 == T);
-            // Both rows are emitted in lock step: the source-lane search is a chain of five dependent
-            // shuffles and the bit pick a chain of dependent integer ops, so two independent chains
-            // per warp double the instruction-level parallelism of this latency-bound stage.
-            uint32_t* __restrict__ row_a = nlist + (size_t)ia * pitch;
-            uint32_t* __restrict__ row_b = nlist + (size_t)ib * pitch;
-            // slots [base, base + tot) receive this round's hits; on the last round the tail of the
-            // final 32-slot group receives the dummy index
-            const uint32_t end_a = last_round ? ((base_a + tot_a + 31u) & ~31u) : base_a + tot_a;
-            const uint32_t end_b = has_b ? (last_round ? ((base_b + tot_b + 31u) & ~31u) : base_b + tot_b) : 0u;
-            const uint32_t s0a = base_a & ~31u, s0b = base_b & ~31u;
-            const uint32_t npass = max(end_a > s0a ? (end_a - s0a + 31u) >> 5 : 0u,
-                                       end_b > s0b ? (end_b - s0b + 31u) >> 5 : 0u);
-            // (four chains — two passes of both rows — measured slower: 0.98 vs 0.93 ms per build, the
-            // odd pass count wastes a quarter of the work)
+            uint32_t off[H], tot[H], base[H], end[H], s0[H];
+            uint32_t npass = 0;
+#pragma unroll
+            for (int h = 0; h < H; h++)
+                {
+                if (!has[h])
+                    hit[h] = 0;
+                off[h] = warp_excl_scan(__popc(hit[h]), lane, tot[h]);
+                base[h] = r0 > 0 ? n_neigh[ih[h]] : 0u;
+                // slots [base, base + tot) receive this round's hits; on the last round the tail of
+                // the final 32-slot group receives the dummy index
+                end[h] = has[h] ? (last_round ? ((base[h] + tot[h] + 31u) & ~31u) : base[h] + tot[h]) : 0u;
+                s0[h] = base[h] & ~31u;
+                npass = max(npass, end[h] > s0[h] ? (end[h] - s0[h] + 31u) >> 5 : 0u);
+                }
             for (uint32_t p = 0; p < npass; p++)
                 {
-                const uint32_t slot_a = s0a + 32u * p + lane, slot_b = s0b + 32u * p + lane;
-                const uint32_t ra = slot_a - base_a, rb = slot_b - base_b; // wanted hit ranks
+                uint32_t slot[H], rk[H], src[H];
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    slot[h] = s0[h] + 32u * p + lane;
+                    rk[h] = slot[h] - base[h]; // wanted hit rank
+                    src[h] = 0;
+                    }
                 // source lane: the last lane whose exclusive offset is <= rank
-                uint32_t src_a = 0, src_b = 0;
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1)
                     {
-                    const uint32_t pa_ = __shfl_sync(0xffffffffu, off_a, (src_a + step) & 31);
-                    const uint32_t pb_ = __shfl_sync(0xffffffffu, off_b, (src_b + step) & 31);
-                    if (pa_ <= ra)
-                        src_a += step;
-                    if (pb_ <= rb)
-                        src_b += step;
+                    uint32_t probe[H];
+#pragma unroll
+                    for (int h = 0; h < H; h++)
+                        probe[h] = __shfl_sync(0xffffffffu, off[h], (src[h] + step) & 31);
+#pragma unroll
+                    for (int h = 0; h < H; h++)
+                        if (probe[h] <= rk[h])
+                            src[h] += step;
                     }
-                const uint32_t ma = __shfl_sync(0xffffffffu, hit_a, src_a);
-                const uint32_t mb = __shfl_sync(0xffffffffu, hit_b, src_b);
-                const uint32_t oa = __shfl_sync(0xffffffffu, off_a, src_a);
-                const uint32_t ob = __shfl_sync(0xffffffffu, off_b, src_b);
-                const bool have_a = slot_a >= base_a && ra < tot_a;
-                const bool have_b = slot_b >= base_b && rb < tot_b;
-                // (a slot without a hit evaluates a harmless pick on a clamped rank)
-                const uint32_t ta_ = nth_set_bit(ma, have_a ? ra - oa : 0u);
-                const uint32_t tb_ = nth_set_bit(mb, have_b ? rb - ob : 0u);
-                const uint32_t va = have_a ? __float_as_uint(sm.cand[src_a * C + min(ta_, C - 1u)].w) : dummy_index;
-                const uint32_t vb = have_b ? __float_as_uint(sm.cand[src_b * C + min(tb_, C - 1u)].w) : dummy_index;
-                if (slot_a >= base_a && slot_a < end_a && slot_a < pitch)
-                    row_a[slot_a] = va;
-                if (slot_b >= base_b && slot_b < end_b && slot_b < pitch)
-                    row_b[slot_b] = vb;
+                uint32_t m[H], o[H];
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    m[h] = __shfl_sync(0xffffffffu, hit[h], src[h]);
+                    o[h] = __shfl_sync(0xffffffffu, off[h], src[h]);
+                    }
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    {
+                    const bool have = slot[h] >= base[h] && rk[h] < tot[h];
+                    // (a slot without a hit evaluates a harmless pick on a clamped rank)
+                    const uint32_t t = nth_set_bit(m[h], have ? rk[h] - o[h] : 0u);
+                    const uint32_t v = have ? __float_as_uint(sm.cand[src[h] * C + min(t, C - 1u)].w)
+                                            : dummy_index;
+                    if (slot[h] >= base[h] && slot[h] < end[h] && slot[h] < pitch)
+                        nlist[(size_t)ih[h] * pitch + slot[h]] = v;
+                    }
                 }
-            if (lane == 0)
+#pragma unroll
+            for (int h = 0; h < H; h++)
                 {
-                n_neigh[ia] = base_a + tot_a;
-                if (has_b)
-                    n_neigh[ib] = base_b + tot_b;
+                if (lane == 0 && has[h])
+                    n_neigh[ih[h]] = base[h] + tot[h];
+                if (has[h])
+                    max_n = max(max_n, base[h] + tot[h]);
                 }
-            max_n = max(max_n, max(base_a + tot_a, base_b + tot_b));
             }
         __syncwarp();
         }
