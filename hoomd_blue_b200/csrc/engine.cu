@@ -12,6 +12,9 @@
 #include "kernels.cuh"
 #include "pair_kernel.cuh"
 #include "engine.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 
 namespace hb2
     {
@@ -731,11 +734,30 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
             return HB2_ERR_BOX_TOO_SMALL;
             }
     cudaStream_t st = s->stream;
+    // HB2_TRACE_REBUILD=1: host-timed (synchronising) breakdown of every rebuild on stderr — a
+    // diagnostic for the multi-GPU path, never on in measurements
+    static const bool trace = getenv("HB2_TRACE_REBUILD") != nullptr;
+    auto tick = [&](const char* what)
+    {
+        static double t_prev = 0.0;
+        if (!trace)
+            return;
+        cudaStreamSynchronize(st);
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        const double t = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+        if (what && s->dom.rank == 0)
+            fprintf(stderr, "[rebuild] %-10s %8.3f ms\n", what, t - t_prev);
+        t_prev = t;
+    };
+    tick(nullptr);
     if (s->dom.active)
         {
         // hoomd/Communicator.cc:1510-1570: migrate, then rebuild the ghost layer, on rebuild steps
         HB2_TRY(domain_migrate(s));
+        tick("migrate");
         HB2_TRY(domain_exchange_ghosts(s, rmax));
+        tick("ghosts");
         }
     HB2_TRY(ensure_capacity());
     const uint32_t N = s->N, Ntot = s->N + s->Ng;
@@ -748,9 +770,11 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
                               s->pos[o], s->vel[o], s->image[o], s->tag[o], nullptr, s->rtag, st));
     s->cur = o;
     s->order_epoch++;
+    tick("sort");
     if (s->dom.active)
         HB2_TRY(domain_remap(s, d_order, Ntot));
     HB2_TRY(system_place_dummy(s));
+    tick("remap");
 
     for (;;)
         {
@@ -790,6 +814,7 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
             return HB2_ERR_OUT_OF_BOX;
             }
         max_neigh = h_conditions[0];
+        tick("build");
         if (max_neigh <= pitch)
             break;
         // overflow: regrow to a multiple of 8 with headroom and rebuild
