@@ -125,15 +125,18 @@ extern "C" hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mo
     a.params = d_params;
     a.rcutsq = d_rcutsq;
     a.ronsq = d_ronsq;
-    float h[4];
-    HB2_CUDA(cudaMemcpyAsync(h, d_params, 2 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    HB2_CUDA(cudaMemcpyAsync(h + 2, d_rcutsq, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    HB2_CUDA(cudaMemcpyAsync(h + 3, d_ronsq, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    float h[HB2_PARAM_FLOATS + 2];
+    HB2_CUDA(cudaMemcpyAsync(h, d_params, HB2_PARAM_FLOATS * sizeof(float), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    HB2_CUDA(cudaMemcpyAsync(h + HB2_PARAM_FLOATS, d_rcutsq, sizeof(float), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    HB2_CUDA(cudaMemcpyAsync(h + HB2_PARAM_FLOATS + 1, d_ronsq, sizeof(float), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
     HB2_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    a.params0[0] = h[0];
-    a.params0[1] = h[1];
-    a.rcutsq0 = h[2];
-    a.ronsq0 = h[3];
+    for (int q = 0; q < HB2_PARAM_FLOATS; q++)
+        a.params0[q] = h[q];
+    a.rcutsq0 = h[HB2_PARAM_FLOATS];
+    a.ronsq0 = h[HB2_PARAM_FLOATS + 1];
     a.ntypes = ntypes;
     a.force = (float4*)d_force4;
     a.virial = d_virial;

@@ -11,6 +11,7 @@
 #include "evaluators.cuh"
 #include "kernels.cuh"
 #include "pair_kernel.cuh"
+#include "evaluators_more.cuh"
 #include "engine.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -1053,60 +1054,65 @@ extern "C" hb2_status hb2_nlist_stats(hb2_nlist* nl, double* mean_neigh, uint32_
 // =================================================================================================
 // pair force
 // =================================================================================================
+// one entry per evaluator id: user-parameter count and the host-side pack
+template<class Ev> static void pack_as(const double* user, float* packed)
+    {
+    typename Ev::param_type p;
+    Ev::pack(user, p);
+    memset(packed, 0, HB2_PARAM_FLOATS * sizeof(float));
+    memcpy(packed, &p, sizeof(p));
+    }
+struct EvalInfo
+    {
+    unsigned n_user;
+    void (*pack)(const double*, float*);
+    };
+static void pack_dpd_conservative(const double* user, float* packed)
+    {
+    memset(packed, 0, HB2_PARAM_FLOATS * sizeof(float));
+    packed[0] = (float)user[0];
+    }
+static const EvalInfo* eval_info(hb2_evaluator ev)
+    {
+    static const EvalInfo table[] = {
+        {EvaluatorPairLJ::n_user_params, pack_as<EvaluatorPairLJ>},
+        {EvaluatorPairDPDThermoDPD::n_user_params, pack_as<EvaluatorPairDPDThermoDPD>},
+        {1, pack_dpd_conservative},
+        {EvaluatorPairExample::n_user_params, pack_as<EvaluatorPairExample>},
+        {EvaluatorPairGauss::n_user_params, pack_as<EvaluatorPairGauss>},
+        {EvaluatorPairYukawa::n_user_params, pack_as<EvaluatorPairYukawa>},
+        {EvaluatorPairLJ1208::n_user_params, pack_as<EvaluatorPairLJ1208>},
+        {EvaluatorPairLJ0804::n_user_params, pack_as<EvaluatorPairLJ0804>},
+        {EvaluatorPairForceShiftedLJ::n_user_params, pack_as<EvaluatorPairForceShiftedLJ>},
+        {EvaluatorPairMie::n_user_params, pack_as<EvaluatorPairMie>},
+        {EvaluatorPairMorse::n_user_params, pack_as<EvaluatorPairMorse>},
+    };
+    if ((unsigned)ev >= sizeof(table) / sizeof(table[0]))
+        return nullptr;
+    return &table[(unsigned)ev];
+    }
 static unsigned n_user_params(hb2_evaluator ev)
     {
-    switch (ev)
-        {
-    case HB2_EVAL_LJ:
-        return EvaluatorPairLJ::n_user_params;
-    case HB2_EVAL_DPD:
-        return EvaluatorPairDPDThermoDPD::n_user_params;
-    case HB2_EVAL_DPD_CONSERVATIVE:
-        return 1;
-    case HB2_EVAL_EXAMPLE:
-        return EvaluatorPairExample::n_user_params;
-        }
-    return 0;
+    const EvalInfo* e = eval_info(ev);
+    return e ? e->n_user : 0;
     }
 
 extern "C" hb2_status hb2_pack_params(hb2_evaluator ev, const double* user, uint32_t n_user,
-                                      float packed[2])
+                                      float packed[HB2_PARAM_FLOATS])
     {
-    if (!user || !packed || n_user < n_user_params(ev))
+    const EvalInfo* e = eval_info(ev);
+    if (!e)
+        {
+        set_error("hb2_pack_params: unknown evaluator");
+        return HB2_ERR_INVALID;
+        }
+    if (!user || !packed || n_user < e->n_user)
         {
         set_error("hb2_pack_params: not enough user parameters for this evaluator");
         return HB2_ERR_INVALID;
         }
-    switch (ev)
-        {
-    case HB2_EVAL_LJ:
-        {
-        EvaluatorPairLJ::param_type p;
-        EvaluatorPairLJ::pack(user, p);
-        memcpy(packed, &p, sizeof(p));
-        return HB2_OK;
-        }
-    case HB2_EVAL_DPD:
-        {
-        EvaluatorPairDPDThermoDPD::param_type p;
-        EvaluatorPairDPDThermoDPD::pack(user, p);
-        memcpy(packed, &p, sizeof(p));
-        return HB2_OK;
-        }
-    case HB2_EVAL_DPD_CONSERVATIVE:
-        packed[0] = (float)user[0];
-        packed[1] = 0.f;
-        return HB2_OK;
-    case HB2_EVAL_EXAMPLE:
-        {
-        EvaluatorPairExample::param_type p;
-        EvaluatorPairExample::pack(user, p);
-        memcpy(packed, &p, sizeof(p));
-        return HB2_OK;
-        }
-        }
-    set_error("hb2_pack_params: unknown evaluator");
-    return HB2_ERR_INVALID;
+    e->pack(user, packed);
+    return HB2_OK;
     }
 
 namespace hb2
@@ -1124,6 +1130,20 @@ hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairA
         return pair_forces_dpd_conservative(mode, a, box, stream);
     case HB2_EVAL_EXAMPLE:
         return pair_forces_example(mode, a, box, stream);
+    case HB2_EVAL_GAUSS:
+        return pair_forces_gauss(mode, a, box, stream);
+    case HB2_EVAL_YUKAWA:
+        return pair_forces_yukawa(mode, a, box, stream);
+    case HB2_EVAL_LJ1208:
+        return pair_forces_lj1208(mode, a, box, stream);
+    case HB2_EVAL_LJ0804:
+        return pair_forces_lj0804(mode, a, box, stream);
+    case HB2_EVAL_FORCE_SHIFTED_LJ:
+        return pair_forces_force_shifted_lj(mode, a, box, stream);
+    case HB2_EVAL_MIE:
+        return pair_forces_mie(mode, a, box, stream);
+    case HB2_EVAL_MORSE:
+        return pair_forces_morse(mode, a, box, stream);
         }
     set_error("pair forces: unknown evaluator");
     return HB2_ERR_INVALID;
@@ -1134,7 +1154,7 @@ hb2_status hb2_pair::upload_params()
     {
     const uint32_t nt = sys->ntypes;
     const size_t nt2 = (size_t)nt * nt;
-    packed.assign(2 * nt2, 0.f);
+    packed.assign(HB2_PARAM_FLOATS * nt2, 0.f);
     rcutsq.assign(nt2, 0.f);
     ronsq.assign(nt2, 0.f);
     rcutsq_d.assign(nt2, 0.0);
@@ -1145,20 +1165,20 @@ hb2_status hb2_pair::upload_params()
             set_error("pair: parameters are not set for every type pair");
             return HB2_ERR_INVALID;
             }
-        HB2_TRY(hb2_pack_params(ev, &user[2 * q], 2, &packed[2 * q]));
+        HB2_TRY(hb2_pack_params(ev, &user[HB2_PARAM_FLOATS * q], HB2_PARAM_FLOATS, &packed[HB2_PARAM_FLOATS * q]));
         rcutsq_d[q] = r_cut[q] * r_cut[q]; // hoomd/md/PotentialPair.h:498
         rcutsq[q] = (float)rcutsq_d[q];
         ronsq[q] = (float)(r_on[q] * r_on[q]);
         }
     if (!d_params)
         {
-        HB2_TRY(dev_alloc(&d_params, 2 * nt2));
+        HB2_TRY(dev_alloc(&d_params, HB2_PARAM_FLOATS * nt2));
         HB2_TRY(dev_alloc(&d_rcutsq, nt2));
         HB2_TRY(dev_alloc(&d_ronsq, nt2));
         HB2_TRY(dev_alloc(&d_rcutsq_d, nt2));
         }
     cudaStream_t st = sys->stream;
-    HB2_CUDA(cudaMemcpyAsync(d_params, packed.data(), sizeof(float) * 2 * nt2, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemcpyAsync(d_params, packed.data(), sizeof(float) * HB2_PARAM_FLOATS * nt2, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaMemcpyAsync(d_rcutsq, rcutsq.data(), sizeof(float) * nt2, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaMemcpyAsync(d_ronsq, ronsq.data(), sizeof(float) * nt2, cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaMemcpyAsync(d_rcutsq_d, rcutsq_d.data(), sizeof(double) * nt2, cudaMemcpyHostToDevice, st));
@@ -1214,8 +1234,8 @@ hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t*
     a.params = d_params;
     a.rcutsq = d_rcutsq;
     a.ronsq = d_ronsq;
-    a.params0[0] = packed[0];
-    a.params0[1] = packed[1];
+    for (int q = 0; q < HB2_PARAM_FLOATS; q++)
+        a.params0[q] = packed[q];
     a.rcutsq0 = rcutsq[0];
     a.ronsq0 = ronsq[0];
     a.rcutsq_d = d_rcutsq_d;
@@ -1258,7 +1278,7 @@ extern "C" hb2_status hb2_pair_create(hb2_pair** out, hb2_system* s, hb2_nlist* 
     p->ev = ev;
     p->mode = mode;
     const size_t nt2 = (size_t)s->ntypes * s->ntypes;
-    p->user.assign(2 * nt2, 0.0);
+    p->user.assign(HB2_PARAM_FLOATS * nt2, 0.0);
     p->have_params.assign(nt2, 0);
     p->r_cut.assign(nt2, 0.0);
     p->r_on.assign(nt2, 0.0);
@@ -1308,15 +1328,15 @@ extern "C" hb2_status hb2_pair_set_params(hb2_pair* p, uint32_t ti, uint32_t tj,
     size_t a, b;
     if (!p || !user_params || !pair_index(p, ti, tj, a, b))
         return HB2_ERR_INVALID;
-    if (n_user < n_user_params(p->ev) || n_user > 2)
+    if (n_user < n_user_params(p->ev) || n_user > HB2_PARAM_FLOATS)
         {
         set_error("hb2_pair_set_params: wrong number of parameters for this evaluator");
         return HB2_ERR_INVALID;
         }
     for (size_t q : {a, b})
         {
-        p->user[2 * q] = user_params[0];
-        p->user[2 * q + 1] = n_user > 1 ? user_params[1] : 0.0;
+        for (uint32_t k = 0; k < HB2_PARAM_FLOATS; k++)
+            p->user[HB2_PARAM_FLOATS * q + k] = k < n_user ? user_params[k] : 0.0;
         p->have_params[q] = 1;
         }
     p->params_dirty = true;
@@ -1549,7 +1569,7 @@ static void tail_correction(hb2_pair* p, double& e, double& w)
             {
             const double rho_j = n_per_type[tj] / volume;
             const size_t tp = (size_t)tj * nt + ti;
-            const double eps = p->user[2 * tp], sig = p->user[2 * tp + 1];
+            const double eps = p->user[HB2_PARAM_FLOATS * tp], sig = p->user[HB2_PARAM_FLOATS * tp + 1];
             const double s6 = sig * sig * sig * sig * sig * sig;
             const double lj1 = 4.0 * eps * s6 * s6, lj2 = 4.0 * eps * s6;
             const double rcutsq = p->r_cut[tp] * p->r_cut[tp];

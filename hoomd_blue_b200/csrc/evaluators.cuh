@@ -48,6 +48,7 @@ class EvaluatorPairLJ
         Scalar lj2; // 4 eps sigma^6
         };
     static constexpr bool needs_thermo = false;
+    static constexpr bool tune_tpp = true;
     static constexpr unsigned n_user_params = 2; // {epsilon, sigma}
 
     // hoomd/md/EvaluatorPairLJ.h:119-140: sigma_6 = sigma^6, epsilon_x_4 = 4 eps (fp64 on the host)
@@ -133,6 +134,7 @@ class EvaluatorPairExample
     {
     public:
     static constexpr bool has_packed = false;
+    static constexpr bool tune_tpp = true;
     struct param_type
         {
         Scalar k;
@@ -185,6 +187,7 @@ class EvaluatorPairDPDThermoDPD
     {
     public:
     static constexpr bool has_packed = false;
+    static constexpr bool tune_tpp = true;
     struct param_type
         {
         Scalar A;

@@ -1,0 +1,339 @@
+// evaluators_more.cuh — further pair potentials through the same evaluator template
+// (the reference generates one kernel per evaluator the same way,
+// hoomd/md/CMakeLists.txt:505-554). Each class restates the arithmetic of the cited reference header in
+// fp32; `pack` is its param_type(pybind11::dict) constructor over a plain array of user parameters.
+// They are instantiated for the default threads-per-particle only (tune_tpp = false).
+#pragma once
+#include "evaluators.cuh"
+
+namespace hb2
+    {
+#define HB2_EVAL_COMMON(NUSER)                          \
+    static constexpr bool needs_thermo = false;         \
+    static constexpr bool has_packed = false;           \
+    static constexpr bool tune_tpp = false;             \
+    static constexpr unsigned n_user_params = NUSER;
+
+// V = eps exp(-r^2 / (2 sigma^2))   (hoomd/md/EvaluatorPairGauss.h:126-147)
+class EvaluatorPairGauss
+    {
+    public:
+    struct param_type
+        {
+        Scalar epsilon, sigma;
+        };
+    HB2_EVAL_COMMON(2) // {epsilon, sigma}
+    static void pack(const double* user, param_type& p)
+        {
+        p.epsilon = (Scalar)user[0];
+        p.sigma = (Scalar)user[1];
+        }
+    HB2_DEVICE EvaluatorPairGauss(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), epsilon(p.epsilon), sigma(p.sigma)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar sigma_sq = sigma * sigma;
+            const Scalar exp_val = __expf(Scalar(-0.5) * rsq / sigma_sq);
+            force_divr = epsilon / sigma_sq * exp_val;
+            pair_eng = epsilon * exp_val;
+            if (energy_shift)
+                pair_eng -= epsilon * __expf(Scalar(-0.5) * rcutsq / sigma_sq);
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "gauss";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, epsilon, sigma;
+    };
+
+// V = eps exp(-kappa r) / r   (hoomd/md/EvaluatorPairYukawa.h:128-154)
+class EvaluatorPairYukawa
+    {
+    public:
+    struct param_type
+        {
+        Scalar epsilon, kappa;
+        };
+    HB2_EVAL_COMMON(2) // {epsilon, kappa}
+    static void pack(const double* user, param_type& p)
+        {
+        p.epsilon = (Scalar)user[0];
+        p.kappa = (Scalar)user[1];
+        }
+    HB2_DEVICE EvaluatorPairYukawa(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), epsilon(p.epsilon), kappa(p.kappa)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && epsilon != 0)
+            {
+            const Scalar rinv = rsqrt_refined(rsq);
+            const Scalar r = rsq * rinv;
+            const Scalar r2inv = rinv * rinv;
+            const Scalar exp_val = expf(-kappa * r);
+            force_divr = epsilon * exp_val * r2inv * (rinv + kappa);
+            pair_eng = epsilon * exp_val * rinv;
+            if (energy_shift)
+                {
+                const Scalar rcutinv = rsqrt_refined(rcutsq);
+                pair_eng -= epsilon * expf(-kappa * rcutsq * rcutinv) * rcutinv;
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "yukawa";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, epsilon, kappa;
+    };
+
+// V = 4 eps [(sigma/r)^12 - (sigma/r)^8]   (hoomd/md/EvaluatorPairLJ1208.h:74-88,139-165)
+class EvaluatorPairLJ1208
+    {
+    public:
+    struct param_type
+        {
+        Scalar lj1, lj2; // 4 eps sigma^12, 4 eps sigma^8
+        };
+    HB2_EVAL_COMMON(2) // {epsilon, sigma}
+    static void pack(const double* user, param_type& p)
+        {
+        const double s4 = user[1] * user[1] * user[1] * user[1];
+        p.lj1 = (Scalar)(4.0 * user[0] * s4 * s4 * s4);
+        p.lj2 = (Scalar)(4.0 * user[0] * s4 * s4);
+        }
+    HB2_DEVICE EvaluatorPairLJ1208(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), lj1(p.lj1), lj2(p.lj2)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && lj1 != 0)
+            {
+            const Scalar r2inv = rcp_refined(rsq);
+            const Scalar r4inv = r2inv * r2inv;
+            const Scalar r8inv = r4inv * r4inv;
+            force_divr = r2inv * r8inv * (Scalar(12.0) * lj1 * r4inv - Scalar(8.0) * lj2);
+            pair_eng = r8inv * (lj1 * r4inv - lj2);
+            if (energy_shift)
+                {
+                const Scalar c2 = rcp_refined(rcutsq);
+                const Scalar c4 = c2 * c2, c8 = c4 * c4;
+                pair_eng -= c8 * (lj1 * c4 - lj2);
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "lj1208";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, lj1, lj2;
+    };
+
+// V = 4 eps [(sigma/r)^8 - (sigma/r)^4]   (hoomd/md/EvaluatorPairLJ0804.h)
+class EvaluatorPairLJ0804
+    {
+    public:
+    struct param_type
+        {
+        Scalar lj1, lj2; // 4 eps sigma^8, 4 eps sigma^4
+        };
+    HB2_EVAL_COMMON(2) // {epsilon, sigma}
+    static void pack(const double* user, param_type& p)
+        {
+        const double s4 = user[1] * user[1] * user[1] * user[1];
+        p.lj1 = (Scalar)(4.0 * user[0] * s4 * s4);
+        p.lj2 = (Scalar)(4.0 * user[0] * s4);
+        }
+    HB2_DEVICE EvaluatorPairLJ0804(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), lj1(p.lj1), lj2(p.lj2)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && lj1 != 0)
+            {
+            const Scalar r2inv = rcp_refined(rsq);
+            const Scalar r4inv = r2inv * r2inv;
+            force_divr = r2inv * r4inv * (Scalar(8.0) * lj1 * r4inv - Scalar(4.0) * lj2);
+            pair_eng = r4inv * (lj1 * r4inv - lj2);
+            if (energy_shift)
+                {
+                const Scalar c2 = rcp_refined(rcutsq);
+                const Scalar c4 = c2 * c2;
+                pair_eng -= c4 * (lj1 * c4 - lj2);
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "lj0804";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, lj1, lj2;
+    };
+
+// LJ with the force shifted to zero at r_cut   (hoomd/md/EvaluatorPairForceShiftedLJ.h:144-176)
+class EvaluatorPairForceShiftedLJ
+    {
+    public:
+    struct param_type
+        {
+        Scalar lj1, lj2;
+        };
+    HB2_EVAL_COMMON(2) // {epsilon, sigma}
+    static void pack(const double* user, param_type& p)
+        {
+        const double s6 = user[1] * user[1] * user[1] * user[1] * user[1] * user[1];
+        p.lj1 = (Scalar)(4.0 * user[0] * s6 * s6);
+        p.lj2 = (Scalar)(4.0 * user[0] * s6);
+        }
+    HB2_DEVICE EvaluatorPairForceShiftedLJ(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), lj1(p.lj1), lj2(p.lj2)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && lj1 != 0)
+            {
+            const Scalar r2inv = rcp_refined(rsq);
+            const Scalar r6inv = r2inv * r2inv * r2inv;
+            force_divr = r2inv * r6inv * (Scalar(12.0) * lj1 * r6inv - Scalar(6.0) * lj2);
+            pair_eng = r6inv * (lj1 * r6inv - lj2);
+            const Scalar rcut2inv = rcp_refined(rcutsq);
+            const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+            if (energy_shift)
+                pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
+            const Scalar rcut_r_inv = rsqrt_refined(rsq * rcutsq);
+            const Scalar force_rcut_at_rcut = rcut6inv * (Scalar(12.0) * lj1 * rcut6inv - Scalar(6.0) * lj2);
+            force_divr -= rcut_r_inv * force_rcut_at_rcut;
+            pair_eng += (rsq * rcut_r_inv - Scalar(1.0)) * force_rcut_at_rcut;
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "force_shifted_lj";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, lj1, lj2;
+    };
+
+// Mie n-m potential   (hoomd/md/EvaluatorPairMie.h:71-82,129-153)
+class EvaluatorPairMie
+    {
+    public:
+    struct param_type
+        {
+        Scalar m1, m2, m3, m4; // prefactor eps sigma^n, prefactor eps sigma^m, n, m
+        };
+    HB2_EVAL_COMMON(4) // {epsilon, sigma, n, m}
+    static void pack(const double* user, param_type& p)
+        {
+        const double eps = user[0], sigma = user[1], n = user[2], m = user[3];
+        const double out_front = (n / (n - m)) * pow(n / m, m / (n - m));
+        p.m1 = (Scalar)(out_front * eps * pow(sigma, n));
+        p.m2 = (Scalar)(out_front * eps * pow(sigma, m));
+        p.m3 = (Scalar)n;
+        p.m4 = (Scalar)m;
+        }
+    HB2_DEVICE EvaluatorPairMie(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), mie1(p.m1), mie2(p.m2), mie3(p.m3), mie4(p.m4)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && mie1 != 0)
+            {
+            const Scalar r2inv = rcp_refined(rsq);
+            const Scalar rninv = powf(r2inv, mie3 * Scalar(0.5));
+            const Scalar rminv = powf(r2inv, mie4 * Scalar(0.5));
+            force_divr = r2inv * (mie3 * mie1 * rninv - mie4 * mie2 * rminv);
+            pair_eng = mie1 * rninv - mie2 * rminv;
+            if (energy_shift)
+                pair_eng -= mie1 * powf(rcutsq, -mie3 * Scalar(0.5)) - mie2 * powf(rcutsq, -mie4 * Scalar(0.5));
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "mie";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, mie1, mie2, mie3, mie4;
+    };
+
+// V = D0 [exp(-2 alpha (r - r0)) - 2 exp(-alpha (r - r0))]   (hoomd/md/EvaluatorPairMorse.h:125-148)
+class EvaluatorPairMorse
+    {
+    public:
+    struct param_type
+        {
+        Scalar D0, alpha, r0, _pad;
+        };
+    HB2_EVAL_COMMON(3) // {D0, alpha, r0}
+    static void pack(const double* user, param_type& p)
+        {
+        p.D0 = (Scalar)user[0];
+        p.alpha = (Scalar)user[1];
+        p.r0 = (Scalar)user[2];
+        p._pad = 0;
+        }
+    HB2_DEVICE EvaluatorPairMorse(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), D0(p.D0), alpha(p.alpha), r0(p.r0)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar rinv = rsqrt_refined(rsq);
+            const Scalar r = rsq * rinv;
+            const Scalar ef = expf(-alpha * (r - r0));
+            pair_eng = D0 * ef * (ef - Scalar(2.0));
+            force_divr = Scalar(2.0) * D0 * alpha * ef * (ef - Scalar(1.0)) * rinv;
+            if (energy_shift)
+                {
+                const Scalar rcut = sqrtf(rcutsq);
+                const Scalar efc = expf(-alpha * (rcut - r0));
+                pair_eng -= D0 * efc * (efc - Scalar(2.0));
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "morse";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, D0, alpha, r0;
+    };
+#undef HB2_EVAL_COMMON
+    } // namespace hb2

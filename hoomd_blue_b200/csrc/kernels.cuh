@@ -60,7 +60,7 @@ struct PairArgs
     const uint32_t* n_neigh;
     const uint32_t* nlist;
     uint32_t pitch;
-    const float* params; // ntypes^2 x 2 floats (packed by the evaluator's param_type)
+    const float* params; // ntypes^2 x HB2_PARAM_FLOATS floats (packed by the evaluator's param_type)
     const float* rcutsq; // ntypes^2
     const float* ronsq;  // ntypes^2
     // r_cut^2 in fp64 (hoomd/md/PotentialPair.h:498 computes it in Scalar = double): decides pairs
@@ -69,7 +69,7 @@ struct PairArgs
     const double* rcutsq_d = nullptr;
     double rcutsq0_d = 0.0;
     // host copies of entry [0] for the one-type fast path (passed in the constant bank)
-    float params0[2];
+    float params0[HB2_PARAM_FLOATS];
     float rcutsq0, ronsq0;
     uint32_t ntypes;
     float4* force;

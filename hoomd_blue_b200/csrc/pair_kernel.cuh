@@ -90,7 +90,7 @@ template<class Ev> struct PairKArgs
     const uint32_t* n_neigh;
     const uint32_t* nlist;
     uint32_t pitch;
-    const typename Ev::param_type* params;
+    const float* params; // HB2_PARAM_FLOATS floats per type pair
     const float* rcutsq;
     const float* ronsq;
     typename Ev::param_type param0;
@@ -139,7 +139,7 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
         const uint32_t nt2 = a.ntypes * a.ntypes;
         for (uint32_t t = threadIdx.x; t < nt2; t += blockDim.x)
             {
-            s_params[t] = a.params[t];
+            s_params[t] = *reinterpret_cast<const param_type*>(a.params + HB2_PARAM_FLOATS * t);
             s_rcutsq[t] = a.rcutsq[t];
             s_ronsq[t] = a.ronsq[t];
             }
@@ -554,6 +554,10 @@ hb2_status pair_launch_tpp(const PairKArgs<Ev>& k, cudaStream_t stream)
 template<class Ev, int MODE, bool VIRIAL>
 hb2_status pair_launch(const PairKArgs<Ev>& k, uint32_t tpp, cudaStream_t stream)
     {
+    // evaluators outside the benchmarked set are built for the default threads-per-particle only
+    if constexpr (!Ev::tune_tpp)
+        return pair_launch_tpp<Ev, MODE, VIRIAL, 8>(k, stream);
+    else
     switch (tpp)
         {
     case 4:
@@ -584,8 +588,9 @@ template<class Ev>
 hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& box,
                          cudaStream_t stream)
     {
-    static_assert(sizeof(typename Ev::param_type) == 2 * sizeof(float),
-                  "packed param_type is two floats on this ABI");
+    static_assert(sizeof(typename Ev::param_type) <= HB2_PARAM_FLOATS * sizeof(float)
+                      && alignof(typename Ev::param_type) <= 16,
+                  "packed param_type is at most four floats on this ABI");
     if (a.N == 0)
         return HB2_OK;
     if (a.ntypes > PAIR_MAX_TYPES_SMEM)
@@ -606,7 +611,7 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.n_neigh = a.n_neigh;
     k.nlist = a.nlist;
     k.pitch = a.pitch;
-    k.params = reinterpret_cast<const typename Ev::param_type*>(a.params);
+    k.params = a.params;
     k.rcutsq = a.rcutsq;
     k.ronsq = a.ronsq;
     memcpy(&k.param0, a.params0, sizeof(k.param0));
@@ -653,4 +658,11 @@ hb2_status pair_forces_lj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaS
 hb2_status pair_forces_dpd(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_example(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_dpd_conservative(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_gauss(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_yukawa(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_lj1208(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_lj0804(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_force_shifted_lj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_mie(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_morse(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
     } // namespace hb2

@@ -219,3 +219,53 @@ class ExamplePair(Pair):
     modes none/shift/xplor."""
     _evaluator = "example_pair"
     _param_keys = ("k", "sigma")
+
+
+# ---- further potentials through the same evaluator template (hoomd/md/pair/pair.py; SURVEY.md 8(f))
+class Gaussian(Pair):
+    """hoomd.md.pair.Gaussian: V = epsilon exp(-r^2 / (2 sigma^2)); params {epsilon, sigma}
+    (hoomd/md/pair/pair.py Gaussian, hoomd/md/EvaluatorPairGauss.h)."""
+    _evaluator = "gauss"
+    _param_keys = ("epsilon", "sigma")
+
+
+Gauss = Gaussian  # the pre-v4 name
+
+
+class Yukawa(Pair):
+    """hoomd.md.pair.Yukawa: V = epsilon exp(-kappa r) / r; params {epsilon, kappa}."""
+    _evaluator = "yukawa"
+    _param_keys = ("epsilon", "kappa")
+
+
+class LJ1208(Pair):
+    """hoomd.md.pair.LJ1208: V = 4 epsilon [(sigma/r)^12 - (sigma/r)^8]; params {epsilon, sigma}."""
+    _evaluator = "lj1208"
+    _param_keys = ("epsilon", "sigma")
+
+
+class LJ0804(Pair):
+    """hoomd.md.pair.LJ0804: V = 4 epsilon [(sigma/r)^8 - (sigma/r)^4]; params {epsilon, sigma}."""
+    _evaluator = "lj0804"
+    _param_keys = ("epsilon", "sigma")
+
+
+class ForceShiftedLJ(Pair):
+    """hoomd.md.pair.ForceShiftedLJ: LJ with the force shifted to zero at r_cut; params {epsilon,
+    sigma}; modes none / shift."""
+    _accepted_modes = ("none", "shift")
+    _evaluator = "force_shifted_lj"
+    _param_keys = ("epsilon", "sigma")
+
+
+class Mie(Pair):
+    """hoomd.md.pair.Mie: the n-m potential; params {epsilon, sigma, n, m}."""
+    _evaluator = "mie"
+    _param_keys = ("epsilon", "sigma", "n", "m")
+
+
+class Morse(Pair):
+    """hoomd.md.pair.Morse: V = D0 [exp(-2 alpha (r - r0)) - 2 exp(-alpha (r - r0))]; params {D0, alpha,
+    r0}."""
+    _evaluator = "morse"
+    _param_keys = ("D0", "alpha", "r0")

@@ -72,8 +72,17 @@ typedef enum
     HB2_EVAL_LJ = 0,  /* hoomd/md/EvaluatorPairLJ.h:95-270; params {epsilon, sigma} */
     HB2_EVAL_DPD = 1, /* hoomd/md/EvaluatorPairDPDThermoDPD.h:144-277; params {A, gamma} (+kT, seed) */
     HB2_EVAL_DPD_CONSERVATIVE = 2, /* same header :186-203; params {A} */
-    HB2_EVAL_EXAMPLE = 3 /* example_plugins/pair_plugin/EvaluatorPairExample.h; params {k, sigma} */
+    HB2_EVAL_EXAMPLE = 3, /* example_plugins/pair_plugin/EvaluatorPairExample.h; params {k, sigma} */
+    /* more evaluators through the same template (hoomd/md/CMakeLists.txt:505-527): */
+    HB2_EVAL_GAUSS = 4,            /* hoomd/md/EvaluatorPairGauss.h; {epsilon, sigma} */
+    HB2_EVAL_YUKAWA = 5,           /* hoomd/md/EvaluatorPairYukawa.h; {epsilon, kappa} */
+    HB2_EVAL_LJ1208 = 6,           /* hoomd/md/EvaluatorPairLJ1208.h; {epsilon, sigma} */
+    HB2_EVAL_LJ0804 = 7,           /* hoomd/md/EvaluatorPairLJ0804.h; {epsilon, sigma} */
+    HB2_EVAL_FORCE_SHIFTED_LJ = 8, /* hoomd/md/EvaluatorPairForceShiftedLJ.h; {epsilon, sigma} */
+    HB2_EVAL_MIE = 9,              /* hoomd/md/EvaluatorPairMie.h; {epsilon, sigma, n, m} */
+    HB2_EVAL_MORSE = 10            /* hoomd/md/EvaluatorPairMorse.h; {D0, alpha, r0} */
     } hb2_evaluator;
+#define HB2_PARAM_FLOATS 4 /* packed evaluator parameters per type pair (param_type is <= 16 bytes) */
 
 /* hoomd/md/PotentialPair.h:104-109 */
 typedef enum
@@ -120,8 +129,8 @@ hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_to
                                         uint32_t* d_conditions, void* stream);
 
 /* Replaces gpu_compute_pair_forces<evaluator> (hoomd/md/PotentialPairGPU.cuh:579-656; args
- * pair_args_t :44-98). d_params: ntypes^2 x 2 floats of evaluator-packed parameters
- * (hb2_pack_params), d_rcutsq / d_ronsq: ntypes^2 floats, all indexed tj*ntypes+ti. d_force4 =
+ * pair_args_t :44-98). d_params: ntypes^2 x HB2_PARAM_FLOATS floats of evaluator-packed
+ * parameters (hb2_pack_params), d_rcutsq / d_ronsq: ntypes^2 floats, all indexed tj*ntypes+ti. d_force4 =
  * (fx,fy,fz,pe) per particle, d_virial = 6 x virial_pitch floats (xx,xy,xz,yy,yz,zz) or NULL
  * (pressure flag off, hoomd/md/PotentialPair.h:739-752). DPD-only inputs may be NULL otherwise.
  * face_margin: a particle farther than this from every box face is guaranteed to have all listed
@@ -139,7 +148,7 @@ hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, co
 /* Host helper: user parameters -> packed evaluator parameters (the param_type constructor of the
  * evaluator, e.g. hoomd/md/EvaluatorPairLJ.h:119-140: lj1 = 4 eps sigma^12, lj2 = 4 eps sigma^6). */
 hb2_status hb2_pack_params(hb2_evaluator ev, const double* user_params, uint32_t n_user,
-                           float packed[2]);
+                           float packed[HB2_PARAM_FLOATS]);
 
 /* Replace gpu_nvt_rescale_step_one / _step_two (hoomd/md/TwoStepConstantVolumeGPU.cu:102-114,
  * :215-223; arithmetic hoomd/md/TwoStepConstantVolume.cc:33-79, :234-260). Step one also performs

@@ -109,7 +109,14 @@ def test_forces_and_energies_json(hoomd, golden_dir):
     with open(os.path.join(golden_dir, "ref_vectors.json")) as f:
         fe = json.load(f)["forces_and_energies"]
     for name, cls_name, keys in (("LJ", "LJ", ("epsilon", "sigma")),
-                                 ("DPDConservative", "DPDConservative", ("A",))):
+                                 ("DPDConservative", "DPDConservative", ("A",)),
+                                 ("Gaussian", "Gaussian", ("epsilon", "sigma")),
+                                 ("Yukawa", "Yukawa", ("epsilon", "kappa")),
+                                 ("LJ1208", "LJ1208", ("epsilon", "sigma")),
+                                 ("LJ0804", "LJ0804", ("epsilon", "sigma")),
+                                 ("ForceShiftedLJ", "ForceShiftedLJ", ("epsilon", "sigma")),
+                                 ("Mie", "Mie", ("epsilon", "sigma", "n", "m")),
+                                 ("Morse", "Morse", ("D0", "alpha", "r0"))):
         tab = fe[name]
         for p, F, E in zip(tab["params"], tab["forces"], tab["energies"]):
             for d, f_ref, e_ref in zip((0.75, 1.5), F, E):
@@ -412,3 +419,66 @@ def test_snapshot_roundtrip_pageable_and_pinned(hoomd):
     assert np.array_equal(out.particles.position, pos)
     assert np.array_equal(out.particles.typeid, tid)
     assert np.array_equal(out.particles.image, img)
+
+
+@pytest.mark.parametrize("cls_name,params", [
+    ("Gaussian", dict(epsilon=1.5, sigma=0.7)), ("Yukawa", dict(epsilon=2.0, kappa=2.5)),
+    ("LJ1208", dict(epsilon=1.0, sigma=1.0)), ("LJ0804", dict(epsilon=1.0, sigma=1.0)),
+    ("ForceShiftedLJ", dict(epsilon=1.0, sigma=1.0)), ("Mie", dict(epsilon=1.0, sigma=1.0, n=14, m=7)),
+    ("Morse", dict(D0=1.2, alpha=3.5, r0=1.1)), ("LJ", dict(epsilon=1.0, sigma=1.0))])
+def test_evaluator_family_consistency(hoomd, cls_name, params):
+    """Every evaluator through the kernel template on a liquid: F = -dE/dr (central differences of the
+    total energy along the force of a few particles), Newton's third law (sum of forces = 0), and
+    mode='shift' changing energies by exactly the pair count inside r_cut times V(r_cut)
+    (hoomd/md/pytest/test_potential.py:901-949 checks the first on two particles). r_cut = 3 keeps the
+    force jump at the cut-off (a kink in E that central differences would smear) negligible."""
+    pos, vel, L = random_liquid(12, 0.7, seed=8, jitter=0.2)
+    N = len(pos)
+    fx = dict(L=L, pos=pos, vel=vel)
+
+    def build(p, mode):
+        sim = make_sim(hoomd, fx["L"], p, fx["vel"])
+        cell = hoomd.md.nlist.Cell(buffer=0.3)
+        pot = getattr(hoomd.md.pair, cls_name)(nlist=cell, default_r_cut=3.0, mode=mode)
+        pot.params[("A", "A")] = params
+        cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.001, methods=[cv], forces=[pot])
+        sim.run(0)
+        return sim, cell, pot
+
+    sim, cell, pot = build(pos, "none")
+    f = pot.forces
+    e0 = pot.energy
+    assert np.abs(f.sum(axis=0)).max() <= 1e-6 * np.abs(f).sum()
+    # energy shift: V(r_cut) per pair inside the cut-off
+    pl = cell.pair_list
+    d = pos[pl[:, 0]].astype(np.float64) - pos[pl[:, 1]].astype(np.float64)
+    d -= float(L[0]) * np.rint(d / float(L[0]))
+    n_in = int((np.einsum("ij,ij->i", d, d) < 9.0).sum())
+    sim_s, cell_s, pot_s = build(pos, "shift")
+    assert np.allclose(pot_s.forces, f, rtol=1e-6, atol=1e-6)
+    two = np.array([[0, 0, 0], [0, 0, np.float32(3.0) - np.float32(1e-4)]], dtype=np.float32)
+    sim2 = make_sim(hoomd, [20.0, 20.0, 20.0], two, np.zeros_like(two))
+    c2 = hoomd.md.nlist.Cell(buffer=0.3)
+    p2 = getattr(hoomd.md.pair, cls_name)(nlist=c2, default_r_cut=3.0)
+    p2.params[("A", "A")] = params
+    sim2.operations.integrator = hoomd.md.Integrator(
+        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[p2])
+    sim2.run(0)
+    v_cut = p2.energy  # V just inside r_cut
+    if cls_name != "ForceShiftedLJ":
+        assert abs((e0 - pot_s.energy) - n_in * v_cut) <= 2e-3 * max(abs(n_in * v_cut), 1e-3) + 1e-4 * abs(e0)
+    # F = -dE/dx by central differences on three particles (fp32 energies: generous tolerance)
+    h = np.float32(2.0 ** -7)
+    scale = np.sqrt(np.mean(f ** 2))
+    for i in (0, N // 2, N - 1):
+        for c in range(3):
+            pp, pm = pos.copy(), pos.copy()
+            pp[i, c] += h
+            pm[i, c] -= h
+            # per-particle energies differenced in fp64: the unchanged particles cancel exactly, so the
+            # total's fp32 rounding (1e-7 of a large sum) does not swamp the derivative
+            ep = build(pp, "shift")[2].energies
+            em = build(pm, "shift")[2].energies
+            step = float(pp[i, c]) - float(pm[i, c])
+            assert abs(-(ep - em).sum() / step - f[i, c]) <= 2e-2 * max(abs(f[i, c]), scale)
