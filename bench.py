@@ -353,7 +353,7 @@ def run_ours(args):
         # host memory), so both directions are plain DMA
         snap = sim.state.get_snapshot(into=hoomd.Snapshot(pinned=True))
     else:
-        loc = sim.state._get_local()
+        loc = sim.state._get_local(pinned=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(calls):
@@ -365,7 +365,7 @@ def run_ours(args):
             tag_, pos_, vel_, mass_, tid_, img_ = loc
             sim.state._set_tagged(N, tag_, pos_, vel_, tid_, mass_, img_)
             sim.run(S)
-            loc = sim.state._get_local()
+            loc = sim.state._get_local(pinned=True, into=loc)
         e = lj.energy
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -394,7 +394,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h / S, "steps_per_call": S, "calls": calls,
                     "what": ("state.set_snapshot(pinned host snapshot) + sim.run(S) + state.get_snapshot() + energy"
                              if world == 1 else
-                             "per rank: state._set_tagged(host arrays) + sim.run(S) + "
+                             "per rank: state._set_tagged(pinned host arrays) + sim.run(S) + "
                              "state._get_local() + energy (collective)")},
             "gpu_launches": launches,
             # dominant kernel: pair_force_kernel. Algorithmic bytes per launch = (4 nbar + 44) N_local

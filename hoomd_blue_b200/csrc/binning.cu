@@ -163,45 +163,60 @@ __global__ void __launch_bounds__(256)
     }
 
 // Snapshot <-> device layout on the device (the host only moves the caller's raw arrays):
-// pack: (pos3, vel3, mass, typeid, image3) in tag order -> pos4 / vel4 / image / tag = index.
+// pack: (pos3, vel3, mass, typeid, image3[, tag]) -> pos4 / vel4 / image / tag (= index when no tags are
+// given). With a domain decomposition (geom.n > 1 somewhere) every particle is also checked for
+// ownership with domain_g, the same function the host filter and the migration use.
 __global__ void __launch_bounds__(256)
     snapshot_pack_kernel(uint32_t N, const float* __restrict__ pos3, const float* __restrict__ vel3,
                          const float* __restrict__ mass, const uint32_t* __restrict__ typeid_,
-                         const int* __restrict__ image3, float4* __restrict__ pos,
-                         float4* __restrict__ vel, int* __restrict__ image,
+                         const int* __restrict__ image3, const uint32_t* __restrict__ tag_in,
+                         float4* __restrict__ pos, float4* __restrict__ vel, int* __restrict__ image,
                          uint32_t* __restrict__ tag, uint32_t* __restrict__ rtag, uint32_t ntypes,
-                         uint32_t* __restrict__ bad_type)
+                         BoxD box, DomainGeom geom, uint32_t* __restrict__ flags)
     {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N)
         return;
     const uint32_t t = typeid_ ? typeid_[i] : 0u;
     if (t >= ntypes)
-        atomicMax(bad_type, i + 1);
-    pos[i] = make_float4(pos3[3 * (size_t)i], pos3[3 * (size_t)i + 1], pos3[3 * (size_t)i + 2],
-                         __uint_as_float(t));
+        atomicMax(&flags[0], i + 1);
+    const float3 p = make_float3(pos3[3 * (size_t)i], pos3[3 * (size_t)i + 1], pos3[3 * (size_t)i + 2]);
+    const float pc[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        if (geom.n[d] > 1)
+            {
+            // plain fp64 arithmetic in the host filter's order (no contraction: separate roundings)
+            const double f = __dmul_rn(__dadd_rn((double)pc[d], -box.lo[d]), box.Linv[d]);
+            const double g = domain_g(f, geom.n[d], geom.coord[d]);
+            if (!(g >= 0.0 && g < 1.0))
+                atomicMax(&flags[1], i + 1);
+            }
+    pos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(t));
     vel[i] = make_float4(vel3 ? vel3[3 * (size_t)i] : 0.f, vel3 ? vel3[3 * (size_t)i + 1] : 0.f,
                          vel3 ? vel3[3 * (size_t)i + 2] : 0.f, mass ? mass[i] : 1.0f);
     image[3 * (size_t)i] = image3 ? image3[3 * (size_t)i] : 0;
     image[3 * (size_t)i + 1] = image3 ? image3[3 * (size_t)i + 1] : 0;
     image[3 * (size_t)i + 2] = image3 ? image3[3 * (size_t)i + 2] : 0;
-    tag[i] = i;
+    const uint32_t tg = tag_in ? tag_in[i] : i;
+    tag[i] = tg;
     if (rtag)
-        rtag[i] = i;
+        rtag[tg] = i;
     }
 
-// unpack: particle k (cell order) -> row tag[k] of the tag-ordered raw arrays
+// unpack: particle k (cell order) -> row tag[k] of the tag-ordered raw arrays (by_tag), or row k with
+// the tags written alongside (local order, domain-decomposed systems)
 __global__ void __launch_bounds__(256)
     snapshot_unpack_kernel(uint32_t N, const float4* __restrict__ pos, const float4* __restrict__ vel,
                            const int* __restrict__ image, const uint32_t* __restrict__ tag,
                            float* __restrict__ pos3, float* __restrict__ vel3,
                            float* __restrict__ mass, uint32_t* __restrict__ typeid_,
-                           int* __restrict__ image3)
+                           int* __restrict__ image3, uint32_t* __restrict__ tag_out, bool by_tag)
     {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N)
         return;
-    const size_t t = tag[k];
+    const size_t t = by_tag ? tag[k] : k;
     const float4 p = pos[k], v = vel[k];
     pos3[3 * t] = p.x;
     pos3[3 * t + 1] = p.y;
@@ -214,29 +229,34 @@ __global__ void __launch_bounds__(256)
     image3[3 * t] = image[3 * (size_t)k];
     image3[3 * t + 1] = image[3 * (size_t)k + 1];
     image3[3 * t + 2] = image[3 * (size_t)k + 2];
+    if (tag_out)
+        tag_out[t] = tag[k];
     }
 
 hb2_status snapshot_pack(uint32_t N, const float* pos3, const float* vel3, const float* mass,
-                         const uint32_t* typeid_, const int* image3, float4* pos, float4* vel,
-                         int* image, uint32_t* tag, uint32_t* rtag, uint32_t ntypes,
-                         uint32_t* bad_type, cudaStream_t stream)
+                         const uint32_t* typeid_, const int* image3, const uint32_t* tag_in,
+                         float4* pos, float4* vel, int* image, uint32_t* tag, uint32_t* rtag,
+                         uint32_t ntypes, const hb2_box& box, const DomainGeom& geom, uint32_t* flags,
+                         cudaStream_t stream)
     {
     if (N == 0)
         return HB2_OK;
-    snapshot_pack_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, pos3, vel3, mass, typeid_, image3, pos,
-                                                              vel, image, tag, rtag, ntypes, bad_type);
+    snapshot_pack_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, pos3, vel3, mass, typeid_, image3,
+                                                              tag_in, pos, vel, image, tag, rtag,
+                                                              ntypes, boxd(box), geom, flags);
     HB2_CHECK_LAUNCH("snapshot_pack_kernel");
     return HB2_OK;
     }
 
 hb2_status snapshot_unpack(uint32_t N, const float4* pos, const float4* vel, const int* image,
                            const uint32_t* tag, float* pos3, float* vel3, float* mass,
-                           uint32_t* typeid_, int* image3, cudaStream_t stream)
+                           uint32_t* typeid_, int* image3, uint32_t* tag_out, bool by_tag,
+                           cudaStream_t stream)
     {
     if (N == 0)
         return HB2_OK;
     snapshot_unpack_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, pos, vel, image, tag, pos3, vel3,
-                                                                mass, typeid_, image3);
+                                                                mass, typeid_, image3, tag_out, by_tag);
     HB2_CHECK_LAUNCH("snapshot_unpack_kernel");
     return HB2_OK;
     }

@@ -312,7 +312,7 @@ static hb2_status system_set(hb2_system* s, uint32_t n_in, uint64_t N_global, co
 
 static hb2_status system_stage(hb2_system* s, uint32_t N)
     {
-    const size_t words = 11 * (size_t)N;
+    const size_t words = 12 * (size_t)N; // pos3 vel3 mass typeid image3 tag
     if (words <= s->stage_cap)
         return HB2_OK;
     dev_free(s->d_stage);
@@ -325,47 +325,35 @@ static hb2_status system_stage(hb2_system* s, uint32_t N)
     return HB2_OK;
     }
 
-extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const float* pos3,
-                                               const float* vel3, const float* mass,
-                                               const uint32_t* typeid_, const int32_t* image3)
+static bool host_pinned(const void* p)
     {
-    if (!s || !pos3)
+    if (!p)
+        return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
         {
-        set_error("hb2_system_set_particles: positions are required");
-        return HB2_ERR_INVALID;
+        cudaGetLastError();
+        return false;
         }
-    if (s->dom.active)
-        return system_set(s, N, N, nullptr, pos3, vel3, mass, typeid_, image3);
-    // Single GPU: the raw arrays cross PCIe once from a pinned bounce buffer and are packed into the
-    // float4 layout on the device.
-    if (!s->has_box)
-        {
-        set_error("hb2_system_set_particles: set the box first");
-        return HB2_ERR_INVALID;
-        }
-    HB2_CUDA(cudaSetDevice(s->device));
-    if (N + 1 > s->cap || !s->pos[0])
-        HB2_TRY(system_allocate(s, N + 1, true, N));
+    return at.type == cudaMemoryTypeHost;
+    }
+
+// Device path of set_particles[_tagged]: the caller's raw arrays cross PCIe once — by direct DMA when
+// they are page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors), through the
+// pinned bounce buffer otherwise — and are packed into the float4 layout on the device. With a domain
+// decomposition every particle must be owned by this rank (checked on the device with domain_g);
+// `*not_owned` reports when that is not so and the caller falls back to the host filter.
+static hb2_status system_set_device(hb2_system* s, uint32_t N, uint64_t N_global, const uint32_t* tag,
+                                    const float* pos3, const float* vel3, const float* mass,
+                                    const uint32_t* typeid_, const int32_t* image3, bool* not_owned)
+    {
     HB2_TRY(system_stage(s, N));
     cudaStream_t st = s->stream;
     const size_t n = N;
     float* h = s->h_stage;
     float* d = s->d_stage;
-    // Page-locked caller arrays (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are
-    // DMA'd straight into the staging area; pageable ones go through the pinned bounce buffer.
-    auto pinned = [](const void* p)
-    {
-        if (!p)
-            return true;
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
-            {
-            cudaGetLastError();
-            return false;
-            }
-        return at.type == cudaMemoryTypeHost;
-    };
-    const bool direct = pinned(pos3) && pinned(vel3) && pinned(mass) && pinned(typeid_) && pinned(image3);
+    const bool direct = host_pinned(pos3) && host_pinned(vel3) && host_pinned(mass)
+                        && host_pinned(typeid_) && host_pinned(image3) && host_pinned(tag);
     auto put = [&](size_t off_words, const void* src, size_t bytes, int fill) -> hb2_status
     {
         if (src && direct)
@@ -388,25 +376,39 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
     HB2_TRY(put(6 * n, mass, 4 * n, 1));
     HB2_TRY(put(7 * n, typeid_, 4 * n, 0));
     HB2_TRY(put(8 * n, image3, 12 * n, 0));
+    if (tag)
+        HB2_TRY(put(11 * n, tag, 4 * n, 0));
     if (!direct)
-        HB2_CUDA(cudaMemcpyAsync(d, h, 44 * n, cudaMemcpyHostToDevice, st));
-    HB2_CUDA(cudaMemsetAsync(s->d_ticket + 3, 0, sizeof(uint32_t), st));
-    s->N = N;
-    s->Ng = 0;
-    s->cur = 0;
-    s->dom.N_global = N;
+        HB2_CUDA(cudaMemcpyAsync(d, h, (tag ? 48 : 44) * n, cudaMemcpyHostToDevice, st));
+    HB2_CUDA(cudaMemsetAsync(s->d_ticket + 2, 0, 2 * sizeof(uint32_t), st));
+    DomainGeom geom;
+    for (int k = 0; k < 3; k++)
+        {
+        geom.n[k] = s->dom.active ? s->dom.grid[k] : 1u;
+        geom.coord[k] = s->dom.active ? s->dom.coord[k] : 0u;
+        geom.dimi[k] = geom.dimt[k] = 1;
+        }
     HB2_TRY(snapshot_pack(N, d, d + 3 * n, d + 6 * n, (const uint32_t*)(d + 7 * n),
-                          (const int*)(d + 8 * n), s->pos[0], s->vel[0], s->image[0], s->tag[0],
-                          s->rtag, s->ntypes, s->d_ticket + 3, st));
-    uint32_t bad = 0;
-    HB2_CUDA(cudaMemcpyAsync(&bad, s->d_ticket + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                          (const int*)(d + 8 * n), tag ? (const uint32_t*)(d + 11 * n) : nullptr,
+                          s->pos[0], s->vel[0], s->image[0], s->tag[0], s->rtag, s->ntypes, s->box, geom,
+                          s->d_ticket + 2, st));
+    uint32_t flags[2] = {0, 0};
+    HB2_CUDA(cudaMemcpyAsync(flags, s->d_ticket + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaMemsetAsync(s->d_ticket + 2, 0, 2 * sizeof(uint32_t), st)); // tickets rest at zero
     HB2_CUDA(cudaStreamSynchronize(st));
-    if (bad)
+    if (flags[0])
         {
         s->N = 0;
         set_error("hb2_system_set_particles: type id out of range");
         return HB2_ERR_INVALID;
         }
+    *not_owned = flags[1] != 0;
+    if (*not_owned)
+        return HB2_OK;
+    s->N = N;
+    s->Ng = 0;
+    s->cur = 0;
+    s->dom.N_global = N_global;
     HB2_TRY(system_place_dummy(s));
     s->order_epoch++;
     for (auto* nl : s->nlists)
@@ -419,6 +421,29 @@ extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const 
     return HB2_OK;
     }
 
+extern "C" hb2_status hb2_system_set_particles(hb2_system* s, uint32_t N, const float* pos3,
+                                               const float* vel3, const float* mass,
+                                               const uint32_t* typeid_, const int32_t* image3)
+    {
+    if (!s || !pos3)
+        {
+        set_error("hb2_system_set_particles: positions are required");
+        return HB2_ERR_INVALID;
+        }
+    if (s->dom.active)
+        return system_set(s, N, N, nullptr, pos3, vel3, mass, typeid_, image3);
+    if (!s->has_box)
+        {
+        set_error("hb2_system_set_particles: set the box first");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    if (N + 1 > s->cap || !s->pos[0])
+        HB2_TRY(system_allocate(s, N + 1, true, N));
+    bool not_owned = false;
+    return system_set_device(s, N, N, nullptr, pos3, vel3, mass, typeid_, image3, &not_owned);
+    }
+
 extern "C" hb2_status hb2_system_set_particles_tagged(hb2_system* s, uint32_t n, uint64_t N_global,
                                                       const uint32_t* tag, const float* pos3,
                                                       const float* vel3, const float* mass,
@@ -428,6 +453,17 @@ extern "C" hb2_status hb2_system_set_particles_tagged(hb2_system* s, uint32_t n,
         {
         set_error("hb2_system_set_particles_tagged: tags are required and must fit 32 bits");
         return HB2_ERR_INVALID;
+        }
+    if (s && pos3 && s->has_box && s->dom.active && s->pos[0] && (uint64_t)n + 1 <= s->cap
+        && N_global == s->dom.N_global)
+        {
+        // a rank handing back (only) its own particles, e.g. after hb2_system_get_local: no host
+        // filtering, the ownership check runs on the device
+        HB2_CUDA(cudaSetDevice(s->device));
+        bool not_owned = false;
+        HB2_TRY(system_set_device(s, n, N_global, tag, pos3, vel3, mass, typeid_, image3, &not_owned));
+        if (!not_owned)
+            return HB2_OK;
         }
     return system_set(s, n, N_global, tag, pos3, vel3, mass, typeid_, image3);
     }
@@ -455,37 +491,43 @@ extern "C" hb2_status hb2_system_get_local(hb2_system* s, uint32_t* tag, float* 
         return HB2_ERR_INVALID;
     HB2_CUDA(cudaSetDevice(s->device));
     const uint32_t N = s->N;
-    std::vector<float4> hp(N), hv(N);
-    std::vector<int> hi(3 * (size_t)N);
+    if (N == 0)
+        return HB2_OK;
+    HB2_TRY(system_stage(s, N));
+    const size_t n = N;
     const int c = s->cur;
     cudaStream_t st = s->stream;
-    HB2_CUDA(cudaMemcpyAsync(hp.data(), s->pos[c], sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
-    HB2_CUDA(cudaMemcpyAsync(hv.data(), s->vel[c], sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
-    HB2_CUDA(cudaMemcpyAsync(hi.data(), s->image[c], sizeof(int) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
-    if (tag)
-        HB2_CUDA(cudaMemcpyAsync(tag, s->tag[c], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
-    HB2_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t k = 0; k < N; k++)
+    float* d = s->d_stage;
+    float* h = s->h_stage;
+    // local (cell) order; the layout conversion runs on the device, one copy brings the arrays back
+    HB2_TRY(snapshot_unpack(N, s->pos[c], s->vel[c], s->image[c], s->tag[c], d, d + 3 * n, d + 6 * n,
+                            (uint32_t*)(d + 7 * n), (int*)(d + 8 * n), (uint32_t*)(d + 11 * n), false,
+                            st));
+    const bool direct = host_pinned(pos3) && host_pinned(vel3) && host_pinned(mass)
+                        && host_pinned(typeid_) && host_pinned(image3) && host_pinned(tag);
+    if (!direct)
         {
-        if (pos3)
-            {
-            pos3[3 * (size_t)k] = hp[k].x;
-            pos3[3 * (size_t)k + 1] = hp[k].y;
-            pos3[3 * (size_t)k + 2] = hp[k].z;
-            }
-        if (typeid_)
-            memcpy(&typeid_[k], &hp[k].w, 4);
-        if (vel3)
-            {
-            vel3[3 * (size_t)k] = hv[k].x;
-            vel3[3 * (size_t)k + 1] = hv[k].y;
-            vel3[3 * (size_t)k + 2] = hv[k].z;
-            }
-        if (mass)
-            mass[k] = hv[k].w;
-        if (image3)
-            memcpy(&image3[3 * (size_t)k], &hi[3 * (size_t)k], 3 * sizeof(int));
+        HB2_CUDA(cudaMemcpyAsync(h, d, 48 * n, cudaMemcpyDeviceToHost, st));
+        HB2_CUDA(cudaStreamSynchronize(st));
         }
+    auto get = [&](void* dst, size_t off_words, size_t bytes) -> hb2_status
+    {
+        if (!dst)
+            return HB2_OK;
+        if (direct)
+            HB2_CUDA(cudaMemcpyAsync(dst, d + off_words, bytes, cudaMemcpyDeviceToHost, st));
+        else
+            memcpy(dst, h + off_words, bytes);
+        return HB2_OK;
+    };
+    HB2_TRY(get(pos3, 0, 12 * n));
+    HB2_TRY(get(vel3, 3 * n, 12 * n));
+    HB2_TRY(get(mass, 6 * n, 4 * n));
+    HB2_TRY(get(typeid_, 7 * n, 4 * n));
+    HB2_TRY(get(image3, 8 * n, 12 * n));
+    HB2_TRY(get(tag, 11 * n, 4 * n));
+    if (direct)
+        HB2_CUDA(cudaStreamSynchronize(st));
     return HB2_OK;
     }
 
@@ -521,20 +563,9 @@ extern "C" hb2_status hb2_system_get_particles(hb2_system* s, float* pos3, float
     float* h = s->h_stage;
     // tag order is restored on the device; one pinned D2H copy brings all five arrays back
     HB2_TRY(snapshot_unpack(N, s->pos[c], s->vel[c], s->image[c], s->tag[c], d, d + 3 * n, d + 6 * n,
-                            (uint32_t*)(d + 7 * n), (int*)(d + 8 * n), st));
-    auto pinned = [](const void* p)
-    {
-        if (!p)
-            return true;
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
-            {
-            cudaGetLastError();
-            return false;
-            }
-        return at.type == cudaMemoryTypeHost;
-    };
-    if (pinned(pos3) && pinned(vel3) && pinned(mass) && pinned(typeid_) && pinned(image3))
+                            (uint32_t*)(d + 7 * n), (int*)(d + 8 * n), nullptr, true, st));
+    if (host_pinned(pos3) && host_pinned(vel3) && host_pinned(mass) && host_pinned(typeid_)
+        && host_pinned(image3))
         {
         // page-locked destinations: DMA straight into the caller's arrays
         if (pos3)

@@ -104,6 +104,21 @@ class _BoxView:
         return self.Lx * self.Ly * self.Lz
 
 
+class LocalParticles:
+    """One rank's particles in local order: capacity-sized arrays, the first n rows are valid."""
+
+    def __init__(self, capacity, pinned=False):
+        alloc = _Particles(pinned)._zeros
+        self.capacity = int(capacity)
+        self.n = 0
+        self._full = (alloc((capacity,), np.uint32), alloc((capacity, 3), np.float32),
+                      alloc((capacity, 3), np.float32), alloc((capacity,), np.float32),
+                      alloc((capacity,), np.uint32), alloc((capacity, 3), np.int32))
+
+    def __iter__(self):  # tag, position, velocity, mass, typeid, image
+        return iter(a[:self.n] for a in self._full)
+
+
 class State:
     """Particle state resident in HBM (hb2_system). With more than one rank in the process group the
     box is split into a 3D grid of domains (hoomd/state.py domain_decomposition,
@@ -185,19 +200,24 @@ class State:
                                          ptr(vel, C.c_float), ptr(mass, C.c_float),
                                          ptr(tid, C.c_uint32), ptr(img, C.c_int32)))
 
-    def _get_local(self):
+    def _get_local(self, pinned=False, into=None):
+        """LocalParticles (tag, position, velocity, mass, typeid, image — also unpackable as that
+        tuple) of the particles this rank owns, in local order. pinned=True allocates the arrays
+        page-locked (direct DMA in both directions); `into` is a previous result whose storage is
+        reused when large enough (page-locked allocations are expensive, and the owned count drifts
+        with migration)."""
         L = _lib.lib()
         n = int(L.hb2_system_n(self._h))
-        tag = np.zeros(n, dtype=np.uint32)
-        pos = np.zeros((n, 3), dtype=np.float32)
-        vel = np.zeros((n, 3), dtype=np.float32)
-        mass = np.zeros(n, dtype=np.float32)
-        tid = np.zeros(n, dtype=np.uint32)
-        img = np.zeros((n, 3), dtype=np.int32)
+        if into is not None and into.capacity >= n:
+            out = into
+        else:
+            out = LocalParticles(n + n // 16 + 1024, pinned)
+        out.n = n
+        tag, pos, vel, mass, tid, img = out
         check(L.hb2_system_get_local(self._h, ptr(tag, C.c_uint32), ptr(pos, C.c_float),
                                      ptr(vel, C.c_float), ptr(mass, C.c_float), ptr(tid, C.c_uint32),
                                      ptr(img, C.c_int32)))
-        return tag, pos, vel, mass, tid, img
+        return out
 
     def get_snapshot(self, into=None):
         """hoomd.State.get_snapshot. `into` (not in the reference) reuses an existing snapshot's
