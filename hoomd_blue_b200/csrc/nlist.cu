@@ -571,7 +571,6 @@ __global__ void __launch_bounds__(NL_WARPS * 32, NL_MIN_BLOCKS)
 constexpr int NR_WARPS = 2;
 constexpr int NR_CAP = 704; // staged candidates per round (multiple of 8)
 constexpr uint32_t NR_MAX_PITCH = 256;
-constexpr double NR_MIN_FILL = 12.0; // mean particles per cell from which the row kernel is used
 constexpr uint32_t NR_SLACK = 16;    // row entries beyond the pitch: one sweep trip appends <= 16
 
 HB2_HOSTDEVICE uint32_t nr_row_stride_words(uint32_t pitch)
@@ -1029,18 +1028,13 @@ hb2_status launch_nlist_build(const NlistBuildArgs& a, const hb2_box& box, cudaS
     bool small = false;
     for (int d = 0; d < 3; d++)
         small = small || (a.geom.n[d] == 1 && a.geom.dimt[d] < 3);
-    // Kernel choice: the row-per-lane build needs one type, full rings and rows that fit in shared
-    // memory; it pays off when a home cell fills a good part of a warp's 32 lanes.
-    // HB2_NLIST_KERNEL=mask|rows overrides the occupancy heuristic (kernel A/B measurements).
-    static const char* force = getenv("HB2_NLIST_KERNEL");
-    const uint32_t Nc = a.geom.dimt[0] * a.geom.dimt[1] * a.geom.dimt[2];
+    // Kernel choice: the row-per-lane build (HB2_NLIST_KERNEL=rows) needs one type, full rings and
+    // rows that fit in shared memory.
     const bool rows_ok = a.ntypes == 1 && !small && a.pitch <= NR_MAX_PITCH && a.r_listsq_single > 0.0;
-    bool rows = rows_ok && (double)a.N >= NR_MIN_FILL * (double)Nc;
-    if (force && force[0] == 'm')
-        rows = false;
-    if (force && force[0] == 'r')
-        rows = rows_ok;
-    if (rows)
+    // The row-per-lane kernel is opt-in: at C2 it runs level with the mask kernel (0.84 vs 0.88 ms under
+    // ncu, 0.98 vs 0.94 ms per rebuild in the step loop).
+    const char* pick = getenv("HB2_NLIST_KERNEL");
+    if (pick && pick[0] == 'r' && rows_ok)
         return launch_rows(a, cst, stream);
     if (a.ntypes > 1)
         return small ? launch_variant<true, true>(a, cst, stream)
