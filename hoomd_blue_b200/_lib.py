@@ -117,6 +117,7 @@ def _declare(L):
     L.hb2_integrator_destroy.restype = None
     L.hb2_integrator_add_force.argtypes = [_vp, _vp]
     L.hb2_integrator_set_constant_volume.argtypes = [_vp, C.c_int, C.c_double, C.c_double]
+    L.hb2_integrator_set_langevin.argtypes = [_vp, C.c_double, _f64p, C.c_uint32]
     L.hb2_integrator_run.argtypes = [_vp, C.c_uint64]
     L.hb2_integrator_thermo.argtypes = [_vp, _f64p, _f64p, _f64p]
     L.hb2_integrator_last_run_ms.argtypes = [_vp, _f32p]

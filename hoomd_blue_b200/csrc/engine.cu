@@ -1693,6 +1693,8 @@ extern "C" void hb2_integrator_destroy(hb2_integrator* it)
     cudaEventDestroy(it->ev1);
     for (auto e : it->pool)
         cudaEventDestroy(e);
+    dev_free(it->d_gamma_coeff);
+    dev_free(it->d_total);
     delete it;
     }
 
@@ -1719,6 +1721,37 @@ extern "C" hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int
     it->thermostat = thermostat;
     it->kT = kT;
     it->tau = tau;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT, const double* gamma,
+                                                  uint32_t ntypes)
+    {
+    if (!it || !gamma || ntypes != it->sys->ntypes || !(it->dt > 0.0) || kT < 0.0)
+        {
+        set_error("hb2_integrator_set_langevin: one gamma per particle type, dt > 0 and kT >= 0 are required");
+        return HB2_ERR_INVALID;
+        }
+    std::vector<float> gc(2 * (size_t)ntypes);
+    for (uint32_t t = 0; t < ntypes; t++)
+        {
+        if (gamma[t] < 0.0)
+            {
+            set_error("hb2_integrator_set_langevin: gamma must be >= 0");
+            return HB2_ERR_INVALID;
+            }
+        gc[2 * t] = (float)gamma[t];
+        gc[2 * t + 1] = (float)std::sqrt(6.0 * gamma[t] * kT / it->dt); // hoomd/md/TwoStepLangevin.cc:269
+        }
+    HB2_CUDA(cudaSetDevice(it->sys->device));
+    if (!it->d_gamma_coeff)
+        HB2_TRY(dev_alloc(&it->d_gamma_coeff, gc.size()));
+    HB2_CUDA(cudaMemcpyAsync(it->d_gamma_coeff, gc.data(), sizeof(float) * gc.size(), cudaMemcpyHostToDevice,
+                             it->sys->stream));
+    HB2_CUDA(cudaStreamSynchronize(it->sys->stream));
+    it->thermostat = 2;
+    it->kT = kT;
+    it->tau = 0.0;
     return HB2_OK;
     }
 
@@ -1752,6 +1785,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         {
         HB2_TRY(pf->compute(s->timestep));
         it->prepared = true;
+        it->total_valid = false; // accelerations restart from the net force (computeAccelerations)
         }
     if (it->thermostat == 1)
         {
@@ -1786,7 +1820,9 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             rescale = d_rescale;
             }
         const bool check = nl->has_list && nl->check_dist;
-        HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], pf->d_force, s->image[s->cur], s->N,
+        // (Langevin: the previous step two left F + F_bd for this half step)
+        const float4* f_one = (it->thermostat == 2 && it->total_valid) ? it->d_total : pf->d_force;
+        HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], f_one, s->image[s->cur], s->N,
                                 s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
                                 nl->maxshift(), nl->d_conditions + 3, st));
         bool flag = false;
@@ -1859,8 +1895,23 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             bn.timestep = t + 1;
             bn.seed = s->seed;
             }
-        HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
-                                s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn));
+        if (it->thermostat == 2)
+            {
+            if (s->N > it->total_cap)
+                {
+                dev_free(it->d_total);
+                it->d_total = nullptr;
+                HB2_TRY(dev_alloc(&it->d_total, (size_t)s->cap));
+                it->total_cap = s->cap;
+                }
+            HB2_TRY(launch_step_two_langevin(s->vel[s->cur], pf->d_force, it->d_total, s->pos[s->cur],
+                                             s->tag[s->cur], s->N, (float)it->dt, it->d_gamma_coeff,
+                                             s->seed, t, st));
+            it->total_valid = true;
+            }
+        else
+            HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
+                                    s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn));
         if (it->thermostat == 1 && s->dom.active)
             HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
         if (it->profiling)

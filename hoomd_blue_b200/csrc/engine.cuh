@@ -181,8 +181,12 @@ struct hb2_integrator
     hb2_system* sys = nullptr;
     double dt = 0.005;
     std::vector<hb2_pair*> forces;
-    int thermostat = 0;
+    int thermostat = 0; // 0 NVE, 1 ConstantVolume + Bussi, 2 Langevin method
     double kT = 1.0, tau = 0.0;
+    float* d_gamma_coeff = nullptr; // Langevin: (gamma, sqrt(6 gamma kT / dt)) per type
+    float4* d_total = nullptr;      // Langevin: F + F_bd of the last step two (next step one's force)
+    size_t total_cap = 0;
+    bool total_valid = false;
     bool prepared = false;
     uint64_t prepared_epoch = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

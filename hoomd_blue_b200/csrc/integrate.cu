@@ -196,6 +196,55 @@ __global__ void __launch_bounds__(INT_BLOCK)
         }
     }
 
+// TwoStepLangevin::integrateStepTwo (hoomd/md/TwoStepLangevin.cc:213-292, translational, 3D):
+// a = (F + r sqrt(6 gamma kT / dt) - gamma v) / m with r uniform in [-1, 1] from
+// RandomGenerator(Seed(TwoStepLangevin, timestep, seed), Counter(tag)); v += 1/2 dt a. The three
+// draws are three Philox calls keyed by the particle's TAG, so the noise does not depend on the
+// memory order or the domain decomposition. gc[2 t] = gamma, gc[2 t + 1] = sqrt(6 gamma kT / dt).
+// The acceleration the reference stores for the next step one includes the BD force
+// (TwoStepLangevin.cc:281-284); here step one derives it from a force array, so the total force
+// F + F_bd is written to `total` for it.
+__global__ void __launch_bounds__(INT_BLOCK)
+    step_two_langevin_kernel(float4* __restrict__ vel, const float4* __restrict__ force,
+                             float4* __restrict__ total, const float4* __restrict__ pos,
+                             const uint32_t* __restrict__ tag, uint32_t N, float dt,
+                             const float* __restrict__ gc, uint32_t seed, uint64_t timestep)
+    {
+    const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
+    if (i >= N)
+        return;
+    float4 v = vel[i];
+    const float4 f = force[i];
+    const uint32_t t = __float_as_uint(pos[i].w);
+    const float gamma = gc[2 * t], coeff = gc[2 * t + 1];
+    Rng g(RNG_ID_LANGEVIN, timestep, (uint16_t)seed, tag[i]);
+    const float rx = (float)(-1.0 + 2.0 * rng_canonical(g));
+    const float ry = (float)(-1.0 + 2.0 * rng_canonical(g));
+    const float rz = (float)(-1.0 + 2.0 * rng_canonical(g));
+    const float minv = 1.0f / v.w;
+    const float hdt = 0.5f * dt;
+    const float tx = f.x + (rx * coeff - gamma * v.x);
+    const float ty = f.y + (ry * coeff - gamma * v.y);
+    const float tz = f.z + (rz * coeff - gamma * v.z);
+    v.x += hdt * (tx * minv);
+    v.y += hdt * (ty * minv);
+    v.z += hdt * (tz * minv);
+    vel[i] = v;
+    total[i] = make_float4(tx, ty, tz, f.w);
+    }
+
+hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,
+                                    const uint32_t* tag, uint32_t N, float dt, const float* d_gamma_coeff,
+                                    uint32_t seed, uint64_t timestep, cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    step_two_langevin_kernel<<<(N + INT_BLOCK - 1) / INT_BLOCK, INT_BLOCK, 0, stream>>>(
+        vel, force, total, pos, tag, N, dt, d_gamma_coeff, seed, timestep);
+    HB2_CHECK_LAUNCH("step_two_langevin_kernel");
+    return HB2_OK;
+    }
+
 // KE of the current velocities only (prepRun / thermo queries)
 __global__ void __launch_bounds__(INT_BLOCK)
     kinetic_kernel(const float4* __restrict__ vel, uint32_t N, double* __restrict__ partial,

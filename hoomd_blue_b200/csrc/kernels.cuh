@@ -108,6 +108,11 @@ uint32_t step_two_blocks(uint32_t N);
 hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
                            const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
                            double* d_ke_out, cudaStream_t stream, const BussiNext* bussi = nullptr);
+// TwoStepLangevin step two; d_gamma_coeff = (gamma, sqrt(6 gamma kT / dt)) per type; total <- F + F_bd
+// (what the next step one integrates with)
+hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,
+                                    const uint32_t* tag, uint32_t N, float dt, const float* d_gamma_coeff,
+                                    uint32_t seed, uint64_t timestep, cudaStream_t stream);
 hb2_status launch_kinetic(const float4* vel, uint32_t N, double* d_partial, uint32_t* d_ticket,
                           double* d_ke_out, cudaStream_t stream);
 // Bussi factor on device (hoomd/md/Thermostat.h:357-447): *d_rescale <- factor for the step-one of

@@ -46,6 +46,7 @@ HB2_HD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
 // RNG ids (hoomd/RNGIdentifiers.h)
 constexpr uint8_t RNG_ID_DPD = 22;   // EvaluatorPairDPDThermo
 constexpr uint8_t RNG_ID_BUSSI = 45; // BussiThermostat
+constexpr uint8_t RNG_ID_LANGEVIN = 25; // TwoStepLangevin
 
 // hoomd/RandomNumbers.h:153-158: key = {id<<24 | seed16<<8 | timestep bits 39..32, timestep low 32}
 HB2_HD void seed_key(uint8_t id, uint64_t timestep, uint16_t seed, uint32_t& k0, uint32_t& k1)

@@ -3,7 +3,9 @@ import ctypes as C
 
 from .. import _lib
 from .._lib import check
-from .methods import ConstantVolume, Bussi
+import numpy as np
+
+from .methods import ConstantVolume, Bussi, Langevin
 
 
 class Integrator:
@@ -25,8 +27,8 @@ class Integrator:
             return
         if len(self.forces) != 1:
             raise NotImplementedError("this path carries exactly one pair force")
-        if len(self.methods) != 1 or not isinstance(self.methods[0], ConstantVolume):
-            raise NotImplementedError("this path integrates with one ConstantVolume method")
+        if len(self.methods) != 1 or not isinstance(self.methods[0], (ConstantVolume, Langevin)):
+            raise NotImplementedError("this path integrates with one ConstantVolume or Langevin method")
         L = _lib.lib()
         h = C.c_void_p()
         check(L.hb2_integrator_create(C.byref(h), sim.state._h, self.dt))
@@ -36,7 +38,11 @@ class Integrator:
         f._attach(sim)
         check(L.hb2_integrator_add_force(h, f._h))
         th = self.methods[0].thermostat
-        if isinstance(th, Bussi):
+        if isinstance(self.methods[0], Langevin):
+            m = self.methods[0]
+            gamma = np.array([m.gamma[t] for t in sim.state.particle_types], dtype=np.float64)
+            check(L.hb2_integrator_set_langevin(h, m.kT, _lib.ptr(gamma, C.c_double), len(gamma)))
+        elif isinstance(th, Bussi):
             check(L.hb2_integrator_set_constant_volume(h, 1, th.kT, th.tau))
         else:
             check(L.hb2_integrator_set_constant_volume(h, 0, 0.0, 0.0))

@@ -33,3 +33,31 @@ class ConstantVolume(Method):
             raise NotImplementedError("thermostat must be None or thermostats.Bussi")
         self.filter = filter
         self.thermostat = thermostat
+
+
+class _TypeDict(dict):
+    """per-type parameter with a default (hoomd TypeParameter, hoomd/data/typeparam.py)"""
+
+    def __init__(self, default):
+        super().__init__()
+        self.default = float(default)
+
+    def __missing__(self, key):
+        return self.default
+
+
+class Langevin(Method):
+    """hoomd.md.methods.Langevin(filter, kT, tally_reservoir_energy=False, default_gamma=1.0)
+    (hoomd/md/methods/methods.py, hoomd/md/TwoStepLangevin.cc): translational Langevin dynamics of
+    filter.All(); `gamma[type]` is the drag coefficient. Rotational degrees of freedom (gamma_r) and the
+    reservoir-energy tally are outside this path."""
+
+    def __init__(self, filter, kT, tally_reservoir_energy=False, default_gamma=1.0, default_gamma_r=None):
+        if not isinstance(filter, All):
+            raise NotImplementedError("this path integrates filter.All() only")
+        if tally_reservoir_energy:
+            raise NotImplementedError("tally_reservoir_energy is outside this path")
+        self.filter = filter
+        self.kT = float(kT)
+        self.gamma = _TypeDict(default_gamma)
+        self.thermostat = None

@@ -283,6 +283,12 @@ hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p);
 /* thermostat: 0 none (NVE), 1 Bussi(kT, tau) (hoomd/md/Thermostat.h:337-447; tau = 0 is allowed). */
 hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat, double kT,
                                               double tau);
+/* hoomd.md.methods.Langevin(filter=All, kT) (hoomd/md/methods/methods.py, hoomd/md/TwoStepLangevin.cc:
+ * 47-82 step one = the NVE half step, :213-292 step two with the BD force): translational degrees of
+ * freedom, 3D, one drag coefficient per particle type (`gamma[ntypes]`), no reservoir tally. Replaces
+ * the ConstantVolume method of this integrator. */
+hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT, const double* gamma,
+                                       uint32_t ntypes);
 /* System::run(nsteps) (hoomd/System.cc:80-181) restricted to this path: prepRun on the first call
  * (hoomd/md/IntegratorTwoStep.cc:226-281), then per step: step one -> nlist check/rebuild -> forces
  * -> step two. No host synchronisation inside the loop. */

@@ -800,6 +800,32 @@ void orc_step_two(double* vel, double* accel, const double* mass, const double* 
         }
     }
 
+void orc_step_two_langevin(double* vel, double* accel, const double* mass, const double* force4,
+                           const uint32_t* type, const uint32_t* tag, uint32_t n, double dt, double kT,
+                           const double* gamma, uint16_t seed, uint64_t timestep)
+    {
+    /* hoomd/md/TwoStepLangevin.cc:245-292; id 25 = TwoStepLangevin (hoomd/RNGIdentifiers.h:51);
+       UniformDistribution(-1, 1): a + width * canonical, hoomd/RandomNumbers.h:325-335 */
+    for (uint32_t j = 0; j < n; j++)
+        {
+        orc_rng g;
+        rng_init(&g, 25, timestep, seed, tag[j], 0, 0, 0);
+        double r[3];
+        for (int d = 0; d < 3; d++)
+            r[d] = -1.0 + 2.0 * rng_canonical(&g);
+        const double gm = gamma[type[j]];
+        const double coeff = sqrt(6.0 * gm * kT / dt);
+        const double minv = 1.0 / mass[j];
+        for (int d = 0; d < 3; d++)
+            {
+            const double bd = r[d] * coeff - gm * vel[3 * (size_t)j + d];
+            const double a = (force4[4 * (size_t)j + d] + bd) * minv;
+            accel[3 * (size_t)j + d] = a;
+            vel[3 * (size_t)j + d] += (1.0 / 2.0) * a * dt;
+            }
+        }
+    }
+
 double orc_kinetic_energy(const double* vel, const double* mass, uint32_t n)
     {
     /* hoomd/md/ComputeThermo.cc:139-153 */
@@ -887,7 +913,17 @@ int orc_run(const orc_box* b, orc_run_cfg* cfg, double* pos, double* vel, double
         else
             orc_pair_lj(b, pos, type, N, n_neigh, head, nlist, 1, params, r_cut, r_cut, nt,
                         cfg->shift_mode, 0, force, virial);
-        if (s > 0)
+        if (s > 0 && cfg->thermostat == 2)
+            {
+            /* integrateStepTwo(timestep) of the step that started at t_force - 1 */
+            double* gm = (double*)malloc(sizeof(double) * nt);
+            for (uint32_t q = 0; q < nt; q++)
+                gm[q] = cfg->gamma;
+            orc_step_two_langevin(vel, accel, mass, force, type, tag, N, cfg->dt, cfg->kT, gm, cfg->seed,
+                                  t_force - 1);
+            free(gm);
+            }
+        else if (s > 0)
             orc_step_two(vel, accel, mass, force, N, cfg->dt, 1.0);
         }
     cfg->timestep += nsteps;

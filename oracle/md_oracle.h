@@ -107,6 +107,12 @@ void orc_step_one(const orc_box* b, double* pos, double* vel, const double* acce
                   uint32_t n, double dt, double rescale);
 void orc_step_two(double* vel, double* accel, const double* mass, const double* force4, uint32_t n,
                   double dt, double rescale);
+/* hoomd/md/TwoStepLangevin.cc:213-292 (translational part, 3D, no reservoir tally): BD force
+ * r * sqrt(6 gamma kT / dt) - gamma v with r uniform in [-1,1] drawn per particle from
+ * RandomGenerator(Seed(TwoStepLangevin = 25, timestep, seed), Counter(tag)); gamma per type. */
+void orc_step_two_langevin(double* vel, double* accel, const double* mass, const double* force4,
+                           const uint32_t* type, const uint32_t* tag, uint32_t n, double dt, double kT,
+                           const double* gamma, uint16_t seed, uint64_t timestep);
 /* hoomd/md/ComputeThermo.cc:139-153 */
 double orc_kinetic_energy(const double* vel, const double* mass, uint32_t n);
 /* hoomd/md/Thermostat.h:357-447 (Bussi) with hoomd/RandomNumbers.h Normal/Gamma */
@@ -115,7 +121,8 @@ double orc_bussi_factor(double K, double dof, double dt, double kT, double tau, 
 
 /* Whole step loop, hoomd/md/IntegratorTwoStep.cc:51-123 + hoomd/md/NeighborList.cc:363-435 (half
  * list like hoomd.device.CPU). Used as the CPU baseline ("port") and for trajectory parity.
- * thermostat: 0 none, 1 Bussi. potential: 0 LJ, 1 DPD. Returns number of nlist builds. */
+ * thermostat: 0 none, 1 Bussi, 2 Langevin method (TwoStepLangevin, one gamma for every type).
+ * potential: 0 LJ, 1 DPD. Returns number of nlist builds. */
 typedef struct
     {
     uint32_t n, ntypes;
@@ -123,6 +130,7 @@ typedef struct
     int thermostat, potential, shift_mode;
     uint16_t seed;
     uint64_t timestep;
+    double gamma; /* Langevin drag coefficient (thermostat == 2) */
     } orc_run_cfg;
 int orc_run(const orc_box* b, orc_run_cfg* cfg, double* pos, double* vel, double* accel, int* image,
             const double* mass, const uint32_t* type, const uint32_t* tag, const double* params,

@@ -30,7 +30,7 @@ class RunCfg(C.Structure):
     _fields_ = [("n", C.c_uint32), ("ntypes", C.c_uint32), ("dt", C.c_double),
                 ("r_buff", C.c_double), ("kT", C.c_double), ("tau", C.c_double),
                 ("thermostat", C.c_int), ("potential", C.c_int), ("shift_mode", C.c_int),
-                ("seed", C.c_uint16), ("timestep", C.c_uint64)]
+                ("seed", C.c_uint16), ("timestep", C.c_uint64), ("gamma", C.c_double)]
 
 
 _lib = None
@@ -270,6 +270,17 @@ def step_two(vel, accel, mass, force4, dt, rescale=1.0):
                        C.c_double(rescale))
 
 
+def step_two_langevin(vel, accel, mass, force4, types, tags, dt, kT, gamma, seed, timestep):
+    """TwoStepLangevin::integrateStepTwo in place on fp64 vel/accel (N,3); gamma per type."""
+    types = _u32(types)
+    tags = _u32(tags)
+    gamma = _f64(gamma)
+    lib().orc_step_two_langevin(_p(vel, C.c_double), _p(accel, C.c_double), _p(_f64(mass), C.c_double),
+                                _p(force4, C.c_double), _p(types, C.c_uint32), _p(tags, C.c_uint32),
+                                C.c_uint32(types.size), C.c_double(dt), C.c_double(kT),
+                                _p(gamma, C.c_double), C.c_uint16(seed), C.c_uint64(timestep))
+
+
 def distance_check(box, pos, last_pos, types, rcut_max, r_buff):
     pos = _f64(pos)
     last_pos = _f64(last_pos)
@@ -281,14 +292,14 @@ def distance_check(box, pos, last_pos, types, rcut_max, r_buff):
 
 
 def run(box, pos, vel, accel, image, mass, types, tags, params, r_cut, nsteps, dt, r_buff,
-        potential="lj", shift_mode=0, thermostat=None, kT=0.0, tau=0.0, seed=0, timestep=0):
+        potential="lj", shift_mode=0, thermostat=None, kT=0.0, tau=0.0, seed=0, timestep=0, gamma=1.0):
     """Whole step loop (half list) in place; returns dict(builds, n_neigh_mean, force, timestep)."""
     n = pos.shape[0]
     r_cut = _f64(r_cut)
     params = _f64(params)
     nt = int(round(np.sqrt(r_cut.size)))
-    cfg = RunCfg(n, nt, dt, r_buff, kT, tau, 1 if thermostat == "bussi" else 0,
-                 1 if potential == "dpd" else 0, shift_mode, seed, timestep)
+    cfg = RunCfg(n, nt, dt, r_buff, kT, tau, {"bussi": 1, "langevin": 2}.get(thermostat, 0),
+                 1 if potential == "dpd" else 0, shift_mode, seed, timestep, gamma)
     force = np.zeros((n, 4))
     nn = C.c_double(0)
     builds = lib().orc_run(C.byref(box), C.byref(cfg), _p(pos, C.c_double), _p(vel, C.c_double),

@@ -34,7 +34,7 @@ def force_err(f, f_ref):
     return np.max(np.linalg.norm(f - f_ref, axis=1) / np.maximum(n_ref, floor))
 
 
-def build(hoomd, fx, device, thermostat=None, dpd=False):
+def build(hoomd, fx, device, thermostat=None, dpd=False, langevin=False):
     sim = hoomd.Simulation(device=device, seed=7)
     snap = hoomd.Snapshot.from_arrays(list(fx["L"]) + [0, 0, 0], fx["pos"], fx["vel"], None, ("A",),
                                       fx["image"])
@@ -48,6 +48,8 @@ def build(hoomd, fx, device, thermostat=None, dpd=False):
         f = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
         f.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
     cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All(), thermostat=thermostat)
+    if langevin:
+        cv = hoomd.md.methods.Langevin(filter=hoomd.filter.All(), kT=1.5, default_gamma=2.0)
     sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[cv], forces=[f])
     return sim, cell, f
 
@@ -142,8 +144,17 @@ def main():
     qs.run(3)
     derr = force_err(dl.forces, ql.forces)
     assert derr <= 1e-4, derr
+    # (6) Langevin method: the noise is keyed on (timestep, seed, tag), not on the owner or the order
+    ls, lc, ll = build(hoomd, fx, hoomd.device.GPU(), langevin=True)
+    ms, mc, ml = build(hoomd, fx, hoomd.device.GPU(gpu_id=local, communicator=one), langevin=True)
+    ls.run(40)
+    ms.run(40)
+    kl = ls.operations.integrator._thermo()[0]
+    km = ms.operations.integrator._thermo()[0]
+    assert abs(kl - km) <= 2e-4 * abs(km), (kl, km)
     if rank == 0:
-        print(msg + f" bussi_KE_rel={abs(kb - kr) / abs(kr):.1e} dpd_force_err={derr:.1e}", flush=True)
+        print(msg + f" bussi_KE_rel={abs(kb - kr) / abs(kr):.1e} dpd_force_err={derr:.1e}"
+              f" langevin_KE_rel={abs(kl - km) / abs(km):.1e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

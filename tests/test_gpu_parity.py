@@ -286,6 +286,62 @@ def test_dpd_trajectory(hoomd, golden_dir):
     assert np.max(np.abs(s.particles.velocity - fx["traj_vel"])) < 2e-3
 
 
+def test_langevin_trajectory_vs_oracle(hoomd, oracle, golden_dir):
+    """hoomd.md.methods.Langevin (hoomd/md/TwoStepLangevin.cc) against the oracle's fp64 restatement on
+    the 2k LJ frame: the noise is a function of (timestep, seed, tag), so the fp32 trajectory tracks the
+    fp64 one like the NVE trajectory does."""
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    n = len(fx["pos"])
+    sim = make_sim(hoomd, fx["L"], fx["pos"], fx["vel"], seed=11)
+    cell = hoomd.md.nlist.Cell(buffer=0.4)
+    lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+    lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+    lv = hoomd.md.methods.Langevin(filter=hoomd.filter.All(), kT=1.5, default_gamma=2.0)
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[lv], forces=[lj])
+    sim.run(20)
+    s = sim.state.get_snapshot()
+
+    box = oracle.make_box([float(v) for v in fx["L"]])
+    pos, vel = fx["pos"].astype(np.float64), fx["vel"].astype(np.float64)
+    img = np.zeros((n, 3), dtype=np.int32)
+    mass, types, tags = np.ones(n), np.zeros(n, dtype=np.uint32), np.arange(n, dtype=np.uint32)
+    nn, head, nl, _ = oracle.nlist(box, pos, types, [2.5], 0.4, full=True)
+    f0, _ = oracle.pair_lj(box, pos, types, nn, head, nl, [[1.0, 1.0]], [2.5], shift_mode=0)
+    accel = np.ascontiguousarray(f0[:, :3] / mass[:, None])
+    oracle.run(box, pos, vel, accel, img, mass, types, tags, [[1.0, 1.0]], [2.5], 20, 0.005, 0.4,
+               thermostat="langevin", kT=1.5, seed=11, gamma=2.0)
+    L = fx["L"].astype(np.float64)
+    d = s.particles.position.astype(np.float64) - pos
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 2e-4
+    assert np.max(np.abs(s.particles.velocity - vel)) < 2e-3
+    # and it is not the NVE trajectory
+    assert np.max(np.abs(s.particles.velocity - fx["nve_vel"])) > 0.05
+
+
+def test_langevin_temperature(hoomd):
+    """Fluctuation-dissipation on the device: a dilute, nearly ideal gas started at rest reaches the
+    set temperature (per-type drag coefficients)."""
+    pos, vel, L = random_liquid(24, 0.05, seed=5)
+    typeid = (np.arange(len(pos)) % 2).astype(np.uint32)
+    sim = make_sim(hoomd, L, pos, np.zeros_like(vel), typeid=typeid, types=("A", "B"), seed=3)
+    cell = hoomd.md.nlist.Cell(buffer=0.4)
+    lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+    lj.params[(["A", "B"], ["A", "B"])] = dict(epsilon=0.0, sigma=1.0)
+    lv = hoomd.md.methods.Langevin(filter=hoomd.filter.All(), kT=2.0)
+    lv.gamma["A"] = 2.0
+    lv.gamma["B"] = 5.0
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.01, methods=[lv], forces=[lj])
+    thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+    thermo._attach(sim)
+    sim.run(600)
+    temps = []
+    for _ in range(40):
+        sim.run(25)
+        temps.append(thermo.kinetic_temperature)
+    assert abs(np.mean(temps) / 2.0 - 1.0) < 0.02
+
+
 # ------------------------------------------------------------------ oracle on seeded inputs ----
 def random_liquid(n_side, rho, seed, jitter=0.1):
     rng = np.random.default_rng(seed)

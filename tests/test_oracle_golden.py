@@ -271,3 +271,67 @@ def test_distance_check(oracle):
     pos[1] = [4.95, 0, 0]
     last[1] = [-4.95, 0, 0]
     assert not oracle.distance_check(box, pos, last, t, [2.5], 0.4)  # min image of displacement
+
+
+def test_langevin_step_two(oracle):
+    """TwoStepLangevin::integrateStepTwo (hoomd/md/TwoStepLangevin.cc:213-292). The reference's own
+    tests of the method check attributes only (hoomd/md/pytest/test_methods.py:66-75, :345-358), so the
+    restatement is pinned through what it shares with the pinned paths — Philox (KAT), Seed/Counter and
+    the uniform draw (DPD fixture) — plus the identities of the update rule and the
+    fluctuation-dissipation statistic. PARITY OF THE LANGEVIN NOISE STREAM IS NOT PINNED by a
+    reference-generated trajectory."""
+    rng = np.random.default_rng(3)
+    n = 4096
+    vel = rng.normal(0, 1.0, size=(n, 3))
+    mass = rng.uniform(0.5, 2.0, size=n)
+    force = np.zeros((n, 4))
+    force[:, :3] = rng.normal(0, 3.0, size=(n, 3))
+    types = (np.arange(n) % 2).astype(np.uint32)
+    tags = rng.permutation(n).astype(np.uint32)
+    # gamma = 0: no drag and no noise -> the NVE half step
+    v0, a0 = vel.copy(), np.zeros((n, 3))
+    oracle.step_two_langevin(v0, a0, mass, force, types, tags, 0.005, 1.5, [0.0, 0.0], 7, 10)
+    v1, a1 = vel.copy(), np.zeros((n, 3))
+    oracle.step_two(v1, a1, mass, force, 0.005)
+    assert np.array_equal(v0, v1) and np.array_equal(a0, a1)
+    # the noise is keyed by (timestep, seed, tag) only: independent of memory order, new every step,
+    # uniform in [-1, 1] scaled by sqrt(6 gamma kT / dt), gamma per type
+    gamma = np.array([0.5, 2.0])
+    v2, a2 = vel.copy(), np.zeros((n, 3))
+    oracle.step_two_langevin(v2, a2, mass, force, types, tags, 0.005, 1.5, gamma, 7, 10)
+    perm = rng.permutation(n)
+    v3, a3 = vel[perm].copy(), np.zeros((n, 3))
+    oracle.step_two_langevin(v3, a3, mass[perm], force[perm], types[perm], tags[perm], 0.005, 1.5, gamma,
+                             7, 10)
+    assert np.array_equal(v3, v2[perm])
+    g = gamma[types][:, None]
+    r = (a2 * mass[:, None] - force[:, :3] + g * vel) / np.sqrt(6.0 * g * 1.5 / 0.005)
+    assert np.all(np.abs(r) <= 1.0 + 1e-12)
+    assert abs(r.mean()) < 0.02 and abs(r.var() - 1.0 / 3.0) < 0.01
+    key = np.array([0, 0], dtype=np.uint32)
+    key_buf = np.zeros(2, dtype=np.uint32)
+    import ctypes as C
+    oracle.lib().orc_seed_key(C.c_uint8(25), C.c_uint64(10), C.c_uint16(7),
+                              key_buf.ctypes.data_as(C.POINTER(C.c_uint32)))
+    ctr = np.array([0, 0, 0, tags[5]], dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    oracle.lib().orc_philox4x32_10(ctr.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   key_buf.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    u = (int(out[0]) << 32 | int(out[1])) * 2.0 ** -64 + 2.0 ** -65
+    assert np.isclose(r[5, 0], -1.0 + 2.0 * u, rtol=0, atol=1e-12)  # first draw = x component
+    v4, a4 = vel.copy(), np.zeros((n, 3))
+    oracle.step_two_langevin(v4, a4, mass, force, types, tags, 0.005, 1.5, gamma, 7, 11)
+    assert not np.allclose(a4, a2)
+    # fluctuation-dissipation: free particles relax to <m v^2> = kT per component
+    vel = np.zeros((n, 3))
+    acc = np.zeros((n, 3))
+    zero = np.zeros((n, 4))
+    dt, kT = 0.01, 1.5
+    kes = []
+    for t in range(1500):
+        vel += 0.5 * dt * acc                      # step one's velocity half (positions play no role)
+        oracle.step_two_langevin(vel, acc, mass, zero, types, tags, dt, kT, [2.0, 4.0], 7, t)
+        if t >= 500:
+            kes.append(oracle.kinetic_energy(vel, mass))
+    assert abs(np.mean(kes) / (1.5 * n * kT) - 1.0) < 0.02
