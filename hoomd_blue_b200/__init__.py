@@ -11,7 +11,7 @@ from . import _lib  # noqa: F401
 from . import device, filter, md  # noqa: F401
 from .simulation import Simulation, Snapshot, State, Operations  # noqa: F401
 from . import gsd_io  # noqa: F401
-from . import write  # noqa: F401
+from . import write, trigger, logging  # noqa: F401
 
-__all__ = ["Simulation", "Snapshot", "device", "filter", "md", "gsd_io", "write"]
+__all__ = ["Simulation", "Snapshot", "device", "filter", "md", "gsd_io", "write", "trigger", "logging"]
 version = "0.1.0+hoomd4.8.2-path"

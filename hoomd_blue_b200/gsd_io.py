@@ -123,58 +123,134 @@ def read_frame(filename, frame=-1):
     return snap, step
 
 
-def write_frames(filename, frames, application="hoomd_blue_b200"):
-    """Write a new GSD file holding `frames` = [(snapshot, step), ...] with the hoomd schema 1.4
-    (hoomd/GSDDumpWriter.cc:265-275,480-660: box and positions as float32, every particle chunk written
-    in every frame)."""
-    chunks = []  # (frame, name, array2d)
-    for k, (snap, step) in enumerate(frames):
-        p = snap.particles
-        n = int(p.N)
+def frame_chunks(snap, step, dynamic=None, first=True, log=None):
+    """The chunks of one frame of the hoomd schema 1.4 (hoomd/GSDDumpWriter.cc:265-275,480-660: box
+    and positions as float32). `first` frames (frame 0 of a file) carry every chunk; later frames carry
+    the configuration and the categories named in `dynamic` ('property': position; 'momentum': velocity
+    and image; 'attribute': N, types, typeid, mass — hoomd/write/gsd.py:103-151), the rest is read back
+    from frame 0. `log`: {name: value} written as log/<name> (float64 / int64 arrays)."""
+    dynamic = set(dynamic if dynamic is not None else ("property",))
+    p = snap.particles
+    n = int(p.N)
+    out = [("configuration/step", np.array([[step]], dtype=np.uint64))]
+    if first:
+        out.append(("configuration/dimensions", np.array([[snap.configuration.dimensions]], dtype=np.uint8)))
+    out.append(("configuration/box", np.asarray(snap.configuration.box, dtype=np.float32).reshape(6, 1)))
+    if first or "attribute" in dynamic:
         tw = max(len(t) for t in p.types) + 1
         types = np.zeros((len(p.types), tw), dtype=np.int8)
         for i, t in enumerate(p.types):
             types[i, :len(t)] = np.frombuffer(t.encode(), dtype=np.int8)
-        chunks += [
-            (k, "configuration/step", np.array([[step]], dtype=np.uint64)),
-            (k, "configuration/dimensions", np.array([[snap.configuration.dimensions]], dtype=np.uint8)),
-            (k, "configuration/box", np.asarray(snap.configuration.box, dtype=np.float32).reshape(6, 1)),
-            (k, "particles/N", np.array([[n]], dtype=np.uint32)),
-            (k, "particles/types", types),
-            (k, "particles/typeid", np.asarray(p.typeid, dtype=np.uint32).reshape(n, 1)),
-            (k, "particles/mass", np.asarray(p.mass, dtype=np.float32).reshape(n, 1)),
-            (k, "particles/position", np.asarray(p.position, dtype=np.float32).reshape(n, 3)),
-            (k, "particles/velocity", np.asarray(p.velocity, dtype=np.float32).reshape(n, 3)),
-            (k, "particles/image", np.asarray(p.image, dtype=np.int32).reshape(n, 3)),
-        ]
-    names = []
-    for _, name, _ in chunks:
-        if name not in names:
-            names.append(name)
-    nl_bytes = b"".join(n.encode() + b"\0" for n in names)
-    nl_entries = max(16, (len(nl_bytes) + 1 + 63) // 64)
-    idx_entries = max(128, len(chunks) + 1)
-    idx_loc = HEADER.size
-    nl_loc = idx_loc + idx_entries * ENTRY.itemsize
-    data_loc = nl_loc + nl_entries * 64
-    index = np.zeros(idx_entries, dtype=ENTRY)
-    order = sorted(range(len(chunks)), key=lambda q: (chunks[q][0], names.index(chunks[q][1])))
-    blobs = []
-    loc = data_loc
-    for slot, q in enumerate(order):
-        frame, name, arr = chunks[q]
-        arr = np.ascontiguousarray(arr)
-        index[slot] = (frame, arr.shape[0], loc, arr.shape[1], names.index(name), TYPE_ID[arr.dtype], 0)
-        blobs.append(arr.tobytes())
-        loc += arr.nbytes
-    header = HEADER.pack(MAGIC, idx_loc, idx_entries, nl_loc, nl_entries, make_version(1, 4),
-                         make_version(2, 0), application.encode()[:63], b"hoomd", b"")
-    with open(filename, "wb") as f:
-        f.write(header)
-        f.write(index.tobytes())
-        f.write(nl_bytes.ljust(nl_entries * 64, b"\0"))
-        for b in blobs:
-            f.write(b)
+        out += [("particles/N", np.array([[n]], dtype=np.uint32)), ("particles/types", types),
+                ("particles/typeid", np.asarray(p.typeid, dtype=np.uint32).reshape(n, 1)),
+                ("particles/mass", np.asarray(p.mass, dtype=np.float32).reshape(n, 1))]
+    if first or "property" in dynamic:
+        out.append(("particles/position", np.asarray(p.position, dtype=np.float32).reshape(n, 3)))
+    if first or "momentum" in dynamic:
+        out += [("particles/velocity", np.asarray(p.velocity, dtype=np.float32).reshape(n, 3)),
+                ("particles/image", np.asarray(p.image, dtype=np.int32).reshape(n, 3))]
+    for name, value in (log or {}).items():
+        arr = np.atleast_1d(np.asarray(value))
+        arr = arr.astype(np.int64 if np.issubdtype(arr.dtype, np.integer) else np.float64)
+        out.append(("log/" + name, arr.reshape(arr.shape[0], -1)))
+    return out
+
+
+class GSDWriter:
+    """Appending GSD writer (file layout of hoomd/extern/gsd.c, GSD 2.0): chunk data goes to the end of
+    the file, the frame's index entries (sorted by name id) follow the earlier frames' in the
+    pre-allocated index, new names are appended to the name list; a full index or name list moves to
+    the end of the file with twice the room (gsd.c:expand_index / append_name). mode 'wb' creates or
+    truncates, 'xb' creates, 'ab' appends to an existing file or creates it."""
+
+    def __init__(self, filename, mode="ab", application="hoomd_blue_b200"):
+        import os
+        if mode not in ("wb", "xb", "ab"):
+            raise ValueError("mode must be 'wb', 'xb' or 'ab'")
+        if mode == "xb" and os.path.exists(filename):
+            raise FileExistsError(filename)
+        self.filename = filename
+        if mode == "ab" and os.path.exists(filename):
+            g = GSDFile(filename)
+            if g.schema != "hoomd" or (g.gsd_version >> 16) != 2:
+                raise RuntimeError(f"{filename}: can only append to GSD 2.x files of the hoomd schema")
+            with open(filename, "rb") as f:
+                (_, self.idx_loc, self.idx_entries, self.nl_loc, self.nl_entries, _, _, app, _,
+                 _) = HEADER.unpack(f.read(HEADER.size))
+            self.application = app.split(b"\0")[0]
+            self.names = list(g.names)
+            self.idx_used = len(g.index)
+            self.nframes = g.nframes
+        else:
+            self.application = application.encode()[:63]
+            self.idx_entries, self.nl_entries = 128, 128
+            self.idx_loc = HEADER.size
+            self.nl_loc = self.idx_loc + self.idx_entries * ENTRY.itemsize
+            self.names, self.idx_used, self.nframes = [], 0, 0
+            with open(filename, "wb") as f:
+                f.write(self._header())
+                f.write(bytes(self.idx_entries * ENTRY.itemsize + self.nl_entries * 64))
+
+    def _header(self):
+        return HEADER.pack(MAGIC, self.idx_loc, self.idx_entries, self.nl_loc, self.nl_entries,
+                           make_version(1, 4), make_version(2, 0), self.application, b"hoomd", b"")
+
+    def _nl_bytes(self):
+        return b"".join(n.encode() + b"\0" for n in self.names)
+
+    def append(self, chunks):
+        """Write one frame: chunks = [(name, 2D array), ...]."""
+        with open(self.filename, "r+b") as f:
+            new_names = []
+            for name, _ in chunks:
+                if name not in self.names and name not in new_names:
+                    new_names.append(name)
+            if new_names:
+                self.names += new_names
+                nl = self._nl_bytes()
+                if len(nl) + 1 > self.nl_entries * 64:
+                    while len(nl) + 1 > self.nl_entries * 64:
+                        self.nl_entries *= 2
+                    f.seek(0, 2)
+                    self.nl_loc = f.tell()
+                f.seek(self.nl_loc)
+                f.write(nl.ljust(self.nl_entries * 64, b"\0"))
+            ids = {n: i for i, n in enumerate(self.names)}
+            entries = np.zeros(len(chunks), dtype=ENTRY)
+            f.seek(0, 2)
+            loc = f.tell()
+            order = sorted(range(len(chunks)), key=lambda q: ids[chunks[q][0]])
+            for slot, q in enumerate(order):
+                name, arr = chunks[q]
+                arr = np.ascontiguousarray(arr)
+                if arr.ndim != 2:
+                    raise ValueError(f"chunk {name} must be a 2D array")
+                entries[slot] = (self.nframes, arr.shape[0], loc, arr.shape[1], ids[name],
+                                 TYPE_ID[arr.dtype], 0)
+                f.write(arr.tobytes())
+                loc += arr.nbytes
+            if self.idx_used + len(entries) + 1 > self.idx_entries:
+                f.seek(self.idx_loc)
+                old = f.read(self.idx_used * ENTRY.itemsize)
+                while self.idx_used + len(entries) + 1 > self.idx_entries:
+                    self.idx_entries *= 2
+                f.seek(0, 2)
+                self.idx_loc = f.tell()
+                f.write(old.ljust(self.idx_entries * ENTRY.itemsize, b"\0"))
+            f.seek(self.idx_loc + self.idx_used * ENTRY.itemsize)
+            f.write(entries.tobytes())
+            self.idx_used += len(entries)
+            self.nframes += 1
+            f.seek(0)
+            f.write(self._header())
+
+
+def write_frames(filename, frames, application="hoomd_blue_b200"):
+    """Write a new GSD file holding `frames` = [(snapshot, step), ...], every particle chunk written
+    in every frame."""
+    w = GSDWriter(filename, "wb", application)
+    for snap, step in frames:
+        w.append(frame_chunks(snap, step, first=True))
 
 
 def write_frame(filename, snapshot, step=0):

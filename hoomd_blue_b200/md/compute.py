@@ -4,6 +4,8 @@ import numpy as np
 
 
 class ThermodynamicQuantities:
+    _loggables = {"kinetic_energy": "scalar", "potential_energy": "scalar", "kinetic_temperature": "scalar",
+                  "pressure": "scalar", "degrees_of_freedom": "scalar"}
 
     def __init__(self, filter):
         self.filter = filter

@@ -18,6 +18,7 @@ def _nonneg(v):
 
 
 class Force:
+    _loggables = {"energy": "scalar"}
     """hoomd.md.force.Force properties (hoomd/md/force.py:77-156), tag-ordered."""
 
     _h = None

@@ -276,11 +276,30 @@ class State:
 
 
 class Operations:
-    """hoomd.Operations restricted to `integrator` (hoomd/operations.py:32)."""
+    """hoomd.Operations restricted to `integrator`, `writers` and `computes` (hoomd/operations.py:32)."""
 
     def __init__(self, simulation):
         self._simulation = simulation
         self._integrator = None
+        self.writers = []
+        self.computes = []
+
+    def __iadd__(self, op):
+        self.add(op)
+        return self
+
+    def add(self, op):
+        from .write import Writer
+        from .md.compute import ThermodynamicQuantities
+        if isinstance(op, Writer):
+            self.writers.append(op)
+        elif isinstance(op, ThermodynamicQuantities):
+            self.computes.append(op)
+            op._attach(self._simulation)
+        elif hasattr(op, "_run"):
+            self.integrator = op
+        else:
+            raise TypeError(f"cannot add {type(op).__name__} to Operations")
 
     @property
     def integrator(self):
@@ -294,6 +313,7 @@ class Operations:
 
 
 class Simulation:
+    _loggables = {"timestep": "scalar", "tps": "scalar", "walltime": "scalar"}
 
     def __init__(self, device, seed=None):
         from .device import GPU
@@ -378,8 +398,36 @@ class Simulation:
         if integ is None:
             raise RuntimeError("No integrator is set")
         integ._attach(self)
+        for c in self.operations.computes:
+            c._attach(self)
+        writers = list(self.operations.writers)
         t0 = time.perf_counter()
-        integ._run(int(steps))
+        device_ms = 0.0
+        if not writers:
+            integ._run(int(steps))
+            device_ms = integ._last_run_ms()
+        else:
+            # System::run (hoomd/System.cc:80-181): writers fire after the step that brings the
+            # timestep to a triggered value (and before the first step with write_at_start). The
+            # step loop itself stays on the device between two triggered steps.
+            now = self.timestep
+            end = now + int(steps)
+            if write_at_start:
+                for w in writers:
+                    if w.trigger(now):
+                        w._write(self)
+            while now < end:
+                nxt = [w.trigger.next_after(now) for w in writers]
+                nxt = min([n for n in nxt if n is not None] + [end])
+                nxt = min(nxt, end)
+                integ._run(nxt - now)
+                device_ms += integ._last_run_ms()
+                now = nxt
+                for w in writers:
+                    if w.trigger(now):
+                        w._write(self)
+            for w in writers:
+                w.flush()
         self._walltime = time.perf_counter() - t0
         self._tps = steps / self._walltime if self._walltime > 0 else 0.0
-        self._last_device_ms = integ._last_run_ms()
+        self._last_device_ms = device_ms

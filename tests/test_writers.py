@@ -1,0 +1,167 @@
+"""Triggers, the logger, the Table writer and the appending GSD trajectory writer (SURVEY 8f rank 1:
+hoomd/write/gsd.py, hoomd/GSDDumpWriter.cc, hoomd/write/table.py, hoomd/trigger.py). The files are read
+back by this package's reader and — where oracle/_ref/libgsd_ref.so exists — by the reference's own
+gsd.c."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from tests import gsd_ref
+from tests.test_gsd_io import _snapshot
+
+
+def test_triggers():
+    from hoomd_blue_b200 import trigger as T
+    p = T.Periodic(100, phase=30)
+    assert [t for t in range(0, 400) if p(t)] == [30, 130, 230, 330]
+    assert p.next_after(30) == 130 and p.next_after(29) == 30 and p.next_after(131) == 230
+    assert T.as_trigger(7).period == 7
+    assert T.On(5)(5) and not T.On(5)(6) and T.On(5).next_after(5) is None and T.On(5).next_after(1) == 5
+    assert T.Before(3)(2) and not T.Before(3)(3) and T.After(3)(4) and not T.After(3)(3)
+    assert T.After(10).next_after(2) == 11 and T.Before(10).next_after(9) is None
+    with pytest.raises(ValueError):
+        T.Periodic(0)
+    with pytest.raises(TypeError):
+        T.as_trigger("x")
+
+
+def test_gsd_append_writer(tmp_path):
+    """300 appended frames (the 128-entry index and the name list both have to move), dynamic
+    categories, log chunks; frame 0 fallback on read."""
+    from hoomd_blue_b200 import gsd_io
+    path = str(tmp_path / "traj.gsd")
+    base = _snapshot(40, 1)
+    w = gsd_io.GSDWriter(path, "wb")
+    frames = []
+    for k in range(300):
+        s = _snapshot(40, 1)
+        s.particles.position[:] = base.particles.position + np.float32(0.001 * k)
+        s.particles.velocity[:] = base.particles.velocity * np.float32(k)
+        dyn = {"property"} if k % 2 else {"property", "momentum"}
+        log = {f"md/q{k % 70}/value": 0.5 * k, "Simulation/timestep": 10 * k}
+        w.append(gsd_io.frame_chunks(s, 10 * k, dynamic=dyn, first=(k == 0), log=log))
+        frames.append(s)
+    g = gsd_io.GSDFile(path)
+    assert g.nframes == 300 and len(g.names) > 70
+    for k in (0, 1, 2, 127, 128, 299):
+        s, step = gsd_io.read_frame(path, k)
+        assert step == 10 * k
+        assert np.array_equal(s.particles.position, frames[k].particles.position)
+        want_vel = frames[k].particles.velocity if k % 2 == 0 else frames[0].particles.velocity
+        assert np.array_equal(s.particles.velocity, want_vel)
+        assert np.array_equal(s.particles.mass, base.particles.mass) and s.particles.types == base.particles.types
+        assert g.chunk(k, f"log/md/q{k % 70}/value")[0, 0] == 0.5 * k
+        assert g.chunk(k, "log/Simulation/timestep").dtype == np.int64
+    # append to the existing file
+    w2 = gsd_io.GSDWriter(path, "ab")
+    assert w2.nframes == 300
+    w2.append(gsd_io.frame_chunks(frames[5], 7777, dynamic={"property"}, first=False))
+    assert gsd_io.read_frame(path, -1)[1] == 7777 and gsd_io.GSDFile(path).nframes == 301
+    with pytest.raises(FileExistsError):
+        gsd_io.GSDWriter(path, "xb")
+    if gsd_ref.available():
+        r = gsd_ref.RefGSD.open(path)
+        assert r.nframes() == 301
+        for k in (0, 129, 300):
+            assert r.read(k, "configuration/step")[0, 0] == (7777 if k == 300 else 10 * k)
+        assert np.array_equal(r.read(299, "particles/position"), frames[299].particles.position)
+        assert r.read(299, "particles/velocity") is None  # odd frame: not dynamic
+        assert r.read(298, "log/md/q18/value")[0, 0] == 149.0
+        r.close()
+
+
+class _Thermo:
+    _loggables = {"kinetic_energy": "scalar", "pressure": "scalar", "tensor": "sequence"}
+    kinetic_energy = 1.25
+    pressure = -3.0
+    tensor = (1.0, 2.0)
+
+
+_Thermo.__module__ = "hoomd_blue_b200.md.compute"
+
+
+def test_logger_and_table():
+    from hoomd_blue_b200 import logging, write, device, Simulation
+    lg = logging.Logger(categories=["scalar"])
+    th = _Thermo()
+    added = lg.add(th)
+    assert added == [("md", "compute", "_Thermo", "kinetic_energy"), ("md", "compute", "_Thermo", "pressure")]
+    lg[("custom", "answer")] = (lambda: 42, "scalar")
+    with pytest.raises(ValueError):
+        lg.add(th, quantities=["nope"])
+    out = io.StringIO()
+
+    class _Sim:
+        class device:
+            class communicator:
+                rank = 0
+    tb = write.Table(trigger=10, logger=lg, output=out, max_header_len=2)
+    tb._write(_Sim)
+    th.kinetic_energy = 2.5
+    tb._write(_Sim)
+    lines = out.getvalue().splitlines()
+    assert lines[0] == "_Thermo.kinetic_energy _Thermo.pressure custom.answer"
+    assert lines[1] == "1.25 -3 42" and lines[2] == "2.5 -3 42"
+
+
+@pytest.mark.gpu
+def test_periodic_gsd_writer_in_run(tmp_path):
+    """A run with writers is the same trajectory as one without; frames land on the triggered steps
+    with the logged thermodynamics of those steps."""
+    import hoomd_blue_b200 as hoomd
+    from tests.test_gpu_parity import random_liquid
+
+    def make():
+        pos, vel, L = random_liquid(12, 0.8, seed=2)
+        sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=4)
+        sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel))
+        cell = hoomd.md.nlist.Cell(buffer=0.4)
+        lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+        lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+        cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.002, methods=[cv], forces=[lj])
+        return sim, lj
+
+    ref, _ = make()
+    ref.run(230)
+    sim, lj = make()
+    thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+    sim.operations += thermo
+    lg = hoomd.logging.Logger(categories=["scalar"])
+    lg.add(thermo, quantities=["kinetic_energy", "potential_energy"])
+    lg.add(sim, quantities=["timestep"])
+    path = str(tmp_path / "traj.gsd")
+    sim.operations.writers.append(hoomd.write.GSD(trigger=hoomd.trigger.Periodic(50), filename=path,
+                                                  mode="wb", dynamic=["property", "momentum"], logger=lg))
+    table = io.StringIO()
+    sim.operations += hoomd.write.Table(trigger=100, logger=lg, output=table)
+    sim.run(230, write_at_start=True)
+    assert sim.timestep == 230
+    a, b = sim.state.get_snapshot(), ref.state.get_snapshot()
+    assert np.array_equal(a.particles.position, b.particles.position)
+    assert np.array_equal(a.particles.velocity, b.particles.velocity)
+    g = hoomd.gsd_io.GSDFile(path)
+    assert g.nframes == 5
+    assert [int(g.chunk(k, "configuration/step")[0, 0]) for k in range(5)] == [0, 50, 100, 150, 200]
+    assert [int(g.chunk(k, "log/Simulation/timestep")[0, 0]) for k in range(5)] == [0, 50, 100, 150, 200]
+    e = [g.chunk(k, "log/md/compute/ThermodynamicQuantities/kinetic_energy")[0, 0]
+         + g.chunk(k, "log/md/compute/ThermodynamicQuantities/potential_energy")[0, 0] for k in range(5)]
+    assert np.ptp(e) < 2e-2 * abs(e[0])  # NVE from a jittered lattice: the logged total energy is conserved
+    s4, step4 = hoomd.gsd_io.read_frame(path, 4)
+    chk, _ = make()
+    chk.run(200)
+    c = chk.state.get_snapshot()
+    assert step4 == 200 and np.array_equal(s4.particles.position, c.particles.position)
+    ke_chk, pe_chk, _ = chk.operations.integrator._thermo()
+    assert g.chunk(4, "log/md/compute/ThermodynamicQuantities/kinetic_energy")[0, 0] == ke_chk
+    assert g.chunk(4, "log/md/compute/ThermodynamicQuantities/potential_energy")[0, 0] == pe_chk
+    assert np.array_equal(s4.particles.image, c.particles.image)
+    rows = table.getvalue().splitlines()
+    assert len(rows) == 1 + 3 and rows[0].split()[-1] == "Simulation.timestep"
+    assert [r.split()[-1] for r in rows[1:]] == ["0", "100", "200"]
+    # restart from the trajectory's last frame
+    sim2 = hoomd.Simulation(device=hoomd.device.GPU(), seed=4)
+    sim2.create_state_from_gsd(path)
+    assert sim2.timestep == 200 and sim2.state.N_particles == 12 ** 3
