@@ -1,0 +1,181 @@
+// bond.cu — harmonic bond forces and the bond-exclusion filter of the neighbour list.
+//
+// Replaces PotentialBond<EvaluatorBondHarmonic>::computeForces (hoomd/md/PotentialBond.h:176-312,
+// GPU: gpu_compute_bond_forces_kernel hoomd/md/PotentialBondGPU.cuh) and NeighborList::filterNlist with
+// updateExListIdx (hoomd/md/NeighborList.cc:1448-1536, GPU: gpu_nlist_filter_kernel
+// hoomd/md/NeighborListGPU.cu:158-267).
+//
+// Bonds live in a table keyed by particle TAG (CSR: head[tag] .. head[tag + 1] -> partner tag, bond
+// type), so the re-ordering of particles at every rebuild does not touch it; a partner's current index
+// comes from rtag. Owner-computes: particle i sums its own bonds (F_i = F/r (r_i - r_j), half the bond
+// energy and half the virial), no atomics, fixed order -> bitwise reproducible.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace hb2
+    {
+constexpr int BOND_BLOCK = 128;
+
+// ACCUM: add to `force` / `virial` (the integrator's net force = pair force + bonds); otherwise
+// overwrite (the bond force's own arrays, for its getters).
+template<bool ACCUM>
+__global__ void __launch_bounds__(BOND_BLOCK)
+    bond_harmonic_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
+                         const uint32_t* __restrict__ rtag, uint32_t N, uint32_t Ntot,
+                         const uint32_t* __restrict__ head, const uint32_t* __restrict__ partner,
+                         const uint32_t* __restrict__ btype, const float2* __restrict__ params, BoxD box,
+                         float4* __restrict__ force, float* __restrict__ virial, size_t virial_pitch,
+                         const uint32_t* __restrict__ skip_flag, uint32_t* __restrict__ err)
+    {
+    if (skip_flag && *skip_flag)
+        return;
+    const uint32_t i = blockIdx.x * BOND_BLOCK + threadIdx.x;
+    if (i >= N)
+        return;
+    const uint32_t t = tag[i];
+    const uint32_t k0 = head[t], k1 = head[t + 1];
+    if (ACCUM && k0 == k1)
+        return;
+    const float4 pi = pos[i];
+    float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (uint32_t k = k0; k < k1; k++)
+        {
+        const uint32_t j = rtag[partner[k]];
+        if (j >= Ntot)
+            {
+            atomicMax(err, partner[k] + 1u); // "bond ... is incomplete" (PotentialBond.h:229-234)
+            continue;
+            }
+        const float4 pj = pos[j];
+        // separation in fp64 with the exact minimum image (a bond may cross the box; an fp32 +-L
+        // would cost half an ulp of L, i.e. k * 4e-6 of absolute force error)
+        double dx = (double)pi.x - (double)pj.x, dy = (double)pi.y - (double)pj.y,
+               dz = (double)pi.z - (double)pj.z;
+        min_image_exact(box, dx, dy, dz);
+        const float x = (float)dx, y = (float)dy, z = (float)dz;
+        const float rsq = x * x + y * y + z * z;
+        // hoomd/md/EvaluatorBondHarmonic.h:104-124
+        const float2 prm = params[btype[k]];
+        const float r = sqrtf(rsq);
+        float fdr = prm.x * (prm.y / r - 1.0f);
+        if (!isfinite(fdr))
+            fdr = 0.f;
+        const float d = prm.y - r;
+        fx += fdr * x;
+        fy += fdr * y;
+        fz += fdr * z;
+        pe += 0.5f * (0.5f * prm.x * d * d);
+        if (virial)
+            {
+            const float f2 = 0.5f * fdr;
+            v[0] += x * x * f2;
+            v[1] += x * y * f2;
+            v[2] += x * z * f2;
+            v[3] += y * y * f2;
+            v[4] += y * z * f2;
+            v[5] += z * z * f2;
+            }
+        }
+    if (ACCUM)
+        {
+        float4 f = force[i];
+        f.x += fx;
+        f.y += fy;
+        f.z += fz;
+        f.w += pe;
+        force[i] = f;
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                virial[q * virial_pitch + i] += v[q];
+        }
+    else
+        {
+        force[i] = make_float4(fx, fy, fz, pe);
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                virial[q * virial_pitch + i] = v[q];
+        }
+    }
+
+hb2_status launch_bond_harmonic(const BondArgs& a, bool accumulate, const hb2_box& box, cudaStream_t stream)
+    {
+    if (a.N == 0)
+        return HB2_OK;
+    const uint32_t blocks = (a.N + BOND_BLOCK - 1) / BOND_BLOCK;
+    if (accumulate)
+        bond_harmonic_kernel<true><<<blocks, BOND_BLOCK, 0, stream>>>(
+            a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, a.partner, a.btype, a.params, boxd(box), a.force,
+            a.virial, a.virial_pitch, a.skip_flag, a.err);
+    else
+        bond_harmonic_kernel<false><<<blocks, BOND_BLOCK, 0, stream>>>(
+            a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, a.partner, a.btype, a.params, boxd(box), a.force,
+            a.virial, a.virial_pitch, a.skip_flag, a.err);
+    HB2_CHECK_LAUNCH("bond_harmonic_kernel");
+    return HB2_OK;
+    }
+
+// One warp per row: entries whose particle is bonded to the row's owner are dropped, the row is
+// compacted in place (a 32-entry chunk is read completely before the chunk's survivors are written at
+// or below its start) and padded again with the dummy index up to a multiple of 32.
+__global__ void __launch_bounds__(128)
+    nlist_filter_bonds_kernel(uint32_t N, const uint32_t* __restrict__ tag,
+                              const uint32_t* __restrict__ rtag, const uint32_t* __restrict__ head,
+                              const uint32_t* __restrict__ partner, uint32_t* __restrict__ nlist,
+                              uint32_t pitch, uint32_t* __restrict__ n_neigh, uint32_t dummy_index)
+    {
+    const uint32_t i = (blockIdx.x * 128 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= N)
+        return;
+    const uint32_t t = tag[i];
+    const uint32_t k0 = head[t], n_ex = head[t + 1] - k0;
+    if (n_ex == 0)
+        return;
+    uint32_t* row = nlist + (size_t)i * pitch;
+    const uint32_t n = n_neigh[i];
+    uint32_t o = 0;
+    for (uint32_t c = 0; c < n; c += 32)
+        {
+        const uint32_t e = c + lane < n ? row[c + lane] : 0xffffffffu;
+        bool excluded = false;
+        for (uint32_t x0 = 0; x0 < n_ex; x0 += 32)
+            {
+            const uint32_t ex = x0 + lane < n_ex ? rtag[partner[k0 + x0 + lane]] : 0xfffffffeu;
+            const uint32_t m = min(32u, n_ex - x0);
+            for (uint32_t l = 0; l < m; l++)
+                excluded |= (e == __shfl_sync(0xffffffffu, ex, l));
+            }
+        const bool keep = (c + lane < n) && !excluded;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep)
+            row[o + __popc(bal & ((1u << lane) - 1u))] = e;
+        o += __popc(bal);
+        __syncwarp();
+        }
+    const uint32_t end = min((o + 31u) & ~31u, pitch);
+    const uint32_t old_end = min((n + 31u) & ~31u, pitch);
+    for (uint32_t k = o + lane; k < max(end, old_end); k += 32)
+        if (k < end)
+            row[k] = dummy_index;
+    if (lane == 0)
+        n_neigh[i] = o;
+    }
+
+hb2_status launch_nlist_filter_bonds(uint32_t N, const uint32_t* tag, const uint32_t* rtag,
+                                     const uint32_t* head, const uint32_t* partner, uint32_t* nlist,
+                                     uint32_t pitch, uint32_t* n_neigh, uint32_t dummy_index,
+                                     cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    const uint32_t blocks = (uint32_t)(((uint64_t)N * 32 + 127) / 128);
+    nlist_filter_bonds_kernel<<<blocks, 128, 0, stream>>>(N, tag, rtag, head, partner, nlist, pitch,
+                                                         n_neigh, dummy_index);
+    HB2_CHECK_LAUNCH("nlist_filter_bonds_kernel");
+    return HB2_OK;
+    }
+    } // namespace hb2

@@ -142,6 +142,9 @@ extern "C" void hb2_system_destroy(hb2_system* s)
         dev_free(s->tag[b]);
         }
     dev_free(s->rtag);
+    dev_free(s->d_bond_head);
+    dev_free(s->d_bond_partner);
+    dev_free(s->d_bond_type);
     dev_free(s->d_stage);
     if (s->h_stage)
         cudaFreeHost(s->h_stage);
@@ -856,6 +859,10 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
         HB2_TRY(ensure_capacity());
         HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
         }
+    // exclusions=('bond',): drop bonded pairs from the rows (hoomd/md/NeighborList.cc:1487-1536)
+    if (exclude_bonds && s->n_bonds)
+        HB2_TRY(launch_nlist_filter_bonds(N, s->tag[s->cur], s->rtag, s->d_bond_head, s->d_bond_partner,
+                                          d_nlist, pitch, d_n_neigh, Ntot, st));
     if (has_list && timestep > last_update_step)
         shortest_rebuild = std::min<uint64_t>(shortest_rebuild, timestep - last_update_step);
     has_list = true;
@@ -1245,6 +1252,7 @@ hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t*
     {
     hb2_system* s = sys;
     const uint32_t N = s->N;
+    extra_added = false;
     if (s->cap > cap_N)
         {
         dev_free(d_force);
@@ -1430,7 +1438,7 @@ static hb2_status pair_ensure(hb2_pair* p, bool need_energy = true)
     {
     // recompute when the particle order changed or nothing was computed yet
     // (hoomd/ForceCompute.cc:562-574: "sorted / new timestep / flags changed")
-    if (!p->computed || p->computed_epoch != p->sys->order_epoch
+    if (!p->computed || p->extra_added || p->computed_epoch != p->sys->order_epoch
         || (p->sys->compute_virial && !p->virial_valid) || (need_energy && !p->energy_valid))
         return p->compute(p->sys->timestep);
     return HB2_OK;
@@ -1670,6 +1678,290 @@ extern "C" hb2_status hb2_pair_get_additional(hb2_pair* p, double* energy, doubl
 // =================================================================================================
 // integrator
 // =================================================================================================
+// ---------------------------------------------------------------------------------- bonds ----
+extern "C" hb2_status hb2_system_set_bonds(hb2_system* s, uint32_t n_bonds, const uint32_t* group,
+                                           const uint32_t* typeid_, uint32_t n_bond_types)
+    {
+    if (!s || (n_bonds && (!group || !typeid_)))
+        return HB2_ERR_INVALID;
+    if (s->dom.active)
+        {
+        set_error("bonds are not supported with a domain decomposition (bond data does not migrate)");
+        return HB2_ERR_INVALID;
+        }
+    if (!s->pos[0] || !s->rtag)
+        {
+        set_error("hb2_system_set_bonds: set the particles first");
+        return HB2_ERR_INVALID;
+        }
+    const uint32_t N = s->N;
+    std::vector<uint32_t> head((size_t)N + 1, 0u), partner(2 * (size_t)n_bonds), type(2 * (size_t)n_bonds);
+    for (uint32_t k = 0; k < n_bonds; k++)
+        {
+        const uint32_t a = group[2 * k], b = group[2 * k + 1];
+        if (a >= N || b >= N || a == b || typeid_[k] >= n_bond_types)
+            {
+            set_error("hb2_system_set_bonds: bond " + std::to_string(k)
+                      + " names a particle tag or a bond type out of range");
+            return HB2_ERR_INVALID;
+            }
+        head[a + 1]++;
+        head[b + 1]++;
+        }
+    for (uint32_t t = 0; t < N; t++)
+        head[t + 1] += head[t];
+    std::vector<uint32_t> fill(N, 0u);
+    for (uint32_t k = 0; k < n_bonds; k++)
+        {
+        const uint32_t a = group[2 * k], b = group[2 * k + 1];
+        partner[head[a] + fill[a]] = b;
+        type[head[a] + fill[a]++] = typeid_[k];
+        partner[head[b] + fill[b]] = a;
+        type[head[b] + fill[b]++] = typeid_[k];
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(s->d_bond_head);
+    dev_free(s->d_bond_partner);
+    dev_free(s->d_bond_type);
+    s->d_bond_head = s->d_bond_partner = s->d_bond_type = nullptr;
+    HB2_TRY(dev_alloc(&s->d_bond_head, head.size()));
+    HB2_TRY(dev_alloc(&s->d_bond_partner, std::max<size_t>(1, partner.size())));
+    HB2_TRY(dev_alloc(&s->d_bond_type, std::max<size_t>(1, type.size())));
+    HB2_CUDA(cudaMemcpy(s->d_bond_head, head.data(), sizeof(uint32_t) * head.size(), cudaMemcpyHostToDevice));
+    if (n_bonds)
+        {
+        HB2_CUDA(cudaMemcpy(s->d_bond_partner, partner.data(), sizeof(uint32_t) * partner.size(),
+                            cudaMemcpyHostToDevice));
+        HB2_CUDA(cudaMemcpy(s->d_bond_type, type.data(), sizeof(uint32_t) * type.size(),
+                            cudaMemcpyHostToDevice));
+        }
+    s->n_bonds = n_bonds;
+    s->n_bond_types = n_bond_types;
+    s->bond_epoch++;
+    for (auto* nl : s->nlists)
+        nl->force_update = true; // the exclusions changed
+    for (auto* pr : s->pairs)
+        pr->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds)
+    {
+    if (!nl)
+        return HB2_ERR_INVALID;
+    nl->exclude_bonds = exclude_bonds != 0;
+    nl->force_update = true;
+    for (auto* pr : nl->consumers)
+        pr->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_bond_create(hb2_bond** out, hb2_system* s)
+    {
+    if (!out || !s)
+        return HB2_ERR_INVALID;
+    hb2_bond* b = new hb2_bond();
+    b->sys = s;
+    HB2_CUDA(cudaSetDevice(s->device));
+    hb2_status st = dev_alloc(&b->d_err, 1);
+    if (st != HB2_OK)
+        {
+        delete b;
+        return st;
+        }
+    cudaMemset(b->d_err, 0, sizeof(uint32_t));
+    *out = b;
+    return HB2_OK;
+    }
+
+extern "C" void hb2_bond_destroy(hb2_bond* b)
+    {
+    if (!b)
+        return;
+    cudaSetDevice(b->sys->device);
+    cudaStreamSynchronize(b->sys->stream);
+    dev_free(b->d_params);
+    dev_free(b->d_force);
+    dev_free(b->d_virial);
+    dev_free(b->d_err);
+    delete b;
+    }
+
+extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, double k, double r0)
+    {
+    if (!b)
+        return HB2_ERR_INVALID;
+    if (type >= b->k.size())
+        {
+        b->k.resize(type + 1, 0.0);
+        b->r0.resize(type + 1, 0.0);
+        b->have.resize(type + 1, 0);
+        }
+    b->k[type] = k;
+    b->r0[type] = r0;
+    b->have[type] = 1;
+    b->params_dirty = true;
+    return HB2_OK;
+    }
+
+hb2_status hb2_bond::upload_params()
+    {
+    const uint32_t nt = sys->n_bond_types;
+    for (uint32_t t = 0; t < nt; t++)
+        if (t >= have.size() || !have[t])
+            {
+            set_error("bond.harmonic: parameters of bond type " + std::to_string(t) + " are not set");
+            return HB2_ERR_INVALID;
+            }
+    std::vector<float2> h(std::max<uint32_t>(1, nt));
+    for (uint32_t t = 0; t < nt; t++)
+        h[t] = make_float2((float)k[t], (float)r0[t]);
+    dev_free(d_params);
+    d_params = nullptr;
+    HB2_TRY(dev_alloc(&d_params, h.size()));
+    HB2_CUDA(cudaMemcpyAsync(d_params, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, sys->stream));
+    HB2_CUDA(cudaStreamSynchronize(sys->stream));
+    params_dirty = false;
+    return HB2_OK;
+    }
+
+hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, bool accumulate,
+                            const uint32_t* skip_flag)
+    {
+    hb2_system* s = sys;
+    if (s->dom.active)
+        {
+        set_error("bonds are not supported with a domain decomposition");
+        return HB2_ERR_INVALID;
+        }
+    if (params_dirty)
+        HB2_TRY(upload_params());
+    if (s->n_bonds == 0 && accumulate)
+        return HB2_OK;
+    if (!s->d_bond_head)
+        {
+        // no bond table was ever set: an empty one
+        HB2_TRY(hb2_system_set_bonds(s, 0, nullptr, nullptr, 0));
+        }
+    BondArgs a;
+    a.pos = s->pos[s->cur];
+    a.tag = s->tag[s->cur];
+    a.rtag = s->rtag;
+    a.N = s->N;
+    a.Ntot = s->N + s->Ng;
+    a.head = s->d_bond_head;
+    a.partner = s->d_bond_partner;
+    a.btype = s->d_bond_type;
+    a.params = d_params;
+    a.force = force;
+    a.virial = s->compute_virial ? virial : nullptr;
+    a.virial_pitch = virial_pitch;
+    a.skip_flag = skip_flag;
+    a.err = d_err;
+    return launch_bond_harmonic(a, accumulate, s->box, s->stream);
+    }
+
+hb2_status hb2_bond::compute_own()
+    {
+    hb2_system* s = sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    if (s->cap > cap_N)
+        {
+        dev_free(d_force);
+        dev_free(d_virial);
+        d_force = nullptr;
+        d_virial = nullptr;
+        HB2_TRY(dev_alloc(&d_force, s->cap));
+        HB2_TRY(dev_alloc(&d_virial, 6 * (size_t)s->cap));
+        cap_N = s->cap;
+        }
+    HB2_TRY(launch(d_force, d_virial, cap_N, false, nullptr));
+    return check_complete();
+    }
+
+hb2_status hb2_bond::check_complete()
+    {
+    uint32_t e = 0;
+    HB2_CUDA(cudaMemcpyAsync(&e, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, sys->stream));
+    HB2_CUDA(cudaStreamSynchronize(sys->stream));
+    if (e)
+        {
+        HB2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), sys->stream));
+        set_error("Error: a bond with particle " + std::to_string(e - 1) + " is incomplete.");
+        return HB2_ERR_INVALID;
+        }
+    return HB2_OK;
+    }
+
+// per-particle results in tag order: forces N x 3, energies N, virials N x 6 (any may be null)
+extern "C" hb2_status hb2_bond_get(hb2_bond* b, double* forces3, double* energies, double* virials6,
+                                   double* energy_total)
+    {
+    if (!b)
+        return HB2_ERR_INVALID;
+    hb2_system* s = b->sys;
+    HB2_TRY(b->compute_own());
+    const uint32_t N = s->N;
+    std::vector<float4> f(N);
+    std::vector<uint32_t> tag(N);
+    std::vector<float> vir;
+    HB2_CUDA(cudaMemcpyAsync(f.data(), b->d_force, sizeof(float4) * N, cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(tag.data(), s->tag[s->cur], sizeof(uint32_t) * N, cudaMemcpyDeviceToHost,
+                             s->stream));
+    if (virials6)
+        {
+        if (!s->compute_virial)
+            {
+            set_error("virials are not computed unless the pressure flag is set "
+                      "(Simulation.always_compute_pressure)");
+            return HB2_ERR_INVALID;
+            }
+        vir.resize(6 * (size_t)b->cap_N);
+        HB2_CUDA(cudaMemcpyAsync(vir.data(), b->d_virial, sizeof(float) * vir.size(), cudaMemcpyDeviceToHost,
+                                 s->stream));
+        }
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    double tot = 0.0;
+    for (uint32_t i = 0; i < N; i++)
+        {
+        const uint32_t t = tag[i];
+        if (forces3)
+            {
+            forces3[3 * (size_t)t] = f[i].x;
+            forces3[3 * (size_t)t + 1] = f[i].y;
+            forces3[3 * (size_t)t + 2] = f[i].z;
+            }
+        if (energies)
+            energies[t] = f[i].w;
+        if (virials6)
+            for (int q = 0; q < 6; q++)
+                virials6[6 * (size_t)t + q] = vir[(size_t)q * b->cap_N + i];
+        tot += f[i].w;
+        }
+    if (energy_total)
+        *energy_total = tot;
+    return HB2_OK;
+    }
+
+static hb2_status integrator_add_bonds(hb2_integrator* it, hb2_pair* pf, const uint32_t* skip_flag)
+    {
+    for (auto* b : it->bonds)
+        HB2_TRY(b->launch(pf->d_force, pf->d_virial, pf->cap_N, true, skip_flag));
+    if (!it->bonds.empty())
+        pf->extra_added = true;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_add_bond(hb2_integrator* it, hb2_bond* b)
+    {
+    if (!it || !b || b->sys != it->sys)
+        return HB2_ERR_INVALID;
+    it->bonds.push_back(b);
+    it->prepared = false;
+    return HB2_OK;
+    }
+
 extern "C" hb2_status hb2_integrator_create(hb2_integrator** out, hb2_system* s, double dt)
     {
     if (!out || !s)
@@ -1781,9 +2073,10 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     HB2_CUDA(cudaEventRecord(it->ev0, st));
     // prepRun (hoomd/md/IntegratorTwoStep.cc:226-281): net force at the current timestep
     if (!it->prepared || !pf->computed || pf->computed_epoch != s->order_epoch
-        || pf->computed_step != s->timestep)
+        || pf->computed_step != s->timestep || (!it->bonds.empty() && !pf->extra_added))
         {
         HB2_TRY(pf->compute(s->timestep));
+        HB2_TRY(integrator_add_bonds(it, pf, nullptr));
         it->prepared = true;
         it->total_valid = false; // accelerations restart from the net force (computeAccelerations)
         }
@@ -1852,12 +2145,14 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             if (s->dom.active)
                 HB2_TRY(domain_update_ghosts(s));
             HB2_TRY(pf->launch(t + 1, step + 1 == nsteps, nl->d_conditions + 3));
+            HB2_TRY(integrator_add_bonds(it, pf, nl->d_conditions + 3));
             HB2_CUDA(cudaEventSynchronize(s->flag_copied));
             flag = nl->h_conditions[3] != 0;
             if (flag)
                 {
                 HB2_TRY(nl->rebuild(t + 1));
                 HB2_TRY(pf->launch(t + 1, step + 1 == nsteps, nullptr));
+                HB2_TRY(integrator_add_bonds(it, pf, nullptr));
                 }
             }
         else
@@ -1878,6 +2173,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             hb2_status cst = pf->compute(t + 1, check, flag, step + 1 == nsteps);
             s->mid_event = nullptr;
             HB2_TRY(cst);
+            HB2_TRY(integrator_add_bonds(it, pf, nullptr));
             }
         if (it->profiling)
             {
@@ -1921,6 +2217,8 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     HB2_CUDA(cudaMemcpyAsync(s->d_timestep, &s->timestep, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     HB2_CUDA(cudaEventRecord(it->ev1, st));
     HB2_CUDA(cudaStreamSynchronize(st));
+    for (auto* b : it->bonds)
+        HB2_TRY(b->check_complete());
     HB2_CUDA(cudaEventElapsedTime(&it->last_ms, it->ev0, it->ev1));
     if (it->profiling)
         {
@@ -1977,6 +2275,18 @@ extern "C" hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic,
     HB2_CUDA(cudaSetDevice(s->device));
     double v[7];
     HB2_TRY(sums7(it->forces[0], v));
+    for (auto* b : it->bonds)
+        {
+        // the bond force's own arrays, reduced like the pair force's
+        HB2_TRY(b->compute_own());
+        double w[7];
+        HB2_TRY(launch_reduce_energy(b->d_force, s->compute_virial ? b->d_virial : nullptr, b->cap_N, s->N,
+                                     s->d_partial, s->d_ticket + 1, s->d_sums + 1, s->stream));
+        HB2_CUDA(cudaMemcpyAsync(w, s->d_sums + 1, sizeof(double) * 7, cudaMemcpyDeviceToHost, s->stream));
+        HB2_CUDA(cudaStreamSynchronize(s->stream));
+        for (int q = 0; q < 7; q++)
+            v[q] += w[q];
+        }
     double ke = 0.0;
     HB2_TRY(launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket + 2, s->d_sums + 9,
                            s->stream));

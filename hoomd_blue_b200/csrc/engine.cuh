@@ -75,6 +75,13 @@ struct hb2_system
     uint32_t* d_ticket = nullptr;
     double* d_sums = nullptr; // [0] KE, [1..7] PE + virial, [8] rescale factor
 
+    // bond table keyed by particle tag (CSR): partners' tags and bond types (csrc/bond.cu)
+    uint32_t n_bonds = 0, n_bond_types = 0;
+    uint32_t* d_bond_head = nullptr;
+    uint32_t* d_bond_partner = nullptr;
+    uint32_t* d_bond_type = nullptr;
+    uint64_t bond_epoch = 0; // bumped by hb2_system_set_bonds
+
     std::vector<hb2_nlist*> nlists;
     std::vector<hb2_pair*> pairs;
     cudaEvent_t mid_event = nullptr; // recorded between the nlist update and the force launch
@@ -122,6 +129,7 @@ struct hb2_nlist
     uint32_t* d_conditions = nullptr; // [0] max n_neigh, [1] nan idx+1, [2] oob idx+1, [3] rebuild flag
     uint32_t* h_conditions = nullptr; // pinned mirror
 
+    bool exclude_bonds = true; // exclusions=('bond',), the reference's default (hoomd/md/nlist.py:87-102)
     bool force_update = true;
     bool has_list = false;
     uint64_t num_builds = 0;
@@ -168,6 +176,7 @@ struct hb2_pair
     bool energy_valid = false; // the last force pass also accumulated per-particle energies
     bool energy_every_step = false;
     bool computed = false;
+    bool extra_added = false; // the integrator added the bond forces into d_force (net force)
     uint64_t computed_step = 0, computed_epoch = 0;
 
     hb2_status upload_params();
@@ -176,11 +185,33 @@ struct hb2_pair
     hb2_status launch(uint64_t timestep, bool want_energy, const uint32_t* skip_flag);
     };
 
+// PotentialBond<EvaluatorBondHarmonic> (hoomd/md/PotentialBond.h): parameters per bond type, own
+// force / virial arrays for its getters; inside the step loop its forces are added to the pair
+// force's array (the net force).
+struct hb2_bond
+    {
+    hb2_system* sys = nullptr;
+    std::vector<double> k, r0;
+    std::vector<char> have;
+    bool params_dirty = true;
+    float2* d_params = nullptr;
+    float4* d_force = nullptr;
+    float* d_virial = nullptr;
+    uint32_t cap_N = 0;
+    uint32_t* d_err = nullptr;
+    hb2_status upload_params();
+    hb2_status launch(float4* force, float* virial, size_t virial_pitch, bool accumulate,
+                      const uint32_t* skip_flag);
+    hb2_status compute_own();
+    hb2_status check_complete();
+    };
+
 struct hb2_integrator
     {
     hb2_system* sys = nullptr;
     double dt = 0.005;
     std::vector<hb2_pair*> forces;
+    std::vector<hb2_bond*> bonds;
     int thermostat = 0; // 0 NVE, 1 ConstantVolume + Bussi, 2 Langevin method
     double kT = 1.0, tau = 0.0;
     float* d_gamma_coeff = nullptr; // Langevin: (gamma, sqrt(6 gamma kT / dt)) per type

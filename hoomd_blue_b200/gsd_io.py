@@ -120,6 +120,20 @@ def read_frame(filename, frame=-1):
         c = g.chunk(f, "particles/" + name, cur_n=n)
         if c is not None:
             arr[...] = c.reshape(arr.shape)
+    nb = g.chunk(f, "bonds/N")
+    nb = int(nb[0, 0]) if nb is not None else 0
+    if nb:
+        snap.bonds.N = nb
+        t = g.chunk(f, "bonds/types")
+        snap.bonds.types = ([bytes(row).split(b"\0")[0].decode() for row in t.astype(np.uint8)]
+                            if t is not None else ["bondA"])
+        tid = g.chunk(f, "bonds/typeid", cur_n=nb)
+        if tid is not None:
+            snap.bonds.typeid[:] = tid.reshape(-1)
+        grp = g.chunk(f, "bonds/group", cur_n=nb)
+        if grp is None:
+            raise RuntimeError(f"{filename}: bonds/N = {nb} but bonds/group is missing")
+        snap.bonds.group[:] = grp.reshape(nb, 2)
     return snap, step
 
 
@@ -144,6 +158,15 @@ def frame_chunks(snap, step, dynamic=None, first=True, log=None):
         out += [("particles/N", np.array([[n]], dtype=np.uint32)), ("particles/types", types),
                 ("particles/typeid", np.asarray(p.typeid, dtype=np.uint32).reshape(n, 1)),
                 ("particles/mass", np.asarray(p.mass, dtype=np.float32).reshape(n, 1))]
+    bonds = getattr(snap, "bonds", None)
+    if bonds is not None and bonds.N and (first or "topology" in dynamic):
+        tw = max(len(t) for t in bonds.types) + 1
+        btypes = np.zeros((len(bonds.types), tw), dtype=np.int8)
+        for i, t in enumerate(bonds.types):
+            btypes[i, :len(t)] = np.frombuffer(t.encode(), dtype=np.int8)
+        out += [("bonds/N", np.array([[bonds.N]], dtype=np.uint32)), ("bonds/types", btypes),
+                ("bonds/typeid", np.asarray(bonds.typeid, dtype=np.uint32).reshape(-1, 1)),
+                ("bonds/group", np.asarray(bonds.group, dtype=np.int32).reshape(-1, 2))]
     if first or "property" in dynamic:
         out.append(("particles/position", np.asarray(p.position, dtype=np.float32).reshape(n, 3)))
     if first or "momentum" in dynamic:

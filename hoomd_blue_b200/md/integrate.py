@@ -25,20 +25,41 @@ class Integrator:
     def _attach(self, sim):
         if self._h is not None:
             return
-        if len(self.forces) != 1:
-            raise NotImplementedError("this path carries exactly one pair force")
-        if len(self.methods) != 1 or not isinstance(self.methods[0], (ConstantVolume, Langevin)):
+        from .bond import Bond
+        from .pair import Pair, LJ
+        from .nlist import Cell
+        bonds = [f for f in self.forces if isinstance(f, Bond)]
+        pairs = [f for f in self.forces if not isinstance(f, Bond)]
+        if len(pairs) > 1 or (pairs and not isinstance(pairs[0], Pair)):
+            raise NotImplementedError("this path carries one pair force (plus bond forces)")
+        if not pairs:
+            # the net-force array belongs to the pair force: a bond-only integrator gets a pair force
+            # that evaluates nothing (epsilon = 0) over a list without exclusions
+            hidden = LJ(nlist=Cell(buffer=0.4, exclusions=()), default_r_cut=1.0)
+            for a in sim.state.particle_types:
+                for b in sim.state.particle_types:
+                    hidden.params[(a, b)] = dict(epsilon=0.0, sigma=1.0)
+            pairs = [hidden]
+            self._hidden_pair = hidden
+        if len(self.methods) > 1 or (self.methods
+                                     and not isinstance(self.methods[0], (ConstantVolume, Langevin))):
             raise NotImplementedError("this path integrates with one ConstantVolume or Langevin method")
         L = _lib.lib()
         h = C.c_void_p()
         check(L.hb2_integrator_create(C.byref(h), sim.state._h, self.dt))
         self._h = h
         self._sim = sim
-        f = self.forces[0]
+        f = pairs[0]
+        self._pair = f
         f._attach(sim)
         check(L.hb2_integrator_add_force(h, f._h))
-        th = self.methods[0].thermostat
-        if isinstance(self.methods[0], Langevin):
+        for b in bonds:
+            b._attach(sim)
+            check(L.hb2_integrator_add_bond(h, b._h))
+        self._bonds = bonds
+        # (no method: forces are computed, particles do not move — only run(0) is meaningful)
+        th = self.methods[0].thermostat if self.methods else None
+        if self.methods and isinstance(self.methods[0], Langevin):
             m = self.methods[0]
             gamma = np.array([m.gamma[t] for t in sim.state.particle_types], dtype=np.float64)
             check(L.hb2_integrator_set_langevin(h, m.kT, _lib.ptr(gamma, C.c_double), len(gamma)))
@@ -51,11 +72,16 @@ class Integrator:
         if self._h is not None:
             _lib.lib().hb2_integrator_destroy(self._h)
             self._h = None
-        for f in self.forces:
+        for f in self.forces + ([self._hidden_pair] if getattr(self, "_hidden_pair", None) else []):
             f._detach()
-            f.nlist._detach()
+            if hasattr(f, "nlist"):
+                f.nlist._detach()
 
     def _run(self, steps):
+        if steps > 0 and not self.methods:
+            raise NotImplementedError("an integrator without a method can only run(0) on this path")
+        for b in getattr(self, "_bonds", []):
+            b._sync()
         check(_lib.lib().hb2_integrator_run(self._h, steps))
 
     def _last_run_ms(self):

@@ -38,6 +38,7 @@ class NeighborList:
                                           self.rebuild_check_delay, int(self.check_dist)))
         self._h = h
         self._sim = sim
+        check(_lib.lib().hb2_nlist_set_exclusions(h, int("bond" in self.exclusions)))
 
     def _detach(self):
         if self._h is not None:

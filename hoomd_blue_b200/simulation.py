@@ -60,13 +60,36 @@ class _Particles:
         self._alloc(self._N)
 
 
+class _Bonds:
+    """hoomd.Snapshot.bonds: N, types, typeid (N,), group (N, 2) member tags (hoomd/snapshot.py)."""
+
+    def __init__(self):
+        self.types = []
+        self._N = 0
+        self._alloc(0)
+
+    def _alloc(self, n):
+        self.typeid = np.zeros((n,), dtype=np.uint32)
+        self.group = np.zeros((n, 2), dtype=np.uint32)
+
+    @property
+    def N(self):
+        return self._N
+
+    @N.setter
+    def N(self, n):
+        self._N = int(n)
+        self._alloc(self._N)
+
+
 class Snapshot:
-    """hoomd.Snapshot (configuration + particles). pinned=True (not in the reference) allocates the
+    """hoomd.Snapshot (configuration + particles + bonds). pinned=True (not in the reference) allocates the
     particle arrays in page-locked memory so that set_snapshot / get_snapshot copy by DMA."""
 
     def __init__(self, communicator=None, pinned=False):
         self.configuration = _Configuration()
         self.particles = _Particles(pinned)
+        self.bonds = _Bonds()
         self.communicator = communicator
 
     @classmethod
@@ -199,6 +222,20 @@ class State:
         check(L.hb2_system_set_particles(self._h, pos.shape[0], ptr(pos, C.c_float),
                                          ptr(vel, C.c_float), ptr(mass, C.c_float),
                                          ptr(tid, C.c_uint32), ptr(img, C.c_int32)))
+        self._set_bonds(getattr(snapshot, "bonds", None))
+
+    def _set_bonds(self, bonds):
+        """BondData of the snapshot (single GPU): the table is kept on the device keyed by tag."""
+        L = _lib.lib()
+        n = 0 if bonds is None else int(bonds.N)
+        self._bond_types = [] if bonds is None else list(bonds.types)
+        self._bond_typeid = np.zeros(0, np.uint32) if n == 0 else np.ascontiguousarray(bonds.typeid, np.uint32)
+        self._bond_group = np.zeros((0, 2), np.uint32) if n == 0 else np.ascontiguousarray(bonds.group, np.uint32)
+        if n == 0 and not getattr(self, "_had_bonds", False):
+            return
+        self._had_bonds = True
+        check(L.hb2_system_set_bonds(self._h, n, ptr(self._bond_group, C.c_uint32),
+                                     ptr(self._bond_typeid, C.c_uint32), len(self._bond_types)))
 
     def _get_local(self, pinned=False, into=None):
         """LocalParticles (tag, position, velocity, mass, typeid, image — also unpackable as that
@@ -229,6 +266,11 @@ class State:
         if s.particles.N != n:
             s.particles.N = n
         s.particles.types = list(self._types)
+        if getattr(self, "_bond_types", None):
+            s.bonds.N = len(self._bond_typeid)
+            s.bonds.types = list(self._bond_types)
+            s.bonds.typeid[:] = self._bond_typeid
+            s.bonds.group[:] = self._bond_group
         p = s.particles
         if self._simulation.device.communicator.num_ranks > 1:
             # gathered by tag (hoomd/ParticleData.cc takeSnapshot does the same with MPI gathers;

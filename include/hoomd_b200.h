@@ -168,6 +168,7 @@ hb2_status hb2_gpu_nve_step_two(float* d_vel4, const float* d_force4, uint32_t N
 typedef struct hb2_system hb2_system;         /* ~ SystemDefinition + ParticleData (hoomd/ParticleData.h:1285) */
 typedef struct hb2_nlist hb2_nlist;           /* ~ NeighborListGPUBinned (hoomd/md/NeighborList.h:121) */
 typedef struct hb2_pair hb2_pair;             /* ~ PotentialPairGPU<evaluator> (hoomd/md/PotentialPairGPU.h:89) */
+typedef struct hb2_bond hb2_bond;             /* ~ PotentialBond<EvaluatorBondHarmonic> */
 typedef struct hb2_integrator hb2_integrator; /* ~ IntegratorTwoStep + TwoStepConstantVolume */
 
 /* device: CUDA ordinal. ntypes: number of particle types. seed: hoomd.Simulation(seed) (16 bit used,
@@ -283,6 +284,23 @@ hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p);
 /* thermostat: 0 none (NVE), 1 Bussi(kT, tau) (hoomd/md/Thermostat.h:337-447; tau = 0 is allowed). */
 hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat, double kT,
                                               double tau);
+/* Bonds (single GPU). hb2_system_set_bonds: BondData of the snapshot
+ * (hoomd/BondedGroupData.h) — `group` holds 2 member TAGS per bond, `typeid_` the bond types; call
+ * after the particles are set. hb2_nlist_set_exclusions: exclusions=('bond',) (the reference's default,
+ * hoomd/md/nlist.py:87-102; hoomd/md/NeighborList.cc:569-640,1487-1536) drops bonded pairs from the
+ * list. hb2_bond_*: hoomd.md.bond.Harmonic (hoomd/md/PotentialBond.h:176-312,
+ * hoomd/md/EvaluatorBondHarmonic.h) with (k, r0) per bond type; hb2_bond_get returns per-particle
+ * forces (N x 3), energies (N), virials (N x 6) in tag order and the total energy (any may be null).
+ * hb2_integrator_add_bond: the bond forces are added to the pair force (net force) every step. */
+hb2_status hb2_system_set_bonds(hb2_system* sys, uint32_t n_bonds, const uint32_t* group,
+                                const uint32_t* typeid_, uint32_t n_bond_types);
+hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds);
+hb2_status hb2_bond_create(hb2_bond** out, hb2_system* sys);
+void hb2_bond_destroy(hb2_bond* b);
+hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, double k, double r0);
+hb2_status hb2_bond_get(hb2_bond* b, double* forces3, double* energies, double* virials6,
+                        double* energy_total);
+hb2_status hb2_integrator_add_bond(hb2_integrator* it, hb2_bond* b);
 /* hoomd.md.methods.Langevin(filter=All, kT) (hoomd/md/methods/methods.py, hoomd/md/TwoStepLangevin.cc:
  * 47-82 step one = the NVE half step, :213-292 step two with the BD force): translational degrees of
  * freedom, 3D, one drag coefficient per particle type (`gamma[ntypes]`), no reservoir tally. Replaces

@@ -573,6 +573,104 @@ double orc_lj_tail_correction(const double* params, const double* r_cut, uint32_
     return e;
     }
 
+/* ----------------------------------------------------------- bonds, exclusions ---- */
+
+void orc_filter_bond_exclusions(uint32_t n, uint32_t* n_neigh, const uint64_t* head, uint32_t* nlist,
+                                const uint32_t* tag, const uint32_t* rtag, const uint32_t* bond_group,
+                                uint32_t n_bonds)
+    {
+    /* addExclusionsFromBonds: addExclusion(tag_a, tag_b) for every bond (duplicates are ignored by
+       isExcluded, hoomd/md/NeighborList.cc:569-640); exclusion lists by tag, then by index, then the
+       filter of :1487-1536 */
+    uint32_t max_tag = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (tag[i] > max_tag)
+            max_tag = tag[i];
+    uint32_t* cnt = (uint32_t*)calloc((size_t)max_tag + 2, sizeof(uint32_t));
+    for (uint32_t k = 0; k < n_bonds; k++)
+        {
+        cnt[bond_group[2 * k] + 1]++;
+        cnt[bond_group[2 * k + 1] + 1]++;
+        }
+    for (uint32_t t = 0; t <= max_tag; t++)
+        cnt[t + 1] += cnt[t];
+    uint32_t* ex = (uint32_t*)malloc(sizeof(uint32_t) * (2 * (size_t)n_bonds + 1));
+    uint32_t* fill = (uint32_t*)calloc((size_t)max_tag + 1, sizeof(uint32_t));
+    for (uint32_t k = 0; k < n_bonds; k++)
+        {
+        const uint32_t a = bond_group[2 * k], c = bond_group[2 * k + 1];
+        ex[cnt[a] + fill[a]++] = c;
+        ex[cnt[c] + fill[c]++] = a;
+        }
+    for (uint32_t idx = 0; idx < n; idx++)
+        {
+        const uint32_t t = tag[idx];
+        const uint32_t n_ex = cnt[t + 1] - cnt[t];
+        uint32_t new_n = 0;
+        for (uint32_t q = 0; q < n_neigh[idx]; q++)
+            {
+            const uint32_t cur = nlist[head[idx] + q];
+            int excluded = 0;
+            for (uint32_t e = 0; e < n_ex; e++)
+                if (rtag[ex[cnt[t] + e]] == cur)
+                    {
+                    excluded = 1;
+                    break;
+                    }
+            if (!excluded)
+                nlist[head[idx] + new_n++] = cur;
+            }
+        n_neigh[idx] = new_n;
+        }
+    free(cnt);
+    free(ex);
+    free(fill);
+    }
+
+int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                      const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
+                      const double* params, double* force, double* virial)
+    {
+    /* hoomd/md/PotentialBond.h:176-312 */
+    memset(force, 0, sizeof(double) * 4 * (size_t)N);
+    memset(virial, 0, sizeof(double) * 6 * (size_t)N);
+    for (uint32_t i = 0; i < n_bonds; i++)
+        {
+        const uint32_t ia = rtag[bond_group[2 * i]], ib = rtag[bond_group[2 * i + 1]];
+        if (ia >= N || ib >= N)
+            return 1 + (int)i;
+        double dx[3];
+        for (int d = 0; d < 3; d++)
+            dx[d] = pos[3 * (size_t)ib + d] - pos[3 * (size_t)ia + d];
+        orc_min_image(b, dx);
+        const double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+        /* hoomd/md/EvaluatorBondHarmonic.h:104-124 */
+        const double K = params[2 * bond_type[i]], r_0 = params[2 * bond_type[i] + 1];
+        const double r = sqrt(rsq);
+        double force_divr = K * (r_0 / r - 1.0);
+        if (!isfinite(force_divr))
+            force_divr = 0.0;
+        double bond_eng = 0.5 * K * (r_0 - r) * (r_0 - r);
+        bond_eng *= 0.5;
+        const double f2 = 0.5 * force_divr;
+        const double v[6] = {dx[0] * dx[0] * f2, dx[0] * dx[1] * f2, dx[0] * dx[2] * f2,
+                             dx[1] * dx[1] * f2, dx[1] * dx[2] * f2, dx[2] * dx[2] * f2};
+        for (int d = 0; d < 3; d++)
+            {
+            force[4 * (size_t)ib + d] += force_divr * dx[d];
+            force[4 * (size_t)ia + d] -= force_divr * dx[d];
+            }
+        force[4 * (size_t)ib + 3] += bond_eng;
+        force[4 * (size_t)ia + 3] += bond_eng;
+        for (int q = 0; q < 6; q++)
+            {
+            virial[(size_t)q * N + ib] += v[q];
+            virial[(size_t)q * N + ia] += v[q];
+            }
+        }
+    return 0;
+    }
+
 /* ---------------------------------------------------------------------- RNG ---- */
 
 void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])

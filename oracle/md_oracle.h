@@ -95,6 +95,21 @@ int orc_eval_dpd_conservative(double rsq, double rcutsq, double A, double* force
 double orc_lj_tail_correction(const double* params, const double* r_cut, uint32_t ntypes,
                               const uint32_t* n_per_type, double volume, double* virial_diag);
 
+/* Exclusions from bonds and the filter pass (hoomd/md/NeighborList.cc:569-640 addExclusionsFromBonds,
+ * :1448-1485 updateExListIdx, :1487-1536 filterNlist): every bonded pair (tags a, b) is removed from
+ * both rows; rows are compacted in place (head stays, n_neigh shrinks). rtag[tag] = index. */
+void orc_filter_bond_exclusions(uint32_t n, uint32_t* n_neigh, const uint64_t* head, uint32_t* nlist,
+                                const uint32_t* tag, const uint32_t* rtag, const uint32_t* bond_group,
+                                uint32_t n_bonds);
+
+/* PotentialBond<EvaluatorBondHarmonic> (hoomd/md/PotentialBond.h:176-312,
+ * hoomd/md/EvaluatorBondHarmonic.h:104-124): V = k/2 (r - r0)^2, half the energy and half the virial
+ * to each member. params = (k, r0) per bond type; bond_group holds member TAGS. force N x 4 and virial
+ * 6 x N are overwritten. Returns 0, or 1 + the index of an incomplete bond. */
+int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                      const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
+                      const double* params, double* force, double* virial);
+
 /* RNG: Philox4x32-10 (Salmon et al., SC'11; hoomd/extern/random123 commit a2c4f04) and HOOMD's
  * Seed/Counter packing hoomd/RandomNumbers.h:136-199 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -270,6 +270,50 @@ def step_two(vel, accel, mass, force4, dt, rescale=1.0):
                        C.c_double(rescale))
 
 
+def filter_bond_exclusions(n_neigh, head, nl, bond_group, tags=None):
+    """hoomd/md/NeighborList.cc:569-640,1448-1536: returns (n_neigh, head, nlist) with every bonded
+    pair removed. The reference compacts each row in place under the old head list; the rows are packed
+    here afterwards so that the result has the layout nlist() returns. bond_group: (n_bonds, 2) tags."""
+    n = n_neigh.size
+    tags = np.arange(n, dtype=np.uint32) if tags is None else _u32(tags)
+    rtag = np.zeros(int(tags.max()) + 1 if n else 1, dtype=np.uint32)
+    rtag[tags] = np.arange(n, dtype=np.uint32)
+    nn = np.array(n_neigh, dtype=np.uint32)
+    out = np.array(nl, dtype=np.uint32)
+    bg = _u32(np.asarray(bond_group).reshape(-1, 2))
+    head = np.ascontiguousarray(head, dtype=np.uint64)
+    lib().orc_filter_bond_exclusions(C.c_uint32(n), _p(nn, C.c_uint32), _p(head, C.c_uint64),
+                                     _p(out, C.c_uint32), _p(tags, C.c_uint32), _p(rtag, C.c_uint32),
+                                     _p(bg, C.c_uint32), C.c_uint32(bg.shape[0]))
+    head2 = np.zeros(n, dtype=np.uint64)
+    if n:
+        head2[1:] = np.cumsum(nn[:-1], dtype=np.uint64)
+    rows = np.repeat(np.arange(n), nn)
+    within = np.arange(int(nn.sum())) - np.repeat(head2, nn).astype(np.int64)
+    packed = out[(head[rows].astype(np.int64) + within)] if len(rows) else out[:0]
+    return nn, head2, packed
+
+
+def bond_harmonic(box, pos, bond_group, bond_type, params, tags=None):
+    """PotentialBond<EvaluatorBondHarmonic>: returns (force N x 4 incl. energy, virial 6 x N)."""
+    pos = _f64(pos)
+    n = pos.shape[0]
+    tags = np.arange(n, dtype=np.uint32) if tags is None else _u32(tags)
+    rtag = np.zeros(int(tags.max()) + 1 if n else 1, dtype=np.uint32)
+    rtag[tags] = np.arange(n, dtype=np.uint32)
+    bg = _u32(np.asarray(bond_group).reshape(-1, 2))
+    bt = _u32(bond_type)
+    params = _f64(np.asarray(params).reshape(-1, 2))
+    force = np.zeros((n, 4))
+    virial = np.zeros((6, n))
+    rc = lib().orc_bond_harmonic(C.byref(box), _p(pos, C.c_double), C.c_uint32(n), _p(rtag, C.c_uint32),
+                                 _p(bg, C.c_uint32), _p(bt, C.c_uint32), C.c_uint32(bg.shape[0]),
+                                 _p(params, C.c_double), _p(force, C.c_double), _p(virial, C.c_double))
+    if rc:
+        raise RuntimeError(f"Error: bond {rc - 1} is incomplete.")
+    return force, virial
+
+
 def step_two_langevin(vel, accel, mass, force4, types, tags, dt, kT, gamma, seed, timestep):
     """TwoStepLangevin::integrateStepTwo in place on fp64 vel/accel (N,3); gamma per type."""
     types = _u32(types)

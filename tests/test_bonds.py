@@ -1,0 +1,221 @@
+"""Bonds and bond exclusions: hoomd.md.bond.Harmonic, Snapshot.bonds and
+nlist.Cell(exclusions=('bond',)) against the oracle's restatement (hoomd/md/PotentialBond.h:176-312,
+hoomd/md/EvaluatorBondHarmonic.h, hoomd/md/NeighborList.cc:569-640,1448-1536), which is pinned to the
+reference's own vectors (hoomd/md/pytest/test_bond.py:17-37, two particles 0.969 apart in a box of 5)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import gsd_ref
+
+# (k, r0, force on particle 0 along x, total energy) hoomd/md/pytest/test_bond.py:17-37
+REF_VECTORS = [(30.0, 1.6, -18.9300, 5.9724), (25.0, 1.7, -18.2750, 6.6795), (20.0, 1.8, -16.6200, 6.9056)]
+
+
+def two_particles(d=0.969):
+    # hoomd/conftest.py:168-196 two_particle_snapshot_factory(d=0.969, L=5)
+    return np.array([[-d / 2, 0, 0.1], [d / 2, 0, 0.1]], dtype=np.float32)
+
+
+@pytest.mark.parametrize("k,r0,force,energy", REF_VECTORS)
+def test_oracle_harmonic_reference_vectors(oracle, k, r0, force, energy):
+    box = oracle.make_box([5.0, 5.0, 5.0])
+    f, v = oracle.bond_harmonic(box, two_particles(), [[0, 1]], [0], [[k, r0]])
+    assert f[:, 3].sum() == pytest.approx(energy, rel=1e-2)   # the reference's own tolerances
+    np.testing.assert_allclose(f[0, :3], [force, 0, 0], rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(f[1, :3], [-force, 0, 0], rtol=1e-2, atol=1e-5)
+    # and exactly: F = k (r0 / r - 1) dx, E = k/2 (r - r0)^2, W_xx = 1/2 F_x dx split over both members
+    r = float(np.float32(0.969 / 2)) * 2
+    assert f[0, 0] == pytest.approx(-k * (r0 / r - 1.0) * r, rel=1e-12)
+    assert f[:, 3].sum() == pytest.approx(0.5 * k * (r - r0) ** 2, rel=1e-12)
+    assert v[0].sum() == pytest.approx(k * (r0 / r - 1.0) * r * r, rel=1e-12)
+    # a bond across the periodic boundary uses the minimum image
+    far = np.array([[-2.4, 0, 0], [2.4, 0, 0]], dtype=np.float32)
+    f2, _ = oracle.bond_harmonic(box, far, [[0, 1]], [0], [[k, r0]])
+    assert f2[0, 0] == pytest.approx(+k * (r0 / 0.2 - 1.0) * 0.2, rel=1e-5)
+
+
+def chains(n_chains, length, rho, seed, bond=0.97):
+    """random-walk bead-spring chains in a cubic box, wrapped"""
+    rng = np.random.default_rng(seed)
+    n = n_chains * length
+    L = np.float32((n / rho) ** (1 / 3))
+    pos = np.zeros((n, 3))
+    group = []
+    for c in range(n_chains):
+        p = rng.uniform(-L / 2, L / 2, 3)
+        for k in range(length):
+            i = c * length + k
+            pos[i] = p
+            if k:
+                group.append((i - 1, i))
+            step = rng.normal(size=3)
+            p = p + bond * step / np.linalg.norm(step)
+    pos = (pos + L / 2) % float(L) - L / 2
+    pos = np.clip(pos.astype(np.float32), -float(L) / 2, np.nextafter(np.float32(float(L) / 2), np.float32(0)))
+    return pos, np.array(group, dtype=np.uint32), np.array([L, L, L], dtype=np.float32)
+
+
+def lattice_chains(nx, ny, nz, length, a, seed, jitter=0.05):
+    """chains laid along x on a cubic lattice (no overlaps): a gentle start for dynamics"""
+    assert nx % length == 0
+    rng = np.random.default_rng(seed)
+    L = np.array([nx * a, ny * a, nz * a], dtype=np.float32)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    order = np.lexsort((ix.ravel(), iy.ravel(), iz.ravel()))  # x fastest
+    pos = (np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1)[order] + 0.5) * a - L.astype(np.float64) / 2
+    pos += rng.uniform(-jitter, jitter, size=pos.shape)
+    n = len(pos)
+    idx = np.arange(n)
+    group = np.stack([idx[:-1], idx[1:]], axis=1)[(idx[1:] % length) != 0]
+    pos = np.clip(pos.astype(np.float32), -L / 2, np.nextafter(L / 2, np.float32(0)))
+    return pos, group.astype(np.uint32), L
+
+
+def test_oracle_exclusion_filter(oracle):
+    """filtered list == full list minus the bonded pairs that were in it"""
+    pos, group, L = chains(40, 10, 0.6, seed=1)
+    box = oracle.make_box([float(v) for v in L])
+    types = np.zeros(len(pos), dtype=np.uint32)
+    nn, head, nl, _ = oracle.nlist(box, pos, types, [2.0], 0.3, full=True)
+    full = set(map(tuple, oracle.pair_set(nn, head, nl)))
+    nn2, head2, nl2 = oracle.filter_bond_exclusions(nn, head, nl, group)
+    filt = set(map(tuple, oracle.pair_set(nn2, head2, nl2)))
+    bonded = set((int(min(a, b)), int(max(a, b))) for a, b in group)
+    assert filt == full - bonded and len(full & bonded) == len(group)  # bond length 0.97 < r_list
+    assert nn.sum() - nn2.sum() == 2 * len(group)
+
+
+def test_gsd_bonds_roundtrip(tmp_path):
+    from hoomd_blue_b200 import gsd_io, Snapshot
+    pos, group, L = chains(5, 6, 0.5, seed=2)
+    s = Snapshot.from_arrays(list(L) + [0, 0, 0], pos)
+    s.bonds.N = len(group)
+    s.bonds.types = ["polymer", "x"]
+    s.bonds.group[:] = group
+    s.bonds.typeid[:] = np.arange(len(group)) % 2
+    path = str(tmp_path / "b.gsd")
+    gsd_io.write_frame(path, s, 5)
+    r, step = gsd_io.read_frame(path)
+    assert step == 5 and r.bonds.N == len(group) and r.bonds.types == ["polymer", "x"]
+    assert np.array_equal(r.bonds.group, group) and np.array_equal(r.bonds.typeid, s.bonds.typeid)
+    if gsd_ref.available():
+        g = gsd_ref.RefGSD.open(path)
+        assert np.array_equal(g.read(0, "bonds/group"), group.astype(np.int32))
+        assert g.read(0, "bonds/N")[0, 0] == len(group)
+        g.close()
+
+
+# ------------------------------------------------------------------------------------ GPU ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,r0,force,energy", REF_VECTORS)
+def test_harmonic_reference_vectors(k, r0, force, energy):
+    """hoomd/md/pytest/test_bond.py:113-144 as written there (a bond-only integrator)."""
+    import hoomd_blue_b200 as hoomd
+    snap = hoomd.Snapshot.from_arrays([5, 5, 5, 0, 0, 0], two_particles())
+    snap.bonds.N = 1
+    snap.bonds.types = ["A-A"]
+    snap.bonds.typeid[0] = 0
+    snap.bonds.group[0] = (0, 1)
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=1)
+    sim.create_state_from_snapshot(snap)
+    potential = hoomd.md.bond.Harmonic()
+    potential.params["A-A"] = dict(k=k, r0=r0)
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.005, forces=[potential])
+    sim.run(0)
+    assert sum(potential.energies) == pytest.approx(energy, rel=1e-2)
+    np.testing.assert_allclose(potential.forces[0], [force, 0.0, 0.0], rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(potential.forces[1], [-1 * force, 0.0, 0.0], rtol=1e-2, atol=1e-5)
+    r = float(np.float32(0.969 / 2)) * 2
+    assert potential.forces[0, 0] == pytest.approx(-k * (r0 / r - 1.0) * r, rel=1e-6)
+    assert potential.energy == pytest.approx(0.5 * k * (r - r0) ** 2, rel=1e-6)
+    back = sim.state.get_snapshot()
+    assert back.bonds.N == 1 and back.bonds.types == ["A-A"] and tuple(back.bonds.group[0]) == (0, 1)
+
+
+@pytest.mark.gpu
+def test_polymer_melt_vs_oracle(oracle):
+    """Kremer-Grest-like melt: WCA pair force over a list that excludes the bonded pairs + harmonic
+    bonds. Pair set bit-exact against the oracle's filtered list, per-force and net results in tolerance,
+    NVE with both forces conserves energy, and the trajectory survives re-ordering at rebuilds."""
+    import hoomd_blue_b200 as hoomd
+    from tests.test_gpu_parity import canon_pairs, force_err, FORCE_RTOL, TOTAL_RTOL
+    pos, group, L = chains(400, 16, 0.7, seed=3)
+    n = len(pos)
+    rc = 2.0 ** (1.0 / 6.0)
+
+    def make(exclusions):
+        snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, np.zeros_like(pos))
+        snap.bonds.N = len(group)
+        snap.bonds.types = ["polymer"]
+        snap.bonds.group[:] = group
+        sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=2)
+        sim.always_compute_pressure = True
+        sim.create_state_from_snapshot(snap)
+        cell = hoomd.md.nlist.Cell(buffer=0.3, exclusions=exclusions)
+        lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=rc, mode="shift")
+        lj.params[("A", "A")] = dict(epsilon=1.0, sigma=0.8)
+        hb = hoomd.md.bond.Harmonic()
+        hb.params["polymer"] = dict(k=200.0, r0=0.9)
+        sim.operations.integrator = hoomd.md.Integrator(
+            dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[lj, hb])
+        return sim, cell, lj, hb
+
+    sim, cell, lj, hb = make(("bond",))
+    sim.run(0)
+    box = oracle.make_box([float(v) for v in L])
+    types = np.zeros(n, dtype=np.uint32)
+    nn, head, nl, _ = oracle.nlist(box, pos, types, [rc], 0.3, full=True)
+    nn_x, head_x, nl_x = oracle.filter_bond_exclusions(nn, head, nl, group)
+    assert np.array_equal(canon_pairs(cell.pair_list), oracle.pair_set(nn_x, head_x, nl_x))
+    f_ref, v_ref = oracle.pair_lj(box, pos, types, nn_x, head_x, nl_x, [[1.0, 0.8]], [rc], shift_mode=1)
+    assert force_err(lj.forces, f_ref[:, :3]) <= FORCE_RTOL
+    assert abs(lj.energy - f_ref[:, 3].sum()) <= TOTAL_RTOL * abs(f_ref[:, 3].sum())
+    b_ref, bv_ref = oracle.bond_harmonic(box, pos, group, np.zeros(len(group), np.uint32), [[200.0, 0.9]])
+    assert force_err(hb.forces, b_ref[:, :3]) <= FORCE_RTOL
+    assert abs(hb.energy - b_ref[:, 3].sum()) <= TOTAL_RTOL * abs(b_ref[:, 3].sum())
+    assert np.allclose(hb.energies, b_ref[:, 3], rtol=1e-5, atol=1e-6)
+    vs, vs_ref = hb.virials.sum(axis=0), bv_ref.sum(axis=1)
+    assert np.max(np.abs(vs - vs_ref)) <= 1e-5 * np.max(np.abs(vs_ref))
+    # thermodynamics see the sum of both forces
+    ke, pe, w = sim.operations.integrator._thermo()
+    e_ref = f_ref[:, 3].sum() + b_ref[:, 3].sum()
+    assert abs(pe - e_ref) <= 1e-6 * abs(e_ref)
+    w_ref = v_ref.sum(axis=1) + vs_ref
+    assert np.max(np.abs(np.array(w)[[0, 3, 5]] - w_ref[[0, 3, 5]])) <= 1e-5 * np.max(np.abs(w_ref))
+    # without exclusions the bonded pairs come back
+    sim0, cell0, lj0, hb0 = make(())
+    sim0.run(0)
+    assert len(cell0.pair_list) == len(cell.pair_list) + len(group)
+    # NVE with the net force, from a gentle start: energy is conserved through rebuilds
+    pos, group, L = lattice_chains(32, 12, 12, 16, 1.0, seed=4)
+    rng = np.random.default_rng(5)
+    vel0 = rng.normal(0, 1.0, size=pos.shape).astype(np.float32)
+    vel0 -= vel0.mean(axis=0)
+    snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel0)
+    snap.bonds.N = len(group)
+    snap.bonds.types = ["polymer"]
+    snap.bonds.group[:] = group
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=2)
+    sim.create_state_from_snapshot(snap)
+    cell = hoomd.md.nlist.Cell(buffer=0.3)
+    lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=rc, mode="shift")
+    lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+    hb = hoomd.md.bond.Harmonic()
+    hb.params["polymer"] = dict(k=200.0, r0=0.95)
+    sim.operations.integrator = hoomd.md.Integrator(
+        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[lj, hb])
+    sim.run(500)
+    e = []
+    for _ in range(10):
+        sim.run(200)
+        ke, pe, _ = sim.operations.integrator._thermo()
+        e.append(ke + pe)
+    assert cell.num_builds >= 1 and ke > 0.5 * len(pos)
+    assert np.ptp(e) <= 2e-3 * ke
+    # bonds are still intact after particles were re-ordered: partner lookup goes through rtag
+    s = sim.state.get_snapshot()
+    d = s.particles.position[group[:, 0]].astype(np.float64) - s.particles.position[group[:, 1]]
+    d -= L * np.round(d / L)
+    assert np.max(np.linalg.norm(d, axis=1)) < 1.6
