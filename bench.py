@@ -23,6 +23,8 @@ import time
 
 import numpy as np
 
+_emit = print  # replaced in __main__ by a writer to the saved stdout descriptor
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -242,7 +244,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def run_ours(args):
@@ -427,7 +429,7 @@ def run_ours(args):
                                               f"{nst} steps of the N={len(cp)} equilibrated liquid of "
                                               f"configs[0] (same rho, kT, r_cut, buffer; {wall:.1f} s "
                                               "wall)"}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
 
 
 if __name__ == "__main__":
@@ -437,6 +439,13 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     a = ap.parse_args()
+    # The contract is ONE JSON line on stdout. Libraries write banners to file descriptor 1 from C
+    # (NCCL prints its version there at communicator creation), so fd 1 is pointed at stderr for the
+    # whole run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    _emit = lambda text: os.write(_json_fd, (text + "\n").encode())  # noqa: E731
     if a.impl == "reference":
         run_reference(a)
     else:
