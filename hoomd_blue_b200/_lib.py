@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("HB2_LIB", "libhoomd_b200.so"))
 (OK, ERR_INVALID, ERR_CUDA, ERR_NAN_POSITION, ERR_OUT_OF_BOX, ERR_BOX_TOO_SMALL, ERR_NLIST_OVERFLOW,
  ERR_NO_DEVICE, ERR_COMM) = range(9)
 EVAL = {"lj": 0, "dpd": 1, "dpd_conservative": 2, "example_pair": 3, "gauss": 4, "yukawa": 5,
-        "lj1208": 6, "lj0804": 7, "force_shifted_lj": 8, "mie": 9, "morse": 10}
+        "lj1208": 6, "lj0804": 7, "force_shifted_lj": 8, "mie": 9, "morse": 10,
+        "buckingham": 11, "expanded_lj": 12, "expanded_gaussian": 13, "lj_gauss": 14, "twf": 15}
 SHIFT = {"none": 0, "shift": 1, "xplor": 2}
 
 

@@ -1124,6 +1124,11 @@ static const EvalInfo* eval_info(hb2_evaluator ev)
         {EvaluatorPairForceShiftedLJ::n_user_params, pack_as<EvaluatorPairForceShiftedLJ>},
         {EvaluatorPairMie::n_user_params, pack_as<EvaluatorPairMie>},
         {EvaluatorPairMorse::n_user_params, pack_as<EvaluatorPairMorse>},
+        {EvaluatorPairBuckingham::n_user_params, pack_as<EvaluatorPairBuckingham>},
+        {EvaluatorPairExpandedLJ::n_user_params, pack_as<EvaluatorPairExpandedLJ>},
+        {EvaluatorPairExpandedGaussian::n_user_params, pack_as<EvaluatorPairExpandedGaussian>},
+        {EvaluatorPairLJGauss::n_user_params, pack_as<EvaluatorPairLJGauss>},
+        {EvaluatorPairTWF::n_user_params, pack_as<EvaluatorPairTWF>},
     };
     if ((unsigned)ev >= sizeof(table) / sizeof(table[0]))
         return nullptr;
@@ -1182,6 +1187,16 @@ hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairA
         return pair_forces_mie(mode, a, box, stream);
     case HB2_EVAL_MORSE:
         return pair_forces_morse(mode, a, box, stream);
+    case HB2_EVAL_BUCKINGHAM:
+        return pair_forces_buckingham(mode, a, box, stream);
+    case HB2_EVAL_EXPANDED_LJ:
+        return pair_forces_expanded_lj(mode, a, box, stream);
+    case HB2_EVAL_EXPANDED_GAUSSIAN:
+        return pair_forces_expanded_gaussian(mode, a, box, stream);
+    case HB2_EVAL_LJ_GAUSS:
+        return pair_forces_lj_gauss(mode, a, box, stream);
+    case HB2_EVAL_TWF:
+        return pair_forces_twf(mode, a, box, stream);
         }
     set_error("pair forces: unknown evaluator");
     return HB2_ERR_INVALID;

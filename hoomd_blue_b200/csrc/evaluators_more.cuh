@@ -335,5 +335,265 @@ class EvaluatorPairMorse
     protected:
     Scalar rsq, rcutsq, D0, alpha, r0;
     };
+
+// V = A exp(-r / rho) - C / r^6   (hoomd/md/EvaluatorPairBuckingham.h:127-158)
+class EvaluatorPairBuckingham
+    {
+    public:
+    struct param_type
+        {
+        Scalar A, rho, C;
+        };
+    HB2_EVAL_COMMON(3) // {A, rho, C}
+    static void pack(const double* user, param_type& p)
+        {
+        p.A = (Scalar)user[0];
+        p.rho = (Scalar)user[1];
+        p.C = (Scalar)user[2];
+        }
+    HB2_DEVICE EvaluatorPairBuckingham(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), A(p.A), rho(p.rho), C(p.C)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && rho > Scalar(0.0))
+            {
+            const Scalar r = sqrtf(rsq);
+            const Scalar exp_factor = A * __expf(-r / rho);
+            const Scalar r2inv = Scalar(1.0) / rsq;
+            const Scalar r6inv = r2inv * r2inv * r2inv;
+            force_divr = (exp_factor / (rho * r)) - (r2inv * r6inv * Scalar(6.0) * C);
+            pair_eng = exp_factor - r6inv * C;
+            if (energy_shift)
+                {
+                const Scalar rcut = sqrtf(rcutsq);
+                const Scalar rcut2inv = Scalar(1.0) / rcutsq;
+                const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+                pair_eng -= A * __expf(-rcut / rho) - rcut6inv * C;
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "buckingham";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, A, rho, C;
+    };
+
+// LJ in r - delta   (hoomd/md/EvaluatorPairExpandedLJ.h:66-84 parameters, :150-186 evaluation)
+class EvaluatorPairExpandedLJ
+    {
+    public:
+    struct param_type
+        {
+        Scalar lj1, lj2, delta;
+        };
+    HB2_EVAL_COMMON(3) // {epsilon, sigma, delta}
+    static void pack(const double* user, param_type& p)
+        {
+        // the reference keeps sigma^6 and 4 epsilon as Scalars and forms lj1, lj2 from them
+        const Scalar sigma = (Scalar)user[1];
+        const Scalar sigma_3 = sigma * sigma * sigma;
+        const Scalar sigma_6 = sigma_3 * sigma_3;
+        const Scalar epsilon_x_4 = Scalar(4.0) * (Scalar)user[0];
+        p.lj1 = epsilon_x_4 * sigma_6 * sigma_6;
+        p.lj2 = epsilon_x_4 * sigma_6;
+        p.delta = (Scalar)user[2];
+        }
+    HB2_DEVICE EvaluatorPairExpandedLJ(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), lj1(p.lj1), lj2(p.lj2), delta(p.delta)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        const Scalar rinv = rsqrt_refined(rsq);
+        const Scalar r = Scalar(1.0) / rinv;
+        if (rsq < rcutsq && lj1 != 0)
+            {
+            const Scalar rmd = r - delta;
+            const Scalar rmdinv = Scalar(1.0) / rmd;
+            const Scalar rmd2inv = rmdinv * rmdinv;
+            const Scalar rmd6inv = rmd2inv * rmd2inv * rmd2inv;
+            force_divr = rinv * rmdinv * rmd6inv * (Scalar(12.0) * lj1 * rmd6inv - Scalar(6.0) * lj2);
+            pair_eng = rmd6inv * (lj1 * rmd6inv - lj2);
+            if (energy_shift)
+                {
+                const Scalar r_cut_shifted_inv = Scalar(1.0) / (sqrtf(rcutsq) - delta);
+                const Scalar r_cut2_inv = r_cut_shifted_inv * r_cut_shifted_inv;
+                const Scalar r_cut6_inv = r_cut2_inv * r_cut2_inv * r_cut2_inv;
+                pair_eng -= r_cut6_inv * (lj1 * r_cut6_inv - lj2);
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "expanded_lj";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, lj1, lj2, delta;
+    };
+
+// V = eps exp(-(r - delta)^2 / (2 sigma^2))   (hoomd/md/EvaluatorPairExpandedGaussian.h:127-162)
+class EvaluatorPairExpandedGaussian
+    {
+    public:
+    struct param_type
+        {
+        Scalar epsilon, sigma, delta;
+        };
+    HB2_EVAL_COMMON(3) // {epsilon, sigma, delta}
+    static void pack(const double* user, param_type& p)
+        {
+        p.epsilon = (Scalar)user[0];
+        p.sigma = (Scalar)user[1];
+        p.delta = (Scalar)user[2];
+        }
+    HB2_DEVICE EvaluatorPairExpandedGaussian(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), epsilon(p.epsilon), sigma(p.sigma), delta(p.delta)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar r = sqrtf(rsq);
+            const Scalar rinv = Scalar(1.0) / r;
+            const Scalar rmd = r - delta;
+            const Scalar sigma_sq = sigma * sigma;
+            const Scalar exp_val = __expf(Scalar(-0.5) * (rmd * rmd) / sigma_sq);
+            force_divr = epsilon / sigma_sq * exp_val * rmd * rinv;
+            pair_eng = epsilon * exp_val;
+            if (energy_shift)
+                {
+                const Scalar rcutmd = sqrtf(rcutsq) - delta;
+                pair_eng -= epsilon * __expf(Scalar(-0.5) * (rcutmd * rcutmd) / sigma_sq);
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "expanded_gaussian";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, epsilon, sigma, delta;
+    };
+
+// V = 1/r^12 - 2/r^6 - eps exp(-(r - r0)^2 / (2 sigma^2))   (hoomd/md/EvaluatorPairLJGauss.h:131-166)
+class EvaluatorPairLJGauss
+    {
+    public:
+    struct param_type
+        {
+        Scalar epsilon, sigma, r0;
+        };
+    HB2_EVAL_COMMON(3) // {epsilon, sigma, r0}
+    static void pack(const double* user, param_type& p)
+        {
+        p.epsilon = (Scalar)user[0];
+        p.sigma = (Scalar)user[1];
+        p.r0 = (Scalar)user[2];
+        }
+    HB2_DEVICE EvaluatorPairLJGauss(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), epsilon(p.epsilon), sigma(p.sigma), r0(p.r0)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq >= rcutsq)
+            return false;
+        const Scalar r = sqrtf(rsq);
+        const Scalar sigma2 = sigma * sigma;
+        const Scalar rdiff = r - r0;
+        const Scalar rdiff_sigma2 = rdiff / sigma2;
+        const Scalar exp_val = __expf(Scalar(-0.5) * rdiff_sigma2 * rdiff);
+        const Scalar r2inv = Scalar(1.0) / rsq;
+        const Scalar r6inv = r2inv * r2inv * r2inv;
+        force_divr = (r2inv * r6inv * Scalar(12.0) * (r6inv - Scalar(1.0)))
+                     - (exp_val * epsilon * rdiff_sigma2 / r);
+        pair_eng = r6inv * (r6inv - Scalar(2.0)) - exp_val * epsilon;
+        if (energy_shift)
+            {
+            const Scalar rcut2inv = Scalar(1.0) / rcutsq;
+            const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+            const Scalar d = sqrtf(rcutsq) - r0;
+            pair_eng -= rcut6inv * (rcut6inv - Scalar(2.0)) - (epsilon * __expf(Scalar(-0.5) * d * d / sigma2));
+            }
+        return true;
+        }
+    static const char* getName()
+        {
+        return "lj_gauss";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, epsilon, sigma, r0;
+    };
+
+// ten Wolde-Frenkel: V = 4 eps / alpha^2 [1/(r^2/sigma^2 - 1)^6 - alpha /(r^2/sigma^2 - 1)^3]
+// (hoomd/md/EvaluatorPairTWF.h:58-64 parameters, :139-180 evaluation; overlapping pairs are infinite)
+class EvaluatorPairTWF
+    {
+    public:
+    struct param_type
+        {
+        Scalar sigma, alpha, prefactor;
+        };
+    HB2_EVAL_COMMON(3) // {epsilon, sigma, alpha}
+    static void pack(const double* user, param_type& p)
+        {
+        p.sigma = (Scalar)user[1];
+        p.alpha = (Scalar)user[2];
+        p.prefactor = (Scalar)(4.0 * (double)(Scalar)user[0] / ((double)p.alpha * (double)p.alpha));
+        }
+    HB2_DEVICE EvaluatorPairTWF(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), sigma(p.sigma), alpha(p.alpha), prefactor(p.prefactor)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq)
+            {
+            const Scalar sigma2 = sigma * sigma;
+            if (rsq <= sigma2)
+                {
+                pair_eng = INFINITY;
+                force_divr = INFINITY;
+                return true;
+                }
+            const Scalar common_term = Scalar(1.0) / (rsq / sigma2 - Scalar(1.0));
+            const Scalar common_term3 = common_term * common_term * common_term;
+            const Scalar common_term6 = common_term3 * common_term3;
+            pair_eng = prefactor * (common_term6 - alpha * common_term3);
+            const Scalar force_term = Scalar(6.0) * common_term / sigma2;
+            force_divr = prefactor * force_term * (Scalar(2.0) * common_term6 - alpha * common_term3);
+            if (energy_shift)
+                {
+                const Scalar ct = Scalar(1.0) / (rcutsq / sigma2 - Scalar(1.0));
+                const Scalar ct3 = ct * ct * ct;
+                pair_eng -= prefactor * (ct3 * ct3 - alpha * ct3);
+                }
+            return true;
+            }
+        return false;
+        }
+    static const char* getName()
+        {
+        return "twf";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, sigma, alpha, prefactor;
+    };
 #undef HB2_EVAL_COMMON
     } // namespace hb2

@@ -665,4 +665,9 @@ hb2_status pair_forces_lj0804(hb2_shift_mode, const PairArgs&, const hb2_box&, c
 hb2_status pair_forces_force_shifted_lj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_mie(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_morse(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_buckingham(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_expanded_lj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_expanded_gaussian(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_lj_gauss(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_twf(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
     } // namespace hb2

@@ -270,3 +270,36 @@ class Morse(Pair):
     r0}."""
     _evaluator = "morse"
     _param_keys = ("D0", "alpha", "r0")
+
+
+class Buckingham(Pair):
+    """hoomd.md.pair.Buckingham: V = A exp(-r / rho) - C / r^6; params {A, rho, C}."""
+    _evaluator = "buckingham"
+    _param_keys = ("A", "rho", "C")
+
+
+class ExpandedLJ(Pair):
+    """hoomd.md.pair.ExpandedLJ: LJ in r - delta; params {epsilon, sigma, delta}."""
+    _evaluator = "expanded_lj"
+    _param_keys = ("epsilon", "sigma", "delta")
+
+
+class ExpandedGaussian(Pair):
+    """hoomd.md.pair.ExpandedGaussian: V = eps exp(-(r - delta)^2 / (2 sigma^2)); params {epsilon, sigma,
+    delta}."""
+    _evaluator = "expanded_gaussian"
+    _param_keys = ("epsilon", "sigma", "delta")
+
+
+class LJGauss(Pair):
+    """hoomd.md.pair.LJGauss: V = 1/r^12 - 2/r^6 - eps exp(-(r - r0)^2 / (2 sigma^2)); params {epsilon,
+    sigma, r0}."""
+    _evaluator = "lj_gauss"
+    _param_keys = ("epsilon", "sigma", "r0")
+
+
+class TWF(Pair):
+    """hoomd.md.pair.TWF (ten Wolde-Frenkel); params {epsilon, sigma, alpha}. Overlapping pairs
+    (r <= sigma) have infinite energy and force, as in the reference."""
+    _evaluator = "twf"
+    _param_keys = ("epsilon", "sigma", "alpha")

@@ -80,7 +80,12 @@ typedef enum
     HB2_EVAL_LJ0804 = 7,           /* hoomd/md/EvaluatorPairLJ0804.h; {epsilon, sigma} */
     HB2_EVAL_FORCE_SHIFTED_LJ = 8, /* hoomd/md/EvaluatorPairForceShiftedLJ.h; {epsilon, sigma} */
     HB2_EVAL_MIE = 9,              /* hoomd/md/EvaluatorPairMie.h; {epsilon, sigma, n, m} */
-    HB2_EVAL_MORSE = 10            /* hoomd/md/EvaluatorPairMorse.h; {D0, alpha, r0} */
+    HB2_EVAL_MORSE = 10,           /* hoomd/md/EvaluatorPairMorse.h; {D0, alpha, r0} */
+    HB2_EVAL_BUCKINGHAM = 11,      /* hoomd/md/EvaluatorPairBuckingham.h; {A, rho, C} */
+    HB2_EVAL_EXPANDED_LJ = 12,     /* hoomd/md/EvaluatorPairExpandedLJ.h; {epsilon, sigma, delta} */
+    HB2_EVAL_EXPANDED_GAUSSIAN = 13, /* hoomd/md/EvaluatorPairExpandedGaussian.h; {epsilon, sigma, delta} */
+    HB2_EVAL_LJ_GAUSS = 14,        /* hoomd/md/EvaluatorPairLJGauss.h; {epsilon, sigma, r0} */
+    HB2_EVAL_TWF = 15              /* hoomd/md/EvaluatorPairTWF.h; {epsilon, sigma, alpha} */
     } hb2_evaluator;
 #define HB2_PARAM_FLOATS 4 /* packed evaluator parameters per type pair (param_type is <= 16 bytes) */
 
