@@ -419,6 +419,59 @@ def test_row_per_lane_build_kernel(hoomd, oracle, monkeypatch, n_side, rho):
     assert np.array_equal(f_rows, f_mask)
 
 
+def random_gas(n, L, seed):
+    rng = np.random.default_rng(seed)
+    L = np.asarray(L, dtype=np.float32)
+    pos = (rng.random((n, 3)) - 0.5) * L.astype(np.float64)
+    pos = np.clip(pos.astype(np.float32), -L / 2, np.nextafter(L / 2, np.float32(0)))
+    return pos, L
+
+
+@pytest.mark.parametrize("L,n,kind", [
+    ((14.3, 23.1, 31.7), 7000, "one"),      # orthorhombic, cell grid 4 x 7 x 10
+    ((6.5, 20.0, 9.1), 900, "one"),         # 2 cells along x: both images of a neighbour in one stencil
+    ((5.9, 6.1, 40.0), 1000, "one"),        # 2 x 2 x 13
+    ((17.0, 12.5, 21.3), 3500, "two"),      # per-type-pair r_cut, one pair switched off (r_cut = 0)
+    ((6.2, 19.0, 8.8), 800, "two"),
+])
+def test_oracle_orthorhombic_boxes(hoomd, oracle, L, n, kind):
+    """Non-cubic boxes, grids with fewer than three cells along an axis, and per-type-pair cut-offs
+    including a disabled pair — the shapes hoomd/md/pytest/test_nlist.py and test_potential.py sweep —
+    on a random ideal gas (close pairs included: ulp-level agreement of steep forces is part of it)."""
+    pos, Lf = random_gas(n, L, seed=int(sum(L) * 10) + n)
+    # push overlapping pairs apart a little: r^-13 forces above 1e12 say nothing about the kernel
+    if kind == "one":
+        types, names = np.zeros(n, dtype=np.uint32), ("A",)
+        r_cut = {("A", "A"): 2.5}
+        params = {("A", "A"): (1.0, 0.3)}
+    else:
+        types, names = (np.arange(n) % 2).astype(np.uint32), ("A", "B")
+        r_cut = {("A", "A"): 2.5, ("A", "B"): 0.0, ("B", "B"): 1.8}
+        params = {("A", "A"): (1.0, 0.3), ("A", "B"): (2.0, 0.25), ("B", "B"): (0.5, 0.35)}
+    fx = dict(L=Lf, pos=pos, vel=np.zeros_like(pos), typeid=types)
+    sim, cell, lj = lj_sim(hoomd, fx, params, r_cut, 0.4, "shift", types=names)
+    sim.run(0)
+    box = oracle.make_box([float(v) for v in Lf])
+    nt = len(names)
+    rc = np.zeros((nt, nt))
+    pr = np.zeros((nt * nt, 2))
+    for (a, b), v in r_cut.items():
+        i, j = names.index(a), names.index(b)
+        rc[i, j] = rc[j, i] = v
+        pr[i * nt + j] = pr[j * nt + i] = params[(a, b)]
+    nn, head, nl, dim = oracle.nlist(box, pos, types, rc.ravel(), 0.4, full=True)
+    assert cell.dimensions == dim
+    assert np.array_equal(canon_pairs(cell.pair_list), oracle.pair_set(nn, head, nl))
+    f_ref, v_ref = oracle.pair_lj(box, pos, types, nn, head, nl, pr, rc.ravel(), shift_mode=1)
+    assert force_err(lj.forces, f_ref[:, :3]) <= FORCE_RTOL
+    e_ref = f_ref[:, 3].sum()
+    assert abs(lj.energy - e_ref) <= TOTAL_RTOL * max(abs(e_ref), np.abs(f_ref[:, 3]).sum() * 1e-3)
+    if kind == "two":
+        # the disabled pair contributes nothing: A-B pairs are absent from the list altogether
+        pl = cell.pair_list
+        assert not np.any(types[pl[:, 0]] != types[pl[:, 1]])
+
+
 def test_edge_cases(hoomd):
     """box too small, NaN position, particle out of the box, empty cells / sparse gas."""
     pos = np.array([[0, 0, 0], [1, 0, 0]], dtype=np.float32)
