@@ -196,9 +196,15 @@ static hb2_status system_allocate(hb2_system* s, uint32_t cap, bool with_rtag, u
         HB2_TRY(dev_alloc(&s->image[b], 3 * (size_t)cap));
         HB2_TRY(dev_alloc(&s->tag[b], (size_t)cap));
         }
-    dev_free(s->rtag);
-    if (with_rtag)
-        HB2_TRY(dev_alloc(&s->rtag, n_tags));
+    // (a domain-decomposed system carries an rtag table only when it has bonds; it is indexed by the
+    // global tag, so it survives a change of the local capacity)
+    if (!(s->dom.active && s->rtag))
+        {
+        dev_free(s->rtag);
+        s->rtag = nullptr;
+        if (with_rtag)
+            HB2_TRY(dev_alloc(&s->rtag, n_tags));
+        }
     dev_free(s->d_partial);
     HB2_TRY(dev_alloc(&s->d_partial, 8 * (size_t)(reduce_blocks(cap) + 1)));
     s->cap = cap;
@@ -798,6 +804,8 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
     const uint32_t N = s->N, Ntot = s->N + s->Ng;
 
     HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
+    if (s->dom.active && s->rtag) // tags that are neither owned nor ghosts here must read "absent"
+        HB2_CUDA(cudaMemsetAsync(s->rtag, 0xff, sizeof(uint32_t) * (size_t)s->dom.N_global, st));
     const int c = s->cur, o = 1 - c;
     HB2_TRY(compute_cell_order(s->pos[c], Ntot, N, s->box, geom, d_order, d_cell_start, d_cell_end,
                                d_conditions, d_tmp, tmp_bytes, st));
@@ -1699,17 +1707,24 @@ extern "C" hb2_status hb2_system_set_bonds(hb2_system* s, uint32_t n_bonds, cons
     {
     if (!s || (n_bonds && (!group || !typeid_)))
         return HB2_ERR_INVALID;
-    if (s->dom.active)
-        {
-        set_error("bonds are not supported with a domain decomposition (bond data does not migrate)");
-        return HB2_ERR_INVALID;
-        }
-    if (!s->pos[0] || !s->rtag)
+    // With a domain decomposition every rank holds the whole bond table (keyed by global tag) and an
+    // rtag table over the global tags that the rebuild refills for its owned + ghost particles: bond
+    // data does not have to migrate, and a bond is complete when its partner is owned or a ghost
+    // (bond length < r_cut + buffer, as in the reference).
+    if (!s->pos[0] || (!s->dom.active && !s->rtag))
         {
         set_error("hb2_system_set_bonds: set the particles first");
         return HB2_ERR_INVALID;
         }
-    const uint32_t N = s->N;
+    if (s->dom.active && s->dom.N_global >= 0xffffffffull)
+        return HB2_ERR_INVALID;
+    const uint32_t N = s->dom.active ? (uint32_t)s->dom.N_global : s->N;
+    if (s->dom.active && !s->rtag)
+        {
+        HB2_CUDA(cudaSetDevice(s->device));
+        HB2_TRY(dev_alloc(&s->rtag, (size_t)N));
+        HB2_CUDA(cudaMemset(s->rtag, 0xff, sizeof(uint32_t) * (size_t)N));
+        }
     std::vector<uint32_t> head((size_t)N + 1, 0u), partner(2 * (size_t)n_bonds), type(2 * (size_t)n_bonds);
     for (uint32_t k = 0; k < n_bonds; k++)
         {
@@ -1845,11 +1860,6 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
                             const uint32_t* skip_flag)
     {
     hb2_system* s = sys;
-    if (s->dom.active)
-        {
-        set_error("bonds are not supported with a domain decomposition");
-        return HB2_ERR_INVALID;
-        }
     if (params_dirty)
         HB2_TRY(upload_params());
     if (s->n_bonds == 0 && accumulate)
@@ -1916,6 +1926,12 @@ extern "C" hb2_status hb2_bond_get(hb2_bond* b, double* forces3, double* energie
     if (!b)
         return HB2_ERR_INVALID;
     hb2_system* s = b->sys;
+    if (s->dom.active)
+        {
+        set_error("the system is domain decomposed: per-particle bond results are not gathered "
+                  "(thermodynamic sums include the bonds)");
+        return HB2_ERR_INVALID;
+        }
     HB2_TRY(b->compute_own());
     const uint32_t N = s->N;
     std::vector<float4> f(N);
@@ -2297,6 +2313,8 @@ extern "C" hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic,
         double w[7];
         HB2_TRY(launch_reduce_energy(b->d_force, s->compute_virial ? b->d_virial : nullptr, b->cap_N, s->N,
                                      s->d_partial, s->d_ticket + 1, s->d_sums + 1, s->stream));
+        if (s->dom.active)
+            HB2_TRY(domain_allreduce_sum_f64(s, s->d_sums + 1, 7));
         HB2_CUDA(cudaMemcpyAsync(w, s->d_sums + 1, sizeof(double) * 7, cudaMemcpyDeviceToHost, s->stream));
         HB2_CUDA(cudaStreamSynchronize(s->stream));
         for (int q = 0; q < 7; q++)

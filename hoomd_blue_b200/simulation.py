@@ -208,10 +208,18 @@ class State:
             # the reference scatters rank 0's snapshot (hoomd/ParticleData.cc initializeFromSnapshot);
             # here every rank receives it and the engine keeps the particles it owns
             p = snapshot.particles if comm.rank == 0 else None
+            b = getattr(snapshot, "bonds", None) if comm.rank == 0 else None
             data = _comm.broadcast_object(
-                None if p is None else (p.position, p.velocity, p.typeid, p.mass, p.image))
-            pos, vel, tid, mass, img = data
+                None if p is None else (p.position, p.velocity, p.typeid, p.mass, p.image,
+                                        None if b is None or not b.N else (list(b.types), b.typeid, b.group)))
+            pos, vel, tid, mass, img, bd = data
             self._set_tagged(len(pos), np.arange(len(pos), dtype=np.uint32), pos, vel, tid, mass, img)
+            bonds = None
+            if bd is not None:
+                bonds = _Bonds()
+                bonds.N = len(bd[1])
+                bonds.types, bonds.typeid[:], bonds.group[:] = bd[0], bd[1], bd[2]
+            self._set_bonds(bonds)
             return
         p = snapshot.particles
         pos = np.ascontiguousarray(p.position, dtype=np.float32)

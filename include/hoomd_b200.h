@@ -289,7 +289,8 @@ hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p);
 /* thermostat: 0 none (NVE), 1 Bussi(kT, tau) (hoomd/md/Thermostat.h:337-447; tau = 0 is allowed). */
 hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat, double kT,
                                               double tau);
-/* Bonds (single GPU). hb2_system_set_bonds: BondData of the snapshot
+/* Bonds. With a domain decomposition every rank passes the same global table.
+ * hb2_system_set_bonds: BondData of the snapshot
  * (hoomd/BondedGroupData.h) — `group` holds 2 member TAGS per bond, `typeid_` the bond types; call
  * after the particles are set. hb2_nlist_set_exclusions: exclusions=('bond',) (the reference's default,
  * hoomd/md/nlist.py:87-102; hoomd/md/NeighborList.cc:569-640,1487-1536) drops bonded pairs from the

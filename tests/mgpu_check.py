@@ -152,9 +152,48 @@ def main():
     kl = ls.operations.integrator._thermo()[0]
     km = ms.operations.integrator._thermo()[0]
     assert abs(kl - km) <= 2e-4 * abs(km), (kl, km)
+    # (7) bonds + bond exclusions: the bond table is keyed by global tag on every rank, partners are
+    # found among owned + ghost particles through rtag
+    from tests.test_bonds import lattice_chains
+
+    def polymer(device):
+        pos, group, L = lattice_chains(32, 12, 12, 16, 1.0, seed=4)
+        vel0 = np.random.default_rng(5).normal(0, 1.0, size=pos.shape).astype(np.float32)
+        snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel0)
+        snap.bonds.N = len(group)
+        snap.bonds.types = ["polymer"]
+        snap.bonds.group[:] = group
+        sim = hoomd.Simulation(device=device, seed=2)
+        sim.create_state_from_snapshot(snap)
+        cell = hoomd.md.nlist.Cell(buffer=0.3)
+        lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.0 ** (1.0 / 6.0), mode="shift")
+        lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+        hb = hoomd.md.bond.Harmonic()
+        hb.params["polymer"] = dict(k=200.0, r0=0.95)
+        sim.operations.integrator = hoomd.md.Integrator(
+            dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[lj, hb])
+        return sim, cell
+
+    ps, pc = polymer(hoomd.device.GPU())
+    os_, oc = polymer(hoomd.device.GPU(gpu_id=local, communicator=one))
+    ps.run(0)
+    os_.run(0)
+    pp, _ = canon_pairs(pc.pair_list)
+    op, _ = canon_pairs(oc.pair_list)
+    assert np.array_equal(pp, op), (len(pp), len(op))
+    e_d = ps.operations.integrator._thermo()
+    e_1 = os_.operations.integrator._thermo()
+    assert abs(e_d[1] - e_1[1]) <= 1e-6 * abs(e_1[1]), (e_d[1], e_1[1])
+    ps.run(400)
+    os_.run(400)
+    e_d = ps.operations.integrator._thermo()
+    e_1 = os_.operations.integrator._thermo()
+    assert abs(e_d[0] - e_1[0]) <= 5e-4 * abs(e_1[0]), (e_d[0], e_1[0])
+    assert abs((e_d[0] + e_d[1]) - (e_1[0] + e_1[1])) <= 5e-4 * abs(e_1[0])
     if rank == 0:
         print(msg + f" bussi_KE_rel={abs(kb - kr) / abs(kr):.1e} dpd_force_err={derr:.1e}"
-              f" langevin_KE_rel={abs(kl - km) / abs(km):.1e}", flush=True)
+              f" langevin_KE_rel={abs(kl - km) / abs(km):.1e}"
+              f" polymer_pairs={len(pp)} polymer_KE_rel={abs(e_d[0] - e_1[0]) / abs(e_1[0]):.1e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
