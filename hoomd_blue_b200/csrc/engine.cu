@@ -1137,6 +1137,7 @@ static const EvalInfo* eval_info(hb2_evaluator ev)
         {EvaluatorPairExpandedGaussian::n_user_params, pack_as<EvaluatorPairExpandedGaussian>},
         {EvaluatorPairLJGauss::n_user_params, pack_as<EvaluatorPairLJGauss>},
         {EvaluatorPairTWF::n_user_params, pack_as<EvaluatorPairTWF>},
+        {EvaluatorPairDPDThermoLJ::n_user_params, pack_as<EvaluatorPairDPDThermoLJ>},
     };
     if ((unsigned)ev >= sizeof(table) / sizeof(table[0]))
         return nullptr;
@@ -1205,6 +1206,8 @@ hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairA
         return pair_forces_lj_gauss(mode, a, box, stream);
     case HB2_EVAL_TWF:
         return pair_forces_twf(mode, a, box, stream);
+    case HB2_EVAL_DPDLJ:
+        return pair_forces_dpdlj(mode, a, box, stream);
         }
     set_error("pair forces: unknown evaluator");
     return HB2_ERR_INVALID;
@@ -1259,7 +1262,7 @@ hb2_status hb2_pair::compute(uint64_t timestep, bool flag_known, bool flag_value
         {
         // DPD reads the velocities of its neighbours (hoomd/md/PotentialPairDPDThermo.h:274-286
         // requests the ghost velocity flag for the same reason)
-        if (ev == HB2_EVAL_DPD && !s->dom.need_vel)
+        if ((ev == HB2_EVAL_DPD || ev == HB2_EVAL_DPDLJ) && !s->dom.need_vel)
             s->dom.need_vel = true;
         // a rebuild has just exchanged the ghost layer; otherwise refresh it
         // (Communicator::beginUpdateGhosts, hoomd/Communicator.cc:2630)

@@ -273,4 +273,94 @@ class EvaluatorPairDPDThermoDPD
     uint64_t m_timestep;
     Scalar m_deltaT, m_dot, m_T;
     };
+
+// DPDLJ: LJ conservative force + the DPD drag and random forces
+// (hoomd/md/EvaluatorPairDPDThermoLJ.h:66-76 parameters, :204-296 evaluation)
+class EvaluatorPairDPDThermoLJ
+    {
+    public:
+    static constexpr bool has_packed = false;
+    static constexpr bool tune_tpp = false;
+    struct param_type
+        {
+        Scalar lj1, lj2, gamma;
+        };
+    static constexpr bool needs_thermo = true;
+    static constexpr unsigned n_user_params = 3; // {epsilon, sigma, gamma}
+    static void pack(const double* user, param_type& p)
+        {
+        const Scalar sigma = (Scalar)user[1];
+        const Scalar sigma_6 = sigma * sigma * sigma * sigma * sigma * sigma;
+        const Scalar epsilon_x_4 = Scalar(4.0) * (Scalar)user[0];
+        p.lj1 = epsilon_x_4 * sigma_6 * sigma_6;
+        p.lj2 = epsilon_x_4 * sigma_6;
+        p.gamma = (Scalar)user[2];
+        }
+    HB2_DEVICE EvaluatorPairDPDThermoLJ(Scalar _rsq, Scalar _rcutsq, const param_type& p)
+        : rsq(_rsq), rcutsq(_rcutsq), lj1(p.lj1), lj2(p.lj2), gamma(p.gamma)
+        {
+        }
+    HB2_DEVICE void set_seed_ij_timestep(uint16_t seed, uint32_t i, uint32_t j, uint64_t timestep)
+        {
+        m_seed = seed;
+        m_i = i;
+        m_j = j;
+        m_timestep = timestep;
+        }
+    HB2_DEVICE void setDeltaT(Scalar dt)
+        {
+        m_deltaT = dt;
+        }
+    HB2_DEVICE void setRDotV(Scalar dot)
+        {
+        m_dot = dot;
+        }
+    HB2_DEVICE void setT(Scalar Temp)
+        {
+        m_T = Temp;
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (rsq < rcutsq && lj1 != 0)
+            {
+            const Scalar r2inv = Scalar(1.0) / rsq;
+            const Scalar r6inv = r2inv * r2inv * r2inv;
+            force_divr = r2inv * r6inv * (Scalar(12.0) * lj1 * r6inv - Scalar(6.0) * lj2);
+            pair_eng = r6inv * (lj1 * r6inv - lj2);
+            if (energy_shift)
+                {
+                const Scalar rcut2inv = Scalar(1.0) / rcutsq;
+                const Scalar rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+                pair_eng -= rcut6inv * (lj1 * rcut6inv - lj2);
+                }
+            return true;
+            }
+        return false;
+        }
+    HB2_DEVICE bool evalForceEnergyThermo(Scalar& force_divr, Scalar& force_divr_cons,
+                                          Scalar& pair_eng, bool energy_shift)
+        {
+        if (!evalForceAndEnergy(force_divr, pair_eng, energy_shift))
+            return false;
+        force_divr_cons = force_divr;
+        const Scalar w = rsqrt_refined(rsq) - rsqrt_refined(rcutsq);
+        uint32_t w0, w1;
+        dpd_pair_bits(m_seed, m_i, m_j, m_timestep, w0, w1);
+        const Scalar alpha = fmaf((Scalar)w0, 4.656612873077393e-10f, -1.0f);
+        force_divr -= gamma * m_dot * w * w;
+        force_divr += rsqrt_refined(m_deltaT / (m_T * gamma * Scalar(6.0))) * w * alpha;
+        return true;
+        }
+    static const char* getName()
+        {
+        return "dpdlj";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, lj1, lj2, gamma;
+    uint16_t m_seed;
+    uint32_t m_i, m_j;
+    uint64_t m_timestep;
+    Scalar m_deltaT, m_dot, m_T;
+    };
     } // namespace hb2

@@ -19,6 +19,10 @@ hb2_status pair_forces_dpd(hb2_shift_mode mode, const PairArgs& a, const hb2_box
     {
     return pair_dispatch<EvaluatorPairDPDThermoDPD>(mode, a, box, stream);
     }
+hb2_status pair_forces_dpdlj(hb2_shift_mode mode, const PairArgs& a, const hb2_box& box, cudaStream_t stream)
+    {
+    return pair_dispatch<EvaluatorPairDPDThermoLJ>(mode, a, box, stream);
+    }
 hb2_status pair_forces_dpd_conservative(hb2_shift_mode mode, const PairArgs& a, const hb2_box& box,
                                         cudaStream_t stream)
     {

@@ -670,4 +670,5 @@ hb2_status pair_forces_expanded_lj(hb2_shift_mode, const PairArgs&, const hb2_bo
 hb2_status pair_forces_expanded_gaussian(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_lj_gauss(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_twf(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_dpdlj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
     } // namespace hb2

@@ -303,3 +303,18 @@ class TWF(Pair):
     (r <= sigma) have infinite energy and force, as in the reference."""
     _evaluator = "twf"
     _param_keys = ("epsilon", "sigma", "alpha")
+
+
+class DPDLJ(Pair):
+    """hoomd.md.pair.DPDLJ(nlist, kT, default_r_cut=None, mode='none'): LJ conservative force with the
+    DPD thermostat; params {epsilon, sigma, gamma} (hoomd/md/pair/pair.py:837-935); modes none / shift."""
+    _accepted_modes = ("none", "shift")
+    _evaluator = "dpdlj"
+    _param_keys = ("epsilon", "sigma", "gamma")
+
+    def __init__(self, nlist, kT, default_r_cut=None, mode="none"):
+        super().__init__(nlist, default_r_cut, 0.0, mode)
+        self.kT = float(kT)
+
+    def _attach_extra(self):
+        check(_lib.lib().hb2_pair_set_kT(self._h, self.kT))

@@ -85,7 +85,8 @@ typedef enum
     HB2_EVAL_EXPANDED_LJ = 12,     /* hoomd/md/EvaluatorPairExpandedLJ.h; {epsilon, sigma, delta} */
     HB2_EVAL_EXPANDED_GAUSSIAN = 13, /* hoomd/md/EvaluatorPairExpandedGaussian.h; {epsilon, sigma, delta} */
     HB2_EVAL_LJ_GAUSS = 14,        /* hoomd/md/EvaluatorPairLJGauss.h; {epsilon, sigma, r0} */
-    HB2_EVAL_TWF = 15              /* hoomd/md/EvaluatorPairTWF.h; {epsilon, sigma, alpha} */
+    HB2_EVAL_TWF = 15,             /* hoomd/md/EvaluatorPairTWF.h; {epsilon, sigma, alpha} */
+    HB2_EVAL_DPDLJ = 16            /* hoomd/md/EvaluatorPairDPDThermoLJ.h; {epsilon, sigma, gamma} (+kT, seed) */
     } hb2_evaluator;
 #define HB2_PARAM_FLOATS 4 /* packed evaluator parameters per type pair (param_type is <= 16 bytes) */
 

@@ -862,6 +862,64 @@ void orc_pair_dpd(const orc_box* b, const double* pos, const double* vel, const 
         }
     }
 
+void orc_pair_dpdlj(const orc_box* b, const double* pos, const double* vel, const uint32_t* type,
+                    const uint32_t* tag, uint32_t N, const uint32_t* n_neigh, const uint64_t* head,
+                    const uint32_t* nlist, const double* params, const double* r_cut, uint32_t nt,
+                    int energy_shift, uint16_t seed, uint64_t timestep, double dt, double kT, double* force,
+                    double* virial)
+    {
+    /* PotentialPairDPDThermo<EvaluatorPairDPDThermoLJ> (hoomd/md/PotentialPairDPDThermo.h:102-268 with
+       hoomd/md/EvaluatorPairDPDThermoLJ.h:66-76 parameters, :236-296 evaluation), full list.
+       params = (epsilon, sigma, gamma) per type pair. */
+    memset(force, 0, sizeof(double) * 4 * (size_t)N);
+    memset(virial, 0, sizeof(double) * 6 * (size_t)N);
+    for (uint32_t i = 0; i < N; i++)
+        {
+        const double* pi = pos + 3 * (size_t)i;
+        const double* vi = vel + 3 * (size_t)i;
+        double acc[10] = {0};
+        for (uint32_t k = 0; k < n_neigh[i]; k++)
+            {
+            uint32_t j = nlist[head[i] + k];
+            const double* pj = pos + 3 * (size_t)j;
+            const double* vj = vel + 3 * (size_t)j;
+            double dx[3] = {pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]};
+            double dv[3] = {vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2]};
+            min_image_inl(b, dx);
+            double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+            double rdotv = dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2];
+            uint32_t tp = type[j] * nt + type[i];
+            double rcutsq = r_cut[tp] * r_cut[tp];
+            const double epsilon = params[3 * tp], sigma = params[3 * tp + 1], gamma = params[3 * tp + 2];
+            const double sigma_6 = sigma * sigma * sigma * sigma * sigma * sigma;
+            const double lj1 = 4.0 * epsilon * sigma_6 * sigma_6, lj2 = 4.0 * epsilon * sigma_6;
+            if (!(rsq < rcutsq && lj1 != 0))
+                continue;
+            double rinv = 1.0 / sqrt(rsq);
+            double r2inv = 1.0 / rsq;
+            double r6inv = r2inv * r2inv * r2inv;
+            double rcutinv = 1.0 / sqrt(rcutsq);
+            double alpha = orc_dpd_alpha(seed, tag[i], tag[j], timestep);
+            double fdivr = r2inv * r6inv * (12.0 * lj1 * r6inv - 6.0 * lj2);
+            double fcons = fdivr;
+            fdivr -= gamma * rdotv * (rinv - rcutinv) * (rinv - rcutinv);
+            fdivr += (1.0 / sqrt(dt / (kT * gamma * 6.0))) * (rinv - rcutinv) * alpha;
+            double eng = r6inv * (lj1 * r6inv - lj2);
+            if (energy_shift)
+                {
+                double rcut2inv = 1.0 / rcutsq;
+                double rcut6inv = rcut2inv * rcut2inv * rcut2inv;
+                eng -= rcut6inv * (lj1 * rcut6inv - lj2);
+                }
+            accumulate_pair(force, virial, N, i, j, dx, fdivr, fcons, eng, 0, 1, acc);
+            }
+        for (int c = 0; c < 4; c++)
+            force[4 * (size_t)i + c] += acc[c];
+        for (int l = 0; l < 6; l++)
+            virial[(size_t)l * N + i] += acc[4 + l];
+        }
+    }
+
 /* ---------------------------------------------------------------- integration ---- */
 
 void orc_step_one(const orc_box* b, double* pos, double* vel, const double* accel, int* image,

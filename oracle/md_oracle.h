@@ -117,6 +117,14 @@ void orc_seed_key(uint8_t id, uint64_t timestep, uint16_t seed, uint32_t key[2])
 /* uniform in [-1,1] for the DPD pair (tag_i, tag_j) — EvaluatorPairDPDThermoDPD.h:250-254 */
 double orc_dpd_alpha(uint16_t seed, uint32_t tag_i, uint32_t tag_j, uint64_t timestep);
 
+/* DPDLJ: LJ conservative force + the DPD thermostat (hoomd/md/EvaluatorPairDPDThermoLJ.h); full list;
+ * params = (epsilon, sigma, gamma) per type pair */
+void orc_pair_dpdlj(const orc_box* b, const double* pos, const double* vel, const uint32_t* type,
+                    const uint32_t* tag, uint32_t N, const uint32_t* n_neigh, const uint64_t* head,
+                    const uint32_t* nlist, const double* params, const double* r_cut, uint32_t nt,
+                    int energy_shift, uint16_t seed, uint64_t timestep, double dt, double kT, double* force,
+                    double* virial);
+
 /* hoomd/md/TwoStepConstantVolume.cc:7-80 / :213-261. vel N x 3, mass N, accel N x 3, image N x 3 */
 void orc_step_one(const orc_box* b, double* pos, double* vel, const double* accel, int* image,
                   uint32_t n, double dt, double rescale);

@@ -202,6 +202,24 @@ def pair_dpd(box, pos, vel, types, tags, n_neigh, head, nl, params, r_cut, seed,
     return force, virial
 
 
+def pair_dpdlj(box, pos, vel, types, tags, n_neigh, head, nl, params, r_cut, seed, timestep, dt, kT,
+               energy_shift=False):
+    """params: flat (ntypes^2, 3) of (epsilon, sigma, gamma); full list."""
+    pos, vel, types, tags = _f64(pos), _f64(vel), _u32(types), _u32(tags)
+    params, r_cut = _f64(params), _f64(r_cut)
+    nt = int(round(np.sqrt(r_cut.size)))
+    n = n_neigh.size
+    force = np.zeros((n, 4))
+    virial = np.zeros((6, n))
+    lib().orc_pair_dpdlj(C.byref(box), _p(pos, C.c_double), _p(vel, C.c_double), _p(types, C.c_uint32),
+                         _p(tags, C.c_uint32), C.c_uint32(n), _p(_u32(n_neigh), C.c_uint32),
+                         _p(np.ascontiguousarray(head, dtype=np.uint64), C.c_uint64), _p(_u32(nl), C.c_uint32),
+                         _p(params, C.c_double), _p(r_cut, C.c_double), C.c_uint32(nt),
+                         C.c_int(int(energy_shift)), C.c_uint16(seed), C.c_uint64(timestep), C.c_double(dt),
+                         C.c_double(kT), _p(force, C.c_double), _p(virial, C.c_double))
+    return force, virial
+
+
 def eval_lj(rsq, rcutsq, epsilon, sigma, energy_shift=False):
     f = C.c_double(0)
     e = C.c_double(0)

@@ -355,6 +355,51 @@ def test_langevin_temperature(hoomd):
     assert abs(np.mean(temps) / 2.0 - 1.0) < 0.02
 
 
+def test_dpdlj(hoomd, oracle, golden_dir):
+    """hoomd.md.pair.DPDLJ: the conservative energies of the reference's table
+    (forces_and_energies.json; the reference skips its force check because of the random force,
+    hoomd/md/pytest/test_potential.py:1019-1021), and conservative + drag + random force against the
+    oracle on a liquid with moving particles, at a timestep beyond 2^32."""
+    with open(os.path.join(golden_dir, "ref_vectors.json")) as f:
+        tab = json.load(f)["forces_and_energies"]["DPDLJ"]
+    for p, E in zip(tab["params"], tab["energies"]):
+        for d, e_ref in zip((0.75, 1.5), E):
+            pos = np.array([[0, 0, 0.1], [0, 0, 0.1 + d]], dtype=np.float32)
+            sim = make_sim(hoomd, [20.0, 20.0, 20.0], pos, np.zeros_like(pos))
+            pot = hoomd.md.pair.DPDLJ(nlist=hoomd.md.nlist.Cell(buffer=0.4), kT=1.0, default_r_cut=2.5)
+            pot.params[("A", "A")] = p
+            cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+            sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[cv], forces=[pot])
+            sim.run(0)
+            assert np.isclose(pot.energy, e_ref, rtol=2e-5, atol=1e-6 if e_ref == 0 else 0), (p, d)
+    pos, vel, L = random_liquid(16, 0.8, seed=21, jitter=0.15)
+    n = len(pos)
+    step = (1 << 33) + 5
+    sim = make_sim(hoomd, L, pos, vel, seed=9, timestep=step)
+    sim.always_compute_pressure = True
+    cell = hoomd.md.nlist.Cell(buffer=0.3)
+    pot = hoomd.md.pair.DPDLJ(nlist=cell, kT=1.3, default_r_cut=2.0, mode="shift")
+    pot.params[("A", "A")] = dict(epsilon=1.0, sigma=0.9, gamma=4.5)
+    cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.004, methods=[cv], forces=[pot])
+    sim.run(0)
+    box = oracle.make_box([float(v) for v in L])
+    types, tags = np.zeros(n, dtype=np.uint32), np.arange(n, dtype=np.uint32)
+    nn, head, nl, _ = oracle.nlist(box, pos, types, [2.0], 0.3, full=True)
+    f_ref, v_ref = oracle.pair_dpdlj(box, pos, vel, types, tags, nn, head, nl, [[1.0, 0.9, 4.5]], [2.0],
+                                     9, step, 0.004, 1.3, energy_shift=True)
+    # the random force is O(sqrt(6 kT gamma / dt)) ~ 90 per pair: fp32 alpha carries 2^-24 of it
+    assert force_err(pot.forces, f_ref[:, :3]) <= 3e-5
+    e_ref = f_ref[:, 3].sum()
+    assert abs(pot.energy - e_ref) <= TOTAL_RTOL * abs(e_ref)
+    assert np.abs(pot.forces.sum(axis=0)).max() <= 1e-5 * np.abs(pot.forces).sum()  # third law incl. noise
+    f_cons, _ = oracle.pair_lj(box, pos, types, nn, head, nl, [[1.0, 0.9]], [2.0], shift_mode=1)
+    assert force_err(pot.forces, f_cons[:, :3]) > 1e-2  # the thermostat forces are really there
+    # virial is the conservative part only (hoomd/md/PotentialPairDPDThermo.h:227-236)
+    vs, vs_ref = pot.virials.sum(axis=0), v_ref.sum(axis=1)
+    assert np.max(np.abs(vs - vs_ref)) <= 1e-5 * np.max(np.abs(vs_ref))
+
+
 # ------------------------------------------------------------------ oracle on seeded inputs ----
 def random_liquid(n_side, rho, seed, jitter=0.1):
     rng = np.random.default_rng(seed)
