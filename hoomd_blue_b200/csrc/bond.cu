@@ -1,4 +1,4 @@
-// bond.cu — harmonic bond forces and the bond-exclusion filter of the neighbour list.
+// bond.cu — bond forces (harmonic, FENE + WCA) and the bond-exclusion filter of the neighbour list.
 //
 // Replaces PotentialBond<EvaluatorBondHarmonic>::computeForces (hoomd/md/PotentialBond.h:176-312,
 // GPU: gpu_compute_bond_forces_kernel hoomd/md/PotentialBondGPU.cuh) and NeighborList::filterNlist with
@@ -16,14 +16,63 @@ namespace hb2
     {
 constexpr int BOND_BLOCK = 128;
 
+// EvaluatorBondHarmonic (hoomd/md/EvaluatorBondHarmonic.h:104-124): p = (k, r0)
+struct BondHarmonic
+    {
+    HB2_DEVICE static bool eval(float rsq, const float* p, float& fdr, float& eng)
+        {
+        const float r = sqrtf(rsq);
+        fdr = p[0] * (p[1] / r - 1.0f);
+        if (!isfinite(fdr))
+            fdr = 0.f;
+        const float d = p[1] - r;
+        eng = 0.5f * p[0] * d * d;
+        return true;
+        }
+    };
+
+// EvaluatorBondFENE (hoomd.md.bond.FENEWCA, hoomd/md/EvaluatorBondFENE.h:117-158):
+// p = (k, r0, lj1, lj2, delta); false when the bond is stretched beyond r0
+struct BondFENEWCA
+    {
+    HB2_DEVICE static bool eval(float rsq_in, const float* p, float& fdr, float& eng)
+        {
+        const float K = p[0], r_0 = p[1], lj1 = p[2], lj2 = p[3], delta = p[4];
+        const float r = sqrtf(rsq_in);
+        const float rtemp = r - delta;
+        const float rmdoverr = rtemp / r;
+        const float rsq = rtemp * rtemp;
+        const float r2inv = 1.0f / rsq;
+        const float r6inv = r2inv * r2inv * r2inv;
+        float wca = 0.f, pair_eng = 0.f;
+        const float sigma6inv = lj2 / lj1;
+        const float epsilon = lj2 * lj2 / 4.0f / lj1;
+        if (lj1 != 0.f && r6inv > sigma6inv / 2.0f)
+            {
+            wca = r2inv * r6inv * (12.0f * lj1 * r6inv - 6.0f * lj2);
+            pair_eng = r6inv * (lj1 * r6inv - lj2) + epsilon;
+            }
+        fdr = wca * rmdoverr;
+        eng = pair_eng;
+        if (K != 0.f)
+            {
+            if (rsq >= r_0 * r_0)
+                return false;
+            fdr += -K / (1.0f - rsq / (r_0 * r_0)) * rmdoverr;
+            eng += -0.5f * K * (r_0 * r_0) * logf(1.0f - rsq / (r_0 * r_0));
+            }
+        return true;
+        }
+    };
+
 // ACCUM: add to `force` / `virial` (the integrator's net force = pair force + bonds); otherwise
 // overwrite (the bond force's own arrays, for its getters).
-template<bool ACCUM>
+template<class Ev, bool ACCUM>
 __global__ void __launch_bounds__(BOND_BLOCK)
-    bond_harmonic_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
+    bond_force_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
                          const uint32_t* __restrict__ rtag, uint32_t N, uint32_t Ntot,
                          const uint32_t* __restrict__ head, const uint32_t* __restrict__ partner,
-                         const uint32_t* __restrict__ btype, const float2* __restrict__ params, BoxD box,
+                         const uint32_t* __restrict__ btype, const float* __restrict__ params, BoxD box,
                          float4* __restrict__ force, float* __restrict__ virial, size_t virial_pitch,
                          const uint32_t* __restrict__ skip_flag, uint32_t* __restrict__ err)
     {
@@ -55,17 +104,16 @@ __global__ void __launch_bounds__(BOND_BLOCK)
         min_image_exact(box, dx, dy, dz);
         const float x = (float)dx, y = (float)dy, z = (float)dz;
         const float rsq = x * x + y * y + z * z;
-        // hoomd/md/EvaluatorBondHarmonic.h:104-124
-        const float2 prm = params[btype[k]];
-        const float r = sqrtf(rsq);
-        float fdr = prm.x * (prm.y / r - 1.0f);
-        if (!isfinite(fdr))
-            fdr = 0.f;
-        const float d = prm.y - r;
+        float fdr, eng;
+        if (!Ev::eval(rsq, params + HB2_BOND_PARAM_FLOATS * btype[k], fdr, eng))
+            {
+            atomicMax(err + 1, t + 1u); // "bond out of bounds" (PotentialBond.h:297-303)
+            continue;
+            }
         fx += fdr * x;
         fy += fdr * y;
         fz += fdr * z;
-        pe += 0.5f * (0.5f * prm.x * d * d);
+        pe += 0.5f * eng;
         if (virial)
             {
             const float f2 = 0.5f * fdr;
@@ -100,21 +148,30 @@ __global__ void __launch_bounds__(BOND_BLOCK)
         }
     }
 
-hb2_status launch_bond_harmonic(const BondArgs& a, bool accumulate, const hb2_box& box, cudaStream_t stream)
+template<class Ev>
+static hb2_status launch_bond_ev(const BondArgs& a, bool accumulate, const hb2_box& box, cudaStream_t stream)
     {
-    if (a.N == 0)
-        return HB2_OK;
     const uint32_t blocks = (a.N + BOND_BLOCK - 1) / BOND_BLOCK;
     if (accumulate)
-        bond_harmonic_kernel<true><<<blocks, BOND_BLOCK, 0, stream>>>(
+        bond_force_kernel<Ev, true><<<blocks, BOND_BLOCK, 0, stream>>>(
             a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, a.partner, a.btype, a.params, boxd(box), a.force,
             a.virial, a.virial_pitch, a.skip_flag, a.err);
     else
-        bond_harmonic_kernel<false><<<blocks, BOND_BLOCK, 0, stream>>>(
+        bond_force_kernel<Ev, false><<<blocks, BOND_BLOCK, 0, stream>>>(
             a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, a.partner, a.btype, a.params, boxd(box), a.force,
             a.virial, a.virial_pitch, a.skip_flag, a.err);
-    HB2_CHECK_LAUNCH("bond_harmonic_kernel");
+    HB2_CHECK_LAUNCH("bond_force_kernel");
     return HB2_OK;
+    }
+
+hb2_status launch_bond_forces(hb2_bond_kind kind, const BondArgs& a, bool accumulate, const hb2_box& box,
+                              cudaStream_t stream)
+    {
+    if (a.N == 0)
+        return HB2_OK;
+    if (kind == HB2_BOND_FENEWCA)
+        return launch_bond_ev<BondFENEWCA>(a, accumulate, box, stream);
+    return launch_bond_ev<BondHarmonic>(a, accumulate, box, stream);
     }
 
 // One warp per row: entries whose particle is bonded to the row's owner are dropped, the row is

@@ -1790,20 +1790,21 @@ extern "C" hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds)
     return HB2_OK;
     }
 
-extern "C" hb2_status hb2_bond_create(hb2_bond** out, hb2_system* s)
+extern "C" hb2_status hb2_bond_create(hb2_bond** out, hb2_system* s, hb2_bond_kind kind)
     {
-    if (!out || !s)
+    if (!out || !s || (kind != HB2_BOND_HARMONIC && kind != HB2_BOND_FENEWCA))
         return HB2_ERR_INVALID;
     hb2_bond* b = new hb2_bond();
     b->sys = s;
+    b->kind = kind;
     HB2_CUDA(cudaSetDevice(s->device));
-    hb2_status st = dev_alloc(&b->d_err, 1);
+    hb2_status st = dev_alloc(&b->d_err, 2);
     if (st != HB2_OK)
         {
         delete b;
         return st;
         }
-    cudaMemset(b->d_err, 0, sizeof(uint32_t));
+    cudaMemset(b->d_err, 0, 2 * sizeof(uint32_t));
     *out = b;
     return HB2_OK;
     }
@@ -1821,18 +1822,32 @@ extern "C" void hb2_bond_destroy(hb2_bond* b)
     delete b;
     }
 
-extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, double k, double r0)
+extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const double* user, uint32_t n_user)
     {
-    if (!b)
-        return HB2_ERR_INVALID;
-    if (type >= b->k.size())
+    const uint32_t need = b && b->kind == HB2_BOND_FENEWCA ? 5u : 2u;
+    if (!b || !user || n_user < need)
         {
-        b->k.resize(type + 1, 0.0);
-        b->r0.resize(type + 1, 0.0);
+        set_error("hb2_bond_set_params: harmonic takes {k, r0}, FENEWCA {k, r0, epsilon, sigma, delta}");
+        return HB2_ERR_INVALID;
+        }
+    if (type >= b->have.size())
+        {
+        b->packed.resize(HB2_BOND_PARAM_FLOATS * (size_t)(type + 1), 0.f);
         b->have.resize(type + 1, 0);
         }
-    b->k[type] = k;
-    b->r0[type] = r0;
+    float* p = &b->packed[HB2_BOND_PARAM_FLOATS * (size_t)type];
+    p[0] = (float)user[0];
+    p[1] = (float)user[1];
+    if (b->kind == HB2_BOND_FENEWCA)
+        {
+        // hoomd/md/EvaluatorBondFENE.h:44-53 keeps sigma^6 and 4 epsilon as Scalars; lj1, lj2 from them
+        const float sigma = (float)user[3];
+        const float sigma_6 = sigma * sigma * sigma * sigma * sigma * sigma;
+        const float epsilon_x_4 = 4.0f * (float)user[2];
+        p[2] = epsilon_x_4 * sigma_6 * sigma_6;
+        p[3] = epsilon_x_4 * sigma_6;
+        p[4] = (float)user[4];
+        }
     b->have[type] = 1;
     b->params_dirty = true;
     return HB2_OK;
@@ -1844,16 +1859,15 @@ hb2_status hb2_bond::upload_params()
     for (uint32_t t = 0; t < nt; t++)
         if (t >= have.size() || !have[t])
             {
-            set_error("bond.harmonic: parameters of bond type " + std::to_string(t) + " are not set");
+            set_error("bond: parameters of bond type " + std::to_string(t) + " are not set");
             return HB2_ERR_INVALID;
             }
-    std::vector<float2> h(std::max<uint32_t>(1, nt));
-    for (uint32_t t = 0; t < nt; t++)
-        h[t] = make_float2((float)k[t], (float)r0[t]);
+    std::vector<float> h(HB2_BOND_PARAM_FLOATS * (size_t)std::max<uint32_t>(1, nt), 0.f);
+    std::copy(packed.begin(), packed.begin() + std::min(packed.size(), h.size()), h.begin());
     dev_free(d_params);
     d_params = nullptr;
     HB2_TRY(dev_alloc(&d_params, h.size()));
-    HB2_CUDA(cudaMemcpyAsync(d_params, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, sys->stream));
+    HB2_CUDA(cudaMemcpyAsync(d_params, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, sys->stream));
     HB2_CUDA(cudaStreamSynchronize(sys->stream));
     params_dirty = false;
     return HB2_OK;
@@ -1887,7 +1901,7 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     a.virial_pitch = virial_pitch;
     a.skip_flag = skip_flag;
     a.err = d_err;
-    return launch_bond_harmonic(a, accumulate, s->box, s->stream);
+    return launch_bond_forces(kind, a, accumulate, s->box, s->stream);
     }
 
 hb2_status hb2_bond::compute_own()
@@ -1910,13 +1924,16 @@ hb2_status hb2_bond::compute_own()
 
 hb2_status hb2_bond::check_complete()
     {
-    uint32_t e = 0;
-    HB2_CUDA(cudaMemcpyAsync(&e, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, sys->stream));
+    uint32_t e[2] = {0, 0};
+    HB2_CUDA(cudaMemcpyAsync(e, d_err, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sys->stream));
     HB2_CUDA(cudaStreamSynchronize(sys->stream));
-    if (e)
+    if (e[0] || e[1])
         {
-        HB2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), sys->stream));
-        set_error("Error: a bond with particle " + std::to_string(e - 1) + " is incomplete.");
+        HB2_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(uint32_t), sys->stream));
+        if (e[0])
+            set_error("Error: a bond with particle " + std::to_string(e[0] - 1) + " is incomplete.");
+        else
+            set_error("bond.fene: bond out of bounds (particle " + std::to_string(e[1] - 1) + ")");
         return HB2_ERR_INVALID;
         }
     return HB2_OK;

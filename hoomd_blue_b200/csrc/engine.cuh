@@ -191,10 +191,11 @@ struct hb2_pair
 struct hb2_bond
     {
     hb2_system* sys = nullptr;
-    std::vector<double> k, r0;
+    hb2_bond_kind kind = HB2_BOND_HARMONIC;
+    std::vector<float> packed; // HB2_BOND_PARAM_FLOATS per bond type
     std::vector<char> have;
     bool params_dirty = true;
-    float2* d_params = nullptr;
+    float* d_params = nullptr;
     float4* d_force = nullptr;
     float* d_virial = nullptr;
     uint32_t cap_N = 0;

@@ -63,14 +63,16 @@ struct BondArgs
     const uint32_t* head;    // bond table by tag (CSR), partner tags, bond types
     const uint32_t* partner;
     const uint32_t* btype;
-    const float2* params;    // (k, r0) per bond type
+    const float* params;     // HB2_BOND_PARAM_FLOATS floats per bond type
     float4* force;
     float* virial;           // null: not computed
     size_t virial_pitch;
     const uint32_t* skip_flag;
-    uint32_t* err;           // <- 1 + tag of a partner that is not on this device
+    uint32_t* err;           // [0] <- 1 + tag of a partner that is not on this device,
+                             // [1] <- 1 + tag of a particle with a bond out of bounds
     };
-hb2_status launch_bond_harmonic(const BondArgs& a, bool accumulate, const hb2_box& box, cudaStream_t stream);
+hb2_status launch_bond_forces(hb2_bond_kind kind, const BondArgs& a, bool accumulate, const hb2_box& box,
+                              cudaStream_t stream);
 hb2_status launch_nlist_filter_bonds(uint32_t N, const uint32_t* tag, const uint32_t* rtag,
                                      const uint32_t* head, const uint32_t* partner, uint32_t* nlist,
                                      uint32_t pitch, uint32_t* n_neigh, uint32_t dummy_index,

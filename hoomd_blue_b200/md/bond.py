@@ -10,11 +10,8 @@ from .._lib import check
 
 class Bond:
     _loggables = {"energy": "scalar"}
-
-
-class Harmonic(Bond):
-    """hoomd.md.bond.Harmonic(): V(r) = k/2 (r - r0)^2, params[bond type] = dict(k=, r0=)
-    (hoomd/md/bond.py:96-131, hoomd/md/EvaluatorBondHarmonic.h)."""
+    _kind = 0
+    _param_keys = ()
 
     def __init__(self):
         self.params = {}
@@ -26,7 +23,7 @@ class Harmonic(Bond):
             return
         L = _lib.lib()
         h = C.c_void_p()
-        check(L.hb2_bond_create(C.byref(h), sim.state._h))
+        check(L.hb2_bond_create(C.byref(h), sim.state._h, self._kind))
         self._h, self._sim = h, sim
         self._sync()
 
@@ -35,8 +32,11 @@ class Harmonic(Bond):
         for name, prm in self.params.items():
             if name not in types:
                 raise KeyError(f"bond type {name!r} is not in the state ({types})")
-            check(_lib.lib().hb2_bond_set_params(self._h, types.index(name), float(prm["k"]),
-                                                 float(prm["r0"])))
+            missing = [k for k in self._param_keys if k not in prm]
+            if missing:
+                raise KeyError(f"bond parameters {missing} are missing for {name!r}")
+            arr = (C.c_double * len(self._param_keys))(*[float(prm[k]) for k in self._param_keys])
+            check(_lib.lib().hb2_bond_set_params(self._h, types.index(name), arr, len(self._param_keys)))
 
     def _detach(self):
         if self._h is not None:
@@ -73,3 +73,18 @@ class Harmonic(Bond):
     @property
     def energy(self):
         return self._get("energy")
+
+
+class Harmonic(Bond):
+    """hoomd.md.bond.Harmonic(): V(r) = k/2 (r - r0)^2, params[bond type] = dict(k=, r0=)
+    (hoomd/md/bond.py:96-131, hoomd/md/EvaluatorBondHarmonic.h)."""
+    _kind = 0
+    _param_keys = ("k", "r0")
+
+
+class FENEWCA(Bond):
+    """hoomd.md.bond.FENEWCA(): FENE spring + WCA core in r - delta, params[bond type] =
+    dict(k=, r0=, epsilon=, sigma=, delta=) (hoomd/md/bond.py:134-196, hoomd/md/EvaluatorBondFENE.h).
+    A bond stretched beyond r0 raises "bond out of bounds"."""
+    _kind = 1
+    _param_keys = ("k", "r0", "epsilon", "sigma", "delta")

@@ -174,6 +174,12 @@ hb2_status hb2_gpu_nve_step_two(float* d_vel4, const float* d_force4, uint32_t N
 typedef struct hb2_system hb2_system;         /* ~ SystemDefinition + ParticleData (hoomd/ParticleData.h:1285) */
 typedef struct hb2_nlist hb2_nlist;           /* ~ NeighborListGPUBinned (hoomd/md/NeighborList.h:121) */
 typedef struct hb2_pair hb2_pair;             /* ~ PotentialPairGPU<evaluator> (hoomd/md/PotentialPairGPU.h:89) */
+#define HB2_BOND_PARAM_FLOATS 8
+typedef enum hb2_bond_kind
+    {
+    HB2_BOND_HARMONIC = 0, /* hoomd/md/EvaluatorBondHarmonic.h */
+    HB2_BOND_FENEWCA = 1   /* hoomd/md/EvaluatorBondFENE.h */
+    } hb2_bond_kind;
 typedef struct hb2_bond hb2_bond;             /* ~ PotentialBond<EvaluatorBondHarmonic> */
 typedef struct hb2_integrator hb2_integrator; /* ~ IntegratorTwoStep + TwoStepConstantVolume */
 
@@ -295,16 +301,16 @@ hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat
  * (hoomd/BondedGroupData.h) — `group` holds 2 member TAGS per bond, `typeid_` the bond types; call
  * after the particles are set. hb2_nlist_set_exclusions: exclusions=('bond',) (the reference's default,
  * hoomd/md/nlist.py:87-102; hoomd/md/NeighborList.cc:569-640,1487-1536) drops bonded pairs from the
- * list. hb2_bond_*: hoomd.md.bond.Harmonic (hoomd/md/PotentialBond.h:176-312,
- * hoomd/md/EvaluatorBondHarmonic.h) with (k, r0) per bond type; hb2_bond_get returns per-particle
+ * list. hb2_bond_*: hoomd.md.bond.Harmonic / FENEWCA (hoomd/md/PotentialBond.h:176-312,
+ * hoomd/md/EvaluatorBondHarmonic.h {k, r0}, hoomd/md/EvaluatorBondFENE.h {k, r0, epsilon, sigma, delta}); hb2_bond_get returns per-particle
  * forces (N x 3), energies (N), virials (N x 6) in tag order and the total energy (any may be null).
  * hb2_integrator_add_bond: the bond forces are added to the pair force (net force) every step. */
 hb2_status hb2_system_set_bonds(hb2_system* sys, uint32_t n_bonds, const uint32_t* group,
                                 const uint32_t* typeid_, uint32_t n_bond_types);
 hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds);
-hb2_status hb2_bond_create(hb2_bond** out, hb2_system* sys);
+hb2_status hb2_bond_create(hb2_bond** out, hb2_system* sys, hb2_bond_kind kind);
 void hb2_bond_destroy(hb2_bond* b);
-hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, double k, double r0);
+hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const double* user_params, uint32_t n_user);
 hb2_status hb2_bond_get(hb2_bond* b, double* forces3, double* energies, double* virials6,
                         double* energy_total);
 hb2_status hb2_integrator_add_bond(hb2_integrator* it, hb2_bond* b);

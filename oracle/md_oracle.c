@@ -627,9 +627,9 @@ void orc_filter_bond_exclusions(uint32_t n, uint32_t* n_neigh, const uint64_t* h
     free(fill);
     }
 
-int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
-                      const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
-                      const double* params, double* force, double* virial)
+static int bond_forces(int kind, const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                       const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
+                       const double* params, uint32_t stride, double* force, double* virial)
     {
     /* hoomd/md/PotentialBond.h:176-312 */
     memset(force, 0, sizeof(double) * 4 * (size_t)N);
@@ -643,14 +643,48 @@ int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uin
         for (int d = 0; d < 3; d++)
             dx[d] = pos[3 * (size_t)ib + d] - pos[3 * (size_t)ia + d];
         orc_min_image(b, dx);
-        const double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
-        /* hoomd/md/EvaluatorBondHarmonic.h:104-124 */
-        const double K = params[2 * bond_type[i]], r_0 = params[2 * bond_type[i] + 1];
-        const double r = sqrt(rsq);
-        double force_divr = K * (r_0 / r - 1.0);
-        if (!isfinite(force_divr))
-            force_divr = 0.0;
-        double bond_eng = 0.5 * K * (r_0 - r) * (r_0 - r);
+        double rsq = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+        const double* prm = params + (size_t)stride * bond_type[i];
+        double force_divr = 0.0, bond_eng = 0.0;
+        if (kind == 0)
+            {
+            /* hoomd/md/EvaluatorBondHarmonic.h:104-124 */
+            const double K = prm[0], r_0 = prm[1];
+            const double r = sqrt(rsq);
+            force_divr = K * (r_0 / r - 1.0);
+            if (!isfinite(force_divr))
+                force_divr = 0.0;
+            bond_eng = 0.5 * K * (r_0 - r) * (r_0 - r);
+            }
+        else
+            {
+            /* hoomd/md/EvaluatorBondFENE.h:44-53 parameters, :117-158 evaluation */
+            const double K = prm[0], r_0 = prm[1], epsilon_in = prm[2], sigma = prm[3], delta = prm[4];
+            const double sigma_6 = sigma * sigma * sigma * sigma * sigma * sigma;
+            const double lj1 = 4.0 * epsilon_in * sigma_6 * sigma_6, lj2 = 4.0 * epsilon_in * sigma_6;
+            const double rtemp = sqrt(rsq) - delta;
+            const double rmdoverr = rtemp / sqrt(rsq);
+            rsq = rtemp * rtemp;
+            const double r2inv = 1.0 / rsq;
+            const double r6inv = r2inv * r2inv * r2inv;
+            double wca = 0.0, pair_eng = 0.0;
+            const double sigma6inv = lj2 / lj1;
+            const double epsilon = lj2 * lj2 / 4.0 / lj1;
+            if (lj1 != 0 && r6inv > sigma6inv / 2.0)
+                {
+                wca = r2inv * r6inv * (12.0 * lj1 * r6inv - 6.0 * lj2);
+                pair_eng = (r6inv * (lj1 * r6inv - lj2) + epsilon);
+                }
+            force_divr = wca * rmdoverr;
+            bond_eng = pair_eng;
+            if (K != 0.0)
+                {
+                if (rsq >= r_0 * r_0)
+                    return -1 - (int)i; /* "bond out of bounds" */
+                force_divr += -K / (1.0 - rsq / (r_0 * r_0)) * rmdoverr;
+                bond_eng += -0.5 * K * (r_0 * r_0) * log(1.0 - rsq / (r_0 * r_0));
+                }
+            }
         bond_eng *= 0.5;
         const double f2 = 0.5 * force_divr;
         const double v[6] = {dx[0] * dx[0] * f2, dx[0] * dx[1] * f2, dx[0] * dx[2] * f2,
@@ -669,6 +703,20 @@ int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uin
             }
         }
     return 0;
+    }
+
+int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                      const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
+                      const double* params, double* force, double* virial)
+    {
+    return bond_forces(0, b, pos, N, rtag, bond_group, bond_type, n_bonds, params, 2, force, virial);
+    }
+
+int orc_bond_fenewca(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                     const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
+                     const double* params, double* force, double* virial)
+    {
+    return bond_forces(1, b, pos, N, rtag, bond_group, bond_type, n_bonds, params, 5, force, virial);
     }
 
 /* ---------------------------------------------------------------------- RNG ---- */

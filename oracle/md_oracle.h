@@ -110,6 +110,13 @@ int orc_bond_harmonic(const orc_box* b, const double* pos, uint32_t N, const uin
                       const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
                       const double* params, double* force, double* virial);
 
+/* PotentialBond<EvaluatorBondFENE> (hoomd.md.bond.FENEWCA, hoomd/md/EvaluatorBondFENE.h): params =
+ * (k, r0, epsilon, sigma, delta) per bond type. Returns 0, 1 + index of an incomplete bond, or
+ * -1 - index of a bond beyond r0 ("bond out of bounds"). */
+int orc_bond_fenewca(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                     const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
+                     const double* params, double* force, double* virial);
+
 /* RNG: Philox4x32-10 (Salmon et al., SC'11; hoomd/extern/random123 commit a2c4f04) and HOOMD's
  * Seed/Counter packing hoomd/RandomNumbers.h:136-199 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -312,7 +312,12 @@ def filter_bond_exclusions(n_neigh, head, nl, bond_group, tags=None):
     return nn, head2, packed
 
 
-def bond_harmonic(box, pos, bond_group, bond_type, params, tags=None):
+def bond_fenewca(box, pos, bond_group, bond_type, params, tags=None):
+    """PotentialBond<EvaluatorBondFENE>; params (k, r0, epsilon, sigma, delta) per bond type."""
+    return bond_harmonic(box, pos, bond_group, bond_type, params, tags, _fn="orc_bond_fenewca", _np=5)
+
+
+def bond_harmonic(box, pos, bond_group, bond_type, params, tags=None, _fn="orc_bond_harmonic", _np=2):
     """PotentialBond<EvaluatorBondHarmonic>: returns (force N x 4 incl. energy, virial 6 x N)."""
     pos = _f64(pos)
     n = pos.shape[0]
@@ -321,14 +326,16 @@ def bond_harmonic(box, pos, bond_group, bond_type, params, tags=None):
     rtag[tags] = np.arange(n, dtype=np.uint32)
     bg = _u32(np.asarray(bond_group).reshape(-1, 2))
     bt = _u32(bond_type)
-    params = _f64(np.asarray(params).reshape(-1, 2))
+    params = _f64(np.asarray(params).reshape(-1, _np))
     force = np.zeros((n, 4))
     virial = np.zeros((6, n))
-    rc = lib().orc_bond_harmonic(C.byref(box), _p(pos, C.c_double), C.c_uint32(n), _p(rtag, C.c_uint32),
+    rc = getattr(lib(), _fn)(C.byref(box), _p(pos, C.c_double), C.c_uint32(n), _p(rtag, C.c_uint32),
                                  _p(bg, C.c_uint32), _p(bt, C.c_uint32), C.c_uint32(bg.shape[0]),
                                  _p(params, C.c_double), _p(force, C.c_double), _p(virial, C.c_double))
-    if rc:
+    if rc > 0:
         raise RuntimeError(f"Error: bond {rc - 1} is incomplete.")
+    if rc < 0:
+        raise RuntimeError(f"bond.fene: bond out of bounds (bond {-rc - 1})")
     return force, virial
 
 

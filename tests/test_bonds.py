@@ -13,6 +13,13 @@ from tests import gsd_ref
 REF_VECTORS = [(30.0, 1.6, -18.9300, 5.9724), (25.0, 1.7, -18.2750, 6.6795), (20.0, 1.8, -16.6200, 6.9056)]
 
 
+# (params, force on particle 0 along x, total energy) hoomd/md/pytest/test_bond.py:38-58
+FENE_VECTORS = [(dict(k=30.0, r0=1.6, epsilon=0.9, sigma=1.1, delta=-0.5), 282.296, 70.5638),
+                (dict(k=25.0, r0=1.7, epsilon=1.0, sigma=1.0, delta=-0.5), 146.288, 49.2476),
+                (dict(k=20.0, r0=1.8, epsilon=1.1, sigma=0.9, delta=-0.5), 88.8238, 35.3135)]
+FENE_KEYS = ("k", "r0", "epsilon", "sigma", "delta")
+
+
 def two_particles(d=0.969):
     # hoomd/conftest.py:168-196 two_particle_snapshot_factory(d=0.969, L=5)
     return np.array([[-d / 2, 0, 0.1], [d / 2, 0, 0.1]], dtype=np.float32)
@@ -34,6 +41,26 @@ def test_oracle_harmonic_reference_vectors(oracle, k, r0, force, energy):
     far = np.array([[-2.4, 0, 0], [2.4, 0, 0]], dtype=np.float32)
     f2, _ = oracle.bond_harmonic(box, far, [[0, 1]], [0], [[k, r0]])
     assert f2[0, 0] == pytest.approx(+k * (r0 / 0.2 - 1.0) * 0.2, rel=1e-5)
+
+
+@pytest.mark.parametrize("prm,force,energy", FENE_VECTORS)
+def test_oracle_fenewca_reference_vectors(oracle, prm, force, energy):
+    box = oracle.make_box([5.0, 5.0, 5.0])
+    f, v = oracle.bond_fenewca(box, two_particles(), [[0, 1]], [0], [[prm[k] for k in FENE_KEYS]])
+    assert f[:, 3].sum() == pytest.approx(energy, rel=1e-2)
+    np.testing.assert_allclose(f[0, :3], [force, 0, 0], rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(f[1, :3], [-force, 0, 0], rtol=1e-2, atol=1e-5)
+    # F = -dE/dr by central differences of the oracle's own energy
+    h = 1e-5
+    e = [oracle.bond_fenewca(box, np.array([[-d / 2, 0, 0.1], [d / 2, 0, 0.1]]), [[0, 1]], [0],
+                             [[prm[k] for k in FENE_KEYS]])[0][:, 3].sum() for d in (0.969 - h, 0.969 + h)]
+    r = float(np.float32(0.969 / 2)) * 2
+    assert -f[1, 0] == pytest.approx((e[1] - e[0]) / (2 * h), rel=1e-4)  # force on 0 = +dE/dr (pushes apart)
+    assert r > 0
+    # stretched beyond r0 (in r - delta): "bond out of bounds"
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        oracle.bond_fenewca(box, two_particles(prm["r0"] + prm["delta"] + 0.01), [[0, 1]], [0],
+                            [[prm[k] for k in FENE_KEYS]])
 
 
 def chains(n_chains, length, rho, seed, bond=0.97):
@@ -132,6 +159,38 @@ def test_harmonic_reference_vectors(k, r0, force, energy):
     assert potential.energy == pytest.approx(0.5 * k * (r - r0) ** 2, rel=1e-6)
     back = sim.state.get_snapshot()
     assert back.bonds.N == 1 and back.bonds.types == ["A-A"] and tuple(back.bonds.group[0]) == (0, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prm,force,energy", FENE_VECTORS)
+def test_fenewca_reference_vectors(oracle, prm, force, energy):
+    import hoomd_blue_b200 as hoomd
+
+    def make(d):
+        snap = hoomd.Snapshot.from_arrays([5, 5, 5, 0, 0, 0], two_particles(d))
+        snap.bonds.N = 1
+        snap.bonds.types = ["A-A"]
+        snap.bonds.group[0] = (0, 1)
+        sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=1)
+        sim.create_state_from_snapshot(snap)
+        potential = hoomd.md.bond.FENEWCA()
+        potential.params["A-A"] = prm
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.005, forces=[potential])
+        return sim, potential
+
+    sim, potential = make(0.969)
+    sim.run(0)
+    assert sum(potential.energies) == pytest.approx(energy, rel=1e-2)
+    np.testing.assert_allclose(potential.forces[0], [force, 0.0, 0.0], rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(potential.forces[1], [-1 * force, 0.0, 0.0], rtol=1e-2, atol=1e-5)
+    box = oracle.make_box([5.0, 5.0, 5.0])
+    f_ref, _ = oracle.bond_fenewca(box, two_particles(), [[0, 1]], [0], [[prm[k] for k in FENE_KEYS]])
+    np.testing.assert_allclose(potential.forces, f_ref[:, :3], rtol=2e-5, atol=1e-5)
+    assert potential.energy == pytest.approx(f_ref[:, 3].sum(), rel=2e-5)
+    sim, potential = make(prm["r0"] + prm["delta"] + 0.01)
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        sim.run(0)
+        potential.forces
 
 
 @pytest.mark.gpu
