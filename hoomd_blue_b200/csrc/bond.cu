@@ -174,6 +174,148 @@ hb2_status launch_bond_forces(hb2_bond_kind kind, const BondArgs& a, bool accumu
     return launch_bond_ev<BondHarmonic>(a, accumulate, box, stream);
     }
 
+// Angle forces, owner-computes: particle i walks the angles it is a member of (table keyed by tag:
+// the three member tags and `type | role << 30`), recomputes the triplet's forces exactly as the
+// reference's loop over angles does and keeps its own share (role 0: a, 1: the vertex b, 2: c).
+// KIND 0: hoomd/md/HarmonicAngleForceCompute.cc:104-258; 1: hoomd/md/CosineSqAngleForceCompute.cc.
+template<int KIND, bool ACCUM>
+__global__ void __launch_bounds__(BOND_BLOCK)
+    angle_force_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
+                       const uint32_t* __restrict__ rtag, uint32_t N, uint32_t Ntot,
+                       const uint32_t* __restrict__ head, const uint4* __restrict__ members,
+                       const float* __restrict__ params, BoxD box, float4* __restrict__ force,
+                       float* __restrict__ virial, size_t virial_pitch,
+                       const uint32_t* __restrict__ skip_flag, uint32_t* __restrict__ err)
+    {
+    if (skip_flag && *skip_flag)
+        return;
+    const uint32_t i = blockIdx.x * BOND_BLOCK + threadIdx.x;
+    if (i >= N)
+        return;
+    const uint32_t t = tag[i];
+    const uint32_t k0 = head[t], k1 = head[t + 1];
+    if (ACCUM && k0 == k1)
+        return;
+    float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (uint32_t k = k0; k < k1; k++)
+        {
+        const uint4 m = members[k];
+        const uint32_t ia = rtag[m.x], ib = rtag[m.y], ic = rtag[m.z];
+        if (ia >= Ntot || ib >= Ntot || ic >= Ntot)
+            {
+            atomicMax(err, t + 1u);
+            continue;
+            }
+        const uint32_t role = m.w >> 30, type = m.w & 0x3fffffffu;
+        const float4 pa = pos[ia], pb = pos[ib], pc = pos[ic];
+        double ax = (double)pa.x - (double)pb.x, ay = (double)pa.y - (double)pb.y, az = (double)pa.z - (double)pb.z;
+        double cx = (double)pc.x - (double)pb.x, cy = (double)pc.y - (double)pb.y, cz = (double)pc.z - (double)pb.z;
+        min_image_exact(box, ax, ay, az);
+        min_image_exact(box, cx, cy, cz);
+        const float dab[3] = {(float)ax, (float)ay, (float)az}, dcb[3] = {(float)cx, (float)cy, (float)cz};
+        const float rsqab = dab[0] * dab[0] + dab[1] * dab[1] + dab[2] * dab[2];
+        const float rab = sqrtf(rsqab);
+        const float rsqcb = dcb[0] * dcb[0] + dcb[1] * dcb[1] + dcb[2] * dcb[2];
+        const float rcb = sqrtf(rsqcb);
+        float c_abbc = (dab[0] * dcb[0] + dab[1] * dcb[1] + dab[2] * dcb[2]) / (rab * rcb);
+        c_abbc = fminf(1.0f, fmaxf(-1.0f, c_abbc));
+        const float K = params[HB2_BOND_PARAM_FLOATS * type], t_0 = params[HB2_BOND_PARAM_FLOATS * type + 1];
+        float a, eng;
+        if (KIND == 0)
+            {
+            float s_abbc = sqrtf(1.0f - c_abbc * c_abbc);
+            if (s_abbc < 0.001f)
+                s_abbc = 0.001f;
+            s_abbc = 1.0f / s_abbc;
+            const float dth = acosf(c_abbc) - t_0;
+            const float tk = K * dth;
+            a = -1.0f * tk * s_abbc;
+            eng = (tk * dth) * (1.0f / 6.0f);
+            }
+        else
+            {
+            const float dcosth = c_abbc - cosf(t_0);
+            const float tk = K * dcosth;
+            a = tk;
+            eng = (tk * dcosth) * (1.0f / 6.0f);
+            }
+        const float a11 = a * c_abbc / rsqab, a12 = -a / (rab * rcb), a22 = a * c_abbc / rsqcb;
+        float fab[3], fcb[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            {
+            fab[d] = a11 * dab[d] + a12 * dcb[d];
+            fcb[d] = a22 * dcb[d] + a12 * dab[d];
+            }
+        const float sa = role == 0 ? 1.f : (role == 1 ? -1.f : 0.f);
+        const float sc = role == 2 ? 1.f : (role == 1 ? -1.f : 0.f);
+        fx += sa * fab[0] + sc * fcb[0];
+        fy += sa * fab[1] + sc * fcb[1];
+        fz += sa * fab[2] + sc * fcb[2];
+        pe += eng;
+        if (virial)
+            {
+            v[0] += (1.f / 3.f) * (dab[0] * fab[0] + dcb[0] * fcb[0]);
+            v[1] += (1.f / 3.f) * (dab[1] * fab[0] + dcb[1] * fcb[0]);
+            v[2] += (1.f / 3.f) * (dab[2] * fab[0] + dcb[2] * fcb[0]);
+            v[3] += (1.f / 3.f) * (dab[1] * fab[1] + dcb[1] * fcb[1]);
+            v[4] += (1.f / 3.f) * (dab[2] * fab[1] + dcb[2] * fcb[1]);
+            v[5] += (1.f / 3.f) * (dab[2] * fab[2] + dcb[2] * fcb[2]);
+            }
+        }
+    if (ACCUM)
+        {
+        float4 f = force[i];
+        f.x += fx;
+        f.y += fy;
+        f.z += fz;
+        f.w += pe;
+        force[i] = f;
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                virial[q * virial_pitch + i] += v[q];
+        }
+    else
+        {
+        force[i] = make_float4(fx, fy, fz, pe);
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                virial[q * virial_pitch + i] = v[q];
+        }
+    }
+
+hb2_status launch_angle_forces(hb2_bond_kind kind, const BondArgs& a, const uint4* members, bool accumulate,
+                               const hb2_box& box, cudaStream_t stream)
+    {
+    if (a.N == 0)
+        return HB2_OK;
+    const uint32_t blocks = (a.N + BOND_BLOCK - 1) / BOND_BLOCK;
+#define HB2_ANGLE_LAUNCH(K, ACC)                                                                          \
+    angle_force_kernel<K, ACC><<<blocks, BOND_BLOCK, 0, stream>>>(                                        \
+        a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, members, a.params, boxd(box), a.force, a.virial,       \
+        a.virial_pitch, a.skip_flag, a.err)
+    if (kind == HB2_ANGLE_COSINESQ)
+        {
+        if (accumulate)
+            HB2_ANGLE_LAUNCH(1, true);
+        else
+            HB2_ANGLE_LAUNCH(1, false);
+        }
+    else
+        {
+        if (accumulate)
+            HB2_ANGLE_LAUNCH(0, true);
+        else
+            HB2_ANGLE_LAUNCH(0, false);
+        }
+#undef HB2_ANGLE_LAUNCH
+    HB2_CHECK_LAUNCH("angle_force_kernel");
+    return HB2_OK;
+    }
+
 // One warp per row: entries whose particle is bonded to the row's owner are dropped, the row is
 // compacted in place (a 32-entry chunk is read completely before the chunk's survivors are written at
 // or below its start) and padded again with the dummy index up to a multiple of 32.

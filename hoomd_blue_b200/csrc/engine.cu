@@ -145,6 +145,8 @@ extern "C" void hb2_system_destroy(hb2_system* s)
     dev_free(s->d_bond_head);
     dev_free(s->d_bond_partner);
     dev_free(s->d_bond_type);
+    dev_free(s->d_angle_head);
+    dev_free(s->d_angle_members);
     dev_free(s->d_stage);
     if (s->h_stage)
         cudaFreeHost(s->h_stage);
@@ -1705,6 +1707,8 @@ extern "C" hb2_status hb2_pair_get_additional(hb2_pair* p, double* energy, doubl
 // integrator
 // =================================================================================================
 // ---------------------------------------------------------------------------------- bonds ----
+static hb2_status ensure_domain_rtag(hb2_system* s);
+
 extern "C" hb2_status hb2_system_set_bonds(hb2_system* s, uint32_t n_bonds, const uint32_t* group,
                                            const uint32_t* typeid_, uint32_t n_bond_types)
     {
@@ -1722,12 +1726,7 @@ extern "C" hb2_status hb2_system_set_bonds(hb2_system* s, uint32_t n_bonds, cons
     if (s->dom.active && s->dom.N_global >= 0xffffffffull)
         return HB2_ERR_INVALID;
     const uint32_t N = s->dom.active ? (uint32_t)s->dom.N_global : s->N;
-    if (s->dom.active && !s->rtag)
-        {
-        HB2_CUDA(cudaSetDevice(s->device));
-        HB2_TRY(dev_alloc(&s->rtag, (size_t)N));
-        HB2_CUDA(cudaMemset(s->rtag, 0xff, sizeof(uint32_t) * (size_t)N));
-        }
+    HB2_TRY(ensure_domain_rtag(s));
     std::vector<uint32_t> head((size_t)N + 1, 0u), partner(2 * (size_t)n_bonds), type(2 * (size_t)n_bonds);
     for (uint32_t k = 0; k < n_bonds; k++)
         {
@@ -1779,6 +1778,73 @@ extern "C" hb2_status hb2_system_set_bonds(hb2_system* s, uint32_t n_bonds, cons
     return HB2_OK;
     }
 
+static hb2_status ensure_domain_rtag(hb2_system* s)
+    {
+    if (s->dom.active && !s->rtag)
+        {
+        HB2_CUDA(cudaSetDevice(s->device));
+        HB2_TRY(dev_alloc(&s->rtag, (size_t)s->dom.N_global));
+        HB2_CUDA(cudaMemset(s->rtag, 0xff, sizeof(uint32_t) * (size_t)s->dom.N_global));
+        for (auto* nl : s->nlists)
+            nl->force_update = true; // the next rebuild fills the table
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_system_set_angles(hb2_system* s, uint32_t n_angles, const uint32_t* group,
+                                            const uint32_t* typeid_, uint32_t n_angle_types)
+    {
+    if (!s || (n_angles && (!group || !typeid_)))
+        return HB2_ERR_INVALID;
+    if (!s->pos[0] || (!s->dom.active && !s->rtag))
+        {
+        set_error("hb2_system_set_angles: set the particles first");
+        return HB2_ERR_INVALID;
+        }
+    if (n_angle_types >= (1u << 30))
+        return HB2_ERR_INVALID;
+    const uint32_t N = s->dom.active ? (uint32_t)s->dom.N_global : s->N;
+    HB2_TRY(ensure_domain_rtag(s));
+    std::vector<uint32_t> head((size_t)N + 1, 0u);
+    for (uint32_t k = 0; k < n_angles; k++)
+        {
+        const uint32_t* g = group + 3 * (size_t)k;
+        if (g[0] >= N || g[1] >= N || g[2] >= N || g[0] == g[1] || g[1] == g[2] || g[0] == g[2]
+            || typeid_[k] >= n_angle_types)
+            {
+            set_error("hb2_system_set_angles: angle " + std::to_string(k)
+                      + " names a particle tag or an angle type out of range");
+            return HB2_ERR_INVALID;
+            }
+        for (int m = 0; m < 3; m++)
+            head[g[m] + 1]++;
+        }
+    for (uint32_t t = 0; t < N; t++)
+        head[t + 1] += head[t];
+    std::vector<uint4> members(std::max<size_t>(1, 3 * (size_t)n_angles));
+    std::vector<uint32_t> fill(N, 0u);
+    for (uint32_t k = 0; k < n_angles; k++)
+        {
+        const uint32_t* g = group + 3 * (size_t)k;
+        for (uint32_t m = 0; m < 3; m++)
+            members[head[g[m]] + fill[g[m]]++] = make_uint4(g[0], g[1], g[2], typeid_[k] | (m << 30));
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(s->d_angle_head);
+    dev_free(s->d_angle_members);
+    s->d_angle_head = nullptr;
+    s->d_angle_members = nullptr;
+    HB2_TRY(dev_alloc(&s->d_angle_head, head.size()));
+    HB2_TRY(dev_alloc(&s->d_angle_members, members.size()));
+    HB2_CUDA(cudaMemcpy(s->d_angle_head, head.data(), sizeof(uint32_t) * head.size(), cudaMemcpyHostToDevice));
+    HB2_CUDA(cudaMemcpy(s->d_angle_members, members.data(), sizeof(uint4) * members.size(),
+                        cudaMemcpyHostToDevice));
+    s->n_angles = n_angles;
+    s->n_angle_types = n_angle_types;
+    return HB2_OK;
+    }
+
 extern "C" hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds)
     {
     if (!nl)
@@ -1792,7 +1858,7 @@ extern "C" hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds)
 
 extern "C" hb2_status hb2_bond_create(hb2_bond** out, hb2_system* s, hb2_bond_kind kind)
     {
-    if (!out || !s || (kind != HB2_BOND_HARMONIC && kind != HB2_BOND_FENEWCA))
+    if (!out || !s || (unsigned)kind > (unsigned)HB2_ANGLE_COSINESQ)
         return HB2_ERR_INVALID;
     hb2_bond* b = new hb2_bond();
     b->sys = s;
@@ -1855,11 +1921,13 @@ extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const doub
 
 hb2_status hb2_bond::upload_params()
     {
-    const uint32_t nt = sys->n_bond_types;
+    const bool is_angle = kind == HB2_ANGLE_HARMONIC || kind == HB2_ANGLE_COSINESQ;
+    const uint32_t nt = is_angle ? sys->n_angle_types : sys->n_bond_types;
     for (uint32_t t = 0; t < nt; t++)
         if (t >= have.size() || !have[t])
             {
-            set_error("bond: parameters of bond type " + std::to_string(t) + " are not set");
+            set_error(std::string(is_angle ? "angle" : "bond") + ": parameters of type " + std::to_string(t)
+                      + " are not set");
             return HB2_ERR_INVALID;
             }
     std::vector<float> h(HB2_BOND_PARAM_FLOATS * (size_t)std::max<uint32_t>(1, nt), 0.f);
@@ -1879,20 +1947,20 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     hb2_system* s = sys;
     if (params_dirty)
         HB2_TRY(upload_params());
-    if (s->n_bonds == 0 && accumulate)
+    const bool is_angle = kind == HB2_ANGLE_HARMONIC || kind == HB2_ANGLE_COSINESQ;
+    if ((is_angle ? s->n_angles : s->n_bonds) == 0 && accumulate)
         return HB2_OK;
-    if (!s->d_bond_head)
-        {
-        // no bond table was ever set: an empty one
+    if (!is_angle && !s->d_bond_head) // no table was ever set: an empty one
         HB2_TRY(hb2_system_set_bonds(s, 0, nullptr, nullptr, 0));
-        }
+    if (is_angle && !s->d_angle_head)
+        HB2_TRY(hb2_system_set_angles(s, 0, nullptr, nullptr, 0));
     BondArgs a;
     a.pos = s->pos[s->cur];
     a.tag = s->tag[s->cur];
     a.rtag = s->rtag;
     a.N = s->N;
     a.Ntot = s->N + s->Ng;
-    a.head = s->d_bond_head;
+    a.head = is_angle ? s->d_angle_head : s->d_bond_head;
     a.partner = s->d_bond_partner;
     a.btype = s->d_bond_type;
     a.params = d_params;
@@ -1901,6 +1969,8 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     a.virial_pitch = virial_pitch;
     a.skip_flag = skip_flag;
     a.err = d_err;
+    if (is_angle)
+        return launch_angle_forces(kind, a, s->d_angle_members, accumulate, s->box, s->stream);
     return launch_bond_forces(kind, a, accumulate, s->box, s->stream);
     }
 

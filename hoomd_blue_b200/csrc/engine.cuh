@@ -81,6 +81,10 @@ struct hb2_system
     uint32_t* d_bond_partner = nullptr;
     uint32_t* d_bond_type = nullptr;
     uint64_t bond_epoch = 0; // bumped by hb2_system_set_bonds
+    // angle table keyed by particle tag: (tag a, tag b, tag c, type | role << 30) per membership
+    uint32_t n_angles = 0, n_angle_types = 0;
+    uint32_t* d_angle_head = nullptr;
+    uint4* d_angle_members = nullptr;
 
     std::vector<hb2_nlist*> nlists;
     std::vector<hb2_pair*> pairs;

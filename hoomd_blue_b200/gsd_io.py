@@ -134,6 +134,20 @@ def read_frame(filename, frame=-1):
         if grp is None:
             raise RuntimeError(f"{filename}: bonds/N = {nb} but bonds/group is missing")
         snap.bonds.group[:] = grp.reshape(nb, 2)
+    na = g.chunk(f, "angles/N")
+    na = int(na[0, 0]) if na is not None else 0
+    if na:
+        snap.angles.N = na
+        t = g.chunk(f, "angles/types")
+        snap.angles.types = ([bytes(row).split(b"\0")[0].decode() for row in t.astype(np.uint8)]
+                             if t is not None else ["angleA"])
+        tid = g.chunk(f, "angles/typeid", cur_n=na)
+        if tid is not None:
+            snap.angles.typeid[:] = tid.reshape(-1)
+        grp = g.chunk(f, "angles/group", cur_n=na)
+        if grp is None:
+            raise RuntimeError(f"{filename}: angles/N = {na} but angles/group is missing")
+        snap.angles.group[:] = grp.reshape(na, 3)
     return snap, step
 
 
@@ -167,6 +181,15 @@ def frame_chunks(snap, step, dynamic=None, first=True, log=None):
         out += [("bonds/N", np.array([[bonds.N]], dtype=np.uint32)), ("bonds/types", btypes),
                 ("bonds/typeid", np.asarray(bonds.typeid, dtype=np.uint32).reshape(-1, 1)),
                 ("bonds/group", np.asarray(bonds.group, dtype=np.int32).reshape(-1, 2))]
+    angles = getattr(snap, "angles", None)
+    if angles is not None and angles.N and (first or "topology" in dynamic):
+        tw = max(len(t) for t in angles.types) + 1
+        atypes = np.zeros((len(angles.types), tw), dtype=np.int8)
+        for i, t in enumerate(angles.types):
+            atypes[i, :len(t)] = np.frombuffer(t.encode(), dtype=np.int8)
+        out += [("angles/N", np.array([[angles.N]], dtype=np.uint32)), ("angles/types", atypes),
+                ("angles/typeid", np.asarray(angles.typeid, dtype=np.uint32).reshape(-1, 1)),
+                ("angles/group", np.asarray(angles.group, dtype=np.int32).reshape(-1, 3))]
     if first or "property" in dynamic:
         out.append(("particles/position", np.asarray(p.position, dtype=np.float32).reshape(n, 3)))
     if first or "momentum" in dynamic:

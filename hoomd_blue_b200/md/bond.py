@@ -12,6 +12,7 @@ class Bond:
     _loggables = {"energy": "scalar"}
     _kind = 0
     _param_keys = ()
+    _types_attr = "_bond_types"
 
     def __init__(self):
         self.params = {}
@@ -28,10 +29,10 @@ class Bond:
         self._sync()
 
     def _sync(self):
-        types = getattr(self._sim.state, "_bond_types", [])
+        types = getattr(self._sim.state, self._types_attr, [])
         for name, prm in self.params.items():
             if name not in types:
-                raise KeyError(f"bond type {name!r} is not in the state ({types})")
+                raise KeyError(f"type {name!r} is not in the state ({types})")
             missing = [k for k in self._param_keys if k not in prm]
             if missing:
                 raise KeyError(f"bond parameters {missing} are missing for {name!r}")

@@ -82,14 +82,23 @@ class _Bonds:
         self._alloc(self._N)
 
 
+class _Angles(_Bonds):
+    """hoomd.Snapshot.angles: N, types, typeid (N,), group (N, 3) member tags (a, b, c; b the vertex)."""
+
+    def _alloc(self, n):
+        self.typeid = np.zeros((n,), dtype=np.uint32)
+        self.group = np.zeros((n, 3), dtype=np.uint32)
+
+
 class Snapshot:
-    """hoomd.Snapshot (configuration + particles + bonds). pinned=True (not in the reference) allocates the
+    """hoomd.Snapshot (configuration + particles + bonds + angles). pinned=True (not in the reference) allocates the
     particle arrays in page-locked memory so that set_snapshot / get_snapshot copy by DMA."""
 
     def __init__(self, communicator=None, pinned=False):
         self.configuration = _Configuration()
         self.particles = _Particles(pinned)
         self.bonds = _Bonds()
+        self.angles = _Angles()
         self.communicator = communicator
 
     @classmethod
@@ -209,10 +218,12 @@ class State:
             # here every rank receives it and the engine keeps the particles it owns
             p = snapshot.particles if comm.rank == 0 else None
             b = getattr(snapshot, "bonds", None) if comm.rank == 0 else None
+            a = getattr(snapshot, "angles", None) if comm.rank == 0 else None
             data = _comm.broadcast_object(
                 None if p is None else (p.position, p.velocity, p.typeid, p.mass, p.image,
-                                        None if b is None or not b.N else (list(b.types), b.typeid, b.group)))
-            pos, vel, tid, mass, img, bd = data
+                                        None if b is None or not b.N else (list(b.types), b.typeid, b.group),
+                                        None if a is None or not a.N else (list(a.types), a.typeid, a.group)))
+            pos, vel, tid, mass, img, bd, ad = data
             self._set_tagged(len(pos), np.arange(len(pos), dtype=np.uint32), pos, vel, tid, mass, img)
             bonds = None
             if bd is not None:
@@ -220,6 +231,12 @@ class State:
                 bonds.N = len(bd[1])
                 bonds.types, bonds.typeid[:], bonds.group[:] = bd[0], bd[1], bd[2]
             self._set_bonds(bonds)
+            angles = None
+            if ad is not None:
+                angles = _Angles()
+                angles.N = len(ad[1])
+                angles.types, angles.typeid[:], angles.group[:] = ad[0], ad[1], ad[2]
+            self._set_angles(angles)
             return
         p = snapshot.particles
         pos = np.ascontiguousarray(p.position, dtype=np.float32)
@@ -231,6 +248,19 @@ class State:
                                          ptr(vel, C.c_float), ptr(mass, C.c_float),
                                          ptr(tid, C.c_uint32), ptr(img, C.c_int32)))
         self._set_bonds(getattr(snapshot, "bonds", None))
+        self._set_angles(getattr(snapshot, "angles", None))
+
+    def _set_angles(self, angles):
+        L = _lib.lib()
+        n = 0 if angles is None else int(angles.N)
+        self._angle_types = [] if angles is None else list(angles.types)
+        self._angle_typeid = np.zeros(0, np.uint32) if n == 0 else np.ascontiguousarray(angles.typeid, np.uint32)
+        self._angle_group = np.zeros((0, 3), np.uint32) if n == 0 else np.ascontiguousarray(angles.group, np.uint32)
+        if n == 0 and not getattr(self, "_had_angles", False):
+            return
+        self._had_angles = True
+        check(L.hb2_system_set_angles(self._h, n, ptr(self._angle_group, C.c_uint32),
+                                      ptr(self._angle_typeid, C.c_uint32), len(self._angle_types)))
 
     def _set_bonds(self, bonds):
         """BondData of the snapshot (single GPU): the table is kept on the device keyed by tag."""
@@ -279,6 +309,11 @@ class State:
             s.bonds.types = list(self._bond_types)
             s.bonds.typeid[:] = self._bond_typeid
             s.bonds.group[:] = self._bond_group
+        if getattr(self, "_angle_types", None):
+            s.angles.N = len(self._angle_typeid)
+            s.angles.types = list(self._angle_types)
+            s.angles.typeid[:] = self._angle_typeid
+            s.angles.group[:] = self._angle_group
         p = s.particles
         if self._simulation.device.communicator.num_ranks > 1:
             # gathered by tag (hoomd/ParticleData.cc takeSnapshot does the same with MPI gathers;

@@ -178,7 +178,9 @@ typedef struct hb2_pair hb2_pair;             /* ~ PotentialPairGPU<evaluator> (
 typedef enum hb2_bond_kind
     {
     HB2_BOND_HARMONIC = 0, /* hoomd/md/EvaluatorBondHarmonic.h */
-    HB2_BOND_FENEWCA = 1   /* hoomd/md/EvaluatorBondFENE.h */
+    HB2_BOND_FENEWCA = 1,  /* hoomd/md/EvaluatorBondFENE.h */
+    HB2_ANGLE_HARMONIC = 2, /* hoomd/md/HarmonicAngleForceCompute.cc; {k, t0} per ANGLE type */
+    HB2_ANGLE_COSINESQ = 3  /* hoomd/md/CosineSqAngleForceCompute.cc; {k, t0} per ANGLE type */
     } hb2_bond_kind;
 typedef struct hb2_bond hb2_bond;             /* ~ PotentialBond<EvaluatorBondHarmonic> */
 typedef struct hb2_integrator hb2_integrator; /* ~ IntegratorTwoStep + TwoStepConstantVolume */
@@ -307,6 +309,10 @@ hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat
  * hb2_integrator_add_bond: the bond forces are added to the pair force (net force) every step. */
 hb2_status hb2_system_set_bonds(hb2_system* sys, uint32_t n_bonds, const uint32_t* group,
                                 const uint32_t* typeid_, uint32_t n_bond_types);
+/* AngleData of the snapshot: `group` holds 3 member TAGS per angle (a, b, c; b is the vertex). The angle
+ * kinds of hb2_bond_create take their parameters per angle type. */
+hb2_status hb2_system_set_angles(hb2_system* sys, uint32_t n_angles, const uint32_t* group,
+                                 const uint32_t* typeid_, uint32_t n_angle_types);
 hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds);
 hb2_status hb2_bond_create(hb2_bond** out, hb2_system* sys, hb2_bond_kind kind);
 void hb2_bond_destroy(hb2_bond* b);

@@ -719,6 +719,92 @@ int orc_bond_fenewca(const orc_box* b, const double* pos, uint32_t N, const uint
     return bond_forces(1, b, pos, N, rtag, bond_group, bond_type, n_bonds, params, 5, force, virial);
     }
 
+int orc_angle(int kind, const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+              const uint32_t* angle_group, const uint32_t* angle_type, uint32_t n_angles,
+              const double* params, double* force, double* virial)
+    {
+    /* kind 0: hoomd/md/HarmonicAngleForceCompute.cc:104-258 (E = k/2 (theta - t0)^2);
+       kind 1: hoomd/md/CosineSqAngleForceCompute.cc:104-262 (E = k/2 (cos theta - cos t0)^2).
+       params = (k, t0) per angle type; angle_group holds 3 member tags (a, b, c), b the vertex. */
+    const double SMALL = 0.001;
+    memset(force, 0, sizeof(double) * 4 * (size_t)N);
+    memset(virial, 0, sizeof(double) * 6 * (size_t)N);
+    for (uint32_t i = 0; i < n_angles; i++)
+        {
+        const uint32_t ia = rtag[angle_group[3 * i]], ib = rtag[angle_group[3 * i + 1]],
+                       ic = rtag[angle_group[3 * i + 2]];
+        if (ia >= N || ib >= N || ic >= N)
+            return 1 + (int)i;
+        double dab[3], dcb[3];
+        for (int d = 0; d < 3; d++)
+            {
+            dab[d] = pos[3 * (size_t)ia + d] - pos[3 * (size_t)ib + d];
+            dcb[d] = pos[3 * (size_t)ic + d] - pos[3 * (size_t)ib + d];
+            }
+        orc_min_image(b, dab);
+        orc_min_image(b, dcb);
+        const double rsqab = dab[0] * dab[0] + dab[1] * dab[1] + dab[2] * dab[2];
+        const double rab = sqrt(rsqab);
+        const double rsqcb = dcb[0] * dcb[0] + dcb[1] * dcb[1] + dcb[2] * dcb[2];
+        const double rcb = sqrt(rsqcb);
+        double c_abbc = dab[0] * dcb[0] + dab[1] * dcb[1] + dab[2] * dcb[2];
+        c_abbc /= rab * rcb;
+        if (c_abbc > 1.0)
+            c_abbc = 1.0;
+        if (c_abbc < -1.0)
+            c_abbc = -1.0;
+        const double K = params[2 * angle_type[i]], t_0 = params[2 * angle_type[i] + 1];
+        double a, eng;
+        if (kind == 0)
+            {
+            double s_abbc = sqrt(1.0 - c_abbc * c_abbc);
+            if (s_abbc < SMALL)
+                s_abbc = SMALL;
+            s_abbc = 1.0 / s_abbc;
+            const double dth = acos(c_abbc) - t_0;
+            const double tk = K * dth;
+            a = -1.0 * tk * s_abbc;
+            eng = (tk * dth) * (1.0 / 6.0);
+            }
+        else
+            {
+            const double dcosth = c_abbc - cos(t_0);
+            const double tk = K * dcosth;
+            a = 1.0 * tk;
+            eng = (tk * dcosth) * (1.0 / 6.0);
+            }
+        const double a11 = a * c_abbc / rsqab;
+        const double a12 = -a / (rab * rcb);
+        const double a22 = a * c_abbc / rsqcb;
+        double fab[3], fcb[3];
+        for (int d = 0; d < 3; d++)
+            {
+            fab[d] = a11 * dab[d] + a12 * dcb[d];
+            fcb[d] = a22 * dcb[d] + a12 * dab[d];
+            }
+        const double v[6] = {(1. / 3.) * (dab[0] * fab[0] + dcb[0] * fcb[0]),
+                             (1. / 3.) * (dab[1] * fab[0] + dcb[1] * fcb[0]),
+                             (1. / 3.) * (dab[2] * fab[0] + dcb[2] * fcb[0]),
+                             (1. / 3.) * (dab[1] * fab[1] + dcb[1] * fcb[1]),
+                             (1. / 3.) * (dab[2] * fab[1] + dcb[2] * fcb[1]),
+                             (1. / 3.) * (dab[2] * fab[2] + dcb[2] * fcb[2])};
+        for (int d = 0; d < 3; d++)
+            {
+            force[4 * (size_t)ia + d] += fab[d];
+            force[4 * (size_t)ib + d] -= fab[d] + fcb[d];
+            force[4 * (size_t)ic + d] += fcb[d];
+            }
+        const uint32_t idx[3] = {ia, ib, ic};
+        for (int m = 0; m < 3; m++)
+            {
+            force[4 * (size_t)idx[m] + 3] += eng;
+            for (int q = 0; q < 6; q++)
+                virial[(size_t)q * N + idx[m]] += v[q];
+            }
+        }
+    return 0;
+    }
+
 /* ---------------------------------------------------------------------- RNG ---- */
 
 void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])

@@ -117,6 +117,13 @@ int orc_bond_fenewca(const orc_box* b, const double* pos, uint32_t N, const uint
                      const uint32_t* bond_group, const uint32_t* bond_type, uint32_t n_bonds,
                      const double* params, double* force, double* virial);
 
+/* Angle forces: kind 0 harmonic (hoomd/md/HarmonicAngleForceCompute.cc), 1 cosine squared
+ * (hoomd/md/CosineSqAngleForceCompute.cc); params = (k, t0) per angle type; a third of the energy and
+ * of the virial to each member. Returns 0 or 1 + the index of an incomplete angle. */
+int orc_angle(int kind, const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+              const uint32_t* angle_group, const uint32_t* angle_type, uint32_t n_angles,
+              const double* params, double* force, double* virial);
+
 /* RNG: Philox4x32-10 (Salmon et al., SC'11; hoomd/extern/random123 commit a2c4f04) and HOOMD's
  * Seed/Counter packing hoomd/RandomNumbers.h:136-199 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -312,6 +312,27 @@ def filter_bond_exclusions(n_neigh, head, nl, bond_group, tags=None):
     return nn, head2, packed
 
 
+def angle(kind, box, pos, angle_group, angle_type, params, tags=None):
+    """kind 'harmonic' | 'cosinesq'; params (k, t0) per angle type; returns (force N x 4, virial 6 x N)."""
+    pos = _f64(pos)
+    n = pos.shape[0]
+    tags = np.arange(n, dtype=np.uint32) if tags is None else _u32(tags)
+    rtag = np.zeros(int(tags.max()) + 1 if n else 1, dtype=np.uint32)
+    rtag[tags] = np.arange(n, dtype=np.uint32)
+    ag = _u32(np.asarray(angle_group).reshape(-1, 3))
+    at = _u32(angle_type)
+    params = _f64(np.asarray(params).reshape(-1, 2))
+    force = np.zeros((n, 4))
+    virial = np.zeros((6, n))
+    rc = lib().orc_angle(C.c_int({"harmonic": 0, "cosinesq": 1}[kind]), C.byref(box), _p(pos, C.c_double),
+                         C.c_uint32(n), _p(rtag, C.c_uint32), _p(ag, C.c_uint32), _p(at, C.c_uint32),
+                         C.c_uint32(ag.shape[0]), _p(params, C.c_double), _p(force, C.c_double),
+                         _p(virial, C.c_double))
+    if rc:
+        raise RuntimeError(f"Error: angle {rc - 1} is incomplete.")
+    return force, virial
+
+
 def bond_fenewca(box, pos, bond_group, bond_type, params, tags=None):
     """PotentialBond<EvaluatorBondFENE>; params (k, r0, epsilon, sigma, delta) per bond type."""
     return bond_harmonic(box, pos, bond_group, bond_type, params, tags, _fn="orc_bond_fenewca", _np=5)

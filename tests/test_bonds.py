@@ -20,6 +20,45 @@ FENE_VECTORS = [(dict(k=30.0, r0=1.6, epsilon=0.9, sigma=1.1, delta=-0.5), 282.2
 FENE_KEYS = ("k", "r0", "epsilon", "sigma", "delta")
 
 
+# (kind, k, t0, force, energy) hoomd/md/pytest/test_angle.py:14-57: three particles at 60 degrees
+ANGLE_VECTORS = [("harmonic", 3.0, np.pi / 2, -1.5708, 0.4112), ("harmonic", 10.0, np.pi / 4, 2.6180, 0.3427),
+                 ("harmonic", 5.0, np.pi / 6, 2.6180, 0.6854), ("cosinesq", 3.0, np.pi / 2, -1.29904, 0.375),
+                 ("cosinesq", 10.0, np.pi / 4, 1.7936, 0.214466), ("cosinesq", 5.0, np.pi / 6, 1.58494, 0.334936)]
+
+
+def triplet(d=1.0, theta_deg=60):
+    # hoomd/md/pytest/test_angle.py:69-107 triplet_snapshot_factory
+    th = theta_deg * np.pi / 180
+    p = np.array([[-d * np.sin(th / 2), d * np.cos(th / 2), 0.0], [0.0, 0.0, 0.0],
+                  [d * np.sin(th / 2), d * np.cos(th / 2), 0.0]])
+    p[:, 2] += 0.1
+    return p.astype(np.float32)
+
+
+def check_angle_vectors(forces, energy, force, e_ref):
+    th = 60 * np.pi / 180
+    fa = force * np.array([np.cos(th / 2), np.sin(th / 2), 0])
+    assert energy == pytest.approx(e_ref, rel=1e-2)
+    np.testing.assert_allclose(forces[0], fa, rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(forces[1], [0, -1 * force, 0], rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(forces[2], [-fa[0], fa[1], fa[2]], rtol=1e-2, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind,k,t0,force,energy", ANGLE_VECTORS)
+def test_oracle_angle_reference_vectors(oracle, kind, k, t0, force, energy):
+    box = oracle.make_box([20.0, 20.0, 20.0])
+    f, v = oracle.angle(kind, box, triplet(), [[0, 1, 2]], [0], [[k, t0]])
+    check_angle_vectors(f[:, :3], f[:, 3].sum(), force, energy)
+    assert np.abs(f[:, :3].sum(axis=0)).max() < 1e-12          # no net force
+    pos = triplet().astype(np.float64)
+    assert np.abs(np.cross(pos, f[:, :3]).sum(axis=0)).max() < 1e-6  # no net torque
+    # across the periodic boundary: same forces for a translated, wrapped triplet
+    shifted = (pos + [9.7, 9.8, 0]) 
+    shifted = (shifted + 10.0) % 20.0 - 10.0
+    f2, _ = oracle.angle(kind, box, shifted, [[0, 1, 2]], [0], [[k, t0]])
+    np.testing.assert_allclose(f2, f, atol=1e-6)
+
+
 def two_particles(d=0.969):
     # hoomd/conftest.py:168-196 two_particle_snapshot_factory(d=0.969, L=5)
     return np.array([[-d / 2, 0, 0.1], [d / 2, 0, 0.1]], dtype=np.float32)
@@ -191,6 +230,86 @@ def test_fenewca_reference_vectors(oracle, prm, force, energy):
     with pytest.raises(RuntimeError, match="out of bounds"):
         sim.run(0)
         potential.forces
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,k,t0,force,energy", ANGLE_VECTORS)
+def test_angle_reference_vectors(oracle, kind, k, t0, force, energy):
+    """hoomd/md/pytest/test_angle.py:137-175 as written there."""
+    import hoomd_blue_b200 as hoomd
+    snap = hoomd.Snapshot.from_arrays([20, 20, 20, 0, 0, 0], triplet())
+    snap.angles.N = 1
+    snap.angles.types = ["A-A-A"]
+    snap.angles.typeid[0] = 0
+    snap.angles.group[0] = (0, 1, 2)
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=1)
+    sim.always_compute_pressure = True
+    sim.create_state_from_snapshot(snap)
+    cls = hoomd.md.angle.Harmonic if kind == "harmonic" else hoomd.md.angle.CosineSquared
+    potential = cls()
+    potential.params["A-A-A"] = dict(k=k, t0=t0)
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.005, forces=[potential])
+    sim.run(0)
+    check_angle_vectors(potential.forces, potential.energy, force, energy)
+    box = oracle.make_box([20.0, 20.0, 20.0])
+    f_ref, v_ref = oracle.angle(kind, box, triplet(), [[0, 1, 2]], [0], [[k, t0]])
+    np.testing.assert_allclose(potential.forces, f_ref[:, :3], rtol=2e-5, atol=2e-6)
+    assert potential.energy == pytest.approx(f_ref[:, 3].sum(), rel=2e-5)
+    np.testing.assert_allclose(potential.virials, v_ref.T, rtol=2e-5, atol=2e-6)
+    back = sim.state.get_snapshot()
+    assert back.angles.N == 1 and tuple(back.angles.group[0]) == (0, 1, 2)
+
+
+@pytest.mark.gpu
+def test_semiflexible_chains_vs_oracle(oracle):
+    """bonds + angles + WCA on lattice chains: every force against the oracle, the net force conserves
+    energy through rebuilds (the angle table follows the particles through rtag)."""
+    import hoomd_blue_b200 as hoomd
+    from tests.test_gpu_parity import force_err, FORCE_RTOL
+    pos, group, L = lattice_chains(32, 12, 12, 16, 1.0, seed=6, jitter=0.08)
+    n = len(pos)
+    bonded = set(map(tuple, group.tolist()))
+    angles = np.array([(i - 1, i, i + 1) for i in range(1, n - 1)
+                       if (i - 1, i) in bonded and (i, i + 1) in bonded], dtype=np.uint32)
+    rng = np.random.default_rng(7)
+    vel0 = rng.normal(0, 0.8, size=pos.shape).astype(np.float32)
+    vel0 -= vel0.mean(axis=0)
+    snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel0)
+    snap.bonds.N = len(group)
+    snap.bonds.types = ["polymer"]
+    snap.bonds.group[:] = group
+    snap.angles.N = len(angles)
+    snap.angles.types = ["stiff", "soft"]
+    snap.angles.group[:] = angles
+    snap.angles.typeid[:] = np.arange(len(angles)) % 2
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=2)
+    sim.create_state_from_snapshot(snap)
+    cell = hoomd.md.nlist.Cell(buffer=0.3)
+    lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.0 ** (1.0 / 6.0), mode="shift")
+    lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+    hb = hoomd.md.bond.Harmonic()
+    hb.params["polymer"] = dict(k=200.0, r0=0.95)
+    ha = hoomd.md.angle.Harmonic()
+    ha.params["stiff"] = dict(k=20.0, t0=np.pi)
+    ha.params["soft"] = dict(k=5.0, t0=2.5)
+    sim.operations.integrator = hoomd.md.Integrator(
+        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[lj, hb, ha])
+    sim.run(0)
+    box = oracle.make_box([float(v) for v in L])
+    a_ref, _ = oracle.angle("harmonic", box, pos, angles, snap.angles.typeid, [[20.0, np.pi], [5.0, 2.5]])
+    assert force_err(ha.forces, a_ref[:, :3]) <= FORCE_RTOL
+    assert abs(ha.energy - a_ref[:, 3].sum()) <= 1e-5 * abs(a_ref[:, 3].sum())
+    b_ref, _ = oracle.bond_harmonic(box, pos, group, np.zeros(len(group), np.uint32), [[200.0, 0.95]])
+    ke, pe, _ = sim.operations.integrator._thermo()
+    assert abs(pe - (lj.energy + b_ref[:, 3].sum() + a_ref[:, 3].sum())) <= 1e-5 * abs(pe)
+    sim.run(500)
+    e = []
+    for _ in range(10):
+        sim.run(200)
+        ke, pe, _ = sim.operations.integrator._thermo()
+        e.append(ke + pe)
+    assert cell.num_builds >= 1 and ke > 0.3 * n
+    assert np.ptp(e) <= 2e-3 * ke
 
 
 @pytest.mark.gpu
