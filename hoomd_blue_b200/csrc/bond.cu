@@ -213,55 +213,59 @@ __global__ void __launch_bounds__(BOND_BLOCK)
         double cx = (double)pc.x - (double)pb.x, cy = (double)pc.y - (double)pb.y, cz = (double)pc.z - (double)pb.z;
         min_image_exact(box, ax, ay, az);
         min_image_exact(box, cx, cy, cz);
-        const float dab[3] = {(float)ax, (float)ay, (float)az}, dcb[3] = {(float)cx, (float)cy, (float)cz};
-        const float rsqab = dab[0] * dab[0] + dab[1] * dab[1] + dab[2] * dab[2];
-        const float rab = sqrtf(rsqab);
-        const float rsqcb = dcb[0] * dcb[0] + dcb[1] * dcb[1] + dcb[2] * dcb[2];
-        const float rcb = sqrtf(rsqcb);
-        float c_abbc = (dab[0] * dcb[0] + dab[1] * dcb[1] + dab[2] * dcb[2]) / (rab * rcb);
-        c_abbc = fminf(1.0f, fmaxf(-1.0f, c_abbc));
-        const float K = params[HB2_BOND_PARAM_FLOATS * type], t_0 = params[HB2_BOND_PARAM_FLOATS * type + 1];
-        float a, eng;
+        // The triplet's geometry is evaluated in fp64: near 0 and 180 degrees 1 - cos^2 and acos lose
+        // half of fp32's digits (chains with t0 = pi sit exactly there), and there are only a few
+        // angles per particle.
+        const double dab[3] = {ax, ay, az}, dcb[3] = {cx, cy, cz};
+        const double rsqab = dab[0] * dab[0] + dab[1] * dab[1] + dab[2] * dab[2];
+        const double rab = sqrt(rsqab);
+        const double rsqcb = dcb[0] * dcb[0] + dcb[1] * dcb[1] + dcb[2] * dcb[2];
+        const double rcb = sqrt(rsqcb);
+        double c_abbc = (dab[0] * dcb[0] + dab[1] * dcb[1] + dab[2] * dcb[2]) / (rab * rcb);
+        c_abbc = fmin(1.0, fmax(-1.0, c_abbc));
+        const double K = (double)params[HB2_BOND_PARAM_FLOATS * type],
+                     t_0 = (double)params[HB2_BOND_PARAM_FLOATS * type + 1];
+        double a, eng;
         if (KIND == 0)
             {
-            float s_abbc = sqrtf(1.0f - c_abbc * c_abbc);
-            if (s_abbc < 0.001f)
-                s_abbc = 0.001f;
-            s_abbc = 1.0f / s_abbc;
-            const float dth = acosf(c_abbc) - t_0;
-            const float tk = K * dth;
-            a = -1.0f * tk * s_abbc;
-            eng = (tk * dth) * (1.0f / 6.0f);
+            double s_abbc = sqrt(1.0 - c_abbc * c_abbc);
+            if (s_abbc < 0.001)
+                s_abbc = 0.001;
+            s_abbc = 1.0 / s_abbc;
+            const double dth = acos(c_abbc) - t_0;
+            const double tk = K * dth;
+            a = -1.0 * tk * s_abbc;
+            eng = (tk * dth) * (1.0 / 6.0);
             }
         else
             {
-            const float dcosth = c_abbc - cosf(t_0);
-            const float tk = K * dcosth;
+            const double dcosth = c_abbc - cos(t_0);
+            const double tk = K * dcosth;
             a = tk;
-            eng = (tk * dcosth) * (1.0f / 6.0f);
+            eng = (tk * dcosth) * (1.0 / 6.0);
             }
-        const float a11 = a * c_abbc / rsqab, a12 = -a / (rab * rcb), a22 = a * c_abbc / rsqcb;
-        float fab[3], fcb[3];
+        const double a11 = a * c_abbc / rsqab, a12 = -a / (rab * rcb), a22 = a * c_abbc / rsqcb;
+        double fab[3], fcb[3];
 #pragma unroll
         for (int d = 0; d < 3; d++)
             {
             fab[d] = a11 * dab[d] + a12 * dcb[d];
             fcb[d] = a22 * dcb[d] + a12 * dab[d];
             }
-        const float sa = role == 0 ? 1.f : (role == 1 ? -1.f : 0.f);
-        const float sc = role == 2 ? 1.f : (role == 1 ? -1.f : 0.f);
-        fx += sa * fab[0] + sc * fcb[0];
-        fy += sa * fab[1] + sc * fcb[1];
-        fz += sa * fab[2] + sc * fcb[2];
-        pe += eng;
+        const double sa = role == 0 ? 1.0 : (role == 1 ? -1.0 : 0.0);
+        const double sc = role == 2 ? 1.0 : (role == 1 ? -1.0 : 0.0);
+        fx += (float)(sa * fab[0] + sc * fcb[0]);
+        fy += (float)(sa * fab[1] + sc * fcb[1]);
+        fz += (float)(sa * fab[2] + sc * fcb[2]);
+        pe += (float)eng;
         if (virial)
             {
-            v[0] += (1.f / 3.f) * (dab[0] * fab[0] + dcb[0] * fcb[0]);
-            v[1] += (1.f / 3.f) * (dab[1] * fab[0] + dcb[1] * fcb[0]);
-            v[2] += (1.f / 3.f) * (dab[2] * fab[0] + dcb[2] * fcb[0]);
-            v[3] += (1.f / 3.f) * (dab[1] * fab[1] + dcb[1] * fcb[1]);
-            v[4] += (1.f / 3.f) * (dab[2] * fab[1] + dcb[2] * fcb[1]);
-            v[5] += (1.f / 3.f) * (dab[2] * fab[2] + dcb[2] * fcb[2]);
+            v[0] += (float)((1. / 3.) * (dab[0] * fab[0] + dcb[0] * fcb[0]));
+            v[1] += (float)((1. / 3.) * (dab[1] * fab[0] + dcb[1] * fcb[0]));
+            v[2] += (float)((1. / 3.) * (dab[2] * fab[0] + dcb[2] * fcb[0]));
+            v[3] += (float)((1. / 3.) * (dab[1] * fab[1] + dcb[1] * fcb[1]));
+            v[4] += (float)((1. / 3.) * (dab[2] * fab[1] + dcb[2] * fcb[1]));
+            v[5] += (float)((1. / 3.) * (dab[2] * fab[2] + dcb[2] * fcb[2]));
             }
         }
     if (ACCUM)
