@@ -121,6 +121,7 @@ def _declare(L):
     L.hb2_system_set_bonds.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
     L.hb2_system_set_angles.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
     L.hb2_nlist_set_exclusions.argtypes = [_vp, C.c_int]
+    L.hb2_nlist_set_exclusion_pairs.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.hb2_bond_create.argtypes = [C.POINTER(_vp), _vp, C.c_int]
     L.hb2_bond_destroy.argtypes = [_vp]
     L.hb2_bond_destroy.restype = None

@@ -873,6 +873,9 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
     if (exclude_bonds && s->n_bonds)
         HB2_TRY(launch_nlist_filter_bonds(N, s->tag[s->cur], s->rtag, s->d_bond_head, s->d_bond_partner,
                                           d_nlist, pitch, d_n_neigh, Ntot, st));
+    if (n_ex_pairs)
+        HB2_TRY(launch_nlist_filter_bonds(N, s->tag[s->cur], s->rtag, d_ex_head, d_ex_partner, d_nlist,
+                                          pitch, d_n_neigh, Ntot, st));
     if (has_list && timestep > last_update_step)
         shortest_rebuild = std::min<uint64_t>(shortest_rebuild, timestep - last_update_step);
     has_list = true;
@@ -958,6 +961,8 @@ extern "C" void hb2_nlist_destroy(hb2_nlist* nl)
     dev_free(nl->d_nlist);
     dev_free(nl->d_n_neigh);
     dev_free(nl->d_last_pos);
+    dev_free(nl->d_ex_head);
+    dev_free(nl->d_ex_partner);
     dev_free(nl->d_conditions);
     if (nl->h_conditions)
         cudaFreeHost(nl->h_conditions);
@@ -1842,6 +1847,61 @@ extern "C" hb2_status hb2_system_set_angles(hb2_system* s, uint32_t n_angles, co
                         cudaMemcpyHostToDevice));
     s->n_angles = n_angles;
     s->n_angle_types = n_angle_types;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_set_exclusion_pairs(hb2_nlist* nl, uint32_t n_pairs, const uint32_t* pairs)
+    {
+    if (!nl || (n_pairs && !pairs))
+        return HB2_ERR_INVALID;
+    hb2_system* s = nl->sys;
+    if (!s->pos[0] || (!s->dom.active && !s->rtag))
+        {
+        set_error("hb2_nlist_set_exclusion_pairs: set the particles first");
+        return HB2_ERR_INVALID;
+        }
+    const uint32_t N = s->dom.active ? (uint32_t)s->dom.N_global : s->N;
+    if (n_pairs)
+        HB2_TRY(ensure_domain_rtag(s));
+    std::vector<uint32_t> head((size_t)N + 1, 0u), partner(std::max<size_t>(1, 2 * (size_t)n_pairs));
+    for (uint32_t k = 0; k < n_pairs; k++)
+        {
+        const uint32_t a = pairs[2 * k], b = pairs[2 * k + 1];
+        if (a >= N || b >= N || a == b)
+            {
+            set_error("hb2_nlist_set_exclusion_pairs: pair " + std::to_string(k) + " is out of range");
+            return HB2_ERR_INVALID;
+            }
+        head[a + 1]++;
+        head[b + 1]++;
+        }
+    for (uint32_t t = 0; t < N; t++)
+        head[t + 1] += head[t];
+    std::vector<uint32_t> fill(N, 0u);
+    for (uint32_t k = 0; k < n_pairs; k++)
+        {
+        const uint32_t a = pairs[2 * k], b = pairs[2 * k + 1];
+        partner[head[a] + fill[a]++] = b;
+        partner[head[b] + fill[b]++] = a;
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(nl->d_ex_head);
+    dev_free(nl->d_ex_partner);
+    nl->d_ex_head = nl->d_ex_partner = nullptr;
+    nl->n_ex_pairs = 0;
+    if (n_pairs)
+        {
+        HB2_TRY(dev_alloc(&nl->d_ex_head, head.size()));
+        HB2_TRY(dev_alloc(&nl->d_ex_partner, partner.size()));
+        HB2_CUDA(cudaMemcpy(nl->d_ex_head, head.data(), sizeof(uint32_t) * head.size(), cudaMemcpyHostToDevice));
+        HB2_CUDA(cudaMemcpy(nl->d_ex_partner, partner.data(), sizeof(uint32_t) * partner.size(),
+                            cudaMemcpyHostToDevice));
+        nl->n_ex_pairs = n_pairs;
+        }
+    nl->force_update = true;
+    for (auto* pr : nl->consumers)
+        pr->computed = false;
     return HB2_OK;
     }
 

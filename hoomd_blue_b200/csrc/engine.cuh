@@ -134,6 +134,10 @@ struct hb2_nlist
     uint32_t* h_conditions = nullptr; // pinned mirror
 
     bool exclude_bonds = true; // exclusions=('bond',), the reference's default (hoomd/md/nlist.py:87-102)
+    // further excluded pairs ('angle', '1-3', ...): CSR keyed by particle tag, like the bond table
+    uint32_t n_ex_pairs = 0;
+    uint32_t* d_ex_head = nullptr;
+    uint32_t* d_ex_partner = nullptr;
     bool force_update = true;
     bool has_list = false;
     uint64_t num_builds = 0;

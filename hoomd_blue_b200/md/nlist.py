@@ -12,8 +12,10 @@ class NeighborList:
     """Base class (hoomd/md/nlist.py:87-323)."""
 
     def __init__(self, buffer, exclusions, rebuild_check_delay, check_dist, mesh, default_r_cut):
-        if exclusions not in ((), None) and tuple(exclusions) != ("bond",):
-            raise NotImplementedError("exclusions other than the default are outside this path")
+        unknown = set(exclusions or ()) - {"bond", "angle", "1-3"}
+        if unknown:
+            raise NotImplementedError(f"exclusions {sorted(unknown)} are outside this path "
+                                      "(supported: 'bond', 'angle', '1-3')")
         if mesh is not None:
             raise NotImplementedError("mesh neighbour lists are outside this path")
         self.buffer = float(buffer)
@@ -39,6 +41,35 @@ class NeighborList:
         self._h = h
         self._sim = sim
         check(_lib.lib().hb2_nlist_set_exclusions(h, int("bond" in self.exclusions)))
+        extra = self._extra_exclusion_pairs(sim.state)
+        if len(extra):
+            check(_lib.lib().hb2_nlist_set_exclusion_pairs(h, len(extra), ptr(extra, C.c_uint32)))
+
+    def _extra_exclusion_pairs(self, state):
+        """Pairs (by tag) that 'angle' and '1-3' add (hoomd/md/NeighborList.cc:881-909: the two end
+        particles of every angle; :1048-1120: every two particles bonded to a common one)."""
+        pairs = []
+        if "angle" in self.exclusions and len(getattr(state, "_angle_group", ())):
+            g = np.asarray(state._angle_group)
+            pairs.append(g[:, [0, 2]])
+        if "1-3" in self.exclusions and len(getattr(state, "_bond_group", ())):
+            g = np.asarray(state._bond_group, dtype=np.int64)
+            both = np.concatenate([g, g[:, ::-1]])          # (centre, partner) for both directions
+            both = both[np.argsort(both[:, 0], kind="stable")]
+            # two entries k apart with the same centre are two partners of that centre
+            k = 1
+            while k < len(both):
+                same = both[:-k, 0] == both[k:, 0]
+                if not same.any():
+                    break
+                pairs.append(np.stack([both[:-k, 1][same], both[k:, 1][same]], axis=1))
+                k += 1
+        if not pairs:
+            return np.zeros((0, 2), dtype=np.uint32)
+        allp = np.concatenate(pairs).astype(np.int64)
+        allp = allp[allp[:, 0] != allp[:, 1]]
+        allp = np.unique(np.sort(allp, axis=1), axis=0)   # addExclusion ignores duplicates
+        return np.ascontiguousarray(allp, dtype=np.uint32)
 
     def _detach(self):
         if self._h is not None:

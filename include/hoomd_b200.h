@@ -314,6 +314,9 @@ hb2_status hb2_system_set_bonds(hb2_system* sys, uint32_t n_bonds, const uint32_
 hb2_status hb2_system_set_angles(hb2_system* sys, uint32_t n_angles, const uint32_t* group,
                                  const uint32_t* typeid_, uint32_t n_angle_types);
 hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds);
+/* Further excluded pairs by TAG (what exclusions=('angle', '1-3', ...) add through
+ * NeighborList::addExclusion, hoomd/md/NeighborList.cc:881-1120); replaces the previous set. */
+hb2_status hb2_nlist_set_exclusion_pairs(hb2_nlist* nl, uint32_t n_pairs, const uint32_t* pairs);
 hb2_status hb2_bond_create(hb2_bond** out, hb2_system* sys, hb2_bond_kind kind);
 void hb2_bond_destroy(hb2_bond* b);
 hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const double* user_params, uint32_t n_user);

@@ -153,6 +153,45 @@ def test_oracle_exclusion_filter(oracle):
     assert nn.sum() - nn2.sum() == 2 * len(group)
 
 
+def test_extra_exclusion_pairs():
+    """'angle' and '1-3' exclusion pairs against a literal restatement of the reference's loops
+    (hoomd/md/NeighborList.cc:881-909 and :1048-1120)."""
+    from hoomd_blue_b200.md.nlist import Cell
+    rng = np.random.default_rng(11)
+    n = 60
+    bonds = set()
+    while len(bonds) < 80:
+        a, b = rng.integers(0, n, 2)
+        if a != b and (a, b) not in bonds and (b, a) not in bonds:
+            bonds.add((int(a), int(b)))
+    bonds = np.array(sorted(bonds), dtype=np.uint32)
+    angles = rng.integers(0, n, (25, 3)).astype(np.uint32)
+    angles = angles[(angles[:, 0] != angles[:, 2])]
+
+    class _State:
+        _bond_group, _angle_group = bonds, angles
+
+    # reference: per-atom partner lists, then every two partners of a common atom
+    partners = {}
+    for a, b in bonds.tolist():
+        partners.setdefault(a, []).append(b)
+        partners.setdefault(b, []).append(a)
+    want13 = set()
+    for c, p in partners.items():
+        for j in range(len(p)):
+            for k in range(j + 1, len(p)):
+                if p[j] != p[k]:
+                    want13.add((min(p[j], p[k]), max(p[j], p[k])))
+    want_angle = set((int(min(a, c)), int(max(a, c))) for a, _, c in angles.tolist())
+    got = lambda ex: set(map(tuple, Cell(buffer=0.4, exclusions=ex)._extra_exclusion_pairs(_State).tolist()))  # noqa: E731
+    assert got(("bond", "1-3")) == want13
+    assert got(("angle",)) == want_angle
+    assert got(("bond", "angle", "1-3")) == want13 | want_angle
+    assert got(("bond",)) == set()
+    with pytest.raises(NotImplementedError):
+        Cell(buffer=0.4, exclusions=("bond", "dihedral"))
+
+
 def test_gsd_bonds_roundtrip(tmp_path):
     from hoomd_blue_b200 import gsd_io, Snapshot
     pos, group, L = chains(5, 6, 0.5, seed=2)
@@ -302,6 +341,27 @@ def test_semiflexible_chains_vs_oracle(oracle):
     b_ref, _ = oracle.bond_harmonic(box, pos, group, np.zeros(len(group), np.uint32), [[200.0, 0.95]])
     ke, pe, _ = sim.operations.integrator._thermo()
     assert abs(pe - (lj.energy + b_ref[:, 3].sum() + a_ref[:, 3].sum())) <= 1e-5 * abs(pe)
+    # exclusions=('bond', 'angle'): the chain ends of every angle leave the list too; for linear chains
+    # ('bond', '1-3') names the same pairs
+    from tests.test_gpu_parity import canon_pairs
+    types = np.zeros(n, dtype=np.uint32)
+    rc = 2.5  # the chain ends of an angle are ~2 apart: inside this list
+    nn, head, nl, _ = oracle.nlist(box, pos, types, [rc], 0.3, full=True)
+    ex = np.concatenate([group, angles[:, [0, 2]]])
+    nn_x, head_x, nl_x = oracle.filter_bond_exclusions(nn, head, nl, ex)
+    want = oracle.pair_set(nn_x, head_x, nl_x)
+    nn_b, head_b, nl_b = oracle.filter_bond_exclusions(nn, head, nl, group)
+    assert len(want) == len(oracle.pair_set(nn_b, head_b, nl_b)) - len(angles)
+    for excl in (("bond", "angle"), ("bond", "1-3")):
+        s2 = hoomd.Simulation(device=hoomd.device.GPU(), seed=2)
+        s2.create_state_from_snapshot(snap)
+        c2 = hoomd.md.nlist.Cell(buffer=0.3, exclusions=excl)
+        l2 = hoomd.md.pair.LJ(nlist=c2, default_r_cut=rc, mode="shift")
+        l2.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+        s2.operations.integrator = hoomd.md.Integrator(
+            dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[l2])
+        s2.run(0)
+        assert np.array_equal(canon_pairs(c2.pair_list), want), excl
     sim.run(500)
     e = []
     for _ in range(10):
