@@ -120,6 +120,7 @@ def _declare(L):
     L.hb2_integrator_set_constant_volume.argtypes = [_vp, C.c_int, C.c_double, C.c_double]
     L.hb2_system_set_bonds.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
     L.hb2_system_set_angles.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
+    L.hb2_system_set_dihedrals.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
     L.hb2_nlist_set_exclusions.argtypes = [_vp, C.c_int]
     L.hb2_nlist_set_exclusion_pairs.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.hb2_bond_create.argtypes = [C.POINTER(_vp), _vp, C.c_int]

@@ -320,6 +320,173 @@ hb2_status launch_angle_forces(hb2_bond_kind kind, const BondArgs& a, const uint
     return HB2_OK;
     }
 
+// Periodic dihedrals (hoomd.md.dihedral.Periodic, hoomd/md/HarmonicDihedralForceCompute.cc:104-356),
+// owner-computes like the angles: table entries hold the four member tags and `type | role << 30`;
+// the quadruplet is evaluated in fp64 with the reference's arithmetic and the particle keeps its share.
+template<bool ACCUM>
+__global__ void __launch_bounds__(BOND_BLOCK)
+    dihedral_force_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
+                          const uint32_t* __restrict__ rtag, uint32_t N, uint32_t Ntot,
+                          const uint32_t* __restrict__ head, const uint4* __restrict__ members,
+                          const uint32_t* __restrict__ type_role, const float* __restrict__ params,
+                          BoxD box, float4* __restrict__ force, float* __restrict__ virial,
+                          size_t virial_pitch, const uint32_t* __restrict__ skip_flag,
+                          uint32_t* __restrict__ err)
+    {
+    if (skip_flag && *skip_flag)
+        return;
+    const uint32_t i = blockIdx.x * BOND_BLOCK + threadIdx.x;
+    if (i >= N)
+        return;
+    const uint32_t t = tag[i];
+    const uint32_t k0 = head[t], k1 = head[t + 1];
+    if (ACCUM && k0 == k1)
+        return;
+    float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (uint32_t k = k0; k < k1; k++)
+        {
+        const uint4 m = members[k];
+        const uint32_t tr = type_role[k];
+        const uint32_t ia = rtag[m.x], ib = rtag[m.y], ic = rtag[m.z], id = rtag[m.w];
+        if (ia >= Ntot || ib >= Ntot || ic >= Ntot || id >= Ntot)
+            {
+            atomicMax(err, t + 1u);
+            continue;
+            }
+        const uint32_t role = tr >> 30, type = tr & 0x3fffffffu;
+        const float4 pa = pos[ia], pb = pos[ib], pc = pos[ic], pd = pos[id];
+        double dab[3] = {(double)pa.x - (double)pb.x, (double)pa.y - (double)pb.y, (double)pa.z - (double)pb.z};
+        double dcb[3] = {(double)pc.x - (double)pb.x, (double)pc.y - (double)pb.y, (double)pc.z - (double)pb.z};
+        double ddc[3] = {(double)pd.x - (double)pc.x, (double)pd.y - (double)pc.y, (double)pd.z - (double)pc.z};
+        min_image_exact(box, dab[0], dab[1], dab[2]);
+        min_image_exact(box, dcb[0], dcb[1], dcb[2]);
+        min_image_exact(box, ddc[0], ddc[1], ddc[2]);
+        const float* prm = params + HB2_BOND_PARAM_FLOATS * type;
+        const double K = (double)prm[0], sign = (double)prm[1], phi_0 = (double)prm[3];
+        const int multi = (int)prm[2];
+
+        double dcbm[3] = {-dcb[0], -dcb[1], -dcb[2]};
+        min_image_exact(box, dcbm[0], dcbm[1], dcbm[2]);
+        const double aax = dab[1] * dcbm[2] - dab[2] * dcbm[1];
+        const double aay = dab[2] * dcbm[0] - dab[0] * dcbm[2];
+        const double aaz = dab[0] * dcbm[1] - dab[1] * dcbm[0];
+        const double bbx = ddc[1] * dcbm[2] - ddc[2] * dcbm[1];
+        const double bby = ddc[2] * dcbm[0] - ddc[0] * dcbm[2];
+        const double bbz = ddc[0] * dcbm[1] - ddc[1] * dcbm[0];
+        const double raasq = aax * aax + aay * aay + aaz * aaz;
+        const double rbbsq = bbx * bbx + bby * bby + bbz * bbz;
+        const double rgsq = dcbm[0] * dcbm[0] + dcbm[1] * dcbm[1] + dcbm[2] * dcbm[2];
+        const double rg = sqrt(rgsq);
+        double rginv = 0.0, raa2inv = 0.0, rbb2inv = 0.0;
+        if (rg > 0.0)
+            rginv = 1.0 / rg;
+        if (raasq > 0.0)
+            raa2inv = 1.0 / raasq;
+        if (rbbsq > 0.0)
+            rbb2inv = 1.0 / rbbsq;
+        const double rabinv = sqrt(raa2inv * rbb2inv);
+        double c_abcd = (aax * bbx + aay * bby + aaz * bbz) * rabinv;
+        const double s_abcd = rg * rabinv * (aax * ddc[0] + aay * ddc[1] + aaz * ddc[2]);
+        if (c_abcd > 1.0)
+            c_abcd = 1.0;
+        if (c_abcd < -1.0)
+            c_abcd = -1.0;
+        double p = 1.0, dfab = 0.0, ddfab = 0.0;
+        for (int j = 0; j < multi; j++)
+            {
+            ddfab = p * c_abcd - dfab * s_abcd;
+            dfab = p * s_abcd + dfab * c_abcd;
+            p = ddfab;
+            }
+        const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
+        p = p * cos_phi_0 + dfab * sin_phi_0;
+        p = p * sign;
+        dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
+        dfab = dfab * sign;
+        dfab *= (double)-multi;
+        p += 1.0;
+        if (multi == 0)
+            {
+            p = 1.0 + sign;
+            dfab = 0.0;
+            }
+        const double fg = dab[0] * dcbm[0] + dab[1] * dcbm[1] + dab[2] * dcbm[2];
+        const double hg = ddc[0] * dcbm[0] + ddc[1] * dcbm[1] + ddc[2] * dcbm[2];
+        const double fga = fg * raa2inv * rginv, hgb = hg * rbb2inv * rginv;
+        const double gaa = -raa2inv * rg, gbb = rbb2inv * rg;
+        const double dtf[3] = {gaa * aax, gaa * aay, gaa * aaz};
+        const double dtg[3] = {fga * aax - hgb * bbx, fga * aay - hgb * bby, fga * aaz - hgb * bbz};
+        const double dth[3] = {gbb * bbx, gbb * bby, gbb * bbz};
+        const double df = -K * dfab * 0.500;
+        double ffa[3], ffb[3], ffc[3], ffd[3];
+        for (int q = 0; q < 3; q++)
+            {
+            const double s2 = df * dtg[q];
+            ffa[q] = df * dtf[q];
+            ffb[q] = s2 - ffa[q];
+            ffd[q] = df * dth[q];
+            ffc[q] = -s2 - ffd[q];
+            }
+        const double eng = p * K * 0.125;
+        const double vir[6] = {(1. / 4.) * (dab[0] * ffa[0] + dcb[0] * ffc[0] + (ddc[0] + dcb[0]) * ffd[0]),
+                               (1. / 4.) * (dab[1] * ffa[0] + dcb[1] * ffc[0] + (ddc[1] + dcb[1]) * ffd[0]),
+                               (1. / 4.) * (dab[2] * ffa[0] + dcb[2] * ffc[0] + (ddc[2] + dcb[2]) * ffd[0]),
+                               (1. / 4.) * (dab[1] * ffa[1] + dcb[1] * ffc[1] + (ddc[1] + dcb[1]) * ffd[1]),
+                               (1. / 4.) * (dab[2] * ffa[1] + dcb[2] * ffc[1] + (ddc[2] + dcb[2]) * ffd[1]),
+                               (1. / 4.) * (dab[2] * ffa[2] + dcb[2] * ffc[2] + (ddc[2] + dcb[2]) * ffd[2])};
+
+        const double* mine = role == 0 ? ffa : (role == 1 ? ffb : (role == 2 ? ffc : ffd));
+        fx += (float)mine[0];
+        fy += (float)mine[1];
+        fz += (float)mine[2];
+        pe += (float)eng;
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                v[q] += (float)vir[q];
+        }
+    if (ACCUM)
+        {
+        float4 f = force[i];
+        f.x += fx;
+        f.y += fy;
+        f.z += fz;
+        f.w += pe;
+        force[i] = f;
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                virial[q * virial_pitch + i] += v[q];
+        }
+    else
+        {
+        force[i] = make_float4(fx, fy, fz, pe);
+        if (virial)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                virial[q * virial_pitch + i] = v[q];
+        }
+    }
+
+hb2_status launch_dihedral_forces(const BondArgs& a, const uint4* members, const uint32_t* type_role,
+                                  bool accumulate, const hb2_box& box, cudaStream_t stream)
+    {
+    if (a.N == 0)
+        return HB2_OK;
+    const uint32_t blocks = (a.N + BOND_BLOCK - 1) / BOND_BLOCK;
+    if (accumulate)
+        dihedral_force_kernel<true><<<blocks, BOND_BLOCK, 0, stream>>>(
+            a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, members, type_role, a.params, boxd(box), a.force,
+            a.virial, a.virial_pitch, a.skip_flag, a.err);
+    else
+        dihedral_force_kernel<false><<<blocks, BOND_BLOCK, 0, stream>>>(
+            a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, members, type_role, a.params, boxd(box), a.force,
+            a.virial, a.virial_pitch, a.skip_flag, a.err);
+    HB2_CHECK_LAUNCH("dihedral_force_kernel");
+    return HB2_OK;
+    }
+
 // One warp per row: entries whose particle is bonded to the row's owner are dropped, the row is
 // compacted in place (a 32-entry chunk is read completely before the chunk's survivors are written at
 // or below its start) and padded again with the dummy index up to a multiple of 32.

@@ -147,6 +147,9 @@ extern "C" void hb2_system_destroy(hb2_system* s)
     dev_free(s->d_bond_type);
     dev_free(s->d_angle_head);
     dev_free(s->d_angle_members);
+    dev_free(s->d_dihedral_head);
+    dev_free(s->d_dihedral_members);
+    dev_free(s->d_dihedral_tr);
     dev_free(s->d_stage);
     if (s->h_stage)
         cudaFreeHost(s->h_stage);
@@ -1850,6 +1853,74 @@ extern "C" hb2_status hb2_system_set_angles(hb2_system* s, uint32_t n_angles, co
     return HB2_OK;
     }
 
+extern "C" hb2_status hb2_system_set_dihedrals(hb2_system* s, uint32_t n_dihedrals, const uint32_t* group,
+                                               const uint32_t* typeid_, uint32_t n_dihedral_types)
+    {
+    if (!s || (n_dihedrals && (!group || !typeid_)))
+        return HB2_ERR_INVALID;
+    if (!s->pos[0] || (!s->dom.active && !s->rtag))
+        {
+        set_error("hb2_system_set_dihedrals: set the particles first");
+        return HB2_ERR_INVALID;
+        }
+    if (n_dihedral_types >= (1u << 30))
+        return HB2_ERR_INVALID;
+    const uint32_t N = s->dom.active ? (uint32_t)s->dom.N_global : s->N;
+    HB2_TRY(ensure_domain_rtag(s));
+    std::vector<uint32_t> head((size_t)N + 1, 0u);
+    for (uint32_t k = 0; k < n_dihedrals; k++)
+        {
+        const uint32_t* g = group + 4 * (size_t)k;
+        bool ok = typeid_[k] < n_dihedral_types;
+        for (int m = 0; m < 4 && ok; m++)
+            {
+            ok = g[m] < N;
+            for (int q = 0; q < m && ok; q++)
+                ok = g[q] != g[m];
+            }
+        if (!ok)
+            {
+            set_error("hb2_system_set_dihedrals: dihedral " + std::to_string(k)
+                      + " names a particle tag or a dihedral type out of range");
+            return HB2_ERR_INVALID;
+            }
+        for (int m = 0; m < 4; m++)
+            head[g[m] + 1]++;
+        }
+    for (uint32_t t = 0; t < N; t++)
+        head[t + 1] += head[t];
+    std::vector<uint4> members(std::max<size_t>(1, 4 * (size_t)n_dihedrals));
+    std::vector<uint32_t> tr(members.size(), 0u), fill(N, 0u);
+    for (uint32_t k = 0; k < n_dihedrals; k++)
+        {
+        const uint32_t* g = group + 4 * (size_t)k;
+        for (uint32_t m = 0; m < 4; m++)
+            {
+            const uint32_t at = head[g[m]] + fill[g[m]]++;
+            members[at] = make_uint4(g[0], g[1], g[2], g[3]);
+            tr[at] = typeid_[k] | (m << 30);
+            }
+        }
+    HB2_CUDA(cudaSetDevice(s->device));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(s->d_dihedral_head);
+    dev_free(s->d_dihedral_members);
+    dev_free(s->d_dihedral_tr);
+    s->d_dihedral_head = nullptr;
+    s->d_dihedral_members = nullptr;
+    s->d_dihedral_tr = nullptr;
+    HB2_TRY(dev_alloc(&s->d_dihedral_head, head.size()));
+    HB2_TRY(dev_alloc(&s->d_dihedral_members, members.size()));
+    HB2_TRY(dev_alloc(&s->d_dihedral_tr, tr.size()));
+    HB2_CUDA(cudaMemcpy(s->d_dihedral_head, head.data(), sizeof(uint32_t) * head.size(), cudaMemcpyHostToDevice));
+    HB2_CUDA(cudaMemcpy(s->d_dihedral_members, members.data(), sizeof(uint4) * members.size(),
+                        cudaMemcpyHostToDevice));
+    HB2_CUDA(cudaMemcpy(s->d_dihedral_tr, tr.data(), sizeof(uint32_t) * tr.size(), cudaMemcpyHostToDevice));
+    s->n_dihedrals = n_dihedrals;
+    s->n_dihedral_types = n_dihedral_types;
+    return HB2_OK;
+    }
+
 extern "C" hb2_status hb2_nlist_set_exclusion_pairs(hb2_nlist* nl, uint32_t n_pairs, const uint32_t* pairs)
     {
     if (!nl || (n_pairs && !pairs))
@@ -1918,7 +1989,7 @@ extern "C" hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds)
 
 extern "C" hb2_status hb2_bond_create(hb2_bond** out, hb2_system* s, hb2_bond_kind kind)
     {
-    if (!out || !s || (unsigned)kind > (unsigned)HB2_ANGLE_COSINESQ)
+    if (!out || !s || (unsigned)kind > (unsigned)HB2_DIHEDRAL_PERIODIC)
         return HB2_ERR_INVALID;
     hb2_bond* b = new hb2_bond();
     b->sys = s;
@@ -1950,7 +2021,7 @@ extern "C" void hb2_bond_destroy(hb2_bond* b)
 
 extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const double* user, uint32_t n_user)
     {
-    const uint32_t need = b && b->kind == HB2_BOND_FENEWCA ? 5u : 2u;
+    const uint32_t need = !b ? 2u : (b->kind == HB2_BOND_FENEWCA ? 5u : (b->kind == HB2_DIHEDRAL_PERIODIC ? 4u : 2u));
     if (!b || !user || n_user < need)
         {
         set_error("hb2_bond_set_params: harmonic takes {k, r0}, FENEWCA {k, r0, epsilon, sigma, delta}");
@@ -1974,6 +2045,11 @@ extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const doub
         p[3] = epsilon_x_4 * sigma_6;
         p[4] = (float)user[4];
         }
+    if (b->kind == HB2_DIHEDRAL_PERIODIC)
+        {
+        p[2] = (float)user[2]; // {k, d (sign), n (multiplicity), phi0}
+        p[3] = (float)user[3];
+        }
     b->have[type] = 1;
     b->params_dirty = true;
     return HB2_OK;
@@ -1982,7 +2058,8 @@ extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const doub
 hb2_status hb2_bond::upload_params()
     {
     const bool is_angle = kind == HB2_ANGLE_HARMONIC || kind == HB2_ANGLE_COSINESQ;
-    const uint32_t nt = is_angle ? sys->n_angle_types : sys->n_bond_types;
+    const uint32_t nt = kind == HB2_DIHEDRAL_PERIODIC ? sys->n_dihedral_types
+                                                       : (is_angle ? sys->n_angle_types : sys->n_bond_types);
     for (uint32_t t = 0; t < nt; t++)
         if (t >= have.size() || !have[t])
             {
@@ -2008,9 +2085,12 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     if (params_dirty)
         HB2_TRY(upload_params());
     const bool is_angle = kind == HB2_ANGLE_HARMONIC || kind == HB2_ANGLE_COSINESQ;
-    if ((is_angle ? s->n_angles : s->n_bonds) == 0 && accumulate)
+    const bool is_dihedral = kind == HB2_DIHEDRAL_PERIODIC;
+    if ((is_dihedral ? s->n_dihedrals : (is_angle ? s->n_angles : s->n_bonds)) == 0 && accumulate)
         return HB2_OK;
-    if (!is_angle && !s->d_bond_head) // no table was ever set: an empty one
+    if (is_dihedral && !s->d_dihedral_head)
+        HB2_TRY(hb2_system_set_dihedrals(s, 0, nullptr, nullptr, 0));
+    if (!is_angle && !is_dihedral && !s->d_bond_head) // no table was ever set: an empty one
         HB2_TRY(hb2_system_set_bonds(s, 0, nullptr, nullptr, 0));
     if (is_angle && !s->d_angle_head)
         HB2_TRY(hb2_system_set_angles(s, 0, nullptr, nullptr, 0));
@@ -2020,7 +2100,7 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     a.rtag = s->rtag;
     a.N = s->N;
     a.Ntot = s->N + s->Ng;
-    a.head = is_angle ? s->d_angle_head : s->d_bond_head;
+    a.head = is_dihedral ? s->d_dihedral_head : (is_angle ? s->d_angle_head : s->d_bond_head);
     a.partner = s->d_bond_partner;
     a.btype = s->d_bond_type;
     a.params = d_params;
@@ -2029,6 +2109,8 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     a.virial_pitch = virial_pitch;
     a.skip_flag = skip_flag;
     a.err = d_err;
+    if (is_dihedral)
+        return launch_dihedral_forces(a, s->d_dihedral_members, s->d_dihedral_tr, accumulate, s->box, s->stream);
     if (is_angle)
         return launch_angle_forces(kind, a, s->d_angle_members, accumulate, s->box, s->stream);
     return launch_bond_forces(kind, a, accumulate, s->box, s->stream);

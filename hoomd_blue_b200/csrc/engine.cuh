@@ -85,6 +85,11 @@ struct hb2_system
     uint32_t n_angles = 0, n_angle_types = 0;
     uint32_t* d_angle_head = nullptr;
     uint4* d_angle_members = nullptr;
+    // dihedral table keyed by particle tag: four member tags + (type | role << 30) per membership
+    uint32_t n_dihedrals = 0, n_dihedral_types = 0;
+    uint32_t* d_dihedral_head = nullptr;
+    uint4* d_dihedral_members = nullptr;
+    uint32_t* d_dihedral_tr = nullptr;
 
     std::vector<hb2_nlist*> nlists;
     std::vector<hb2_pair*> pairs;

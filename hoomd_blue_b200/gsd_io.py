@@ -148,6 +148,20 @@ def read_frame(filename, frame=-1):
         if grp is None:
             raise RuntimeError(f"{filename}: angles/N = {na} but angles/group is missing")
         snap.angles.group[:] = grp.reshape(na, 3)
+    nd = g.chunk(f, "dihedrals/N")
+    nd = int(nd[0, 0]) if nd is not None else 0
+    if nd:
+        snap.dihedrals.N = nd
+        t = g.chunk(f, "dihedrals/types")
+        snap.dihedrals.types = ([bytes(row).split(b"\0")[0].decode() for row in t.astype(np.uint8)]
+                                if t is not None else ["dihedralA"])
+        tid = g.chunk(f, "dihedrals/typeid", cur_n=nd)
+        if tid is not None:
+            snap.dihedrals.typeid[:] = tid.reshape(-1)
+        grp = g.chunk(f, "dihedrals/group", cur_n=nd)
+        if grp is None:
+            raise RuntimeError(f"{filename}: dihedrals/N = {nd} but dihedrals/group is missing")
+        snap.dihedrals.group[:] = grp.reshape(nd, 4)
     return snap, step
 
 
@@ -190,6 +204,15 @@ def frame_chunks(snap, step, dynamic=None, first=True, log=None):
         out += [("angles/N", np.array([[angles.N]], dtype=np.uint32)), ("angles/types", atypes),
                 ("angles/typeid", np.asarray(angles.typeid, dtype=np.uint32).reshape(-1, 1)),
                 ("angles/group", np.asarray(angles.group, dtype=np.int32).reshape(-1, 3))]
+    dihedrals = getattr(snap, "dihedrals", None)
+    if dihedrals is not None and dihedrals.N and (first or "topology" in dynamic):
+        tw = max(len(t) for t in dihedrals.types) + 1
+        dtypes = np.zeros((len(dihedrals.types), tw), dtype=np.int8)
+        for i, t in enumerate(dihedrals.types):
+            dtypes[i, :len(t)] = np.frombuffer(t.encode(), dtype=np.int8)
+        out += [("dihedrals/N", np.array([[dihedrals.N]], dtype=np.uint32)), ("dihedrals/types", dtypes),
+                ("dihedrals/typeid", np.asarray(dihedrals.typeid, dtype=np.uint32).reshape(-1, 1)),
+                ("dihedrals/group", np.asarray(dihedrals.group, dtype=np.int32).reshape(-1, 4))]
     if first or "property" in dynamic:
         out.append(("particles/position", np.asarray(p.position, dtype=np.float32).reshape(n, 3)))
     if first or "momentum" in dynamic:

@@ -90,8 +90,16 @@ class _Angles(_Bonds):
         self.group = np.zeros((n, 3), dtype=np.uint32)
 
 
+class _Dihedrals(_Bonds):
+    """hoomd.Snapshot.dihedrals: N, types, typeid (N,), group (N, 4) member tags."""
+
+    def _alloc(self, n):
+        self.typeid = np.zeros((n,), dtype=np.uint32)
+        self.group = np.zeros((n, 4), dtype=np.uint32)
+
+
 class Snapshot:
-    """hoomd.Snapshot (configuration + particles + bonds + angles). pinned=True (not in the reference) allocates the
+    """hoomd.Snapshot (configuration + particles + bonds + angles + dihedrals). pinned=True (not in the reference) allocates the
     particle arrays in page-locked memory so that set_snapshot / get_snapshot copy by DMA."""
 
     def __init__(self, communicator=None, pinned=False):
@@ -99,6 +107,7 @@ class Snapshot:
         self.particles = _Particles(pinned)
         self.bonds = _Bonds()
         self.angles = _Angles()
+        self.dihedrals = _Dihedrals()
         self.communicator = communicator
 
     @classmethod
@@ -219,11 +228,13 @@ class State:
             p = snapshot.particles if comm.rank == 0 else None
             b = getattr(snapshot, "bonds", None) if comm.rank == 0 else None
             a = getattr(snapshot, "angles", None) if comm.rank == 0 else None
+            dh = getattr(snapshot, "dihedrals", None) if comm.rank == 0 else None
             data = _comm.broadcast_object(
                 None if p is None else (p.position, p.velocity, p.typeid, p.mass, p.image,
                                         None if b is None or not b.N else (list(b.types), b.typeid, b.group),
-                                        None if a is None or not a.N else (list(a.types), a.typeid, a.group)))
-            pos, vel, tid, mass, img, bd, ad = data
+                                        None if a is None or not a.N else (list(a.types), a.typeid, a.group),
+                                        None if dh is None or not dh.N else (list(dh.types), dh.typeid, dh.group)))
+            pos, vel, tid, mass, img, bd, ad, dd = data
             self._set_tagged(len(pos), np.arange(len(pos), dtype=np.uint32), pos, vel, tid, mass, img)
             bonds = None
             if bd is not None:
@@ -237,6 +248,12 @@ class State:
                 angles.N = len(ad[1])
                 angles.types, angles.typeid[:], angles.group[:] = ad[0], ad[1], ad[2]
             self._set_angles(angles)
+            dihedrals = None
+            if dd is not None:
+                dihedrals = _Dihedrals()
+                dihedrals.N = len(dd[1])
+                dihedrals.types, dihedrals.typeid[:], dihedrals.group[:] = dd[0], dd[1], dd[2]
+            self._set_dihedrals(dihedrals)
             return
         p = snapshot.particles
         pos = np.ascontiguousarray(p.position, dtype=np.float32)
@@ -249,6 +266,19 @@ class State:
                                          ptr(tid, C.c_uint32), ptr(img, C.c_int32)))
         self._set_bonds(getattr(snapshot, "bonds", None))
         self._set_angles(getattr(snapshot, "angles", None))
+        self._set_dihedrals(getattr(snapshot, "dihedrals", None))
+
+    def _set_dihedrals(self, dih):
+        L = _lib.lib()
+        n = 0 if dih is None else int(dih.N)
+        self._dihedral_types = [] if dih is None else list(dih.types)
+        self._dihedral_typeid = np.zeros(0, np.uint32) if n == 0 else np.ascontiguousarray(dih.typeid, np.uint32)
+        self._dihedral_group = np.zeros((0, 4), np.uint32) if n == 0 else np.ascontiguousarray(dih.group, np.uint32)
+        if n == 0 and not getattr(self, "_had_dihedrals", False):
+            return
+        self._had_dihedrals = True
+        check(L.hb2_system_set_dihedrals(self._h, n, ptr(self._dihedral_group, C.c_uint32),
+                                         ptr(self._dihedral_typeid, C.c_uint32), len(self._dihedral_types)))
 
     def _set_angles(self, angles):
         L = _lib.lib()
@@ -309,6 +339,11 @@ class State:
             s.bonds.types = list(self._bond_types)
             s.bonds.typeid[:] = self._bond_typeid
             s.bonds.group[:] = self._bond_group
+        if getattr(self, "_dihedral_types", None):
+            s.dihedrals.N = len(self._dihedral_typeid)
+            s.dihedrals.types = list(self._dihedral_types)
+            s.dihedrals.typeid[:] = self._dihedral_typeid
+            s.dihedrals.group[:] = self._dihedral_group
         if getattr(self, "_angle_types", None):
             s.angles.N = len(self._angle_typeid)
             s.angles.types = list(self._angle_types)

@@ -180,7 +180,8 @@ typedef enum hb2_bond_kind
     HB2_BOND_HARMONIC = 0, /* hoomd/md/EvaluatorBondHarmonic.h */
     HB2_BOND_FENEWCA = 1,  /* hoomd/md/EvaluatorBondFENE.h */
     HB2_ANGLE_HARMONIC = 2, /* hoomd/md/HarmonicAngleForceCompute.cc; {k, t0} per ANGLE type */
-    HB2_ANGLE_COSINESQ = 3  /* hoomd/md/CosineSqAngleForceCompute.cc; {k, t0} per ANGLE type */
+    HB2_ANGLE_COSINESQ = 3, /* hoomd/md/CosineSqAngleForceCompute.cc; {k, t0} per ANGLE type */
+    HB2_DIHEDRAL_PERIODIC = 4 /* hoomd/md/HarmonicDihedralForceCompute.cc; {k, d, n, phi0} per DIHEDRAL type */
     } hb2_bond_kind;
 typedef struct hb2_bond hb2_bond;             /* ~ PotentialBond<EvaluatorBondHarmonic> */
 typedef struct hb2_integrator hb2_integrator; /* ~ IntegratorTwoStep + TwoStepConstantVolume */
@@ -313,6 +314,9 @@ hb2_status hb2_system_set_bonds(hb2_system* sys, uint32_t n_bonds, const uint32_
  * kinds of hb2_bond_create take their parameters per angle type. */
 hb2_status hb2_system_set_angles(hb2_system* sys, uint32_t n_angles, const uint32_t* group,
                                  const uint32_t* typeid_, uint32_t n_angle_types);
+/* DihedralData of the snapshot: 4 member TAGS per dihedral. */
+hb2_status hb2_system_set_dihedrals(hb2_system* sys, uint32_t n_dihedrals, const uint32_t* group,
+                                    const uint32_t* typeid_, uint32_t n_dihedral_types);
 hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds);
 /* Further excluded pairs by TAG (what exclusions=('angle', '1-3', ...) add through
  * NeighborList::addExclusion, hoomd/md/NeighborList.cc:881-1120); replaces the previous set. */

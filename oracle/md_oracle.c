@@ -805,6 +805,122 @@ int orc_angle(int kind, const orc_box* b, const double* pos, uint32_t N, const u
     return 0;
     }
 
+int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                          const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals,
+                          const double* params, double* force, double* virial)
+    {
+    /* hoomd/md/HarmonicDihedralForceCompute.cc:104-356 (hoomd.md.dihedral.Periodic):
+       E = k/2 (1 + d cos(n phi - phi0)); params = (k, d, n, phi0) per dihedral type; a quarter of the
+       energy and of the virial to each member. */
+    memset(force, 0, sizeof(double) * 4 * (size_t)N);
+    memset(virial, 0, sizeof(double) * 6 * (size_t)N);
+    for (uint32_t i = 0; i < n_dihedrals; i++)
+        {
+        uint32_t idx[4];
+        for (int m = 0; m < 4; m++)
+            {
+            idx[m] = rtag[group[4 * i + m]];
+            if (idx[m] >= N)
+                return 1 + (int)i;
+            }
+        double dab[3], dcb[3], ddc[3];
+        for (int d = 0; d < 3; d++)
+            {
+            dab[d] = pos[3 * (size_t)idx[0] + d] - pos[3 * (size_t)idx[1] + d];
+            dcb[d] = pos[3 * (size_t)idx[2] + d] - pos[3 * (size_t)idx[1] + d];
+            ddc[d] = pos[3 * (size_t)idx[3] + d] - pos[3 * (size_t)idx[2] + d];
+            }
+        orc_min_image(b, dab);
+        orc_min_image(b, dcb);
+        orc_min_image(b, ddc);
+        const double* prm = params + 4 * (size_t)type[i];
+        const double K = prm[0], sign = prm[1], phi_0 = prm[3];
+        const int multi = (int)prm[2];
+#define MINIMAGE(v) orc_min_image(b, v)
+
+        double dcbm[3] = {-dcb[0], -dcb[1], -dcb[2]};
+        MINIMAGE(dcbm);
+        const double aax = dab[1] * dcbm[2] - dab[2] * dcbm[1];
+        const double aay = dab[2] * dcbm[0] - dab[0] * dcbm[2];
+        const double aaz = dab[0] * dcbm[1] - dab[1] * dcbm[0];
+        const double bbx = ddc[1] * dcbm[2] - ddc[2] * dcbm[1];
+        const double bby = ddc[2] * dcbm[0] - ddc[0] * dcbm[2];
+        const double bbz = ddc[0] * dcbm[1] - ddc[1] * dcbm[0];
+        const double raasq = aax * aax + aay * aay + aaz * aaz;
+        const double rbbsq = bbx * bbx + bby * bby + bbz * bbz;
+        const double rgsq = dcbm[0] * dcbm[0] + dcbm[1] * dcbm[1] + dcbm[2] * dcbm[2];
+        const double rg = sqrt(rgsq);
+        double rginv = 0.0, raa2inv = 0.0, rbb2inv = 0.0;
+        if (rg > 0.0)
+            rginv = 1.0 / rg;
+        if (raasq > 0.0)
+            raa2inv = 1.0 / raasq;
+        if (rbbsq > 0.0)
+            rbb2inv = 1.0 / rbbsq;
+        const double rabinv = sqrt(raa2inv * rbb2inv);
+        double c_abcd = (aax * bbx + aay * bby + aaz * bbz) * rabinv;
+        const double s_abcd = rg * rabinv * (aax * ddc[0] + aay * ddc[1] + aaz * ddc[2]);
+        if (c_abcd > 1.0)
+            c_abcd = 1.0;
+        if (c_abcd < -1.0)
+            c_abcd = -1.0;
+        double p = 1.0, dfab = 0.0, ddfab = 0.0;
+        for (int j = 0; j < multi; j++)
+            {
+            ddfab = p * c_abcd - dfab * s_abcd;
+            dfab = p * s_abcd + dfab * c_abcd;
+            p = ddfab;
+            }
+        const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
+        p = p * cos_phi_0 + dfab * sin_phi_0;
+        p = p * sign;
+        dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
+        dfab = dfab * sign;
+        dfab *= (double)-multi;
+        p += 1.0;
+        if (multi == 0)
+            {
+            p = 1.0 + sign;
+            dfab = 0.0;
+            }
+        const double fg = dab[0] * dcbm[0] + dab[1] * dcbm[1] + dab[2] * dcbm[2];
+        const double hg = ddc[0] * dcbm[0] + ddc[1] * dcbm[1] + ddc[2] * dcbm[2];
+        const double fga = fg * raa2inv * rginv, hgb = hg * rbb2inv * rginv;
+        const double gaa = -raa2inv * rg, gbb = rbb2inv * rg;
+        const double dtf[3] = {gaa * aax, gaa * aay, gaa * aaz};
+        const double dtg[3] = {fga * aax - hgb * bbx, fga * aay - hgb * bby, fga * aaz - hgb * bbz};
+        const double dth[3] = {gbb * bbx, gbb * bby, gbb * bbz};
+        const double df = -K * dfab * 0.500;
+        double ffa[3], ffb[3], ffc[3], ffd[3];
+        for (int q = 0; q < 3; q++)
+            {
+            const double s2 = df * dtg[q];
+            ffa[q] = df * dtf[q];
+            ffb[q] = s2 - ffa[q];
+            ffd[q] = df * dth[q];
+            ffc[q] = -s2 - ffd[q];
+            }
+        const double eng = p * K * 0.125;
+        const double vir[6] = {(1. / 4.) * (dab[0] * ffa[0] + dcb[0] * ffc[0] + (ddc[0] + dcb[0]) * ffd[0]),
+                               (1. / 4.) * (dab[1] * ffa[0] + dcb[1] * ffc[0] + (ddc[1] + dcb[1]) * ffd[0]),
+                               (1. / 4.) * (dab[2] * ffa[0] + dcb[2] * ffc[0] + (ddc[2] + dcb[2]) * ffd[0]),
+                               (1. / 4.) * (dab[1] * ffa[1] + dcb[1] * ffc[1] + (ddc[1] + dcb[1]) * ffd[1]),
+                               (1. / 4.) * (dab[2] * ffa[1] + dcb[2] * ffc[1] + (ddc[2] + dcb[2]) * ffd[1]),
+                               (1. / 4.) * (dab[2] * ffa[2] + dcb[2] * ffc[2] + (ddc[2] + dcb[2]) * ffd[2])};
+#undef MINIMAGE
+        const double* ff[4] = {ffa, ffb, ffc, ffd};
+        for (int m = 0; m < 4; m++)
+            {
+            for (int d = 0; d < 3; d++)
+                force[4 * (size_t)idx[m] + d] += ff[m][d];
+            force[4 * (size_t)idx[m] + 3] += eng;
+            for (int q = 0; q < 6; q++)
+                virial[(size_t)q * N + idx[m]] += vir[q];
+            }
+        }
+    return 0;
+    }
+
 /* ---------------------------------------------------------------------- RNG ---- */
 
 void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])

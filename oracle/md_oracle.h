@@ -124,6 +124,12 @@ int orc_angle(int kind, const orc_box* b, const double* pos, uint32_t N, const u
               const uint32_t* angle_group, const uint32_t* angle_type, uint32_t n_angles,
               const double* params, double* force, double* virial);
 
+/* hoomd.md.dihedral.Periodic (hoomd/md/HarmonicDihedralForceCompute.cc): params = (k, d, n, phi0) per
+ * dihedral type; group = 4 member tags. Returns 0 or 1 + the index of an incomplete dihedral. */
+int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                          const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals,
+                          const double* params, double* force, double* virial);
+
 /* RNG: Philox4x32-10 (Salmon et al., SC'11; hoomd/extern/random123 commit a2c4f04) and HOOMD's
  * Seed/Counter packing hoomd/RandomNumbers.h:136-199 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -333,6 +333,26 @@ def angle(kind, box, pos, angle_group, angle_type, params, tags=None):
     return force, virial
 
 
+def dihedral_periodic(box, pos, group, types, params, tags=None):
+    """hoomd.md.dihedral.Periodic; params (k, d, n, phi0) per type; returns (force N x 4, virial 6 x N)."""
+    pos = _f64(pos)
+    n = pos.shape[0]
+    tags = np.arange(n, dtype=np.uint32) if tags is None else _u32(tags)
+    rtag = np.zeros(int(tags.max()) + 1 if n else 1, dtype=np.uint32)
+    rtag[tags] = np.arange(n, dtype=np.uint32)
+    dg = _u32(np.asarray(group).reshape(-1, 4))
+    dt = _u32(types)
+    params = _f64(np.asarray(params).reshape(-1, 4))
+    force = np.zeros((n, 4))
+    virial = np.zeros((6, n))
+    rc = lib().orc_dihedral_periodic(C.byref(box), _p(pos, C.c_double), C.c_uint32(n), _p(rtag, C.c_uint32),
+                                     _p(dg, C.c_uint32), _p(dt, C.c_uint32), C.c_uint32(dg.shape[0]),
+                                     _p(params, C.c_double), _p(force, C.c_double), _p(virial, C.c_double))
+    if rc:
+        raise RuntimeError(f"Error: dihedral {rc - 1} is incomplete.")
+    return force, virial
+
+
 def bond_fenewca(box, pos, bond_group, bond_type, params, tags=None):
     """PotentialBond<EvaluatorBondFENE>; params (k, r0, epsilon, sigma, delta) per bond type."""
     return bond_harmonic(box, pos, bond_group, bond_type, params, tags, _fn="orc_bond_fenewca", _np=5)

@@ -59,6 +59,48 @@ def test_oracle_angle_reference_vectors(oracle, kind, k, t0, force, energy):
     np.testing.assert_allclose(f2, f, atol=1e-6)
 
 
+# (k, d, n, phi0, force, energy) hoomd/md/pytest/test_dihedral.py:14-35: four particles, phi = 45 degrees
+DIHEDRAL_VECTORS = [(3.0, -1, 2, np.pi / 2, 0, 3), (10.0, 1, 1, np.pi / 4, 5.0, 5.0),
+                    (5.0, 1, 3, np.pi / 6, 1.9411, 0.0852)]
+
+
+def quadruplet(d=1.0, phi_deg=45):
+    # hoomd/md/pytest/test_dihedral.py:69-104 dihedral_snapshot_factory
+    ph = phi_deg * np.pi / 180
+    return np.array([[0.0, d * np.cos(ph / 2), d * np.sin(ph / 2) + 0.1], [0.0, 0.0, 0.1], [d, 0.0, 0.1],
+                     [d, d * np.cos(ph / 2), -d * np.sin(ph / 2) + 0.1]], dtype=np.float32)
+
+
+def check_dihedral_vectors(forces, energy, force, e_ref):
+    ph = 45 * np.pi / 180
+    fa = force * np.array([0, np.sin(-ph / 2), np.cos(-ph / 2)])
+    assert energy == pytest.approx(e_ref, rel=1e-2, abs=1e-5)
+    np.testing.assert_allclose(forces[0], fa, rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(forces[1], -1 * fa, rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(forces[2], [0, -1 * fa[1], fa[2]], rtol=1e-2, atol=1e-5)
+    np.testing.assert_allclose(forces[3], [0, fa[1], -1 * fa[2]], rtol=1e-2, atol=1e-5)
+
+
+@pytest.mark.parametrize("k,d,n,phi0,force,energy", DIHEDRAL_VECTORS)
+def test_oracle_dihedral_reference_vectors(oracle, k, d, n, phi0, force, energy):
+    box = oracle.make_box([20.0, 20.0, 20.0])
+    f, v = oracle.dihedral_periodic(box, quadruplet(), [[0, 1, 2, 3]], [0], [[k, d, n, phi0]])
+    check_dihedral_vectors(f[:, :3], f[:, 3].sum(), force, energy)
+    assert np.abs(f[:, :3].sum(axis=0)).max() < 1e-12
+    pos = quadruplet().astype(np.float64)
+    assert np.abs(np.cross(pos, f[:, :3]).sum(axis=0)).max() < 1e-6
+    # F = -dE/dx by central differences of the oracle's energy, every particle and component
+    h = 1e-6
+    for i in range(4):
+        for c in range(3):
+            pp, pm = pos.copy(), pos.copy()
+            pp[i, c] += h
+            pm[i, c] -= h
+            ep = oracle.dihedral_periodic(box, pp, [[0, 1, 2, 3]], [0], [[k, d, n, phi0]])[0][:, 3].sum()
+            em = oracle.dihedral_periodic(box, pm, [[0, 1, 2, 3]], [0], [[k, d, n, phi0]])[0][:, 3].sum()
+            assert -(ep - em) / (2 * h) == pytest.approx(f[i, c], rel=1e-4, abs=1e-6)
+
+
 def two_particles(d=0.969):
     # hoomd/conftest.py:168-196 two_particle_snapshot_factory(d=0.969, L=5)
     return np.array([[-d / 2, 0, 0.1], [d / 2, 0, 0.1]], dtype=np.float32)
@@ -300,6 +342,31 @@ def test_angle_reference_vectors(oracle, kind, k, t0, force, energy):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,d,n,phi0,force,energy", DIHEDRAL_VECTORS)
+def test_dihedral_reference_vectors(oracle, k, d, n, phi0, force, energy):
+    """hoomd/md/pytest/test_dihedral.py:138-177 as written there, plus the oracle to 2e-5."""
+    import hoomd_blue_b200 as hoomd
+    snap = hoomd.Snapshot.from_arrays([20, 20, 20, 0, 0, 0], quadruplet())
+    snap.dihedrals.N = 1
+    snap.dihedrals.types = ["A-A-A-A"]
+    snap.dihedrals.group[0] = (0, 1, 2, 3)
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=1)
+    sim.always_compute_pressure = True
+    sim.create_state_from_snapshot(snap)
+    potential = hoomd.md.dihedral.Periodic()
+    potential.params["A-A-A-A"] = dict(k=k, d=d, n=n, phi0=phi0)
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.005, forces=[potential])
+    sim.run(0)
+    check_dihedral_vectors(potential.forces, sum(potential.energies), force, energy)
+    box = oracle.make_box([20.0, 20.0, 20.0])
+    f_ref, v_ref = oracle.dihedral_periodic(box, quadruplet(), [[0, 1, 2, 3]], [0], [[k, d, n, phi0]])
+    np.testing.assert_allclose(potential.forces, f_ref[:, :3], rtol=2e-5, atol=2e-6)
+    assert potential.energy == pytest.approx(f_ref[:, 3].sum(), rel=2e-5, abs=1e-6)
+    np.testing.assert_allclose(potential.virials, v_ref.T, rtol=2e-5, atol=2e-6)
+    assert tuple(sim.state.get_snapshot().dihedrals.group[0]) == (0, 1, 2, 3)
+
+
+@pytest.mark.gpu
 def test_semiflexible_chains_vs_oracle(oracle):
     """bonds + angles + WCA on lattice chains: every force against the oracle, the net force conserves
     energy through rebuilds (the angle table follows the particles through rtag)."""
@@ -321,6 +388,12 @@ def test_semiflexible_chains_vs_oracle(oracle):
     snap.angles.types = ["stiff", "soft"]
     snap.angles.group[:] = angles
     snap.angles.typeid[:] = np.arange(len(angles)) % 2
+    dihedrals = np.array([(i - 1, i, i + 1, i + 2) for i in range(1, n - 2)
+                          if (i - 1, i) in bonded and (i, i + 1) in bonded and (i + 1, i + 2) in bonded],
+                         dtype=np.uint32)
+    snap.dihedrals.N = len(dihedrals)
+    snap.dihedrals.types = ["torsion"]
+    snap.dihedrals.group[:] = dihedrals
     sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=2)
     sim.create_state_from_snapshot(snap)
     cell = hoomd.md.nlist.Cell(buffer=0.3)
@@ -331,16 +404,25 @@ def test_semiflexible_chains_vs_oracle(oracle):
     ha = hoomd.md.angle.Harmonic()
     ha.params["stiff"] = dict(k=20.0, t0=np.pi)
     ha.params["soft"] = dict(k=5.0, t0=2.5)
+    hd = hoomd.md.dihedral.Periodic()
+    hd.params["torsion"] = dict(k=2.0, d=1, n=3, phi0=0.4)
     sim.operations.integrator = hoomd.md.Integrator(
-        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[lj, hb, ha])
+        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())],
+        forces=[lj, hb, ha, hd])
     sim.run(0)
     box = oracle.make_box([float(v) for v in L])
     a_ref, _ = oracle.angle("harmonic", box, pos, angles, snap.angles.typeid, [[20.0, np.pi], [5.0, 2.5]])
     assert force_err(ha.forces, a_ref[:, :3]) <= FORCE_RTOL
     assert abs(ha.energy - a_ref[:, 3].sum()) <= 1e-5 * abs(a_ref[:, 3].sum())
     b_ref, _ = oracle.bond_harmonic(box, pos, group, np.zeros(len(group), np.uint32), [[200.0, 0.95]])
+    d_ref, _ = oracle.dihedral_periodic(box, pos, dihedrals, np.zeros(len(dihedrals), np.uint32),
+                                        [[2.0, 1, 3, 0.4]])
+    # nearly straight chains: the torsion forces are ill-conditioned (1 / |a x b|^2), compare to 1e-4
+    assert force_err(hd.forces, d_ref[:, :3]) <= 1e-4
+    assert abs(hd.energy - d_ref[:, 3].sum()) <= 1e-5 * abs(d_ref[:, 3].sum())
     ke, pe, _ = sim.operations.integrator._thermo()
-    assert abs(pe - (lj.energy + b_ref[:, 3].sum() + a_ref[:, 3].sum())) <= 1e-5 * abs(pe)
+    e_all = lj.energy + b_ref[:, 3].sum() + a_ref[:, 3].sum() + d_ref[:, 3].sum()
+    assert abs(pe - e_all) <= 1e-5 * abs(pe)
     # exclusions=('bond', 'angle'): the chain ends of every angle leave the list too; for linear chains
     # ('bond', '1-3') names the same pairs
     from tests.test_gpu_parity import canon_pairs
@@ -362,6 +444,10 @@ def test_semiflexible_chains_vs_oracle(oracle):
             dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[l2])
         s2.run(0)
         assert np.array_equal(canon_pairs(c2.pair_list), want), excl
+    # dynamics without the torsion (it is singular for the straight triplets these chains start from;
+    # test_zigzag_chains_nve integrates it): energy is conserved through rebuilds
+    sim.operations.integrator = hoomd.md.Integrator(
+        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[lj, hb, ha])
     sim.run(500)
     e = []
     for _ in range(10):
@@ -369,6 +455,54 @@ def test_semiflexible_chains_vs_oracle(oracle):
         ke, pe, _ = sim.operations.integrator._thermo()
         e.append(ke + pe)
     assert cell.num_builds >= 1 and ke > 0.3 * n
+    assert np.ptp(e) <= 2e-3 * ke
+
+
+@pytest.mark.gpu
+def test_zigzag_chains_nve():
+    """bonds + angles + periodic dihedrals on bent (zig-zag) chains: the net force conserves energy."""
+    import hoomd_blue_b200 as hoomd
+    rng = np.random.default_rng(3)
+    nc, ln, b0, th = 216, 8, 1.0, 1.911
+    L = np.float32(6 * 9.0)
+    pos, bonds, angles, dih = [], [], [], []
+    for c in range(nc):
+        o = (np.array([c % 6, (c // 6) % 6, c // 36]) + 0.5) * 9.0 - float(L) / 2
+        for k in range(ln):
+            i = c * ln + k
+            pos.append(o + [k * b0 * np.sin(th / 2), (k % 2) * b0 * np.cos(th / 2), 0.0])
+            if k >= 1:
+                bonds.append((i - 1, i))
+            if k >= 2:
+                angles.append((i - 2, i - 1, i))
+            if k >= 3:
+                dih.append((i - 3, i - 2, i - 1, i))
+    pos = np.array(pos) + rng.normal(0, 0.03, (nc * ln, 3))
+    pos = (pos + float(L) / 2) % float(L) - float(L) / 2   # chains of the last column cross the box face
+    pos = np.clip(pos.astype(np.float32), -L / 2, np.nextafter(L / 2, np.float32(0)))
+    vel = rng.normal(0, 0.5, pos.shape).astype(np.float32)
+    snap = hoomd.Snapshot.from_arrays([L, L, L, 0, 0, 0], pos, vel)
+    for grp, data, name in ((snap.bonds, bonds, "b"), (snap.angles, angles, "a"), (snap.dihedrals, dih, "d")):
+        grp.N = len(data)
+        grp.types = [name]
+        grp.group[:] = data
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=2)
+    sim.create_state_from_snapshot(snap)
+    hb = hoomd.md.bond.Harmonic()
+    hb.params["b"] = dict(k=300.0, r0=1.0)
+    ha = hoomd.md.angle.Harmonic()
+    ha.params["a"] = dict(k=30.0, t0=th)
+    hd = hoomd.md.dihedral.Periodic()
+    hd.params["d"] = dict(k=3.0, d=1, n=3, phi0=0.0)
+    sim.operations.integrator = hoomd.md.Integrator(
+        dt=0.001, methods=[hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())], forces=[hb, ha, hd])
+    sim.run(200)
+    e = []
+    for _ in range(10):
+        sim.run(200)
+        ke, pe, _ = sim.operations.integrator._thermo()
+        e.append(ke + pe)
+    assert hd.energy > 0 and ke > 0.05 * len(pos)
     assert np.ptp(e) <= 2e-3 * ke
 
 
