@@ -320,10 +320,11 @@ hb2_status launch_angle_forces(hb2_bond_kind kind, const BondArgs& a, const uint
     return HB2_OK;
     }
 
-// Periodic dihedrals (hoomd.md.dihedral.Periodic, hoomd/md/HarmonicDihedralForceCompute.cc:104-356),
+// Dihedrals: KIND 0 Periodic (hoomd/md/HarmonicDihedralForceCompute.cc:104-356), KIND 1 OPLS
+// (hoomd/md/OPLSDihedralForceCompute.cc:100-352, parameters k_i / 2),
 // owner-computes like the angles: table entries hold the four member tags and `type | role << 30`;
 // the quadruplet is evaluated in fp64 with the reference's arithmetic and the particle keeps its share.
-template<bool ACCUM>
+template<int KIND, bool ACCUM>
 __global__ void __launch_bounds__(BOND_BLOCK)
     dihedral_force_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
                           const uint32_t* __restrict__ rtag, uint32_t N, uint32_t Ntot,
@@ -363,8 +364,7 @@ __global__ void __launch_bounds__(BOND_BLOCK)
         min_image_exact(box, dcb[0], dcb[1], dcb[2]);
         min_image_exact(box, ddc[0], ddc[1], ddc[2]);
         const float* prm = params + HB2_BOND_PARAM_FLOATS * type;
-        const double K = (double)prm[0], sign = (double)prm[1], phi_0 = (double)prm[3];
-        const int multi = (int)prm[2];
+        const double prm_d[4] = {(double)prm[0], (double)prm[1], (double)prm[2], (double)prm[3]};
 
         double dcbm[3] = {-dcb[0], -dcb[1], -dcb[2]};
         min_image_exact(box, dcbm[0], dcbm[1], dcbm[2]);
@@ -392,24 +392,57 @@ __global__ void __launch_bounds__(BOND_BLOCK)
             c_abcd = 1.0;
         if (c_abcd < -1.0)
             c_abcd = -1.0;
-        double p = 1.0, dfab = 0.0, ddfab = 0.0;
-        for (int j = 0; j < multi; j++)
+        double df, eng;
+        if (KIND == 1)
             {
-            ddfab = p * c_abcd - dfab * s_abcd;
-            dfab = p * s_abcd + dfab * c_abcd;
-            p = ddfab;
+            // hoomd/md/OPLSDihedralForceCompute.cc:236-279: p = sum_i k_i/2 (1 + (-1)^(i+1) cos(i phi)),
+            // df = dp/dphi through the Chebyshev-like recursion; the halved k_i are the parameters
+            const double k1 = prm_d[0], k2 = prm_d[1], k3 = prm_d[2], k4 = prm_d[3];
+            double ddf1 = c_abcd, df1 = s_abcd, cos_term = ddf1;
+            double p = k1 * (1.0 + cos_term);
+            df = k1 * df1;
+            ddf1 = cos_term * c_abcd - df1 * s_abcd;
+            df1 = cos_term * s_abcd + df1 * c_abcd;
+            cos_term = ddf1;
+            p += k2 * (1.0 - cos_term);
+            df += -2.0 * k2 * df1;
+            ddf1 = cos_term * c_abcd - df1 * s_abcd;
+            df1 = cos_term * s_abcd + df1 * c_abcd;
+            cos_term = ddf1;
+            p += k3 * (1.0 + cos_term);
+            df += 3.0 * k3 * df1;
+            ddf1 = cos_term * c_abcd - df1 * s_abcd;
+            df1 = cos_term * s_abcd + df1 * c_abcd;
+            cos_term = ddf1;
+            p += k4 * (1.0 - cos_term);
+            df += -4.0 * k4 * df1;
+            eng = 0.25 * p;
             }
-        const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
-        p = p * cos_phi_0 + dfab * sin_phi_0;
-        p = p * sign;
-        dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
-        dfab = dfab * sign;
-        dfab *= (double)-multi;
-        p += 1.0;
-        if (multi == 0)
+        else
             {
-            p = 1.0 + sign;
-            dfab = 0.0;
+            const double K = prm_d[0], sign = prm_d[1], phi_0 = prm_d[3];
+            const int multi = (int)prm_d[2];
+            double p = 1.0, dfab = 0.0, ddfab = 0.0;
+            for (int j = 0; j < multi; j++)
+                {
+                ddfab = p * c_abcd - dfab * s_abcd;
+                dfab = p * s_abcd + dfab * c_abcd;
+                p = ddfab;
+                }
+            const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
+            p = p * cos_phi_0 + dfab * sin_phi_0;
+            p = p * sign;
+            dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
+            dfab = dfab * sign;
+            dfab *= (double)-multi;
+            p += 1.0;
+            if (multi == 0)
+                {
+                p = 1.0 + sign;
+                dfab = 0.0;
+                }
+            df = -K * dfab * 0.500;
+            eng = p * K * 0.125;
             }
         const double fg = dab[0] * dcbm[0] + dab[1] * dcbm[1] + dab[2] * dcbm[2];
         const double hg = ddc[0] * dcbm[0] + ddc[1] * dcbm[1] + ddc[2] * dcbm[2];
@@ -418,7 +451,6 @@ __global__ void __launch_bounds__(BOND_BLOCK)
         const double dtf[3] = {gaa * aax, gaa * aay, gaa * aaz};
         const double dtg[3] = {fga * aax - hgb * bbx, fga * aay - hgb * bby, fga * aaz - hgb * bbz};
         const double dth[3] = {gbb * bbx, gbb * bby, gbb * bbz};
-        const double df = -K * dfab * 0.500;
         double ffa[3], ffb[3], ffc[3], ffd[3];
         for (int q = 0; q < 3; q++)
             {
@@ -428,7 +460,6 @@ __global__ void __launch_bounds__(BOND_BLOCK)
             ffd[q] = df * dth[q];
             ffc[q] = -s2 - ffd[q];
             }
-        const double eng = p * K * 0.125;
         const double vir[6] = {(1. / 4.) * (dab[0] * ffa[0] + dcb[0] * ffc[0] + (ddc[0] + dcb[0]) * ffd[0]),
                                (1. / 4.) * (dab[1] * ffa[0] + dcb[1] * ffc[0] + (ddc[1] + dcb[1]) * ffd[0]),
                                (1. / 4.) * (dab[2] * ffa[0] + dcb[2] * ffc[0] + (ddc[2] + dcb[2]) * ffd[0]),
@@ -469,20 +500,32 @@ __global__ void __launch_bounds__(BOND_BLOCK)
         }
     }
 
-hb2_status launch_dihedral_forces(const BondArgs& a, const uint4* members, const uint32_t* type_role,
-                                  bool accumulate, const hb2_box& box, cudaStream_t stream)
+hb2_status launch_dihedral_forces(hb2_bond_kind kind, const BondArgs& a, const uint4* members,
+                                  const uint32_t* type_role, bool accumulate, const hb2_box& box,
+                                  cudaStream_t stream)
     {
     if (a.N == 0)
         return HB2_OK;
     const uint32_t blocks = (a.N + BOND_BLOCK - 1) / BOND_BLOCK;
-    if (accumulate)
-        dihedral_force_kernel<true><<<blocks, BOND_BLOCK, 0, stream>>>(
-            a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, members, type_role, a.params, boxd(box), a.force,
-            a.virial, a.virial_pitch, a.skip_flag, a.err);
+#define HB2_DIHEDRAL_LAUNCH(K, ACC)                                                                       \
+    dihedral_force_kernel<K, ACC><<<blocks, BOND_BLOCK, 0, stream>>>(                                     \
+        a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, members, type_role, a.params, boxd(box), a.force,      \
+        a.virial, a.virial_pitch, a.skip_flag, a.err)
+    if (kind == HB2_DIHEDRAL_OPLS)
+        {
+        if (accumulate)
+            HB2_DIHEDRAL_LAUNCH(1, true);
+        else
+            HB2_DIHEDRAL_LAUNCH(1, false);
+        }
     else
-        dihedral_force_kernel<false><<<blocks, BOND_BLOCK, 0, stream>>>(
-            a.pos, a.tag, a.rtag, a.N, a.Ntot, a.head, members, type_role, a.params, boxd(box), a.force,
-            a.virial, a.virial_pitch, a.skip_flag, a.err);
+        {
+        if (accumulate)
+            HB2_DIHEDRAL_LAUNCH(0, true);
+        else
+            HB2_DIHEDRAL_LAUNCH(0, false);
+        }
+#undef HB2_DIHEDRAL_LAUNCH
     HB2_CHECK_LAUNCH("dihedral_force_kernel");
     return HB2_OK;
     }

@@ -1989,7 +1989,7 @@ extern "C" hb2_status hb2_nlist_set_exclusions(hb2_nlist* nl, int exclude_bonds)
 
 extern "C" hb2_status hb2_bond_create(hb2_bond** out, hb2_system* s, hb2_bond_kind kind)
     {
-    if (!out || !s || (unsigned)kind > (unsigned)HB2_DIHEDRAL_PERIODIC)
+    if (!out || !s || (unsigned)kind > (unsigned)HB2_DIHEDRAL_OPLS)
         return HB2_ERR_INVALID;
     hb2_bond* b = new hb2_bond();
     b->sys = s;
@@ -2021,7 +2021,7 @@ extern "C" void hb2_bond_destroy(hb2_bond* b)
 
 extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const double* user, uint32_t n_user)
     {
-    const uint32_t need = !b ? 2u : (b->kind == HB2_BOND_FENEWCA ? 5u : (b->kind == HB2_DIHEDRAL_PERIODIC ? 4u : 2u));
+    const uint32_t need = !b ? 2u : (b->kind == HB2_BOND_FENEWCA ? 5u : ((b->kind == HB2_DIHEDRAL_PERIODIC || b->kind == HB2_DIHEDRAL_OPLS) ? 4u : 2u));
     if (!b || !user || n_user < need)
         {
         set_error("hb2_bond_set_params: harmonic takes {k, r0}, FENEWCA {k, r0, epsilon, sigma, delta}");
@@ -2050,6 +2050,9 @@ extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const doub
         p[2] = (float)user[2]; // {k, d (sign), n (multiplicity), phi0}
         p[3] = (float)user[3];
         }
+    if (b->kind == HB2_DIHEDRAL_OPLS)
+        for (int q = 0; q < 4; q++) // OPLSDihedralForceCompute::setParams stores k_i / 2
+            p[q] = (float)(user[q] / 2.0);
     b->have[type] = 1;
     b->params_dirty = true;
     return HB2_OK;
@@ -2058,7 +2061,7 @@ extern "C" hb2_status hb2_bond_set_params(hb2_bond* b, uint32_t type, const doub
 hb2_status hb2_bond::upload_params()
     {
     const bool is_angle = kind == HB2_ANGLE_HARMONIC || kind == HB2_ANGLE_COSINESQ;
-    const uint32_t nt = kind == HB2_DIHEDRAL_PERIODIC ? sys->n_dihedral_types
+    const uint32_t nt = (kind == HB2_DIHEDRAL_PERIODIC || kind == HB2_DIHEDRAL_OPLS) ? sys->n_dihedral_types
                                                        : (is_angle ? sys->n_angle_types : sys->n_bond_types);
     for (uint32_t t = 0; t < nt; t++)
         if (t >= have.size() || !have[t])
@@ -2085,7 +2088,7 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     if (params_dirty)
         HB2_TRY(upload_params());
     const bool is_angle = kind == HB2_ANGLE_HARMONIC || kind == HB2_ANGLE_COSINESQ;
-    const bool is_dihedral = kind == HB2_DIHEDRAL_PERIODIC;
+    const bool is_dihedral = kind == HB2_DIHEDRAL_PERIODIC || kind == HB2_DIHEDRAL_OPLS;
     if ((is_dihedral ? s->n_dihedrals : (is_angle ? s->n_angles : s->n_bonds)) == 0 && accumulate)
         return HB2_OK;
     if (is_dihedral && !s->d_dihedral_head)
@@ -2110,7 +2113,8 @@ hb2_status hb2_bond::launch(float4* force, float* virial, size_t virial_pitch, b
     a.skip_flag = skip_flag;
     a.err = d_err;
     if (is_dihedral)
-        return launch_dihedral_forces(a, s->d_dihedral_members, s->d_dihedral_tr, accumulate, s->box, s->stream);
+        return launch_dihedral_forces(kind, a, s->d_dihedral_members, s->d_dihedral_tr, accumulate, s->box,
+                                      s->stream);
     if (is_angle)
         return launch_angle_forces(kind, a, s->d_angle_members, accumulate, s->box, s->stream);
     return launch_bond_forces(kind, a, accumulate, s->box, s->stream);

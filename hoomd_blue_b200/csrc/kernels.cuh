@@ -77,8 +77,9 @@ hb2_status launch_bond_forces(hb2_bond_kind kind, const BondArgs& a, bool accumu
 hb2_status launch_angle_forces(hb2_bond_kind kind, const BondArgs& a, const uint4* members, bool accumulate,
                                const hb2_box& box, cudaStream_t stream);
 // dihedrals: members = the four tags, type_role = type | role << 30 per table entry
-hb2_status launch_dihedral_forces(const BondArgs& a, const uint4* members, const uint32_t* type_role,
-                                  bool accumulate, const hb2_box& box, cudaStream_t stream);
+hb2_status launch_dihedral_forces(hb2_bond_kind kind, const BondArgs& a, const uint4* members,
+                                  const uint32_t* type_role, bool accumulate, const hb2_box& box,
+                                  cudaStream_t stream);
 hb2_status launch_nlist_filter_bonds(uint32_t N, const uint32_t* tag, const uint32_t* rtag,
                                      const uint32_t* head, const uint32_t* partner, uint32_t* nlist,
                                      uint32_t pitch, uint32_t* n_neigh, uint32_t dummy_index,

@@ -181,7 +181,8 @@ typedef enum hb2_bond_kind
     HB2_BOND_FENEWCA = 1,  /* hoomd/md/EvaluatorBondFENE.h */
     HB2_ANGLE_HARMONIC = 2, /* hoomd/md/HarmonicAngleForceCompute.cc; {k, t0} per ANGLE type */
     HB2_ANGLE_COSINESQ = 3, /* hoomd/md/CosineSqAngleForceCompute.cc; {k, t0} per ANGLE type */
-    HB2_DIHEDRAL_PERIODIC = 4 /* hoomd/md/HarmonicDihedralForceCompute.cc; {k, d, n, phi0} per DIHEDRAL type */
+    HB2_DIHEDRAL_PERIODIC = 4, /* hoomd/md/HarmonicDihedralForceCompute.cc; {k, d, n, phi0} per DIHEDRAL type */
+    HB2_DIHEDRAL_OPLS = 5      /* hoomd/md/OPLSDihedralForceCompute.cc; {k1, k2, k3, k4} per DIHEDRAL type */
     } hb2_bond_kind;
 typedef struct hb2_bond hb2_bond;             /* ~ PotentialBond<EvaluatorBondHarmonic> */
 typedef struct hb2_integrator hb2_integrator; /* ~ IntegratorTwoStep + TwoStepConstantVolume */

@@ -805,10 +805,12 @@ int orc_angle(int kind, const orc_box* b, const double* pos, uint32_t N, const u
     return 0;
     }
 
-int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
-                          const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals,
-                          const double* params, double* force, double* virial)
+int orc_dihedral(int kind, const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                 const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals, const double* params,
+                 double* force, double* virial)
     {
+    /* kind 1: hoomd.md.dihedral.OPLS (hoomd/md/OPLSDihedralForceCompute.cc:100-352), params =
+       (k1, k2, k3, k4) per type (halved on entry like setParams :57-72). kind 0: */
     /* hoomd/md/HarmonicDihedralForceCompute.cc:104-356 (hoomd.md.dihedral.Periodic):
        E = k/2 (1 + d cos(n phi - phi0)); params = (k, d, n, phi0) per dihedral type; a quarter of the
        energy and of the virial to each member. */
@@ -834,8 +836,8 @@ int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const
         orc_min_image(b, dcb);
         orc_min_image(b, ddc);
         const double* prm = params + 4 * (size_t)type[i];
-        const double K = prm[0], sign = prm[1], phi_0 = prm[3];
-        const int multi = (int)prm[2];
+        const double half = kind == 1 ? 0.5 : 1.0;
+        const double prm_d[4] = {prm[0] * half, prm[1] * half, prm[2] * half, prm[3] * half};
 #define MINIMAGE(v) orc_min_image(b, v)
 
         double dcbm[3] = {-dcb[0], -dcb[1], -dcb[2]};
@@ -864,24 +866,57 @@ int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const
             c_abcd = 1.0;
         if (c_abcd < -1.0)
             c_abcd = -1.0;
-        double p = 1.0, dfab = 0.0, ddfab = 0.0;
-        for (int j = 0; j < multi; j++)
+        double df, eng;
+        if (kind == 1)
             {
-            ddfab = p * c_abcd - dfab * s_abcd;
-            dfab = p * s_abcd + dfab * c_abcd;
-            p = ddfab;
+            // hoomd/md/OPLSDihedralForceCompute.cc:236-279: p = sum_i k_i/2 (1 + (-1)^(i+1) cos(i phi)),
+            // df = dp/dphi through the Chebyshev-like recursion; the halved k_i are the parameters
+            const double k1 = prm_d[0], k2 = prm_d[1], k3 = prm_d[2], k4 = prm_d[3];
+            double ddf1 = c_abcd, df1 = s_abcd, cos_term = ddf1;
+            double p = k1 * (1.0 + cos_term);
+            df = k1 * df1;
+            ddf1 = cos_term * c_abcd - df1 * s_abcd;
+            df1 = cos_term * s_abcd + df1 * c_abcd;
+            cos_term = ddf1;
+            p += k2 * (1.0 - cos_term);
+            df += -2.0 * k2 * df1;
+            ddf1 = cos_term * c_abcd - df1 * s_abcd;
+            df1 = cos_term * s_abcd + df1 * c_abcd;
+            cos_term = ddf1;
+            p += k3 * (1.0 + cos_term);
+            df += 3.0 * k3 * df1;
+            ddf1 = cos_term * c_abcd - df1 * s_abcd;
+            df1 = cos_term * s_abcd + df1 * c_abcd;
+            cos_term = ddf1;
+            p += k4 * (1.0 - cos_term);
+            df += -4.0 * k4 * df1;
+            eng = 0.25 * p;
             }
-        const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
-        p = p * cos_phi_0 + dfab * sin_phi_0;
-        p = p * sign;
-        dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
-        dfab = dfab * sign;
-        dfab *= (double)-multi;
-        p += 1.0;
-        if (multi == 0)
+        else
             {
-            p = 1.0 + sign;
-            dfab = 0.0;
+            const double K = prm_d[0], sign = prm_d[1], phi_0 = prm_d[3];
+            const int multi = (int)prm_d[2];
+            double p = 1.0, dfab = 0.0, ddfab = 0.0;
+            for (int j = 0; j < multi; j++)
+                {
+                ddfab = p * c_abcd - dfab * s_abcd;
+                dfab = p * s_abcd + dfab * c_abcd;
+                p = ddfab;
+                }
+            const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
+            p = p * cos_phi_0 + dfab * sin_phi_0;
+            p = p * sign;
+            dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
+            dfab = dfab * sign;
+            dfab *= (double)-multi;
+            p += 1.0;
+            if (multi == 0)
+                {
+                p = 1.0 + sign;
+                dfab = 0.0;
+                }
+            df = -K * dfab * 0.500;
+            eng = p * K * 0.125;
             }
         const double fg = dab[0] * dcbm[0] + dab[1] * dcbm[1] + dab[2] * dcbm[2];
         const double hg = ddc[0] * dcbm[0] + ddc[1] * dcbm[1] + ddc[2] * dcbm[2];
@@ -890,7 +925,6 @@ int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const
         const double dtf[3] = {gaa * aax, gaa * aay, gaa * aaz};
         const double dtg[3] = {fga * aax - hgb * bbx, fga * aay - hgb * bby, fga * aaz - hgb * bbz};
         const double dth[3] = {gbb * bbx, gbb * bby, gbb * bbz};
-        const double df = -K * dfab * 0.500;
         double ffa[3], ffb[3], ffc[3], ffd[3];
         for (int q = 0; q < 3; q++)
             {
@@ -900,7 +934,6 @@ int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const
             ffd[q] = df * dth[q];
             ffc[q] = -s2 - ffd[q];
             }
-        const double eng = p * K * 0.125;
         const double vir[6] = {(1. / 4.) * (dab[0] * ffa[0] + dcb[0] * ffc[0] + (ddc[0] + dcb[0]) * ffd[0]),
                                (1. / 4.) * (dab[1] * ffa[0] + dcb[1] * ffc[0] + (ddc[1] + dcb[1]) * ffd[0]),
                                (1. / 4.) * (dab[2] * ffa[0] + dcb[2] * ffc[0] + (ddc[2] + dcb[2]) * ffd[0]),
@@ -919,6 +952,13 @@ int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const
             }
         }
     return 0;
+    }
+
+int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                          const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals,
+                          const double* params, double* force, double* virial)
+    {
+    return orc_dihedral(0, b, pos, N, rtag, group, type, n_dihedrals, params, force, virial);
     }
 
 /* ---------------------------------------------------------------------- RNG ---- */

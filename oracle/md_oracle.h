@@ -130,6 +130,12 @@ int orc_dihedral_periodic(const orc_box* b, const double* pos, uint32_t N, const
                           const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals,
                           const double* params, double* force, double* virial);
 
+/* kind 0: Periodic as above; kind 1: hoomd.md.dihedral.OPLS (hoomd/md/OPLSDihedralForceCompute.cc),
+ * params = (k1, k2, k3, k4) per dihedral type */
+int orc_dihedral(int kind, const orc_box* b, const double* pos, uint32_t N, const uint32_t* rtag,
+                 const uint32_t* group, const uint32_t* type, uint32_t n_dihedrals, const double* params,
+                 double* force, double* virial);
+
 /* RNG: Philox4x32-10 (Salmon et al., SC'11; hoomd/extern/random123 commit a2c4f04) and HOOMD's
  * Seed/Counter packing hoomd/RandomNumbers.h:136-199 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

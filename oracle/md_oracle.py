@@ -333,7 +333,12 @@ def angle(kind, box, pos, angle_group, angle_type, params, tags=None):
     return force, virial
 
 
-def dihedral_periodic(box, pos, group, types, params, tags=None):
+def dihedral_opls(box, pos, group, types, params, tags=None):
+    """hoomd.md.dihedral.OPLS; params (k1, k2, k3, k4) per type."""
+    return dihedral_periodic(box, pos, group, types, params, tags, _kind=1)
+
+
+def dihedral_periodic(box, pos, group, types, params, tags=None, _kind=0):
     """hoomd.md.dihedral.Periodic; params (k, d, n, phi0) per type; returns (force N x 4, virial 6 x N)."""
     pos = _f64(pos)
     n = pos.shape[0]
@@ -345,9 +350,10 @@ def dihedral_periodic(box, pos, group, types, params, tags=None):
     params = _f64(np.asarray(params).reshape(-1, 4))
     force = np.zeros((n, 4))
     virial = np.zeros((6, n))
-    rc = lib().orc_dihedral_periodic(C.byref(box), _p(pos, C.c_double), C.c_uint32(n), _p(rtag, C.c_uint32),
-                                     _p(dg, C.c_uint32), _p(dt, C.c_uint32), C.c_uint32(dg.shape[0]),
-                                     _p(params, C.c_double), _p(force, C.c_double), _p(virial, C.c_double))
+    rc = lib().orc_dihedral(C.c_int(_kind), C.byref(box), _p(pos, C.c_double), C.c_uint32(n),
+                            _p(rtag, C.c_uint32), _p(dg, C.c_uint32), _p(dt, C.c_uint32),
+                            C.c_uint32(dg.shape[0]), _p(params, C.c_double), _p(force, C.c_double),
+                            _p(virial, C.c_double))
     if rc:
         raise RuntimeError(f"Error: dihedral {rc - 1} is incomplete.")
     return force, virial

@@ -64,6 +64,11 @@ DIHEDRAL_VECTORS = [(3.0, -1, 2, np.pi / 2, 0, 3), (10.0, 1, 1, np.pi / 4, 5.0, 
                     (5.0, 1, 3, np.pi / 6, 1.9411, 0.0852)]
 
 
+# (k1, k2, k3, k4, force, energy) hoomd/md/pytest/test_dihedral.py:36-56
+OPLS_VECTORS = [(1.0, 1.5, 0.5, 0.75, -0.616117, 2.42678), (0.5, 2.5, 1.5, 1.0, -0.732233, 2.89645),
+                (2.0, 1.0, 0.25, 3.5, -0.0277282, 5.74372)]
+
+
 def quadruplet(d=1.0, phi_deg=45):
     # hoomd/md/pytest/test_dihedral.py:69-104 dihedral_snapshot_factory
     ph = phi_deg * np.pi / 180
@@ -99,6 +104,30 @@ def test_oracle_dihedral_reference_vectors(oracle, k, d, n, phi0, force, energy)
             ep = oracle.dihedral_periodic(box, pp, [[0, 1, 2, 3]], [0], [[k, d, n, phi0]])[0][:, 3].sum()
             em = oracle.dihedral_periodic(box, pm, [[0, 1, 2, 3]], [0], [[k, d, n, phi0]])[0][:, 3].sum()
             assert -(ep - em) / (2 * h) == pytest.approx(f[i, c], rel=1e-4, abs=1e-6)
+
+
+@pytest.mark.parametrize("k1,k2,k3,k4,force,energy", OPLS_VECTORS)
+def test_oracle_opls_reference_vectors(oracle, k1, k2, k3, k4, force, energy):
+    box = oracle.make_box([20.0, 20.0, 20.0])
+    prm = [[k1, k2, k3, k4]]
+    f, v = oracle.dihedral_opls(box, quadruplet(), [[0, 1, 2, 3]], [0], prm)
+    check_dihedral_vectors(f[:, :3], f[:, 3].sum(), force, energy)
+    assert np.abs(f[:, :3].sum(axis=0)).max() < 1e-12
+    pos = quadruplet().astype(np.float64)
+    h = 1e-6
+    for i in range(4):
+        for c in range(3):
+            pp, pm = pos.copy(), pos.copy()
+            pp[i, c] += h
+            pm[i, c] -= h
+            ep = oracle.dihedral_opls(box, pp, [[0, 1, 2, 3]], [0], prm)[0][:, 3].sum()
+            em = oracle.dihedral_opls(box, pm, [[0, 1, 2, 3]], [0], prm)[0][:, 3].sum()
+            assert -(ep - em) / (2 * h) == pytest.approx(f[i, c], rel=1e-4, abs=1e-6)
+    # the closed form: V = 1/2 [k1 (1 + cos) + k2 (1 - cos 2) + k3 (1 + cos 3) + k4 (1 - cos 4)] at 45 deg
+    ph = np.pi / 4
+    want = 0.5 * (k1 * (1 + np.cos(ph)) + k2 * (1 - np.cos(2 * ph)) + k3 * (1 + np.cos(3 * ph))
+                  + k4 * (1 - np.cos(4 * ph)))
+    assert f[:, 3].sum() == pytest.approx(want, rel=1e-6)
 
 
 def two_particles(d=0.969):
@@ -364,6 +393,27 @@ def test_dihedral_reference_vectors(oracle, k, d, n, phi0, force, energy):
     assert potential.energy == pytest.approx(f_ref[:, 3].sum(), rel=2e-5, abs=1e-6)
     np.testing.assert_allclose(potential.virials, v_ref.T, rtol=2e-5, atol=2e-6)
     assert tuple(sim.state.get_snapshot().dihedrals.group[0]) == (0, 1, 2, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k1,k2,k3,k4,force,energy", OPLS_VECTORS)
+def test_opls_reference_vectors(oracle, k1, k2, k3, k4, force, energy):
+    import hoomd_blue_b200 as hoomd
+    snap = hoomd.Snapshot.from_arrays([20, 20, 20, 0, 0, 0], quadruplet())
+    snap.dihedrals.N = 1
+    snap.dihedrals.types = ["A-A-A-A"]
+    snap.dihedrals.group[0] = (0, 1, 2, 3)
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=1)
+    sim.create_state_from_snapshot(snap)
+    potential = hoomd.md.dihedral.OPLS()
+    potential.params["A-A-A-A"] = dict(k1=k1, k2=k2, k3=k3, k4=k4)
+    sim.operations.integrator = hoomd.md.Integrator(dt=0.005, forces=[potential])
+    sim.run(0)
+    check_dihedral_vectors(potential.forces, sum(potential.energies), force, energy)
+    box = oracle.make_box([20.0, 20.0, 20.0])
+    f_ref, _ = oracle.dihedral_opls(box, quadruplet(), [[0, 1, 2, 3]], [0], [[k1, k2, k3, k4]])
+    np.testing.assert_allclose(potential.forces, f_ref[:, :3], rtol=2e-5, atol=2e-6)
+    assert potential.energy == pytest.approx(f_ref[:, 3].sum(), rel=2e-5)
 
 
 @pytest.mark.gpu
