@@ -1474,9 +1474,14 @@ static hb2_status pair_ensure(hb2_pair* p, bool need_energy = true)
     {
     // recompute when the particle order changed or nothing was computed yet
     // (hoomd/ForceCompute.cc:562-574: "sorted / new timestep / flags changed")
-    if (!p->computed || p->extra_added || p->computed_epoch != p->sys->order_epoch
-        || (p->sys->compute_virial && !p->virial_valid) || (need_energy && !p->energy_valid))
+    if (!p->computed || p->computed_epoch != p->sys->order_epoch)
         return p->compute(p->sys->timestep);
+    // Same particles, same positions, same list: only the array's content is not what the getter wants
+    // (bond forces were added into it, or the energy / virial variant did not run). Launch the force
+    // pass again over the current list — going through the neighbour list's update logic would
+    // rebuild (and re-order the particles) where an uninterrupted run would not.
+    if (p->extra_added || (p->sys->compute_virial && !p->virial_valid) || (need_energy && !p->energy_valid))
+        return p->launch(p->computed_step, true, nullptr);
     return HB2_OK;
     }
 
@@ -2340,12 +2345,18 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     HB2_CUDA(cudaEventRecord(it->ev0, st));
     // prepRun (hoomd/md/IntegratorTwoStep.cc:226-281): net force at the current timestep
     if (!it->prepared || !pf->computed || pf->computed_epoch != s->order_epoch
-        || pf->computed_step != s->timestep || (!it->bonds.empty() && !pf->extra_added))
+        || pf->computed_step != s->timestep)
         {
         HB2_TRY(pf->compute(s->timestep));
         HB2_TRY(integrator_add_bonds(it, pf, nullptr));
         it->prepared = true;
-        it->total_valid = false; // accelerations restart from the net force (computeAccelerations)
+        }
+    else if (!it->bonds.empty() && !pf->extra_added)
+        {
+        // a getter left the pure pair force in the array: same state, same list — put the net force
+        // back without touching the neighbour list (an uninterrupted run would not rebuild here)
+        HB2_TRY(pf->launch(s->timestep, true, nullptr));
+        HB2_TRY(integrator_add_bonds(it, pf, nullptr));
         }
     if (it->thermostat == 1)
         {
@@ -2381,7 +2392,12 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             }
         const bool check = nl->has_list && nl->check_dist;
         // (Langevin: the previous step two left F + F_bd for this half step)
-        const float4* f_one = (it->thermostat == 2 && it->total_valid) ? it->d_total : pf->d_force;
+        // (valid for this particle order and this timestep only: a snapshot set in between, or a
+        // rebuild triggered by a getter, falls back to the net force like computeAccelerations)
+        const float4* f_one = (it->thermostat == 2 && it->total_valid && it->total_epoch == s->order_epoch
+                               && it->total_step == t)
+                                  ? it->d_total
+                                  : pf->d_force;
         HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], f_one, s->image[s->cur], s->N,
                                 s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
                                 nl->maxshift(), nl->d_conditions + 3, st));
@@ -2471,6 +2487,8 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                                              s->tag[s->cur], s->N, (float)it->dt, it->d_gamma_coeff,
                                              s->seed, t, st));
             it->total_valid = true;
+            it->total_epoch = s->order_epoch;
+            it->total_step = t + 1;
             }
         else
             HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,

@@ -232,6 +232,7 @@ struct hb2_integrator
     float4* d_total = nullptr;      // Langevin: F + F_bd of the last step two (next step one's force)
     size_t total_cap = 0;
     bool total_valid = false;
+    uint64_t total_epoch = 0, total_step = 0; // particle order and timestep d_total belongs to
     bool prepared = false;
     uint64_t prepared_epoch = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -165,3 +165,56 @@ def test_periodic_gsd_writer_in_run(tmp_path):
     sim2 = hoomd.Simulation(device=hoomd.device.GPU(), seed=4)
     sim2.create_state_from_gsd(path)
     assert sim2.timestep == 200 and sim2.state.N_particles == 12 ** 3
+
+
+@pytest.mark.gpu
+def test_molecular_run_with_writers_equals_plain_run(tmp_path):
+    """The composition INTEGRATION.md shows (pair + FENE bonds + angles, bond / 1-3 exclusions, the
+    Langevin method, a trajectory writer with logged thermodynamics): interrupting the run for the writer
+    and its logger must not change the trajectory (the BD force carried into the next step one survives
+    the getters' recomputation of the pair force)."""
+    import hoomd_blue_b200 as hoomd
+    from tests.test_bonds import lattice_chains
+
+    def make():
+        pos, group, L = lattice_chains(16, 8, 8, 8, 1.0, seed=9, jitter=0.05)
+        n = len(pos)
+        bonded = set(map(tuple, group.tolist()))
+        angles = np.array([(i - 1, i, i + 1) for i in range(1, n - 1)
+                           if (i - 1, i) in bonded and (i, i + 1) in bonded], dtype=np.uint32)
+        snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, np.zeros_like(pos))
+        snap.bonds.N, snap.bonds.types = len(group), ["polymer"]
+        snap.bonds.group[:] = group
+        snap.angles.N, snap.angles.types = len(angles), ["backbone"]
+        snap.angles.group[:] = angles
+        sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=12)
+        sim.create_state_from_snapshot(snap)
+        cell = hoomd.md.nlist.Cell(buffer=0.3, exclusions=("bond", "1-3"))
+        lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.0 ** (1.0 / 6.0), mode="shift")
+        lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+        fene = hoomd.md.bond.FENEWCA()
+        fene.params["polymer"] = dict(k=30.0, r0=1.5, epsilon=1.0, sigma=1.0, delta=0.0)
+        bend = hoomd.md.angle.Harmonic()
+        bend.params["backbone"] = dict(k=5.0, t0=2.6)
+        lv = hoomd.md.methods.Langevin(filter=hoomd.filter.All(), kT=1.0)
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.002, methods=[lv], forces=[lj, fene, bend])
+        return sim
+
+    plain = make()
+    plain.run(300)
+    sim = make()
+    thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+    sim.operations += thermo
+    lg = hoomd.logging.Logger(categories=["scalar"])
+    lg.add(thermo, quantities=["kinetic_temperature", "potential_energy"])
+    path = str(tmp_path / "mol.gsd")
+    sim.operations.writers.append(hoomd.write.GSD(trigger=hoomd.trigger.Periodic(70), filename=path, mode="wb",
+                                                  dynamic=["property", "momentum"], logger=lg))
+    sim.run(300)
+    a, b = sim.state.get_snapshot(), plain.state.get_snapshot()
+    assert np.array_equal(a.particles.position, b.particles.position)
+    assert np.array_equal(a.particles.velocity, b.particles.velocity)
+    g = hoomd.gsd_io.GSDFile(path)
+    assert g.nframes == 4 and int(g.chunk(0, "bonds/N")[0, 0]) == a.bonds.N
+    temps = [g.chunk(k, "log/md/compute/ThermodynamicQuantities/kinetic_temperature")[0, 0] for k in range(4)]
+    assert 0.2 < temps[-1] < 2.0
