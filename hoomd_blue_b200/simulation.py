@@ -110,6 +110,68 @@ class Snapshot:
         self.dihedrals = _Dihedrals()
         self.communicator = communicator
 
+    def replicate(self, nx, ny, nz=1):
+        """hoomd.Snapshot.replicate (hoomd/snapshot.py:424-444, SnapshotParticleData::replicate
+        hoomd/ParticleData.cc:3742-3810): the box grows by (nx, ny, nz); replica j = (l * ny + m) * nz + n
+        holds particle i at index j * N + i, its unwrapped fractional coordinate divided by the
+        replication count and shifted by (l/nx, m/ny, n/nz); bonds / angles / dihedrals follow with
+        shifted tags. Orthorhombic boxes."""
+        nx, ny, nz = int(nx), int(ny), int(nz)
+        if min(nx, ny, nz) < 1:
+            raise ValueError("replication counts must be positive")
+        box = np.asarray(self.configuration.box, dtype=np.float64)
+        if np.any(box[3:] != 0):
+            raise NotImplementedError("replicate: tilt factors must be zero on this path")
+        p = self.particles
+        n_old = int(p.N)
+        reps = np.array([nx, ny, nz], dtype=np.float64)
+        L, Ln = box[:3], box[:3] * reps
+        old = {k: getattr(p, k).copy() for k in ("position", "velocity", "image", "typeid", "mass")}
+        types = list(p.types)
+        unwrapped = old["position"].astype(np.float64) + old["image"] * L
+        f = (unwrapped + L / 2) / L
+        p.N = n_old * nx * ny * nz
+        p.types = types
+        j = 0
+        for l in range(nx):
+            for m in range(ny):
+                for n in range(nz):
+                    f_new = f / reps + np.array([l, m, n]) / reps
+                    q = -Ln / 2 + f_new * Ln
+                    img = np.floor((q + Ln / 2) / Ln)
+                    q = q - img * Ln
+                    q32 = q.astype(np.float32)
+                    hi = (Ln / 2).astype(np.float32)
+                    over, under = q32 >= hi, q32 < -hi
+                    q32 = np.where(over, q32 - Ln.astype(np.float32), q32)
+                    q32 = np.where(under, q32 + Ln.astype(np.float32), q32)
+                    img = img + over.astype(np.float64) - under.astype(np.float64)
+                    sl = slice(j * n_old, (j + 1) * n_old)
+                    p.position[sl] = q32
+                    p.image[sl] = img.astype(np.int32)
+                    p.velocity[sl] = old["velocity"]
+                    p.typeid[sl] = old["typeid"]
+                    p.mass[sl] = old["mass"]
+                    j += 1
+        self.configuration.box = [float(Ln[0]), float(Ln[1]), float(Ln[2]), 0.0, 0.0, 0.0]
+        for grp in (self.bonds, self.angles, self.dihedrals):
+            _replicate_groups(grp, nx * ny * nz, n_old)
+        return self
+
+    def wrap(self):
+        """hoomd.Snapshot.wrap (hoomd/snapshot.py:446-461): particles back into the box, images updated."""
+        L = np.asarray(self.configuration.box[:3], dtype=np.float64)
+        p = self.particles
+        q = p.position.astype(np.float64)
+        img = np.floor((q + L / 2) / L)
+        q32 = (q - img * L).astype(np.float32)
+        hi = (L / 2).astype(np.float32)
+        over = q32 >= hi
+        q32 = np.where(over, q32 - L.astype(np.float32), q32)
+        p.position[:] = q32
+        p.image[:] = p.image + (img + over).astype(np.int32)
+        return self
+
     @classmethod
     def from_arrays(cls, box, position, velocity=None, typeid=None, types=("A",), image=None,
                     mass=None):
@@ -129,6 +191,20 @@ class Snapshot:
         if mass is not None:
             s.particles.mass[:] = mass
         return s
+
+
+def _replicate_groups(grp, n_rep, old_n_particles):
+    """BondedGroupData::Snapshot::replicate (hoomd/BondedGroupData.cc:1366-1405): replica j holds the
+    groups with every member tag shifted by j * old_n_particles, at indices j * old_size + i."""
+    if grp.N == 0:
+        return
+    tid, g = grp.typeid.copy(), grp.group.astype(np.int64)
+    types = list(grp.types)
+    grp.N = len(tid) * n_rep
+    grp.types = types
+    for j in range(n_rep):
+        grp.typeid[j * len(tid):(j + 1) * len(tid)] = tid
+        grp.group[j * len(tid):(j + 1) * len(tid)] = g + j * old_n_particles
 
 
 class _BoxView:

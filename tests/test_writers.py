@@ -27,6 +27,44 @@ def test_triggers():
         T.as_trigger("x")
 
 
+def test_snapshot_replicate_and_wrap():
+    """hoomd.Snapshot.replicate / wrap (hoomd/ParticleData.cc:3742-3810, hoomd/BondedGroupData.cc:1366-1405)."""
+    from hoomd_blue_b200 import Snapshot
+    s = _snapshot(30, 5)
+    L = np.array(s.configuration.box[:3])
+    s.bonds.N, s.bonds.types = 3, ["b"]
+    s.bonds.group[:] = [(0, 1), (1, 2), (28, 29)]
+    s.angles.N, s.angles.types = 1, ["a"]
+    s.angles.group[:] = [(0, 1, 2)]
+    pos0 = s.particles.position.astype(np.float64) + s.particles.image * L
+    vel0, tid0 = s.particles.velocity.copy(), s.particles.typeid.copy()
+    s.replicate(2, 3, 1)
+    assert s.particles.N == 180 and s.configuration.box[:3] == list(L * [2, 3, 1])
+    Ln = L * [2, 3, 1]
+    un = s.particles.position.astype(np.float64) + s.particles.image * Ln
+    j = 0
+    for l in range(2):
+        for m in range(3):
+            blk = slice(30 * j, 30 * (j + 1))
+            # replica (l, m, 0): the unwrapped original, moved to the replica's cell of the new box
+            want = pos0 + L / 2 - Ln / 2 + L * [l, m, 0]
+            assert np.allclose(un[blk], want, atol=2e-5)
+            assert np.array_equal(s.particles.velocity[blk], vel0) and np.array_equal(s.particles.typeid[blk], tid0)
+            assert np.array_equal(s.bonds.group[3 * j:3 * j + 3], np.array([(0, 1), (1, 2), (28, 29)]) + 30 * j)
+            assert np.array_equal(s.angles.group[j], np.array([0, 1, 2]) + 30 * j)
+            j += 1
+    assert s.bonds.N == 18 and s.angles.N == 6 and s.bonds.types == ["b"]
+    assert np.all(s.particles.position < (Ln / 2).astype(np.float32))
+    assert np.all(s.particles.position >= -(Ln / 2).astype(np.float32))
+    # wrap
+    t = Snapshot.from_arrays([4, 4, 4, 0, 0, 0], np.array([[2.5, -2.0, 0.0], [-6.1, 1.9, 7.9]], dtype=np.float32))
+    t.wrap()
+    assert np.allclose(t.particles.position, [[-1.5, -2.0, 0.0], [1.9, 1.9, -0.1]], atol=1e-6)
+    assert np.array_equal(t.particles.image, [[1, 0, 0], [-2, 0, 2]])
+    with pytest.raises(ValueError):
+        t.replicate(0, 1, 1)
+
+
 def test_gsd_append_writer(tmp_path):
     """300 appended frames (the 128-entry index and the name list both have to move), dynamic
     categories, log chunks; frame 0 fallback on read."""
