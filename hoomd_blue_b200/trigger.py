@@ -63,6 +63,58 @@ class After(Trigger):
         return max(timestep, self.timestep) + 1
 
 
+class Or(Trigger):
+    """fires when any of the triggers fires (hoomd.trigger.Or)"""
+
+    def __init__(self, triggers):
+        self.triggers = [as_trigger(t) for t in triggers]
+
+    def compute(self, timestep):
+        return any(t(timestep) for t in self.triggers)
+
+    def next_after(self, timestep):
+        nxt = [n for n in (t.next_after(timestep) for t in self.triggers) if n is not None]
+        return min(nxt) if nxt else None
+
+
+class And(Trigger):
+    """fires when all of the triggers fire (hoomd.trigger.And)"""
+
+    def __init__(self, triggers):
+        self.triggers = [as_trigger(t) for t in triggers]
+
+    def compute(self, timestep):
+        return all(t(timestep) for t in self.triggers)
+
+    def next_after(self, timestep):
+        step = timestep
+        for _ in range(1000000):  # leap to the latest of the children's next steps until they agree
+            nxt = [t.next_after(step) for t in self.triggers]
+            if any(n is None for n in nxt):
+                return None
+            cand = max(nxt)
+            if all(t(cand) for t in self.triggers):
+                return cand
+            step = cand - 1 if cand - 1 > step else cand
+        return None
+
+
+class Not(Trigger):
+    """fires when the trigger does not (hoomd.trigger.Not)"""
+
+    def __init__(self, trigger):
+        self.trigger = as_trigger(trigger)
+
+    def compute(self, timestep):
+        return not self.trigger(timestep)
+
+    def next_after(self, timestep):
+        for step in range(timestep + 1, timestep + 1000001):
+            if not self.trigger(step):
+                return step
+        return None
+
+
 def as_trigger(t):
     if isinstance(t, Trigger):
         return t

@@ -40,7 +40,7 @@ class GSD(Writer):
     def _log_chunks(self):
         if self.logger is None:
             return None
-        return {"/".join(ns): v for ns, v in self.logger.log().items()}
+        return {"/".join(ns): v for ns, v in self.logger._flat().items()}
 
     def _write(self, sim):
         state = sim.state
@@ -89,7 +89,7 @@ class Table(Writer):
         self._header_written = False
 
     def _write(self, sim):
-        vals = self.logger.log()
+        vals = self.logger._flat()
         if sim.device.communicator.rank != 0:
             return
         if not self._header_written:

@@ -21,6 +21,15 @@ def test_triggers():
     assert T.On(5)(5) and not T.On(5)(6) and T.On(5).next_after(5) is None and T.On(5).next_after(1) == 5
     assert T.Before(3)(2) and not T.Before(3)(3) and T.After(3)(4) and not T.After(3)(3)
     assert T.After(10).next_after(2) == 11 and T.Before(10).next_after(9) is None
+    both = T.And([T.Periodic(6), T.Periodic(4)])
+    assert [t for t in range(0, 40) if both(t)] == [0, 12, 24, 36]
+    assert both.next_after(0) == 12 and both.next_after(12) == 24 and both.next_after(13) == 24
+    either = T.Or([T.Periodic(6), T.On(7)])
+    assert [t for t in range(0, 20) if either(t)] == [0, 6, 7, 12, 18] and either.next_after(6) == 7
+    late = T.And([T.Periodic(5), T.After(12)])
+    assert late.next_after(0) == 15 and not late(10)
+    assert T.Not(T.Periodic(2)).next_after(2) == 3 and T.Not(T.Periodic(2))(3)
+    assert T.And([T.On(3), T.On(4)]).next_after(0) is None
     with pytest.raises(ValueError):
         T.Periodic(0)
     with pytest.raises(TypeError):
@@ -139,6 +148,14 @@ def test_logger_and_table():
     tb._write(_Sim)
     th.kinetic_energy = 2.5
     tb._write(_Sim)
+    nested = lg.log()
+    assert nested["md"]["compute"]["_Thermo"]["pressure"] == (-3.0, "scalar")
+    assert nested["custom"]["answer"] == (42, "scalar")
+    lg2 = logging.Logger()
+    lg2.add(th)
+    assert lg2.log()["md"]["compute"]["_Thermo"]["tensor"] == ((1.0, 2.0), "sequence")
+    lg2.remove(th, quantities=["tensor"])
+    assert "tensor" not in lg2.log()["md"]["compute"]["_Thermo"]
     lines = out.getvalue().splitlines()
     assert lines[0] == "_Thermo.kinetic_energy _Thermo.pressure custom.answer"
     assert lines[1] == "1.25 -3 42" and lines[2] == "2.5 -3 42"
