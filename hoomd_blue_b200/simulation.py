@@ -441,6 +441,21 @@ class State:
                                          ptr(p.typeid, C.c_uint32), ptr(p.image, C.c_int32)))
         return s
 
+    def thermalize_particle_momenta(self, filter, kT):
+        """hoomd.State.thermalize_particle_momenta (hoomd/state.py:759-800): Gaussian velocities at kT
+        from every particle's own counter-based stream (keyed by tag, the simulation seed and the
+        current timestep), centre-of-mass momentum removed. filter must be All()."""
+        from .filter import All
+        from . import rng
+        if not isinstance(filter, All):
+            raise NotImplementedError("this path thermalizes filter.All() only")
+        snap = self.get_snapshot()
+        n = snap.particles.N
+        v = rng.thermal_velocities(np.arange(n, dtype=np.uint32), snap.particles.mass, float(kT),
+                                   self._simulation.seed, self._simulation.timestep)
+        snap.particles.velocity[:] = v.astype(np.float32)
+        self.set_snapshot(snap)
+
     @property
     def N_particles(self):
         """Global particle count (hoomd/state.py:N_particles)."""

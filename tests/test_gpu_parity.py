@@ -332,6 +332,25 @@ def test_langevin_trajectory_vs_oracle(hoomd, oracle, golden_dir):
     assert np.max(np.abs(s.particles.velocity - fx["nve_vel"])) > 0.05
 
 
+def test_thermalize_particle_momenta(hoomd):
+    """hoomd.State.thermalize_particle_momenta: velocities at kT with zero total momentum, a function of
+    (seed, timestep, tag) only."""
+    from hoomd_blue_b200 import rng
+    pos, vel, L = random_liquid(16, 0.8, seed=3)
+    mass = np.random.default_rng(4).uniform(0.5, 2.0, len(pos)).astype(np.float32)
+    snap = hoomd.Snapshot.from_arrays(list(L) + [0, 0, 0], pos, vel, mass=mass)
+    sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=7)
+    sim.create_state_from_snapshot(snap)
+    sim.state.thermalize_particle_momenta(filter=hoomd.filter.All(), kT=1.5)
+    s = sim.state.get_snapshot()
+    v = s.particles.velocity.astype(np.float64)
+    assert np.array_equal(s.particles.position, pos) and np.array_equal(s.particles.mass, mass)
+    assert np.abs((mass[:, None] * v).sum(axis=0)).max() < 1e-3
+    assert abs((mass[:, None] * v ** 2).mean() / 1.5 - 1.0) < 0.05
+    want = rng.thermal_velocities(np.arange(len(pos), dtype=np.uint32), mass, 1.5, 7, 0).astype(np.float32)
+    assert np.array_equal(s.particles.velocity, want)
+
+
 def test_langevin_temperature(hoomd):
     """Fluctuation-dissipation on the device: a dilute, nearly ideal gas started at rest reaches the
     set temperature (per-type drag coefficients)."""

@@ -335,3 +335,50 @@ def test_langevin_step_two(oracle):
         if t >= 500:
             kes.append(oracle.kinetic_energy(vel, mass))
     assert abs(np.mean(kes) / (1.5 * n * kT) - 1.0) < 0.02
+
+
+def test_host_rng_and_thermalize(oracle):
+    """hoomd_blue_b200/rng.py (numpy Philox, Seed/Counter, Box-Muller) against the oracle's Philox and a
+    scalar restatement of hoomd/RandomNumbers.h:63-87,361-374, and thermal_velocities
+    (hoomd/ParticleGroup.cc:690-806): tag-keyed, zero total momentum, <m v^2> = kT per component.
+    THE THERMALIZE STREAM IS NOT PINNED by reference output (RNG id 35 from hoomd/RNGIdentifiers.h:60)."""
+    import ctypes as C
+    from hoomd_blue_b200 import rng
+    g = np.random.default_rng(1)
+    ctr = g.integers(0, 2 ** 32, size=(64, 4), dtype=np.uint64).astype(np.uint32)
+    key = g.integers(0, 2 ** 32, size=2, dtype=np.uint64).astype(np.uint32)
+    got = rng.philox4x32_10(ctr, key)
+    out = np.zeros(4, dtype=np.uint32)
+    for i in range(len(ctr)):
+        c = np.ascontiguousarray(ctr[i])
+        oracle.lib().orc_philox4x32_10(c.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       key.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert np.array_equal(got[i], out)
+    kb = np.zeros(2, dtype=np.uint32)
+    oracle.lib().orc_seed_key(C.c_uint8(35), C.c_uint64((1 << 35) + 17), C.c_uint16(7),
+                              kb.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert np.array_equal(rng.seed_key(35, (1 << 35) + 17, 7), kb)
+    tags = np.array([0, 5, 123456, 2 ** 31 + 3], dtype=np.uint32)
+    nd = rng.normal_draws(35, 99, 7, tags, 3)
+    for a, tag in enumerate(tags):
+        for d in range(3):
+            c = np.array([d, 0, 0, tag], dtype=np.uint32)
+            k2 = rng.seed_key(35, 99, 7)
+            oracle.lib().orc_philox4x32_10(c.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           k2.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           out.ctypes.data_as(C.POINTER(C.c_uint32)))
+            u0 = (int(out[0]) << 32) | int(out[1])
+            u1 = (int(out[2]) << 32) | int(out[3])
+            s0 = u0 - (1 << 64) if u0 >= (1 << 63) else u0
+            x = np.sin(np.pi * (s0 * 2.0 ** -63 + 2.0 ** -64)) * np.sqrt(-2.0 * np.log(u1 * 2.0 ** -64 + 2.0 ** -65))
+            assert np.isclose(nd[a, d], x, rtol=1e-13, atol=1e-15)
+    n = 20000
+    mass = g.uniform(0.5, 3.0, n)
+    tg = g.permutation(n).astype(np.uint32)
+    v = rng.thermal_velocities(tg, mass, 1.5, 7, 0)
+    assert np.abs((mass[:, None] * v).sum(axis=0)).max() < 1e-9
+    assert abs((mass[:, None] * v ** 2).mean() / 1.5 - 1.0) < 0.02
+    perm = g.permutation(n)
+    assert np.allclose(rng.thermal_velocities(tg[perm], mass[perm], 1.5, 7, 0), v[perm], atol=1e-12)
+    assert not np.allclose(rng.thermal_velocities(tg, mass, 1.5, 7, 1), v)
