@@ -11,7 +11,8 @@ from . import _lib  # noqa: F401
 from . import device, filter, md  # noqa: F401
 from .simulation import Simulation, Snapshot, State, Operations  # noqa: F401
 from . import gsd_io  # noqa: F401
-from . import write, trigger, logging  # noqa: F401
+from . import write, trigger, logging, box  # noqa: F401
+from .box import Box  # noqa: F401
 
-__all__ = ["Simulation", "Snapshot", "device", "filter", "md", "gsd_io", "write", "trigger", "logging"]
+__all__ = ["Simulation", "Snapshot", "device", "filter", "md", "gsd_io", "write", "trigger", "logging", "Box"]
 version = "0.1.0+hoomd4.8.2-path"

@@ -18,9 +18,19 @@ from ._lib import check, ptr
 class _Configuration:
 
     def __init__(self):
-        self.box = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]  # Lx, Ly, Lz, xy, xz, yz
+        self._box = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]  # Lx, Ly, Lz, xy, xz, yz
         self.dimensions = 3
         self.step = 0
+
+    @property
+    def box(self):
+        return self._box
+
+    @box.setter
+    def box(self, value):
+        """a hoomd.Box, 3 lengths, or 3 lengths + 3 tilt factors; stored as a list of six floats"""
+        from .box import Box
+        self._box = [float(v) for v in Box.from_box(value)]
 
 
 class _Particles:

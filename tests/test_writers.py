@@ -36,6 +36,23 @@ def test_triggers():
         T.as_trigger("x")
 
 
+def test_box():
+    import hoomd_blue_b200 as hoomd
+    b = hoomd.Box.cube(5)
+    assert list(b) == [5, 5, 5, 0, 0, 0] and b.volume == 125 and not b.is2D and b.dimensions == 3
+    assert hoomd.Box.square(4).is2D and hoomd.Box.square(4).volume == 16
+    assert hoomd.Box.from_box([1, 2, 3]) == hoomd.Box(1, 2, 3)
+    assert hoomd.Box.from_box(dict(Lx=1, Ly=2, Lz=3, xy=0.5)).xy == 0.5
+    assert hoomd.Box.from_box(hoomd.Box(1, 2, 3, 0.1, 0.2, 0.3)).tilts.tolist() == [0.1, 0.2, 0.3]
+    b.L = 7
+    assert b.L.tolist() == [7, 7, 7]
+    s = hoomd.Snapshot()
+    s.configuration.box = hoomd.Box(3, 4, 5)
+    assert list(s.configuration.box) == [3, 4, 5, 0, 0, 0]
+    with pytest.raises(ValueError):
+        hoomd.Box.from_box([1, 2])
+
+
 def test_snapshot_replicate_and_wrap():
     """hoomd.Snapshot.replicate / wrap (hoomd/ParticleData.cc:3742-3810, hoomd/BondedGroupData.cc:1366-1405)."""
     from hoomd_blue_b200 import Snapshot
