@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "rng.cuh"
+#include "reduce.cuh"
 
 namespace hb2
     {
@@ -91,74 +92,6 @@ __global__ void __launch_bounds__(INT_BLOCK)
         }
     }
 
-// Deterministic block -> grid fp64 sum: every block writes its partial, the last block to finish
-// (ticket) adds the partials in index order with a fixed tree.
-// Returns true in the one thread that wrote the final sums (so a caller can chain scalar work).
-template<int NV>
-HB2_DEVICE bool grid_sum(double (&v)[NV], double* __restrict__ partial, uint32_t* __restrict__ ticket,
-                         double* __restrict__ out)
-    {
-    __shared__ double s_w[NV][INT_BLOCK / 32];
-    __shared__ bool s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int q = 0; q < NV; q++)
-        {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
-        if (lane == 0)
-            s_w[q][warp] = v[q];
-        }
-    __syncthreads();
-    if (threadIdx.x == 0)
-        {
-#pragma unroll
-        for (int q = 0; q < NV; q++)
-            {
-            double t = 0.0;
-            for (int w = 0; w < INT_BLOCK / 32; w++)
-                t += s_w[q][w];
-            partial[(size_t)q * gridDim.x + blockIdx.x] = t;
-            }
-        __threadfence();
-        const uint32_t done = atomicAdd(ticket, 1u);
-        s_last = (done == gridDim.x - 1);
-        }
-    __syncthreads();
-    if (s_last)
-        {
-        __threadfence();
-#pragma unroll
-        for (int q = 0; q < NV; q++)
-            {
-            double t = 0.0;
-            for (uint32_t b = threadIdx.x; b < gridDim.x; b += INT_BLOCK)
-                t += partial[(size_t)q * gridDim.x + b];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-                t += __shfl_xor_sync(0xffffffffu, t, off);
-            if (lane == 0)
-                s_w[q][warp] = t;
-            }
-        __syncthreads();
-        if (threadIdx.x == 0)
-            {
-#pragma unroll
-            for (int q = 0; q < NV; q++)
-                {
-                double t = 0.0;
-                for (int w = 0; w < INT_BLOCK / 32; w++)
-                    t += s_w[q][w];
-                out[q] = t;
-                }
-            *ticket = 0u;
-            return true;
-            }
-        }
-    return false;
-    }
-
 // a = F/m; v *= s; v += 1/2 dt a (hoomd/md/TwoStepConstantVolume.cc:234-260), optionally followed
 // by KE = 1/2 sum m v^2 in fp64 (hoomd/md/ComputeThermo.cc:139-153).
 // When `bussi.rescale` is set, the thread that finishes the KE sum also draws the Bussi factor of the
@@ -189,7 +122,7 @@ __global__ void __launch_bounds__(INT_BLOCK)
         }
     if (KE)
         {
-        const bool fin = grid_sum<1>(ke, partial, ticket, ke_out);
+        const bool fin = grid_sum<1, INT_BLOCK>(ke, partial, ticket, ke_out);
         if (fin && bussi.rescale)
             *bussi.rescale = bussi_factor(*ke_out, bussi.dof, bussi.dt, bussi.kT, bussi.tau,
                                           bussi.timestep, (uint16_t)bussi.seed, bussi.first_tag);
@@ -258,7 +191,7 @@ __global__ void __launch_bounds__(INT_BLOCK)
         ke[0] = 0.5 * (double)v.w
                 * ((double)v.x * (double)v.x + (double)v.y * (double)v.y + (double)v.z * (double)v.z);
         }
-    grid_sum<1>(ke, partial, ticket, ke_out);
+    grid_sum<1, INT_BLOCK>(ke, partial, ticket, ke_out);
     }
 
 // sum of per-particle potential energy (force.w, hoomd/ForceCompute.cc:213-220) and the six
@@ -277,7 +210,7 @@ __global__ void __launch_bounds__(INT_BLOCK)
             for (int q = 0; q < 6; q++)
                 v[1 + q] = (double)virial[q * virial_pitch + i];
         }
-    grid_sum<7>(v, partial, ticket, out7);
+    grid_sum<7, INT_BLOCK>(v, partial, ticket, out7);
     }
 
 __global__ void bussi_kernel(const double* __restrict__ d_ke, double dof, double dt, double kT,

@@ -19,6 +19,7 @@
 //     hits: rows come out in ascending particle index, deterministically, without atomics.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "nlist_common.cuh"
 #include <stdlib.h>
 #include <algorithm>
 
@@ -33,121 +34,12 @@ constexpr int NL_WARPS = 4;     // warps (home cells) per block
 #endif
 constexpr int NL_CMAX = NL_CMAX_DEF; // candidates per lane per round (odd); 21 -> 5 blocks per SM
 constexpr int NL_CAP = 32 * NL_CMAX;
-constexpr float NL_FAR = 1.0e18f;
 
 template<bool MULTITYPE> struct NlWarpSmem
     {
     float4 cand[NL_CAP]; // x, y, z (image-shifted), particle index (bits)
     uint8_t type[MULTITYPE ? NL_CAP : 16];
     };
-
-struct NlConst
-    {
-    BoxF bf;
-    BoxD bd;
-    float band; // relative guard band of the fp32 distance test
-    };
-
-// k-th (ascending) member of the sorted, de-duplicated periodic neighbourhood {c-1, c, c+1} of
-// coordinate c on a ring of size dim, and the image shift (in units of L) that brings that cell next
-// to c. Returns the neighbourhood size.
-HB2_DEVICE int ring3(int c, int dim, int k, int& coord, int& shift)
-    {
-    shift = 0;
-    if (dim == 1)
-        {
-        coord = 0;
-        return 1;
-        }
-    if (dim == 2)
-        {
-        coord = k & 1;
-        return 2;
-        }
-    if (c == 0)
-        {
-        coord = (k == 2) ? dim - 1 : k;
-        shift = (k == 2) ? -1 : 0;
-        }
-    else if (c == dim - 1)
-        {
-        coord = (k == 0) ? 0 : dim - 3 + k;
-        shift = (k == 0) ? 1 : 0;
-        }
-    else
-        coord = c - 1 + k;
-    return 3;
-    }
-
-// position of the q-th (0-based) set bit of m (m < 2^24 and popc(m) > q): binary search on popc
-HB2_DEVICE uint32_t nth_set_bit(uint32_t m, uint32_t q)
-    {
-    uint32_t t = 0, c;
-    c = __popc(m & 0xFFFu);
-    if (q >= c)
-        {
-        q -= c;
-        t = 12;
-        m >>= 12;
-        }
-    c = __popc(m & 0x3Fu);
-    if (q >= c)
-        {
-        q -= c;
-        t += 6;
-        m >>= 6;
-        }
-    c = __popc(m & 0x7u);
-    if (q >= c)
-        {
-        q -= c;
-        t += 3;
-        m >>= 3;
-        }
-    c = m & 1u;
-    if (q >= c)
-        {
-        q -= c;
-        t += 1;
-        m >>= 1;
-        }
-    c = m & 1u;
-    if (q >= c)
-        t += 1;
-    return t;
-    }
-
-// The same along a dimension that may be decomposed over n ranks (this rank at grid coordinate rc):
-// the local grid is then open — interior home cells 1..dim-2 always have both neighbours — and only
-// the ghost-cell layers that lie across the GLOBAL periodic boundary carry an image shift.
-HB2_DEVICE int stencil3(int c, int dim, int n, int rc, int k, int& coord, int& shift)
-    {
-    if (n > 1)
-        {
-        coord = c - 1 + k;
-        shift = 0;
-        if (coord == 0 && rc == 0)
-            shift = -1;
-        else if (coord == dim - 1 && rc == n - 1)
-            shift = 1;
-        return 3;
-        }
-    return ring3(c, dim, k, coord, shift);
-    }
-
-HB2_DEVICE uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total)
-    {
-    uint32_t incl = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1)
-        {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off)
-            incl += t;
-        }
-    total = __shfl_sync(0xffffffffu, incl, 31);
-    return incl - v;
-    }
 
 // MULTITYPE: per-type-pair r_list; SMALLDIM: some grid dimension < 3, so a stencil cell can hold
 // both images of a neighbour and the sweep applies the minimum image itself.
@@ -552,434 +444,6 @@ __global__ void __launch_bounds__(NL_WARPS * 32, NL_MIN_BLOCKS)
         atomicMax(&conditions[0], max_n);
     }
 
-// ------------------------------------------------------------------------------------------------
-// Row-per-lane build (one particle type, every periodic ring >= 3 cells, pitch <= NR_MAX_PITCH).
-//
-// Same stencil and staging as above, but the sweep is transposed: LANE l OWNS HOME PARTICLE l of the
-// cell and every lane walks the whole staged stencil. Candidates are staged structure-of-arrays, so
-// one broadcast LDS.128 per coordinate feeds four candidates to all 32 home particles, and the
-// distance arithmetic runs two candidates per packed fp32 instruction. A hit appends the candidate's
-// 16-bit staged index to the lane's private row in shared memory (predicated STS + pointer bump): the
-// row comes out ascending with no masks, no scans and no compaction pass — that pass was 40 % of
-// the mask-based kernel's instructions. Rows are then written to HBM one after the other with full
-// 128-byte coalesced stores (the staged index is translated to the particle index on the way out).
-// The kernel holds ~10 warps per SM (shared memory), so everything outside the sweep is written to
-// keep many independent loads in flight: all 27 stencil cells are fetched before the first is
-// staged, and the write-out reads four 32-entry groups of a row before it stores the first.
-// Bit-exactness: hits are collected for r <= hi (the guard band's upper edge); a lane that saw any
-// r >= lo re-walks its own row and re-decides those entries in fp64 like the CPU build.
-constexpr int NR_WARPS = 2;
-constexpr int NR_CAP = 704; // staged candidates per round (multiple of 8)
-constexpr uint32_t NR_MAX_PITCH = 256;
-constexpr uint32_t NR_SLACK = 16;    // row entries beyond the pitch: one sweep trip appends <= 16
-
-HB2_HOSTDEVICE uint32_t nr_row_stride_words(uint32_t pitch)
-    {
-    return ((pitch + NR_SLACK) >> 1) | 1u; // odd: the lanes' row heads fall into distinct banks
-    }
-HB2_HOSTDEVICE size_t nr_warp_smem(uint32_t pitch)
-    {
-    return 16u * (size_t)NR_CAP + 128u * (size_t)nr_row_stride_words(pitch);
-    }
-
-// rows are addressed by their 32-bit shared-window byte address (one register, one add per hit)
-HB2_DEVICE void sts_u16(uint32_t addr, int v)
-    {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
-    }
-
-// eight staged candidates (two float4 groups per coordinate), starting at staged index idx0, against
-// this lane's home particle. SELF: the group may hold the home particle itself, which must not list
-// itself (hoomd/md/NeighborListBinned.cc:144).
-template<bool SELF>
-HB2_DEVICE void nr_test8(const float4 (&X)[2], const float4 (&Y)[2], const float4 (&Z)[2], int idx0,
-                         float2 npx, float2 npy, float2 npz, int hi1, int self, uint32_t& rp, int& mx)
-    {
-#pragma unroll
-    for (int u = 0; u < 2; u++)
-        {
-#pragma unroll
-        for (int v = 0; v < 2; v++)
-            {
-            const float2 cx = v ? make_float2(X[u].z, X[u].w) : make_float2(X[u].x, X[u].y);
-            const float2 cy = v ? make_float2(Y[u].z, Y[u].w) : make_float2(Y[u].x, Y[u].y);
-            const float2 cz = v ? make_float2(Z[u].z, Z[u].w) : make_float2(Z[u].x, Z[u].y);
-            const float2 dx = __fadd2_rn(cx, npx);
-            const float2 dy = __fadd2_rn(cy, npy);
-            const float2 dz = __fadd2_rn(cz, npz);
-            const float2 r = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-            const int idx = idx0 + 4 * u + 2 * v;
-            const int ra = __float_as_int(r.x), rb = __float_as_int(r.y);
-            bool pa = ra < hi1, pb = rb < hi1;
-            if (SELF)
-                {
-                pa = pa && idx != self;
-                pb = pb && idx + 1 != self;
-                }
-            if (pa)
-                {
-                sts_u16(rp, idx);
-                rp += 2;
-                mx = max(mx, ra);
-                }
-            if (pb)
-                {
-                sts_u16(rp, idx + 1);
-                rp += 2;
-                mx = max(mx, rb);
-                }
-            }
-        }
-    }
-
-// one sweep segment: steps [it0, it1) of 8 candidates each, two steps per loop trip and the
-// shared-memory loads of a step issued one step ahead of its arithmetic (software pipeline: at ~2.5
-// warps per scheduler the LDS latency is otherwise exposed once per step).
-template<bool SELF>
-HB2_DEVICE void nr_sweep(const float4* __restrict__ sx4, const float4* __restrict__ sy4,
-                         const float4* __restrict__ sz4, uint32_t it0, uint32_t it1, float2 npx,
-                         float2 npy, float2 npz, int hi1, int self, uint32_t& rp,
-                         const uint32_t rp_lim, uint32_t& over, int& mx)
-    {
-    if (it0 >= it1)
-        return;
-    float4 XA[2], YA[2], ZA[2], XB[2], YB[2], ZB[2];
-    auto load = [&](float4 (&X)[2], float4 (&Y)[2], float4 (&Z)[2], uint32_t it)
-    {
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-            {
-            X[u] = sx4[2 * it + u];
-            Y[u] = sy4[2 * it + u];
-            Z[u] = sz4[2 * it + u];
-            }
-    };
-    auto check = [&]()
-    {
-        if (rp > rp_lim)
-            {
-            // row full: keep counting, stop advancing (the host regrows the list and rebuilds)
-            over += (rp - rp_lim) >> 1;
-            rp = rp_lim;
-            }
-    };
-    uint32_t it = it0;
-    load(XA, YA, ZA, it);
-#pragma unroll 1
-    for (; it + 1 < it1; it += 2)
-        {
-        load(XB, YB, ZB, it + 1);
-        nr_test8<SELF>(XA, YA, ZA, (int)(8 * it), npx, npy, npz, hi1, self, rp, mx);
-        load(XA, YA, ZA, min(it + 2, it1 - 1)); // (the last trip re-reads a valid step)
-        nr_test8<SELF>(XB, YB, ZB, (int)(8 * it + 8), npx, npy, npz, hi1, self, rp, mx);
-        check();
-        }
-    if (it < it1)
-        {
-        nr_test8<SELF>(XA, YA, ZA, (int)(8 * it), npx, npy, npz, hi1, self, rp, mx);
-        check();
-        }
-    }
-
-// per-lane description of one stencil cell of the warp's home cell (lane < 27)
-struct NrStencil
-    {
-    uint32_t c_start, c_cnt;
-    float shx, shy, shz;
-    bool is_home;
-    uint32_t h0, hend; // (uniform) the home cell's owned particles
-    };
-
-HB2_DEVICE NrStencil nr_load_stencil(uint32_t cell, uint3 dim, const DomainGeom& geom, const BoxF& bf,
-                                     const uint32_t* __restrict__ cell_start,
-                                     const uint32_t* __restrict__ cell_end, uint32_t N, int lane)
-    {
-    NrStencil st;
-    st.h0 = __ldg(cell_start + cell);
-    st.hend = min(__ldg(cell_end + cell), N); // ghost-layer cells start at or beyond N
-    st.c_start = st.c_cnt = 0;
-    st.shx = st.shy = st.shz = 0.f;
-    st.is_home = false;
-    if (lane < 27)
-        {
-        const int cx = cell % dim.x, cy = (cell / dim.x) % dim.y, cz = cell / (dim.x * dim.y);
-        const int kx = lane % 3, ky = (lane / 3) % 3, kz = lane / 9;
-        int nx, ny, nz, sx_, sy_, sz_;
-        stencil3(cx, dim.x, geom.n[0], geom.coord[0], kx, nx, sx_);
-        stencil3(cy, dim.y, geom.n[1], geom.coord[1], ky, ny, sy_);
-        stencil3(cz, dim.z, geom.n[2], geom.coord[2], kz, nz, sz_);
-        const uint32_t cid = ((uint32_t)nz * dim.y + (uint32_t)ny) * dim.x + (uint32_t)nx;
-        st.c_start = __ldg(cell_start + cid);
-        st.c_cnt = __ldg(cell_end + cid) - st.c_start;
-        st.shx = (float)sx_ * bf.L[0];
-        st.shy = (float)sy_ * bf.L[1];
-        st.shz = (float)sz_ * bf.L[2];
-        st.is_home = (cid == cell);
-        }
-    return st;
-    }
-
-// Persistent warps: warp w builds the rows of cells w, w + W, w + 2W, ... While it writes one cell's
-// rows out it already has the next cell's 27 position loads in flight (and that cell's table
-// entries were requested before the sweep), so the global-memory latency of the staging is off the
-// critical path — with ~10 warps per SM it would otherwise be a third of the kernel's time.
-__global__ void __launch_bounds__(NR_WARPS * 32, 5)
-    nlist_build_rows_kernel(const float4* __restrict__ pos, uint32_t N, DomainGeom geom,
-                            const uint32_t* __restrict__ cell_start,
-                            const uint32_t* __restrict__ cell_end, double r_listsq_single,
-                            NlConst cst, uint32_t* __restrict__ nlist, uint32_t pitch,
-                            uint32_t* __restrict__ n_neigh, float4* __restrict__ last_pos,
-                            uint32_t* __restrict__ conditions, uint32_t dummy_index)
-    {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const int lane = threadIdx.x & 31;
-    const uint32_t rstride = nr_row_stride_words(pitch);
-    unsigned char* s_warp = s_raw + nr_warp_smem(pitch) * (threadIdx.x >> 5);
-    float* sx = reinterpret_cast<float*>(s_warp);
-    float* sy = sx + NR_CAP;
-    float* sz = sy + NR_CAP;
-    uint32_t* sj = reinterpret_cast<uint32_t*>(sz + NR_CAP);
-    uint16_t* rows = reinterpret_cast<uint16_t*>(sj + NR_CAP);
-    uint16_t* const myrow = rows + (size_t)lane * 2u * rstride;
-    const float4* sx4 = reinterpret_cast<const float4*>(sx);
-    const float4* sy4 = reinterpret_cast<const float4*>(sy);
-    const float4* sz4 = reinterpret_cast<const float4*>(sz);
-
-    const uint3 dim = make_uint3(geom.dimt[0], geom.dimt[1], geom.dimt[2]);
-    const uint32_t Nc = dim.x * dim.y * dim.z;
-    const uint32_t n_warps = gridDim.x * NR_WARPS;
-    const float rl2 = (float)r_listsq_single;
-    const int lo1 = __float_as_int(rl2 * (1.0f - cst.band));
-    const int hi1 = __float_as_int(rl2 * (1.0f + cst.band)) + 1;
-
-    uint32_t max_n = 0;
-    uint32_t cell = blockIdx.x * NR_WARPS + (threadIdx.x >> 5);
-    if (cell >= Nc)
-        return;
-
-    // the first 32 particles of each stencil cell of the NEXT cell to process, and its layout
-    float4 v[27];
-    NrStencil nx = nr_load_stencil(cell, dim, geom, cst.bf, cell_start, cell_end, N, lane);
-    uint32_t nx_T = 0, nx_off = 0;
-    auto prefetch = [&]()
-    {
-        nx_off = warp_excl_scan(nx.c_cnt, lane, nx_T);
-        if (nx.h0 >= nx.hend)
-            return; // no owned particles in that cell: nothing to stage
-#pragma unroll
-        for (int u = 0; u < 27; u++)
-            {
-            const uint32_t s = __shfl_sync(0xffffffffu, nx.c_start, u);
-            const uint32_t cnt = __shfl_sync(0xffffffffu, nx.c_cnt, u);
-            const uint32_t q = __shfl_sync(0xffffffffu, nx_off, u) + lane;
-            v[u] = ((uint32_t)lane < cnt && q < (uint32_t)NR_CAP) ? __ldg(pos + s + lane)
-                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-    };
-    prefetch();
-
-    for (; cell < Nc; cell += n_warps)
-        {
-        const NrStencil st = nx;
-        const uint32_t T = nx_T, c_off = nx_off;
-        const uint32_t h0 = st.h0, hend = st.hend;
-        const bool cell_live = h0 < hend;
-        const uint32_t cell_next = cell + n_warps;
-        uint32_t home_off = 0;
-        if (cell_live)
-            {
-            home_off = __shfl_sync(0xffffffffu, c_off, __ffs(__ballot_sync(0xffffffffu, st.is_home)) - 1);
-            // ---- staging of round 0 from the prefetched registers
-#pragma unroll
-            for (int u = 0; u < 27; u++)
-                {
-                const uint32_t s = __shfl_sync(0xffffffffu, st.c_start, u);
-                const uint32_t cnt = __shfl_sync(0xffffffffu, st.c_cnt, u);
-                const uint32_t q = __shfl_sync(0xffffffffu, c_off, u) + lane;
-                const float ox = __shfl_sync(0xffffffffu, st.shx, u);
-                const float oy = __shfl_sync(0xffffffffu, st.shy, u);
-                const float oz = __shfl_sync(0xffffffffu, st.shz, u);
-                if ((uint32_t)lane < cnt && q < (uint32_t)NR_CAP)
-                    {
-                    sx[q] = v[u].x + ox;
-                    sy[q] = v[u].y + oy;
-                    sz[q] = v[u].z + oz;
-                    sj[q] = s + lane;
-                    }
-                }
-            }
-        // the next cell's table entries: requested now, consumed after the sweep
-        if (cell_next < Nc)
-            nx = nr_load_stencil(cell_next, dim, geom, cst.bf, cell_start, cell_end, N, lane);
-        bool prefetched = false;
-
-        for (uint32_t r0 = 0; cell_live && r0 < T; r0 += NR_CAP)
-            {
-            const uint32_t r1 = min(T, r0 + NR_CAP);
-            const uint32_t ncand = r1 - r0;
-            const bool last_round = (r1 == T);
-            // ---- what the prefetch did not cover: later rounds, and cells with more than 32 particles
-            auto stage = [&](uint32_t q, uint32_t j, float4 p, float ox, float oy, float oz)
-            {
-                sx[q - r0] = p.x + ox;
-                sy[q - r0] = p.y + oy;
-                sz[q - r0] = p.z + oz;
-                sj[q - r0] = j;
-            };
-            if (r0 > 0 || __any_sync(0xffffffffu, st.c_cnt > 32u))
-                for (int u = 0; u < 27; u++)
-                    {
-                    const uint32_t s = __shfl_sync(0xffffffffu, st.c_start, u);
-                    const uint32_t cnt = __shfl_sync(0xffffffffu, st.c_cnt, u);
-                    const uint32_t off = __shfl_sync(0xffffffffu, c_off, u);
-                    const float ox = __shfl_sync(0xffffffffu, st.shx, u);
-                    const float oy = __shfl_sync(0xffffffffu, st.shy, u);
-                    const float oz = __shfl_sync(0xffffffffu, st.shz, u);
-                    for (uint32_t k = (r0 > 0 ? 0u : 32u) + lane; k < cnt; k += 32)
-                        if (off + k >= r0 && off + k < r1)
-                            stage(off + k, s + k, __ldg(pos + s + k), ox, oy, oz);
-                    }
-            const uint32_t n_it = (ncand + 7u) >> 3; // sweep steps of 8 candidates
-            if (ncand + lane < 8u * n_it)
-                {
-                sx[ncand + lane] = sy[ncand + lane] = sz[ncand + lane] = NL_FAR;
-                sj[ncand + lane] = dummy_index;
-                }
-            __syncwarp();
-
-            // ---- batches of 32 home particles (one batch unless the cell is crowded)
-            for (uint32_t hb = h0; hb < hend; hb += 32)
-                {
-                const uint32_t i = hb + lane;
-                const bool has = i < hend;
-                // staged entries [hs_lo, hs_lo + 32) are this batch's own particles (zero image shift)
-                const int hs_lo = (int)(home_off + (hb - h0)) - (int)r0;
-                const int self = hs_lo + lane;
-                // an idle lane sits far away from everything, padding included
-                float4 ph = make_float4(-NL_FAR, -NL_FAR, -NL_FAR, 0.f);
-                if (has)
-                    ph = (self >= 0 && self < (int)ncand) ? make_float4(sx[self], sy[self], sz[self], 0.f)
-                                                          : __ldg(pos + i);
-                const uint32_t it_a = (uint32_t)min(max(hs_lo >> 3, 0), (int)n_it);
-                const uint32_t it_b = (uint32_t)min(max((hs_lo + 32 + 7) >> 3, 0), (int)n_it);
-
-                const uint32_t rp0 = (uint32_t)__cvta_generic_to_shared(myrow);
-                uint32_t rp = rp0;
-                const uint32_t rp_lim = rp0 + 2u * pitch;
-                uint32_t over = 0;
-                int mx = 0;
-                const float2 npx = make_float2(-ph.x, -ph.x), npy = make_float2(-ph.y, -ph.y),
-                             npz = make_float2(-ph.z, -ph.z);
-                nr_sweep<false>(sx4, sy4, sz4, 0, it_a, npx, npy, npz, hi1, self, rp, rp_lim, over, mx);
-                nr_sweep<true>(sx4, sy4, sz4, it_a, it_b, npx, npy, npz, hi1, self, rp, rp_lim, over, mx);
-                nr_sweep<false>(sx4, sy4, sz4, it_b, n_it, npx, npy, npz, hi1, self, rp, rp_lim, over, mx);
-                uint32_t n = (rp - rp0) >> 1;
-                __syncwarp(); // (also orders the sweep's asm stores before the reads below)
-
-                // ---- guard band: entries with lo <= r <= hi are decided exactly as the fp64 CPU build
-                if (mx >= lo1 && over == 0 && has)
-                    {
-                    uint32_t n2 = 0;
-                    for (uint32_t s = 0; s < n; s++)
-                        {
-                        const uint32_t idx = myrow[s];
-                        // the sweep's arithmetic, operation for operation
-                        const float ax = __fadd_rn(sx[idx], -ph.x), ay = __fadd_rn(sy[idx], -ph.y),
-                                    az = __fadd_rn(sz[idx], -ph.z);
-                        const int rb = __float_as_int(
-                            __fmaf_rn(az, az, __fmaf_rn(ay, ay, __fmul_rn(ax, ax))));
-                        bool keep = true;
-                        if (rb >= lo1)
-                            keep = dist_sq_exact(cst.bd, ph, __ldg(pos + sj[idx])) <= r_listsq_single;
-                        if (keep)
-                            myrow[n2++] = (uint16_t)idx;
-                        }
-                    n = n2;
-                    }
-                n += over;
-                const uint32_t n_out = over ? 0u : n; // an overflowed row holds nothing worth writing
-                if (r0 == 0 && last_pos && has)
-                    last_pos[i] = ph;
-                __syncwarp();
-
-                // the staged candidates are not needed any more after this write-out: get the next
-                // cell's positions on their way
-                if (last_round && hb + 32 >= hend && cell_next < Nc)
-                    {
-                    prefetch();
-                    prefetched = true;
-                    }
-
-                // ---- rows to HBM, one after the other, 128 bytes per store instruction; the last
-                // 32-slot group of a row is filled up with the dummy particle's index. Four groups are
-                // read before the first is stored.
-                const uint32_t base = (r0 > 0 && has) ? n_neigh[i] : 0u;
-                const uint32_t nh = min(32u, hend - hb);
-                const uint16_t* row = rows;
-                uint32_t* out = nlist + (size_t)hb * pitch;
-                for (uint32_t r = 0; r < nh; r++, row += 2u * rstride, out += pitch)
-                    {
-                    const uint32_t n_r = __shfl_sync(0xffffffffu, n_out, r);
-                    const uint32_t b_r = r0 > 0 ? min(__shfl_sync(0xffffffffu, base, r), pitch) : 0u;
-                    const uint32_t tot = b_r + n_r;
-                    const uint32_t kend = min(last_round ? ((tot + 31u) & ~31u) : tot, pitch) - b_r;
-                    for (uint32_t k0 = lane; k0 < kend; k0 += 128)
-                        {
-                        uint32_t idx[4], val[4];
-#pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            idx[p] = k0 + 32u * p < n_r ? row[k0 + 32u * p] : 0xffffu;
-#pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            val[p] = idx[p] != 0xffffu ? sj[idx[p]] : dummy_index;
-#pragma unroll
-                        for (int p = 0; p < 4; p++)
-                            if (k0 + 32u * p < kend)
-                                out[b_r + k0 + 32u * p] = val[p];
-                        }
-                    }
-                if (has)
-                    {
-                    n_neigh[i] = base + n;
-                    max_n = max(max_n, base + n);
-                    }
-                __syncwarp();
-                }
-            }
-        if (!prefetched && cell_next < Nc)
-            prefetch(); // (this cell had no owned particles)
-        }
-
-    max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, 16));
-    max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, 8));
-    max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, 4));
-    max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, 2));
-    max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, 1));
-    if (lane == 0 && max_n)
-        atomicMax(&conditions[0], max_n);
-    }
-
-static hb2_status launch_rows(const NlistBuildArgs& a, const NlConst& cst, cudaStream_t stream)
-    {
-    const uint32_t Nc = a.geom.dimt[0] * a.geom.dimt[1] * a.geom.dimt[2];
-    const size_t smem = nr_warp_smem(a.pitch) * NR_WARPS;
-    // persistent warps: as many blocks as fit on the 148 SMs at once
-    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
-    const uint32_t blocks = std::min<uint32_t>((Nc + NR_WARPS - 1) / NR_WARPS, NUM_SMS * per_sm);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem)
-        {
-        HB2_CUDA(cudaFuncSetAttribute(nlist_build_rows_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-        }
-    nlist_build_rows_kernel<<<blocks, NR_WARPS * 32, smem, stream>>>(
-        a.pos, a.N, a.geom, a.cell_start, a.cell_end, a.r_listsq_single, cst, a.nlist, a.pitch, a.n_neigh,
-        a.last_pos, a.conditions, a.dummy_index);
-    HB2_CHECK_LAUNCH("nlist_build_rows_kernel");
-    return HB2_OK;
-    }
-
 template<bool MT, bool SD>
 static hb2_status launch_variant(const NlistBuildArgs& a, const NlConst& cst, cudaStream_t stream)
     {
@@ -1011,31 +475,12 @@ hb2_status launch_nlist_build(const NlistBuildArgs& a, const hb2_box& box, cudaS
         set_error("nlist build: at most 64 particle types are supported");
         return HB2_ERR_INVALID;
         }
-    NlConst cst;
-    cst.bf = boxf(box);
-    cst.bd = boxd(box);
-    // fp32 error model of rsq (DESIGN.md "guard band"): each component of the separation carries at
-    // most 2^-23 Lmax absolute error (one rounding of a difference of magnitude <= Lmax, one of the
-    // image shift), so rsq carries <= 2 sqrt(3) r 2^-23 Lmax + 2^-22 rsq. The band is twice that,
-    // relative to the smallest r_list in use.
-    const double rl_min = a.r_list_min > 0 ? a.r_list_min : 1.0;
-    double band = 2.0 * (2.0 * 1.7320508 * ldexp(1.0, -23) * (double)a.Lmax / rl_min + ldexp(1.0, -22));
-    if (band > 0.25)
-        band = 0.25;
-    cst.band = (float)band;
+    const NlConst cst = nl_make_const(box, a.r_list_min, a.Lmax);
 
     // only a periodic ring of fewer than 3 cells can hold two images of one neighbour
     bool small = false;
     for (int d = 0; d < 3; d++)
         small = small || (a.geom.n[d] == 1 && a.geom.dimt[d] < 3);
-    // Kernel choice: the row-per-lane build (HB2_NLIST_KERNEL=rows) needs one type, full rings and
-    // rows that fit in shared memory.
-    const bool rows_ok = a.ntypes == 1 && !small && a.pitch <= NR_MAX_PITCH && a.r_listsq_single > 0.0;
-    // The row-per-lane kernel is opt-in: at C2 it runs level with the mask kernel (0.84 vs 0.88 ms under
-    // ncu, 0.98 vs 0.94 ms per rebuild in the step loop).
-    const char* pick = getenv("HB2_NLIST_KERNEL");
-    if (pick && pick[0] == 'r' && rows_ok)
-        return launch_rows(a, cst, stream);
     if (a.ntypes > 1)
         return small ? launch_variant<true, true>(a, cst, stream)
                      : launch_variant<true, false>(a, cst, stream);

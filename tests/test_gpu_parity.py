@@ -457,32 +457,6 @@ def test_oracle_random_liquid(hoomd, oracle, n_side, rho):
     assert np.max(np.abs(vs[[0, 3, 5]] - vs_ref[[0, 3, 5]])) <= TOTAL_RTOL * scale
 
 
-@pytest.mark.parametrize("n_side,rho", [(30, 0.9), (36, 1.6)])
-def test_row_per_lane_build_kernel(hoomd, oracle, monkeypatch, n_side, rho):
-    """The opt-in row-per-lane build (HB2_NLIST_KERNEL=rows, csrc/nlist.cu) against the oracle and
-    against the default mask kernel: same pair set bit for bit, same forces bit for bit (the rows hold
-    the same neighbours in the same ascending order). rho = 1.6 fills home cells beyond 32 particles
-    (several batches of home particles per cell)."""
-    pos, vel, L = random_liquid(n_side, rho, seed=7 * n_side, jitter=0.25)
-    fx = dict(L=L, pos=pos, vel=vel)
-
-    def build():
-        sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "shift")
-        sim.run(0)
-        return canon_pairs(cell.pair_list), lj.forces.copy(), cell._stats()
-
-    pairs_mask, f_mask, st_mask = build()
-    monkeypatch.setenv("HB2_NLIST_KERNEL", "rows")
-    pairs_rows, f_rows, st_rows = build()
-    monkeypatch.delenv("HB2_NLIST_KERNEL")
-    box = oracle.make_box([float(v) for v in L])
-    nn, head, nl, dim = oracle.nlist(box, pos, np.zeros(len(pos), dtype=np.uint32), [2.5], 0.4, full=True)
-    assert np.array_equal(pairs_rows, oracle.pair_set(nn, head, nl))
-    assert np.array_equal(pairs_rows, pairs_mask)
-    assert st_rows["max_neighbors"] == st_mask["max_neighbors"] == int(nn.max())
-    assert np.array_equal(f_rows, f_mask)
-
-
 def random_gas(n, L, seed):
     rng = np.random.default_rng(seed)
     L = np.asarray(L, dtype=np.float32)
