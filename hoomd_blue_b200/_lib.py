@@ -11,8 +11,10 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("HB2_LIB", "libhoomd_b200.so"))
  ERR_NO_DEVICE, ERR_COMM) = range(9)
 EVAL = {"lj": 0, "dpd": 1, "dpd_conservative": 2, "example_pair": 3, "gauss": 4, "yukawa": 5,
         "lj1208": 6, "lj0804": 7, "force_shifted_lj": 8, "mie": 9, "morse": 10,
-        "buckingham": 11, "expanded_lj": 12, "expanded_gaussian": 13, "lj_gauss": 14, "twf": 15, "dpdlj": 16}
+        "buckingham": 11, "expanded_lj": 12, "expanded_gaussian": 13, "lj_gauss": 14, "twf": 15, "dpdlj": 16,
+        "table": 17}
 SHIFT = {"none": 0, "shift": 1, "xplor": 2}
+PARAM_FLOATS = 8  # HB2_PARAM_FLOATS (include/hoomd_b200.h)
 
 
 class Box(C.Structure):
@@ -103,6 +105,7 @@ def _declare(L):
     L.hb2_pair_destroy.restype = None
     L.hb2_pair_set_params.argtypes = [_vp, C.c_uint32, C.c_uint32, _f64p, C.c_uint32]
     L.hb2_pair_set_r_cut.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double]
+    L.hb2_pair_set_table.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, _f64p, _f64p]
     L.hb2_pair_set_r_on.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double]
     L.hb2_pair_set_kT.argtypes = [_vp, C.c_double]
     L.hb2_pair_set_threads_per_particle.argtypes = [_vp, C.c_uint32]
@@ -117,6 +120,7 @@ def _declare(L):
     L.hb2_integrator_destroy.argtypes = [_vp]
     L.hb2_integrator_destroy.restype = None
     L.hb2_integrator_add_force.argtypes = [_vp, _vp]
+    L.hb2_integrator_set_reset_stats.argtypes = [_vp, C.c_int]
     L.hb2_integrator_set_constant_volume.argtypes = [_vp, C.c_int, C.c_double, C.c_double]
     L.hb2_system_set_bonds.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
     L.hb2_system_set_angles.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
@@ -147,7 +151,7 @@ def lib():
                 "(there is no CPU or PyTorch fallback for this path)")
         L = C.CDLL(LIB_PATH)
         _declare(L)
-        if L.hb2_abi_version() != 1:
+        if L.hb2_abi_version() != 2:
             raise ImportError("libhoomd_b200.so ABI version mismatch")
         _lib = L
     return _lib

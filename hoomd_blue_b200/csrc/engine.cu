@@ -629,9 +629,9 @@ extern "C" hb2_status hb2_system_set_compute_virial(hb2_system* s, int on)
     {
     if (!s)
         return HB2_ERR_INVALID;
-    if (s->compute_virial != (on != 0))
-        for (auto* p : s->pairs)
-            p->computed = false; // flags changed -> recompute (hoomd/ForceCompute.cc:562-574)
+    // flags changed -> the next getter recomputes (hoomd/ForceCompute.cc:562-574): pair_ensure sees
+    // compute_virial && !virial_valid and relaunches the force pass over the CURRENT list, so switching
+    // the flag never triggers a rebuild that an uninterrupted run would not do
     s->compute_virial = on != 0;
     return HB2_OK;
     }
@@ -1148,6 +1148,7 @@ static const EvalInfo* eval_info(hb2_evaluator ev)
         {EvaluatorPairLJGauss::n_user_params, pack_as<EvaluatorPairLJGauss>},
         {EvaluatorPairTWF::n_user_params, pack_as<EvaluatorPairTWF>},
         {EvaluatorPairDPDThermoLJ::n_user_params, pack_as<EvaluatorPairDPDThermoLJ>},
+        {0, nullptr}, // Table: variable-size parameters, hb2_pair_set_table
     };
     if ((unsigned)ev >= sizeof(table) / sizeof(table[0]))
         return nullptr;
@@ -1166,6 +1167,11 @@ extern "C" hb2_status hb2_pack_params(hb2_evaluator ev, const double* user, uint
     if (!e)
         {
         set_error("hb2_pack_params: unknown evaluator");
+        return HB2_ERR_INVALID;
+        }
+    if (!e->pack)
+        {
+        set_error("hb2_pack_params: this evaluator's parameters are not a fixed list (Table: hb2_pair_set_table)");
         return HB2_ERR_INVALID;
         }
     if (!user || !packed || n_user < e->n_user)
@@ -1218,6 +1224,8 @@ hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairA
         return pair_forces_twf(mode, a, box, stream);
     case HB2_EVAL_DPDLJ:
         return pair_forces_dpdlj(mode, a, box, stream);
+    case HB2_EVAL_TABLE:
+        return pair_forces_table(mode, a, box, stream);
         }
     set_error("pair forces: unknown evaluator");
     return HB2_ERR_INVALID;
@@ -1239,10 +1247,44 @@ hb2_status hb2_pair::upload_params()
             set_error("pair: parameters are not set for every type pair");
             return HB2_ERR_INVALID;
             }
-        HB2_TRY(hb2_pack_params(ev, &user[HB2_PARAM_FLOATS * q], HB2_PARAM_FLOATS, &packed[HB2_PARAM_FLOATS * q]));
+        if (ev != HB2_EVAL_TABLE)
+            HB2_TRY(hb2_pack_params(ev, &user[HB2_PARAM_FLOATS * q], HB2_PARAM_FLOATS, &packed[HB2_PARAM_FLOATS * q]));
         rcutsq_d[q] = r_cut[q] * r_cut[q]; // hoomd/md/PotentialPair.h:498
         rcutsq[q] = (float)rcutsq_d[q];
         ronsq[q] = (float)(r_on[q] * r_on[q]);
+        }
+    if (ev == HB2_EVAL_TABLE)
+        {
+        // all tables back to back in one device buffer (V then F per type pair); param_type points into it
+        size_t total = 0;
+        for (size_t q = 0; q < nt2; q++)
+            total += tables[q].size();
+        std::vector<float> flat;
+        flat.reserve(total);
+        std::vector<size_t> off(nt2);
+        for (size_t q = 0; q < nt2; q++)
+            {
+            off[q] = flat.size();
+            flat.insert(flat.end(), tables[q].begin(), tables[q].end());
+            }
+        if (total > table_cap)
+            {
+            dev_free(d_tables);
+            HB2_TRY(dev_alloc(&d_tables, total));
+            table_cap = total;
+            }
+        if (total)
+            HB2_CUDA(cudaMemcpyAsync(d_tables, flat.data(), sizeof(float) * total, cudaMemcpyHostToDevice,
+                                     sys->stream));
+        HB2_CUDA(cudaStreamSynchronize(sys->stream));
+        for (size_t q = 0; q < nt2; q++)
+            {
+            EvaluatorPairTable::param_type pt;
+            pt.rmin = (float)table_rmin[q];
+            pt.width = (uint32_t)(tables[q].size() / 2);
+            pt.table = d_tables + off[q];
+            memcpy(&packed[HB2_PARAM_FLOATS * q], &pt, sizeof(pt));
+            }
         }
     if (!d_params)
         {
@@ -1379,6 +1421,7 @@ extern "C" void hb2_pair_destroy(hb2_pair* p)
     dev_free(p->d_rcutsq);
     dev_free(p->d_ronsq);
     dev_free(p->d_rcutsq_d);
+    dev_free(p->d_tables);
     dev_free(p->d_force);
     dev_free(p->d_virial);
     delete p;
@@ -1412,6 +1455,41 @@ extern "C" hb2_status hb2_pair_set_params(hb2_pair* p, uint32_t ti, uint32_t tj,
         {
         for (uint32_t k = 0; k < HB2_PARAM_FLOATS; k++)
             p->user[HB2_PARAM_FLOATS * q + k] = k < n_user ? user_params[k] : 0.0;
+        p->have_params[q] = 1;
+        }
+    p->params_dirty = true;
+    p->computed = false;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_pair_set_table(hb2_pair* p, uint32_t ti, uint32_t tj, double r_min, uint32_t width,
+                                         const double* U, const double* F)
+    {
+    size_t a, b;
+    if (!p || !U || !F || !pair_index(p, ti, tj, a, b))
+        return HB2_ERR_INVALID;
+    if (p->ev != HB2_EVAL_TABLE)
+        {
+        set_error("hb2_pair_set_table: not a Table pair force");
+        return HB2_ERR_INVALID;
+        }
+    if (width == 0)
+        {
+        set_error("The length of V and F must not be zero."); // hoomd/md/EvaluatorPairTable.h:85-88
+        return HB2_ERR_INVALID;
+        }
+    const size_t nt2 = (size_t)p->sys->ntypes * p->sys->ntypes;
+    p->tables.resize(nt2);
+    p->table_rmin.resize(nt2, 0.0);
+    for (size_t q : {a, b})
+        {
+        p->tables[q].resize(2 * (size_t)width);
+        for (uint32_t k = 0; k < width; k++)
+            {
+            p->tables[q][k] = (float)U[k];
+            p->tables[q][width + k] = (float)F[k];
+            }
+        p->table_rmin[q] = r_min;
         p->have_params[q] = 1;
         }
     p->params_dirty = true;
@@ -1711,7 +1789,9 @@ extern "C" hb2_status hb2_pair_get_additional(hb2_pair* p, double* energy, doubl
         {
         for (int q = 0; q < 6; q++)
             virial6[q] = 0.0;
-        virial6[0] = virial6[3] = virial6[5] = w / 3.0 * 1.0; // diagonal share (PotentialPair.h:330-337)
+        // delta_virial = D V delta_P / 3 goes on EACH diagonal element (hoomd/md/PotentialPair.h:318-337),
+        // so that P = (2 K / 3 + (W_xx + W_yy + W_zz) / 3) / V moves by delta_P
+        virial6[0] = virial6[3] = virial6[5] = w;
         }
     return HB2_OK;
     }
@@ -2216,8 +2296,25 @@ extern "C" hb2_status hb2_bond_get(hb2_bond* b, double* forces3, double* energie
     return HB2_OK;
     }
 
-static hb2_status integrator_add_bonds(hb2_integrator* it, hb2_pair* pf, const uint32_t* skip_flag)
+// Integrator::computeNetForce (hoomd/Integrator.cc:166-246): the net force is the sum of every force.
+// The first pair force's arrays ARE the net-force arrays; every further pair force runs its own pass
+// over the shared neighbour list (whose r_cut matrix is the maximum over its consumers,
+// hoomd/md/NeighborList.cc:452-529) into its own arrays and is then added in, and the bonded forces
+// accumulate directly.
+static hb2_status integrator_add_extra(hb2_integrator* it, hb2_pair* pf, uint64_t timestep, bool want_energy,
+                                       const uint32_t* skip_flag)
     {
+    hb2_system* s = it->sys;
+    for (size_t k = 1; k < it->forces.size(); k++)
+        {
+        hb2_pair* p = it->forces[k];
+        if (p->params_dirty)
+            HB2_TRY(p->upload_params());
+        HB2_TRY(p->launch(timestep, want_energy, skip_flag));
+        HB2_TRY(launch_accumulate_force(pf->d_force, s->compute_virial ? pf->d_virial : nullptr, pf->cap_N,
+                                        p->d_force, p->d_virial, p->cap_N, s->N, skip_flag, s->stream));
+        pf->extra_added = true;
+        }
     for (auto* b : it->bonds)
         HB2_TRY(b->launch(pf->d_force, pf->d_virial, pf->cap_N, true, skip_flag));
     if (!it->bonds.empty())
@@ -2266,14 +2363,31 @@ extern "C" hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p)
     {
     if (!it || !p || p->sys != it->sys)
         return HB2_ERR_INVALID;
-    if (!it->forces.empty())
+    if (!it->forces.empty() && it->forces[0]->nl != p->nl)
         {
-        set_error("integrator: this path carries exactly one pair force (net force aliases it, "
-                  "hoomd/Integrator.cc:166-246 with one ForceCompute)");
+        set_error("integrator: the pair forces of one integrator share one neighbour list on this path "
+                  "(its r_cut matrix is the maximum over them, hoomd/md/NeighborList.cc:452-529)");
         return HB2_ERR_INVALID;
         }
+    for (auto* q : it->forces)
+        if (q == p)
+            {
+            set_error("integrator: this force is already attached");
+            return HB2_ERR_INVALID;
+            }
     it->forces.push_back(p);
     it->prepared = false;
+    return HB2_OK;
+    }
+
+// System::run resets the per-run statistics of every compute once per run; a caller that splits one run
+// into several hb2_integrator_run segments (writers between them) switches the reset off for all but the
+// first segment.
+extern "C" hb2_status hb2_integrator_set_reset_stats(hb2_integrator* it, int on)
+    {
+    if (!it)
+        return HB2_ERR_INVALID;
+    it->reset_stats = on != 0;
     return HB2_OK;
     }
 
@@ -2331,7 +2445,14 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     hb2_nlist* nl = pf->nl;
     HB2_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
-    pf->dt = it->dt;
+    bool any_dirty = false;
+    for (auto* p : it->forces)
+        {
+        p->dt = it->dt;
+        // DPD reads the velocities of its neighbours, ghosts included
+        if (s->dom.active && (p->ev == HB2_EVAL_DPD || p->ev == HB2_EVAL_DPDLJ))
+            s->dom.need_vel = true;
+        }
     double* d_ke = s->d_sums;
     double* d_rescale = s->d_sums + 8;
     // translational degrees of freedom of filter All, momentum conserving, 3D
@@ -2340,23 +2461,26 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
 
     // System::run resets the per-run statistics of every compute (hoomd/System.cc:103-110 ->
     // NeighborList::resetStats, hoomd/md/NeighborList.cc:1420-1427): num_builds counts this run only
-    nl->num_builds = 0;
-    nl->shortest_rebuild = ~0ull;
+    if (it->reset_stats)
+        {
+        nl->num_builds = 0;
+        nl->shortest_rebuild = ~0ull;
+        }
     HB2_CUDA(cudaEventRecord(it->ev0, st));
     // prepRun (hoomd/md/IntegratorTwoStep.cc:226-281): net force at the current timestep
     if (!it->prepared || !pf->computed || pf->computed_epoch != s->order_epoch
         || pf->computed_step != s->timestep)
         {
         HB2_TRY(pf->compute(s->timestep));
-        HB2_TRY(integrator_add_bonds(it, pf, nullptr));
+        HB2_TRY(integrator_add_extra(it, pf, s->timestep, true, nullptr));
         it->prepared = true;
         }
-    else if (!it->bonds.empty() && !pf->extra_added)
+    else if ((!it->bonds.empty() || it->forces.size() > 1) && !pf->extra_added)
         {
         // a getter left the pure pair force in the array: same state, same list — put the net force
         // back without touching the neighbour list (an uninterrupted run would not rebuild here)
         HB2_TRY(pf->launch(s->timestep, true, nullptr));
-        HB2_TRY(integrator_add_bonds(it, pf, nullptr));
+        HB2_TRY(integrator_add_extra(it, pf, s->timestep, true, nullptr));
         }
     if (it->thermostat == 1)
         {
@@ -2409,8 +2533,11 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         // decision. When the flag turns out set, the skipped launch cost ~2 us; rebuild and launch
         // again. (The reference reads the flag with a blocking copy every step,
         // hoomd/md/NeighborListGPU.cc:78-82.)
+        any_dirty = false;
+        for (auto* p : it->forces)
+            any_dirty = any_dirty || p->params_dirty;
         const bool speculate = check && !it->profiling && !nl->force_update && !nl->params_dirty
-                               && !pf->params_dirty && nl->buffer >= 1e-6
+                               && !any_dirty && nl->buffer >= 1e-6
                                && t + 1 >= nl->last_update_step + nl->rebuild_check_delay;
         if (check)
             {
@@ -2428,14 +2555,14 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             if (s->dom.active)
                 HB2_TRY(domain_update_ghosts(s));
             HB2_TRY(pf->launch(t + 1, step + 1 == nsteps, nl->d_conditions + 3));
-            HB2_TRY(integrator_add_bonds(it, pf, nl->d_conditions + 3));
+            HB2_TRY(integrator_add_extra(it, pf, t + 1, step + 1 == nsteps, nl->d_conditions + 3));
             HB2_CUDA(cudaEventSynchronize(s->flag_copied));
             flag = nl->h_conditions[3] != 0;
             if (flag)
                 {
                 HB2_TRY(nl->rebuild(t + 1));
                 HB2_TRY(pf->launch(t + 1, step + 1 == nsteps, nullptr));
-                HB2_TRY(integrator_add_bonds(it, pf, nullptr));
+                HB2_TRY(integrator_add_extra(it, pf, t + 1, step + 1 == nsteps, nullptr));
                 }
             }
         else
@@ -2456,7 +2583,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             hb2_status cst = pf->compute(t + 1, check, flag, step + 1 == nsteps);
             s->mid_event = nullptr;
             HB2_TRY(cst);
-            HB2_TRY(integrator_add_bonds(it, pf, nullptr));
+            HB2_TRY(integrator_add_extra(it, pf, t + 1, step + 1 == nsteps, nullptr));
             }
         if (it->profiling)
             {
@@ -2558,8 +2685,25 @@ extern "C" hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic,
         return HB2_ERR_INVALID;
     hb2_system* s = it->sys;
     HB2_CUDA(cudaSetDevice(s->device));
-    double v[7];
-    HB2_TRY(sums7(it->forces[0], v));
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (auto* p : it->forces)
+        {
+        double w[7];
+        HB2_TRY(sums7(p, w));
+        for (int q = 0; q < 7; q++)
+            v[q] += w[q];
+        // external energy / virial of the force (LJ tail correction): ComputeThermo adds
+        // getExternalEnergy() and getExternalVirial() (hoomd/md/ComputeThermo.cc:212-220)
+        double te, tw;
+        tail_correction(p, te, tw);
+        v[0] += te;
+        if (s->compute_virial)
+            {
+            v[1] += tw;
+            v[4] += tw;
+            v[6] += tw;
+            }
+        }
     for (auto* b : it->bonds)
         {
         // the bond force's own arrays, reduced like the pair force's

@@ -176,6 +176,11 @@ struct hb2_pair
     float* d_ronsq = nullptr;
     std::vector<double> rcutsq_d;
     double* d_rcutsq_d = nullptr;
+    // Table evaluator: per type pair V[width] then F[width], and r_min
+    std::vector<std::vector<float>> tables;
+    std::vector<double> table_rmin;
+    float* d_tables = nullptr;
+    size_t table_cap = 0;
     bool params_dirty = true;
     double kT = 1.0;
     double dt = 0.005;
@@ -234,6 +239,7 @@ struct hb2_integrator
     bool total_valid = false;
     uint64_t total_epoch = 0, total_step = 0; // particle order and timestep d_total belongs to
     bool prepared = false;
+    bool reset_stats = true; // reset the neighbour list's num_builds / shortest_rebuild at the start of run
     uint64_t prepared_epoch = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;

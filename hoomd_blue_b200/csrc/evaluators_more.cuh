@@ -596,4 +596,64 @@ class EvaluatorPairTWF
     Scalar rsq, rcutsq, sigma, alpha, prefactor;
     };
 #undef HB2_EVAL_COMMON
+// ---------------------------------------------------------------------------------------------
+// Tabulated potential (hoomd/md/EvaluatorPairTable.h:42-205): U(r) and F(r) = -dU/dr sampled at
+// r_min + i (r_cut - r_min) / width, linear interpolation, nothing outside [r_min, r_cut). The
+// variable-size tables live in one device buffer of the pair force; param_type carries a pointer into
+// it (V[width] followed by F[width]) — the role ManagedArray plays in the reference.
+// ---------------------------------------------------------------------------------------------
+class EvaluatorPairTable
+    {
+    public:
+    static constexpr bool has_packed = false;
+    static constexpr bool tune_tpp = false;
+    static constexpr bool needs_thermo = false;
+    struct param_type
+        {
+        Scalar rmin;
+        uint32_t width;
+        const Scalar* table;
+        };
+    static constexpr unsigned n_user_params = 0; // set through hb2_pair_set_table
+    HB2_DEVICE EvaluatorPairTable(Scalar _rsq, Scalar _rcutsq, const param_type& _params)
+        : rsq(_rsq), rcutsq(_rcutsq), rmin(_params.rmin), width(_params.width), table(_params.table)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        const Scalar r = sqrtf(rsq);
+        if (rsq >= rcutsq || r < rmin || width == 0)
+            return false;
+        const Scalar rcut = sqrtf(rcutsq);
+        const Scalar delta_r = (rcut - rmin) / (Scalar)width;
+        const Scalar value_f = (r - rmin) / delta_r;
+        uint32_t value_i = (uint32_t)floorf(value_f);
+        if (value_i >= width) // r within rounding of r_cut
+            value_i = width - 1;
+        const Scalar V0 = __ldg(table + value_i), F0 = __ldg(table + width + value_i);
+        Scalar V1 = 0, F1 = 0;
+        if (value_i + 1 < width)
+            {
+            V1 = __ldg(table + value_i + 1);
+            F1 = __ldg(table + width + value_i + 1);
+            }
+        const Scalar f = value_f - (Scalar)value_i;
+        const Scalar V = V0 + f * (V1 - V0);
+        const Scalar F = F0 + f * (F1 - F0);
+        if (rsq > Scalar(0.0))
+            force_divr = F / r;
+        pair_eng = V;
+        return true;
+        }
+    static const char* getName()
+        {
+        return "table";
+        }
+
+    protected:
+    Scalar rsq, rcutsq, rmin;
+    uint32_t width;
+    const Scalar* table;
+    };
+
     } // namespace hb2

@@ -166,6 +166,44 @@ __global__ void __launch_bounds__(INT_BLOCK)
     total[i] = make_float4(tx, ty, tz, f.w);
     }
 
+// net force += one more force (Integrator::computeNetForce, hoomd/Integrator.cc:166-246)
+__global__ void __launch_bounds__(INT_BLOCK)
+    accumulate_force_kernel(float4* __restrict__ dst, float* __restrict__ dst_virial, size_t dst_pitch,
+                            const float4* __restrict__ src, const float* __restrict__ src_virial,
+                            size_t src_pitch, uint32_t N, const uint32_t* __restrict__ skip_flag)
+    {
+    if (skip_flag && *skip_flag)
+        return;
+    const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
+    if (i >= N)
+        return;
+    float4 d = dst[i];
+    const float4 s = src[i];
+    d.x += s.x;
+    d.y += s.y;
+    d.z += s.z;
+    d.w += s.w;
+    dst[i] = d;
+    if (dst_virial && src_virial)
+        {
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            dst_virial[q * dst_pitch + i] += src_virial[q * src_pitch + i];
+        }
+    }
+
+hb2_status launch_accumulate_force(float4* dst, float* dst_virial, size_t dst_pitch, const float4* src,
+                                   const float* src_virial, size_t src_pitch, uint32_t N,
+                                   const uint32_t* skip_flag, cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    accumulate_force_kernel<<<(N + INT_BLOCK - 1) / INT_BLOCK, INT_BLOCK, 0, stream>>>(
+        dst, dst_virial, dst_pitch, src, src_virial, src_pitch, N, skip_flag);
+    HB2_CHECK_LAUNCH("accumulate_force_kernel");
+    return HB2_OK;
+    }
+
 hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,
                                     const uint32_t* tag, uint32_t N, float dt, const float* d_gamma_coeff,
                                     uint32_t seed, uint64_t timestep, cudaStream_t stream)

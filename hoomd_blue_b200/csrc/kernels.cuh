@@ -153,6 +153,11 @@ hb2_status launch_bussi(const double* d_ke, double dof, double dt, double kT, do
                         uint64_t timestep, uint32_t seed, uint32_t first_tag, double* d_rescale,
                         cudaStream_t stream);
 hb2_status launch_advance_timestep(uint64_t* d_timestep, cudaStream_t stream);
+// dst += src over N particles (force float4 and, when both virial arrays are given, the six virial rows);
+// skip_flag as in PairArgs
+hb2_status launch_accumulate_force(float4* dst, float* dst_virial, size_t dst_pitch, const float4* src,
+                                   const float* src_virial, size_t src_pitch, uint32_t N,
+                                   const uint32_t* skip_flag, cudaStream_t stream);
 // sum of force.w (potential energy), deterministic; and 6 virial sums
 hb2_status launch_reduce_energy(const float4* force, const float* virial, size_t virial_pitch,
                                 uint32_t N, double* d_partial, uint32_t* d_ticket, double* d_out7,

@@ -590,7 +590,7 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     {
     static_assert(sizeof(typename Ev::param_type) <= HB2_PARAM_FLOATS * sizeof(float)
                       && alignof(typename Ev::param_type) <= 16,
-                  "packed param_type is at most four floats on this ABI");
+                  "packed param_type is at most HB2_PARAM_FLOATS floats on this ABI");
     if (a.N == 0)
         return HB2_OK;
     if (a.ntypes > PAIR_MAX_TYPES_SMEM)
@@ -671,4 +671,5 @@ hb2_status pair_forces_expanded_gaussian(hb2_shift_mode, const PairArgs&, const 
 hb2_status pair_forces_lj_gauss(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_twf(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_dpdlj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_table(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
     } // namespace hb2

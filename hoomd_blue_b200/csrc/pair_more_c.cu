@@ -24,4 +24,8 @@ hb2_status pair_forces_twf(hb2_shift_mode m, const PairArgs& a, const hb2_box& b
     {
     return pair_dispatch<EvaluatorPairTWF>(m, a, b, s);
     }
+hb2_status pair_forces_table(hb2_shift_mode m, const PairArgs& a, const hb2_box& b, cudaStream_t s)
+    {
+    return pair_dispatch<EvaluatorPairTable>(m, a, b, s);
+    }
     } // namespace hb2

@@ -14,10 +14,22 @@ class ThermodynamicQuantities:
     def _attach(self, sim):
         self._sim = sim
 
-    def _q(self):
+    def _q(self, need_virial=False):
         if self._sim is None or self._sim.operations.integrator is None:
             raise RuntimeError("ThermodynamicQuantities is not attached")
-        return self._sim.operations.integrator._thermo()
+        integ = self._sim.operations.integrator
+        if need_virial and not self._sim.always_compute_pressure:
+            # The reference raises the pressure flag on the steps where a logger or writer asks for the
+            # pressure (hoomd/md/compute.py -> ComputeThermo::computeProperties with PDataFlags
+            # pressure_tensor). Here the observer switches the virial on for its own force pass over the
+            # current list and off again: the trajectory is not perturbed.
+            from .._lib import check, lib
+            check(lib().hb2_system_set_compute_virial(self._sim.state._h, 1))
+            try:
+                return integ._thermo()
+            finally:
+                check(lib().hb2_system_set_compute_virial(self._sim.state._h, 0))
+        return integ._thermo()
 
     @property
     def kinetic_energy(self):
@@ -29,7 +41,7 @@ class ThermodynamicQuantities:
 
     @property
     def degrees_of_freedom(self):
-        return 3 * self._sim.state.N_particles - 3
+        return self._sim.operations.integrator._translational_dof
 
     @property
     def kinetic_temperature(self):
@@ -38,8 +50,8 @@ class ThermodynamicQuantities:
     @property
     def pressure(self):
         """P = (2 K_trans / 3 + W) / V with W = (W_xx + W_yy + W_zz) / 3 summed over particles
-        (hoomd/md/ComputeThermo.cc, 3D). Needs always_compute_pressure."""
-        ke, pe, w = self._q()
+        (hoomd/md/ComputeThermo.cc, 3D), including the forces' external virial (LJ tail correction)."""
+        ke, pe, w = self._q(need_virial=True)
         V = self._sim.state.box.volume
         return (2.0 * ke / 3.0 + (w[0] + w[3] + w[5]) / 3.0) / V
 

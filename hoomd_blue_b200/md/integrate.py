@@ -9,8 +9,9 @@ from .methods import ConstantVolume, Bussi, Langevin
 
 
 class Integrator:
-    """hoomd.md.Integrator(dt, forces=[pair], methods=[ConstantVolume(...)]). Constraints, rigid
-    bodies, half-step hooks and integrate_rotational_dof are outside this path."""
+    """hoomd.md.Integrator(dt, forces=[pair, ...], methods=[ConstantVolume(...)]): every force
+    contributes to the net force (hoomd/Integrator.cc:166-246); pair forces share one neighbour list.
+    Constraints, rigid bodies, half-step hooks and integrate_rotational_dof are outside this path."""
 
     def __init__(self, dt, integrate_rotational_dof=False, forces=None, constraints=None,
                  methods=None, rigid=None, half_step_hook=None):
@@ -30,8 +31,10 @@ class Integrator:
         from .nlist import Cell
         bonds = [f for f in self.forces if isinstance(f, Bond)]
         pairs = [f for f in self.forces if not isinstance(f, Bond)]
-        if len(pairs) > 1 or (pairs and not isinstance(pairs[0], Pair)):
-            raise NotImplementedError("this path carries one pair force (plus bond forces)")
+        if any(not isinstance(f, Pair) for f in pairs):
+            raise NotImplementedError("this path carries pair and bonded forces")
+        if any(f.nlist is not pairs[0].nlist for f in pairs):
+            raise NotImplementedError("the pair forces of one integrator share one neighbour list on this path")
         if not pairs:
             # the net-force array belongs to the pair force: a bond-only integrator gets a pair force
             # that evaluates nothing (epsilon = 0) over a list without exclusions
@@ -49,10 +52,11 @@ class Integrator:
         check(L.hb2_integrator_create(C.byref(h), sim.state._h, self.dt))
         self._h = h
         self._sim = sim
-        f = pairs[0]
-        self._pair = f
-        f._attach(sim)
-        check(L.hb2_integrator_add_force(h, f._h))
+        self._pair = pairs[0]
+        self._pairs = pairs
+        for f in pairs:
+            f._attach(sim)
+            check(L.hb2_integrator_add_force(h, f._h))
         for b in bonds:
             b._attach(sim)
             check(L.hb2_integrator_add_bond(h, b._h))
@@ -77,11 +81,14 @@ class Integrator:
             if hasattr(f, "nlist"):
                 f.nlist._detach()
 
-    def _run(self, steps):
+    def _run(self, steps, first_segment=True):
+        """One segment of Simulation.run; the per-run statistics (nlist.num_builds, shortest_rebuild)
+        are reset by the first segment only (System::run, hoomd/System.cc:103-110)."""
         if steps > 0 and not self.methods:
             raise NotImplementedError("an integrator without a method can only run(0) on this path")
         for b in getattr(self, "_bonds", []):
             b._sync()
+        check(_lib.lib().hb2_integrator_set_reset_stats(self._h, int(bool(first_segment))))
         check(_lib.lib().hb2_integrator_run(self._h, steps))
 
     def _last_run_ms(self):
@@ -107,3 +114,14 @@ class Integrator:
         v = (C.c_double * 6)()
         check(_lib.lib().hb2_integrator_thermo(self._h, C.byref(ke), C.byref(pe), v))
         return ke.value, pe.value, list(v)
+
+    @property
+    def _translational_dof(self):
+        """hoomd/md/IntegratorTwoStep.cc:154-189: the method's group size times the dimension, minus
+        the three centre-of-mass degrees when the (single) method conserves momentum —
+        ConstantVolume does (hoomd/md/TwoStepConstantVolume.h), Langevin does not
+        (hoomd/md/TwoStepLangevinBase.h) — and 0 without a method."""
+        if not self.methods or self._sim is None:
+            return 0
+        n = 3 * self._sim.state.N_particles
+        return n if isinstance(self.methods[0], Langevin) else n - 3

@@ -318,3 +318,41 @@ class DPDLJ(Pair):
 
     def _attach_extra(self):
         check(_lib.lib().hb2_pair_set_kT(self._h, self.kT))
+
+
+class Table(Pair):
+    """hoomd.md.pair.Table(nlist, default_r_cut=None): tabulated potential, params {r_min, U, F} with
+    U and F = -dU/dr sampled at r_min + i (r_cut - r_min) / len(U), linearly interpolated
+    (hoomd/md/pair/pair.py Table, hoomd/md/EvaluatorPairTable.h). No energy shift modes."""
+    _accepted_modes = ("none",)
+    _evaluator = "table"
+    _param_keys = ("r_min", "U", "F")
+
+    def __init__(self, nlist, default_r_cut=None):
+        super().__init__(nlist, default_r_cut, 0.0, "none")
+
+    def _validate_params(self, v):
+        missing = [k for k in self._param_keys if k not in v]
+        if missing:
+            raise ValueError(f"missing parameters {missing}")
+        U = np.ascontiguousarray(v["U"], dtype=np.float64).reshape(-1)
+        F = np.ascontiguousarray(v["F"], dtype=np.float64).reshape(-1)
+        if len(U) != len(F):
+            raise ValueError("The length of V and F arrays must be equal.")
+        if len(U) == 0:
+            raise ValueError("The length of V and F must not be zero.")
+        return dict(r_min=float(v["r_min"]), U=U, F=F)
+
+    def _sync(self):
+        if self._h is None:
+            return
+        L = _lib.lib()
+        types = self._sim.state.particle_types
+        for i, a in enumerate(types):
+            for j, b in enumerate(types):
+                if j < i:
+                    continue
+                p = self.params[(a, b)]
+                check(L.hb2_pair_set_table(self._h, i, j, p["r_min"], len(p["U"]),
+                                           _lib.ptr(p["U"], C.c_double), _lib.ptr(p["F"], C.c_double)))
+                check(L.hb2_pair_set_r_cut(self._h, i, j, self.r_cut[(a, b)]))

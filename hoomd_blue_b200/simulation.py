@@ -580,7 +580,7 @@ class Simulation:
         snap, step = gsd_io.read_frame(filename, frame)
         if self.state is None and self._initial_timestep == 0:
             self._initial_timestep = step
-        self.create_state_from_snapshot(snap)
+        self.create_state_from_snapshot(snap, domain_decomposition)
 
     @property
     def timestep(self):
@@ -637,11 +637,13 @@ class Simulation:
                 for w in writers:
                     if w.trigger(now):
                         w._write(self)
+            first = True
             while now < end:
                 nxt = [w.trigger.next_after(now) for w in writers]
                 nxt = min([n for n in nxt if n is not None] + [end])
                 nxt = min(nxt, end)
-                integ._run(nxt - now)
+                integ._run(nxt - now, first_segment=first)
+                first = False
                 device_ms += integ._last_run_ms()
                 now = nxt
                 for w in writers:

@@ -31,7 +31,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define HB2_ABI_VERSION 1
+#define HB2_ABI_VERSION 2
 
 typedef enum
     {
@@ -86,9 +86,13 @@ typedef enum
     HB2_EVAL_EXPANDED_GAUSSIAN = 13, /* hoomd/md/EvaluatorPairExpandedGaussian.h; {epsilon, sigma, delta} */
     HB2_EVAL_LJ_GAUSS = 14,        /* hoomd/md/EvaluatorPairLJGauss.h; {epsilon, sigma, r0} */
     HB2_EVAL_TWF = 15,             /* hoomd/md/EvaluatorPairTWF.h; {epsilon, sigma, alpha} */
-    HB2_EVAL_DPDLJ = 16            /* hoomd/md/EvaluatorPairDPDThermoLJ.h; {epsilon, sigma, gamma} (+kT, seed) */
+    HB2_EVAL_DPDLJ = 16,           /* hoomd/md/EvaluatorPairDPDThermoLJ.h; {epsilon, sigma, gamma} (+kT, seed) */
+    HB2_EVAL_TABLE = 17            /* hoomd/md/EvaluatorPairTable.h; tabulated U(r), F(r): hb2_pair_set_table */
     } hb2_evaluator;
-#define HB2_PARAM_FLOATS 4 /* packed evaluator parameters per type pair (param_type is <= 16 bytes) */
+/* Stride, in floats, of one type pair's packed evaluator parameters (param_type is at most 32 bytes;
+ * evaluators with variable-size data, like Table, keep a device pointer in it) and the most user
+ * parameters hb2_pair_set_params takes. */
+#define HB2_PARAM_FLOATS 8
 
 /* hoomd/md/PotentialPair.h:104-109 */
 typedef enum
@@ -271,6 +275,10 @@ void hb2_pair_destroy(hb2_pair* p);
  * user_params: evaluator's user parameters in declaration order, e.g. LJ {epsilon, sigma}. */
 hb2_status hb2_pair_set_params(hb2_pair* p, uint32_t ti, uint32_t tj, const double* user_params,
                                uint32_t n_user);
+/* hoomd.md.pair.Table params {r_min, U, F} (hoomd/md/EvaluatorPairTable.h:42-110): `width` samples of
+ * U(r) and F(r) = -dU/dr at r_min + i (r_cut - r_min) / width, linearly interpolated; HB2_EVAL_TABLE only. */
+hb2_status hb2_pair_set_table(hb2_pair* p, uint32_t ti, uint32_t tj, double r_min, uint32_t width,
+                              const double* U, const double* F);
 hb2_status hb2_pair_set_r_cut(hb2_pair* p, uint32_t ti, uint32_t tj, double r_cut);
 hb2_status hb2_pair_set_r_on(hb2_pair* p, uint32_t ti, uint32_t tj, double r_on);
 hb2_status hb2_pair_set_kT(hb2_pair* p, double kT); /* DPD thermostat temperature */
@@ -296,7 +304,13 @@ hb2_status hb2_pair_get_additional(hb2_pair* p, double* energy, double virial6[6
  * hoomd/md/integrate.py:267-293, hoomd/md/methods/methods.py:145-175. */
 hb2_status hb2_integrator_create(hb2_integrator** out, hb2_system* sys, double dt);
 void hb2_integrator_destroy(hb2_integrator* it);
+/* Every pair force added contributes to the net force (Integrator::computeNetForce,
+ * hoomd/Integrator.cc:166-246); they must share one neighbour list, whose r_cut matrix is the maximum
+ * over them (hoomd/md/NeighborList.cc:452-529). */
 hb2_status hb2_integrator_add_force(hb2_integrator* it, hb2_pair* p);
+/* System::run resets num_builds / shortest_rebuild once per run (hoomd/System.cc:103-110); a caller that
+ * splits one run into several hb2_integrator_run calls switches the reset off after the first. */
+hb2_status hb2_integrator_set_reset_stats(hb2_integrator* it, int on);
 /* thermostat: 0 none (NVE), 1 Bussi(kT, tau) (hoomd/md/Thermostat.h:337-447; tau = 0 is allowed). */
 hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int thermostat, double kT,
                                               double tau);

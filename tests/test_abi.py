@@ -24,7 +24,7 @@ def test_header_symbols_exported():
     assert len(names) >= 60
     for n in names:
         assert hasattr(L, n), f"{n} is declared in include/hoomd_b200.h but not exported"
-    assert L.hb2_abi_version() == 1
+    assert L.hb2_abi_version() == 2
 
 
 def test_ctypes_binding_covers_header():
@@ -61,12 +61,12 @@ def test_host_helpers():
     assert L.hb2_box_make(C.byref(b), -1.0, 1.0, 1.0) == _lib.ERR_INVALID
     # LJ packing: lj1 = 4 eps sigma^12, lj2 = 4 eps sigma^6 (hoomd/md/EvaluatorPairLJ.h:119-140)
     user = (C.c_double * 2)(1.5, 0.8)
-    out = (C.c_float * 4)()
+    out = (C.c_float * _lib.PARAM_FLOATS)()
     assert L.hb2_pack_params(_lib.EVAL["lj"], user, 2, out) == 0
     assert np.allclose(list(out)[:2], [4 * 1.5 * 0.8 ** 12, 4 * 1.5 * 0.8 ** 6], rtol=1e-6)
     # Mie packs four: prefactor eps sigma^n, prefactor eps sigma^m, n, m (hoomd/md/EvaluatorPairMie.h:71-82)
     user4 = (C.c_double * 4)(1.0, 1.0, 12.0, 6.0)
     assert L.hb2_pack_params(_lib.EVAL["mie"], user4, 4, out) == 0
-    assert np.allclose(list(out), [4.0, 4.0, 12.0, 6.0], rtol=1e-6)
+    assert np.allclose(list(out)[:4], [4.0, 4.0, 12.0, 6.0], rtol=1e-6)
     assert L.hb2_pack_params(_lib.EVAL["mie"], user4, 3, out) == _lib.ERR_INVALID
     assert L.hb2_pack_params(_lib.EVAL["lj"], user, 1, out) == _lib.ERR_INVALID

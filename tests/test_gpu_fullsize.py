@@ -1,16 +1,71 @@
-"""Parity at BASELINE.json's full sizes through size-independent properties (the CPU oracle cannot
-reach them in seconds): an independent fp64 recomputation of energy and forces from the device's own
-pair list (numpy), a k-d tree check of sampled neighbour rows, momentum conservation (sum of forces
-= 0 for a full list with antisymmetric pair terms, including the DPD random force whose per-pair
-Philox draw is symmetric in the tags), bitwise run-to-run reproducibility, and bounded NVE drift.
+"""Parity at BASELINE.json's full sizes.
 
-configs[1] LJ N=1,048,576; configs[2] Kob-Andersen N=4,000,000 (full recomputation on a 500k system of
-the same state point); configs[4] DPD N=8,000,000.
+configs[1] LJ N=1,048,576, configs[2] Kob-Andersen N=4,000,000 and configs[4] DPD N=8,000,000 are each
+compared at run(0), AT THE CONFIGURED SIZE, with the reference itself (the HOOMD-blue CPU build under
+baseline/_ref, run in a subprocess by tests/ref_run0.py; the oracle port when that build did not travel
+to the box, and the assertion message says which): the neighbour-pair set bit for bit (count, per-tag
+degree and an order-independent 64-bit digest of the (min, max) tag pairs), per-particle forces to 1e-5,
+total energy and the virial sums to 1e-6. On top of that the size-independent properties: an independent
+fp64 recomputation from the device's own pair list (numpy), a k-d tree check of sampled rows, momentum
+conservation (including the DPD random force whose per-pair Philox draw is symmetric in the tags),
+bitwise run-to-run reproducibility, and bounded NVE drift.
 """
 import hashlib
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from pair_digest import degree, pair_digest  # noqa: E402
+
+FORCE_RTOL = 1e-5   # north_star: per-particle forces within 1e-5 relative (norm-wise, floored at the rms)
+TOTAL_RTOL = 1e-6   # north_star: total energy and virial within 1e-6 relative
+
+
+def reference_run0(tmp_path, L, pos, vel, typeid, types, kind, table, mode="none", buffer=0.4,
+                   dt=0.005, kT=1.0, seed=1, timestep=0):
+    """run(0) of the reference on this frame (tests/ref_run0.py). table: {(a, b): (p0, p1, r_cut)}."""
+    N = len(pos)
+    keys = list(table)
+    inp = dict(L=np.asarray([L, L, L], dtype=np.float64), pos=pos, vel=vel,
+               typeid=np.zeros(N, np.uint32) if typeid is None else typeid, types=np.array(list(types)),
+               kind=kind, pairs_a=np.array([k[0] for k in keys]), pairs_b=np.array([k[1] for k in keys]),
+               p0=np.array([table[k][0] for k in keys], dtype=np.float64),
+               p1=np.array([table[k][1] for k in keys], dtype=np.float64),
+               r_cut=np.array([table[k][2] for k in keys], dtype=np.float64), mode=mode, buffer=buffer,
+               dt=dt, kT=kT, seed=seed, timestep=timestep)
+    fin, fout = str(tmp_path / "ref_in.npz"), str(tmp_path / "ref_out.npz")
+    np.savez(fin, **inp)
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_run0.py")
+    r = subprocess.run([sys.executable, script, fin, fout], capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = dict(np.load(fout))
+    os.remove(fin)
+    os.remove(fout)
+    return out
+
+
+def assert_matches_reference(cell, pot, ref, N, virial=True):
+    """Pair set bit-exact, forces 1e-5, energy and virial 1e-6 against `ref` (reference_run0)."""
+    src = str(ref["source"])
+    pl = cell.pair_list
+    n, h, x = pair_digest(pl)
+    assert n == int(ref["n_pairs"]), (src, n, int(ref["n_pairs"]))
+    assert np.array_equal(degree(pl, N), ref["degree"]), src
+    assert (h, x) == (int(ref["pair_hash"]), int(ref["pair_xor"])), src
+    assert tuple(cell.dimensions) == tuple(int(d) for d in ref["dims"]), src
+    del pl
+    err = force_err(pot.forces, ref["force"])
+    assert err <= FORCE_RTOL, (src, err)
+    e_ref = float(ref["energy"])
+    assert abs(pot.energy - e_ref) <= TOTAL_RTOL * abs(e_ref), (src, pot.energy, e_ref)
+    if virial:
+        vs, vs_ref = pot.virials.sum(axis=0), ref["virial_sum"]
+        scale = np.max(np.abs(vs_ref[[0, 3, 5]]))
+        assert np.max(np.abs(vs - vs_ref)) <= TOTAL_RTOL * scale, (src, vs, vs_ref)
 
 pytestmark = pytest.mark.gpu
 
@@ -89,7 +144,7 @@ def lj_system(hoomd, pos, vel, L, typeid=None, types=("A",), params=None, r_cut=
     return sim, cell, lj
 
 
-def test_c2_lj_1m(hoomd):
+def test_c2_lj_1m(hoomd, tmp_path):
     rho, kT = 0.9, 1.5
     pos, vel, L = fcc(64, rho, kT, seed=1)
     N = len(pos)
@@ -106,7 +161,11 @@ def test_c2_lj_1m(hoomd):
         return lj_system(hoomd, p, v, L, params={("A", "A"): (1.0, 1.0)}, r_cut={("A", "A"): 2.5})
 
     s1, c1, l1 = fresh()
+    s1.always_compute_pressure = True
     s1.run(0)
+    # the configured size against the reference itself: pair set bit-exact, forces, energy, virial
+    ref = reference_run0(tmp_path, Lf, p, v, None, ("A",), "lj", {("A", "A"): (1.0, 1.0, 2.5)})
+    assert_matches_reference(c1, l1, ref, N)
     pl = c1.pair_list
     # every unordered pair once, no self pairs, degrees add up
     assert (pl[:, 0] != pl[:, 1]).all()
@@ -169,7 +228,7 @@ def ka_system(hoomd, ncell, seed):
     return sim, cell, lj, pos, typeid, float(L)
 
 
-def test_c3_kob_andersen(hoomd):
+def test_c3_kob_andersen(hoomd, tmp_path):
     # full fp64 recomputation with per-type-pair parameters on a 500k system of the same state point
     sim, cell, lj, pos, typeid, L = ka_system(hoomd, 50, seed=4)
     sim.run(0)
@@ -189,7 +248,13 @@ def test_c3_kob_andersen(hoomd):
     sim, cell, lj, pos, typeid, L = ka_system(hoomd, 100, seed=5)
     N = len(pos)
     assert N == 4_000_000
+    sim.always_compute_pressure = True
     sim.run(0)
+    ref = reference_run0(tmp_path, L, pos, np.zeros_like(pos), typeid, ("A", "B"), "lj",
+                         {k: (KA[k][0], KA[k][1], KA_RC[k]) for k in KA}, mode="shift", buffer=0.3,
+                         dt=0.0025)
+    assert_matches_reference(cell, lj, ref, N)
+    del ref
     f = lj.forces
     assert np.abs(f.sum(axis=0)).max() <= 1e-7 * np.abs(f).sum()
     st = cell._stats()
@@ -201,7 +266,7 @@ def test_c3_kob_andersen(hoomd):
     assert cell.num_builds >= 1
 
 
-def test_c5_dpd_8m(hoomd):
+def test_c5_dpd_8m(hoomd, tmp_path):
     n_side, rho = 200, 3.0
     N = n_side ** 3
     assert N == 8_000_000
@@ -227,7 +292,14 @@ def test_c5_dpd_8m(hoomd):
         return sim, cell, dpd
 
     s1, c1, d1 = make(5)
+    s1.always_compute_pressure = True
     s1.run(0)
+    # the configured size against the reference: pair set, and forces INCLUDING the random force
+    # (same seed, timestep and tags => the same per-pair Philox draws)
+    ref = reference_run0(tmp_path, float(L), pos, vel, None, ("A",), "dpd", {("A", "A"): (25.0, 4.5, 1.0)},
+                         buffer=0.4, dt=0.01, kT=1.0, seed=5)
+    assert_matches_reference(c1, d1, ref, N)
+    del ref
     f1 = d1.forces
     # alpha_ij = alpha_ji (Philox counter = (max tag, min tag)): random forces cancel pairwise
     assert np.abs(f1.sum(axis=0)).max() <= 1e-7 * np.abs(f1).sum()

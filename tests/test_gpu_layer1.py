@@ -79,7 +79,7 @@ def test_stateless_drivers_against_oracle(oracle):
     assert np.array_equal(d_last.cpu().numpy()[:, :3], ps)
 
     # pair forces
-    prm = (C.c_float * 4)()
+    prm = (C.c_float * _lib.PARAM_FLOATS)()
     _lib.check(L.hb2_pack_params(_lib.EVAL["lj"], (C.c_double * 2)(1.0, 1.0), 2, prm))
     d_prm = torch.tensor(list(prm), dtype=torch.float32, device=dev)
     d_rc = torch.tensor([r_cut ** 2], dtype=torch.float32, device=dev)

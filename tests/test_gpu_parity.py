@@ -12,6 +12,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FORCE_RTOL = 1e-5
 TOTAL_RTOL = 1e-6
 
@@ -121,7 +122,8 @@ def test_forces_and_energies_json(hoomd, golden_dir):
                                  ("ExpandedLJ", "ExpandedLJ", ("epsilon", "sigma", "delta")),
                                  ("ExpandedGaussian", "ExpandedGaussian", ("epsilon", "sigma", "delta")),
                                  ("LJGauss", "LJGauss", ("epsilon", "sigma", "r0")),
-                                 ("TWF", "TWF", ("epsilon", "sigma", "alpha"))):
+                                 ("TWF", "TWF", ("epsilon", "sigma", "alpha")),
+                                 ("Table", "Table", ("r_min", "U", "F"))):
         tab = fe[name]
         for p, F, E in zip(tab["params"], tab["forces"], tab["energies"]):
             for d, f_ref, e_ref in zip((0.75, 1.5), F, E):
@@ -671,3 +673,180 @@ def test_evaluator_family_consistency(hoomd, cls_name, params):
             em = build(pm, "shift")[2].energies
             step = float(pp[i, c]) - float(pm[i, c])
             assert abs(-(ep - em).sum() / step - f[i, c]) <= 2e-2 * max(abs(f[i, c]), scale)
+
+
+# ------------------------------------------------ net force, tail correction, observers ----
+def _two_particle_sim(hoomd, d, L=20.0, vel=None):
+    pos = np.array([[-d / 2, 0, 0.1], [d / 2, 0, 0.1]], dtype=np.float32)
+    vel = np.zeros_like(pos) if vel is None else np.asarray(vel, dtype=np.float32)
+    return make_sim(hoomd, [L, L, L], pos, vel)
+
+
+def test_tail_corrections(hoomd, oracle):
+    """hoomd/md/pytest/test_potential.py:1209-1290 (test_tail_corrections), same numbers: the energy and
+    pressure corrections of the LJ potential against the closed forms, and against the oracle's
+    restatement of PotentialPair::computeTailCorrection (hoomd/md/PotentialPair.h:255-341)."""
+    sigma, epsilon, d_pair, r_cut = 1.0, 0.5, 1.5, 2.0
+    v1 = np.array([0.46168675, -0.21020661, 0.21240303])
+    out = {}
+    for tail in (True, False):
+        sim = _two_particle_sim(hoomd, d_pair, vel=[v1, -v1])
+        cell = hoomd.md.nlist.Cell(buffer=0.4)
+        lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=r_cut, mode="none", tail_correction=tail)
+        lj.params[("A", "A")] = dict(sigma=sigma, epsilon=epsilon)
+        lang = hoomd.md.methods.Langevin(filter=hoomd.filter.All(), kT=1.0)
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[lang], forces=[lj])
+        sim.always_compute_pressure = True
+        thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+        sim.operations.computes.append(thermo)
+        sim.run(0)
+        out[tail] = (thermo.potential_energy, thermo.pressure, lj.energy, lj.additional_energy,
+                     lj.additional_virial, sim.state.box.volume)
+    N, volume = 2, out[True][5]
+    rho = N / volume
+    lj1, lj2 = 4 * epsilon * sigma ** 12, 4 * epsilon * sigma ** 6
+    e_pair = 4 * epsilon * ((sigma / d_pair) ** 12 - (sigma / d_pair) ** 6)
+    dE = 2 * N * np.pi * rho * (lj1 / 9 / r_cut ** 9 - lj2 / 3 / r_cut ** 3)
+    dP = 4 / 6 * rho ** 2 * np.pi * (lj1 * 4 / 3 / r_cut ** 9 - lj2 * 2 / r_cut ** 3)
+    ke = 0.5 * (v1 @ v1 + v1 @ v1)
+    ljf = 24 * epsilon / d_pair * (2 * (sigma / d_pair) ** 12 - (sigma / d_pair) ** 6)
+    p_plain = (2 * ke / 3 + ljf * d_pair / 3) / volume
+    assert np.isclose(out[False][0], e_pair, rtol=1e-6)
+    assert np.isclose(out[True][0], e_pair + dE, rtol=1e-6)
+    assert np.isclose(out[False][1], p_plain, rtol=1e-6)
+    assert np.isclose(out[True][1], p_plain + dP, rtol=1e-6)
+    assert dE < 0 and dP < 0
+    # Force.energy includes the external energy, additional_* expose it (hoomd/md/force.py:113-156)
+    assert np.isclose(out[True][2], e_pair + dE, rtol=1e-6) and np.isclose(out[True][3], dE, rtol=1e-12)
+    assert out[False][3] == 0.0
+    e_orc, w_orc = oracle.lj_tail_correction([[epsilon, sigma]], [r_cut], [N], volume)
+    assert np.isclose(out[True][3], e_orc, rtol=1e-12)
+    av = np.asarray(out[True][4])
+    assert np.allclose(av[[0, 3, 5]], w_orc, rtol=1e-12) and np.all(av[[1, 2, 4]] == 0)
+    assert np.isclose(w_orc, volume * dP, rtol=1e-12)
+
+
+def test_tail_correction_two_types(hoomd, oracle):
+    """Per-type-pair densities in the correction (KA mixture)."""
+    fx = dict(np.load(os.path.join(GOLDEN_DIR, "ka_2k.npz")))
+    sim, cell, lj = lj_sim(hoomd, fx, KA_PARAMS, KA_RC, 0.3, "none", types=("A", "B"))
+    lj.tail_correction = True
+    sim.run(0)
+    n_per_type = np.bincount(fx["typeid"], minlength=2)
+    volume = float(np.prod(fx["L"].astype(np.float64)))
+    order = [("A", "A"), ("A", "B"), ("A", "B"), ("B", "B")]  # tj * ntypes + ti
+    e_orc, w_orc = oracle.lj_tail_correction([list(KA_PARAMS[k]) for k in order], [KA_RC[k] for k in order],
+                                             n_per_type, volume)
+    assert np.isclose(lj.additional_energy, e_orc, rtol=1e-12)
+    assert np.allclose(np.asarray(lj.additional_virial)[[0, 3, 5]], w_orc, rtol=1e-12)
+
+
+def test_net_force_of_two_pair_forces(hoomd, oracle):
+    """Integrator::computeNetForce (hoomd/Integrator.cc:166-246): LJ + Yukawa on ONE neighbour list whose
+    r_cut matrix is the maximum over both (hoomd/md/NeighborList.cc:452-529). Each force keeps its own
+    per-particle arrays; the trajectory follows the sum; the list holds the larger cut-off."""
+    fx = dict(np.load(os.path.join(GOLDEN_DIR, "lj_2k.npz")))
+    N = len(fx["pos"])
+
+    def build(which):
+        sim = make_sim(hoomd, fx["L"], fx["pos"], fx["vel"], seed=11)
+        sim.always_compute_pressure = True
+        cell = hoomd.md.nlist.Cell(buffer=0.4)
+        forces = []
+        if "lj" in which:
+            lj = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+            lj.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+            forces.append(lj)
+        if "yuk" in which:
+            yk = hoomd.md.pair.Yukawa(nlist=cell, default_r_cut=3.0)
+            yk.params[("A", "A")] = dict(epsilon=0.7, kappa=1.3)
+            forces.append(yk)
+        cv = hoomd.md.methods.ConstantVolume(filter=hoomd.filter.All())
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[cv], forces=forces)
+        thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+        thermo._attach(sim)
+        return sim, cell, forces, thermo
+
+    s_lj, c_lj, (lj0,), _ = build(("lj",))
+    s_yk, c_yk, (yk0,), _ = build(("yuk",))
+    s_both, c_both, (lj, yk), thermo = build(("lj", "yuk"))
+    for s in (s_lj, s_yk, s_both):
+        s.run(0)
+    # the shared list carries max(r_cut) + buffer: the Yukawa-only list
+    assert np.array_equal(canon_pairs(c_both.pair_list), canon_pairs(c_yk.pair_list))
+    assert len(c_both.pair_list) > len(c_lj.pair_list)
+    # per-force results are those of the force alone (summation order differs: longer rows)
+    frms = np.sqrt(np.mean(np.sum(lj0.forces ** 2, axis=1)))
+    assert np.max(np.linalg.norm(lj.forces - lj0.forces, axis=1)) <= 1e-5 * frms
+    assert np.array_equal(yk.forces, yk0.forces)
+    assert abs(lj.energy - lj0.energy) <= 1e-6 * abs(lj0.energy)
+    # the oracle's LJ forces on the oracle's list with the larger cut-off
+    box = oracle.make_box([float(v) for v in fx["L"]])
+    types = np.zeros(N, dtype=np.uint32)
+    nn, head, nl, _ = oracle.nlist(box, fx["pos"], types, [3.0], 0.4, full=True)
+    f_orc, _ = oracle.pair_lj(box, fx["pos"], types, nn, head, nl, [[1.0, 1.0]], [2.5])
+    assert force_err(lj.forces, f_orc[:, :3]) <= FORCE_RTOL
+    # thermodynamics see the sum
+    assert np.isclose(thermo.potential_energy, lj.energy + yk.energy, rtol=1e-9)
+    p_sum = thermo.pressure
+    # the trajectory integrates the NET force: v(dt) = v(0) + dt/2 (F_net(0) + F_net(dt)) / m exactly
+    # (velocity Verlet, unit masses), with both forces' own getters giving F_net at either end
+    ke0 = thermo.kinetic_energy
+    f_net0 = lj.forces + yk.forces
+    s_both.run(1)
+    f_net1 = lj.forces + yk.forces
+    v1 = s_both.state.get_snapshot().particles.velocity.astype(np.float64)
+    v0 = fx["vel"].astype(np.float64)
+    want = 0.5 * 0.005 * (f_net0 + f_net1)
+    assert np.max(np.linalg.norm((v1 - v0) - want, axis=1)) <= 2e-5 * np.max(np.linalg.norm(want, axis=1)) + 1e-6
+    assert np.isfinite(p_sum) and thermo.kinetic_energy != ke0
+    # both forces stay valid through rebuilds: 50 steps conserve energy
+    e0 = thermo.kinetic_energy + thermo.potential_energy
+    s_both.run(50)
+    e1 = thermo.kinetic_energy + thermo.potential_energy
+    assert abs(e1 - e0) / N < 2e-3
+    assert c_both.num_builds >= 1
+
+
+def test_pressure_without_always_compute_pressure(hoomd, golden_dir):
+    """ThermodynamicQuantities.pressure must not silently drop the virial when the simulation does not
+    keep the pressure flag on (the reference raises the flag on the steps where it is logged): same value
+    as with always_compute_pressure, and asking for it does not perturb the trajectory."""
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+
+    def build(always):
+        sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none", seed=11)
+        sim.always_compute_pressure = always
+        thermo = hoomd.md.compute.ThermodynamicQuantities(filter=hoomd.filter.All())
+        thermo._attach(sim)
+        return sim, lj, thermo
+
+    s_on, _, t_on = build(True)
+    s_off, lj_off, t_off = build(False)
+    s_plain, _, _ = build(False)
+    for s in (s_on, s_off, s_plain):
+        s.run(10)
+    p_on, p_off = t_on.pressure, t_off.pressure
+    assert np.isclose(p_off, p_on, rtol=1e-6) and abs(p_on) > 0.1
+    assert lj_off.virials is None  # the flag is off again for the force's own getters
+    assert t_off.degrees_of_freedom == 3 * len(fx["pos"]) - 3
+    s_off.run(10)
+    s_plain.run(10)
+    assert np.array_equal(s_off.state.get_snapshot().particles.position,
+                          s_plain.state.get_snapshot().particles.position)
+
+
+def test_num_builds_covers_the_whole_run(hoomd, golden_dir):
+    """nlist.num_builds / shortest_rebuild cover one Simulation.run (System::run resets them once,
+    hoomd/System.cc:103-110), whether or not a writer splits the run into segments."""
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none", seed=11)
+    sim.run(40)
+    want = (cell.num_builds, cell.shortest_rebuild)
+    sim2, cell2, lj2 = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none", seed=11)
+    import io
+    logger = hoomd.logging.Logger(categories=["scalar"])
+    logger.add(lj2, quantities=["energy"])
+    sim2.operations.writers.append(hoomd.write.Table(hoomd.trigger.Periodic(1), logger, io.StringIO("")))
+    sim2.run(40)
+    assert (cell2.num_builds, cell2.shortest_rebuild) == want and want[0] >= 2
