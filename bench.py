@@ -10,8 +10,11 @@ Inputs are synthetic (seeded lattice + Maxwell velocities, equilibrated on the d
 
 Prints ONE JSON line (see the task contract): value = particle-steps/s with the state resident in HBM;
 e2e = the same metric through the public API with HOST snapshots in and out inside the timed region;
-roofline = the pair-force kernel against the measured HBM peak; cpu_baseline = the CPU oracle port
-timed on this box's host cores on a bounded sample.
+roofline = the pair-force kernel against the measured HBM peak; cpu_baseline = the reference's own CPU
+implementation (HOOMD-blue built by baseline/build_ref.sh into baseline/_ref, one single-core process per
+host core; the oracle port when that build is absent) timed on this box's host cores on a bounded sample.
+`--impl reference` is that CPU arm alone. With N > 1 GPUs the line also carries `parity` (the decomposed
+C1 frame against the reference fixture) and `strong_baseline` (the same 64 M system on ONE GPU).
 """
 import argparse
 import json
@@ -55,18 +58,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def roofline_pair(prof, nbar, N, hbm, peak_src):
+def roofline_pair(prof, nbar, N, hbm, peak_src, world=1):
     t = prof["force_ms"] / max(prof["force_launches"], 1) * 1e-3
     alg = (4.0 * nbar + 44.0) * N
-    traffic = None
+    # traffic = dram bytes per launch from an `ncu --set full` capture of THIS workload (C2 on one GPU;
+    # profiles/pair_force_summary.json). It is a recorded measurement, not taken in this run, and it
+    # does not apply to other particle counts: null there.
+    traffic, traffic_src = None, None
     summ = os.path.join(ROOT, "profiles", "pair_force_summary.json")
-    if os.path.exists(summ):
+    if world == 1 and N == 1048576 and os.path.exists(summ):
         with open(summ) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            js = json.load(f)
+        traffic = js.get("dram_bytes_per_launch")
+        traffic_src = "ncu capture " + js.get("capture", "profiles/pair_force_summary.json")
     return {"kernel": "pair_force_kernel<EvaluatorPairLJ>", "bound": "hbm",
             "achieved": alg / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / t / 1e9 / hbm,
-            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3,
-            "peak_source": peak_src}
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg,
+            "launch_ms": t * 1e3, "peak_source": peak_src}
 
 
 class ClockSampler:
@@ -197,8 +205,7 @@ def c1_sample():
 
 
 def cpu_baseline(pos, vel, L, nsteps, replicas):
-    """`replicas` independent single-core oracle runs concurrently (HOOMD's MD CPU path is
-    single-threaded per rank and no MPI exists here: SURVEY.md §8(d)); aggregate throughput."""
+    """`replicas` independent single-core oracle-port runs concurrently; aggregate throughput."""
     out = [None] * replicas
 
     def work(i):
@@ -216,35 +223,137 @@ def cpu_baseline(pos, vel, L, nsteps, replicas):
     return replicas * nsteps * len(pos) / slowest, wall
 
 
+def reference_available():
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "hoomd")) and not os.environ.get("HB2_FORCE_PORT")
+
+
+def reference_cpu(warmup, nsteps, replicas):
+    """The reference's own CPU path (hoomd.device.CPU of the build under baseline/_ref) on the C1
+    workload: one single-core process per replica (HOOMD's MD CPU path is single-threaded per rank and
+    this image has no MPI: SURVEY.md 8(d)), all running concurrently; aggregate particle-steps/s on the
+    slowest replica's clock. Returns (value, wall seconds, N, version) or None when a worker fails."""
+    worker = os.path.join(ROOT, "baseline", "ref_worker.py")
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([sys.executable, worker, str(warmup), str(nsteps)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for _ in range(replicas)]
+    outs = [p.communicate() for p in procs]
+    wall = time.perf_counter() - t0
+    res = []
+    for p, (so, se) in zip(procs, outs):
+        if p.returncode != 0:
+            sys.stderr.write("reference worker failed:\n" + se[-2000:] + "\n")
+            return None
+        res.append(json.loads(so.strip().splitlines()[-1]))
+    slowest = max(r["seconds"] for r in res)
+    return replicas * nsteps * res[0]["N"] / slowest, wall, res[0]["N"], res[0]["version"]
+
+
+def cpu_arm(warmup, nsteps):
+    """(value, cpu_baseline dict, N) of the CPU arm on this box's host cores: the reference when its
+    build travelled with the repository, else the oracle port."""
+    cores = os.cpu_count() or 1
+    if reference_available():
+        r = reference_cpu(warmup, nsteps, cores)
+        if r is not None:
+            value, wall, n, ver = r
+            return value, {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                           "sample": f"{cores} independent single-core hoomd.device.CPU processes "
+                                     f"(HOOMD-blue {ver}, fp64, baseline/_ref) x {nsteps} steps after "
+                                     f"{warmup} warm-up steps of the N={n} equilibrated liquid of "
+                                     "configs[0] (same rho, kT, r_cut, buffer, Bussi as the 1M workload; "
+                                     "no MPI in this image: throughput-equivalent, not strong-scaled; "
+                                     f"{wall:.1f} s wall)"}, n
+    pos, vel, L = c1_sample()
+    value, wall = cpu_baseline(pos, vel, L, nsteps, cores)
+    return value, {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cores} independent single-core oracle-port replicas x {nsteps} steps of "
+                             f"the N={len(pos)} equilibrated liquid of configs[0] (same rho, kT, r_cut, "
+                             f"buffer; baseline/_ref not present; {wall:.1f} s wall)"}, len(pos)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import md_oracle as orc
-    orc.lib()
-    cores = os.cpu_count() or 1
-    # bounded sample of the same workload: a 64^3-cell FCC liquid is 1,048,576 particles; the oracle
-    # does ~5e5 particle-steps/s/core, so the sample is the same state advanced a few steps
-    pos, vel, L = c1_sample()
-    nsteps = max(1, min(args.steps, int(os.environ.get("HB2_REF_STEPS", "100"))))
-    # the oracle's untimed step-0 call (prepRun) is its warm-up
-    value, wall = cpu_baseline(pos, vel, L, nsteps, cores)
+    # a bounded sample of the workload: the C1 liquid (configs[0]) advanced `steps` steps after `warmup`
+    # warm-up steps per host core; HB2_REF_STEPS caps the timed steps (CPU: ~9 steps/s per core)
+    nsteps = max(1, min(args.steps, int(os.environ.get("HB2_REF_STEPS", "1000"))))
+    warmup = max(0, min(args.warmup, 200))
+    value, cb, n = cpu_arm(warmup, nsteps)
+    cores = cb["cores"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": nsteps, "warmup": 1, "ms_per_step": 1e3 * len(pos) * cores / value,
+        "steps": nsteps, "warmup": warmup, "ms_per_step": 1e3 * n * cores / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"LJ liquid N={len(pos)} rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4 Bussi "
-                               "(CPU oracle port of the reference's half-list path)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} independent single-core replicas x {nsteps} steps of the "
-                                   f"N={len(pos)} equilibrated liquid of configs[0] (same rho, kT, "
-                                   "r_cut, buffer as the 1M workload; no MPI in this image: "
-                                   f"throughput-equivalent, not strong-scaled; {wall:.1f} s wall)"},
+        "config": {"workload": f"LJ liquid N={n} rho=0.9 kT=1.5 r_cut=2.5 buffer=0.4, Cell nlist + "
+                               "ConstantVolume/Bussi, dt=0.005 (BASELINE.json configs[0], the reference's "
+                               f"CPU-runnable case) x {cores} single-core replicas"},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(json.dumps(line))
+
+
+def parity_check(hoomd, dist, rank, world, local):
+    """The reference-generated C1 frame (tests/golden/c1_64k.npz) on the same device(s) and
+    decomposition as the benchmark: pair set against the reference's sha256, forces, energy."""
+    import hashlib
+    fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "c1_64k.npz")))
+    sim = hoomd.Simulation(device=hoomd.device.GPU(gpu_id=local), seed=7)
+    sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays(list(fx["L"]) + [0, 0, 0], fx["pos"], fx["vel"],
+                                                              None, ("A",), fx["image"]))
+    sim, cell, lj = attach_ops(hoomd, sim, thermostat=False)
+    sim.run(0)
+    pl = np.asarray(cell.pair_list, dtype=np.uint32).reshape(-1, 2)   # collective with N > 1
+    f = lj.forces
+    e = lj.energy
+    grid = list(sim.state.domain_decomposition)
+    out = None
+    if rank == 0:
+        lo, hi = pl.min(axis=1), pl.max(axis=1)
+        key = np.unique(lo.astype(np.uint64) << np.uint64(32) | hi.astype(np.uint64))
+        pairs = np.stack([(key >> np.uint64(32)).astype(np.uint32),
+                          (key & np.uint64(0xFFFFFFFF)).astype(np.uint32)], axis=1)
+        n_ref = np.linalg.norm(fx["force"], axis=1)
+        floor = np.sqrt(np.mean(n_ref ** 2))
+        ferr = float(np.max(np.linalg.norm(f - fx["force"], axis=1) / np.maximum(n_ref, floor)))
+        e_ref = float(fx["total_energy"])
+        out = {"frame": "tests/golden/c1_64k.npz (reference-generated, N=64000)", "decomposition": grid,
+               "pairs_listed": int(len(pl)), "pairs_unique": int(len(pairs)),
+               "pairs_reference": int(fx["n_pairs"]),
+               "pair_set_sha256_match": hashlib.sha256(pairs.tobytes()).hexdigest() == str(fx["pairs_sha256"]),
+               "force_rel_err_max": ferr, "energy_rel_err": abs(e - e_ref) / abs(e_ref),
+               "pass": bool(len(pl) == len(pairs) == int(fx["n_pairs"])
+                            and hashlib.sha256(pairs.tobytes()).hexdigest() == str(fx["pairs_sha256"])
+                            and ferr <= 1e-5 and abs(e - e_ref) <= 1e-6 * abs(e_ref))}
+    sim.operations.integrator._detach()
+    sim.state._destroy()
+    return out
+
+
+def strong_baseline(hoomd, local, repl, steps, warmup):
+    """The N > 1 workload (configs[3], 64 M particles) on ONE B200 — it fits in 180 GB — so that the
+    multi-GPU numbers have a same-system denominator."""
+    from hoomd_blue_b200.communicator import Communicator
+    one = Communicator()
+    one.rank, one.num_ranks = 0, 1
+    N, tags, pos, vel, L = replicated_c1(repl, (1, 1, 1), (0, 0, 0))
+    sim = hoomd.Simulation(device=hoomd.device.GPU(gpu_id=local, communicator=one), seed=1)
+    sim._create_state_from_local([float(v) for v in L] + [0, 0, 0], ["A"], N, tags, pos, vel)
+    del tags, pos, vel
+    sim, cell, lj = attach_ops(hoomd, sim)
+    sim.run(50)
+    sim.run(warmup)
+    sim.run(steps)
+    ms = sim._last_device_ms
+    out = {"n_gpus": 1, "N": int(N), "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+           "value": N * steps / (ms * 1e-3), "unit": UNIT,
+           "what": "the same 64 M-particle system, undivided, on rank 0's GPU (device-timed)"}
+    sim.operations.integrator._detach()
+    sim.state._destroy()
+    return out
 
 
 def run_ours(args):
@@ -315,15 +424,16 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sim.run(args.warmup)
-    L0c = _lib.lib().hb2_launch_count()
+    # clocks and throttle reasons are sampled from the warm-up to the end of the e2e loop: the timed
+    # region alone is shorter than nvidia-smi's sampling period at C2
     sampler = ClockSampler(local)
     sampler.start()
+    sim.run(args.warmup)
+    L0c = _lib.lib().hb2_launch_count()
     barrier()
     sim.run(args.steps)
     ms = sim._last_device_ms  # CUDA events on the engine's stream around the K steps
     barrier()
-    clocks = sampler.stop()
     launches = int(_lib.lib().hb2_launch_count() - L0c)
     builds = cell.num_builds
     ms = max_over_ranks(ms)
@@ -358,20 +468,44 @@ def run_ours(args):
         loc = sim.state._get_local(pinned=True)
     barrier()
     t0 = time.perf_counter()
+    dbg = os.environ.get("HB2_BENCH_DEBUG")
     for _ in range(calls):
+        ta = time.perf_counter()
         if world == 1:
             sim.state.set_snapshot(snap)
+            tb = time.perf_counter()
             sim.run(S)
+            tc = time.perf_counter()
             snap = sim.state.get_snapshot(into=snap)
         else:
             tag_, pos_, vel_, mass_, tid_, img_ = loc
             sim.state._set_tagged(N, tag_, pos_, vel_, tid_, mass_, img_)
+            tb = time.perf_counter()
             sim.run(S)
+            tc = time.perf_counter()
             loc = sim.state._get_local(pinned=True, into=loc)
+        td = time.perf_counter()
         e = lj.energy
+        if dbg and rank == 0:
+            print("e2e call: set %.1f ms, run %.1f ms (device %.1f ms), get %.1f ms, energy %.1f ms"
+                  % ((tb - ta) * 1e3, (tc - tb) * 1e3, sim._last_device_ms, (td - tc) * 1e3,
+                     (time.perf_counter() - td) * 1e3), file=sys.stderr)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = N * S * calls / e2e_s
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps + instrumented steps + e2e loop"
+    parity = parity_check(hoomd, dist if world > 1 else None, rank, world, local)
+    strong = None
+    if world > 1 and (os.environ.get("HB2_BENCH_STRONG", "" if repl_env else "1") == "1"):
+        # free this rank's share of the decomposed system before the single-GPU run of the same system
+        integ = None
+        sim.operations.integrator._detach()
+        sim.state._destroy()
+        barrier()
+        if rank == 0:
+            strong = strong_baseline(hoomd, local, repl, min(args.steps, 100), min(args.warmup, 20))
+        barrier()
     h2d = N * (12 + 12 + 4 + 4 + 12) + (0 if world == 1 else 4 * N)
     d2h = h2d + 8
 
@@ -399,9 +533,11 @@ def run_ours(args):
                              "per rank: state._set_tagged(pinned host arrays) + sim.run(S) + "
                              "state._get_local() + energy (collective)")},
             "gpu_launches": launches,
+            "parity": parity,
+            "strong_baseline": strong,
             # dominant kernel: pair_force_kernel. Algorithmic bytes per launch = (4 nbar + 44) N_local
             # (neighbour row + own position + count + head + force write)
-            "roofline": roofline_pair(prof, pstats["mean_neighbors"], n_local, hbm, peak_src),
+            "roofline": roofline_pair(prof, pstats["mean_neighbors"], n_local, hbm, peak_src, world),
             "phases": {"force_ms_per_step": prof["force_ms"] / max(prof["force_launches"], 1),
                        "nlist_ms_per_build": prof["nlist_ms"] / max(prof["builds"], 1),
                        "nlist_ms_per_step": prof["nlist_ms"] / max(prof["steps"], 1),
@@ -420,15 +556,8 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         if os.environ.get("HB2_BENCH_CPU", "1") != "0" and world == 1:
-            cores = os.cpu_count() or 1
-            nst = int(os.environ.get("HB2_REF_STEPS", "100"))
-            cp, cv, cL = c1_sample()
-            v, wall = cpu_baseline(cp, cv, cL, nst, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{cores} independent single-core oracle replicas x "
-                                              f"{nst} steps of the N={len(cp)} equilibrated liquid of "
-                                              f"configs[0] (same rho, kT, r_cut, buffer; {wall:.1f} s "
-                                              "wall)"}
+            # bounded: ~10-30 s of CPU work (100 steps of the 64,000-particle liquid per core)
+            _, line["cpu_baseline"], _ = cpu_arm(10, int(os.environ.get("HB2_CPU_STEPS", "100")))
         _emit(json.dumps(line))
 
 

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256)
                          const int* __restrict__ image3, const uint32_t* __restrict__ tag_in,
                          float4* __restrict__ pos, float4* __restrict__ vel, int* __restrict__ image,
                          uint32_t* __restrict__ tag, uint32_t* __restrict__ rtag, uint32_t ntypes,
-                         BoxD box, DomainGeom geom, uint32_t* __restrict__ flags)
+                         BoxD box, DomainGeom geom, OwnMargin margin, uint32_t* __restrict__ flags)
     {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N)
@@ -188,8 +188,11 @@ __global__ void __launch_bounds__(256)
             {
             // plain fp64 arithmetic in the host filter's order (no contraction: separate roundings)
             const double f = __dmul_rn(__dadd_rn((double)pc[d], -box.lo[d]), box.Linv[d]);
+            // a particle a rank hands back may have drifted just past a face since the last migration
+            // (the next rebuild moves it); anything farther out means the caller passed particles of
+            // other domains
             const double g = domain_g(f, geom.n[d], geom.coord[d]);
-            if (!(g >= 0.0 && g < 1.0))
+            if (!(g >= -margin.frac[d] && g < 1.0 + margin.frac[d]))
                 atomicMax(&flags[1], i + 1);
             }
     pos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(t));
@@ -236,14 +239,14 @@ __global__ void __launch_bounds__(256)
 hb2_status snapshot_pack(uint32_t N, const float* pos3, const float* vel3, const float* mass,
                          const uint32_t* typeid_, const int* image3, const uint32_t* tag_in,
                          float4* pos, float4* vel, int* image, uint32_t* tag, uint32_t* rtag,
-                         uint32_t ntypes, const hb2_box& box, const DomainGeom& geom, uint32_t* flags,
-                         cudaStream_t stream)
+                         uint32_t ntypes, const hb2_box& box, const DomainGeom& geom,
+                         const OwnMargin& margin, uint32_t* flags, cudaStream_t stream)
     {
     if (N == 0)
         return HB2_OK;
     snapshot_pack_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, pos3, vel3, mass, typeid_, image3,
                                                               tag_in, pos, vel, image, tag, rtag,
-                                                              ntypes, boxd(box), geom, flags);
+                                                              ntypes, boxd(box), geom, margin, flags);
     HB2_CHECK_LAUNCH("snapshot_pack_kernel");
     return HB2_OK;
     }

@@ -326,9 +326,14 @@ static hb2_status system_set(hb2_system* s, uint32_t n_in, uint64_t N_global, co
 
 static hb2_status system_stage(hb2_system* s, uint32_t N)
     {
-    const size_t words = 12 * (size_t)N; // pos3 vel3 mass typeid image3 tag
+    size_t words = 12 * (size_t)N; // pos3 vel3 mass typeid image3 tag
     if (words <= s->stage_cap)
         return HB2_OK;
+    // With a domain decomposition the owned count drifts with every migration: size the staging for the
+    // particle capacity once (page-locked allocations cost ~100 ms per 200 MB, and were being repeated
+    // whenever a rank had gained a few particles).
+    if (s->dom.active)
+        words = std::max(words, 12 * (size_t)s->cap);
     dev_free(s->d_stage);
     if (s->h_stage)
         cudaFreeHost(s->h_stage);
@@ -402,10 +407,17 @@ static hb2_status system_set_device(hb2_system* s, uint32_t N, uint64_t N_global
         geom.coord[k] = s->dom.active ? s->dom.coord[k] : 0u;
         geom.dimi[k] = geom.dimt[k] = 1;
         }
+    // Particles a rank hands back (hb2_system_get_local -> ... -> set_particles_tagged) may have drifted
+    // past a face since the last migration — at most half the list buffer before a rebuild is forced;
+    // one length unit of slack covers every list in use. The rebuild this call forces migrates them.
+    OwnMargin margin;
+    if (s->dom.active && tag)
+        for (int k = 0; k < 3; k++)
+            margin.frac[k] = std::min(0.25, 1.0 / (s->box.L[k] / (double)s->dom.grid[k]));
     HB2_TRY(snapshot_pack(N, d, d + 3 * n, d + 6 * n, (const uint32_t*)(d + 7 * n),
                           (const int*)(d + 8 * n), tag ? (const uint32_t*)(d + 11 * n) : nullptr,
                           s->pos[0], s->vel[0], s->image[0], s->tag[0], s->rtag, s->ntypes, s->box, geom,
-                          s->d_ticket + 2, st));
+                          margin, s->d_ticket + 2, st));
     uint32_t flags[2] = {0, 0};
     HB2_CUDA(cudaMemcpyAsync(flags, s->d_ticket + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     HB2_CUDA(cudaMemsetAsync(s->d_ticket + 2, 0, 2 * sizeof(uint32_t), st)); // tickets rest at zero

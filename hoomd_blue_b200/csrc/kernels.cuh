@@ -19,13 +19,19 @@ hb2_status reorder_particles(const uint32_t* d_order, uint32_t N, const float4* 
                              uint32_t* tag_out, float4* force_out, uint32_t* rtag,
                              cudaStream_t stream);
 
+// how far past a face of its domain (in units of the domain width) a particle handed to snapshot_pack
+// may lie and still count as this rank's own
+struct OwnMargin
+    {
+    double frac[3] = {0.0, 0.0, 0.0};
+    };
 // snapshot (raw arrays, all DEVICE pointers) <-> engine layout. flags[0] <- index+1 of a particle with
 // a bad type id, flags[1] <- index+1 of a particle this rank does not own (domain decompositions).
 hb2_status snapshot_pack(uint32_t N, const float* pos3, const float* vel3, const float* mass,
                          const uint32_t* typeid_, const int* image3, const uint32_t* tag_in,
                          float4* pos, float4* vel, int* image, uint32_t* tag, uint32_t* rtag,
-                         uint32_t ntypes, const hb2_box& box, const DomainGeom& geom, uint32_t* flags,
-                         cudaStream_t stream);
+                         uint32_t ntypes, const hb2_box& box, const DomainGeom& geom,
+                         const OwnMargin& margin, uint32_t* flags, cudaStream_t stream);
 hb2_status snapshot_unpack(uint32_t N, const float4* pos, const float4* vel, const int* image,
                            const uint32_t* tag, float* pos3, float* vel3, float* mass,
                            uint32_t* typeid_, int* image3, uint32_t* tag_out, bool by_tag,

@@ -487,11 +487,15 @@ class State:
     def box(self):
         return _BoxView(self._box)
 
+    def _destroy(self):
+        """Free the device state now (every rank of a decomposed system calls it)."""
+        if getattr(self, "_h", None):
+            _lib.lib().hb2_system_destroy(self._h)
+            self._h = None
+
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
-                _lib.lib().hb2_system_destroy(self._h)
-                self._h = None
+            self._destroy()
         except Exception:
             pass
 
