@@ -174,10 +174,65 @@ hb2_status launch_bond_forces(hb2_bond_kind kind, const BondArgs& a, bool accumu
     return launch_bond_ev<BondHarmonic>(a, accumulate, box, stream);
     }
 
+// ---- fp64 3-vectors for the bonded geometry (a few triplets / quadruplets per particle)
+struct V3
+    {
+    double x, y, z;
+    };
+HB2_DEVICE V3 v3(double x, double y, double z)
+    {
+    V3 r = {x, y, z};
+    return r;
+    }
+HB2_DEVICE V3 operator+(V3 a, V3 b)
+    {
+    return v3(a.x + b.x, a.y + b.y, a.z + b.z);
+    }
+HB2_DEVICE V3 operator-(V3 a, V3 b)
+    {
+    return v3(a.x - b.x, a.y - b.y, a.z - b.z);
+    }
+HB2_DEVICE V3 operator*(double s, V3 a)
+    {
+    return v3(s * a.x, s * a.y, s * a.z);
+    }
+HB2_DEVICE double dot(V3 a, V3 b)
+    {
+    return a.x * b.x + a.y * b.y + a.z * b.z;
+    }
+HB2_DEVICE V3 cross(V3 a, V3 b)
+    {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    }
+// minimum-image separation p - q of two stored positions
+HB2_DEVICE V3 sep(const BoxD& box, const float4& p, const float4& q)
+    {
+    double x = (double)p.x - (double)q.x, y = (double)p.y - (double)q.y, z = (double)p.z - (double)q.z;
+    min_image_exact(box, x, y, z);
+    return v3(x, y, z);
+    }
+// upper triangle (xx, xy, xz, yy, yz, zz) of r (x) f added to w with weight s
+HB2_DEVICE void add_outer(double (&w)[6], double s, V3 r, V3 f)
+    {
+    w[0] += s * r.x * f.x;
+    w[1] += s * r.x * f.y;
+    w[2] += s * r.x * f.z;
+    w[3] += s * r.y * f.y;
+    w[4] += s * r.y * f.z;
+    w[5] += s * r.z * f.z;
+    }
+
 // Angle forces, owner-computes: particle i walks the angles it is a member of (table keyed by tag:
-// the three member tags and `type | role << 30`), recomputes the triplet's forces exactly as the
-// reference's loop over angles does and keeps its own share (role 0: a, 1: the vertex b, 2: c).
-// KIND 0: hoomd/md/HarmonicAngleForceCompute.cc:104-258; 1: hoomd/md/CosineSqAngleForceCompute.cc.
+// the three member tags and `type | role << 30`), evaluates the triplet and keeps its own share (role
+// 0: a, 1: the vertex b, 2: c). Same potentials and conventions as the reference (KIND 0:
+// hoomd/md/HarmonicAngleForceCompute.cc:104-258, V = K/2 (theta - t0)^2 with sin(theta) clamped at
+// 0.001; KIND 1: hoomd/md/CosineSqAngleForceCompute.cc, V = K/2 (cos theta - cos t0)^2; a third of
+// the energy and of the virial to each member), written as a torque: with u = r_a - r_b and
+// w = r_c - r_b, the part of w^ perpendicular to u^ is p_a = w^ - cos(theta) u^ (length sin theta,
+// in the plane, pointing from u towards w), and the force on the end particle a is
+//     F_a = V'(theta) / (|u| sin theta) p_a        (harmonic)
+//     F_a = -dV/dcos(theta) / |u| p_a               (cosine squared: no division by sin theta)
+// likewise F_c with u and w exchanged; F_b = -(F_a + F_c); W = (u (x) F_a + w (x) F_c) / 3.
 template<int KIND, bool ACCUM>
 __global__ void __launch_bounds__(BOND_BLOCK)
     angle_force_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
@@ -209,63 +264,45 @@ __global__ void __launch_bounds__(BOND_BLOCK)
             }
         const uint32_t role = m.w >> 30, type = m.w & 0x3fffffffu;
         const float4 pa = pos[ia], pb = pos[ib], pc = pos[ic];
-        double ax = (double)pa.x - (double)pb.x, ay = (double)pa.y - (double)pb.y, az = (double)pa.z - (double)pb.z;
-        double cx = (double)pc.x - (double)pb.x, cy = (double)pc.y - (double)pb.y, cz = (double)pc.z - (double)pb.z;
-        min_image_exact(box, ax, ay, az);
-        min_image_exact(box, cx, cy, cz);
-        // The triplet's geometry is evaluated in fp64: near 0 and 180 degrees 1 - cos^2 and acos lose
-        // half of fp32's digits (chains with t0 = pi sit exactly there), and there are only a few
-        // angles per particle.
-        const double dab[3] = {ax, ay, az}, dcb[3] = {cx, cy, cz};
-        const double rsqab = dab[0] * dab[0] + dab[1] * dab[1] + dab[2] * dab[2];
-        const double rab = sqrt(rsqab);
-        const double rsqcb = dcb[0] * dcb[0] + dcb[1] * dcb[1] + dcb[2] * dcb[2];
-        const double rcb = sqrt(rsqcb);
-        double c_abbc = (dab[0] * dcb[0] + dab[1] * dcb[1] + dab[2] * dcb[2]) / (rab * rcb);
-        c_abbc = fmin(1.0, fmax(-1.0, c_abbc));
+        // fp64: near 0 and 180 degrees sin(theta) and acos lose half of fp32's digits (chains with
+        // t0 = pi sit exactly there), and there are only a few angles per particle
+        const V3 u = sep(box, pa, pb), w = sep(box, pc, pb);
+        const double lu = sqrt(dot(u, u)), lw = sqrt(dot(w, w));
+        const V3 uh = (1.0 / lu) * u, wh = (1.0 / lw) * w;
+        const double c = fmin(1.0, fmax(-1.0, dot(uh, wh)));
+        const V3 p_a = wh - c * uh, p_c = uh - c * wh;
         const double K = (double)params[HB2_BOND_PARAM_FLOATS * type],
                      t_0 = (double)params[HB2_BOND_PARAM_FLOATS * type + 1];
-        double a, eng;
+        double ga, gc, energy; // F_a = ga p_a, F_c = gc p_c
         if (KIND == 0)
             {
-            double s_abbc = sqrt(1.0 - c_abbc * c_abbc);
-            if (s_abbc < 0.001)
-                s_abbc = 0.001;
-            s_abbc = 1.0 / s_abbc;
-            const double dth = acos(c_abbc) - t_0;
-            const double tk = K * dth;
-            a = -1.0 * tk * s_abbc;
-            eng = (tk * dth) * (1.0 / 6.0);
+            const double s = fmax(sqrt(1.0 - c * c), 0.001);
+            const double dth = acos(c) - t_0;
+            ga = K * dth / (lu * s);
+            gc = K * dth / (lw * s);
+            energy = 0.5 * K * dth * dth;
             }
         else
             {
-            const double dcosth = c_abbc - cos(t_0);
-            const double tk = K * dcosth;
-            a = tk;
-            eng = (tk * dcosth) * (1.0 / 6.0);
+            const double dc = c - cos(t_0);
+            ga = -K * dc / lu;
+            gc = -K * dc / lw;
+            energy = 0.5 * K * dc * dc;
             }
-        const double a11 = a * c_abbc / rsqab, a12 = -a / (rab * rcb), a22 = a * c_abbc / rsqcb;
-        double fab[3], fcb[3];
-#pragma unroll
-        for (int d = 0; d < 3; d++)
-            {
-            fab[d] = a11 * dab[d] + a12 * dcb[d];
-            fcb[d] = a22 * dcb[d] + a12 * dab[d];
-            }
-        const double sa = role == 0 ? 1.0 : (role == 1 ? -1.0 : 0.0);
-        const double sc = role == 2 ? 1.0 : (role == 1 ? -1.0 : 0.0);
-        fx += (float)(sa * fab[0] + sc * fcb[0]);
-        fy += (float)(sa * fab[1] + sc * fcb[1]);
-        fz += (float)(sa * fab[2] + sc * fcb[2]);
-        pe += (float)eng;
+        const V3 Fa = ga * p_a, Fc = gc * p_c;
+        const V3 mine = role == 0 ? Fa : (role == 2 ? Fc : v3(0, 0, 0) - (Fa + Fc));
+        fx += (float)mine.x;
+        fy += (float)mine.y;
+        fz += (float)mine.z;
+        pe += (float)(energy * (1.0 / 3.0));
         if (virial)
             {
-            v[0] += (float)((1. / 3.) * (dab[0] * fab[0] + dcb[0] * fcb[0]));
-            v[1] += (float)((1. / 3.) * (dab[1] * fab[0] + dcb[1] * fcb[0]));
-            v[2] += (float)((1. / 3.) * (dab[2] * fab[0] + dcb[2] * fcb[0]));
-            v[3] += (float)((1. / 3.) * (dab[1] * fab[1] + dcb[1] * fcb[1]));
-            v[4] += (float)((1. / 3.) * (dab[2] * fab[1] + dcb[2] * fcb[1]));
-            v[5] += (float)((1. / 3.) * (dab[2] * fab[2] + dcb[2] * fcb[2]));
+            double wv[6] = {0, 0, 0, 0, 0, 0};
+            add_outer(wv, 1.0 / 3.0, u, Fa);
+            add_outer(wv, 1.0 / 3.0, w, Fc);
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                v[q] += (float)wv[q];
             }
         }
     if (ACCUM)
@@ -320,10 +357,19 @@ hb2_status launch_angle_forces(hb2_bond_kind kind, const BondArgs& a, const uint
     return HB2_OK;
     }
 
-// Dihedrals: KIND 0 Periodic (hoomd/md/HarmonicDihedralForceCompute.cc:104-356), KIND 1 OPLS
-// (hoomd/md/OPLSDihedralForceCompute.cc:100-352, parameters k_i / 2),
-// owner-computes like the angles: table entries hold the four member tags and `type | role << 30`;
-// the quadruplet is evaluated in fp64 with the reference's arithmetic and the particle keeps its share.
+// Dihedrals, owner-computes like the angles (table entries hold the four member tags and
+// `type | role << 30`). Same potentials and conventions as the reference — KIND 0 Periodic
+// V = k/2 (1 + d cos(n phi - phi0)) (hoomd/md/HarmonicDihedralForceCompute.cc:104-356), KIND 1 OPLS
+// V = 1/2 [k1 (1 + cos phi) + k2 (1 - cos 2 phi) + k3 (1 + cos 3 phi) + k4 (1 - cos 4 phi)]
+// (hoomd/md/OPLSDihedralForceCompute.cc:100-352); a quarter of the energy and of the virial to each
+// member — evaluated from the angle itself: with F = r_a - r_b, G = r_b - r_c, H = r_d - r_c, A = F x G
+// and B = H x G,
+//     phi = atan2((B x A) . G / |G|, A . B),
+// V and dV/dphi come straight from cos / sin of the multiples of phi, and the forces are -dV/dphi times
+// the gradients of phi (Blondel and Karplus, J. Comput. Chem. 17, 1132 (1996)):
+//     dphi/dr_a = -|G| A / A^2,  dphi/dr_d = |G| B / B^2,
+//     dphi/dr_b = -dphi/dr_a + S,  dphi/dr_c = -dphi/dr_d - S,  S = (F.G) A / (A^2 |G|) - (H.G) B / (B^2 |G|).
+// The virial is sum_i (r_i - r_b) (x) F_i (torque-free, hence symmetric).
 template<int KIND, bool ACCUM>
 __global__ void __launch_bounds__(BOND_BLOCK)
     dihedral_force_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ tag,
@@ -357,125 +403,51 @@ __global__ void __launch_bounds__(BOND_BLOCK)
             }
         const uint32_t role = tr >> 30, type = tr & 0x3fffffffu;
         const float4 pa = pos[ia], pb = pos[ib], pc = pos[ic], pd = pos[id];
-        double dab[3] = {(double)pa.x - (double)pb.x, (double)pa.y - (double)pb.y, (double)pa.z - (double)pb.z};
-        double dcb[3] = {(double)pc.x - (double)pb.x, (double)pc.y - (double)pb.y, (double)pc.z - (double)pb.z};
-        double ddc[3] = {(double)pd.x - (double)pc.x, (double)pd.y - (double)pc.y, (double)pd.z - (double)pc.z};
-        min_image_exact(box, dab[0], dab[1], dab[2]);
-        min_image_exact(box, dcb[0], dcb[1], dcb[2]);
-        min_image_exact(box, ddc[0], ddc[1], ddc[2]);
+        const V3 F = sep(box, pa, pb), G = sep(box, pb, pc), H = sep(box, pd, pc);
+        const V3 A = cross(F, G), B = cross(H, G);
+        const double A2 = dot(A, A), B2 = dot(B, B), lG = sqrt(dot(G, G));
+        const double phi = atan2(dot(cross(B, A), G) / lG, dot(A, B));
         const float* prm = params + HB2_BOND_PARAM_FLOATS * type;
-        const double prm_d[4] = {(double)prm[0], (double)prm[1], (double)prm[2], (double)prm[3]};
-
-        double dcbm[3] = {-dcb[0], -dcb[1], -dcb[2]};
-        min_image_exact(box, dcbm[0], dcbm[1], dcbm[2]);
-        const double aax = dab[1] * dcbm[2] - dab[2] * dcbm[1];
-        const double aay = dab[2] * dcbm[0] - dab[0] * dcbm[2];
-        const double aaz = dab[0] * dcbm[1] - dab[1] * dcbm[0];
-        const double bbx = ddc[1] * dcbm[2] - ddc[2] * dcbm[1];
-        const double bby = ddc[2] * dcbm[0] - ddc[0] * dcbm[2];
-        const double bbz = ddc[0] * dcbm[1] - ddc[1] * dcbm[0];
-        const double raasq = aax * aax + aay * aay + aaz * aaz;
-        const double rbbsq = bbx * bbx + bby * bby + bbz * bbz;
-        const double rgsq = dcbm[0] * dcbm[0] + dcbm[1] * dcbm[1] + dcbm[2] * dcbm[2];
-        const double rg = sqrt(rgsq);
-        double rginv = 0.0, raa2inv = 0.0, rbb2inv = 0.0;
-        if (rg > 0.0)
-            rginv = 1.0 / rg;
-        if (raasq > 0.0)
-            raa2inv = 1.0 / raasq;
-        if (rbbsq > 0.0)
-            rbb2inv = 1.0 / rbbsq;
-        const double rabinv = sqrt(raa2inv * rbb2inv);
-        double c_abcd = (aax * bbx + aay * bby + aaz * bbz) * rabinv;
-        const double s_abcd = rg * rabinv * (aax * ddc[0] + aay * ddc[1] + aaz * ddc[2]);
-        if (c_abcd > 1.0)
-            c_abcd = 1.0;
-        if (c_abcd < -1.0)
-            c_abcd = -1.0;
-        double df, eng;
-        if (KIND == 1)
+        double energy, dE; // V(phi), dV/dphi
+        if (KIND == 0)
             {
-            // hoomd/md/OPLSDihedralForceCompute.cc:236-279: p = sum_i k_i/2 (1 + (-1)^(i+1) cos(i phi)),
-            // df = dp/dphi through the Chebyshev-like recursion; the halved k_i are the parameters
-            const double k1 = prm_d[0], k2 = prm_d[1], k3 = prm_d[2], k4 = prm_d[3];
-            double ddf1 = c_abcd, df1 = s_abcd, cos_term = ddf1;
-            double p = k1 * (1.0 + cos_term);
-            df = k1 * df1;
-            ddf1 = cos_term * c_abcd - df1 * s_abcd;
-            df1 = cos_term * s_abcd + df1 * c_abcd;
-            cos_term = ddf1;
-            p += k2 * (1.0 - cos_term);
-            df += -2.0 * k2 * df1;
-            ddf1 = cos_term * c_abcd - df1 * s_abcd;
-            df1 = cos_term * s_abcd + df1 * c_abcd;
-            cos_term = ddf1;
-            p += k3 * (1.0 + cos_term);
-            df += 3.0 * k3 * df1;
-            ddf1 = cos_term * c_abcd - df1 * s_abcd;
-            df1 = cos_term * s_abcd + df1 * c_abcd;
-            cos_term = ddf1;
-            p += k4 * (1.0 - cos_term);
-            df += -4.0 * k4 * df1;
-            eng = 0.25 * p;
+            const double k = (double)prm[0], d = (double)prm[1], n = (double)prm[2], phi0 = (double)prm[3];
+            double sn, cn;
+            sincos(n * phi - phi0, &sn, &cn);
+            energy = 0.5 * k * (1.0 + d * cn);
+            dE = -0.5 * k * d * n * sn;
             }
         else
             {
-            const double K = prm_d[0], sign = prm_d[1], phi_0 = prm_d[3];
-            const int multi = (int)prm_d[2];
-            double p = 1.0, dfab = 0.0, ddfab = 0.0;
-            for (int j = 0; j < multi; j++)
-                {
-                ddfab = p * c_abcd - dfab * s_abcd;
-                dfab = p * s_abcd + dfab * c_abcd;
-                p = ddfab;
-                }
-            const double sin_phi_0 = sin(phi_0), cos_phi_0 = cos(phi_0);
-            p = p * cos_phi_0 + dfab * sin_phi_0;
-            p = p * sign;
-            dfab = dfab * cos_phi_0 - ddfab * sin_phi_0;
-            dfab = dfab * sign;
-            dfab *= (double)-multi;
-            p += 1.0;
-            if (multi == 0)
-                {
-                p = 1.0 + sign;
-                dfab = 0.0;
-                }
-            df = -K * dfab * 0.500;
-            eng = p * K * 0.125;
+            const double k1 = (double)prm[0], k2 = (double)prm[1], k3 = (double)prm[2], k4 = (double)prm[3];
+            double s1, c1, s2, c2, s3, c3, s4, c4;
+            sincos(phi, &s1, &c1);
+            sincos(2.0 * phi, &s2, &c2);
+            sincos(3.0 * phi, &s3, &c3);
+            sincos(4.0 * phi, &s4, &c4);
+            energy = 0.5 * (k1 * (1.0 + c1) + k2 * (1.0 - c2) + k3 * (1.0 + c3) + k4 * (1.0 - c4));
+            dE = 0.5 * (-k1 * s1 + 2.0 * k2 * s2 - 3.0 * k3 * s3 + 4.0 * k4 * s4);
             }
-        const double fg = dab[0] * dcbm[0] + dab[1] * dcbm[1] + dab[2] * dcbm[2];
-        const double hg = ddc[0] * dcbm[0] + ddc[1] * dcbm[1] + ddc[2] * dcbm[2];
-        const double fga = fg * raa2inv * rginv, hgb = hg * rbb2inv * rginv;
-        const double gaa = -raa2inv * rg, gbb = rbb2inv * rg;
-        const double dtf[3] = {gaa * aax, gaa * aay, gaa * aaz};
-        const double dtg[3] = {fga * aax - hgb * bbx, fga * aay - hgb * bby, fga * aaz - hgb * bbz};
-        const double dth[3] = {gbb * bbx, gbb * bby, gbb * bbz};
-        double ffa[3], ffb[3], ffc[3], ffd[3];
-        for (int q = 0; q < 3; q++)
-            {
-            const double s2 = df * dtg[q];
-            ffa[q] = df * dtf[q];
-            ffb[q] = s2 - ffa[q];
-            ffd[q] = df * dth[q];
-            ffc[q] = -s2 - ffd[q];
-            }
-        const double vir[6] = {(1. / 4.) * (dab[0] * ffa[0] + dcb[0] * ffc[0] + (ddc[0] + dcb[0]) * ffd[0]),
-                               (1. / 4.) * (dab[1] * ffa[0] + dcb[1] * ffc[0] + (ddc[1] + dcb[1]) * ffd[0]),
-                               (1. / 4.) * (dab[2] * ffa[0] + dcb[2] * ffc[0] + (ddc[2] + dcb[2]) * ffd[0]),
-                               (1. / 4.) * (dab[1] * ffa[1] + dcb[1] * ffc[1] + (ddc[1] + dcb[1]) * ffd[1]),
-                               (1. / 4.) * (dab[2] * ffa[1] + dcb[2] * ffc[1] + (ddc[2] + dcb[2]) * ffd[1]),
-                               (1. / 4.) * (dab[2] * ffa[2] + dcb[2] * ffc[2] + (ddc[2] + dcb[2]) * ffd[2])};
-
-        const double* mine = role == 0 ? ffa : (role == 1 ? ffb : (role == 2 ? ffc : ffd));
-        fx += (float)mine[0];
-        fy += (float)mine[1];
-        fz += (float)mine[2];
-        pe += (float)eng;
+        const V3 ga = (-lG / A2) * A, gd = (lG / B2) * B;
+        const V3 S = (dot(F, G) / (A2 * lG)) * A - (dot(H, G) / (B2 * lG)) * B;
+        const V3 Fa = (-dE) * ga, Fd = (-dE) * gd;
+        const V3 Fb = (-dE) * (S - ga), Fc = dE * (gd + S);
+        const V3 mine = role == 0 ? Fa : (role == 1 ? Fb : (role == 2 ? Fc : Fd));
+        fx += (float)mine.x;
+        fy += (float)mine.y;
+        fz += (float)mine.z;
+        pe += (float)(0.25 * energy);
         if (virial)
+            {
+            // relative to b: r_a - r_b = F, r_c - r_b = -G, r_d - r_b = H - G
+            double wv[6] = {0, 0, 0, 0, 0, 0};
+            add_outer(wv, 0.25, F, Fa);
+            add_outer(wv, -0.25, G, Fc);
+            add_outer(wv, 0.25, H - G, Fd);
 #pragma unroll
             for (int q = 0; q < 6; q++)
-                v[q] += (float)vir[q];
+                v[q] += (float)wv[q];
+            }
         }
     if (ACCUM)
         {

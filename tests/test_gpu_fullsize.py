@@ -158,10 +158,11 @@ def test_c2_lj_1m(hoomd, tmp_path):
     Lf = float(L)
 
     def fresh():
-        return lj_system(hoomd, p, v, L, params={("A", "A"): (1.0, 1.0)}, r_cut={("A", "A"): 2.5})
+        s, c, l = lj_system(hoomd, p, v, L, params={("A", "A"): (1.0, 1.0)}, r_cut={("A", "A"): 2.5})
+        s.always_compute_pressure = True  # (both copies: the virial variant is another instantiation)
+        return s, c, l
 
     s1, c1, l1 = fresh()
-    s1.always_compute_pressure = True
     s1.run(0)
     # the configured size against the reference itself: pair set bit-exact, forces, energy, virial
     ref = reference_run0(tmp_path, Lf, p, v, None, ("A",), "lj", {("A", "A"): (1.0, 1.0, 2.5)})
@@ -284,6 +285,7 @@ def test_c5_dpd_8m(hoomd, tmp_path):
     def make(seed):
         sim = hoomd.Simulation(device=hoomd.device.GPU(), seed=seed)
         sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays([L, L, L, 0, 0, 0], pos, vel))
+        sim.always_compute_pressure = True  # (every copy: the virial variant is another instantiation)
         cell = hoomd.md.nlist.Cell(buffer=0.4)
         dpd = hoomd.md.pair.DPD(nlist=cell, kT=1.0, default_r_cut=1.0)
         dpd.params[("A", "A")] = dict(A=25.0, gamma=4.5)
@@ -292,7 +294,6 @@ def test_c5_dpd_8m(hoomd, tmp_path):
         return sim, cell, dpd
 
     s1, c1, d1 = make(5)
-    s1.always_compute_pressure = True
     s1.run(0)
     # the configured size against the reference: pair set, and forces INCLUDING the random force
     # (same seed, timestep and tags => the same per-pair Philox draws)
