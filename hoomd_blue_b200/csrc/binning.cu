@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "comm.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 
 namespace hb2
     {
@@ -18,6 +19,31 @@ namespace hb2
 // so that 8 consecutive particles (one 128-byte line of float4 positions) form a compact blob and the
 // force kernel's position gathers share lines (DESIGN.md "gather locality").
 constexpr int SUB_BITS = 6;
+
+// Cell order along a Morton (Z-order) curve over the cell coordinates, up to 8 bits per axis: spatially
+// close cells are close in memory, where the row-major order puts the y neighbours of a cell a whole x-row
+// and the z neighbours a whole xy-plane away (SFCPackTuner's role, hoomd/SFCPackTuner.cc:541-649, at
+// cell granularity; DESIGN.md "cell order").
+HB2_HOSTDEVICE uint32_t spread3(uint32_t v) // 8 bits -> every third bit
+    {
+    v &= 0xffu;
+    v = (v | (v << 8)) & 0x00f00fu;
+    v = (v | (v << 4)) & 0x0c30c3u;
+    v = (v | (v << 2)) & 0x249249u;
+    return v;
+    }
+HB2_HOSTDEVICE uint32_t compact3(uint32_t v)
+    {
+    v &= 0x249249u;
+    v = (v | (v >> 2)) & 0x0c30c3u;
+    v = (v | (v >> 4)) & 0x00f00fu;
+    v = (v | (v >> 8)) & 0xffu;
+    return v;
+    }
+HB2_HOSTDEVICE uint32_t morton_cell(uint32_t x, uint32_t y, uint32_t z)
+    {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+    }
 
 HB2_DEVICE uint32_t morton2x3(uint32_t x, uint32_t y, uint32_t z)
     {
@@ -35,7 +61,7 @@ HB2_DEVICE uint32_t morton2x3(uint32_t x, uint32_t y, uint32_t z)
 // owned particles in [0, N_owned) and ghosts behind them, both in cell order.
 __global__ void __launch_bounds__(256)
     bin_kernel(const float4* __restrict__ pos, uint32_t N, uint32_t N_owned, BoxD box, DomainGeom geom,
-               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+               int curve, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                uint32_t* __restrict__ conditions)
     {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,9 +134,12 @@ __global__ void __launch_bounds__(256)
         if (out)
             atomicMax(&conditions[2], i + 1);
         else
-            key = ((((uint32_t)ib[2] * geom.dimt[1] + (uint32_t)ib[1]) * geom.dimt[0] + (uint32_t)ib[0])
-                   << SUB_BITS)
-                  | morton2x3(sb[0], sb[1], sb[2]);
+            {
+            const uint32_t cell
+                = curve ? morton_cell((uint32_t)ib[0], (uint32_t)ib[1], (uint32_t)ib[2])
+                        : ((uint32_t)ib[2] * geom.dimt[1] + (uint32_t)ib[1]) * geom.dimt[0] + (uint32_t)ib[0];
+            key = (cell << SUB_BITS) | morton2x3(sb[0], sb[1], sb[2]);
+            }
         }
     if (i >= N_owned)
         key |= 0x80000000u;
@@ -122,14 +151,16 @@ __global__ void __launch_bounds__(256)
 // previous slot holds another cell (or the other side of the owned / ghost split) and closes the
 // previous one. Both arrays are zeroed first, so empty cells read as [0, 0).
 __global__ void __launch_bounds__(256)
-    cell_range_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t N,
-                      uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end)
+    cell_range_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t N, int curve, uint32_t dimx,
+                      uint32_t dimy, uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end)
     {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N)
         return;
     const uint32_t key = keys_sorted[k] >> SUB_BITS;
-    const uint32_t cell = key & ((1u << (31 - SUB_BITS)) - 1u);
+    uint32_t cell = key & ((1u << (31 - SUB_BITS)) - 1u);
+    if (curve) // the tables stay indexed by the row-major cell id
+        cell = (compact3(cell >> 2) * dimy + compact3(cell >> 1)) * dimx + compact3(cell);
     if (k == 0 || (keys_sorted[k - 1] >> SUB_BITS) != key)
         cell_start[cell] = k;
     if (k == N - 1 || (keys_sorted[k + 1] >> SUB_BITS) != key)
@@ -264,14 +295,30 @@ hb2_status snapshot_unpack(uint32_t N, const float4* pos, const float4* vel, con
     return HB2_OK;
     }
 
-static inline int key_bits(uint32_t Nc, bool ghosts)
+static inline int key_bits(uint32_t max_cell_code, bool ghosts)
     {
     if (ghosts)
         return 32; // bit 31 splits owned / ghost particles
     int b = 1;
-    while (b < 32 && (1ull << b) < (unsigned long long)Nc)
+    while (b < 32 && (1ull << b) <= (unsigned long long)max_cell_code)
         b++;
     return b + SUB_BITS;
+    }
+
+// HB2_CELL_ORDER=rowmajor|morton (default morton when every axis has at most 256 cells)
+static int cell_curve(const DomainGeom& geom, int requested)
+    {
+    static int env = -1;
+    if (env < 0)
+        {
+        const char* e = getenv("HB2_CELL_ORDER");
+        env = (e && e[0] == 'r') ? 0 : 1;
+        }
+    int curve = requested >= 0 ? requested : env;
+    for (int d = 0; d < 3; d++)
+        if (geom.dimt[d] > 256)
+            curve = 0;
+    return curve;
     }
 
 size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc)
@@ -287,9 +334,11 @@ size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc)
 hb2_status compute_cell_order(const float4* d_pos, uint32_t N, uint32_t N_owned, const hb2_box& box,
                               const DomainGeom& geom, uint32_t* d_order, uint32_t* d_cell_start,
                               uint32_t* d_cell_end, uint32_t* d_conditions, void* d_tmp,
-                              size_t tmp_bytes, cudaStream_t stream)
+                              size_t tmp_bytes, cudaStream_t stream, int curve_request)
     {
     const uint32_t Nc = geom.dimt[0] * geom.dimt[1] * geom.dimt[2];
+    const int curve = cell_curve(geom, curve_request);
+    const uint32_t max_code = curve ? morton_cell(geom.dimt[0] - 1, geom.dimt[1] - 1, geom.dimt[2] - 1) : Nc - 1;
     if (tmp_bytes < cell_order_tmp_bytes(N, Nc))
         {
         set_error("compute_cell_order: scratch buffer too small");
@@ -307,18 +356,18 @@ hb2_status compute_cell_order(const float4* d_pos, uint32_t N, uint32_t N_owned,
     HB2_CUDA(cudaMemsetAsync(d_cell_end, 0, sizeof(uint32_t) * (size_t)Nc, stream));
     if (N > 0)
         {
-        bin_kernel<<<(N + 255) / 256, 256, 0, stream>>>(d_pos, N, N_owned, boxd(box), geom, keys,
+        bin_kernel<<<(N + 255) / 256, 256, 0, stream>>>(d_pos, N, N_owned, boxd(box), geom, curve, keys,
                                                         d_order, d_conditions);
         HB2_CHECK_LAUNCH("bin_kernel");
         cub::DoubleBuffer<uint32_t> k(keys, keys_alt), v(d_order, vals_alt);
         HB2_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k, v, (int)N, 0,
-                                                 key_bits(Nc, N_owned < N), stream));
+                                                 key_bits(max_code, N_owned < N), stream));
         count_launch(3);
         if (v.Current() != d_order)
             HB2_CUDA(cudaMemcpyAsync(d_order, v.Current(), (size_t)N * sizeof(uint32_t),
                                      cudaMemcpyDeviceToDevice, stream));
-        cell_range_kernel<<<(N + 255) / 256, 256, 0, stream>>>(k.Current(), N, d_cell_start,
-                                                               d_cell_end);
+        cell_range_kernel<<<(N + 255) / 256, 256, 0, stream>>>(k.Current(), N, curve, geom.dimt[0],
+                                                               geom.dimt[1], d_cell_start, d_cell_end);
         HB2_CHECK_LAUNCH("cell_range_kernel");
         }
     return HB2_OK;

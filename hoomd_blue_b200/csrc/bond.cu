@@ -419,7 +419,9 @@ __global__ void __launch_bounds__(BOND_BLOCK)
             }
         else
             {
-            const double k1 = (double)prm[0], k2 = (double)prm[1], k3 = (double)prm[2], k4 = (double)prm[3];
+            // (the host packs the OPLS coefficients as k_i / 2, like hoomd/md/OPLSDihedralForceCompute.cc:73-78)
+            const double k1 = 2.0 * (double)prm[0], k2 = 2.0 * (double)prm[1], k3 = 2.0 * (double)prm[2],
+                         k4 = 2.0 * (double)prm[3];
             double s1, c1, s2, c2, s3, c3, s4, c4;
             sincos(phi, &s1, &c1);
             sincos(2.0 * phi, &s2, &c2);

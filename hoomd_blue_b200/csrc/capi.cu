@@ -39,7 +39,7 @@ extern "C" hb2_status hb2_gpu_compute_cell_order(const float* d_pos4, uint32_t N
         }
     return compute_cell_order((const float4*)d_pos4, N, N, *box, periodic_geom(dim), d_order,
                               d_cell_start, d_cell_end, d_conditions, d_tmp, *tmp_bytes,
-                              (cudaStream_t)stream);
+                              (cudaStream_t)stream, 0);
     }
 
 extern "C" hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_total,

@@ -12,7 +12,9 @@ size_t cell_order_tmp_bytes(uint32_t N, uint32_t Nc);
 hb2_status compute_cell_order(const float4* d_pos, uint32_t N, uint32_t N_owned, const hb2_box& box,
                               const DomainGeom& geom, uint32_t* d_order, uint32_t* d_cell_start,
                               uint32_t* d_cell_end, uint32_t* d_conditions, void* d_tmp,
-                              size_t tmp_bytes, cudaStream_t stream);
+                              size_t tmp_bytes, cudaStream_t stream, int curve_request = -1);
+// curve_request: -1 the engine's choice (HB2_CELL_ORDER, default a Morton curve over the cells), 0 cells
+// in row-major order, 1 Morton
 hb2_status reorder_particles(const uint32_t* d_order, uint32_t N, const float4* pos_in,
                              const float4* vel_in, const int* img_in, const uint32_t* tag_in,
                              const float4* force_in, float4* pos_out, float4* vel_out, int* img_out,
