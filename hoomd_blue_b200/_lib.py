@@ -93,6 +93,9 @@ def _declare(L):
     L.hb2_nlist_set_buffer.argtypes = [_vp, C.c_double]
     L.hb2_nlist_compute.argtypes = [_vp]
     L.hb2_nlist_num_builds.argtypes = [_vp]
+    L.hb2_nlist_set_r_cut.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double]
+    L.hb2_nlist_device_arrays.argtypes = [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.hb2_nlist_num_builds.restype = C.c_uint64
     L.hb2_nlist_shortest_rebuild.argtypes = [_vp]
     L.hb2_nlist_shortest_rebuild.restype = C.c_uint64

@@ -663,7 +663,11 @@ hb2_status hb2_nlist::update_r_list()
     {
     // hoomd/md/NeighborList.cc:452-529: r_cut = max over consumers; r_listsq = (r_cut + buff)^2 or 0
     const uint32_t nt = sys->ntypes;
+    // the list's own r_cut matrix (hoomd.md.nlist.NeighborList.r_cut, hoomd/md/nlist.py:127-131) is
+    // one more consumer matrix
     r_cut.assign((size_t)nt * nt, 0.0);
+    if (base_r_cut.size() == r_cut.size())
+        r_cut = base_r_cut;
     for (auto* p : consumers)
         for (size_t q = 0; q < r_cut.size(); q++)
             r_cut[q] = std::max(r_cut[q], p->r_cut[q]);
@@ -992,6 +996,44 @@ extern "C" hb2_status hb2_nlist_set_buffer(hb2_nlist* nl, double buffer)
     nl->params_dirty = true;
     nl->force_update = true;
     nl->pitch = 0; // re-estimate
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_nlist_set_r_cut(hb2_nlist* nl, uint32_t ti, uint32_t tj, double r_cut)
+    {
+    if (!nl || ti >= nl->sys->ntypes || tj >= nl->sys->ntypes || r_cut < 0)
+        {
+        set_error("hb2_nlist_set_r_cut: bad arguments");
+        return HB2_ERR_INVALID;
+        }
+    const uint32_t nt = nl->sys->ntypes;
+    if (nl->base_r_cut.size() != (size_t)nt * nt)
+        nl->base_r_cut.assign((size_t)nt * nt, 0.0);
+    nl->base_r_cut[(size_t)tj * nt + ti] = nl->base_r_cut[(size_t)ti * nt + tj] = r_cut;
+    nl->params_dirty = true;
+    nl->force_update = true;
+    return HB2_OK;
+    }
+
+// The list of the last build as the reference lays it out (hoomd/md/NeighborList.h:662-722
+// LocalNeighborListData: head_list, n_neigh, nlist): device pointers valid until the next rebuild. Row i
+// starts at i * pitch (the head list is implicit), entries in local particle indices.
+extern "C" hb2_status hb2_nlist_device_arrays(hb2_nlist* nl, const uint32_t** d_n_neigh,
+                                              const uint32_t** d_nlist, uint32_t* pitch, uint32_t* n_rows)
+    {
+    if (!nl || !d_n_neigh || !d_nlist || !pitch || !n_rows)
+        return HB2_ERR_INVALID;
+    if (!nl->has_list)
+        {
+        set_error("nlist: no neighbour list has been built yet");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(nl->sys->device));
+    HB2_CUDA(cudaStreamSynchronize(nl->sys->stream));
+    *d_n_neigh = nl->d_n_neigh;
+    *d_nlist = nl->d_nlist;
+    *pitch = nl->pitch;
+    *n_rows = nl->sys->N;
     return HB2_OK;
     }
 

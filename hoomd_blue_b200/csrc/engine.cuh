@@ -117,6 +117,7 @@ struct hb2_nlist
 
     std::vector<hb2_pair*> consumers;
     std::vector<double> r_cut, r_listsq, rcut_max;
+    std::vector<double> base_r_cut; // the list's own r_cut matrix (empty: all zero)
     double rcut_max_max = 0.0, r_list_min = 0.0;
     bool params_dirty = true;
 

@@ -6,6 +6,57 @@ import numpy as np
 from .. import _lib
 from .. import communicator as _comm
 from .._lib import check, ptr
+from .typeparam import TypePairDict
+
+
+class _DeviceArray:
+    """A read-only view of device memory through __cuda_array_interface__ (version 3): CuPy, PyTorch
+    (torch.as_tensor) and Numba wrap it without a copy, like the reference's HOOMDGPUArray."""
+
+    def __init__(self, pointer, shape, typestr="<i4"):  # int32 view of the uint32 data (indices < 2^31)
+        self.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr=typestr,
+                                             data=(int(pointer), True), version=3, strides=None)
+        self.shape = tuple(int(s) for s in shape)
+
+
+class LocalNeighborListData:
+    """hoomd.md.data.LocalNeighborListData{CPU,GPU} for a full list (hoomd/md/nlist.py:154-268,
+    hoomd/md/NeighborList.h:662-722): `head_list[i]` is the offset of particle i's row in `nlist`,
+    `n_neigh[i]` its length; indices are local (rank-local, cell-ordered) particle indices — the
+    state's local snapshot gives the tags. `half_nlist` is False. Use as a context manager."""
+
+    def __init__(self, nl, on_device):
+        L = _lib.lib()
+        d_nn, d_nl = C.c_void_p(), C.c_void_p()
+        pitch, rows = C.c_uint32(0), C.c_uint32(0)
+        check(L.hb2_nlist_device_arrays(nl._h, C.byref(d_nn), C.byref(d_nl), C.byref(pitch), C.byref(rows)))
+        self.half_nlist = False
+        n, p = rows.value, pitch.value
+        if on_device:
+            self.n_neigh = _DeviceArray(d_nn.value, (n,))
+            self.nlist = _DeviceArray(d_nl.value, (n * p,))
+            self._head = None
+        else:
+            import torch  # device memory plumbing only
+            dev = torch.device("cuda", nl._sim.device.gpu_id)
+            self.n_neigh = torch.as_tensor(_DeviceArray(d_nn.value, (n,)), device=dev).cpu().numpy().view(np.uint32)
+            self.nlist = torch.as_tensor(_DeviceArray(d_nl.value, (n * p,)), device=dev).cpu().numpy().view(np.uint32)
+            self.n_neigh.flags.writeable = self.nlist.flags.writeable = False
+        self.head_list = np.arange(n, dtype=np.uint64) * np.uint64(p)
+        self.head_list.flags.writeable = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _nonneg(v):
+    v = float(v)
+    if v < 0:
+        raise ValueError("r_cut must be non-negative")
+    return v
 
 
 class NeighborList:
@@ -23,6 +74,10 @@ class NeighborList:
         self.rebuild_check_delay = int(rebuild_check_delay)
         self.check_dist = bool(check_dist)
         self.default_r_cut = float(default_r_cut)
+        # hoomd/md/nlist.py:127-131: the list's own r_cut per unordered type pair; the effective cut-off
+        # is the maximum over this matrix and the pair forces attached to the list
+        self.r_cut = TypePairDict("r_cut", lambda v: _nonneg(v), float(default_r_cut))
+        self.r_cut._on_change = self._sync_r_cut
         self._h = None
         self._sim = None
 
@@ -40,10 +95,33 @@ class NeighborList:
                                           self.rebuild_check_delay, int(self.check_dist)))
         self._h = h
         self._sim = sim
+        self._sync_r_cut()
         check(_lib.lib().hb2_nlist_set_exclusions(h, int("bond" in self.exclusions)))
         extra = self._extra_exclusion_pairs(sim.state)
         if len(extra):
             check(_lib.lib().hb2_nlist_set_exclusion_pairs(h, len(extra), ptr(extra, C.c_uint32)))
+
+    def _sync_r_cut(self):
+        if self._h is None:
+            return
+        types = self._sim.state.particle_types
+        for i, a in enumerate(types):
+            for j, b in enumerate(types):
+                if j >= i:
+                    check(_lib.lib().hb2_nlist_set_r_cut(self._h, i, j, self.r_cut[(a, b)]))
+
+    @property
+    def cpu_local_nlist_arrays(self):
+        """Host copies of the list of the last build (hoomd/md/nlist.py:154-209)."""
+        self._need()
+        return LocalNeighborListData(self, on_device=False)
+
+    @property
+    def gpu_local_nlist_arrays(self):
+        """Zero-copy device views (__cuda_array_interface__) of the list of the last build
+        (hoomd/md/nlist.py:211-268); valid until the next rebuild."""
+        self._need()
+        return LocalNeighborListData(self, on_device=True)
 
     def _extra_exclusion_pairs(self, state):
         """Pairs (by tag) that 'angle' and '1-3' add (hoomd/md/NeighborList.cc:881-909: the two end

@@ -251,6 +251,15 @@ hb2_status hb2_nlist_create(hb2_nlist** out, hb2_system* sys, double buffer,
                             uint32_t rebuild_check_delay, int check_dist);
 void hb2_nlist_destroy(hb2_nlist* nl);
 hb2_status hb2_nlist_set_buffer(hb2_nlist* nl, double buffer);
+/* hoomd.md.nlist.NeighborList.r_cut (hoomd/md/nlist.py:127-131): the list's own cut-off for the unordered
+ * type pair; the effective r_cut is the maximum over this matrix and every pair force on the list
+ * (hoomd/md/NeighborList.cc:452-529). */
+hb2_status hb2_nlist_set_r_cut(hb2_nlist* nl, uint32_t ti, uint32_t tj, double r_cut);
+/* cpu/gpu_local_nlist_arrays (hoomd/md/nlist.py:154-268, hoomd/md/NeighborList.h:662-722): device pointers
+ * to n_neigh (n_rows entries) and nlist (row i at i * pitch, local particle indices) of the last build,
+ * valid until the next rebuild; the head list is i * pitch. */
+hb2_status hb2_nlist_device_arrays(hb2_nlist* nl, const uint32_t** d_n_neigh, const uint32_t** d_nlist,
+                                   uint32_t* pitch, uint32_t* n_rows);
 /* Force a (re)build now at the current positions (NeighborList::compute with m_force_update,
  * hoomd/md/NeighborList.cc:363-435). */
 hb2_status hb2_nlist_compute(hb2_nlist* nl);

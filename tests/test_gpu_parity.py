@@ -850,3 +850,34 @@ def test_num_builds_covers_the_whole_run(hoomd, golden_dir):
     sim2.operations.writers.append(hoomd.write.Table(hoomd.trigger.Periodic(1), logger, io.StringIO("")))
     sim2.run(40)
     assert (cell2.num_builds, cell2.shortest_rebuild) == want and want[0] >= 2
+
+
+def test_nlist_r_cut_and_local_arrays(hoomd, oracle, golden_dir):
+    """hoomd.md.nlist.NeighborList.r_cut (hoomd/md/nlist.py:127-131): the list's own cut-off widens the
+    list beyond the pair force's (maximum over both, hoomd/md/NeighborList.cc:452-529) without changing
+    the forces; cpu/gpu_local_nlist_arrays (hoomd/md/nlist.py:154-268) expose head_list / n_neigh / nlist
+    of that build in local indices."""
+    import torch
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    N = len(fx["pos"])
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "none")
+    cell.r_cut[("A", "A")] = 3.0
+    sim.run(0)
+    box = oracle.make_box([float(v) for v in fx["L"]])
+    types = np.zeros(N, dtype=np.uint32)
+    nn, head, nl, _ = oracle.nlist(box, fx["pos"], types, [3.0], 0.4, full=True)
+    assert np.array_equal(canon_pairs(cell.pair_list), oracle.pair_set(nn, head, nl))
+    check_forces(lj, fx, "none_")
+    # local arrays: rows in local (cell-ordered) indices; map to tags through the local snapshot
+    loc_tag = np.asarray(list(sim.state._get_local())[0])
+    with cell.cpu_local_nlist_arrays as data:
+        assert not data.half_nlist and len(data.n_neigh) == N
+        i = np.repeat(np.arange(N), data.n_neigh)
+        k = np.concatenate([np.arange(h, h + n) for h, n in zip(data.head_list, data.n_neigh)])
+        j = data.nlist[k.astype(np.int64)]
+        pl = np.stack([loc_tag[i], loc_tag[j]], axis=1)
+        assert np.array_equal(canon_pairs(pl), oracle.pair_set(nn, head, nl))
+        assert int(data.n_neigh.sum()) == 2 * len(oracle.pair_set(nn, head, nl))
+    with cell.gpu_local_nlist_arrays as gdata:
+        d_nn = torch.as_tensor(gdata.n_neigh, device="cuda")
+        assert np.array_equal(d_nn.cpu().numpy().view(np.uint32), data.n_neigh)
