@@ -1,8 +1,11 @@
 """Generate tests/golden/*.npz from the REFERENCE ITSELF (HOOMD-blue v4.8.2 CPU build, fp64).
 
-Run in the build container only (needs the reference build, default /tmp/oracle/build — the
-driver-side CPU build described in SURVEY.md §8(c); override with HOOMD_REF_BUILD). The GPU box has
-neither /root/reference nor this build: tests read only the committed .npz/.json files.
+Needs the reference build that `baseline/build_ref.sh` produces from /root/reference into the
+git-ignored baseline/_ref (SURVEY.md §8(c) recipe; override the location with HOOMD_REF_BUILD). Tests
+read only the committed .npz/.json files; `tests/ref_run0.py` re-runs the reference on a frame when the
+build travelled to the GPU box. (The fixtures committed in round 1 were made with the survey's
+pre-session build of the same sources; the rebuilt reference reproduces them bit for bit: lj_2k
+none_force differs by 0.0 from a fresh run(0).)
 
     python tests/golden/make_golden.py [--only NAME]
 
@@ -24,7 +27,9 @@ import json
 import os
 import sys
 
-BUILD = os.environ.get("HOOMD_REF_BUILD", "/tmp/oracle/build")
+BUILD = os.environ.get("HOOMD_REF_BUILD",
+                       os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                                    "baseline", "_ref"))
 sys.path.insert(0, BUILD)
 # hoomd must be imported BEFORE numpy in this container (libstdc++ load order; SURVEY.md §4 note)
 import hoomd  # noqa: E402

@@ -332,6 +332,23 @@ def test_langevin_trajectory_vs_oracle(hoomd, oracle, golden_dir):
     assert np.max(np.abs(s.particles.velocity - vel)) < 2e-3
     # and it is not the NVE trajectory
     assert np.max(np.abs(s.particles.velocity - fx["nve_vel"])) > 0.05
+    # the REFERENCE's own Langevin trajectory from the same frame and seed (tests/golden/langevin_2k.npz,
+    # made by tests/golden/make_langevin.py): same noise stream, fp32 vs fp64 arithmetic
+    ref = dict(np.load(os.path.join(golden_dir, "langevin_2k.npz")))
+    d = s.particles.position.astype(np.float64) - ref["pos_20"]
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 2e-4
+    assert np.max(np.abs(s.particles.velocity - ref["vel_20"])) < 2e-3
+    sim1 = make_sim(hoomd, fx["L"], fx["pos"], fx["vel"], seed=11)
+    cell1 = hoomd.md.nlist.Cell(buffer=0.4)
+    lj1 = hoomd.md.pair.LJ(nlist=cell1, default_r_cut=2.5)
+    lj1.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+    lv1 = hoomd.md.methods.Langevin(filter=hoomd.filter.All(), kT=1.5, default_gamma=2.0)
+    sim1.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[lv1], forces=[lj1])
+    sim1.run(1)
+    s1 = sim1.state.get_snapshot()
+    # one step: the random kick is ~0.1 per component; agreement to 1e-5 means the same draws
+    assert np.max(np.abs(s1.particles.velocity - ref["vel_1"])) < 1e-5
 
 
 def test_thermalize_particle_momenta(hoomd):
@@ -576,6 +593,48 @@ def test_nve_drift_1e5(hoomd, golden_dir):
     assert abs(drift) <= max(5.0 * abs(drift_ref), 3e-3)
     # same rebuild cadence (identical criterion, different chaotic trajectory)
     assert abs(builds - int(ref["builds"])) <= 0.02 * int(ref["builds"])
+
+
+def test_nve_drift_1e5_reference_8k(hoomd, golden_dir):
+    """SURVEY.md 8(d) gate 4 as specified: NVE (thermostat=None) over 1e5 steps at N = 8,000 against the
+    trace of the REFERENCE ITSELF from the same frame (tests/golden/nve_drift_8k.npz, made by
+    tests/golden/make_drift_ref.py with the HOOMD-blue CPU build under baseline/_ref). Trajectories
+    diverge chaotically; what compares is (a) the chunk-to-chunk energy noise — the integrator and the
+    truncated, shifted force are the same — (b) the long-time drift, measured between the means of the
+    first and the last 20 samples so that the noise averages out, and (c) the rebuild cadence."""
+    ref = dict(np.load(os.path.join(golden_dir, "nve_drift_8k.npz")))
+    N = len(ref["pos"])
+    assert N == 8000
+    L = float(ref["L"])
+    fx = dict(L=np.array([L, L, L], dtype=np.float32), pos=ref["pos"], vel=ref["vel"])
+    sim, cell, lj = lj_sim(hoomd, fx, {("A", "A"): (1.0, 1.0)}, {("A", "A"): 2.5}, 0.4, "shift")
+    sim.run(0)
+    integ = sim.operations.integrator
+    every = int(ref["every"])
+    e_ref = (ref["ke"] + ref["pe"]) / N
+    ke, pe, _ = integ._thermo()
+    e = [(ke + pe) / N]
+    builds = 0
+    for _ in range(len(e_ref) - 1):
+        sim.run(every)
+        builds += cell.num_builds
+        ke, pe, _ = integ._thermo()
+        e.append((ke + pe) / N)
+    e = np.array(e)
+    # same starting energy (same frame, fp32 vs fp64 force pass)
+    assert abs(e[0] - e_ref[0]) <= 1e-6 * abs(e_ref[0])
+    fluct, fluct_ref = np.std(np.diff(e)), np.std(np.diff(e_ref))
+    drift = e[-20:].mean() - e[:20].mean()
+    drift_ref = e_ref[-20:].mean() - e_ref[:20].mean()
+    noise_ref = np.std(e_ref - np.polyval(np.polyfit(np.arange(len(e_ref)), e_ref, 1), np.arange(len(e_ref))))
+    print(f"NVE 1e5 steps N=8000: drift/N gpu {drift:.2e} reference {drift_ref:.2e} (reference noise "
+          f"{noise_ref:.2e}); chunk-to-chunk sigma gpu {fluct:.2e} reference {fluct_ref:.2e}; builds gpu "
+          f"{builds} reference {int(ref['builds'])}")
+    assert fluct <= 1.5 * fluct_ref
+    # kT = 1.5: a drift of 1e-3 per particle is 4.4e-4 of the kinetic energy per particle over 1e5 steps;
+    # the fp64 reference itself wanders by its noise (~1e-4)
+    assert abs(drift) <= 1e-3
+    assert abs(builds - int(ref["builds"])) <= 0.01 * int(ref["builds"])
 
 
 def test_snapshot_roundtrip_pageable_and_pinned(hoomd):

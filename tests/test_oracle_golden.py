@@ -382,3 +382,51 @@ def test_host_rng_and_thermalize(oracle):
     perm = g.permutation(n)
     assert np.allclose(rng.thermal_velocities(tg[perm], mass[perm], 1.5, 7, 0), v[perm], atol=1e-12)
     assert not np.allclose(rng.thermal_velocities(tg, mass, 1.5, 7, 1), v)
+
+
+def test_langevin_noise_stream_pinned_by_the_reference(oracle, golden_dir):
+    """tests/golden/langevin_2k.npz was produced by the reference itself (tests/golden/make_langevin.py,
+    HOOMD-blue CPU build under baseline/_ref): Langevin(kT = 1.5, gamma = 2) on the 2k LJ frame, seed 11.
+    The oracle's restatement (orc_step_two_langevin inside orc run) must reproduce the reference's
+    velocities after ONE step to fp64 round-off — that pins the Philox key / counter layout, the three
+    draws per particle and their order — and track it over 20 steps."""
+    import os
+    fx = dict(np.load(os.path.join(golden_dir, "lj_2k.npz")))
+    ref = dict(np.load(os.path.join(golden_dir, "langevin_2k.npz")))
+    n = len(fx["pos"])
+    box = oracle.make_box([float(v) for v in fx["L"]])
+    L = fx["L"].astype(np.float64)
+
+    def run(steps):
+        pos, vel = fx["pos"].astype(np.float64), fx["vel"].astype(np.float64)
+        img = np.zeros((n, 3), dtype=np.int32)
+        mass, types, tags = np.ones(n), np.zeros(n, dtype=np.uint32), np.arange(n, dtype=np.uint32)
+        nn, head, nl, _ = oracle.nlist(box, pos, types, [2.5], 0.4, full=True)
+        f0, _ = oracle.pair_lj(box, pos, types, nn, head, nl, [[1.0, 1.0]], [2.5], shift_mode=0)
+        accel = np.ascontiguousarray(f0[:, :3] / mass[:, None])
+        oracle.run(box, pos, vel, accel, img, mass, types, tags, [[1.0, 1.0]], [2.5], steps, 0.005, 0.4,
+                   thermostat="langevin", kT=float(ref["kT"]), seed=int(ref["seed"]), gamma=float(ref["gamma"]))
+        return pos, vel
+
+    pos, vel = run(1)
+    d = pos - ref["pos_1"]
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 1e-12
+    assert np.max(np.abs(vel - ref["vel_1"])) < 1e-11
+    pos, vel = run(20)
+    d = pos - ref["pos_20"]
+    d -= L * np.round(d / L)
+    assert np.max(np.abs(d)) < 1e-9 and np.max(np.abs(vel - ref["vel_20"])) < 1e-8
+
+
+def test_thermalize_pinned_by_the_reference(golden_dir):
+    """State.thermalize_particle_momenta of the reference (seed 7, timestep 0, kT 1.5, unit masses)
+    against the host implementation in hoomd_blue_b200/rng.py (hoomd/ParticleData / hoomd/State.cc
+    thermalizeParticleMomenta: Philox keyed by tag, Box-Muller normals, centre-of-mass momentum removed)."""
+    import os
+    from hoomd_blue_b200 import rng
+    ref = dict(np.load(os.path.join(golden_dir, "langevin_2k.npz")))
+    n = len(ref["thermal_vel"])
+    got = rng.thermal_velocities(np.arange(n, dtype=np.uint32), np.ones(n, dtype=np.float32), 1.5,
+                                 int(ref["thermal_seed"]), 0)
+    assert np.max(np.abs(got - ref["thermal_vel"])) < 1e-12
