@@ -305,14 +305,16 @@ static inline int key_bits(uint32_t max_cell_code, bool ghosts)
     return b + SUB_BITS;
     }
 
-// HB2_CELL_ORDER=rowmajor|morton (default morton when every axis has at most 256 cells)
+// HB2_CELL_ORDER=rowmajor|morton. Default row-major: x-neighbouring cells are contiguous in memory, so the
+// tile kernels stage a stencil with one bulk copy per x-row of cells (Morton measured level for the
+// per-particle-row kernels, profiles/r02_cell_order_ab.txt, and needs at most 256 cells per axis)
 static int cell_curve(const DomainGeom& geom, int requested)
     {
     static int env = -1;
     if (env < 0)
         {
         const char* e = getenv("HB2_CELL_ORDER");
-        env = (e && e[0] == 'r') ? 0 : 1;
+        env = (e && e[0] == 'm') ? 1 : 0;
         }
     int curve = requested >= 0 ? requested : env;
     for (int d = 0; d < 3; d++)

@@ -766,13 +766,90 @@ hb2_status hb2_nlist::ensure_capacity()
         }
     // rows exist for owned particles only; allocate with room for the owned count to drift between
     // builds, and only reallocate when the rows in use no longer fit
+    tg = tile_geom(geom);
+    const size_t rows = D.active ? std::min<size_t>(cap, (size_t)(sys->N * 1.1) + 1024) : sys->N;
+    if (want_tiles())
+        {
+        if (stage_cap == 0)
+            {
+            // first guess: 64 stencil cells at the mean occupancy, a third of head-room; grows on overflow
+            const double mean = (double)(sys->N + sys->Ng) / (double)Nc;
+            stage_cap = ((uint32_t)(64.0 * mean * 1.35) + 64u + 63u) & ~63u;
+            }
+        if ((size_t)sys->N * pitch > rows16_cap)
+            {
+            dev_free(d_rows16);
+            HB2_TRY(dev_alloc(&d_rows16, rows * pitch));
+            rows16_cap = rows * pitch;
+            }
+        return HB2_OK;
+        }
     if ((size_t)sys->N * pitch > nlist_cap)
         {
-        const size_t rows = D.active ? std::min<size_t>(cap, (size_t)(sys->N * 1.1) + 1024) : sys->N;
         dev_free(d_nlist);
         HB2_TRY(dev_alloc(&d_nlist, rows * pitch));
         nlist_cap = rows * pitch;
         }
+    return HB2_OK;
+    }
+
+// The tile path covers grids with at least three cells per periodic ring and lists without exclusions
+// (the exclusion filter edits rows of global indices).
+bool hb2_nlist::want_tiles() const
+    {
+    if (!tile_enabled || !tile_capable(geom))
+        return false;
+    if ((exclude_bonds && sys->n_bonds) || n_ex_pairs)
+        return false;
+    // consumers that read rows of global indices on every step (thermostatted evaluators gather
+    // velocities and tags; an explicit threads_per_particle selects the per-particle-row kernel)
+    for (auto* p : consumers)
+        if (p->ev == HB2_EVAL_DPD || p->ev == HB2_EVAL_DPDLJ || p->tpp != 8)
+            return false;
+    return sys->ntypes <= 16;
+    }
+
+TileBuildArgs hb2_nlist::tile_args() const
+    {
+    hb2_system* s = sys;
+    TileBuildArgs a;
+    a.pos = s->pos[s->cur];
+    a.N = s->N;
+    a.geom = geom;
+    a.tg = tg;
+    a.cell_start = d_cell_start;
+    a.cell_end = d_cell_end;
+    a.r_listsq = d_r_listsq;
+    a.ntypes = s->ntypes;
+    a.r_listsq_single = r_listsq[0];
+    a.r_list_min = r_list_min;
+    a.Lmax = (float)std::max(s->box.L[0], std::max(s->box.L[1], s->box.L[2]));
+    a.rows16 = d_rows16;
+    a.pitch = pitch;
+    a.n_neigh = d_n_neigh;
+    a.last_pos = d_last_pos;
+    a.conditions = d_conditions;
+    a.stage_cap = stage_cap;
+    return a;
+    }
+
+// Rows of global indices for the consumers that need them while the tile layout is the live one.
+hb2_status hb2_nlist::global_rows()
+    {
+    if (global_valid || !has_list)
+        return HB2_OK;
+    hb2_system* s = sys;
+    if ((size_t)s->N * pitch > nlist_cap)
+        {
+        const size_t rows = s->dom.active ? std::min<size_t>(s->cap, (size_t)(s->N * 1.1) + 1024) : s->N;
+        dev_free(d_nlist);
+        HB2_TRY(dev_alloc(&d_nlist, rows * pitch));
+        nlist_cap = rows * pitch;
+        }
+    TileBuildArgs a = tile_args();
+    a.last_pos = nullptr;
+    HB2_TRY(launch_tile_rows_to_global(a, d_nlist, s->N + s->Ng, s->stream));
+    global_valid = true;
     return HB2_OK;
     }
 
@@ -824,7 +901,7 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
     HB2_TRY(ensure_capacity());
     const uint32_t N = s->N, Ntot = s->N + s->Ng;
 
-    HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
+    HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 8 * sizeof(uint32_t), st));
     if (s->dom.active && s->rtag) // tags that are neither owned nor ghosts here must read "absent"
         HB2_CUDA(cudaMemsetAsync(s->rtag, 0xff, sizeof(uint32_t) * (size_t)s->dom.N_global, st));
     const int c = s->cur, o = 1 - c;
@@ -840,29 +917,44 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
     HB2_TRY(system_place_dummy(s));
     tick("remap");
 
+    bool tiles = false;
     for (;;)
         {
-        NlistBuildArgs a;
-        a.pos = s->pos[s->cur];
-        a.N = N;
-        a.geom = geom;
-        a.cell_start = d_cell_start;
-        a.cell_end = d_cell_end;
-        a.r_listsq = d_r_listsq;
-        a.ntypes = s->ntypes;
-        a.r_listsq_single = r_listsq[0];
-        a.r_list_min = r_list_min;
-        a.Lmax = (float)std::max(s->box.L[0], std::max(s->box.L[1], s->box.L[2]));
-        a.nlist = d_nlist;
-        a.pitch = pitch;
-        a.n_neigh = d_n_neigh;
-        a.last_pos = d_last_pos;
-        a.conditions = d_conditions;
-        a.dummy_index = Ntot;
-        HB2_TRY(launch_nlist_build(a, s->box, st));
+        tiles = want_tiles();
+        if (tiles && tile_build_smem(stage_cap, pitch, s->ntypes) == 0)
+            {
+            // the stencil of a tile no longer fits in shared memory: per-particle rows from here on
+            tile_enabled = false;
+            nlist_cap = 0;
+            HB2_TRY(ensure_capacity());
+            continue;
+            }
+        if (tiles)
+            HB2_TRY(launch_nlist_build_tiles(tile_args(), s->box, st));
+        else
+            {
+            NlistBuildArgs a;
+            a.pos = s->pos[s->cur];
+            a.N = N;
+            a.geom = geom;
+            a.cell_start = d_cell_start;
+            a.cell_end = d_cell_end;
+            a.r_listsq = d_r_listsq;
+            a.ntypes = s->ntypes;
+            a.r_listsq_single = r_listsq[0];
+            a.r_list_min = r_list_min;
+            a.Lmax = (float)std::max(s->box.L[0], std::max(s->box.L[1], s->box.L[2]));
+            a.nlist = d_nlist;
+            a.pitch = pitch;
+            a.n_neigh = d_n_neigh;
+            a.last_pos = d_last_pos;
+            a.conditions = d_conditions;
+            a.dummy_index = Ntot;
+            HB2_TRY(launch_nlist_build(a, s->box, st));
+            }
         if (s->dom.active) // every rank must take the same branch below
-            HB2_TRY(domain_allreduce_max_u32(s, d_conditions, 3));
-        HB2_CUDA(cudaMemcpyAsync(h_conditions, d_conditions, 4 * sizeof(uint32_t),
+            HB2_TRY(domain_allreduce_max_u32(s, d_conditions, 6));
+        HB2_CUDA(cudaMemcpyAsync(h_conditions, d_conditions, 8 * sizeof(uint32_t),
                                  cudaMemcpyDeviceToHost, st));
         HB2_CUDA(cudaStreamSynchronize(st));
         if (h_conditions[1])
@@ -877,6 +969,15 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
                       + " is no longer in the simulation box.");
             return HB2_ERR_OUT_OF_BOX;
             }
+        if (tiles && (h_conditions[4] || h_conditions[5]))
+            {
+            // a tile's stencil (or one home cell's 27 cells) holds more particles than the staging
+            // capacity: grow it and build again
+            const uint32_t need = std::max(h_conditions[4], (h_conditions[5] * 16u + 8u) / 9u);
+            stage_cap = ((uint32_t)(need * 1.125) + 64u + 63u) & ~63u;
+            HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 8 * sizeof(uint32_t), st));
+            continue;
+            }
         max_neigh = h_conditions[0];
         tick("build");
         if (max_neigh <= pitch)
@@ -885,9 +986,12 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
         // (hoomd/md/NeighborList.cc:411-427, :1601-1617)
         pitch = ((uint32_t)(max_neigh * 1.125) + 8u + 31u) & ~31u;
         nlist_cap = 0;
+        rows16_cap = 0;
         HB2_TRY(ensure_capacity());
-        HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 4 * sizeof(uint32_t), st));
+        HB2_CUDA(cudaMemsetAsync(d_conditions, 0, 8 * sizeof(uint32_t), st));
         }
+    tile_active = tiles;
+    global_valid = !tiles;
     // exclusions=('bond',): drop bonded pairs from the rows (hoomd/md/NeighborList.cc:1487-1536)
     if (exclude_bonds && s->n_bonds)
         HB2_TRY(launch_nlist_filter_bonds(N, s->tag[s->cur], s->rtag, s->d_bond_head, s->d_bond_partner,
@@ -949,15 +1053,17 @@ extern "C" hb2_status hb2_nlist_create(hb2_nlist** out, hb2_system* s, double bu
     nl->buffer = buffer;
     nl->rebuild_check_delay = rebuild_check_delay;
     nl->check_dist = check_dist != 0;
-    hb2_status st = dev_alloc(&nl->d_conditions, 4);
-    if (st == HB2_OK && cudaMallocHost((void**)&nl->h_conditions, 4 * sizeof(uint32_t)) != cudaSuccess)
+    if (const char* e = getenv("HB2_TILE"))
+        nl->tile_enabled = atoi(e) != 0;
+    hb2_status st = dev_alloc(&nl->d_conditions, 8);
+    if (st == HB2_OK && cudaMallocHost((void**)&nl->h_conditions, 8 * sizeof(uint32_t)) != cudaSuccess)
         st = cuda_fail(cudaGetLastError(), "cudaMallocHost");
     if (st != HB2_OK)
         {
         delete nl;
         return st;
         }
-    cudaMemsetAsync(nl->d_conditions, 0, 4 * sizeof(uint32_t), s->stream);
+    cudaMemsetAsync(nl->d_conditions, 0, 8 * sizeof(uint32_t), s->stream);
     s->nlists.push_back(nl);
     *out = nl;
     return HB2_OK;
@@ -978,6 +1084,7 @@ extern "C" void hb2_nlist_destroy(hb2_nlist* nl)
         cudaFree(nl->d_tmp);
     dev_free(nl->d_r_listsq);
     dev_free(nl->d_nlist);
+    dev_free(nl->d_rows16);
     dev_free(nl->d_n_neigh);
     dev_free(nl->d_last_pos);
     dev_free(nl->d_ex_head);
@@ -1029,6 +1136,7 @@ extern "C" hb2_status hb2_nlist_device_arrays(hb2_nlist* nl, const uint32_t** d_
         return HB2_ERR_INVALID;
         }
     HB2_CUDA(cudaSetDevice(nl->sys->device));
+    HB2_TRY(nl->global_rows());
     HB2_CUDA(cudaStreamSynchronize(nl->sys->stream));
     *d_n_neigh = nl->d_n_neigh;
     *d_nlist = nl->d_nlist;
@@ -1071,6 +1179,7 @@ static hb2_status nlist_download(hb2_nlist* nl, std::vector<uint32_t>& n_neigh,
         set_error("nlist: no neighbour list has been built yet");
         return HB2_ERR_INVALID;
         }
+    HB2_TRY(nl->global_rows());
     const uint32_t N = s->N;
     n_neigh.resize(N);
     tag.resize((size_t)N + s->Ng);
@@ -1402,6 +1511,25 @@ hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t*
     a.n_neigh = nl->d_n_neigh;
     a.nlist = nl->d_nlist;
     a.pitch = nl->pitch;
+    if (nl->tile_active)
+        {
+        // thermostatted evaluators gather velocities and tags by global index; a non-default
+        // threads_per_particle asks for the per-particle-row kernel explicitly
+        if (ev == HB2_EVAL_DPD || ev == HB2_EVAL_DPDLJ || tpp != 8)
+            {
+            HB2_TRY(nl->global_rows());
+            a.nlist = nl->d_nlist;
+            }
+        else
+            {
+            a.rows16 = nl->d_rows16;
+            a.tg = nl->tg;
+            a.geom = nl->geom;
+            a.cell_start = nl->d_cell_start;
+            a.cell_end = nl->d_cell_end;
+            a.stage_cap = nl->stage_cap;
+            }
+        }
     a.params = d_params;
     a.rcutsq = d_rcutsq;
     a.ronsq = d_ronsq;

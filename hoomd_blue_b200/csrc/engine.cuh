@@ -130,13 +130,26 @@ struct hb2_nlist
     size_t tmp_bytes = 0;
     double* d_r_listsq = nullptr;
 
+    // Two layouts of the same full list. The tile-shared layout (tile.cuh: 16-bit staged slots, built by
+    // nlist_tile.cu, consumed by pair_tile.cuh) is the step loop's; the per-particle rows of global
+    // indices (nlist.cu) serve the thermostatted evaluators, the exclusion filter, the exported arrays and
+    // grids the tile path does not cover. With the tile layout active the global rows are produced on
+    // demand from it (global_rows()).
+    bool tile_enabled = true; // HB2_TILE=0 switches the tile path off
+    bool tile_active = false; // the last build produced rows16
+    bool global_valid = false; // d_nlist matches the last build
+    uint16_t* d_rows16 = nullptr;
+    size_t rows16_cap = 0;
+    uint32_t stage_cap = 0; // staged slots per tile (0: not yet estimated)
+    TileGeom tg;
     uint32_t* d_nlist = nullptr;
     uint32_t pitch = 0;
     size_t nlist_cap = 0;
     uint32_t* d_n_neigh = nullptr;
     float4* d_last_pos = nullptr;
     uint32_t cap_N = 0;
-    uint32_t* d_conditions = nullptr; // [0] max n_neigh, [1] nan idx+1, [2] oob idx+1, [3] rebuild flag
+    uint32_t* d_conditions = nullptr; // [0] max n_neigh, [1] nan idx+1, [2] oob idx+1, [3] rebuild flag,
+                                      // [4] / [5] tile build: staged slots / candidates beyond capacity
     uint32_t* h_conditions = nullptr; // pinned mirror
 
     bool exclude_bonds = true; // exclusions=('bond',), the reference's default (hoomd/md/nlist.py:87-102)
@@ -155,6 +168,9 @@ struct hb2_nlist
     hb2_status ensure_capacity();
     hb2_status rebuild(uint64_t timestep);
     hb2_status compute(uint64_t timestep, bool flag_known, bool flag_value);
+    bool want_tiles() const;
+    TileBuildArgs tile_args() const;
+    hb2_status global_rows(); // make d_nlist valid for the current build
     float maxshift() const
         {
         // hoomd/md/NeighborList.cc:1244-1260 with a fixed box (lambda = 1): (r_max - r_min)/2

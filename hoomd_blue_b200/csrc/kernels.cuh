@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "comm.cuh"
+#include "tile.cuh"
 
 namespace hb2
     {
@@ -126,6 +127,14 @@ struct PairArgs
     uint32_t tpp;
     bool energy = true; // false: skip the per-particle potential energy (force.w = 0)
     const uint32_t* skip_flag = nullptr; // device word; non-zero => the launch does nothing
+    // tile-shared list (tile.cuh): when rows16 is set the pass runs pair_force_tile_kernel over it and
+    // n_neigh; nlist / tpp / face_margin are not used
+    const uint16_t* rows16 = nullptr;
+    TileGeom tg;
+    DomainGeom geom;
+    const uint32_t* cell_start = nullptr;
+    const uint32_t* cell_end = nullptr;
+    uint32_t stage_cap = 0;
     };
 hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,
                               const hb2_box& box, cudaStream_t stream);

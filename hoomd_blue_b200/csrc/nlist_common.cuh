@@ -2,7 +2,6 @@
 // (nlist.cu: per-particle rows, the layer-1 driver; nlist_quad.cu: quad rows, the engine's list).
 #pragma once
 #include "common.cuh"
-#include "kernels.cuh"
 #include <math.h>
 
 namespace hb2

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "evaluators.cuh"
 #include "kernels.cuh"
+#include "tile.cuh"
 #include <algorithm>
 
 namespace hb2
@@ -111,6 +112,13 @@ template<class Ev> struct PairKArgs
     const uint32_t* skip_flag; // non-zero word => return at once (speculative launch, engine.cu)
     BoxF box;
     BoxD boxd;
+    // tile-shared list (tile.cuh / pair_tile.cuh); rows16 == nullptr: per-particle rows of global indices
+    const uint16_t* rows16;
+    TileGeom tg;
+    DomainGeom geom;
+    const uint32_t* cell_start;
+    const uint32_t* cell_end;
+    uint32_t stage_cap;
     };
 
 // MODE: 0 none, 1 shift, 2 xplor (hoomd/md/PotentialPair.h:104-109)
@@ -528,6 +536,10 @@ __global__ void PAIR_BOUNDS pair_force_kernel(const PairKArgs<Ev> a)
         }
     }
 
+    } // namespace hb2
+#include "pair_tile.cuh"
+namespace hb2
+    {
 template<class Ev, int MODE, bool VIRIAL, int TPP>
 hb2_status pair_launch_tpp(const PairKArgs<Ev>& k, cudaStream_t stream)
     {
@@ -634,12 +646,36 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.energy = a.energy;
     k.skip_flag = a.skip_flag;
     k.stage = std::min<uint32_t>(std::max<uint32_t>(a.pitch / 32u, 1u), PAIR_STAGE_MAX);
+    k.rows16 = a.rows16;
+    k.tg = a.tg;
+    k.geom = a.geom;
+    k.cell_start = a.cell_start;
+    k.cell_end = a.cell_end;
+    k.stage_cap = a.stage_cap;
     if (Ev::needs_thermo && (!a.vel || !a.tag))
         {
         set_error("pair forces: this evaluator needs velocities and tags");
         return HB2_ERR_INVALID;
         }
     const bool virial = a.virial != nullptr;
+    if (a.rows16)
+        {
+        if constexpr (Ev::needs_thermo)
+            {
+            set_error("pair forces: thermostatted evaluators read the per-particle rows, not the tile list");
+            return HB2_ERR_INVALID;
+            }
+        else
+            switch (mode)
+                {
+            case HB2_SHIFT_NONE:
+                return pair_tile_launch_mode<Ev, 0>(k, virial, stream);
+            case HB2_SHIFT_SHIFT:
+                return pair_tile_launch_mode<Ev, 1>(k, virial, stream);
+            case HB2_SHIFT_XPLOR:
+                return pair_tile_launch_mode<Ev, 2>(k, virial, stream);
+                }
+        }
     switch (mode)
         {
     case HB2_SHIFT_NONE:

@@ -10,12 +10,14 @@ from .typeparam import TypePairDict
 
 
 class _DeviceArray:
-    """A read-only view of device memory through __cuda_array_interface__ (version 3): CuPy, PyTorch
-    (torch.as_tensor) and Numba wrap it without a copy, like the reference's HOOMDGPUArray."""
+    """A view of device memory through __cuda_array_interface__ (version 3): CuPy, PyTorch
+    (torch.as_tensor) and Numba wrap it without a copy, like the reference's HOOMDGPUArray. The list is
+    the library's: treat it as read-only (the interface's read-only flag stays off because PyTorch refuses
+    to wrap arrays that set it)."""
 
-    def __init__(self, pointer, shape, typestr="<i4"):  # int32 view of the uint32 data (indices < 2^31)
+    def __init__(self, pointer, shape, typestr="<i4", read_only=False):  # int32 view of the uint32 data
         self.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr=typestr,
-                                             data=(int(pointer), True), version=3, strides=None)
+                                             data=(int(pointer), bool(read_only)), version=3, strides=None)
         self.shape = tuple(int(s) for s in shape)
 
 
