@@ -761,7 +761,8 @@ hb2_status hb2_nlist::ensure_capacity()
         const double rl = rcut_max_max + buffer;
         const double Ng = D.active ? (double)D.N_global : (double)sys->N;
         const double est = Ng / vol * 4.18879020478639 * rl * rl * rl;
-        pitch = (uint32_t)std::min<double>(std::max(16.0, 1.25 * est + 16.0), std::max(Ng, 8.0));
+        // (the tile kernels hold rows in shared memory: a tight pitch is worth the occasional regrow)
+        pitch = (uint32_t)std::min<double>(std::max(16.0, 1.15 * est + 12.0), std::max(Ng, 8.0));
         pitch = (pitch + 31u) & ~31u; // rows are padded to whole 32-entry chunks
         }
     // rows exist for owned particles only; allocate with room for the owned count to drift between
@@ -774,7 +775,7 @@ hb2_status hb2_nlist::ensure_capacity()
             {
             // first guess: 64 stencil cells at the mean occupancy, a third of head-room; grows on overflow
             const double mean = (double)(sys->N + sys->Ng) / (double)Nc;
-            stage_cap = ((uint32_t)(64.0 * mean * 1.35) + 64u + 63u) & ~63u;
+            stage_cap = ((uint32_t)(64.0 * mean * 1.2) + 32u + 63u) & ~63u;
             }
         if ((size_t)sys->N * pitch > rows16_cap)
             {

@@ -163,9 +163,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) nlist_build_tile_kernel(const
         uint32_t t0 = 0, t1 = 0;
             {
             const float4 p0 = lds128(stage_s + li0 * 16u), p1 = lds128(has1 ? stage_s + li1 * 16u : stage_s);
+            // packed once per pass and kept as 64-bit register pairs (the empty asm hides where the halves
+            // came from, or the compiler re-packs them from the two float4 loads inside the sweep)
             px = make_float2(p0.x, p1.x);
             py = make_float2(p0.y, p1.y);
             pz = make_float2(p0.z, p1.z);
+            asm volatile("" : "+f"(px.x), "+f"(px.y), "+f"(py.x), "+f"(py.y), "+f"(pz.x), "+f"(pz.y));
             if (MULTITYPE)
                 {
                 t0 = __float_as_uint(p0.w);

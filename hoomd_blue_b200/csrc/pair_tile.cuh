@@ -23,7 +23,7 @@ namespace hb2
 #define PAIR_TILE_MIN_BLOCKS 4
 #endif
 
-constexpr int PT_HCAP = 448; // home particles of a tile resolved through the shared-memory table
+constexpr int PT_HCAP = 384; // home particles of a tile with a record in shared memory
 
 inline size_t pair_tile_smem(uint32_t stage_cap, uint32_t pitch)
     {
@@ -31,6 +31,29 @@ inline size_t pair_tile_smem(uint32_t stage_cap, uint32_t pitch)
            + sizeof(uint16_t) * TILE_WARPS * 2 * 4 * pitch;
     }
 
+// does any stencil cell of this tile lie across a periodic boundary? (geometry only: the same answer as
+// TileLayout::any_shift, before anything is loaded)
+HB2_DEVICE bool tile_is_shifting(const uint32_t tile, const TileGeom& tg, const DomainGeom& geom)
+    {
+    const uint32_t tt[3] = {tile % tg.nt[0], (tile / tg.nt[0]) % tg.nt[1], tile / (tg.nt[0] * tg.nt[1])};
+    bool sh = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        {
+        const int c0 = (int)(tg.first[d] + 2u * tt[d]);
+        const int nc = min(2, (int)(tg.first[d] + geom.dimi[d]) - c0);
+        const int below = c0 - 1, above = c0 + nc;
+        if (geom.n[d] > 1)
+            sh = sh || (below == 0 && geom.coord[d] == 0) || (above == (int)geom.dimt[d] - 1 && geom.coord[d] == geom.n[d] - 1);
+        else
+            sh = sh || below < 0 || above >= (int)geom.dimt[d];
+        }
+    return sh;
+    }
+
+// Tiles that touch a periodic boundary use the (hi, lo) image-shift separations of pair_kernel.cuh; their
+// per-particle shift operands live in shared memory (one slot per thread, read inside the pair loop), so
+// that the plain tiles' loop — all tiles but a surface layer — does not carry nine more registers.
 template<class Ev, int MODE, bool VIRIAL, bool ONETYPE, bool ENERGY>
 __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_TILE_MIN_BLOCKS)
     pair_force_tile_kernel(const PairKArgs<Ev> a)
@@ -38,12 +61,13 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
     typedef typename Ev::param_type param_type;
     if (a.skip_flag && *a.skip_flag)
         return;
+    const bool SHIFT = tile_is_shifting(blockIdx.x, a.tg, a.geom);
     __shared__ param_type s_params[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_rcutsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_ronsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_hgi[PT_HCAP];
-    __shared__ uint16_t s_hli[PT_HCAP];
+    __shared__ __align__(8) uint2 s_home[PT_HCAP];   // global index, staged byte offset | n_neigh << 16
+    __shared__ float2 s_shift[3][TILE_THREADS / 8];  // (hi, lo) of pi -/+ L per component and particle
     extern __shared__ __align__(128) unsigned char s_raw[];
     TileLayout& L = *reinterpret_cast<TileLayout*>(s_raw);
     float4* __restrict__ stage = reinterpret_cast<float4*>(s_raw + ((sizeof(TileLayout) + 15) & ~(size_t)15));
@@ -66,7 +90,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
     const uint32_t ns = L.nk[0] * L.nk[1] * L.nk[2];
     if (total > a.stage_cap)
         __trap(); // the build ran with the same capacity over the same cells
-    // ---- 1. stage the stencil: warp 0 issues one bulk copy per stencil cell
+    // ---- 1. stage the stencil: warp 0 issues the bulk copies
     if (w == 0)
         {
         if (lane == 0)
@@ -102,100 +126,71 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
     const uint32_t nhome = L.hoff[8];
     const uint32_t npass = (nhome + 3u) >> 2;
     const uint32_t sub = lane & 7u, grp = lane >> 3;
-    const bool shifting = L.any_shift != 0u;
-    const bool tabled = nhome <= (uint32_t)PT_HCAP;
 
-    // home slot hs of the tile -> (staged slot, global index)
-    auto resolve = [&](const uint32_t hs, uint32_t& li, uint32_t& gi)
+    // home slot hs of the tile -> (global index, staged byte offset | n_neigh << 16)
+    auto resolve = [&](const uint32_t hs) -> uint2
     {
         uint32_t c = (hs >= L.hoff[4]) ? 4u : 0u;
         c += (hs >= L.hoff[c + 2]) ? 2u : 0u;
         c += (hs >= L.hoff[c + 1]) ? 1u : 0u;
         const uint32_t sc = L.hcell[c], k = hs - L.hoff[c];
-        li = L.off[sc] + k;
-        gi = L.gstart[sc] + k;
+        const uint32_t gi = L.gstart[sc] + k;
+        return make_uint2(gi, ((L.off[sc] + k) * 16u) | (__ldg(a.n_neigh + gi) << 16));
     };
-    if (tabled)
-        for (uint32_t hs = threadIdx.x; hs < nhome; hs += TILE_THREADS)
-            {
-            uint32_t li, gi;
-            resolve(hs, li, gi);
-            s_hgi[hs] = gi;
-            s_hli[hs] = (uint16_t)li;
-            }
+    for (uint32_t hs = threadIdx.x; hs < min(nhome, (uint32_t)PT_HCAP); hs += TILE_THREADS)
+        s_home[hs] = resolve(hs);
     // the positions have landed (one warp polls the mbarrier; the others sleep in the block barrier)
     if (w == 0)
         mbar_wait(&s_bar, 0);
     __syncthreads();
-    auto home = [&](const uint32_t hs, uint32_t& li, uint32_t& gi)
+    const uint32_t home_s = smem_u32(s_home);
+    auto home = [&](const uint32_t hs) -> uint2
     {
-        if (tabled)
-            {
-            li = s_hli[hs];
-            gi = s_hgi[hs];
-            }
-        else
-            resolve(hs, li, gi);
+        if (hs >= nhome)
+            return make_uint2(0u, 0u); // no particle: the far-away dummy with an empty row
+        if (hs < (uint32_t)PT_HCAP)
+            return lds64(home_s + hs * 8u);
+        return resolve(hs);
     };
 
     // ---- 2. rows: 16-byte asynchronous copies (cp.async, LDGSTS) into a per-warp double buffer, requested
-    // one pass ahead (their length n_neigh two passes ahead). Lane `sub` of a particle copies quarter
-    // sub & 3 of chunks sub >> 2, sub >> 2 + 2, ...: one instruction moves two 64-byte chunks per particle.
-    const uint32_t stage_s = smem_addr(stage);
-    uint16_t* const rowbuf = rowbuf_all + (size_t)w * (2u * 4u * a.pitch);
-    const uint32_t rowbuf_s = smem_addr(rowbuf);
+    // one pass ahead. Lane `sub` of a particle copies quarter sub & 3 of chunks sub >> 2, sub >> 2 + 2, ...
+    const uint32_t stage_s = smem_u32(stage);
     const uint32_t pitch_b = a.pitch * 2u; // bytes per row
-    auto load_n = [&](const uint32_t q) -> uint32_t
+    const uint32_t rowbuf_s = smem_u32(rowbuf_all) + (uint32_t)w * (8u * pitch_b) + grp * pitch_b;
+    const uint32_t lane_off = (sub >> 2) * 64u + (sub & 3u) * 16u;
+    auto request_rows = [&](const uint2 h, const uint32_t b)
     {
-        const uint32_t hs = 4u * q + grp;
-        if (q >= npass || hs >= nhome)
-            return 0u;
-        uint32_t li, gi;
-        home(hs, li, gi);
-        return __ldg(a.n_neigh + gi);
-    };
-    auto request_rows = [&](const uint32_t q, const uint32_t nq)
-    {
-        const uint32_t hs = 4u * q + grp;
-        if (q < npass && hs < nhome)
+        const uint32_t nch = ((h.y >> 16) + 31u) >> 5;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.rows16) + (size_t)h.x * pitch_b + lane_off;
+        uint32_t dst = rowbuf_s + b * (4u * pitch_b) + lane_off;
+        for (uint32_t c = sub >> 2; c < nch; c += 2u)
             {
-            uint32_t li, gi;
-            home(hs, li, gi);
-            const uint32_t b = (q / TILE_WARPS) & 1u;
-            const uint32_t nch = (nq + 31u) >> 5;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.rows16) + (size_t)gi * pitch_b
-                                       + (sub >> 2) * 64u + (sub & 3u) * 16u;
-            const uint32_t dst = rowbuf_s + (b * 4u + grp) * pitch_b + (sub >> 2) * 64u + (sub & 3u) * 16u;
-            for (uint32_t c = sub >> 2; c < nch; c += 2u)
-                {
-                const uint32_t o = (c - (sub >> 2)) * 64u;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
-                }
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            src += 128;
+            dst += 128u;
             }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     uint32_t q = w;
-    uint32_t n = load_n(q), n_next = load_n(q + TILE_WARPS);
-    request_rows(q, n);
+    uint2 hcur = home(4u * q + grp);
+    request_rows(hcur, 0u);
+    uint32_t b = 0;
 
     while (q < npass)
         {
-        const uint32_t b = (q / TILE_WARPS) & 1u;
         const uint32_t qn = q + TILE_WARPS;
         // this pass's rows have landed; the other buffer was last read in pass q - 1 (the reduction's
         // shuffles at its end joined the warp), so the next pass's rows can be requested into it
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        request_rows(qn, n_next);
-        const uint32_t n_next2 = load_n(qn + TILE_WARPS);
+        const uint2 hnext = home(4u * qn + grp);
+        request_rows(hnext, b ^ 1u);
 
-        const uint32_t hs = 4u * q + grp;
-        const bool valid = hs < nhome;
-        uint32_t li = 0, gi = 0;
-        if (valid)
-            home(hs, li, gi);
-        const float4 pi = lds128(stage_s + li * 16u);
+        const bool valid = 4u * q + grp < nhome;
+        const uint32_t gi = hcur.x, n = hcur.y >> 16;
+        const float4 pi = lds128(stage_s + (hcur.y & 0xffffu));
         const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
         const uint32_t nchunks = (n + 31u) >> 5;
         const uint32_t nch_warp = __reduce_max_sync(0xffffffffu, nchunks);
@@ -297,44 +292,48 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
         };
 
         // (hi, lo) of pi -/+ L, see pair_kernel.cuh
-        float sh[3], sl[3];
         const float pc[3] = {pi.x, pi.y, pi.z};
         const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
-        if (shifting)
+        const uint32_t shift_s = smem_u32(&s_shift[0][threadIdx.x >> 3]);
+        if (SHIFT)
             {
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 {
                 const double m = pc[c] >= 0.f ? (double)pc[c] - a.boxd.L[c] : (double)pc[c] + a.boxd.L[c];
-                sh[c] = (float)m;
-                sl[c] = (float)(m - (double)sh[c]);
+                const float hi = (float)m;
+                if (sub == 0u)
+                    s_shift[c][threadIdx.x >> 3] = make_float2(hi, (float)(m - (double)hi));
                 }
+            __syncwarp();
             }
-        auto separation_shift = [&](const float4 qq, float& dx, float& dy, float& dz)
+        auto separation_shift = [&](const float4 (&pj)[4], float (&dx)[4], float (&dy)[4], float (&dz)[4])
         {
-            float d[3];
-            const float qc[3] = {qq.x, qq.y, qq.z};
+            float* const d[3] = {dx, dy, dz};
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 {
-                const float d0 = pc[c] - qc[c];
-                const float ds = (sh[c] - qc[c]) + sl[c];
-                d[c] = fabsf(d0) >= hc[c] ? ds : d0;
+                const uint2 hl = lds64(shift_s + c * (uint32_t)(TILE_THREADS / 8 * sizeof(float2)));
+                const float sh = __uint_as_float(hl.x), sl = __uint_as_float(hl.y);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    {
+                    const float qc = c == 0 ? pj[u].x : (c == 1 ? pj[u].y : pj[u].z);
+                    const float d0 = pc[c] - qc;
+                    const float ds = (sh - qc) + sl;
+                    d[c][u] = fabsf(d0) >= hc[c] ? ds : d0;
+                    }
                 }
-            dx = d[0];
-            dy = d[1];
-            dz = d[2];
         };
         auto rsq_of = [](const float dx, const float dy, const float dz)
         { return fmaf(dz, dz, fmaf(dy, dy, dx * dx)); };
 
-        const uint32_t idx_s = rowbuf_s + (b * 4u + grp) * pitch_b + sub * 8u;
-        uint2 wc = nchunks ? lds64(idx_s) : make_uint2(0u, 0u);
+        const uint32_t idx_s = rowbuf_s + b * (4u * pitch_b) + sub * 8u;
         for (uint32_t c = 0; c < nch_warp; c++)
             {
-            uint2 wn = make_uint2(0u, 0u);
-            if (c + 1u < nchunks)
-                wn = lds64(idx_s + (c + 1u) * 64u);
+            uint2 wc = lds64(idx_s + c * 64u);
+            if (c >= nchunks) // a shorter row than the warp's longest: the dummy slot
+                wc = make_uint2(0u, 0u);
             // row entries are staged slots times 16: byte offsets into the staged array
             float4 pj[4];
             pj[0] = lds128(stage_s + (wc.x & 0xffffu));
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
             pj[2] = lds128(stage_s + (wc.y & 0xffffu));
             pj[3] = lds128(stage_s + (wc.y >> 16));
             float dxs[4], dys[4], dzs[4];
-            if (!shifting)
+            if (!SHIFT)
                 {
 #pragma unroll
                 for (int u = 0; u < 4; u++)
@@ -353,11 +352,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                     }
                 }
             else
-                {
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    separation_shift(pj[u], dxs[u], dys[u], dzs[u]);
-                }
+                separation_shift(pj, dxs, dys, dzs);
             if constexpr (PACKED)
                 {
 #pragma unroll
@@ -375,14 +370,14 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                     pair_body(pj[u], dxs[u], dys[u], dzs[u], rsq, 1.0f);
                     }
                 }
-            wc = wn;
             }
         if (near_min <= 64u)
             {
             // rare (about one pass in 1e5): some rsq came within 32 ulp of r_cut^2. Re-walk the row, decide
             // those pairs with the CPU build's exact arithmetic — the staged positions ARE the stored
             // global coordinates — and repair the pairs where fp32 and the reference disagree.
-            const uint16_t* __restrict__ row = rowbuf + (size_t)(b * 4u + grp) * a.pitch + 4u * sub;
+            const uint16_t* __restrict__ row
+                = rowbuf_all + (size_t)((w * 2u + b) * 4u + grp) * a.pitch + 4u * sub;
             for (uint32_t e = 0; e < nchunks * 4u; e++)
                 {
                 // this lane's storage slots: 4 sub .. 4 sub + 3 of every chunk
@@ -390,15 +385,14 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                 if (jj == 0u)
                     continue;
                 const float4 qq = stage[jj >> 4];
-                float dx, dy, dz;
-                if (!shifting)
+                float dx = pi.x - qq.x, dy = pi.y - qq.y, dz = pi.z - qq.z;
+                if (SHIFT)
                     {
-                    dx = pi.x - qq.x;
-                    dy = pi.y - qq.y;
-                    dz = pi.z - qq.z;
+                    const float2 sx = s_shift[0][threadIdx.x >> 3], sy = s_shift[1][threadIdx.x >> 3], sz = s_shift[2][threadIdx.x >> 3];
+                    dx = fabsf(dx) >= hc[0] ? (sx.x - qq.x) + sx.y : dx;
+                    dy = fabsf(dy) >= hc[1] ? (sy.x - qq.y) + sy.y : dy;
+                    dz = fabsf(dz) >= hc[2] ? (sz.x - qq.z) + sz.y : dz;
                     }
-                else
-                    separation_shift(qq, dx, dy, dz);
                 const float rsq = rsq_of(dx, dy, dz);
                 const uint32_t tp = ONETYPE ? 0u : __float_as_uint(qq.w) * a.ntypes + ti;
                 const float rcutsq = ONETYPE ? a.rcutsq0 : s_rcutsq[tp];
@@ -462,8 +456,8 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                 }
             }
         q = qn;
-        n = n_next;
-        n_next = n_next2;
+        hcur = hnext;
+        b ^= 1u;
         }
     }
 
