@@ -777,6 +777,11 @@ hb2_status hb2_nlist::ensure_capacity()
             const double mean = (double)(sys->N + sys->Ng) / (double)Nc;
             stage_cap = ((uint32_t)(64.0 * mean * 1.2) + 32u + 63u) & ~63u;
             }
+        if (!d_tile_ticket)
+            {
+            HB2_TRY(dev_alloc(&d_tile_ticket, 2));
+            HB2_CUDA(cudaMemsetAsync(d_tile_ticket, 0, 2 * sizeof(uint32_t), sys->stream));
+            }
         if ((size_t)sys->N * pitch > rows16_cap)
             {
             dev_free(d_rows16);
@@ -831,6 +836,7 @@ TileBuildArgs hb2_nlist::tile_args() const
     a.last_pos = d_last_pos;
     a.conditions = d_conditions;
     a.stage_cap = stage_cap;
+    a.desc = d_tile_desc;
     return a;
     }
 
@@ -931,7 +937,17 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
             continue;
             }
         if (tiles)
+            {
+            const size_t need = (size_t)tg.nt[0] * tg.nt[1] * tg.nt[2] * tile_desc_stride(tile_hcap(stage_cap));
+            if (need > tile_desc_cap)
+                {
+                dev_free(d_tile_desc);
+                d_tile_desc = nullptr;
+                HB2_TRY(dev_alloc(&d_tile_desc, need + need / 8));
+                tile_desc_cap = need + need / 8;
+                }
             HB2_TRY(launch_nlist_build_tiles(tile_args(), s->box, st));
+            }
         else
             {
             NlistBuildArgs a;
@@ -1086,6 +1102,8 @@ extern "C" void hb2_nlist_destroy(hb2_nlist* nl)
     dev_free(nl->d_r_listsq);
     dev_free(nl->d_nlist);
     dev_free(nl->d_rows16);
+    dev_free(nl->d_tile_ticket);
+    dev_free(nl->d_tile_desc);
     dev_free(nl->d_n_neigh);
     dev_free(nl->d_last_pos);
     dev_free(nl->d_ex_head);
@@ -1529,6 +1547,8 @@ hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t*
             a.cell_start = nl->d_cell_start;
             a.cell_end = nl->d_cell_end;
             a.stage_cap = nl->stage_cap;
+            a.tile_ticket = nl->d_tile_ticket;
+            a.tile_desc = nl->d_tile_desc;
             }
         }
     a.params = d_params;
@@ -2539,6 +2559,7 @@ extern "C" void hb2_integrator_destroy(hb2_integrator* it)
         cudaEventDestroy(e);
     dev_free(it->d_gamma_coeff);
     dev_free(it->d_total);
+    dev_free(it->d_gen);
     delete it;
     }
 
@@ -2674,6 +2695,15 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
 
     it->pool_used = 0;
     it->marks.clear();
+    // ConstantVolume on one GPU: step two of a timestep and step one of the next share a launch
+    static const bool fuse_enabled = !(getenv("HB2_FUSE_INTEGRATE") && atoi(getenv("HB2_FUSE_INTEGRATE")) == 0);
+    const bool fuse = fuse_enabled && it->thermostat != 2 && !s->dom.active;
+    if (fuse && !it->d_gen)
+        {
+        HB2_TRY(dev_alloc(&it->d_gen, 1));
+        HB2_CUDA(cudaMemsetAsync(it->d_gen, 0, sizeof(uint32_t), st));
+        }
+    bool one_done = false; // the previous iteration's fused launch already did this timestep's step one
     for (uint64_t step = 0; step < nsteps; step++)
         {
         const uint64_t t = s->timestep;
@@ -2698,6 +2728,8 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             rescale = d_rescale;
             }
         const bool check = nl->has_list && nl->check_dist;
+        if (!one_done)
+            {
         // (Langevin: the previous step two left F + F_bd for this half step)
         // (valid for this particle order and this timestep only: a snapshot set in between, or a
         // rebuild triggered by a getter, falls back to the net force like computeAccelerations)
@@ -2708,6 +2740,8 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], f_one, s->image[s->cur], s->N,
                                 s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
                                 nl->maxshift(), nl->d_conditions + 3, st));
+            }
+        one_done = false;
         bool flag = false;
         const uint64_t builds_before = nl->num_builds;
         // Speculative force launch. On most steps the list is still valid, so the force pass is
@@ -2799,6 +2833,17 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             it->total_valid = true;
             it->total_epoch = s->order_epoch;
             it->total_step = t + 1;
+            }
+        else if (fuse && step + 1 < nsteps)
+            {
+            // step two of this timestep and step one of the next in one launch (integrate.cu); the Bussi
+            // factor of the next step is drawn between the halves
+            HB2_TRY(launch_step_two_one(s->pos[s->cur], s->vel[s->cur], pf->d_force, s->image[s->cur], s->N, s->box,
+                                        (float)it->dt, check ? nl->d_last_pos : nullptr, nl->maxshift(),
+                                        nl->d_conditions + 3, s->d_partial, s->d_ticket,
+                                        it->thermostat == 1 ? d_ke : nullptr, it->thermostat == 1 ? &bn : nullptr,
+                                        it->d_gen, ++it->gen_epoch, st));
+            one_done = true;
             }
         else
             HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,

@@ -139,6 +139,9 @@ struct hb2_nlist
     bool tile_active = false; // the last build produced rows16
     bool global_valid = false; // d_nlist matches the last build
     uint16_t* d_rows16 = nullptr;
+    unsigned char* d_tile_desc = nullptr; // per-tile descriptors (tile.cuh), rewritten by every build
+    size_t tile_desc_cap = 0;
+    uint32_t* d_tile_ticket = nullptr; // work ticket of the persistent tile force kernel (pair_tile.cuh)
     size_t rows16_cap = 0;
     uint32_t stage_cap = 0; // staged slots per tile (0: not yet estimated)
     TileGeom tg;
@@ -254,6 +257,8 @@ struct hb2_integrator
     float4* d_total = nullptr;      // Langevin: F + F_bd of the last step two (next step one's force)
     size_t total_cap = 0;
     bool total_valid = false;
+    uint32_t* d_gen = nullptr; // generation word of the fused step-two/step-one kernel (integrate.cu)
+    uint32_t gen_epoch = 0;
     uint64_t total_epoch = 0, total_step = 0; // particle order and timestep d_total belongs to
     bool prepared = false;
     bool reset_stats = true; // reset the neighbour list's num_builds / shortest_rebuild at the start of run

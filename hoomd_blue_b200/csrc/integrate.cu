@@ -11,10 +11,23 @@
 #include "kernels.cuh"
 #include "rng.cuh"
 #include "reduce.cuh"
+#include <algorithm>
 
 namespace hb2
     {
 constexpr int INT_BLOCK = 256;
+
+// The half kicks and the drift with explicit roundings: the stand-alone kernels and the fused
+// step-two/step-one kernel must produce the same bits (a run cut into segments by a writer is the same
+// trajectory as an uninterrupted one), whatever the compiler would contract.
+HB2_DEVICE float kick(const float v, const float f, const float minv, const float hdt)
+    {
+    return __fmaf_rn(hdt, __fmul_rn(f, minv), v);
+    }
+HB2_DEVICE float drift(const float p, const float v, const float dt)
+    {
+    return __fmaf_rn(dt, v, p);
+    }
 
 // v += 1/2 a dt; v *= s; r += v dt; wrap (x, y, z; >= hi -> -L, image+1; < lo -> +L, image-1:
 // hoomd/BoxDim.h:407-474). The acceleration is F/m of the force array left by the previous step
@@ -36,12 +49,12 @@ __global__ void __launch_bounds__(INT_BLOCK)
     const float4 f = force[i];
     const float minv = 1.0f / v.w;
     const float hdt = 0.5f * dt;
-    v.x = (v.x + hdt * (f.x * minv)) * s;
-    v.y = (v.y + hdt * (f.y * minv)) * s;
-    v.z = (v.z + hdt * (f.z * minv)) * s;
-    p.x += dt * v.x;
-    p.y += dt * v.y;
-    p.z += dt * v.z;
+    v.x = __fmul_rn(kick(v.x, f.x, minv, hdt), s);
+    v.y = __fmul_rn(kick(v.y, f.y, minv, hdt), s);
+    v.z = __fmul_rn(kick(v.z, f.z, minv, hdt), s);
+    p.x = drift(p.x, v.x, dt);
+    p.y = drift(p.y, v.y, dt);
+    p.z = drift(p.z, v.z, dt);
     int ix = 0, iy = 0, iz = 0;
     if (p.x >= box.hi[0])
         {
@@ -111,9 +124,9 @@ __global__ void __launch_bounds__(INT_BLOCK)
         const float4 f = force[i];
         const float minv = 1.0f / v.w;
         const float hdt = 0.5f * dt;
-        v.x = v.x * s + hdt * (f.x * minv);
-        v.y = v.y * s + hdt * (f.y * minv);
-        v.z = v.z * s + hdt * (f.z * minv);
+        v.x = kick(__fmul_rn(v.x, s), f.x, minv, hdt);
+        v.y = kick(__fmul_rn(v.y, s), f.y, minv, hdt);
+        v.z = kick(__fmul_rn(v.z, s), f.z, minv, hdt);
         vel[i] = v;
         if (KE)
             ke[0] = 0.5 * (double)v.w
@@ -126,6 +139,231 @@ __global__ void __launch_bounds__(INT_BLOCK)
         if (fin && bussi.rescale)
             *bussi.rescale = bussi_factor(*ke_out, bussi.dof, bussi.dt, bussi.kT, bussi.tau,
                                           bussi.timestep, (uint16_t)bussi.seed, bussi.first_tag);
+        }
+    }
+
+// ---- step two of timestep t fused with step one of timestep t + 1 (the same force array serves both:
+// what step two stores as the acceleration is what the next step one reads, hoomd/md/
+// TwoStepConstantVolume.cc:247-250): one launch, and the velocities written by the first half are read
+// back by the second out of L2 — 96 instead of 144 bytes of HBM traffic per particle while the velocity
+// and force arrays fit in L2.
+// With the Bussi thermostat the factor of step t + 1 depends on the kinetic energy of ALL particles after
+// step two: the kernel is then persistent (one co-resident wave of blocks, each walking "virtual blocks" of
+// INT_BLOCK consecutive particles), the deterministic KE sum is the one of step_two_kernel (same virtual
+// blocks, same trees: bit-identical), the block that completes it draws the factor and publishes a
+// generation word, and every block waits for that word between the halves.
+HB2_DEVICE uint32_t ld_volatile_u32(const uint32_t* p)
+    {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+    }
+
+template<bool THERMO>
+__global__ void __launch_bounds__(INT_BLOCK)
+    step_two_one_kernel(float4* __restrict__ pos, float4* __restrict__ vel, const float4* __restrict__ force,
+                        int* __restrict__ image, uint32_t N, BoxF box, float dt,
+                        const float4* __restrict__ last_pos, float maxshiftsq, uint32_t* __restrict__ d_flag,
+                        double* __restrict__ partial, uint32_t* __restrict__ ticket,
+                        double* __restrict__ ke_out, BussiNext bussi, uint32_t* __restrict__ d_gen,
+                        uint32_t epoch)
+    {
+    __shared__ double s_w[4][INT_BLOCK / 32];
+    __shared__ bool s_last;
+    const uint32_t nvb = (N + INT_BLOCK - 1) / INT_BLOCK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float hdt = 0.5f * dt;
+    // ---- step two of timestep t (no rescale: the factor is applied in step one). FU virtual blocks per
+    // trip: their loads are all issued before the first is used
+    constexpr int FU = 4;
+    for (uint32_t vb0 = blockIdx.x; vb0 < nvb; vb0 += FU * gridDim.x)
+        {
+        float4 v[FU], f[FU];
+        uint32_t idx[FU];
+#pragma unroll
+        for (int u = 0; u < FU; u++)
+            {
+            const uint32_t vb = vb0 + u * gridDim.x;
+            idx[u] = vb < nvb ? vb * INT_BLOCK + threadIdx.x : N;
+            if (idx[u] < N)
+                {
+                v[u] = vel[idx[u]];
+                f[u] = force[idx[u]];
+                }
+            }
+        double ke[FU];
+#pragma unroll
+        for (int u = 0; u < FU; u++)
+            {
+            ke[u] = 0.0;
+            if (idx[u] < N)
+                {
+                const float minv = 1.0f / v[u].w;
+                v[u].x = kick(v[u].x, f[u].x, minv, hdt);
+                v[u].y = kick(v[u].y, f[u].y, minv, hdt);
+                v[u].z = kick(v[u].z, f[u].z, minv, hdt);
+                vel[idx[u]] = v[u];
+                if (THERMO)
+                    ke[u] = 0.5 * (double)v[u].w
+                            * ((double)v[u].x * (double)v[u].x + (double)v[u].y * (double)v[u].y
+                               + (double)v[u].z * (double)v[u].z);
+                }
+            }
+        if (THERMO)
+            {
+            // the block stage of grid_sum, for each of the FU virtual blocks
+#pragma unroll
+            for (int u = 0; u < FU; u++)
+                {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+                    ke[u] += __shfl_xor_sync(0xffffffffu, ke[u], off);
+                if (lane == 0)
+                    s_w[u][warp] = ke[u];
+                }
+            __syncthreads();
+            if (threadIdx.x < FU)
+                {
+                const uint32_t vb = vb0 + threadIdx.x * gridDim.x;
+                if (vb < nvb)
+                    {
+                    double t = 0.0;
+                    for (int w = 0; w < INT_BLOCK / 32; w++)
+                        t += s_w[threadIdx.x][w];
+                    partial[vb] = t;
+                    }
+                }
+            __syncthreads();
+            }
+        }
+    float s = 1.0f;
+    if (THERMO)
+        {
+        if (threadIdx.x == 0)
+            {
+            __threadfence();
+            s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+            }
+        __syncthreads();
+        if (s_last)
+            {
+            // the grid stage of grid_sum over the nvb partials
+            __threadfence();
+            double t = 0.0;
+            for (uint32_t b = threadIdx.x; b < nvb; b += INT_BLOCK)
+                t += partial[b];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+                t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0)
+                s_w[0][warp] = t;
+            __syncthreads();
+            if (threadIdx.x == 0)
+                {
+                double tot = 0.0;
+                for (int w = 0; w < INT_BLOCK / 32; w++)
+                    tot += s_w[0][w];
+                *ke_out = tot;
+                *ticket = 0u;
+                *bussi.rescale = bussi_factor(tot, bussi.dof, bussi.dt, bussi.kT, bussi.tau, bussi.timestep,
+                                              (uint16_t)bussi.seed, bussi.first_tag);
+                __threadfence();
+                atomicExch(d_gen, epoch);
+                }
+            }
+        if (threadIdx.x == 0)
+            {
+            while (ld_volatile_u32(d_gen) != epoch)
+                __nanosleep(64);
+            __threadfence();
+            }
+        __syncthreads();
+        s = (float)__ldcg(bussi.rescale);
+        }
+    // ---- step one of timestep t + 1 (step_one_kernel), two virtual blocks per trip
+    constexpr int GU = 2;
+    for (uint32_t vb0 = blockIdx.x; vb0 < nvb; vb0 += GU * gridDim.x)
+        {
+        float4 pp[GU], vv[GU], ff[GU], qq[GU];
+        uint32_t idx[GU];
+#pragma unroll
+        for (int u = 0; u < GU; u++)
+            {
+            const uint32_t vb = vb0 + u * gridDim.x;
+            idx[u] = vb < nvb ? vb * INT_BLOCK + threadIdx.x : N;
+            if (idx[u] < N)
+                {
+                pp[u] = pos[idx[u]];
+                vv[u] = vel[idx[u]];
+                ff[u] = force[idx[u]];
+                if (last_pos)
+                    qq[u] = last_pos[idx[u]];
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < GU; u++)
+            {
+            const uint32_t i = idx[u];
+            if (i >= N)
+                continue;
+            float4 p = pp[u], v = vv[u];
+            const float4 f = ff[u];
+            const float minv = 1.0f / v.w;
+            v.x = __fmul_rn(kick(v.x, f.x, minv, hdt), s);
+            v.y = __fmul_rn(kick(v.y, f.y, minv, hdt), s);
+            v.z = __fmul_rn(kick(v.z, f.z, minv, hdt), s);
+            p.x = drift(p.x, v.x, dt);
+            p.y = drift(p.y, v.y, dt);
+            p.z = drift(p.z, v.z, dt);
+            int ix = 0, iy = 0, iz = 0;
+            if (p.x >= box.hi[0])
+                {
+                p.x -= box.L[0];
+                ix = 1;
+                }
+            else if (p.x < box.lo[0])
+                {
+                p.x += box.L[0];
+                ix = -1;
+                }
+            if (p.y >= box.hi[1])
+                {
+                p.y -= box.L[1];
+                iy = 1;
+                }
+            else if (p.y < box.lo[1])
+                {
+                p.y += box.L[1];
+                iy = -1;
+                }
+            if (p.z >= box.hi[2])
+                {
+                p.z -= box.L[2];
+                iz = 1;
+                }
+            else if (p.z < box.lo[2])
+                {
+                p.z += box.L[2];
+                iz = -1;
+                }
+            pos[i] = p;
+            vel[i] = v;
+            if (ix | iy | iz)
+                {
+                image[3 * i + 0] += ix;
+                image[3 * i + 1] += iy;
+                image[3 * i + 2] += iz;
+                }
+            if (last_pos)
+                {
+                const float4 q = qq[u];
+                const float dx = min_image_f(p.x - q.x, box.L[0], box.hi[0]);
+                const float dy = min_image_f(p.y - q.y, box.L[1], box.hi[1]);
+                const float dz = min_image_f(p.z - q.z, box.L[2], box.hi[2]);
+                if (dx * dx + dy * dy + dz * dz >= maxshiftsq)
+                    *d_flag = 1u;
+                }
+            }
         }
     }
 
@@ -304,6 +542,49 @@ hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float d
         step_two_kernel<false><<<blocks, INT_BLOCK, 0, stream>>>(vel, force, N, dt, d_rescale,
                                                                  nullptr, nullptr, nullptr, b);
     HB2_CHECK_LAUNCH("step_two_kernel");
+    return HB2_OK;
+    }
+
+// Step two of timestep t and step one of timestep t + 1 in one launch. bussi (with bussi->rescale set):
+// the KE after step two goes to d_ke_out and the factor drawn from it is applied in the step-one half;
+// d_gen is a zero-initialised device word, epoch a value that differs from launch to launch.
+hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
+                               const hb2_box& box, float dt, const float4* last_pos, float maxshift,
+                               uint32_t* d_flag, double* d_ke_partial, uint32_t* d_ticket, double* d_ke_out,
+                               const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream)
+    {
+    if (N == 0)
+        return HB2_OK;
+    const uint32_t nvb = (N + INT_BLOCK - 1) / INT_BLOCK;
+    if (bussi && bussi->rescale)
+        {
+        // one co-resident wave: the blocks wait for each other between the halves
+        static int wave = 0;
+        if (wave == 0)
+            {
+            int dev = 0, sms = 0, per_sm = 0;
+            HB2_CUDA(cudaGetDevice(&dev));
+            HB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            HB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_two_one_kernel<true>, INT_BLOCK, 0));
+            wave = sms * per_sm;
+            if (wave <= 0)
+                {
+                set_error("step_two_one_kernel: no resident blocks");
+                return HB2_ERR_INVALID;
+                }
+            }
+        step_two_one_kernel<true><<<std::min<uint32_t>(nvb, (uint32_t)wave), INT_BLOCK, 0, stream>>>(
+            pos, vel, force, image, N, boxf(box), dt, last_pos, maxshift * maxshift, d_flag, d_ke_partial,
+            d_ticket, d_ke_out, *bussi, d_gen, epoch);
+        }
+    else
+        {
+        BussiNext none;
+        step_two_one_kernel<false><<<nvb, INT_BLOCK, 0, stream>>>(pos, vel, force, image, N, boxf(box), dt, last_pos,
+                                                                  maxshift * maxshift, d_flag, nullptr, nullptr,
+                                                                  nullptr, none, nullptr, 0u);
+        }
+    HB2_CHECK_LAUNCH("step_two_one_kernel");
     return HB2_OK;
     }
 

@@ -135,6 +135,8 @@ struct PairArgs
     const uint32_t* cell_start = nullptr;
     const uint32_t* cell_end = nullptr;
     uint32_t stage_cap = 0;
+    const unsigned char* tile_desc = nullptr; // per-tile descriptors of the last list build
+    uint32_t* tile_ticket = nullptr; // two zeroed words (the persistent tile kernel's work ticket)
     };
 hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairArgs& a,
                               const hb2_box& box, cudaStream_t stream);
@@ -157,6 +159,12 @@ uint32_t step_two_blocks(uint32_t N);
 hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
                            const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
                            double* d_ke_out, cudaStream_t stream, const BussiNext* bussi = nullptr);
+// step two of timestep t fused with step one of timestep t + 1 (integrate.cu); bussi with rescale set:
+// persistent kernel with the grid-wide KE sum and the factor of step t + 1 between the halves
+hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
+                               const hb2_box& box, float dt, const float4* last_pos, float maxshift,
+                               uint32_t* d_flag, double* d_ke_partial, uint32_t* d_ticket, double* d_ke_out,
+                               const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream);
 // TwoStepLangevin step two; d_gamma_coeff = (gamma, sqrt(6 gamma kT / dt)) per type; total <- F + F_bd
 // (what the next step one integrates with)
 hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,

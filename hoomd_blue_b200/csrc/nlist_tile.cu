@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) nlist_build_tile_kernel(const
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t total = tile_layout(L, blockIdx.x, a.tg, a.geom, a.cell_start, a.cell_end);
     const uint32_t ns = L.nk[0] * L.nk[1] * L.nk[2];
-    if (total > a.stage_cap)
+    const uint32_t hcap = tile_hcap(a.stage_cap);
+    if (total > a.stage_cap || L.hoff[8] > hcap)
         {
         if (threadIdx.x == 0)
-            atomicMax(&a.conditions[4], total);
+            atomicMax(&a.conditions[4], max(total, 4u * L.hoff[8]));
         return;
         }
     // ---- 2. staging, shifted into the tile's image (fp32 add: the guard band covers its rounding)
@@ -262,6 +263,71 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) nlist_build_tile_kernel(const
         atomicMax(&a.conditions[0], max_n);
     }
 
+// One warp per tile: the descriptor the force pass's producer warp reads instead of laying the stencil
+// out again on every step (tile.cuh) — header, copy runs (stencil cells that follow each other in memory
+// travel as one bulk copy) and the home records (global index, staged byte offset | row length << 16).
+// Tiles the build kernel rejected (conditions[4]) are skipped: the build is repeated with more room.
+__global__ void __launch_bounds__(TILE_THREADS) tile_desc_kernel(const TileBuildArgs a, const uint32_t ntiles)
+    {
+    __shared__ TileLayout s_L[TILE_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * TILE_WARPS + w;
+    if (tile >= ntiles)
+        return;
+    TileLayout& L = s_L[w];
+    const uint32_t total = tile_layout_warp(L, tile, a.tg, a.geom, a.cell_start, a.cell_end, lane);
+    const uint32_t ns = L.nk[0] * L.nk[1] * L.nk[2];
+    const uint32_t hcap = tile_hcap(a.stage_cap);
+    if (total > a.stage_cap || L.hoff[8] > hcap)
+        return;
+    unsigned char* const desc = a.desc + (size_t)tile * tile_desc_stride(hcap);
+    uint2* const desc_home = reinterpret_cast<uint2*>(desc + sizeof(TileDescHeader));
+    uint4* const runs = reinterpret_cast<uint4*>(desc + sizeof(TileDescHeader) + sizeof(uint2) * (size_t)hcap);
+    uint32_t nruns = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        {
+        const uint32_t s = lane + 32 * h;
+        bool head = false;
+        uint32_t o = 0, g0 = 0, tot = 0;
+        if (s < ns)
+            {
+            o = L.off[s];
+            g0 = L.gstart[s];
+            head = s == 0u || L.gstart[s - 1] + (o - L.off[s - 1]) != g0;
+            if (head)
+                {
+                uint32_t t = s + 1u;
+                tot = L.off[t] - o;
+                while (t < ns && L.gstart[t] == g0 + tot)
+                    {
+                    t++;
+                    tot = L.off[t] - o;
+                    }
+                head = tot != 0u;
+                }
+            }
+        const uint32_t hm = __ballot_sync(0xffffffffu, head);
+        if (head)
+            runs[nruns + __popc(hm & ((1u << lane) - 1u))] = make_uint4(g0, o, tot, 0u);
+        nruns += __popc(hm);
+        }
+    for (uint32_t r = nruns + lane; r < 64u; r += 32u)
+        runs[r] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0)
+        *reinterpret_cast<uint4*>(desc) = make_uint4(1u, L.hoff[8], L.any_shift, total);
+    const uint32_t nh = (L.nk[0] - 2u) * (L.nk[1] - 2u) * (L.nk[2] - 2u);
+    for (uint32_t c = 0; c < nh; c++)
+        {
+        const uint32_t sc = L.hcell[c], g0 = L.gstart[sc], o = L.off[sc], cnt = L.off[sc + 1] - o;
+        for (uint32_t k = lane; k < cnt; k += 32)
+            {
+            const uint32_t n = a.n_neigh[g0 + k];
+            desc_home[L.hoff[c] + k] = make_uint2(g0 + k, ((o + k) * 16u) | (min(n, 0xffffu) << 16));
+            }
+        }
+    }
+
 // rows16 -> global indices in nlist.cu's row layout (entry e of a row at nlist + i * pitch + e)
 __global__ void __launch_bounds__(TILE_THREADS) tile_rows_to_global_kernel(const TileBuildArgs a,
                                                                           uint32_t* __restrict__ nlist,
@@ -310,19 +376,19 @@ hb2_status launch_nlist_build_tiles(const TileBuildArgs& a, const hb2_box& box, 
         return HB2_ERR_INVALID;
         }
     const uint32_t blocks = a.tg.nt[0] * a.tg.nt[1] * a.tg.nt[2];
-    if (a.ntypes > 1)
-        {
-        HB2_CUDA(cudaFuncSetAttribute(nlist_build_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        nlist_build_tile_kernel<true><<<blocks, TILE_THREADS, smem, stream>>>(ka);
-        }
-    else
-        {
-        HB2_CUDA(cudaFuncSetAttribute(nlist_build_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        nlist_build_tile_kernel<false><<<blocks, TILE_THREADS, smem, stream>>>(ka);
-        }
+    auto go = [&](auto kern) -> hb2_status
+    {
+        HB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, TILE_THREADS, smem, stream>>>(ka);
+        return HB2_OK;
+    };
+    const hb2_status st = a.ntypes > 1 ? go(nlist_build_tile_kernel<true>) : go(nlist_build_tile_kernel<false>);
+    if (st != HB2_OK)
+        return st;
     HB2_CHECK_LAUNCH("nlist_build_tile_kernel");
+    // the tiles' descriptors for the force pass (tile.cuh): layout, copy runs, home records
+    tile_desc_kernel<<<(blocks + TILE_WARPS - 1) / TILE_WARPS, TILE_THREADS, 0, stream>>>(a, blocks);
+    HB2_CHECK_LAUNCH("tile_desc_kernel");
     return HB2_OK;
     }
 

@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "tile.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace hb2
     {
@@ -119,6 +120,9 @@ template<class Ev> struct PairKArgs
     const uint32_t* cell_start;
     const uint32_t* cell_end;
     uint32_t stage_cap;
+    uint32_t tile_flags;            // bit 0: L2 prefetch of the rows, bit 1: of the positions (producer warp)
+    const unsigned char* tile_desc; // per-tile descriptors written by the list build (tile.cuh)
+    uint32_t* tile_ticket; // [0] next tile, [1] blocks that ran out (pair_tile.cuh); zero between launches
     };
 
 // MODE: 0 none, 1 shift, 2 xplor (hoomd/md/PotentialPair.h:104-109)
@@ -652,6 +656,12 @@ hb2_status pair_dispatch(hb2_shift_mode mode, const PairArgs& a, const hb2_box& 
     k.cell_start = a.cell_start;
     k.cell_end = a.cell_end;
     k.stage_cap = a.stage_cap;
+    k.tile_ticket = a.tile_ticket;
+    k.tile_desc = a.tile_desc;
+        {
+        static const uint32_t flags = getenv("HB2_TILE_PREFETCH") ? (uint32_t)atoi(getenv("HB2_TILE_PREFETCH")) : 2u;
+        k.tile_flags = flags;
+        }
     if (Ev::needs_thermo && (!a.vel || !a.tag))
         {
         set_error("pair forces: this evaluator needs velocities and tags");

@@ -2,80 +2,87 @@
 // (tile.cuh). Same semantics as pair_kernel.cuh (hoomd/md/PotentialPair.h:587-794,
 // hoomd/md/PotentialPairGPU.cuh:146-404); included by it.
 //
-// One block per tile of 2 x 2 x 2 home cells.
-//  1. tile_layout, then one bulk copy (cp.async.bulk, TMA 1-D, UBLKCP in SASS) per stencil cell brings
-//     the 4 x 4 x 4 stencil's float4 positions — the stored global coordinates, bit for bit — into shared
-//     memory; completion on one mbarrier. No register pass, no LSU wavefronts.
-//  2. Each warp takes four home particles per pass, eight lanes per particle. Lane `sub` reads its four
-//     16-bit neighbour slots of a 32-entry chunk with one coalesced 8-byte load (rows are stored
-//     lane-interleaved, TILE_SLOT) — the next chunk, and the first chunk of the warp's next pass, are
-//     requested before the current one is evaluated — and gathers the four positions with LDS.128 from
-//     the staged stencil instead of through L1.
-//  3. Separations: a tile none of whose stencil cells lies across a periodic boundary uses the plain
-//     difference (exact or correctly rounded); otherwise the (hi, lo) image-shift form of
-//     pair_kernel.cuh. Arithmetic, exact cut-off fix-up and the reduction tree are those of
-//     pair_kernel.cuh: owner-computes, no atomics, bitwise reproducible.
+// A PERSISTENT kernel: a few blocks per SM, each a producer warp and eight consumer warps joined by a
+// two-stage pipeline of tiles in shared memory (mbarriers "full" / "empty" per stage, no
+// __syncthreads after start-up).
+//  * The producer draws the next tile from a global ticket, reads the tile's descriptor — header, home
+//    records (global index, staged offset, row length) and copy runs, written once per list build
+//    (tile.cuh, nlist_tile.cu) — and issues one bulk copy (cp.async.bulk, TMA 1-D, UBLKCP in SASS) for
+//    the header + home records and one per run of stencil cells that are contiguous in memory: the stored
+//    global coordinates arrive bit for bit, without a register pass or LSU wavefronts, while the
+//    consumers are still busy with the previous tile. It also asks for the tile's rows to be brought into
+//    L2 (cp.async.bulk.prefetch.L2) so that the consumers' row loads are short.
+//  * A consumer warp takes four home particles per pass, eight lanes per particle. A lane keeps its four
+//    16-bit neighbour slots of every 32-entry chunk of the row in registers (rows are stored
+//    lane-interleaved, TILE_SLOT: one coalesced 8-byte load per chunk) — the rows of the NEXT pass, also
+//    across a tile boundary, are requested before the current pass is evaluated — and gathers neighbour
+//    positions with LDS.128 from the staged stencil instead of through L1.
+//  * Passes are dealt to the warps round-robin and the deal continues across tiles, so no warp collects
+//    the odd passes; a warp that finishes a tile walks on into the next one without waiting for the others.
+//  * Separations: a tile none of whose stencil cells lies across a periodic boundary uses the plain
+//    difference (exact or correctly rounded); otherwise the (hi, lo) image-shift form of
+//    pair_kernel.cuh. Arithmetic, exact cut-off fix-up and the reduction tree are those of
+//    pair_kernel.cuh: owner-computes, no atomics, bitwise reproducible (the result does not depend on
+//    which block or warp evaluates a particle).
 #pragma once
 
 namespace hb2
     {
-#ifndef PAIR_TILE_MIN_BLOCKS
-#define PAIR_TILE_MIN_BLOCKS 4
-#endif
+constexpr int PT_CONSUMERS = 8;                     // consumer warps per block
+constexpr int PT_THREADS = 32 * (PT_CONSUMERS + 1); // + the producer warp
+constexpr int PT_NPRE = 4;                          // chunks of a row held in registers (longer rows: loads in the loop)
 
-constexpr int PT_HCAP = 384; // home particles of a tile with a record in shared memory
-
-inline size_t pair_tile_smem(uint32_t stage_cap, uint32_t pitch)
+// one pipeline stage in shared memory: [TileDescHeader][home records: hcap x uint2][staged positions]
+inline size_t pair_tile_slot_bytes(uint32_t stage_cap)
     {
-    return ((sizeof(TileLayout) + 15) & ~(size_t)15) + sizeof(float4) * stage_cap
-           + sizeof(uint16_t) * TILE_WARPS * 2 * 4 * pitch;
+    return sizeof(TileDescHeader) + sizeof(uint2) * (size_t)tile_hcap(stage_cap) + sizeof(float4) * stage_cap;
+    }
+inline size_t pair_tile_smem(uint32_t stage_cap)
+    {
+    return 2 * pair_tile_slot_bytes(stage_cap);
     }
 
-// does any stencil cell of this tile lie across a periodic boundary? (geometry only: the same answer as
-// TileLayout::any_shift, before anything is loaded)
-HB2_DEVICE bool tile_is_shifting(const uint32_t tile, const TileGeom& tg, const DomainGeom& geom)
+HB2_DEVICE void mbar_arrive(uint64_t* bar)
     {
-    const uint32_t tt[3] = {tile % tg.nt[0], (tile / tg.nt[0]) % tg.nt[1], tile / (tg.nt[0] * tg.nt[1])};
-    bool sh = false;
-#pragma unroll
-    for (int d = 0; d < 3; d++)
-        {
-        const int c0 = (int)(tg.first[d] + 2u * tt[d]);
-        const int nc = min(2, (int)(tg.first[d] + geom.dimi[d]) - c0);
-        const int below = c0 - 1, above = c0 + nc;
-        if (geom.n[d] > 1)
-            sh = sh || (below == 0 && geom.coord[d] == 0) || (above == (int)geom.dimt[d] - 1 && geom.coord[d] == geom.n[d] - 1);
-        else
-            sh = sh || below < 0 || above >= (int)geom.dimt[d];
-        }
-    return sh;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+    }
+HB2_DEVICE void bulk_prefetch_l2(const void* src, uint32_t bytes)
+    {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     }
 
-// Tiles that touch a periodic boundary use the (hi, lo) image-shift separations of pair_kernel.cuh; their
-// per-particle shift operands live in shared memory (one slot per thread, read inside the pair loop), so
-// that the plain tiles' loop — all tiles but a surface layer — does not carry nine more registers.
 template<class Ev, int MODE, bool VIRIAL, bool ONETYPE, bool ENERGY>
-__global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_TILE_MIN_BLOCKS)
+__global__ void __launch_bounds__(PT_THREADS, (VIRIAL || !ONETYPE) ? 2 : 3)
     pair_force_tile_kernel(const PairKArgs<Ev> a)
     {
     typedef typename Ev::param_type param_type;
     if (a.skip_flag && *a.skip_flag)
         return;
-    const bool SHIFT = tile_is_shifting(blockIdx.x, a.tg, a.geom);
     __shared__ param_type s_params[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_rcutsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
     __shared__ float s_ronsq[ONETYPE ? 1 : PAIR_MAX_TYPES_SMEM * PAIR_MAX_TYPES_SMEM];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(8) uint2 s_home[PT_HCAP];   // global index, staged byte offset | n_neigh << 16
-    __shared__ float2 s_shift[3][TILE_THREADS / 8];  // (hi, lo) of pi -/+ L per component and particle
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    __shared__ float2 s_shift[3][PT_CONSUMERS * 4]; // (hi, lo) of pi -/+ L per component and particle
     extern __shared__ __align__(128) unsigned char s_raw[];
-    TileLayout& L = *reinterpret_cast<TileLayout*>(s_raw);
-    float4* __restrict__ stage = reinterpret_cast<float4*>(s_raw + ((sizeof(TileLayout) + 15) & ~(size_t)15));
-    uint16_t* rowbuf_all = reinterpret_cast<uint16_t*>(stage + a.stage_cap);
+    const uint32_t hcap = tile_hcap(a.stage_cap);
+    const uint32_t home_off = (uint32_t)sizeof(TileDescHeader);
+    const uint32_t stage_off = home_off + (uint32_t)sizeof(uint2) * hcap;
+    const uint32_t slot_bytes = stage_off + (uint32_t)sizeof(float4) * a.stage_cap;
+    const size_t desc_stride = tile_desc_stride(hcap);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t ntiles = a.tg.nt[0] * a.tg.nt[1] * a.tg.nt[2];
+    const uint32_t pitch_b = a.pitch * 2u; // bytes per row
 
     if (threadIdx.x == 0)
-        mbar_init(&s_bar, 1);
+        {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], PT_CONSUMERS);
+        mbar_init(&s_empty[1], PT_CONSUMERS);
+        // slot 0 of either stage: the far-away dummy (the copies start at slot 1)
+        *reinterpret_cast<float4*>(s_raw + stage_off) = make_float4(NL_FAR, NL_FAR, NL_FAR, 0.f);
+        *reinterpret_cast<float4*>(s_raw + slot_bytes + stage_off) = make_float4(NL_FAR, NL_FAR, NL_FAR, 0.f);
+        }
     if (!ONETYPE)
         {
         const uint32_t nt2 = a.ntypes * a.ntypes;
@@ -86,109 +93,116 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
             s_ronsq[t] = a.ronsq[t];
             }
         }
-    const uint32_t total = tile_layout(L, blockIdx.x, a.tg, a.geom, a.cell_start, a.cell_end);
-    const uint32_t ns = L.nk[0] * L.nk[1] * L.nk[2];
-    if (total > a.stage_cap)
-        __trap(); // the build ran with the same capacity over the same cells
-    // ---- 1. stage the stencil: warp 0 issues the bulk copies
-    if (w == 0)
-        {
-        if (lane == 0)
-            {
-            stage[0] = make_float4(NL_FAR, NL_FAR, NL_FAR, 0.f);
-            mbar_expect_tx(&s_bar, (total - 1u) * (uint32_t)sizeof(float4));
-            }
-        __syncwarp();
-        // stencil cells that follow each other in memory (the x-neighbours of a row-major cell order)
-        // travel as one copy: the lane of the first cell of such a run issues it
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-            {
-            const uint32_t s = lane + 32 * h;
-            if (s < ns)
-                {
-                const uint32_t o = L.off[s], g0 = L.gstart[s];
-                const bool head = s == 0u || L.gstart[s - 1] + (o - L.off[s - 1]) != g0;
-                if (head)
-                    {
-                    uint32_t t = s + 1u, tot = L.off[t] - o;
-                    while (t < ns && L.gstart[t] == g0 + tot)
-                        {
-                        t++;
-                        tot = L.off[t] - o;
-                        }
-                    if (tot)
-                        bulk_copy_g2s(stage + o, a.pos + g0, tot * (uint32_t)sizeof(float4), &s_bar);
-                    }
-                }
-            }
-        }
-    const uint32_t nhome = L.hoff[8];
-    const uint32_t npass = (nhome + 3u) >> 2;
-    const uint32_t sub = lane & 7u, grp = lane >> 3;
-
-    // home slot hs of the tile -> (global index, staged byte offset | n_neigh << 16)
-    auto resolve = [&](const uint32_t hs) -> uint2
-    {
-        uint32_t c = (hs >= L.hoff[4]) ? 4u : 0u;
-        c += (hs >= L.hoff[c + 2]) ? 2u : 0u;
-        c += (hs >= L.hoff[c + 1]) ? 1u : 0u;
-        const uint32_t sc = L.hcell[c], k = hs - L.hoff[c];
-        const uint32_t gi = L.gstart[sc] + k;
-        return make_uint2(gi, ((L.off[sc] + k) * 16u) | (__ldg(a.n_neigh + gi) << 16));
-    };
-    for (uint32_t hs = threadIdx.x; hs < min(nhome, (uint32_t)PT_HCAP); hs += TILE_THREADS)
-        s_home[hs] = resolve(hs);
-    // the positions have landed (one warp polls the mbarrier; the others sleep in the block barrier)
-    if (w == 0)
-        mbar_wait(&s_bar, 0);
     __syncthreads();
-    const uint32_t home_s = smem_u32(s_home);
-    auto home = [&](const uint32_t hs) -> uint2
-    {
-        if (hs >= nhome)
-            return make_uint2(0u, 0u); // no particle: the far-away dummy with an empty row
-        if (hs < (uint32_t)PT_HCAP)
-            return lds64(home_s + hs * 8u);
-        return resolve(hs);
-    };
 
-    // ---- 2. rows: 16-byte asynchronous copies (cp.async, LDGSTS) into a per-warp double buffer, requested
-    // one pass ahead. Lane `sub` of a particle copies quarter sub & 3 of chunks sub >> 2, sub >> 2 + 2, ...
-    const uint32_t stage_s = smem_u32(stage);
-    const uint32_t pitch_b = a.pitch * 2u; // bytes per row
-    const uint32_t rowbuf_s = smem_u32(rowbuf_all) + (uint32_t)w * (8u * pitch_b) + grp * pitch_b;
-    const uint32_t lane_off = (sub >> 2) * 64u + (sub & 3u) * 16u;
-    auto request_rows = [&](const uint2 h, const uint32_t b)
+    if (w == PT_CONSUMERS)
+        {
+        // ================= producer =================
+        // The ticket and the descriptor of the NEXT tile are drawn right after a tile's copies are issued,
+        // and the next tile's positions and rows are asked into L2 before its stage is free: the path from
+        // "stage released" to "tile landed" is one bulk copy out of L2.
+        uint32_t tile = 0;
+        uint4 hdr = make_uint4(0u, 0u, 0u, 0u), r0 = hdr, r1 = hdr;
+        const unsigned char* desc = nullptr;
+        auto draw = [&]()
+        {
+            if (lane == 0)
+                tile = atomicAdd(a.tile_ticket, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile < ntiles)
+                {
+                desc = a.tile_desc + (size_t)tile * desc_stride;
+                // (the runs follow the hcap home records: the same offset as the staged array in a stage)
+                const uint4* const runs = reinterpret_cast<const uint4*>(desc + stage_off);
+                hdr = __ldg(reinterpret_cast<const uint4*>(desc)); // valid, nhome, shifting, total
+                r0 = __ldg(runs + lane);
+                r1 = __ldg(runs + 32 + lane);
+                }
+        };
+        draw();
+        for (uint32_t it = 0;; it++)
+            {
+            const uint32_t b = it & 1u;
+            unsigned char* const slot = s_raw + b * slot_bytes;
+            if (tile >= ntiles)
+                {
+                if (it >= 2u)
+                    mbar_wait(&s_empty[b], ((it >> 1) - 1u) & 1u);
+                if (lane == 0)
+                    {
+                    reinterpret_cast<TileDescHeader*>(slot)->valid = 0u;
+                    mbar_arrive(&s_full[b]);
+                    // the last block to run out re-arms the ticket for the next launch
+                    if (atomicAdd(a.tile_ticket + 1, 1u) == gridDim.x - 1u)
+                        {
+                        a.tile_ticket[0] = 0u;
+                        a.tile_ticket[1] = 0u;
+                        }
+                    }
+                break;
+                }
+            const uint32_t nhome = hdr.y;
+            // into L2 ahead of use: the stencil's positions and the rows of the home particles
+            if (r0.z && (a.tile_flags & 2u))
+                bulk_prefetch_l2(a.pos + r0.x, r0.z * (uint32_t)sizeof(float4));
+            if (r1.z && (a.tile_flags & 2u))
+                bulk_prefetch_l2(a.pos + r1.x, r1.z * (uint32_t)sizeof(float4));
+            const uint2* const dh = reinterpret_cast<const uint2*>(desc + home_off);
+            for (uint32_t hs = lane; hs < ((a.tile_flags & 1u) ? nhome : 0u); hs += 32u)
+                {
+                const uint2 h = __ldg(dh + hs);
+                const uint32_t nch = ((h.y >> 16) + 31u) >> 5;
+                if (nch)
+                    bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(a.rows16) + (size_t)h.x * pitch_b, nch * 64u);
+                }
+            if (it >= 2u) // the consumers have left the tile this stage held before
+                mbar_wait(&s_empty[b], ((it >> 1) - 1u) & 1u);
+            const uint32_t head_bytes = (home_off + (uint32_t)sizeof(uint2) * nhome + 15u) & ~15u;
+            if (lane == 0)
+                {
+                mbar_expect_tx(&s_full[b], head_bytes + (hdr.w - 1u) * (uint32_t)sizeof(float4));
+                bulk_copy_g2s(slot, desc, head_bytes, &s_full[b]);
+                }
+            if (r0.z)
+                bulk_copy_g2s(slot + stage_off + r0.y * 16u, a.pos + r0.x, r0.z * (uint32_t)sizeof(float4), &s_full[b]);
+            if (r1.z)
+                bulk_copy_g2s(slot + stage_off + r1.y * 16u, a.pos + r1.x, r1.z * (uint32_t)sizeof(float4), &s_full[b]);
+            __syncwarp();
+            draw();
+            }
+        return;
+        }
+
+    // ================= consumers =================
+    const uint32_t sub = lane & 7u, grp = lane >> 3;
+    const unsigned char* const rows_b = reinterpret_cast<const unsigned char*>(a.rows16) + sub * 8u;
+    auto header_of = [&](const uint32_t b) -> const TileDescHeader&
+    { return *reinterpret_cast<const TileDescHeader*>(s_raw + b * slot_bytes); };
+    auto home = [&](const uint32_t b, const uint32_t hs) -> uint2
+    {
+        if (hs >= header_of(b).nhome)
+            return make_uint2(0u, 0u); // no particle: the far-away dummy with an empty row
+        return *reinterpret_cast<const uint2*>(s_raw + b * slot_bytes + home_off + hs * 8u);
+    };
+    // this lane's four slots of each of the first PT_NPRE chunks of a row
+    auto load_rows = [&](const uint2 h, uint2 (&ix)[PT_NPRE])
     {
         const uint32_t nch = ((h.y >> 16) + 31u) >> 5;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.rows16) + (size_t)h.x * pitch_b + lane_off;
-        uint32_t dst = rowbuf_s + b * (4u * pitch_b) + lane_off;
-        for (uint32_t c = sub >> 2; c < nch; c += 2u)
-            {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            src += 128;
-            dst += 128u;
-            }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        const uint2* src = reinterpret_cast<const uint2*>(rows_b + (size_t)h.x * pitch_b);
+#pragma unroll
+        for (int c = 0; c < PT_NPRE; c++)
+            ix[c] = (uint32_t)c < nch ? __ldg(src + 8 * c) : make_uint2(0u, 0u);
     };
 
-    uint32_t q = w;
-    uint2 hcur = home(4u * q + grp);
-    request_rows(hcur, 0u);
-    uint32_t b = 0;
+    const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
+    const uint32_t shift_s = smem_u32(&s_shift[0][w * 4 + grp]);
 
-    while (q < npass)
-        {
-        const uint32_t qn = q + TILE_WARPS;
-        // this pass's rows have landed; the other buffer was last read in pass q - 1 (the reduction's
-        // shuffles at its end joined the warp), so the next pass's rows can be requested into it
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        const uint2 hnext = home(4u * qn + grp);
-        request_rows(hnext, b ^ 1u);
-
-        const bool valid = 4u * q + grp < nhome;
+    // ---- one pass: four home particles of the tile in stage b
+    auto compute_pass = [&](const uint32_t b, const uint2 hcur, const uint2 (&ic)[PT_NPRE])
+    {
+        const uint32_t stage_s = smem_u32(s_raw + b * slot_bytes + stage_off);
+        const bool SHIFT = header_of(b).shifting != 0u;
+        const bool valid = hcur.y != 0u;
         const uint32_t gi = hcur.x, n = hcur.y >> 16;
         const float4 pi = lds128(stage_s + (hcur.y & 0xffffu));
         const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
@@ -291,19 +305,19 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                 }
         };
 
-        // (hi, lo) of pi -/+ L, see pair_kernel.cuh
+        // (hi, lo) of pi -/+ L, see pair_kernel.cuh; kept in shared memory so that the plain tiles' loop
+        // — all tiles but a surface layer — does not carry six more registers
         const float pc[3] = {pi.x, pi.y, pi.z};
-        const float hc[3] = {a.box.hi[0], a.box.hi[1], a.box.hi[2]};
-        const uint32_t shift_s = smem_u32(&s_shift[0][threadIdx.x >> 3]);
         if (SHIFT)
             {
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 {
                 const double m = pc[c] >= 0.f ? (double)pc[c] - a.boxd.L[c] : (double)pc[c] + a.boxd.L[c];
                 const float hi = (float)m;
                 if (sub == 0u)
-                    s_shift[c][threadIdx.x >> 3] = make_float2(hi, (float)(m - (double)hi));
+                    s_shift[c][w * 4 + grp] = make_float2(hi, (float)(m - (double)hi));
                 }
             __syncwarp();
             }
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 {
-                const uint2 hl = lds64(shift_s + c * (uint32_t)(TILE_THREADS / 8 * sizeof(float2)));
+                const uint2 hl = lds64(shift_s + c * (uint32_t)(PT_CONSUMERS * 4 * sizeof(float2)));
                 const float sh = __uint_as_float(hl.x), sl = __uint_as_float(hl.y);
 #pragma unroll
                 for (int u = 0; u < 4; u++)
@@ -328,20 +342,16 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
         auto rsq_of = [](const float dx, const float dy, const float dz)
         { return fmaf(dz, dz, fmaf(dy, dy, dx * dx)); };
 
-        const uint32_t idx_s = rowbuf_s + b * (4u * pitch_b) + sub * 8u;
-        for (uint32_t c = 0; c < nch_warp; c++)
-            {
-            uint2 wc = lds64(idx_s + c * 64u);
-            if (c >= nchunks) // a shorter row than the warp's longest: the dummy slot
-                wc = make_uint2(0u, 0u);
-            // row entries are staged slots times 16: byte offsets into the staged array
+        // one 32-entry chunk: wc = this lane's four staged byte offsets
+        auto chunk = [&](const uint2 wc, const bool shifted)
+        {
             float4 pj[4];
             pj[0] = lds128(stage_s + (wc.x & 0xffffu));
             pj[1] = lds128(stage_s + (wc.x >> 16));
             pj[2] = lds128(stage_s + (wc.y & 0xffffu));
             pj[3] = lds128(stage_s + (wc.y >> 16));
             float dxs[4], dys[4], dzs[4];
-            if (!SHIFT)
+            if (!shifted)
                 {
 #pragma unroll
                 for (int u = 0; u < 4; u++)
@@ -370,25 +380,44 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                     pair_body(pj[u], dxs[u], dys[u], dzs[u], rsq, 1.0f);
                     }
                 }
-            }
+        };
+        auto walk = [&](const bool shifted)
+        {
+#pragma unroll
+            for (int c = 0; c < PT_NPRE; c++)
+                if ((uint32_t)c < nch_warp)
+                    chunk(ic[c], shifted);
+            if (nch_warp > (uint32_t)PT_NPRE)
+                {
+                // rows longer than the register window
+                const uint2* src = reinterpret_cast<const uint2*>(rows_b + (size_t)gi * pitch_b);
+                for (uint32_t c = PT_NPRE; c < nch_warp; c++)
+                    chunk(c < nchunks ? __ldg(src + 8u * c) : make_uint2(0u, 0u), shifted);
+                }
+        };
+        if (SHIFT)
+            walk(true);
+        else
+            walk(false);
+
         if (near_min <= 64u)
             {
             // rare (about one pass in 1e5): some rsq came within 32 ulp of r_cut^2. Re-walk the row, decide
             // those pairs with the CPU build's exact arithmetic — the staged positions ARE the stored
             // global coordinates — and repair the pairs where fp32 and the reference disagree.
-            const uint16_t* __restrict__ row
-                = rowbuf_all + (size_t)((w * 2u + b) * 4u + grp) * a.pitch + 4u * sub;
+            const uint16_t* __restrict__ row = a.rows16 + (size_t)gi * a.pitch + 4u * sub;
+            const float4* stage = reinterpret_cast<const float4*>(s_raw + b * slot_bytes + stage_off);
             for (uint32_t e = 0; e < nchunks * 4u; e++)
                 {
                 // this lane's storage slots: 4 sub .. 4 sub + 3 of every chunk
-                const uint32_t jj = row[(e >> 2) * 32u + (e & 3u)];
+                const uint32_t jj = __ldg(row + (e >> 2) * 32u + (e & 3u));
                 if (jj == 0u)
                     continue;
                 const float4 qq = stage[jj >> 4];
                 float dx = pi.x - qq.x, dy = pi.y - qq.y, dz = pi.z - qq.z;
                 if (SHIFT)
                     {
-                    const float2 sx = s_shift[0][threadIdx.x >> 3], sy = s_shift[1][threadIdx.x >> 3], sz = s_shift[2][threadIdx.x >> 3];
+                    const float2 sx = s_shift[0][w * 4 + grp], sy = s_shift[1][w * 4 + grp], sz = s_shift[2][w * 4 + grp];
                     dx = fabsf(dx) >= hc[0] ? (sx.x - qq.x) + sx.y : dx;
                     dy = fabsf(dy) >= hc[1] ? (sy.x - qq.y) + sy.y : dy;
                     dz = fabsf(dz) >= hc[2] ? (sz.x - qq.z) + sz.y : dz;
@@ -455,21 +484,163 @@ __global__ void __launch_bounds__(TILE_THREADS, (VIRIAL || !ONETYPE) ? 3 : PAIR_
                 a.virial[5 * a.virial_pitch + gi] = vzz;
                 }
             }
-        q = qn;
+    };
+
+    // ---- the walk over tiles. Pass p of a tile goes to warp (p + rot) mod 8 and rot advances by the
+    // tile's pass count: the deal continues across tiles. (it, b, rot, npass) is the tile the warp is
+    // positioned on — acquired: its stage has landed; q is this warp's next pass in it.
+    // The rows of an item are loaded at ONE place in the loop and reach the evaluation through register
+    // copies only, so that the evaluation of one pass never waits on the loads of the next.
+    // The walk's state is five registers — it, rot, q, npass and a word of flags (separate bools ended up
+    // in local memory, and a local load queues behind the row loads in the L1 pipe).
+    uint32_t it = 0, rot = 0, q = 0, npass = 0;
+    constexpr uint32_t F_ITEM = 1u, F_CUR = 2u, F_LAST = 4u, F_ENDED = 8u;
+    // F_ITEM: (it, q) names the next pass to fetch; F_CUR: hcur / ic hold a pass to evaluate;
+    // F_LAST: that pass is the warp's last in its tile (stage (it - 1) & 1, released after it);
+    // F_ENDED: the ticket ran out
+    uint32_t flags = 0;
+    auto arrive = [&](const uint32_t stage)
+    {
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(&s_empty[stage]);
+    };
+    // from the acquired tile on: the first tile that holds a pass for this warp (tiles without one are
+    // released at once); false: the ticket ran out
+    auto seek = [&]() -> bool
+    {
+        for (;;)
+            {
+            q = ((uint32_t)w - rot) & (PT_CONSUMERS - 1);
+            if (q < npass)
+                return true;
+            arrive(it & 1u);
+            rot = (rot + npass) & (PT_CONSUMERS - 1);
+            it++;
+            mbar_wait(&s_full[it & 1u], (it >> 1) & 1u);
+            if (header_of(it & 1u).valid == 0u)
+                return false;
+            npass = (header_of(it & 1u).nhome + 3u) >> 2;
+            }
+    };
+    mbar_wait(&s_full[0], 0u);
+    if (header_of(0).valid == 0u)
+        return;
+    npass = (header_of(0).nhome + 3u) >> 2;
+    flags = seek() ? F_ITEM : F_ENDED;
+    uint2 hcur = make_uint2(0u, 0u), ic[PT_NPRE];
+#pragma unroll
+    for (int c = 0; c < PT_NPRE; c++)
+        ic[c] = make_uint2(0u, 0u);
+    for (;;)
+        {
+        uint2 hnext = make_uint2(0u, 0u), in_[PT_NPRE];
+#pragma unroll
+        for (int c = 0; c < PT_NPRE; c++)
+            in_[c] = make_uint2(0u, 0u);
+        if (flags & F_ITEM)
+            {
+            hnext = home(it & 1u, 4u * q + grp);
+            load_rows(hnext, in_);
+            }
+        if (flags & F_CUR)
+            {
+            const uint32_t bcur = (it - ((flags & F_LAST) ? 1u : 0u)) & 1u;
+            compute_pass(bcur, hcur, ic);
+            if (flags & F_LAST)
+                arrive(bcur);
+            }
+        if (!(flags & F_ITEM))
+            {
+            if (flags & F_ENDED)
+                break;
+            // the tile the warp is positioned on holds no pass for it (a small tile): walk on
+            flags = seek() ? F_ITEM : F_ENDED;
+            if (flags & F_ENDED)
+                break;
+            continue;
+            }
         hcur = hnext;
-        b ^= 1u;
+#pragma unroll
+        for (int c = 0; c < PT_NPRE; c++)
+            ic[c] = in_[c];
+        flags = F_ITEM | F_CUR;
+        // the item after this one
+        q += PT_CONSUMERS;
+        if (q >= npass)
+            {
+            // look into the next tile: its stage was released by this warp before it entered the current
+            // one, which is released once the item just fetched has been evaluated
+            flags = F_CUR | F_LAST;
+            rot = (rot + npass) & (PT_CONSUMERS - 1);
+            it++;
+            mbar_wait(&s_full[it & 1u], (it >> 1) & 1u);
+            if (header_of(it & 1u).valid == 0u)
+                flags |= F_ENDED;
+            else
+                {
+                npass = (header_of(it & 1u).nhome + 3u) >> 2;
+                q = ((uint32_t)w - rot) & (PT_CONSUMERS - 1);
+                if (q < npass)
+                    flags |= F_ITEM;
+                }
+            }
         }
+    }
+
+// blocks per SM of a kernel instantiation at this shared-memory size (cached per kernel: instantiations
+// share the function-pointer type, so the key is the pointer)
+template<class K> int pair_tile_occupancy(K kern, size_t smem)
+    {
+    struct Entry
+        {
+        const void* fn;
+        size_t smem;
+        int blocks;
+        };
+    static std::vector<Entry> cache;
+    for (const Entry& e : cache)
+        if (e.fn == (const void*)kern && e.smem == smem)
+            return e.blocks;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return 0;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PT_THREADS, smem) != cudaSuccess)
+        return 0;
+    for (Entry& e : cache)
+        if (e.fn == (const void*)kern)
+            {
+            e.smem = smem;
+            e.blocks = nb;
+            return nb;
+            }
+    cache.push_back({(const void*)kern, smem, nb});
+    return nb;
     }
 
 template<class Ev, int MODE, bool VIRIAL>
 hb2_status pair_tile_launch(const PairKArgs<Ev>& k, cudaStream_t stream)
     {
-    const uint32_t blocks = k.tg.nt[0] * k.tg.nt[1] * k.tg.nt[2];
-    const size_t smem = pair_tile_smem(k.stage_cap, k.pitch);
+    const uint32_t ntiles = k.tg.nt[0] * k.tg.nt[1] * k.tg.nt[2];
+    const size_t smem = pair_tile_smem(k.stage_cap);
+    static int sms = 0;
+    if (sms == 0)
+        {
+        int dev = 0;
+        HB2_CUDA(cudaGetDevice(&dev));
+        HB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
     auto go = [&](auto kern) -> hb2_status
     {
-        HB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, TILE_THREADS, smem, stream>>>(k);
+        const int per_sm = pair_tile_occupancy(kern, smem);
+        if (per_sm <= 0)
+            {
+            cudaGetLastError();
+            set_error("pair forces (tiles): the pipeline does not fit in shared memory");
+            return HB2_ERR_INVALID;
+            }
+        const uint32_t blocks = std::min<uint32_t>(ntiles, (uint32_t)(per_sm * sms));
+        kern<<<blocks, PT_THREADS, smem, stream>>>(k);
         HB2_CHECK_LAUNCH("pair_force_tile_kernel");
         return HB2_OK;
     };

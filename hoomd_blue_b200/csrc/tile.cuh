@@ -35,6 +35,28 @@ constexpr int TILE_WARPS = TILE_THREADS / 32;
 #define TILE_SLOT(e) ((((e) & 7u) << 2) | ((e) >> 3))
 #define TILE_ENTRY(s) ((((s) & 3u) << 3) | ((s) >> 2))
 
+// ---- per-tile descriptor: written by the list build (the layout only changes when the particles are
+// re-binned), read by the force pass's producer warp, so that no step lays a stencil out again.
+//   [TileDescHeader][home records: hcap x uint2][runs: TILE_MAXC x uint4]
+// home record: (global index, staged byte offset | n_neigh << 16), in the tile's home order;
+// run: (global index of the first particle, staged slot of the first particle, particles, 0) — the stencil
+// cells that follow each other in memory travel as one bulk copy; unused runs have zero particles.
+struct TileDescHeader
+    {
+    uint32_t valid;    // 1 (the force pass writes 0 into its shared-memory copy when the tiles ran out)
+    uint32_t nhome;    // home particles
+    uint32_t shifting; // some stencil cell lies across a periodic boundary
+    uint32_t total;    // staged slots including the dummy slot 0
+    };
+HB2_HOSTDEVICE uint32_t tile_hcap(uint32_t stage_cap) // home records per tile: a quarter of the stencil's slots
+    {
+    return (stage_cap / 4u + 1u) & ~1u;
+    }
+HB2_HOSTDEVICE size_t tile_desc_stride(uint32_t hcap)
+    {
+    return sizeof(TileDescHeader) + sizeof(uint2) * (size_t)hcap + sizeof(uint4) * 64;
+    }
+
 struct TileGeom // passed by value to kernels
     {
     uint32_t nt[3];    // tiles along x, y, z (over the interior cells)
@@ -105,14 +127,13 @@ HB2_DEVICE void tile_dim(int c0, int ncell, int dimt, int n, int rc, int k, int&
         }
     }
 
-// Block-wide: resolve the stencil of tile `tile`, lay its cells out back to back (slot 0 = dummy) and
-// list the home cells. Ends with a __syncthreads(); returns the number of staged slots.
-// n_owned: owned particles occupy [0, n_owned) — home cells are interior cells and hold only those.
-HB2_DEVICE uint32_t tile_layout(TileLayout& L, uint32_t tile, const TileGeom& tg, const DomainGeom& geom,
-                                const uint32_t* __restrict__ cell_start,
-                                const uint32_t* __restrict__ cell_end)
+// One warp: resolve the stencil of tile `tile`, lay its cells out back to back (slot 0 = dummy) and
+// list the home cells (interior cells: they hold owned particles only). t = lane. Ends with a
+// __syncwarp(); returns the number of staged slots.
+HB2_DEVICE uint32_t tile_layout_warp(TileLayout& L, uint32_t tile, const TileGeom& tg, const DomainGeom& geom,
+                                     const uint32_t* __restrict__ cell_start,
+                                     const uint32_t* __restrict__ cell_end, const int t)
     {
-    const int t = threadIdx.x;
     const uint32_t tx = tile % tg.nt[0], ty = (tile / tg.nt[0]) % tg.nt[1], tz = tile / (tg.nt[0] * tg.nt[1]);
     const uint32_t tt[3] = {tx, ty, tz};
     int c0[3], nc[3], nk[3];
@@ -124,7 +145,6 @@ HB2_DEVICE uint32_t tile_layout(TileLayout& L, uint32_t tile, const TileGeom& tg
         nk[d] = nc[d] + 2;
         }
     const int ns = nk[0] * nk[1] * nk[2];
-    if (t < 32)
         {
         // lane l resolves stencil cells l and l + 32
         uint32_t cnt[2] = {0u, 0u};
@@ -185,8 +205,19 @@ HB2_DEVICE uint32_t tile_layout(TileLayout& L, uint32_t tile, const TileGeom& tg
         if (t == 8)
             L.hoff[8] = htot;
         }
-    __syncthreads();
+    __syncwarp();
     return L.off[ns];
+    }
+
+// Block-wide form: warp 0 lays the tile out; ends with a __syncthreads().
+HB2_DEVICE uint32_t tile_layout(TileLayout& L, uint32_t tile, const TileGeom& tg, const DomainGeom& geom,
+                                const uint32_t* __restrict__ cell_start,
+                                const uint32_t* __restrict__ cell_end)
+    {
+    if (threadIdx.x < 32)
+        tile_layout_warp(L, tile, tg, geom, cell_start, cell_end, (int)threadIdx.x);
+    __syncthreads();
+    return L.off[L.nk[0] * L.nk[1] * L.nk[2]];
     }
 
 // stencil cell that holds staged slot q (1 <= q < L.off[ns]): the last s with off[s] <= q
@@ -259,6 +290,7 @@ struct TileBuildArgs
     uint32_t* conditions; // [0] <- max n_neigh, [4] <- staged slots needed when they exceed stage_cap,
                           // [5] <- candidates of one home cell when they exceed the table capacity
     uint32_t stage_cap;   // staged slots (float4) a block may hold
+    unsigned char* desc;  // per-tile descriptors (tile_desc_stride(tile_hcap(stage_cap)) bytes each)
     };
 hb2_status launch_nlist_build_tiles(const TileBuildArgs& a, const hb2_box& box, cudaStream_t stream);
 // rows16 -> rows of global indices (the layout of nlist.cu, without its ascending order across cells)
