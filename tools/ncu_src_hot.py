@@ -1,17 +1,18 @@
 """Per-SASS-instruction execution counts of the first kernel in an ncu report: plateaus of equal count
-(loop structure) and the instructions with the most stall samples. usage: ncu_src_hot.py report.ncu-rep"""
+(loop structure) and the instructions with the most stall samples. usage: ncu_src_hot.py report.ncu-rep [n_top [kernel-name substring]]"""
 import csv, subprocess, sys, io
 txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--print-source", "sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-out = []; k = 0
+out = []; k = 0; want = sys.argv[3] if len(sys.argv) > 3 else ""; on = False
 for r in rows:
     if r and r[0] == "Kernel Name":
-        k += 1
-        if k > 1: break
-        print(r[1][:100]); continue
+        if on: break
+        on = want in r[1]
+        if on: print(r[1][:100])
+        continue
     if r and r[0] == "Address": hdr = r; continue
-    if len(r) > 10: out.append(r)
+    if on and len(r) > 10: out.append(r)
 ix = {h: i for i, h in enumerate(hdr)}
 E_ = ix["Instructions Executed"]
 tot = sum(int(r[E_]) for r in out)
