@@ -201,10 +201,21 @@ __global__ void __launch_bounds__(PT_THREADS, (VIRIAL || !ONETYPE) ? 2 : 3)
     auto compute_pass = [&](const uint32_t b, const uint2 hcur, const uint2 (&ic)[PT_NPRE])
     {
         const uint32_t stage_s = smem_u32(s_raw + b * slot_bytes + stage_off);
-        const bool SHIFT = header_of(b).shifting != 0u;
         const bool valid = hcur.y != 0u;
         const uint32_t gi = hcur.x, n = hcur.y >> 16;
         const float4 pi = lds128(stage_s + (hcur.y & 0xffffu));
+        // In a tile that touches a periodic boundary only the particles within reach of a (global) face
+        // can have a neighbour across it (the face_margin test of pair_kernel.cuh): half the passes of a
+        // face tile take the plain loop.
+        bool SHIFT = header_of(b).shifting != 0u;
+        if (SHIFT)
+            {
+            const float m = a.face_margin > 0.f ? a.face_margin : 3.0e38f;
+            const bool near_face = valid
+                                   && ((pi.x >= a.box.hi[0] - m) || (pi.x < a.box.lo[0] + m) || (pi.y >= a.box.hi[1] - m)
+                                       || (pi.y < a.box.lo[1] + m) || (pi.z >= a.box.hi[2] - m) || (pi.z < a.box.lo[2] + m));
+            SHIFT = __any_sync(0xffffffffu, near_face);
+            }
         const uint32_t ti = ONETYPE ? 0u : __float_as_uint(pi.w);
         const uint32_t nchunks = (n + 31u) >> 5;
         const uint32_t nch_warp = __reduce_max_sync(0xffffffffu, nchunks);

@@ -359,7 +359,11 @@ hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT, const doub
                                        uint32_t ntypes);
 /* System::run(nsteps) (hoomd/System.cc:80-181) restricted to this path: prepRun on the first call
  * (hoomd/md/IntegratorTwoStep.cc:226-281), then per step: step one -> nlist check/rebuild -> forces
- * -> step two. No host synchronisation inside the loop. */
+ * -> step two (step two of a timestep and step one of the next share one launch for ConstantVolume on
+ * one GPU). The host reads one word per step — the rebuild flag, copied on a side stream while the
+ * force pass it may invalidate is already queued behind step one (the reference blocks on the same flag,
+ * hoomd/md/NeighborListGPU.cc:78-82) — and synchronises fully only on rebuild steps (capacity checks) and
+ * at the end of the run. */
 hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps);
 /* ComputeThermo quantities of the current state (hoomd/md/ComputeThermo.cc:76-…): kinetic energy,
  * potential energy, and the 6 virial sums (virial valid only with the pressure flag). */

@@ -634,7 +634,15 @@ def test_nve_drift_1e5_reference_8k(hoomd, golden_dir):
     # kT = 1.5: a drift of 1e-3 per particle is 4.4e-4 of the kinetic energy per particle over 1e5 steps;
     # the fp64 reference itself wanders by its noise (~1e-4)
     assert abs(drift) <= 1e-3
-    assert abs(builds - int(ref["builds"])) <= 0.01 * int(ref["builds"])
+    # Rebuild cadence. The reference run carries HOOMD's default ParticleSorter (hoomd/tune/sorter.py:44,
+    # every 200 steps), whose sort signal forces a list update (hoomd/md/NeighborList.cc:222): each forced
+    # update restarts the displacement clock at a random phase of a natural interval, i.e. adds half a build
+    # on average. This engine re-orders at every rebuild and has no separate sorter, so the comparison is
+    # against the reference's count less those extra half builds.
+    steps = every * (len(e_ref) - 1)
+    natural_ref = int(ref["builds"]) - 0.5 * (steps // 200)
+    print(f"reference builds less the sorter's forced updates: {natural_ref:.0f}")
+    assert abs(builds - natural_ref) <= 0.01 * natural_ref
 
 
 def test_snapshot_roundtrip_pageable_and_pinned(hoomd):
