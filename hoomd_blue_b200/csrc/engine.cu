@@ -828,6 +828,7 @@ TileBuildArgs hb2_nlist::tile_args() const
     a.r_listsq = d_r_listsq;
     a.ntypes = s->ntypes;
     a.r_listsq_single = r_listsq[0];
+    a.r_listsq_max = *std::max_element(r_listsq.begin(), r_listsq.end());
     a.r_list_min = r_list_min;
     a.Lmax = (float)std::max(s->box.L[0], std::max(s->box.L[1], s->box.L[2]));
     a.rows16 = d_rows16;

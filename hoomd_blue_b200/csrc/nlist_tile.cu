@@ -32,6 +32,7 @@ struct TileBuildKArgs
     TileBuildArgs a;
     NlConst cst;
     uint32_t vcap; // candidate-table entries per warp (multiple of 32)
+    uint32_t prune; // prune the candidate tables against the home cells' bounding boxes
     };
 
 HB2_DEVICE size_t align16(size_t x)
@@ -140,6 +141,53 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) nlist_build_tile_kernel(const
         const uint32_t vo = __shfl_sync(0xffffffffu, voff, r);
         for (uint32_t k = lane; k < ln; k += 32)
             tab[vo + k] = (uint16_t)(st + k);
+        }
+    __syncwarp();
+    // ---- 3b. prune the table against the bounding box of the home cell's particles: a candidate farther
+    // than the largest r_list from the box is farther than that from every home particle. At a cell width of
+    // r_list this drops the far parts of the 12 edge and 8 corner cells (about a quarter of the candidates).
+    // fp32 on the staged coordinates — the ones the sweep uses — with the sweep's guard band as margin.
+    if (ka.prune)
+        {
+        float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        for (uint32_t k = lane; k < hcnt; k += 32)
+            {
+            const float4 p = stage[hstart + k];
+            blo[0] = fminf(blo[0], p.x);
+            bhi[0] = fmaxf(bhi[0], p.x);
+            blo[1] = fminf(blo[1], p.y);
+            bhi[1] = fmaxf(bhi[1], p.y);
+            blo[2] = fminf(blo[2], p.z);
+            bhi[2] = fmaxf(bhi[2], p.z);
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                {
+                blo[c] = fminf(blo[c], __shfl_xor_sync(0xffffffffu, blo[c], off));
+                bhi[c] = fmaxf(bhi[c], __shfl_xor_sync(0xffffffffu, bhi[c], off));
+                }
+        const float thr = (float)a.r_listsq_max * (1.0f + 2.0f * band) ;
+        const uint32_t Vin = (V + 31u) & ~31u;
+        uint32_t Vout = 0;
+        for (uint32_t v = 0; v < Vin; v += 32)
+            {
+            const uint32_t e = v + lane;
+            const uint32_t slot = e < V ? tab[e] : 0u;
+            const float4 c = stage[slot];
+            const float dx = fmaxf(fmaxf(blo[0] - c.x, c.x - bhi[0]), 0.f);
+            const float dy = fmaxf(fmaxf(blo[1] - c.y, c.y - bhi[1]), 0.f);
+            const float dz = fmaxf(fmaxf(blo[2] - c.z, c.z - bhi[2]), 0.f);
+            const bool keep = e < V && fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            __syncwarp(); // every lane has read its entry before the compacted ones overwrite the front
+            if (keep)
+                tab[Vout + __popc(m & ((1u << lane) - 1u))] = (uint16_t)slot;
+            Vout += __popc(m);
+            }
+        V = Vout;
+        __syncwarp();
         }
     const uint32_t Vpad = (V + 31u) & ~31u;
     if (V + lane < Vpad)
@@ -369,6 +417,8 @@ hb2_status launch_nlist_build_tiles(const TileBuildArgs& a, const hb2_box& box, 
     ka.a = a;
     ka.cst = nl_make_const(box, a.r_list_min, a.Lmax);
     ka.vcap = tile_vcap(a.stage_cap);
+    static const uint32_t prune = getenv("HB2_TILE_PRUNE") ? (uint32_t)atoi(getenv("HB2_TILE_PRUNE")) : 1u;
+    ka.prune = prune;
     const size_t smem = tile_build_smem(a.stage_cap, a.pitch, a.ntypes);
     if (smem == 0)
         {

@@ -281,6 +281,7 @@ struct TileBuildArgs
     const double* r_listsq; // ntypes^2 (device), tj * ntypes + ti
     uint32_t ntypes;
     double r_listsq_single;
+    double r_listsq_max; // largest r_list^2 over the type pairs (candidate pruning against a home cell's box)
     double r_list_min;
     float Lmax;
     uint16_t* rows16;
