@@ -8,5 +8,5 @@ P
 }
 run prune1 A=1
 run prune0 HB2_TILE_PRUNE=0
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'nlist_build_tile' -s 3 -c 1 -o gpurun_out/r02_tileb_v3 -f python bench.py --steps 30 --warmup 5 > gpurun_out/ncu_tileb_v3.log 2>&1
-ncu -i gpurun_out/r02_tileb_v3.ncu-rep --page raw --csv > gpurun_out/r02_tileb_v3_raw.csv; python tools/ncu_summary.py gpurun_out/r02_tileb_v3_raw.csv --all 2>/dev/null | grep -E "=====|time_duration|inst_executed.sum|issue_active|wavefronts.avg|registers|dram__bytes"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'nlist_build_tile' -s 3 -c 1 -o gpurun_out/r02_tileb_v4 -f python bench.py --steps 30 --warmup 5 > gpurun_out/ncu_tileb_v4.log 2>&1
+ncu -i gpurun_out/r02_tileb_v4.ncu-rep --page raw --csv > gpurun_out/r02_tileb_v4_raw.csv; python tools/ncu_summary.py gpurun_out/r02_tileb_v4_raw.csv --all 2>/dev/null | grep -E "=====|time_duration|inst_executed.sum|issue_active|wavefronts.avg|registers|dram__bytes"
