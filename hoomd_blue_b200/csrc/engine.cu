@@ -2698,7 +2698,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     it->marks.clear();
     // ConstantVolume on one GPU: step two of a timestep and step one of the next share a launch
     static const bool fuse_enabled = !(getenv("HB2_FUSE_INTEGRATE") && atoi(getenv("HB2_FUSE_INTEGRATE")) == 0);
-    const bool fuse = fuse_enabled && it->thermostat != 2 && !s->dom.active;
+    bool fuse = fuse_enabled && it->thermostat != 2 && !s->dom.active;
     if (fuse && !it->d_gen)
         {
         HB2_TRY(dev_alloc(&it->d_gen, 1));
@@ -2843,8 +2843,13 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                                         (float)it->dt, check ? nl->d_last_pos : nullptr, nl->maxshift(),
                                         nl->d_conditions + 3, s->d_partial, s->d_ticket,
                                         it->thermostat == 1 ? d_ke : nullptr, it->thermostat == 1 ? &bn : nullptr,
-                                        it->d_gen, ++it->gen_epoch, st));
-            one_done = true;
+                                        it->d_gen, ++it->gen_epoch, st, &one_done));
+            if (!one_done) // the cooperative launch was refused: the stand-alone kernels from here on
+                {
+                fuse = false;
+                HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
+                                        s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn));
+                }
             }
         else
             HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,

@@ -551,8 +551,11 @@ hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float d
 hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
                                const hb2_box& box, float dt, const float4* last_pos, float maxshift,
                                uint32_t* d_flag, double* d_ke_partial, uint32_t* d_ticket, double* d_ke_out,
-                               const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream)
+                               const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream,
+                               bool* fused)
     {
+    if (fused)
+        *fused = true;
     if (N == 0)
         return HB2_OK;
     const uint32_t nvb = (N + INT_BLOCK - 1) / INT_BLOCK;
@@ -573,9 +576,41 @@ hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, in
                 return HB2_ERR_INVALID;
                 }
             }
-        step_two_one_kernel<true><<<std::min<uint32_t>(nvb, (uint32_t)wave), INT_BLOCK, 0, stream>>>(
-            pos, vel, force, image, N, boxf(box), dt, last_pos, maxshift * maxshift, d_flag, d_ke_partial,
-            d_ticket, d_ke_out, *bussi, d_gen, epoch);
+        // A cooperative launch: the runtime guarantees that the whole grid is resident together (the blocks
+        // wait for each other between the halves) or refuses — then *fused is cleared and the caller uses
+        // the two stand-alone kernels.
+        float4* a_pos = pos;
+        float4* a_vel = vel;
+        const float4* a_force = force;
+        int* a_image = image;
+        uint32_t a_N = N;
+        BoxF a_box = boxf(box);
+        float a_dt = dt;
+        const float4* a_last = last_pos;
+        float a_ms = maxshift * maxshift;
+        uint32_t* a_flag = d_flag;
+        double* a_part = d_ke_partial;
+        uint32_t* a_ticket = d_ticket;
+        double* a_ke = d_ke_out;
+        BussiNext a_b = *bussi;
+        uint32_t* a_gen = d_gen;
+        uint32_t a_epoch = epoch;
+        void* args[] = {&a_pos, &a_vel, &a_force, &a_image, &a_N, &a_box, &a_dt, &a_last, &a_ms, &a_flag,
+                        &a_part, &a_ticket, &a_ke, &a_b, &a_gen, &a_epoch};
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void*)step_two_one_kernel<true>,
+                                                          dim3(std::min<uint32_t>(nvb, (uint32_t)wave)),
+                                                          dim3(INT_BLOCK), args, 0, stream);
+        if (e != cudaSuccess)
+            {
+            cudaGetLastError();
+            if (fused)
+                *fused = false;
+            return HB2_OK;
+            }
+        count_launch(1);
+        if (fused)
+            *fused = true;
+        return HB2_OK;
         }
     else
         {

@@ -164,7 +164,8 @@ hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float d
 hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
                                const hb2_box& box, float dt, const float4* last_pos, float maxshift,
                                uint32_t* d_flag, double* d_ke_partial, uint32_t* d_ticket, double* d_ke_out,
-                               const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream);
+                               const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream,
+                               bool* fused = nullptr); // *fused = false: not launched (no co-resident grid); use the two kernels
 // TwoStepLangevin step two; d_gamma_coeff = (gamma, sqrt(6 gamma kT / dt)) per type; total <- F + F_bd
 // (what the next step one integrates with)
 hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,
