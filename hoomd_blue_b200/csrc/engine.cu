@@ -2561,6 +2561,7 @@ extern "C" void hb2_integrator_destroy(hb2_integrator* it)
     dev_free(it->d_gamma_coeff);
     dev_free(it->d_total);
     dev_free(it->d_gen);
+    dev_free(it->d_member);
     delete it;
     }
 
@@ -2604,6 +2605,83 @@ extern "C" hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int
     it->thermostat = thermostat;
     it->kT = kT;
     it->tau = tau;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_set_filter_tags(hb2_integrator* it, const uint32_t* tags, uint64_t n)
+    {
+    if (!it || (n && !tags))
+        return HB2_ERR_INVALID;
+    hb2_system* s = it->sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    const uint64_t Ng = s->dom.active ? s->dom.N_global : s->N;
+    dev_free(it->d_member);
+    it->d_member = nullptr;
+    it->n_member = Ng;
+    it->prepared = false;
+    it->total_valid = false;
+    if (!tags && n == 0)
+        return HB2_OK; // filter.All
+    std::vector<uint8_t> m((size_t)Ng, 0);
+    uint64_t cnt = 0;
+    for (uint64_t k = 0; k < n; k++)
+        {
+        if (tags[k] >= Ng)
+            {
+            set_error("hb2_integrator_set_filter_tags: tag out of range");
+            return HB2_ERR_INVALID;
+            }
+        cnt += m[tags[k]] ? 0 : 1;
+        m[tags[k]] = 1;
+        }
+    it->n_member = cnt;
+    if (cnt == Ng)
+        return HB2_OK; // every particle: no mask
+    HB2_TRY(dev_alloc(&it->d_member, (size_t)std::max<uint64_t>(Ng, 1)));
+    HB2_CUDA(cudaMemcpyAsync(it->d_member, m.data(), (size_t)Ng, cudaMemcpyHostToDevice, s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_kinetic_of_tags(hb2_integrator* it, const uint32_t* tags, uint64_t n,
+                                                     double* kinetic)
+    {
+    if (!it || !kinetic || (n && !tags))
+        return HB2_ERR_INVALID;
+    hb2_system* s = it->sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    const uint64_t Ng = s->dom.active ? s->dom.N_global : s->N;
+    uint8_t* d_m = nullptr;
+    if (tags)
+        {
+        std::vector<uint8_t> m((size_t)Ng, 0);
+        for (uint64_t k = 0; k < n; k++)
+            {
+            if (tags[k] >= Ng)
+                {
+                set_error("hb2_integrator_kinetic_of_tags: tag out of range");
+                return HB2_ERR_INVALID;
+                }
+            m[tags[k]] = 1;
+            }
+        HB2_TRY(dev_alloc(&d_m, (size_t)std::max<uint64_t>(Ng, 1)));
+        HB2_CUDA(cudaMemcpyAsync(d_m, m.data(), (size_t)Ng, cudaMemcpyHostToDevice, s->stream));
+        HB2_CUDA(cudaStreamSynchronize(s->stream)); // m goes out of scope
+        }
+    double ke = 0.0;
+    hb2_status st = launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket + 2, s->d_sums + 9, s->stream,
+                                   GroupMask {d_m, s->tag[s->cur]});
+    if (st == HB2_OK && s->dom.active)
+        st = domain_allreduce_sum_f64(s, s->d_sums + 9, 1);
+    if (st == HB2_OK)
+        {
+        cudaMemcpyAsync(&ke, s->d_sums + 9, sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+        cudaStreamSynchronize(s->stream);
+        }
+    dev_free(d_m);
+    if (st != HB2_OK)
+        return st;
+    *kinetic = ke;
     return HB2_OK;
     }
 
@@ -2662,7 +2740,11 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
     double* d_rescale = s->d_sums + 8;
     // translational degrees of freedom of filter All, momentum conserving, 3D
     // (hoomd/md/IntegratorTwoStep.cc:154-189)
-    const double dof = 3.0 * (double)(s->dom.active ? s->dom.N_global : s->N) - 3.0;
+    // (a method on a proper subset of the particles keeps all 3 n: the centre of mass of the group is not
+    // conserved, hoomd/md/IntegratorTwoStep.cc:172-178)
+    const uint64_t n_all = s->dom.active ? s->dom.N_global : s->N;
+    const uint64_t n_grp = it->d_member ? it->n_member : n_all;
+    const double dof = 3.0 * (double)n_grp - (n_grp == n_all ? 3.0 : 0.0);
 
     // System::run resets the per-run statistics of every compute (hoomd/System.cc:103-110 ->
     // NeighborList::resetStats, hoomd/md/NeighborList.cc:1420-1427): num_builds counts this run only
@@ -2689,7 +2771,8 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         }
     if (it->thermostat == 1)
         {
-        HB2_TRY(launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket, d_ke, st));
+        HB2_TRY(launch_kinetic(s->vel[s->cur], s->N, s->d_partial, s->d_ticket, d_ke, st,
+                               GroupMask {it->d_member, s->tag[s->cur]}));
         if (s->dom.active)
             HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
         }
@@ -2740,7 +2823,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                                   : pf->d_force;
         HB2_TRY(launch_step_one(s->pos[s->cur], s->vel[s->cur], f_one, s->image[s->cur], s->N,
                                 s->box, (float)it->dt, rescale, check ? nl->d_last_pos : nullptr,
-                                nl->maxshift(), nl->d_conditions + 3, st));
+                                nl->maxshift(), nl->d_conditions + 3, st, GroupMask {it->d_member, s->tag[s->cur]}));
             }
         one_done = false;
         bool flag = false;
@@ -2830,7 +2913,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                 }
             HB2_TRY(launch_step_two_langevin(s->vel[s->cur], pf->d_force, it->d_total, s->pos[s->cur],
                                              s->tag[s->cur], s->N, (float)it->dt, it->d_gamma_coeff,
-                                             s->seed, t, st));
+                                             s->seed, t, st, it->d_member));
             it->total_valid = true;
             it->total_epoch = s->order_epoch;
             it->total_step = t + 1;
@@ -2843,17 +2926,20 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                                         (float)it->dt, check ? nl->d_last_pos : nullptr, nl->maxshift(),
                                         nl->d_conditions + 3, s->d_partial, s->d_ticket,
                                         it->thermostat == 1 ? d_ke : nullptr, it->thermostat == 1 ? &bn : nullptr,
-                                        it->d_gen, ++it->gen_epoch, st, &one_done));
+                                        it->d_gen, ++it->gen_epoch, st, &one_done,
+                                        GroupMask {it->d_member, s->tag[s->cur]}));
             if (!one_done) // the cooperative launch was refused: the stand-alone kernels from here on
                 {
                 fuse = false;
                 HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
-                                        s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn));
+                                        s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn,
+                                        GroupMask {it->d_member, s->tag[s->cur]}));
                 }
             }
         else
             HB2_TRY(launch_step_two(s->vel[s->cur], pf->d_force, s->N, (float)it->dt, nullptr, s->d_partial,
-                                    s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn));
+                                    s->d_ticket, it->thermostat == 1 ? d_ke : nullptr, st, &bn,
+                                    GroupMask {it->d_member, s->tag[s->cur]}));
         if (it->thermostat == 1 && s->dom.active)
             HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
         if (it->profiling)

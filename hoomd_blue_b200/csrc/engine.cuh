@@ -257,6 +257,8 @@ struct hb2_integrator
     float4* d_total = nullptr;      // Langevin: F + F_bd of the last step two (next step one's force)
     size_t total_cap = 0;
     bool total_valid = false;
+    uint8_t* d_member = nullptr; // the method's group: a byte per particle tag (null: every particle)
+    uint64_t n_member = 0;       // group size (global)
     uint32_t* d_gen = nullptr; // generation word of the fused step-two/step-one kernel (integrate.cu)
     uint32_t gen_epoch = 0;
     uint64_t total_epoch = 0, total_step = 0; // particle order and timestep d_total belongs to

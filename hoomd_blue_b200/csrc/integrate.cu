@@ -20,6 +20,10 @@ constexpr int INT_BLOCK = 256;
 // The half kicks and the drift with explicit roundings: the stand-alone kernels and the fused
 // step-two/step-one kernel must produce the same bits (a run cut into segments by a writer is the same
 // trajectory as an uninterrupted one), whatever the compiler would contract.
+HB2_DEVICE bool in_group(const GroupMask& g, const uint32_t i)
+    {
+    return !g.member || g.member[g.tag[i]] != 0;
+    }
 HB2_DEVICE float kick(const float v, const float f, const float minv, const float hdt)
     {
     return __fmaf_rn(hdt, __fmul_rn(f, minv), v);
@@ -38,10 +42,10 @@ __global__ void __launch_bounds__(INT_BLOCK)
                     const float4* __restrict__ force, int* __restrict__ image, uint32_t N, BoxF box,
                     float dt, const double* __restrict__ d_rescale,
                     const float4* __restrict__ last_pos, float maxshiftsq,
-                    uint32_t* __restrict__ d_flag)
+                    uint32_t* __restrict__ d_flag, GroupMask group)
     {
     const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
-    if (i >= N)
+    if (i >= N || !in_group(group, i)) // particles outside the method's group do not move
         return;
     const float s = d_rescale ? (float)(*d_rescale) : 1.0f;
     float4 p = pos[i];
@@ -113,11 +117,11 @@ template<bool KE>
 __global__ void __launch_bounds__(INT_BLOCK)
     step_two_kernel(float4* __restrict__ vel, const float4* __restrict__ force, uint32_t N, float dt,
                     const double* __restrict__ d_rescale, double* __restrict__ partial,
-                    uint32_t* __restrict__ ticket, double* __restrict__ ke_out, BussiNext bussi)
+                    uint32_t* __restrict__ ticket, double* __restrict__ ke_out, BussiNext bussi, GroupMask group)
     {
     const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
     double ke[1] = {0.0};
-    if (i < N)
+    if (i < N && in_group(group, i))
         {
         const float s = d_rescale ? (float)(*d_rescale) : 1.0f;
         float4 v = vel[i];
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(INT_BLOCK)
                         const float4* __restrict__ last_pos, float maxshiftsq, uint32_t* __restrict__ d_flag,
                         double* __restrict__ partial, uint32_t* __restrict__ ticket,
                         double* __restrict__ ke_out, BussiNext bussi, uint32_t* __restrict__ d_gen,
-                        uint32_t epoch)
+                        uint32_t epoch, GroupMask group)
     {
     __shared__ double s_w[4][INT_BLOCK / 32];
     __shared__ bool s_last;
@@ -185,6 +189,8 @@ __global__ void __launch_bounds__(INT_BLOCK)
             {
             const uint32_t vb = vb0 + u * gridDim.x;
             idx[u] = vb < nvb ? vb * INT_BLOCK + threadIdx.x : N;
+            if (idx[u] < N && !in_group(group, idx[u]))
+                idx[u] = N;
             if (idx[u] < N)
                 {
                 v[u] = vel[idx[u]];
@@ -291,6 +297,8 @@ __global__ void __launch_bounds__(INT_BLOCK)
             {
             const uint32_t vb = vb0 + u * gridDim.x;
             idx[u] = vb < nvb ? vb * INT_BLOCK + threadIdx.x : N;
+            if (idx[u] < N && !in_group(group, idx[u]))
+                idx[u] = N;
             if (idx[u] < N)
                 {
                 pp[u] = pos[idx[u]];
@@ -379,11 +387,17 @@ __global__ void __launch_bounds__(INT_BLOCK)
     step_two_langevin_kernel(float4* __restrict__ vel, const float4* __restrict__ force,
                              float4* __restrict__ total, const float4* __restrict__ pos,
                              const uint32_t* __restrict__ tag, uint32_t N, float dt,
-                             const float* __restrict__ gc, uint32_t seed, uint64_t timestep)
+                             const float* __restrict__ gc, uint32_t seed, uint64_t timestep,
+                             const uint8_t* __restrict__ member)
     {
     const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
     if (i >= N)
         return;
+    if (member && !member[tag[i]])
+        {
+        total[i] = force[i]; // not integrated; the array stays defined
+        return;
+        }
     float4 v = vel[i];
     const float4 f = force[i];
     const uint32_t t = __float_as_uint(pos[i].w);
@@ -444,12 +458,12 @@ hb2_status launch_accumulate_force(float4* dst, float* dst_virial, size_t dst_pi
 
 hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,
                                     const uint32_t* tag, uint32_t N, float dt, const float* d_gamma_coeff,
-                                    uint32_t seed, uint64_t timestep, cudaStream_t stream)
+                                    uint32_t seed, uint64_t timestep, cudaStream_t stream, const uint8_t* member)
     {
     if (N == 0)
         return HB2_OK;
     step_two_langevin_kernel<<<(N + INT_BLOCK - 1) / INT_BLOCK, INT_BLOCK, 0, stream>>>(
-        vel, force, total, pos, tag, N, dt, d_gamma_coeff, seed, timestep);
+        vel, force, total, pos, tag, N, dt, d_gamma_coeff, seed, timestep, member);
     HB2_CHECK_LAUNCH("step_two_langevin_kernel");
     return HB2_OK;
     }
@@ -457,11 +471,11 @@ hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* to
 // KE of the current velocities only (prepRun / thermo queries)
 __global__ void __launch_bounds__(INT_BLOCK)
     kinetic_kernel(const float4* __restrict__ vel, uint32_t N, double* __restrict__ partial,
-                   uint32_t* __restrict__ ticket, double* __restrict__ ke_out)
+                   uint32_t* __restrict__ ticket, double* __restrict__ ke_out, GroupMask group)
     {
     const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
     double ke[1] = {0.0};
-    if (i < N)
+    if (i < N && in_group(group, i))
         {
         const float4 v = vel[i];
         ke[0] = 0.5 * (double)v.w
@@ -515,19 +529,19 @@ uint32_t reduce_blocks(uint32_t N)
 hb2_status launch_step_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
                            const hb2_box& box, float dt, const double* d_rescale,
                            const float4* last_pos, float maxshift, uint32_t* d_flag,
-                           cudaStream_t stream)
+                           cudaStream_t stream, GroupMask group)
     {
     if (N == 0)
         return HB2_OK;
     step_one_kernel<<<(N + INT_BLOCK - 1) / INT_BLOCK, INT_BLOCK, 0, stream>>>(
-        pos, vel, force, image, N, boxf(box), dt, d_rescale, last_pos, maxshift * maxshift, d_flag);
+        pos, vel, force, image, N, boxf(box), dt, d_rescale, last_pos, maxshift * maxshift, d_flag, group);
     HB2_CHECK_LAUNCH("step_one_kernel");
     return HB2_OK;
     }
 
 hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
                            const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
-                           double* d_ke_out, cudaStream_t stream, const BussiNext* bussi)
+                           double* d_ke_out, cudaStream_t stream, const BussiNext* bussi, GroupMask group)
     {
     if (N == 0)
         return HB2_OK;
@@ -537,10 +551,10 @@ hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float d
         b = *bussi;
     if (d_ke_out)
         step_two_kernel<true><<<blocks, INT_BLOCK, 0, stream>>>(vel, force, N, dt, d_rescale,
-                                                                d_ke_partial, d_ticket, d_ke_out, b);
+                                                                d_ke_partial, d_ticket, d_ke_out, b, group);
     else
         step_two_kernel<false><<<blocks, INT_BLOCK, 0, stream>>>(vel, force, N, dt, d_rescale,
-                                                                 nullptr, nullptr, nullptr, b);
+                                                                 nullptr, nullptr, nullptr, b, group);
     HB2_CHECK_LAUNCH("step_two_kernel");
     return HB2_OK;
     }
@@ -552,7 +566,7 @@ hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, in
                                const hb2_box& box, float dt, const float4* last_pos, float maxshift,
                                uint32_t* d_flag, double* d_ke_partial, uint32_t* d_ticket, double* d_ke_out,
                                const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream,
-                               bool* fused)
+                               bool* fused, GroupMask group)
     {
     if (fused)
         *fused = true;
@@ -595,8 +609,9 @@ hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, in
         BussiNext a_b = *bussi;
         uint32_t* a_gen = d_gen;
         uint32_t a_epoch = epoch;
+        GroupMask a_group = group;
         void* args[] = {&a_pos, &a_vel, &a_force, &a_image, &a_N, &a_box, &a_dt, &a_last, &a_ms, &a_flag,
-                        &a_part, &a_ticket, &a_ke, &a_b, &a_gen, &a_epoch};
+                        &a_part, &a_ticket, &a_ke, &a_b, &a_gen, &a_epoch, &a_group};
         const cudaError_t e = cudaLaunchCooperativeKernel((const void*)step_two_one_kernel<true>,
                                                           dim3(std::min<uint32_t>(nvb, (uint32_t)wave)),
                                                           dim3(INT_BLOCK), args, 0, stream);
@@ -617,18 +632,18 @@ hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, in
         BussiNext none;
         step_two_one_kernel<false><<<nvb, INT_BLOCK, 0, stream>>>(pos, vel, force, image, N, boxf(box), dt, last_pos,
                                                                   maxshift * maxshift, d_flag, nullptr, nullptr,
-                                                                  nullptr, none, nullptr, 0u);
+                                                                  nullptr, none, nullptr, 0u, group);
         }
     HB2_CHECK_LAUNCH("step_two_one_kernel");
     return HB2_OK;
     }
 
 hb2_status launch_kinetic(const float4* vel, uint32_t N, double* d_partial, uint32_t* d_ticket,
-                          double* d_ke_out, cudaStream_t stream)
+                          double* d_ke_out, cudaStream_t stream, GroupMask group)
     {
     if (N == 0)
         return HB2_OK;
-    kinetic_kernel<<<reduce_blocks(N), INT_BLOCK, 0, stream>>>(vel, N, d_partial, d_ticket, d_ke_out);
+    kinetic_kernel<<<reduce_blocks(N), INT_BLOCK, 0, stream>>>(vel, N, d_partial, d_ticket, d_ke_out, group);
     HB2_CHECK_LAUNCH("kinetic_kernel");
     return HB2_OK;
     }

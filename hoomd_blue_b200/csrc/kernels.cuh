@@ -142,10 +142,17 @@ hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairA
                               const hb2_box& box, cudaStream_t stream);
 
 // ---- integrate.cu
+// The particles an integration method acts on (hoomd ParticleGroup of the method's filter,
+// hoomd/md/IntegrationMethodTwoStep.h): a byte per particle TAG; member == nullptr: every particle.
+struct GroupMask
+    {
+    const uint8_t* member = nullptr;
+    const uint32_t* tag = nullptr;
+    };
 hb2_status launch_step_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
                            const hb2_box& box, float dt, const double* d_rescale,
                            const float4* last_pos, float maxshift, uint32_t* d_flag,
-                           cudaStream_t stream);
+                           cudaStream_t stream, GroupMask group = GroupMask());
 // Bussi factor of the next step, drawn by the thread that completes step two's KE sum
 struct BussiNext
     {
@@ -158,21 +165,24 @@ struct BussiNext
 uint32_t step_two_blocks(uint32_t N);
 hb2_status launch_step_two(float4* vel, const float4* force, uint32_t N, float dt,
                            const double* d_rescale, double* d_ke_partial, uint32_t* d_ticket,
-                           double* d_ke_out, cudaStream_t stream, const BussiNext* bussi = nullptr);
+                           double* d_ke_out, cudaStream_t stream, const BussiNext* bussi = nullptr,
+                           GroupMask group = GroupMask());
 // step two of timestep t fused with step one of timestep t + 1 (integrate.cu); bussi with rescale set:
 // persistent kernel with the grid-wide KE sum and the factor of step t + 1 between the halves
 hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
                                const hb2_box& box, float dt, const float4* last_pos, float maxshift,
                                uint32_t* d_flag, double* d_ke_partial, uint32_t* d_ticket, double* d_ke_out,
                                const BussiNext* bussi, uint32_t* d_gen, uint32_t epoch, cudaStream_t stream,
-                               bool* fused = nullptr); // *fused = false: not launched (no co-resident grid); use the two kernels
+                               bool* fused = nullptr, // *fused = false: not launched (no co-resident grid); use the two kernels
+                               GroupMask group = GroupMask());
 // TwoStepLangevin step two; d_gamma_coeff = (gamma, sqrt(6 gamma kT / dt)) per type; total <- F + F_bd
 // (what the next step one integrates with)
 hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* total, const float4* pos,
                                     const uint32_t* tag, uint32_t N, float dt, const float* d_gamma_coeff,
-                                    uint32_t seed, uint64_t timestep, cudaStream_t stream);
+                                    uint32_t seed, uint64_t timestep, cudaStream_t stream,
+                                    const uint8_t* member = nullptr);
 hb2_status launch_kinetic(const float4* vel, uint32_t N, double* d_partial, uint32_t* d_ticket,
-                          double* d_ke_out, cudaStream_t stream);
+                          double* d_ke_out, cudaStream_t stream, GroupMask group = GroupMask());
 // Bussi factor on device (hoomd/md/Thermostat.h:357-447): *d_rescale <- factor for the step-one of
 // timestep *d_timestep; reads *d_ke.
 hb2_status launch_bussi(const double* d_ke, double dof, double dt, double kT, double tau,

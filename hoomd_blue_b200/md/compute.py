@@ -1,5 +1,6 @@
 """hoomd.md.compute.ThermodynamicQuantities for this path (hoomd/md/compute.py:55-192):
-kinetic/potential energy, temperature, pressure of filter.All()."""
+kinetic/potential energy, temperature, pressure of filter.All(); for any other filter the kinetic energy,
+degrees of freedom and kinetic temperature of its group (what a thermostat on a sub-group uses)."""
 import numpy as np
 
 
@@ -13,6 +14,12 @@ class ThermodynamicQuantities:
 
     def _attach(self, sim):
         self._sim = sim
+
+    def _tags(self):
+        from ..filter import All
+        if isinstance(self.filter, All):
+            return None
+        return np.ascontiguousarray(self.filter(self._sim.state), dtype=np.uint32)
 
     def _q(self, need_virial=False):
         if self._sim is None or self._sim.operations.integrator is None:
@@ -33,15 +40,20 @@ class ThermodynamicQuantities:
 
     @property
     def kinetic_energy(self):
+        tags = self._tags()
+        if tags is not None:
+            return self._sim.operations.integrator._kinetic_of(tags)
         return self._q()[0]
 
     @property
     def potential_energy(self):
+        if self._tags() is not None:
+            raise NotImplementedError("potential energy of a sub-group is outside this path")
         return self._q()[1]
 
     @property
     def degrees_of_freedom(self):
-        return self._sim.operations.integrator._translational_dof
+        return self._sim.operations.integrator._translational_dof_of(self._tags())
 
     @property
     def kinetic_temperature(self):
@@ -51,6 +63,8 @@ class ThermodynamicQuantities:
     def pressure(self):
         """P = (2 K_trans / 3 + W) / V with W = (W_xx + W_yy + W_zz) / 3 summed over particles
         (hoomd/md/ComputeThermo.cc, 3D), including the forces' external virial (LJ tail correction)."""
+        if self._tags() is not None:
+            raise NotImplementedError("pressure of a sub-group is outside this path")
         ke, pe, w = self._q(need_virial=True)
         V = self._sim.state.box.volume
         return (2.0 * ke / 3.0 + (w[0] + w[3] + w[5]) / 3.0) / V

@@ -71,6 +71,16 @@ class Integrator:
             check(L.hb2_integrator_set_constant_volume(h, 1, th.kT, th.tau))
         else:
             check(L.hb2_integrator_set_constant_volume(h, 0, 0.0, 0.0))
+        # the method's particle group (hoomd/md/methods/methods.py:145-175 takes any filter)
+        self._group_tags = None
+        if self.methods:
+            from ..filter import All
+            flt = self.methods[0].filter
+            if not isinstance(flt, All):
+                tags = np.ascontiguousarray(flt(sim.state), dtype=np.uint32)
+                self._group_tags = tags
+                buf = tags if len(tags) else np.zeros(1, dtype=np.uint32)
+                check(L.hb2_integrator_set_filter_tags(h, _lib.ptr(buf, C.c_uint32), len(tags)))
 
     def _detach(self):
         if self._h is not None:
@@ -117,11 +127,32 @@ class Integrator:
 
     @property
     def _translational_dof(self):
-        """hoomd/md/IntegratorTwoStep.cc:154-189: the method's group size times the dimension, minus
-        the three centre-of-mass degrees when the (single) method conserves momentum —
+        return self._translational_dof_of(None)
+
+    def _translational_dof_of(self, tags):
+        """hoomd/md/IntegratorTwoStep.cc:154-189 for the query group `tags` (None: every particle): the
+        dimension times the size of (method group ∩ query group), less the query group's share of the three
+        centre-of-mass degrees when the (single) method conserves momentum AND acts on every particle —
         ConstantVolume does (hoomd/md/TwoStepConstantVolume.h), Langevin does not
         (hoomd/md/TwoStepLangevinBase.h) — and 0 without a method."""
         if not self.methods or self._sim is None:
             return 0
-        n = 3 * self._sim.state.N_particles
-        return n if isinstance(self.methods[0], Langevin) else n - 3
+        N = self._sim.state.N_particles
+        method_tags = getattr(self, "_group_tags", None)
+        n_query = N if tags is None else len(tags)
+        if method_tags is None:
+            n_both = n_query
+        elif tags is None:
+            n_both = len(method_tags)
+        else:
+            n_both = len(np.intersect1d(method_tags, tags))
+        dof = 3.0 * n_both
+        if not isinstance(self.methods[0], Langevin) and (method_tags is None or len(method_tags) == N) and N:
+            dof -= 3.0 * n_query / N
+        return int(dof) if float(dof).is_integer() else dof
+
+    def _kinetic_of(self, tags):
+        ke = C.c_double(0)
+        buf = tags if len(tags) else np.zeros(1, dtype=np.uint32)
+        check(_lib.lib().hb2_integrator_kinetic_of_tags(self._h, _lib.ptr(buf, C.c_uint32), len(tags), C.byref(ke)))
+        return ke.value

@@ -1,5 +1,5 @@
 """hoomd.md.methods for this path (hoomd/md/methods/methods.py:85-175, thermostats.py)."""
-from ..filter import All
+from ..filter import All, ParticleFilter
 
 
 class Thermostat:
@@ -27,8 +27,8 @@ class ConstantVolume(Method):
     """hoomd.md.methods.ConstantVolume(filter, thermostat=None)."""
 
     def __init__(self, filter, thermostat=None):
-        if not isinstance(filter, All):
-            raise NotImplementedError("this path integrates filter.All() only")
+        if not isinstance(filter, ParticleFilter):
+            raise TypeError("filter must be a hoomd.filter.ParticleFilter")
         if thermostat is not None and not isinstance(thermostat, Bussi):
             raise NotImplementedError("thermostat must be None or thermostats.Bussi")
         self.filter = filter
@@ -49,12 +49,12 @@ class _TypeDict(dict):
 class Langevin(Method):
     """hoomd.md.methods.Langevin(filter, kT, tally_reservoir_energy=False, default_gamma=1.0)
     (hoomd/md/methods/methods.py, hoomd/md/TwoStepLangevin.cc): translational Langevin dynamics of
-    filter.All(); `gamma[type]` is the drag coefficient. Rotational degrees of freedom (gamma_r) and the
+    any hoomd.filter; `gamma[type]` is the drag coefficient. Rotational degrees of freedom (gamma_r) and the
     reservoir-energy tally are outside this path."""
 
     def __init__(self, filter, kT, tally_reservoir_energy=False, default_gamma=1.0, default_gamma_r=None):
-        if not isinstance(filter, All):
-            raise NotImplementedError("this path integrates filter.All() only")
+        if not isinstance(filter, ParticleFilter):
+            raise TypeError("filter must be a hoomd.filter.ParticleFilter")
         if tally_reservoir_energy:
             raise NotImplementedError("tally_reservoir_energy is outside this path")
         self.filter = filter

@@ -355,6 +355,16 @@ hb2_status hb2_integrator_add_bond(hb2_integrator* it, hb2_bond* b);
  * 47-82 step one = the NVE half step, :213-292 step two with the BD force): translational degrees of
  * freedom, 3D, one drag coefficient per particle type (`gamma[ntypes]`), no reservoir tally. Replaces
  * the ConstantVolume method of this integrator. */
+/* The method's particle group (the ParticleGroup of the method's filter: hoomd/md/IntegrationMethodTwoStep.h,
+ * hoomd/filter/ParticleFilter*.h; hoomd.md.methods.*(filter=...) hoomd/md/methods/methods.py:145-175): the
+ * tags the filter selects. Particles outside the group are not integrated (they keep position and
+ * velocity), the thermostat's kinetic energy and degrees of freedom are the group's (3 n, less 3 only when
+ * the group is every particle: hoomd/md/IntegratorTwoStep.cc:154-189). tags == NULL, n == 0: filter.All. */
+hb2_status hb2_integrator_set_filter_tags(hb2_integrator* it, const uint32_t* tags, uint64_t n);
+/* Kinetic energy of the particles with the given tags (ComputeThermo over a group,
+ * hoomd/md/ComputeThermo.cc:139-153); tags == NULL: every particle. */
+hb2_status hb2_integrator_kinetic_of_tags(hb2_integrator* it, const uint32_t* tags, uint64_t n,
+                                          double* kinetic);
 hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT, const double* gamma,
                                        uint32_t ntypes);
 /* System::run(nsteps) (hoomd/System.cc:80-181) restricted to this path: prepRun on the first call
