@@ -173,6 +173,47 @@ __global__ void __launch_bounds__(CB)
         tag_o[k] = tag[i];
     }
 
+// In-place compaction after the leavers of a migration stage were copied out. `leave` holds the m
+// leaving indices in ascending order; the owned range shrinks to [0, N - m). Every stayer in the tail
+// [N - m, N) moves into a hole below N - m: the r-th tail stayer (ascending) takes the r-th hole
+// (ascending) — as many of one as of the other. The order of the survivors is a pure function of the
+// leaver set, so the run stays reproducible; the cell sort that follows re-orders everything anyway.
+__global__ void __launch_bounds__(CB)
+    fill_holes_kernel(const uint32_t* __restrict__ leave, uint32_t m, uint32_t N,
+                      const uint8_t* __restrict__ cls, float4* __restrict__ pos,
+                      float4* __restrict__ vel, int* __restrict__ img, uint32_t* __restrict__ tag)
+    {
+    const uint32_t k = blockIdx.x * CB + threadIdx.x;
+    if (k >= m)
+        return;
+    const uint32_t n_stay = N - m;
+    const uint32_t t = n_stay + k;
+    if (cls[t] != 0)
+        return;
+    auto lower_bound = [&](uint32_t v)
+    {
+        uint32_t lo = 0, hi = m;
+        while (lo < hi)
+            {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (leave[mid] < v)
+                lo = mid + 1;
+            else
+                hi = mid;
+            }
+        return lo;
+    };
+    const uint32_t h = lower_bound(n_stay);          // holes below the new end
+    const uint32_t r = k - (lower_bound(t) - h);     // stayers in [n_stay, t)
+    const uint32_t dst = leave[r];
+    pos[dst] = pos[t];
+    vel[dst] = vel[t];
+    img[3 * dst] = img[3 * t];
+    img[3 * dst + 1] = img[3 * t + 1];
+    img[3 * dst + 2] = img[3 * t + 2];
+    tag[dst] = tag[t];
+    }
+
 // per-step ghost refresh: sendbuf[k] = pos[idx[k]] (and vel behind it)
 __global__ void __launch_bounds__(CB)
     pack_ghost_kernel(const uint32_t* __restrict__ idx, uint32_t n, const float4* __restrict__ pos,
@@ -398,7 +439,7 @@ static hb2_status exchange(hb2_system* s, int d, const void* send, void* recv, s
     return HB2_OK;
     }
 
-hb2_status domain_migrate(hb2_system* s)
+static hb2_status domain_migrate_copying(hb2_system* s)
     {
     Domain& D = s->dom;
     HB2_TRY(domain_ensure_scratch(s));
@@ -473,6 +514,104 @@ hb2_status domain_migrate(hb2_system* s)
     return HB2_OK;
     }
 
+// HB2_COMM_LEGACY=1 keeps the round-1 exchange (copying compaction, one message per field) for A/B runs
+static bool comm_legacy()
+    {
+    static const bool v = getenv("HB2_COMM_LEGACY") && atoi(getenv("HB2_COMM_LEGACY")) != 0;
+    return v;
+    }
+
+// Migration, in place. Per decomposed dimension: classify, three stream compactions (to above, to below,
+// either — the leavers are a per-mille of the domain between two rebuilds), one host read of the four
+// counts, the leavers' records copied out, ONE grouped NCCL exchange for all four fields (received
+// straight behind the stayers), and the holes of the leavers filled from the tail. Nothing of the size of
+// the domain is copied (the round-1 path gathered every staying particle into the other buffer, three
+// times per rebuild on a 2x2x2 grid).
+hb2_status domain_migrate(hb2_system* s)
+    {
+    if (comm_legacy())
+        return domain_migrate_copying(s);
+    Domain& D = s->dom;
+    HB2_TRY(domain_ensure_scratch(s));
+    cudaStream_t st = s->stream;
+    const BoxD bd = boxd(s->box);
+    const uint32_t cap = s->cap;
+    uint32_t* sel_leave = D.d_sel;
+    uint32_t* sel_up = D.d_sel + cap;
+    uint32_t* sel_down = D.d_sel + 2 * (size_t)cap;
+    float4* sb_pos = D.d_sendbuf;
+    float4* sb_vel = D.d_sendbuf + D.buf_cap;
+    int* sb_img = (int*)D.d_recvbuf; // the receive staging is unused while migrating (direct receive)
+    uint32_t* sb_tag = (uint32_t*)(D.d_recvbuf + D.buf_cap);
+    for (int d = 0; d < 3; d++)
+        {
+        if (D.grid[d] == 1)
+            continue;
+        const uint32_t N = s->N;
+        const int c = s->cur;
+        if (N)
+            {
+            classify_migrate_kernel<<<nblk(N), CB, 0, st>>>(s->pos[c], N, bd, d, D.grid[d], D.coord[d],
+                                                            D.d_cls);
+            HB2_CHECK_LAUNCH("classify_migrate_kernel");
+            }
+        HB2_TRY(select_class(s, N, 3, true, sel_leave, 0));
+        HB2_TRY(select_class(s, N, 1, false, sel_up, 1));
+        HB2_TRY(select_class(s, N, 2, false, sel_down, 2));
+        uint32_t n_up, n_down, from_below, from_above;
+        HB2_TRY(exchange_counts(s, d, 1, 2, n_up, n_down, from_below, from_above));
+        const uint32_t n_leave = n_up + n_down;
+        if (D.h_count[0] != n_leave || n_leave > N)
+            {
+            set_error("domain decomposition: inconsistent migration counts");
+            return HB2_ERR_INVALID;
+            }
+        const uint32_t n_stay = N - n_leave;
+        const uint64_t newN = (uint64_t)n_stay + from_below + from_above;
+        if (newN + s->Ng + 1 > cap || (size_t)n_leave * 3 > D.buf_cap * 4)
+            {
+            set_error("domain decomposition: local particle capacity exceeded during migration");
+            return HB2_ERR_INVALID;
+            }
+        if (n_up)
+            {
+            gather_particles_kernel<<<nblk(n_up), CB, 0, st>>>(sel_up, n_up, s->pos[c], s->vel[c],
+                                                               s->image[c], s->tag[c], sb_pos, sb_vel,
+                                                               sb_img, sb_tag);
+            HB2_CHECK_LAUNCH("gather_particles_kernel");
+            }
+        if (n_down)
+            {
+            gather_particles_kernel<<<nblk(n_down), CB, 0, st>>>(
+                sel_down, n_down, s->pos[c], s->vel[c], s->image[c], s->tag[c], sb_pos + n_up,
+                sb_vel + n_up, sb_img + 3 * (size_t)n_up, sb_tag + n_up);
+            HB2_CHECK_LAUNCH("gather_particles_kernel");
+            }
+        if (n_leave)
+            {
+            fill_holes_kernel<<<nblk(n_leave), CB, 0, st>>>(sel_leave, n_leave, N, D.d_cls, s->pos[c],
+                                                            s->vel[c], s->image[c], s->tag[c]);
+            HB2_CHECK_LAUNCH("fill_holes_kernel");
+            }
+        if (n_leave || from_below || from_above)
+            {
+            HB2_NCCL(g_nccl.GroupStart());
+            HB2_TRY(exchange(s, d, sb_pos, s->pos[c] + n_stay, sizeof(float4), n_up, n_down, from_below,
+                             from_above));
+            HB2_TRY(exchange(s, d, sb_vel, s->vel[c] + n_stay, sizeof(float4), n_up, n_down, from_below,
+                             from_above));
+            HB2_TRY(exchange(s, d, sb_img, s->image[c] + 3 * (size_t)n_stay, 3 * sizeof(int), n_up, n_down,
+                             from_below, from_above));
+            HB2_TRY(exchange(s, d, sb_tag, s->tag[c] + n_stay, sizeof(uint32_t), n_up, n_down, from_below,
+                             from_above));
+            HB2_NCCL(g_nccl.GroupEnd());
+            s->order_epoch++;
+            }
+        s->N = (uint32_t)newN;
+        }
+    return HB2_OK;
+    }
+
 hb2_status domain_exchange_ghosts(hb2_system* s, double r_ghost)
     {
     Domain& D = s->dom;
@@ -529,12 +668,17 @@ hb2_status domain_exchange_ghosts(hb2_system* s, double r_ghost)
                                                              sb_tag);
             HB2_CHECK_LAUNCH("gather_particles_kernel");
             }
+        // one NCCL launch for the three fields of the stage (groups nest; posting order is kept)
+        if (!comm_legacy())
+            HB2_NCCL(g_nccl.GroupStart());
         HB2_TRY(exchange(s, d, sb_pos, s->pos[c] + Ntot, sizeof(float4), n_up, n_down, from_below,
                          from_above));
         HB2_TRY(exchange(s, d, sb_vel, s->vel[c] + Ntot, sizeof(float4), n_up, n_down, from_below,
                          from_above));
         HB2_TRY(exchange(s, d, sb_tag, s->tag[c] + Ntot, sizeof(uint32_t), n_up, n_down, from_below,
                          from_above));
+        if (!comm_legacy())
+            HB2_NCCL(g_nccl.GroupEnd());
         D.n_send[d][1] = n_up;
         D.n_send[d][0] = n_down;
         D.n_recv[d][0] = from_below;
@@ -594,9 +738,14 @@ hb2_status domain_update_ghosts(hb2_system* s)
                                                        sb_pos, D.need_vel ? sb_vel : nullptr);
             HB2_CHECK_LAUNCH("pack_ghost_kernel");
             }
+        if (D.need_vel)
+            HB2_NCCL(g_nccl.GroupStart());
         HB2_TRY(exchange(s, d, sb_pos, rb_pos, sizeof(float4), n_up, n_down, fb, fa));
         if (D.need_vel)
+            {
             HB2_TRY(exchange(s, d, sb_vel, rb_vel, sizeof(float4), n_up, n_down, fb, fa));
+            HB2_NCCL(g_nccl.GroupEnd());
+            }
         if (nr)
             {
             unpack_ghost_kernel<<<nblk(nr), CB, 0, st>>>(D.d_ghost_slot + D.ghost_off[d], nr, rb_pos,
