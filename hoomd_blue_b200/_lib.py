@@ -137,6 +137,13 @@ def _declare(L):
     L.hb2_bond_get.argtypes = [_vp, _f64p, _f64p, _f64p, _f64p]
     L.hb2_integrator_add_bond.argtypes = [_vp, _vp]
     L.hb2_integrator_set_langevin.argtypes = [_vp, C.c_double, _f64p, C.c_uint32]
+    L.hb2_integrator_set_constant_pressure.argtypes = [_vp, _f64p, C.c_double, C.c_int, C.POINTER(C.c_int),
+                                                       C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
+    L.hb2_integrator_get_barostat_dof.argtypes = [_vp, _f64p]
+    L.hb2_integrator_set_barostat_dof.argtypes = [_vp, _f64p]
+    L.hb2_integrator_thermalize_barostat_dof.argtypes = [_vp, C.c_uint64]
+    L.hb2_integrator_barostat_energy.argtypes = [_vp, _f64p]
+    L.hb2_system_get_box.argtypes = [_vp, _f64p]
     L.hb2_integrator_set_filter_tags.argtypes = [_vp, C.POINTER(C.c_uint32), C.c_uint64]
     L.hb2_integrator_kinetic_of_tags.argtypes = [_vp, C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_double)]
     L.hb2_integrator_run.argtypes = [_vp, C.c_uint64]

@@ -1021,6 +1021,8 @@ hb2_status hb2_nlist::rebuild(uint64_t timestep)
         shortest_rebuild = std::min<uint64_t>(shortest_rebuild, timestep - last_update_step);
     has_list = true;
     force_update = false;
+    for (int d = 0; d < 3; d++)
+        last_L[d] = s->box.L[d];
     num_builds++;
     last_update_step = timestep;
     return HB2_OK;
@@ -1903,7 +1905,10 @@ static hb2_status sums7(hb2_pair* p, double out[7])
     return HB2_OK;
     }
 
-static void tail_correction(hb2_pair* p, double& e, double& w)
+// n_per_type_in: particle counts per type already known (the ConstantPressure loop evaluates the correction at
+// every step's volume without downloading the positions again); n_per_type_out: hand the counts back
+static void tail_correction(hb2_pair* p, double& e, double& w, const std::vector<uint32_t>* n_per_type_in = nullptr,
+                            std::vector<uint32_t>* n_per_type_out = nullptr)
     {
     // hoomd/md/PotentialPair.h:283-337 with hoomd/md/EvaluatorPairLJ.h:213-248
     e = 0.0;
@@ -1912,16 +1917,23 @@ static void tail_correction(hb2_pair* p, double& e, double& w)
         return;
     hb2_system* s = p->sys;
     const uint32_t nt = s->ntypes;
-    std::vector<float4> hp(s->N);
-    cudaMemcpyAsync(hp.data(), s->pos[s->cur], sizeof(float4) * s->N, cudaMemcpyDeviceToHost, s->stream);
-    cudaStreamSynchronize(s->stream);
-    std::vector<uint32_t> n_per_type(nt, 0);
-    for (auto& q : hp)
+    std::vector<uint32_t> counted;
+    if (!n_per_type_in)
         {
-        uint32_t t;
-        memcpy(&t, &q.w, 4);
-        n_per_type[t]++;
+        std::vector<float4> hp(s->N);
+        cudaMemcpyAsync(hp.data(), s->pos[s->cur], sizeof(float4) * s->N, cudaMemcpyDeviceToHost, s->stream);
+        cudaStreamSynchronize(s->stream);
+        counted.assign(nt, 0);
+        for (auto& q : hp)
+            {
+            uint32_t t;
+            memcpy(&t, &q.w, 4);
+            counted[t]++;
+            }
+        if (n_per_type_out)
+            *n_per_type_out = counted;
         }
+    const std::vector<uint32_t>& n_per_type = n_per_type_in ? *n_per_type_in : counted;
     const double volume = s->box.L[0] * s->box.L[1] * s->box.L[2];
     const double pi = 3.14159265358979323846;
     for (uint32_t ti = 0; ti < nt; ti++)
@@ -2562,6 +2574,8 @@ extern "C" void hb2_integrator_destroy(hb2_integrator* it)
     dev_free(it->d_total);
     dev_free(it->d_gen);
     dev_free(it->d_member);
+    if (it->npt.h_thermo)
+        cudaFreeHost(it->npt.h_thermo);
     delete it;
     }
 
@@ -2605,6 +2619,7 @@ extern "C" hb2_status hb2_integrator_set_constant_volume(hb2_integrator* it, int
     it->thermostat = thermostat;
     it->kT = kT;
     it->tau = tau;
+    it->npt.on = false;
     return HB2_OK;
     }
 
@@ -2711,8 +2726,289 @@ extern "C" hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT,
                              it->sys->stream));
     HB2_CUDA(cudaStreamSynchronize(it->sys->stream));
     it->thermostat = 2;
+    it->npt.on = false;
     it->kT = kT;
     it->tau = 0.0;
+    return HB2_OK;
+    }
+
+// =================================================================================================
+// ConstantPressure: the barostat lives on the host in fp64 (six numbers), the particles on the device.
+// hoomd/md/TwoStepConstantPressure.cc: advanceBarostat :860-1000, updatePropagator :716-858,
+// getRelevantCouplings :128-170, thermalizeBarostatDOF :501-580, getBarostatEnergy :693-714.
+// Orthorhombic box degrees of freedom only (x, y, z): the engine has no tilt.
+// =================================================================================================
+static int npt_relevant_couplings(int couple, int flags)
+    {
+    // 0 none, 1 xy, 2 xz, 3 yz, 4 xyz
+    if (!(flags & 1))
+        {
+        if (couple == 4)
+            couple = 3;
+        if (couple == 1 || couple == 2)
+            couple = 0;
+        }
+    if (!(flags & 2))
+        {
+        if (couple == 4)
+            couple = 2;
+        if (couple == 3 || couple == 1)
+            couple = 0;
+        }
+    if (!(flags & 4))
+        {
+        if (couple == 4)
+            couple = 1;
+        if (couple == 3 || couple == 2)
+            couple = 0;
+        }
+    return couple;
+    }
+
+static double npt_W(const hb2_integrator* it)
+    {
+    const auto& n = it->npt;
+    const double T = it->thermostat == 1 ? it->kT : 1.0;
+    return (n.ndof + 3.0) / 3.0 * T * n.tauS * n.tauS;
+    }
+
+static void npt_advance_barostat(hb2_integrator* it, uint64_t timestep)
+    {
+    auto& n = it->npt;
+    hb2_system* s = it->sys;
+    const double dt = it->dt;
+    const double V = s->box.L[0] * s->box.L[1] * s->box.L[2];
+    const double T = it->thermostat == 1 ? it->kT : 1.0;
+    const double W = npt_W(it);
+    double mtk_term = 2.0 * n.ke;
+    mtk_term *= 0.5 * dt / n.ndof / W;
+    const int couple = npt_relevant_couplings(n.couple, n.flags);
+    const double Pxx = n.P[0], Pyy = n.P[3], Pzz = n.P[5];
+    double Pd[3] = {0, 0, 0}, Rd[3] = {0, 0, 0};
+    double z[3];
+    rng_normals_host(46 /* RNGIdentifier::ConstantPressure */, timestep, s->seed, 0u, 3, z);
+    switch (couple)
+        {
+    case 0:
+        Pd[0] = Pxx;
+        Rd[0] = z[0];
+        Pd[1] = Pyy;
+        Rd[1] = z[1];
+        Pd[2] = Pzz;
+        Rd[2] = z[2];
+        break;
+    case 1:
+        Pd[0] = Pd[1] = 0.5 * (Pxx + Pyy);
+        Rd[0] = Rd[1] = z[0];
+        Pd[2] = Pzz;
+        Rd[2] = z[1];
+        break;
+    case 2:
+        Pd[0] = Pd[2] = 0.5 * (Pxx + Pzz);
+        Rd[0] = Rd[2] = z[0];
+        Pd[1] = Pyy;
+        Rd[1] = z[1];
+        break;
+    case 3:
+        Pd[0] = Pxx;
+        Rd[0] = z[0];
+        Pd[1] = Pd[2] = 0.5 * (Pyy + Pzz);
+        Rd[1] = Rd[2] = z[1];
+        break;
+    default:
+        Pd[0] = Pd[1] = Pd[2] = (1.0 / 3.0) * (Pxx + Pyy + Pzz);
+        Rd[0] = Rd[1] = Rd[2] = z[0];
+        break;
+        }
+    const double e = std::exp(-n.gamma * dt / 2.0);
+    const double coeff = std::sqrt(T * (1.0 - e * e) / W);
+    const int nu_idx[3] = {0, 3, 5}; // nu_xx, nu_yy, nu_zz
+    for (int d = 0; d < 3; d++)
+        if (n.flags & (1 << d))
+            {
+            double& nu = n.nu[nu_idx[d]];
+            nu = nu * e + coeff * Rd[d];
+            nu += 0.5 * dt * V / W * (Pd[d] - n.S[d]) + mtk_term;
+            }
+    }
+
+static void npt_update_propagator(hb2_integrator* it)
+    {
+    auto& n = it->npt;
+    const double dt = it->dt;
+    static const double f_coeff[6] = {1.0, 1.0 / 6.0, 1.0 / 120.0, 1.0 / 5040.0, 1.0 / 362880.0, 1.0 / 39916800.0};
+    const int nu_idx[3] = {0, 3, 5};
+    for (int d = 0; d < 3; d++)
+        {
+        const double nu = n.nu[nu_idx[d]];
+        const double v_fac = -0.25 * nu;
+        const double arg_r = 0.5 * nu * dt;
+        double f_r = 0.0, term = 1.0;
+        for (int i = 0; i < 6; i++)
+            {
+            f_r += f_coeff[i] * term;
+            term = term * arg_r * arg_r;
+            }
+        n.exp_v[d] = std::exp(2.0 * v_fac * dt);
+        n.exp_r[d] = std::exp(nu * dt);
+        n.exp_r_int[d] = dt * std::exp(0.5 * nu * dt) * f_r;
+        }
+    }
+
+// the thermodynamic quantities the barostat reads (ComputeThermo of the method's group, every particle on
+// this path): kinetic tensor of the current velocities (k.dt == 0) or left in d_sums + 10 by step two,
+// virial sums of the net force plus the forces' external virial; one host read.
+static hb2_status npt_thermo(hb2_integrator* it, hb2_pair* pf, bool kinetic_from_velocities)
+    {
+    hb2_system* s = it->sys;
+    auto& n = it->npt;
+    cudaStream_t st = s->stream;
+    if (kinetic_from_velocities)
+        {
+        NptFactors k0;
+        HB2_TRY(launch_step_two_npt(s->vel[s->cur], pf->d_force, s->N, k0, s->d_partial, s->d_ticket + 2,
+                                    s->d_sums + 10, st, GroupMask {it->d_member, s->tag[s->cur]}));
+        }
+    HB2_TRY(launch_reduce_energy(pf->d_force, pf->d_virial, pf->cap_N, s->N, s->d_partial, s->d_ticket + 1,
+                                 s->d_sums + 1, st));
+    HB2_CUDA(cudaMemcpyAsync(n.h_thermo, s->d_sums + 1, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaMemcpyAsync(n.h_thermo + 7, s->d_sums + 10, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB2_CUDA(cudaStreamSynchronize(st));
+    const double V = s->box.L[0] * s->box.L[1] * s->box.L[2];
+    // external virial: the LJ tail correction at the current volume (hoomd/md/PotentialPair.h:283-337),
+    // a function of the volume and the type counts alone, so a run cut into segments sees the same numbers
+    double wext = 0.0;
+    if (n.tail_valid)
+        for (auto* p : it->forces)
+            {
+            double te, tw;
+            tail_correction(p, te, tw, &n.n_per_type);
+            wext += tw;
+            }
+    const double* w = n.h_thermo + 1; // xx xy xz yy yz zz
+    const double* kt = n.h_thermo + 7;
+    for (int q = 0; q < 6; q++)
+        {
+        const bool diag = q == 0 || q == 3 || q == 5;
+        n.P[q] = (kt[q] + w[q] + (diag ? wext : 0.0)) / V;
+        }
+    n.ke = 0.5 * (kt[0] + kt[3] + kt[5]);
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_set_constant_pressure(hb2_integrator* it, const double S[6], double tauS,
+                                                           int couple, const int box_dof[6], int rescale_all,
+                                                           double gamma, int thermostat, double kT, double tau)
+    {
+    if (!it || !S || !box_dof || couple < 0 || couple > 4 || (thermostat != 0 && thermostat != 1) || !(tauS > 0.0))
+        {
+        set_error("hb2_integrator_set_constant_pressure: bad arguments");
+        return HB2_ERR_INVALID;
+        }
+    if (box_dof[3] || box_dof[4] || box_dof[5])
+        {
+        set_error("ConstantPressure: the shear degrees of freedom (xy, xz, yz) need a triclinic box, which is "
+                  "outside this path's scope");
+        return HB2_ERR_INVALID;
+        }
+    if (it->sys->dom.active)
+        {
+        set_error("ConstantPressure under domain decomposition is not built on this path");
+        return HB2_ERR_INVALID;
+        }
+    HB2_CUDA(cudaSetDevice(it->sys->device));
+    auto& n = it->npt;
+    n.on = true;
+    for (int q = 0; q < 6; q++)
+        n.S[q] = S[q];
+    n.tauS = tauS;
+    n.couple = couple;
+    n.flags = (box_dof[0] ? 1 : 0) | (box_dof[1] ? 2 : 0) | (box_dof[2] ? 4 : 0);
+    n.rescale_all = rescale_all != 0;
+    n.gamma = gamma;
+    if (!n.h_thermo)
+        HB2_CUDA(cudaMallocHost((void**)&n.h_thermo, 16 * sizeof(double)));
+    it->thermostat = thermostat;
+    it->kT = kT;
+    it->tau = tau;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_get_barostat_dof(hb2_integrator* it, double nu[6])
+    {
+    if (!it || !nu)
+        return HB2_ERR_INVALID;
+    for (int q = 0; q < 6; q++)
+        nu[q] = it->npt.nu[q];
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_set_barostat_dof(hb2_integrator* it, const double nu[6])
+    {
+    if (!it || !nu)
+        return HB2_ERR_INVALID;
+    for (int q = 0; q < 6; q++)
+        it->npt.nu[q] = nu[q];
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_thermalize_barostat_dof(hb2_integrator* it, uint64_t timestep)
+    {
+    if (!it || !it->npt.on)
+        return HB2_ERR_INVALID;
+    auto& n = it->npt;
+    const double sigmasq = 1.0 / ((n.ndof + 3.0) / 3.0 * n.tauS * n.tauS);
+    // one draw per enabled degree of freedom in the order xx, xy, xz, yy, yz, zz
+    // (RNGIdentifier::TwoStepConstantPressureThermalizeBarostat = 27)
+    double z[3];
+    int nd = 0;
+    for (int d = 0; d < 3; d++)
+        nd += (n.flags >> d) & 1;
+    rng_normals_host(27, timestep, it->sys->seed, 0u, nd, z);
+    const int nu_idx[3] = {0, 3, 5};
+    int k = 0;
+    for (int d = 0; d < 3; d++)
+        if (n.flags & (1 << d))
+            n.nu[nu_idx[d]] = std::sqrt(sigmasq) * z[k++];
+    switch (npt_relevant_couplings(n.couple, n.flags))
+        {
+    case 1:
+        n.nu[3] = n.nu[0];
+        break;
+    case 2:
+        n.nu[5] = n.nu[0];
+        break;
+    case 3:
+        n.nu[3] = n.nu[5];
+        break;
+    case 4:
+        n.nu[0] = n.nu[5];
+        n.nu[3] = n.nu[5];
+        break;
+    default:
+        break;
+        }
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_integrator_barostat_energy(hb2_integrator* it, double* energy)
+    {
+    if (!it || !energy || !it->npt.on)
+        return HB2_ERR_INVALID;
+    const auto& n = it->npt;
+    double s2 = 0.0;
+    for (int q = 0; q < 6; q++)
+        s2 += n.nu[q] * n.nu[q];
+    *energy = npt_W(it) * s2 / 2.0;
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_system_get_box(hb2_system* s, double L[3])
+    {
+    if (!s || !L || !s->has_box)
+        return HB2_ERR_INVALID;
+    for (int d = 0; d < 3; d++)
+        L[d] = s->box.L[d];
     return HB2_OK;
     }
 
@@ -2738,6 +3034,21 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         }
     double* d_ke = s->d_sums;
     double* d_rescale = s->d_sums + 8;
+    auto& npt = it->npt;
+    // the barostat reads the pressure tensor every step: the pressure flag is up for the whole run
+    // (TwoStepConstantPressure::getRequestedPDataFlags) and handed back afterwards
+    struct VirialFlag
+        {
+        hb2_system* s;
+        bool saved, active;
+        ~VirialFlag()
+            {
+            if (active)
+                s->compute_virial = saved;
+            }
+        } virial_flag {s, s->compute_virial, npt.on};
+    if (npt.on)
+        s->compute_virial = true;
     // translational degrees of freedom of filter All, momentum conserving, 3D
     // (hoomd/md/IntegratorTwoStep.cc:154-189)
     // (a method on a proper subset of the particles keeps all 3 n: the centre of mass of the group is not
@@ -2776,12 +3087,38 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         if (s->dom.active)
             HB2_TRY(domain_allreduce_sum_f64(s, d_ke, 1));
         }
+    if (npt.on)
+        {
+        if (s->dom.active)
+            {
+            set_error("ConstantPressure under domain decomposition is not built on this path");
+            return HB2_ERR_INVALID;
+            }
+        if (!pf->virial_valid)
+            {
+            // the net force of this timestep exists but without its virial: same list, one more pass
+            HB2_TRY(pf->launch(s->timestep, true, nullptr));
+            HB2_TRY(integrator_add_extra(it, pf, s->timestep, true, nullptr));
+            }
+        npt.tail_valid = false;
+        npt.n_per_type.clear();
+        for (auto* p : it->forces)
+            if (p->tail_correction && !npt.tail_valid)
+                {
+                double te, tw;
+                tail_correction(p, te, tw, nullptr, &npt.n_per_type);
+                npt.tail_valid = true;
+                }
+        // thermo of the current timestep (the reference's advanceBarostat(timestep) at the top of step one
+        // computes it when no step two left it behind)
+        HB2_TRY(npt_thermo(it, pf, true));
+        }
 
     it->pool_used = 0;
     it->marks.clear();
     // ConstantVolume on one GPU: step two of a timestep and step one of the next share a launch
     static const bool fuse_enabled = !(getenv("HB2_FUSE_INTEGRATE") && atoi(getenv("HB2_FUSE_INTEGRATE")) == 0);
-    bool fuse = fuse_enabled && it->thermostat != 2 && !s->dom.active;
+    bool fuse = fuse_enabled && it->thermostat != 2 && !s->dom.active && !npt.on;
     if (fuse && !it->d_gen)
         {
         HB2_TRY(dev_alloc(&it->d_gen, 1));
@@ -2802,7 +3139,7 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
                 }
             HB2_CUDA(cudaEventRecord(pe[0], st));
             }
-        if (it->thermostat == 1)
+        if (it->thermostat == 1 && !npt.on)
             {
             // the factor of step t comes from the KE left by step t-1: drawn inside step two's
             // reduction on a single GPU; after the KE all-reduce with a domain decomposition, and for
@@ -2812,7 +3149,53 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             rescale = d_rescale;
             }
         const bool check = nl->has_list && nl->check_dist;
-        if (!one_done)
+        NptFactors nk;
+        if (npt.on)
+            {
+            // TwoStepConstantPressure::integrateStepOne, host part: half a barostat step with the thermo of
+            // this timestep, MTK and thermostat factors, propagators, the box; then the particles
+            npt.ndof = dof;
+            npt_advance_barostat(it, t);
+            const double mtk = std::exp(-0.5 * it->dt * (npt.nu[0] + npt.nu[3] + npt.nu[5]) / npt.ndof);
+            const double th = it->thermostat == 1
+                                  ? bussi_factor_host(npt.ke, dof, it->dt, it->kT, it->tau, t, s->seed, 0u)
+                                  : 1.0;
+            npt_update_propagator(it);
+            HB2_TRY(hb2_box_make(&s->box, npt.exp_r[0] * s->box.L[0], npt.exp_r[1] * s->box.L[1],
+                                 npt.exp_r[2] * s->box.L[2]));
+            nk.dt = (float)it->dt;
+            nk.rescale_all = npt.rescale_all ? 1 : 0;
+            double lambda_min = 1e300;
+            for (int d = 0; d < 3; d++)
+                {
+                nk.exp_v[d] = (float)npt.exp_v[d];
+                nk.exp_r[d] = (float)npt.exp_r[d];
+                nk.exp_r_int[d] = (float)npt.exp_r_int[d];
+                const double lam = check ? s->box.L[d] / nl->last_L[d] : 1.0;
+                nk.lambda[d] = (float)lam;
+                lambda_min = std::min(lambda_min, lam);
+                }
+            // hoomd/md/NeighborList.cc:1236-1260: the displacement left after the homogeneous dilation is
+            // taken out, against ((r_cut_max + buffer) lambda_min - r_cut_max) / 2 per type
+            double worst = 1e300;
+            for (uint32_t ty = 0; ty < s->ntypes; ty++)
+                {
+                const double rmin = nl->rcut_max.size() > ty ? nl->rcut_max[ty] : nl->rcut_max_max;
+                const double dmax = ((rmin + nl->buffer) * lambda_min - rmin) / 2.0;
+                const double msq = dmax > 0.0 ? dmax * dmax : 0.0;
+                worst = std::min(worst, msq);
+                if (ty < (uint32_t)NPT_MAX_TYPES)
+                    nk.maxsq[ty] = (float)msq;
+                }
+            if (s->ntypes > (uint32_t)NPT_MAX_TYPES) // more types than slots: the strictest threshold for the rest
+                nk.maxsq[NPT_MAX_TYPES - 1] = (float)worst;
+            nk.mtk = (float)(mtk * th);
+            HB2_TRY(launch_step_one_npt(s->pos[s->cur], s->vel[s->cur], pf->d_force, s->image[s->cur], s->N, s->box,
+                                        nk, nullptr, check ? nl->d_last_pos : nullptr, nl->d_conditions + 3, st,
+                                        GroupMask {it->d_member, s->tag[s->cur]}));
+            nk.mtk = (float)mtk; // step two: the MTK factor alone (Bussi rescales in step one only)
+            }
+        else if (!one_done)
             {
         // (Langevin: the previous step two left F + F_bd for this half step)
         // (valid for this particle order and this timestep only: a snapshot set in between, or a
@@ -2902,7 +3285,16 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
             bn.timestep = t + 1;
             bn.seed = s->seed;
             }
-        if (it->thermostat == 2)
+        if (npt.on)
+            {
+            // TwoStepConstantPressure::integrateStepTwo: kick with the same propagator, then the thermo of
+            // timestep t + 1 and the second half of the barostat step
+            HB2_TRY(launch_step_two_npt(s->vel[s->cur], pf->d_force, s->N, nk, s->d_partial, s->d_ticket + 2,
+                                        s->d_sums + 10, st, GroupMask {it->d_member, s->tag[s->cur]}));
+            HB2_TRY(npt_thermo(it, pf, false));
+            npt_advance_barostat(it, t + 1);
+            }
+        else if (it->thermostat == 2)
             {
             if (s->N > it->total_cap)
                 {

@@ -174,6 +174,7 @@ struct hb2_nlist
     bool want_tiles() const;
     TileBuildArgs tile_args() const;
     hb2_status global_rows(); // make d_nlist valid for the current build
+    double last_L[3] = {0, 0, 0}; // box lengths at the last build (hoomd/md/NeighborList.cc m_last_L)
     float maxshift() const
         {
         // hoomd/md/NeighborList.cc:1244-1260 with a fixed box (lambda = 1): (r_max - r_min)/2
@@ -262,6 +263,24 @@ struct hb2_integrator
     uint32_t* d_gen = nullptr; // generation word of the fused step-two/step-one kernel (integrate.cu)
     uint32_t gen_epoch = 0;
     uint64_t total_epoch = 0, total_step = 0; // particle order and timestep d_total belongs to
+    // ConstantPressure (hoomd/md/TwoStepConstantPressure.h): barostat state, host side, fp64
+    struct Npt
+        {
+        bool on = false;
+        double S[6] = {0, 0, 0, 0, 0, 0}; // set point, Voigt order xx yy zz yz xz xy (the reference's m_S)
+        double tauS = 1.0, gamma = 0.0;
+        int couple = 0;                   // 0 none, 1 xy, 2 xz, 3 yz, 4 xyz
+        int flags = 7;                    // bit 0 x, bit 1 y, bit 2 z
+        bool rescale_all = false;
+        double nu[6] = {0, 0, 0, 0, 0, 0}; // nu_xx, nu_xy, nu_xz, nu_yy, nu_yz, nu_zz
+        double ndof = 0.0;                 // set by step one, as the reference's m_ndof
+        double P[6] = {0, 0, 0, 0, 0, 0};  // pressure tensor xx xy xz yy yz zz of the last thermo
+        double ke = 0.0;
+        double exp_v[3] = {1, 1, 1}, exp_r[3] = {1, 1, 1}, exp_r_int[3] = {0, 0, 0};
+        std::vector<uint32_t> n_per_type; // particles per type (the tail correction's densities)
+        bool tail_valid = false;          // some force carries a tail correction
+        double* h_thermo = nullptr; // pinned: 7 energy/virial sums + 6 kinetic sums
+        } npt;
     bool prepared = false;
     bool reset_stats = true; // reset the neighbour list's num_builds / shortest_rebuild at the start of run
     uint64_t prepared_epoch = 0;

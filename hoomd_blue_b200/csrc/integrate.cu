@@ -12,6 +12,7 @@
 #include "rng.cuh"
 #include "reduce.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace hb2
     {
@@ -418,6 +419,153 @@ __global__ void __launch_bounds__(INT_BLOCK)
     total[i] = make_float4(tx, ty, tz, f.w);
     }
 
+// ---- ConstantPressure (MTK barostat, orthorhombic box degrees of freedom) -------------------------
+// TwoStepConstantPressure::integrateStepOne (hoomd/md/TwoStepConstantPressure.cc:213-395; GPU kernels
+// hoomd/md/TwoStepConstantPressureGPU.cu): v += 1/2 dt a; v <- exp_v v; v *= s; r <- exp_r r + exp_r_int v;
+// wrap into the NEW box; then the neighbour list's distance check with the homogeneous dilation taken
+// out (hoomd/md/NeighborList.cc:1236-1260): |minImage(r - lambda r_last)|^2 >= maxsq[type]. The
+// propagator matrices are upper triangular; the host hands the diagonals (tilt is outside this path).
+// Particles outside the group are only rescaled, and only with rescale_all.
+__global__ void __launch_bounds__(INT_BLOCK)
+    step_one_npt_kernel(float4* __restrict__ pos, float4* __restrict__ vel, const float4* __restrict__ force,
+                        int* __restrict__ image, uint32_t N, BoxF box, NptFactors k,
+                        const double* __restrict__ d_rescale, const float4* __restrict__ last_pos,
+                        uint32_t* __restrict__ d_flag, GroupMask group)
+    {
+    const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
+    if (i >= N)
+        return;
+    const bool member = in_group(group, i);
+    if (!member && !k.rescale_all)
+        return;
+    float4 p = pos[i];
+    p.x *= k.exp_r[0];
+    p.y *= k.exp_r[1];
+    p.z *= k.exp_r[2];
+    if (member)
+        {
+        const float s = (d_rescale ? (float)(*d_rescale) : 1.0f) * k.mtk;
+        float4 v = vel[i];
+        const float4 f = force[i];
+        const float minv = 1.0f / v.w;
+        const float hdt = 0.5f * k.dt;
+        v.x = kick(v.x, f.x, minv, hdt) * k.exp_v[0] * s;
+        v.y = kick(v.y, f.y, minv, hdt) * k.exp_v[1] * s;
+        v.z = kick(v.z, f.z, minv, hdt) * k.exp_v[2] * s;
+        p.x = __fmaf_rn(k.exp_r_int[0], v.x, p.x);
+        p.y = __fmaf_rn(k.exp_r_int[1], v.y, p.y);
+        p.z = __fmaf_rn(k.exp_r_int[2], v.z, p.z);
+        vel[i] = v;
+        }
+    int ix = 0, iy = 0, iz = 0;
+    // a rescaled coordinate can sit a rounding error outside the rescaled box as well as a drift outside
+    if (p.x >= box.hi[0])
+        {
+        p.x -= box.L[0];
+        ix = 1;
+        }
+    else if (p.x < box.lo[0])
+        {
+        p.x += box.L[0];
+        ix = -1;
+        }
+    if (p.y >= box.hi[1])
+        {
+        p.y -= box.L[1];
+        iy = 1;
+        }
+    else if (p.y < box.lo[1])
+        {
+        p.y += box.L[1];
+        iy = -1;
+        }
+    if (p.z >= box.hi[2])
+        {
+        p.z -= box.L[2];
+        iz = 1;
+        }
+    else if (p.z < box.lo[2])
+        {
+        p.z += box.L[2];
+        iz = -1;
+        }
+    pos[i] = p;
+    if (ix | iy | iz)
+        {
+        image[3 * i + 0] += ix;
+        image[3 * i + 1] += iy;
+        image[3 * i + 2] += iz;
+        }
+    if (last_pos)
+        {
+        const float4 q = last_pos[i];
+        const uint32_t t = __float_as_uint(p.w);
+        const float dx = min_image_f(p.x - k.lambda[0] * q.x, box.L[0], box.hi[0]);
+        const float dy = min_image_f(p.y - k.lambda[1] * q.y, box.L[1], box.hi[1]);
+        const float dz = min_image_f(p.z - k.lambda[2] * q.z, box.L[2], box.hi[2]);
+        if (dx * dx + dy * dy + dz * dz >= k.maxsq[t < NPT_MAX_TYPES ? t : NPT_MAX_TYPES - 1])
+            *d_flag = 1u;
+        }
+    }
+
+// TwoStepConstantPressure::integrateStepTwo (hoomd/md/TwoStepConstantPressure.cc:583-640):
+// v *= s; v <- exp_v v; v += 1/2 dt a; then the kinetic part of the pressure tensor, sum m v_a v_b over
+// the group in fp64 (hoomd/md/ComputeThermo.cc:104-123), out6 = xx, xy, xz, yy, yz, zz.
+__global__ void __launch_bounds__(INT_BLOCK)
+    step_two_npt_kernel(float4* __restrict__ vel, const float4* __restrict__ force, uint32_t N, NptFactors k,
+                        double* __restrict__ partial, uint32_t* __restrict__ ticket, double* __restrict__ out6,
+                        GroupMask group)
+    {
+    const uint32_t i = blockIdx.x * INT_BLOCK + threadIdx.x;
+    double kt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i < N && in_group(group, i))
+        {
+        float4 v = vel[i];
+        if (k.dt != 0.0f) // dt = 0: the tensor of the velocities as they are (thermo at the start of a run)
+            {
+            const float4 f = force[i];
+            const float minv = 1.0f / v.w;
+            const float hdt = 0.5f * k.dt;
+            v.x = kick(v.x * k.mtk * k.exp_v[0], f.x, minv, hdt);
+            v.y = kick(v.y * k.mtk * k.exp_v[1], f.y, minv, hdt);
+            v.z = kick(v.z * k.mtk * k.exp_v[2], f.z, minv, hdt);
+            vel[i] = v;
+            }
+        const double m = (double)v.w, x = (double)v.x, y = (double)v.y, z = (double)v.z;
+        kt[0] = m * (x * x);
+        kt[1] = m * (x * y);
+        kt[2] = m * (x * z);
+        kt[3] = m * (y * y);
+        kt[4] = m * (y * z);
+        kt[5] = m * (z * z);
+        }
+    grid_sum<6, INT_BLOCK>(kt, partial, ticket, out6);
+    }
+
+hb2_status launch_step_one_npt(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
+                               const hb2_box& box, const NptFactors& k, const double* d_rescale,
+                               const float4* last_pos, uint32_t* d_flag, cudaStream_t stream, GroupMask group)
+    {
+    if (N == 0)
+        return HB2_OK;
+    step_one_npt_kernel<<<(N + INT_BLOCK - 1) / INT_BLOCK, INT_BLOCK, 0, stream>>>(
+        pos, vel, force, image, N, boxf(box), k, d_rescale, last_pos, d_flag, group);
+    HB2_CHECK_LAUNCH("step_one_npt_kernel");
+    return HB2_OK;
+    }
+
+hb2_status launch_step_two_npt(float4* vel, const float4* force, uint32_t N, const NptFactors& k,
+                               double* d_partial, uint32_t* d_ticket, double* d_out6, cudaStream_t stream,
+                               GroupMask group)
+    {
+    if (N == 0)
+        return HB2_OK;
+    step_two_npt_kernel<<<(N + INT_BLOCK - 1) / INT_BLOCK, INT_BLOCK, 0, stream>>>(vel, force, N, k, d_partial,
+                                                                                   d_ticket, d_out6, group);
+    HB2_CHECK_LAUNCH("step_two_npt_kernel");
+    return HB2_OK;
+    }
+
 // net force += one more force (Integrator::computeNetForce, hoomd/Integrator.cc:166-246)
 __global__ void __launch_bounds__(INT_BLOCK)
     accumulate_force_kernel(float4* __restrict__ dst, float* __restrict__ dst_virial, size_t dst_pitch,
@@ -612,9 +760,15 @@ hb2_status launch_step_two_one(float4* pos, float4* vel, const float4* force, in
         GroupMask a_group = group;
         void* args[] = {&a_pos, &a_vel, &a_force, &a_image, &a_N, &a_box, &a_dt, &a_last, &a_ms, &a_flag,
                         &a_part, &a_ticket, &a_ke, &a_b, &a_gen, &a_epoch, &a_group};
-        const cudaError_t e = cudaLaunchCooperativeKernel((const void*)step_two_one_kernel<true>,
-                                                          dim3(std::min<uint32_t>(nvb, (uint32_t)wave)),
-                                                          dim3(INT_BLOCK), args, 0, stream);
+        // HB2_FUSE_COOP=0: a plain launch of the same one-wave grid (A/B of the cooperative launch's cost; the
+        // blocks still all become resident on a stream that runs nothing else, but nothing guarantees it)
+        static const bool coop = !(getenv("HB2_FUSE_COOP") && atoi(getenv("HB2_FUSE_COOP")) == 0);
+        const cudaError_t e = coop ? cudaLaunchCooperativeKernel((const void*)step_two_one_kernel<true>,
+                                                                 dim3(std::min<uint32_t>(nvb, (uint32_t)wave)),
+                                                                 dim3(INT_BLOCK), args, 0, stream)
+                                   : cudaLaunchKernel((const void*)step_two_one_kernel<true>,
+                                                      dim3(std::min<uint32_t>(nvb, (uint32_t)wave)),
+                                                      dim3(INT_BLOCK), args, 0, stream);
         if (e != cudaSuccess)
             {
             cudaGetLastError();
@@ -674,6 +828,15 @@ hb2_status launch_advance_timestep(uint64_t* d_timestep, cudaStream_t stream)
     advance_timestep_kernel<<<1, 32, 0, stream>>>(d_timestep);
     HB2_CHECK_LAUNCH("advance_timestep_kernel");
     return HB2_OK;
+    }
+
+// n successive standard-normal draws of RandomGenerator(Seed(id, timestep, seed), Counter(first_tag)) on
+// the host (the barostat's noise, hoomd/md/TwoStepConstantPressure.cc:907-945, and its thermalisation)
+void rng_normals_host(uint8_t id, uint64_t timestep, uint32_t seed, uint32_t first_tag, int n, double* out)
+    {
+    Rng g(id, timestep, (uint16_t)seed, first_tag);
+    for (int k = 0; k < n; k++)
+        out[k] = rng_normal(g);
     }
 
 double bussi_factor_host(double K, double dof, double dt, double kT, double tau, uint64_t timestep,

@@ -181,6 +181,27 @@ hb2_status launch_step_two_langevin(float4* vel, const float4* force, float4* to
                                     const uint32_t* tag, uint32_t N, float dt, const float* d_gamma_coeff,
                                     uint32_t seed, uint64_t timestep, cudaStream_t stream,
                                     const uint8_t* member = nullptr);
+// ConstantPressure half steps (integrate.cu): the host advances the barostat and hands the propagators
+constexpr int NPT_MAX_TYPES = 8;
+struct NptFactors
+    {
+    float dt = 0.f;
+    float mtk = 1.f;                          // exp(-dt/2 (nu_xx + nu_yy + nu_zz) / ndof)
+    float exp_v[3] = {1.f, 1.f, 1.f};         // velocity propagator, diagonal
+    float exp_r[3] = {1.f, 1.f, 1.f};         // position (and box) propagator, diagonal
+    float exp_r_int[3] = {0.f, 0.f, 0.f};     // integrated position propagator (multiplies v), diagonal
+    float lambda[3] = {1.f, 1.f, 1.f};        // L_now / L_at_last_build
+    float maxsq[NPT_MAX_TYPES] = {0, 0, 0, 0, 0, 0, 0, 0}; // distance-check threshold per type
+    int rescale_all = 0;
+    };
+hb2_status launch_step_one_npt(float4* pos, float4* vel, const float4* force, int* image, uint32_t N,
+                               const hb2_box& box, const NptFactors& k, const double* d_rescale,
+                               const float4* last_pos, uint32_t* d_flag, cudaStream_t stream,
+                               GroupMask group = GroupMask());
+// k.dt = 0: only the kinetic tensor of the current velocities
+hb2_status launch_step_two_npt(float4* vel, const float4* force, uint32_t N, const NptFactors& k,
+                               double* d_partial, uint32_t* d_ticket, double* d_out6, cudaStream_t stream,
+                               GroupMask group = GroupMask());
 hb2_status launch_kinetic(const float4* vel, uint32_t N, double* d_partial, uint32_t* d_ticket,
                           double* d_ke_out, cudaStream_t stream, GroupMask group = GroupMask());
 // Bussi factor on device (hoomd/md/Thermostat.h:357-447): *d_rescale <- factor for the step-one of
@@ -200,6 +221,7 @@ hb2_status launch_reduce_energy(const float4* force, const float* virial, size_t
                                 cudaStream_t stream);
 uint32_t reduce_blocks(uint32_t N);
 
+void rng_normals_host(uint8_t id, uint64_t timestep, uint32_t seed, uint32_t first_tag, int n, double* out);
 double bussi_factor_host(double K, double dof, double dt, double kT, double tau, uint64_t timestep,
                          uint32_t seed, uint32_t first_tag);
     } // namespace hb2

@@ -5,7 +5,7 @@ from .. import _lib
 from .._lib import check
 import numpy as np
 
-from .methods import ConstantVolume, Bussi, Langevin
+from .methods import ConstantVolume, ConstantPressure, Bussi, Langevin
 
 
 class Integrator:
@@ -45,8 +45,9 @@ class Integrator:
             pairs = [hidden]
             self._hidden_pair = hidden
         if len(self.methods) > 1 or (self.methods
-                                     and not isinstance(self.methods[0], (ConstantVolume, Langevin))):
-            raise NotImplementedError("this path integrates with one ConstantVolume or Langevin method")
+                                     and not isinstance(self.methods[0], (ConstantVolume, ConstantPressure, Langevin))):
+            raise NotImplementedError("this path integrates with one ConstantVolume, ConstantPressure or "
+                                      "Langevin method")
         L = _lib.lib()
         h = C.c_void_p()
         check(L.hb2_integrator_create(C.byref(h), sim.state._h, self.dt))
@@ -67,6 +68,18 @@ class Integrator:
             m = self.methods[0]
             gamma = np.array([m.gamma[t] for t in sim.state.particle_types], dtype=np.float64)
             check(L.hb2_integrator_set_langevin(h, m.kT, _lib.ptr(gamma, C.c_double), len(gamma)))
+        elif self.methods and isinstance(self.methods[0], ConstantPressure):
+            m = self.methods[0]
+            from ..filter import All
+            if not isinstance(m.filter, All):
+                raise NotImplementedError("ConstantPressure integrates every particle on this path (filter.All)")
+            S = (C.c_double * 6)(*m.S)
+            dofs = (C.c_int * 6)(*[int(b) for b in m.box_dof])
+            check(L.hb2_integrator_set_constant_pressure(
+                h, S, m.tauS, m._couples[m.couple], dofs, int(m.rescale_all), m.gamma,
+                1 if isinstance(th, Bussi) else 0, th.kT if th else 0.0, th.tau if th else 0.0))
+            m._integrator = self
+            check(L.hb2_integrator_set_barostat_dof(h, (C.c_double * 6)(*m._barostat_dof)))
         elif isinstance(th, Bussi):
             check(L.hb2_integrator_set_constant_volume(h, 1, th.kT, th.tau))
         else:
@@ -99,7 +112,17 @@ class Integrator:
         for b in getattr(self, "_bonds", []):
             b._sync()
         check(_lib.lib().hb2_integrator_set_reset_stats(self._h, int(bool(first_segment))))
+        if self.methods and isinstance(self.methods[0], ConstantPressure):
+            # parameters may have been changed between runs (npt.S = ..., npt.tauS = ...)
+            m = self.methods[0]
+            th = m.thermostat
+            check(_lib.lib().hb2_integrator_set_constant_pressure(
+                self._h, (C.c_double * 6)(*m.S), m.tauS, m._couples[m.couple],
+                (C.c_int * 6)(*[int(b) for b in m.box_dof]), int(m.rescale_all), m.gamma,
+                1 if isinstance(th, Bussi) else 0, th.kT if th else 0.0, th.tau if th else 0.0))
         check(_lib.lib().hb2_integrator_run(self._h, steps))
+        if self.methods and isinstance(self.methods[0], ConstantPressure):
+            self._sim.state._refresh_box()
 
     def _last_run_ms(self):
         ms = C.c_float(0)

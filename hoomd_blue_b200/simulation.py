@@ -487,6 +487,13 @@ class State:
     def box(self):
         return _BoxView(self._box)
 
+    def _refresh_box(self):
+        """Box lengths back from the engine (a ConstantPressure run rescales them)."""
+        import ctypes as C
+        L3 = (C.c_double * 3)()
+        check(_lib.lib().hb2_system_get_box(self._h, L3))
+        self._box = [L3[0], L3[1], L3[2]] + list(self._box[3:])
+
     def _destroy(self):
         """Free the device state now (every rank of a decomposed system calls it)."""
         if getattr(self, "_h", None):

@@ -367,6 +367,27 @@ hb2_status hb2_integrator_kinetic_of_tags(hb2_integrator* it, const uint32_t* ta
                                           double* kinetic);
 hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT, const double* gamma,
                                        uint32_t ntypes);
+/* hoomd.md.methods.ConstantPressure(filter=All, S, tauS, couple, thermostat=None|Bussi, box_dof, rescale_all,
+ * gamma) (hoomd/md/methods/methods.py:177-580; hoomd/md/TwoStepConstantPressure.cc: integrateStepOne
+ * :213-499, integrateStepTwo :583-690, advanceBarostat :860-1000, updatePropagator :716-858; GPU kernels
+ * hoomd/md/TwoStepConstantPressureGPU.cu). Martyna-Tobias-Klein barostat on the box lengths (box_dof[0..2];
+ * the shear degrees of freedom box_dof[3..5] need a triclinic box and are refused), couplings
+ * couple = 0 none, 1 xy, 2 xz, 3 yz, 4 xyz, optional Langevin piston (gamma), thermostat 0 none / 1 Bussi.
+ * S[6] is the stress set point in the reference's Voigt order xx yy zz yz xz xy. The barostat state is six
+ * fp64 numbers on the host; every step reads the pressure tensor (kinetic tensor + net virial + external
+ * virial) once, rescales the box, and the neighbour list's distance check takes the homogeneous dilation
+ * out (hoomd/md/NeighborList.cc:1236-1260). Replaces the integrator's method. Single GPU. */
+hb2_status hb2_integrator_set_constant_pressure(hb2_integrator* it, const double S[6], double tauS,
+                                                int couple, const int box_dof[6], int rescale_all,
+                                                double gamma, int thermostat, double kT, double tau);
+/* barostat_dof (nu_xx, nu_xy, nu_xz, nu_yy, nu_yz, nu_zz), thermalize_barostat_dof and barostat_energy
+ * (TwoStepConstantPressure::getBarostatDOF / setBarostatDOF / thermalizeBarostatDOF / getBarostatEnergy) */
+hb2_status hb2_integrator_get_barostat_dof(hb2_integrator* it, double nu[6]);
+hb2_status hb2_integrator_set_barostat_dof(hb2_integrator* it, const double nu[6]);
+hb2_status hb2_integrator_thermalize_barostat_dof(hb2_integrator* it, uint64_t timestep);
+hb2_status hb2_integrator_barostat_energy(hb2_integrator* it, double* energy);
+/* the current global box lengths (State.box after a ConstantPressure run: ParticleData::getGlobalBox) */
+hb2_status hb2_system_get_box(hb2_system* s, double L[3]);
 /* System::run(nsteps) (hoomd/System.cc:80-181) restricted to this path: prepRun on the first call
  * (hoomd/md/IntegratorTwoStep.cc:226-281), then per step: step one -> nlist check/rebuild -> forces
  * -> step two (step two of a timestep and step one of the next share one launch for ConstantVolume on

@@ -430,3 +430,28 @@ def test_thermalize_pinned_by_the_reference(golden_dir):
     got = rng.thermal_velocities(np.arange(n, dtype=np.uint32), np.ones(n, dtype=np.float32), 1.5,
                                  int(ref["thermal_seed"]), 0)
     assert np.max(np.abs(got - ref["thermal_vel"])) < 1e-12
+
+
+def test_npt_barostat_replay(golden_dir):
+    """The barostat restatement (oracle/npt_oracle.py) replays the reference's NPH trajectory: from the
+    recorded pressure, kinetic energy and box of every step it reproduces nu and the box lengths of the next
+    (hoomd/md/TwoStepConstantPressure.cc advanceBarostat / updatePropagator / integrateStepOne)."""
+    from oracle import npt_oracle as npt
+    fx = np.load(os.path.join(golden_dir, "npt_2k.npz"))
+    N = len(fx["a_pos"])
+    ndof, dt, tauS, S3 = 3 * N - 3, 0.005, 0.5, [2.0] * 3
+    box, nu6, P, ke = fx["a_box"], fx["a_nu"], fx["a_P"], fx["a_ke"]
+    for k in range(len(P) - 1):
+        nu = nu6[k][[0, 3, 5]]
+        V = float(np.prod(box[k]))
+        half = npt.advance_barostat(nu, [P[k]] * 3, ke[k], V, S3, ndof, tauS, dt)
+        _, exp_r, _ = npt.propagator(half, dt)
+        Lnew = exp_r * box[k]
+        np.testing.assert_allclose(Lnew, box[k + 1], rtol=1e-13)
+        full = npt.advance_barostat(half, [P[k + 1]] * 3, ke[k + 1], float(np.prod(Lnew)), S3, ndof, tauS, dt)
+        np.testing.assert_allclose(full, nu6[k + 1][[0, 3, 5]], rtol=1e-10, atol=1e-14)
+    assert abs(npt.barostat_energy(nu6[-1], ndof, tauS) - float(fx["a_benergy"])) <= 1e-10 * abs(float(fx["a_benergy"]))
+    # the couplings that drop out when a box degree of freedom is frozen
+    assert npt.relevant_couple("xyz", (True, True, False)) == "xy"
+    assert npt.relevant_couple("xy", (True, False, True)) == "none"
+    assert npt.relevant_couple("yz", (False, True, True)) == "yz"
