@@ -3447,6 +3447,24 @@ extern "C" hb2_status hb2_integrator_thermo(hb2_integrator* it, double* kinetic,
     return HB2_OK;
     }
 
+// Kinetic part of the pressure tensor, sum m v_a v_b over every particle (hoomd/md/ComputeThermo.cc:104-123):
+// xx, xy, xz, yy, yz, zz. With the virial sums of hb2_integrator_thermo: P_ab = (K_ab + W_ab) / V.
+extern "C" hb2_status hb2_integrator_kinetic_tensor(hb2_integrator* it, double kt[6])
+    {
+    if (!it || !kt)
+        return HB2_ERR_INVALID;
+    hb2_system* s = it->sys;
+    HB2_CUDA(cudaSetDevice(s->device));
+    NptFactors k0; // dt = 0: the velocities as they are
+    HB2_TRY(launch_step_two_npt(s->vel[s->cur], nullptr, s->N, k0, s->d_partial, s->d_ticket + 2, s->d_sums + 10,
+                                s->stream));
+    if (s->dom.active)
+        HB2_TRY(domain_allreduce_sum_f64(s, s->d_sums + 10, 6));
+    HB2_CUDA(cudaMemcpyAsync(kt, s->d_sums + 10, 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    return HB2_OK;
+    }
+
 extern "C" hb2_status hb2_integrator_last_run_ms(hb2_integrator* it, float* ms)
     {
     if (!it || !ms)

@@ -6,7 +6,7 @@ import numpy as np
 
 class ThermodynamicQuantities:
     _loggables = {"kinetic_energy": "scalar", "potential_energy": "scalar", "kinetic_temperature": "scalar",
-                  "pressure": "scalar", "degrees_of_freedom": "scalar"}
+                  "pressure": "scalar", "degrees_of_freedom": "scalar", "pressure_tensor": "sequence"}
 
     def __init__(self, filter):
         self.filter = filter
@@ -71,4 +71,14 @@ class ThermodynamicQuantities:
 
     @property
     def pressure_tensor(self):
-        raise NotImplementedError("pressure_tensor needs the kinetic tensor; outside this path")
+        """(P_xx, P_xy, P_xz, P_yy, P_yz, P_zz) = (sum m v_a v_b + W_ab) / V (hoomd/md/ComputeThermo.cc:104-123,
+        :236-252), the external virial (LJ tail correction) on the diagonal."""
+        if self._tags() is not None:
+            raise NotImplementedError("pressure tensor of a sub-group is outside this path")
+        import ctypes as C
+        from .._lib import check, lib
+        _, _, w = self._q(need_virial=True)
+        kt = (C.c_double * 6)()
+        check(lib().hb2_integrator_kinetic_tensor(self._sim.operations.integrator._h, kt))
+        V = self._sim.state.box.volume
+        return tuple((kt[q] + w[q]) / V for q in range(6))

@@ -386,6 +386,9 @@ hb2_status hb2_integrator_get_barostat_dof(hb2_integrator* it, double nu[6]);
 hb2_status hb2_integrator_set_barostat_dof(hb2_integrator* it, const double nu[6]);
 hb2_status hb2_integrator_thermalize_barostat_dof(hb2_integrator* it, uint64_t timestep);
 hb2_status hb2_integrator_barostat_energy(hb2_integrator* it, double* energy);
+/* Kinetic part of the pressure tensor, sum m v_a v_b (xx, xy, xz, yy, yz, zz; hoomd/md/ComputeThermo.cc:
+ * 104-123): with hb2_integrator_thermo's virial sums, ThermodynamicQuantities.pressure_tensor. */
+hb2_status hb2_integrator_kinetic_tensor(hb2_integrator* it, double kt[6]);
 /* the current global box lengths (State.box after a ConstantPressure run: ParticleData::getGlobalBox) */
 hb2_status hb2_system_get_box(hb2_system* s, double L[3]);
 /* System::run(nsteps) (hoomd/System.cc:80-181) restricted to this path: prepRun on the first call

@@ -8,7 +8,7 @@ HOOMD-blue 4.8.2 CPU build under baseline/_ref (baseline/build_ref.sh) from the 
        (pins the barostat's noise stream), 30 steps
   c_*  couple 'xy', box_dof x and y only, LJ with tail_correction (external virial), barostat momenta drawn
        by thermalize_barostat_dof after run(0), 30 steps
-Per case: box lengths, barostat_dof, pressure and kinetic energy after every step (index 0: after run(0)),
+Per case: box lengths, barostat_dof, pressure, pressure tensor (xx, xy, xz, yy, yz, zz) and kinetic energy after every step (index 0: after run(0)),
 final positions / velocities / images, barostat_energy at the end.
 """
 import os
@@ -56,7 +56,7 @@ def run_case(fx, c):
     sim.run(0)
     if c["thermalize"]:
         npt.thermalize_barostat_dof()
-    box, nu, P, ke, builds = [], [], [], [], 0
+    box, nu, P, ke, builds, Pt = [], [], [], [], 0, []
 
     def rec():
         b = sim.state.box
@@ -64,6 +64,7 @@ def run_case(fx, c):
         nu.append(list(npt.barostat_dof))
         P.append(tq.pressure)
         ke.append(tq.kinetic_energy)
+        Pt.append(list(tq.pressure_tensor))
 
     rec()
     for _ in range(c["steps"]):
@@ -71,7 +72,7 @@ def run_case(fx, c):
         builds += cell.num_builds
         rec()
     s = sim.state.get_snapshot()
-    return dict(box=np.array(box), nu=np.array(nu), P=np.array(P), ke=np.array(ke),
+    return dict(box=np.array(box), nu=np.array(nu), P=np.array(P), ke=np.array(ke), Pt=np.array(Pt),
                 pos=np.array(s.particles.position), vel=np.array(s.particles.velocity),
                 image=np.array(s.particles.image, dtype=np.int32), benergy=np.array(npt.barostat_energy),
                 builds=np.array(builds), pe=np.array(tq.potential_energy))

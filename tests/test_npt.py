@@ -73,7 +73,7 @@ def test_constant_pressure_vs_reference(golden_dir, name):
     sim.run(0)
     if c["thermalize"]:
         npt.thermalize_barostat_dof()
-    box, nu, P, ke, builds = [], [], [], [], 0
+    box, nu, P, ke, builds, Pt = [], [], [], [], 0, []
 
     def rec():
         b = sim.state.box
@@ -81,6 +81,7 @@ def test_constant_pressure_vs_reference(golden_dir, name):
         nu.append(list(npt.barostat_dof))
         P.append(tq.pressure)
         ke.append(tq.kinetic_energy)
+        Pt.append(list(tq.pressure_tensor))
 
     rec()
     for _ in range(c["steps"]):
@@ -97,6 +98,9 @@ def test_constant_pressure_vs_reference(golden_dir, name):
     assert np.max(np.abs(nu - r["nu"])) <= 2e-4 * scale
     np.testing.assert_allclose(P, r["P"], rtol=0, atol=2e-4 * np.max(np.abs(r["P"])))
     np.testing.assert_allclose(ke, r["ke"], rtol=5e-5)
+    # ThermodynamicQuantities.pressure_tensor (kinetic tensor + virial sums; off-diagonals are small numbers
+    # made of large cancelling terms: tolerance on the scale of the diagonal)
+    np.testing.assert_allclose(np.array(Pt), ref[f"{name}_Pt"], rtol=0, atol=2e-4 * np.max(np.abs(r["P"])))
     assert abs(npt.barostat_energy - float(r["benergy"])) <= 5e-4 * abs(float(r["benergy"]))
     assert abs(builds - int(r["builds"])) <= 1
     s = sim.state.get_snapshot()
