@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("HB2_LIB", "libhoomd_b200.so"))
 EVAL = {"lj": 0, "dpd": 1, "dpd_conservative": 2, "example_pair": 3, "gauss": 4, "yukawa": 5,
         "lj1208": 6, "lj0804": 7, "force_shifted_lj": 8, "mie": 9, "morse": 10,
         "buckingham": 11, "expanded_lj": 12, "expanded_gaussian": 13, "lj_gauss": 14, "twf": 15, "dpdlj": 16,
-        "table": 17}
+        "table": 17, "expanded_mie": 18, "opp": 19, "fourier": 20}
 SHIFT = {"none": 0, "shift": 1, "xplor": 2}
 PARAM_FLOATS = 8  # HB2_PARAM_FLOATS (include/hoomd_b200.h)
 

@@ -1334,6 +1334,9 @@ static const EvalInfo* eval_info(hb2_evaluator ev)
         {EvaluatorPairTWF::n_user_params, pack_as<EvaluatorPairTWF>},
         {EvaluatorPairDPDThermoLJ::n_user_params, pack_as<EvaluatorPairDPDThermoLJ>},
         {0, nullptr}, // Table: variable-size parameters, hb2_pair_set_table
+        {EvaluatorPairExpandedMie::n_user_params, pack_as<EvaluatorPairExpandedMie>},
+        {EvaluatorPairOPP::n_user_params, pack_as<EvaluatorPairOPP>},
+        {EvaluatorPairFourier::n_user_params, pack_as<EvaluatorPairFourier>},
     };
     if ((unsigned)ev >= sizeof(table) / sizeof(table[0]))
         return nullptr;
@@ -1411,6 +1414,12 @@ hb2_status launch_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const PairA
         return pair_forces_dpdlj(mode, a, box, stream);
     case HB2_EVAL_TABLE:
         return pair_forces_table(mode, a, box, stream);
+    case HB2_EVAL_EXPANDED_MIE:
+        return pair_forces_expanded_mie(mode, a, box, stream);
+    case HB2_EVAL_OPP:
+        return pair_forces_opp(mode, a, box, stream);
+    case HB2_EVAL_FOURIER:
+        return pair_forces_fourier(mode, a, box, stream);
         }
     set_error("pair forces: unknown evaluator");
     return HB2_ERR_INVALID;

@@ -595,7 +595,6 @@ class EvaluatorPairTWF
     protected:
     Scalar rsq, rcutsq, sigma, alpha, prefactor;
     };
-#undef HB2_EVAL_COMMON
 // ---------------------------------------------------------------------------------------------
 // Tabulated potential (hoomd/md/EvaluatorPairTable.h:42-205): U(r) and F(r) = -dU/dr sampled at
 // r_min + i (r_cut - r_min) / width, linear interpolation, nothing outside [r_min, r_cut). The
@@ -656,4 +655,168 @@ class EvaluatorPairTable
     const Scalar* table;
     };
 
+// ---------------------------------------------------------------------------------------------
+// Evaluators with five and six packed parameters (the parameter stride is HB2_PARAM_FLOATS = 8).
+// ---------------------------------------------------------------------------------------------
+
+// Mie n-m in r - delta: V = A (sigma/(r-delta))^n - B (sigma/(r-delta))^m with the Mie prefactor
+// (hoomd/md/EvaluatorPairExpandedMie.h:60-75 parameters, :127-160 evaluation)
+class EvaluatorPairExpandedMie
+    {
+    public:
+    struct param_type
+        {
+        Scalar rep, att, n, m, delta;
+        };
+    HB2_EVAL_COMMON(5) // {epsilon, sigma, n, m, delta}
+    static void pack(const double* user, param_type& p)
+        {
+        const double eps = user[0], sigma = user[1], n = user[2], m = user[3];
+        const double pref = (n / (n - m)) * pow(n / m, m / (n - m));
+        p.rep = (Scalar)(pref * eps * pow(sigma, n));
+        p.att = (Scalar)(pref * eps * pow(sigma, m));
+        p.n = (Scalar)n;
+        p.m = (Scalar)m;
+        p.delta = (Scalar)user[4];
+        }
+    HB2_DEVICE EvaluatorPairExpandedMie(Scalar _rsq, Scalar _rcutsq, const param_type& q)
+        : rsq(_rsq), rcutsq(_rcutsq), p(q)
+        {
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (!(rsq < rcutsq) || p.rep == 0)
+            return false;
+        const Scalar rinv = rsqrt_refined(rsq);
+        const Scalar s = Scalar(1.0) / rinv - p.delta; // r - delta
+        const Scalar sn = p.rep * powf(s, -p.n), sm = p.att * powf(s, -p.m);
+        pair_eng = sn - sm;
+        force_divr = rinv * (p.n * sn - p.m * sm) / s;
+        if (energy_shift)
+            {
+            const Scalar sc = sqrtf(rcutsq) - p.delta;
+            pair_eng -= p.rep * powf(sc, -p.n) - p.att * powf(sc, -p.m);
+            }
+        return true;
+        }
+    static const char* getName()
+        {
+        return "expanded_mie";
+        }
+
+    protected:
+    Scalar rsq, rcutsq;
+    param_type p;
+    };
+
+// Oscillating pair potential V = C1 r^-eta1 + C2 r^-eta2 cos(k r - phi)
+// (hoomd/md/EvaluatorPairOPP.h:46-82 parameters, :128-163 evaluation)
+class EvaluatorPairOPP
+    {
+    public:
+    struct param_type
+        {
+        Scalar C1, C2, eta1, eta2, k, phi;
+        };
+    HB2_EVAL_COMMON(6) // {C1, C2, eta1, eta2, k, phi}
+    static void pack(const double* user, param_type& p)
+        {
+        p.C1 = (Scalar)user[0];
+        p.C2 = (Scalar)user[1];
+        p.eta1 = (Scalar)user[2];
+        p.eta2 = (Scalar)user[3];
+        p.k = (Scalar)user[4];
+        p.phi = (Scalar)user[5];
+        }
+    HB2_DEVICE EvaluatorPairOPP(Scalar _rsq, Scalar _rcutsq, const param_type& q) : rsq(_rsq), rcutsq(_rcutsq), p(q) { }
+    HB2_DEVICE static void terms(const param_type& p, const Scalar r, Scalar& t1, Scalar& env, Scalar& sn, Scalar& cs)
+        {
+        t1 = p.C1 * powf(r, -p.eta1);  // C1 r^-eta1
+        env = p.C2 * powf(r, -p.eta2); // C2 r^-eta2, the envelope of the oscillation
+        sincosf(p.k * r - p.phi, &sn, &cs);
+        }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (!(rsq < rcutsq))
+            return false;
+        const Scalar r = sqrtf(rsq), rinv = Scalar(1.0) / r;
+        Scalar t1, env, sn, cs;
+        terms(p, r, t1, env, sn, cs);
+        pair_eng = t1 + env * cs;
+        // -dV/dr = eta1 t1 / r + env (eta2 cos / r + k sin)
+        force_divr = rinv * (rinv * (p.eta1 * t1 + p.eta2 * env * cs) + p.k * env * sn);
+        if (energy_shift)
+            {
+            Scalar c1, ce, s2, c2;
+            terms(p, sqrtf(rcutsq), c1, ce, s2, c2);
+            pair_eng -= c1 + ce * c2;
+            }
+        return true;
+        }
+    static const char* getName()
+        {
+        return "opp";
+        }
+
+    protected:
+    Scalar rsq, rcutsq;
+    param_type p;
+    };
+
+// Fourier pair potential: V = r^-12 + r^-2 sum_{n=1..4} [a_n cos(n x) + b_n sin(n x)], x = pi r / r_cut, with
+// a_1 and b_1 fixed by a_2..4, b_2..4 so that V and its slope vanish at the cut-off
+// (hoomd/md/EvaluatorPairFourier.h:55-99 parameters, :135-180 evaluation). No energy shift.
+class EvaluatorPairFourier
+    {
+    public:
+    struct param_type
+        {
+        Scalar a[3], b[3];
+        };
+    HB2_EVAL_COMMON(6) // {a2, a3, a4, b2, b3, b4}
+    static void pack(const double* user, param_type& p)
+        {
+        for (int i = 0; i < 3; i++)
+            {
+            p.a[i] = (Scalar)user[i];
+            p.b[i] = (Scalar)user[3 + i];
+            }
+        }
+    HB2_DEVICE EvaluatorPairFourier(Scalar _rsq, Scalar _rcutsq, const param_type& q) : rsq(_rsq), rcutsq(_rcutsq), p(q) { }
+    HB2_DEVICE bool evalForceAndEnergy(Scalar& force_divr, Scalar& pair_eng, bool energy_shift)
+        {
+        if (!(rsq < rcutsq))
+            return false;
+        const Scalar r = sqrtf(rsq), rinv = Scalar(1.0) / r, r2inv = rinv * rinv;
+        const Scalar w = Scalar(3.14159265358979323846) / sqrtf(rcutsq); // dx/dr
+        const Scalar x = r * w;
+        // first harmonic: a_1 = a_2 - a_3 + a_4, b_1 = 2 b_2 - 3 b_3 + 4 b_4
+        const Scalar an[4] = {p.a[0] - p.a[1] + p.a[2], p.a[0], p.a[1], p.a[2]};
+        const Scalar bn[4] = {Scalar(2.0) * p.b[0] - Scalar(3.0) * p.b[1] + Scalar(4.0) * p.b[2], p.b[0], p.b[1], p.b[2]};
+        Scalar series = 0, dseries = 0; // S(x) and -dS/dx
+#pragma unroll
+        for (int n = 1; n <= 4; n++)
+            {
+            Scalar sn, cs;
+            sincosf((Scalar)n * x, &sn, &cs);
+            series += an[n - 1] * cs + bn[n - 1] * sn;
+            dseries += (Scalar)n * (an[n - 1] * sn - bn[n - 1] * cs);
+            }
+        const Scalar r6inv = r2inv * r2inv * r2inv, r12inv = r6inv * r6inv;
+        pair_eng = r12inv + r2inv * series;
+        // -dV/dr / r = 12 r^-14 + 2 S r^-4 + w (-dS/dx) r^-3
+        force_divr = r2inv * (Scalar(12.0) * r12inv + Scalar(2.0) * r2inv * series + w * rinv * dseries);
+        return true;
+        }
+    static const char* getName()
+        {
+        return "fourier";
+        }
+
+    protected:
+    Scalar rsq, rcutsq;
+    param_type p;
+    };
+
+#undef HB2_EVAL_COMMON
     } // namespace hb2

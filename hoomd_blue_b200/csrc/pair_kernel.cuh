@@ -718,4 +718,7 @@ hb2_status pair_forces_lj_gauss(hb2_shift_mode, const PairArgs&, const hb2_box&,
 hb2_status pair_forces_twf(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_dpdlj(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
 hb2_status pair_forces_table(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_expanded_mie(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_opp(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
+hb2_status pair_forces_fourier(hb2_shift_mode, const PairArgs&, const hb2_box&, cudaStream_t);
     } // namespace hb2

@@ -320,6 +320,36 @@ class DPDLJ(Pair):
         check(_lib.lib().hb2_pair_set_kT(self._h, self.kT))
 
 
+class ExpandedMie(Pair):
+    """hoomd.md.pair.ExpandedMie: Mie n-m potential in r - delta; params {epsilon, sigma, n, m, delta}
+    (hoomd/md/pair/pair.py:1222-1300)."""
+    _evaluator = "expanded_mie"
+    _param_keys = ("epsilon", "sigma", "n", "m", "delta")
+
+
+class OPP(Pair):
+    """hoomd.md.pair.OPP: V = C1 r^-eta1 + C2 r^-eta2 cos(k r - phi); params {C1, C2, eta1, eta2, k, phi}
+    (hoomd/md/pair/pair.py:1690-1760)."""
+    _evaluator = "opp"
+    _param_keys = ("C1", "C2", "eta1", "eta2", "k", "phi")
+
+
+class Fourier(Pair):
+    """hoomd.md.pair.Fourier: V = r^-12 + r^-2 sum_n [a_n cos(n pi r / r_cut) + b_n sin(n pi r / r_cut)];
+    params dict(a=[a2, a3, a4], b=[b2, b3, b4]); modes 'none' and 'xplor' (hoomd/md/pair/pair.py:1614-1680)."""
+    _accepted_modes = ("none", "xplor")
+    _evaluator = "fourier"
+    _param_keys = ("a2", "a3", "a4", "b2", "b3", "b4")
+
+    def _validate_params(self, v):
+        if "a" not in v or "b" not in v:
+            raise ValueError("missing parameters: a=[a2, a3, a4], b=[b2, b3, b4]")
+        a, b = [float(x) for x in v["a"]], [float(x) for x in v["b"]]
+        if len(a) != 3 or len(b) != 3:
+            raise ValueError("a and b have three elements each")
+        return dict(a=tuple(a), b=tuple(b), a2=a[0], a3=a[1], a4=a[2], b2=b[0], b3=b[1], b4=b[2])
+
+
 class Table(Pair):
     """hoomd.md.pair.Table(nlist, default_r_cut=None): tabulated potential, params {r_min, U, F} with
     U and F = -dU/dr sampled at r_min + i (r_cut - r_min) / len(U), linearly interpolated

@@ -87,7 +87,10 @@ typedef enum
     HB2_EVAL_LJ_GAUSS = 14,        /* hoomd/md/EvaluatorPairLJGauss.h; {epsilon, sigma, r0} */
     HB2_EVAL_TWF = 15,             /* hoomd/md/EvaluatorPairTWF.h; {epsilon, sigma, alpha} */
     HB2_EVAL_DPDLJ = 16,           /* hoomd/md/EvaluatorPairDPDThermoLJ.h; {epsilon, sigma, gamma} (+kT, seed) */
-    HB2_EVAL_TABLE = 17            /* hoomd/md/EvaluatorPairTable.h; tabulated U(r), F(r): hb2_pair_set_table */
+    HB2_EVAL_TABLE = 17,           /* hoomd/md/EvaluatorPairTable.h; tabulated U(r), F(r): hb2_pair_set_table */
+    HB2_EVAL_EXPANDED_MIE = 18,    /* hoomd/md/EvaluatorPairExpandedMie.h; {epsilon, sigma, n, m, delta} */
+    HB2_EVAL_OPP = 19,             /* hoomd/md/EvaluatorPairOPP.h; {C1, C2, eta1, eta2, k, phi} */
+    HB2_EVAL_FOURIER = 20          /* hoomd/md/EvaluatorPairFourier.h; {a2, a3, a4, b2, b3, b4}; modes none / xplor */
     } hb2_evaluator;
 /* Stride, in floats, of one type pair's packed evaluator parameters (param_type is at most 32 bytes;
  * evaluators with variable-size data, like Table, keep a device pointer in it) and the most user

@@ -123,6 +123,9 @@ def test_forces_and_energies_json(hoomd, golden_dir):
                                  ("ExpandedGaussian", "ExpandedGaussian", ("epsilon", "sigma", "delta")),
                                  ("LJGauss", "LJGauss", ("epsilon", "sigma", "r0")),
                                  ("TWF", "TWF", ("epsilon", "sigma", "alpha")),
+                                 ("ExpandedMie", "ExpandedMie", ("epsilon", "sigma", "n", "m", "delta")),
+                                 ("OPP", "OPP", ("C1", "C2", "eta1", "eta2", "k", "phi")),
+                                 ("Fourier", "Fourier", ("a", "b")),
                                  ("Table", "Table", ("r_min", "U", "F"))):
         tab = fe[name]
         for p, F, E in zip(tab["params"], tab["forces"], tab["energies"]):
@@ -683,7 +686,9 @@ def test_snapshot_roundtrip_pageable_and_pinned(hoomd):
     ("Morse", dict(D0=1.2, alpha=3.5, r0=1.1)), ("LJ", dict(epsilon=1.0, sigma=1.0)),
     ("Buckingham", dict(A=400.0, rho=0.25, C=1.0)), ("ExpandedLJ", dict(epsilon=1.0, sigma=0.8, delta=0.2)),
     ("ExpandedGaussian", dict(epsilon=1.5, sigma=0.6, delta=0.3)),
-    ("LJGauss", dict(epsilon=1.0, sigma=0.2, r0=1.5)), ("TWF", dict(epsilon=1.0, sigma=0.45, alpha=20.0))])
+    ("LJGauss", dict(epsilon=1.0, sigma=0.2, r0=1.5)), ("TWF", dict(epsilon=1.0, sigma=0.45, alpha=20.0)),
+    ("ExpandedMie", dict(epsilon=1.0, sigma=0.8, n=13, m=7, delta=0.15)),
+    ("OPP", dict(C1=1.0, C2=1.0, eta1=15.0, eta2=3.0, k=3.0, phi=0.5))])
 def test_evaluator_family_consistency(hoomd, cls_name, params):
     """Every evaluator through the kernel template on a liquid: F = -dE/dr (central differences of the
     total energy along the force of a few particles), Newton's third law (sum of forces = 0), and
