@@ -84,10 +84,47 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows = []
+        self.nvml_rows = None
         self.proc = None
         self.index = index
 
+    def _nvml_loop(self):
+        import pynvml as nv
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.nvml_rows.append((sm, [n for n, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
     def start(self):
+        # NVML in-process, one sample every 5 ms (nvidia-smi -lms needs ~0.3 s to start, longer than the timed
+        # region at C2); the nvidia-smi loop below is the fallback where pynvml is missing
+        self.nvml_rows = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self._h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self._max = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self.nvml_rows = []
+            self._stop = threading.Event()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            self.proc = None
+            return
+        except Exception:
+            self.nvml_rows = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -105,6 +142,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml_rows is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            sm = [r[0] for r in self.nvml_rows]
+            reasons = sorted({n for r in self.nvml_rows for n in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self._max), "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 5 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()

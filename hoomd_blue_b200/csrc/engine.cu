@@ -2880,6 +2880,13 @@ static hb2_status npt_thermo(hb2_integrator* it, hb2_pair* pf, bool kinetic_from
         }
     HB2_TRY(launch_reduce_energy(pf->d_force, pf->d_virial, pf->cap_N, s->N, s->d_partial, s->d_ticket + 1,
                                  s->d_sums + 1, st));
+    if (s->dom.active)
+        {
+        // every rank holds the same barostat: the sums over the owned particles of all domains, in one
+        // all-reduce each (identical bits on every rank, so the boxes never drift apart)
+        HB2_TRY(domain_allreduce_sum_f64(s, s->d_sums + 1, 7));
+        HB2_TRY(domain_allreduce_sum_f64(s, s->d_sums + 10, 6));
+        }
     HB2_CUDA(cudaMemcpyAsync(n.h_thermo, s->d_sums + 1, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
     HB2_CUDA(cudaMemcpyAsync(n.h_thermo + 7, s->d_sums + 10, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
     HB2_CUDA(cudaStreamSynchronize(st));
@@ -2918,11 +2925,6 @@ extern "C" hb2_status hb2_integrator_set_constant_pressure(hb2_integrator* it, c
         {
         set_error("ConstantPressure: the shear degrees of freedom (xy, xz, yz) need a triclinic box, which is "
                   "outside this path's scope");
-        return HB2_ERR_INVALID;
-        }
-    if (it->sys->dom.active)
-        {
-        set_error("ConstantPressure under domain decomposition is not built on this path");
         return HB2_ERR_INVALID;
         }
     HB2_CUDA(cudaSetDevice(it->sys->device));
@@ -3098,11 +3100,6 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         }
     if (npt.on)
         {
-        if (s->dom.active)
-            {
-            set_error("ConstantPressure under domain decomposition is not built on this path");
-            return HB2_ERR_INVALID;
-            }
         if (!pf->virial_valid)
             {
             // the net force of this timestep exists but without its virial: same list, one more pass
@@ -3114,6 +3111,12 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         for (auto* p : it->forces)
             if (p->tail_correction && !npt.tail_valid)
                 {
+                if (s->dom.active)
+                    {
+                    set_error("ConstantPressure with an LJ tail correction under domain decomposition is not built "
+                              "(the correction needs the global particle counts per type)");
+                    return HB2_ERR_INVALID;
+                    }
                 double te, tw;
                 tail_correction(p, te, tw, nullptr, &npt.n_per_type);
                 npt.tail_valid = true;

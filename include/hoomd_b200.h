@@ -379,7 +379,8 @@ hb2_status hb2_integrator_set_langevin(hb2_integrator* it, double kT, const doub
  * S[6] is the stress set point in the reference's Voigt order xx yy zz yz xz xy. The barostat state is six
  * fp64 numbers on the host; every step reads the pressure tensor (kinetic tensor + net virial + external
  * virial) once, rescales the box, and the neighbour list's distance check takes the homogeneous dilation
- * out (hoomd/md/NeighborList.cc:1236-1260). Replaces the integrator's method. Single GPU. */
+ * out (hoomd/md/NeighborList.cc:1236-1260). Replaces the integrator's method. Under a domain decomposition
+ * the sums are all-reduced and every rank keeps the same barostat (collective call, like every run). */
 hb2_status hb2_integrator_set_constant_pressure(hb2_integrator* it, const double S[6], double tauS,
                                                 int couple, const int box_dof[6], int rescale_all,
                                                 double gamma, int thermostat, double kT, double tau);

@@ -190,7 +190,32 @@ def main():
     e_1 = os_.operations.integrator._thermo()
     assert abs(e_d[0] - e_1[0]) <= 5e-4 * abs(e_1[0]), (e_d[0], e_1[0])
     assert abs((e_d[0] + e_d[1]) - (e_1[0] + e_1[1])) <= 5e-4 * abs(e_1[0])
+    # (8) ConstantPressure: every rank carries the same barostat (all-reduced pressure tensor), the sub-domains
+    # rescale with the box, the lambda-scaled distance check votes the rebuilds
+    def npt_run(device):
+        sim = hoomd.Simulation(device=device, seed=9)
+        sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays(list(fx["L"]) + [0, 0, 0], fx["pos"], fx["vel"],
+                                                                  None, ("A",), fx["image"]))
+        cell = hoomd.md.nlist.Cell(buffer=0.4)
+        f = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+        f.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
+        npt = hoomd.md.methods.ConstantPressure(filter=hoomd.filter.All(), S=[2.0, 3.0, 4.0, 0, 0, 0], tauS=0.5,
+                                                couple="none", gamma=0.3,
+                                                thermostat=hoomd.md.methods.thermostats.Bussi(kT=1.5))
+        sim.operations.integrator = hoomd.md.Integrator(dt=0.005, methods=[npt], forces=[f])
+        sim.run(60)
+        return (np.array(sim.state.box.L), np.array(npt.barostat_dof), sim.operations.integrator._thermo()[0],
+                cell.num_builds)
+
+    Ld, nud, ked, bd_ = npt_run(hoomd.device.GPU())
+    L1, nu1, ke1, b1_ = npt_run(hoomd.device.GPU(gpu_id=local, communicator=one))
+    assert np.max(np.abs(Ld / L1 - 1.0)) <= 1e-7, (Ld, L1)
+    assert np.max(np.abs(Ld - np.array(fx["L"], dtype=np.float64))) > 0.05  # the box did move
+    assert np.max(np.abs(nud - nu1)) <= 1e-5 * np.max(np.abs(nu1)), (nud, nu1)
+    assert abs(ked - ke1) <= 2e-4 * abs(ke1), (ked, ke1)
+    assert abs(int(bd_) - int(b1_)) <= 1
     if rank == 0:
+        msg += f" npt_box_rel={np.max(np.abs(Ld / L1 - 1.0)):.1e} npt_nu_rel={np.max(np.abs(nud - nu1)) / np.max(np.abs(nu1)):.1e}"
         print(msg + f" bussi_KE_rel={abs(kb - kr) / abs(kr):.1e} dpd_force_err={derr:.1e}"
               f" langevin_KE_rel={abs(kl - km) / abs(km):.1e}"
               f" polymer_pairs={len(pp)} polymer_KE_rel={abs(e_d[0] - e_1[0]) / abs(e_1[0]):.1e}", flush=True)
