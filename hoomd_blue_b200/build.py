@@ -17,7 +17,7 @@ _VAR = os.environ.get("HB2_VARIANT", "")
 OBJ = os.path.join(HERE, "build" + ("_" + _VAR if _VAR else ""))
 LIB = os.path.join(HERE, "libhoomd_b200" + ("_" + _VAR if _VAR else "") + ".so")
 SOURCES = ["engine.cu", "capi.cu", "binning.cu", "nlist.cu", "nlist_tile.cu", "integrate.cu", "pair_lj.cu",
-           "pair_dpd.cu", "pair_example.cu", "pair_more_a.cu", "pair_more_b.cu", "pair_more_c.cu", "pair_more_d.cu", "comm.cu", "bond.cu"]
+           "pair_dpd.cu", "pair_example.cu", "pair_more_a.cu", "pair_more_b.cu", "pair_more_c.cu", "pair_more_d.cu", "pair_more_e.cu", "pair_more_f.cu", "pair_more_g.cu", "comm.cu", "bond.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
