@@ -1581,7 +1581,11 @@ hb2_status hb2_pair::launch(uint64_t timestep, bool want_energy, const uint32_t*
     a.timestep = timestep;
     a.dt = (float)dt;
     a.kT = (float)kT;
-    a.face_margin = (float)(nl->rcut_max_max + 2.0 * nl->buffer) * 1.0001f;
+    // A pair across a periodic face with a separation below r_cut needs its home particle within r_cut of that
+    // face. Farther away, a listed neighbour may still sit in another image (the list reaches r_cut + buffer and
+    // both particles have moved since), but then its true separation and the plain difference (>= L - r_list
+    // >= r_list) are both beyond the cut-off: no contribution either way, so the plain loop serves.
+    a.face_margin = (float)nl->rcut_max_max * 1.0001f;
     a.tpp = tpp;
     a.energy = want_energy || energy_every_step || tpp != 8;
     a.skip_flag = skip_flag;

@@ -123,7 +123,7 @@ struct PairArgs
     const uint64_t* d_timestep; // device timestep (graph-replay safe) or null -> timestep
     uint64_t timestep;
     float dt, kT;
-    float face_margin; // r_list_max + buffer (distance from a face beyond which no image shift occurs)
+    float face_margin; // >= r_cut_max: farther than this from every face, no pair inside the cut-off crosses a face
     uint32_t tpp;
     bool energy = true; // false: skip the per-particle potential energy (force.w = 0)
     const uint32_t* skip_flag = nullptr; // device word; non-zero => the launch does nothing

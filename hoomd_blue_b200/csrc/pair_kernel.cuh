@@ -107,7 +107,7 @@ template<class Ev> struct PairKArgs
     const uint64_t* d_timestep;
     uint64_t timestep;
     float dt, kT;
-    float face_margin; // r_list_max + buffer: farther than this from every face => no image shifts
+    float face_margin; // >= r_cut_max: farther than this from every face => no pair inside the cut-off crosses a face
     uint32_t stage;    // chunks of a row staged per pass (<= PAIR_STAGE_MAX)
     bool energy;       // accumulate the per-particle potential energy
     const uint32_t* skip_flag; // non-zero word => return at once (speculative launch, engine.cu)

@@ -146,8 +146,9 @@ hb2_status hb2_gpu_compute_nlist_binned(float* d_pos4, uint32_t N, uint32_t N_to
  * parameters (hb2_pack_params), d_rcutsq / d_ronsq: ntypes^2 floats, all indexed tj*ntypes+ti. d_force4 =
  * (fx,fy,fz,pe) per particle, d_virial = 6 x virial_pitch floats (xx,xy,xz,yy,yz,zz) or NULL
  * (pressure flag off, hoomd/md/PotentialPair.h:739-752). DPD-only inputs may be NULL otherwise.
- * face_margin: a particle farther than this from every box face is guaranteed to have all listed
- * neighbours in its own periodic image (pass r_cut_max + 2 * buffer; <= 0 disables the shortcut). */
+ * face_margin: a particle farther than this from every box face takes the loop without image shifts: no pair
+ * closer than r_cut can cross a face from there, and a listed neighbour in another image lies beyond the cut-off
+ * both truly and by the plain difference (pass r_cut_max or more; <= 0 disables the shortcut). */
 hb2_status hb2_gpu_compute_pair_forces(hb2_evaluator ev, hb2_shift_mode mode, const float* d_pos4,
                                        const float* d_vel4, const uint32_t* d_tag, uint32_t N,
                                        const hb2_box* box, const uint32_t* d_n_neigh,
