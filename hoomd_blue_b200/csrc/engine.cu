@@ -1943,6 +1943,25 @@ static void tail_correction(hb2_pair* p, double& e, double& w, const std::vector
             memcpy(&t, &q.w, 4);
             counted[t]++;
             }
+        if (s->dom.active)
+            {
+            // the densities are the global ones: sum the counts over the domains (collective, like every
+            // getter of a decomposed system; counts travel as doubles, exact below 2^53)
+            std::vector<double> c(nt);
+            for (uint32_t q = 0; q < nt; q++)
+                c[q] = (double)counted[q];
+            double* d_c = nullptr;
+            if (dev_alloc(&d_c, nt) == HB2_OK)
+                {
+                cudaMemcpyAsync(d_c, c.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, s->stream);
+                domain_allreduce_sum_f64(s, d_c, nt);
+                cudaMemcpyAsync(c.data(), d_c, sizeof(double) * nt, cudaMemcpyDeviceToHost, s->stream);
+                cudaStreamSynchronize(s->stream);
+                dev_free(d_c);
+                for (uint32_t q = 0; q < nt; q++)
+                    counted[q] = (uint32_t)c[q];
+                }
+            }
         if (n_per_type_out)
             *n_per_type_out = counted;
         }
@@ -1996,11 +2015,7 @@ extern "C" hb2_status hb2_pair_set_tail_correction(hb2_pair* p, int on)
         set_error("tail_correction is only available for the LJ evaluator");
         return HB2_ERR_INVALID;
         }
-    if (on && p->sys->dom.active)
-        {
-        set_error("tail_correction is not available with a domain decomposition on this path");
-        return HB2_ERR_INVALID;
-        }
+    // (with a domain decomposition the densities come from the all-reduced type counts: tail_correction())
     p->tail_correction = on != 0;
     return HB2_OK;
     }
@@ -3115,12 +3130,6 @@ extern "C" hb2_status hb2_integrator_run(hb2_integrator* it, uint64_t nsteps)
         for (auto* p : it->forces)
             if (p->tail_correction && !npt.tail_valid)
                 {
-                if (s->dom.active)
-                    {
-                    set_error("ConstantPressure with an LJ tail correction under domain decomposition is not built "
-                              "(the correction needs the global particle counts per type)");
-                    return HB2_ERR_INVALID;
-                    }
                 double te, tw;
                 tail_correction(p, te, tw, nullptr, &npt.n_per_type);
                 npt.tail_valid = true;

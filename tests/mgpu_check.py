@@ -197,7 +197,7 @@ def main():
         sim.create_state_from_snapshot(hoomd.Snapshot.from_arrays(list(fx["L"]) + [0, 0, 0], fx["pos"], fx["vel"],
                                                                   None, ("A",), fx["image"]))
         cell = hoomd.md.nlist.Cell(buffer=0.4)
-        f = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5)
+        f = hoomd.md.pair.LJ(nlist=cell, default_r_cut=2.5, tail_correction=True)  # global densities on every rank
         f.params[("A", "A")] = dict(epsilon=1.0, sigma=1.0)
         npt = hoomd.md.methods.ConstantPressure(filter=hoomd.filter.All(), S=[2.0, 3.0, 4.0, 0, 0, 0], tauS=0.5,
                                                 couple="none", gamma=0.3,
