@@ -144,6 +144,9 @@ def _declare(L):
     L.hb2_integrator_thermalize_barostat_dof.argtypes = [_vp, C.c_uint64]
     L.hb2_integrator_barostat_energy.argtypes = [_vp, _f64p]
     L.hb2_system_get_box.argtypes = [_vp, _f64p]
+    L.hb2_domain_ipc_handle.argtypes = [_vp, C.c_void_p]
+    L.hb2_domain_set_peers.argtypes = [_vp, C.c_void_p, C.c_uint32]
+    L.hb2_domain_p2p_active.argtypes = [_vp]
     L.hb2_integrator_kinetic_tensor.argtypes = [_vp, _f64p]
     L.hb2_integrator_set_filter_tags.argtypes = [_vp, C.POINTER(C.c_uint32), C.c_uint64]
     L.hb2_integrator_kinetic_of_tags.argtypes = [_vp, C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_double)]

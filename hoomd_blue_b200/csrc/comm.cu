@@ -268,6 +268,51 @@ __global__ void __launch_bounds__(CB)
         slot[k] = inv[N + k];
     }
 
+// One warp. op 0: max of one uint32 at ptr; op 1: sum of one double at ptr (rank order).
+// Replaces, for the two one-word reductions of every step (the rebuild vote, hoomd/md/NeighborList.cc:1271-1285,
+// and the thermostat's kinetic energy), an ncclAllReduce launch each: the exchange is n stores over NVLink and a
+// spin on local HBM.
+__global__ void __launch_bounds__(32)
+    p2p_allreduce_kernel(P2PBox* const* __restrict__ peers, P2PBox* __restrict__ mine, int rank, int n,
+                         unsigned long long epoch, int op, void* ptr)
+    {
+    const int lane = threadIdx.x;
+    const int par = (int)(epoch & 1ull);
+    const double v = op == 0 ? (double)*reinterpret_cast<const uint32_t*>(ptr) : *reinterpret_cast<const double*>(ptr);
+    double got = 0.0;
+    if (lane < n)
+        {
+        P2PBox* dst = peers[lane] + par * P2P_MAX_RANKS + rank;
+        *reinterpret_cast<volatile double*>(&dst->value) = v;
+        __threadfence_system(); // the value is visible system-wide before the epoch that announces it
+        *reinterpret_cast<volatile unsigned long long*>(&dst->epoch) = epoch;
+        const volatile P2PBox* src = mine + par * P2P_MAX_RANKS + lane;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (src->epoch != epoch)
+            if (clock64() - t0 > 8000000000ll) // ~4 s: a peer died; poison the result instead of hanging
+                {
+                ok = false;
+                break;
+                }
+        __threadfence_system();
+        got = ok ? src->value : __longlong_as_double(0x7ff8000000000000ll);
+        }
+    double acc = 0.0;
+    for (int r = 0; r < n; r++)
+        {
+        const double x = __shfl_sync(0xffffffffu, got, r);
+        acc = op == 0 ? fmax(acc, x) : acc + x;
+        }
+    if (lane == 0)
+        {
+        if (op == 0)
+            *reinterpret_cast<uint32_t*>(ptr) = (uint32_t)acc;
+        else
+            *reinterpret_cast<double*>(ptr) = acc;
+        }
+    }
+
 static inline uint32_t nblk(uint32_t n)
     {
     return (n + CB - 1) / CB;
@@ -321,6 +366,11 @@ void domain_destroy(hb2_system* s)
         return;
     if (D.comm && g_nccl.CommDestroy)
         g_nccl.CommDestroy((ncclComm_t)D.comm);
+    for (int r = 0; r < D.nranks && r < P2P_MAX_RANKS; r++)
+        if (r != D.rank && D.peer_mail[r])
+            cudaIpcCloseMemHandle(D.peer_mail[r]);
+    dev_free(D.d_mail);
+    dev_free(D.d_peer_mail);
     for (int d = 0; d < 3; d++)
         dev_free(D.d_send_idx[d]);
     dev_free(D.d_ghost_slot);
@@ -757,14 +807,27 @@ hb2_status domain_update_ghosts(hb2_system* s)
     return HB2_OK;
     }
 
+static hb2_status p2p_allreduce(hb2_system* s, void* d_val, int op)
+    {
+    Domain& D = s->dom;
+    D.p2p_epoch++;
+    p2p_allreduce_kernel<<<1, 32, 0, s->stream>>>(D.d_peer_mail, D.d_mail, D.rank, D.nranks, D.p2p_epoch, op, d_val);
+    HB2_CHECK_LAUNCH("p2p_allreduce_kernel");
+    return HB2_OK;
+    }
+
 hb2_status domain_allreduce_max_u32(hb2_system* s, uint32_t* d_val, uint32_t n)
     {
+    if (s->dom.p2p && n == 1)
+        return p2p_allreduce(s, d_val, 0);
     HB2_NCCL(g_nccl.AllReduce(d_val, d_val, n, ncclUint32, ncclMax, (ncclComm_t)s->dom.comm, s->stream));
     return HB2_OK;
     }
 
 hb2_status domain_allreduce_sum_f64(hb2_system* s, double* d_val, uint32_t n)
     {
+    if (s->dom.p2p && n == 1)
+        return p2p_allreduce(s, d_val, 1);
     HB2_NCCL(g_nccl.AllReduce(d_val, d_val, n, ncclDouble, ncclSum, (ncclComm_t)s->dom.comm, s->stream));
     return HB2_OK;
     }
@@ -773,6 +836,93 @@ hb2_status domain_allreduce_sum_f64(hb2_system* s, double* d_val, uint32_t n)
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// ---- peer-memory mailboxes: bootstrap. Every rank allocates its mailbox and exports it
+// (hb2_domain_ipc_handle), the handles are gathered by the caller's side channel (torch.distributed, like the
+// NCCL unique id), and hb2_domain_set_peers maps them. The switch is collective: if the mapping fails on any rank
+// (or HB2_P2P=0), every rank keeps the NCCL all-reduces.
+extern "C" hb2_status hb2_domain_ipc_handle(hb2_system* s, void* out64)
+    {
+    if (!s || !out64 || !s->dom.active)
+        return HB2_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    Domain& D = s->dom;
+    HB2_CUDA(cudaSetDevice(s->device));
+    memset(out64, 0, 64);
+    if (D.nranks > P2P_MAX_RANKS)
+        return HB2_OK; // too many ranks for the mailbox: the zero handle switches the path off everywhere
+    if (!D.d_mail)
+        HB2_TRY(dev_alloc(&D.d_mail, 2 * (size_t)P2P_MAX_RANKS));
+    HB2_CUDA(cudaMemset(D.d_mail, 0, sizeof(P2PBox) * 2 * P2P_MAX_RANKS));
+    HB2_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, D.d_mail) != cudaSuccess)
+        {
+        cudaGetLastError();
+        return HB2_OK; // zero handle
+        }
+    memcpy(out64, &h, 64);
+    return HB2_OK;
+    }
+
+extern "C" hb2_status hb2_domain_set_peers(hb2_system* s, const void* handles, uint32_t nranks)
+    {
+    if (!s || !handles || !s->dom.active || (int)nranks != s->dom.nranks)
+        return HB2_ERR_INVALID;
+    Domain& D = s->dom;
+    HB2_CUDA(cudaSetDevice(s->device));
+    static const bool enabled = !(getenv("HB2_P2P") && atoi(getenv("HB2_P2P")) == 0);
+    uint32_t failed = (enabled && D.d_mail && (int)nranks <= P2P_MAX_RANKS) ? 0u : 1u;
+    const unsigned char zero[64] = {0};
+    for (uint32_t r = 0; r < nranks && !failed; r++)
+        {
+        const unsigned char* hr = (const unsigned char*)handles + 64 * (size_t)r;
+        if (memcmp(hr, zero, 64) == 0)
+            {
+            failed = 1u;
+            break;
+            }
+        if ((int)r == D.rank)
+            {
+            D.peer_mail[r] = D.d_mail;
+            continue;
+            }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hr, 64);
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+            {
+            cudaGetLastError();
+            failed = 1u;
+            break;
+            }
+        D.peer_mail[r] = (P2PBox*)p;
+        }
+    // agree: one failure anywhere keeps NCCL everywhere
+    uint32_t* d_f = nullptr;
+    HB2_TRY(dev_alloc(&d_f, 1));
+    HB2_CUDA(cudaMemcpyAsync(d_f, &failed, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    HB2_NCCL(g_nccl.AllReduce(d_f, d_f, 1, ncclUint32, ncclMax, (ncclComm_t)D.comm, s->stream));
+    HB2_CUDA(cudaMemcpyAsync(&failed, d_f, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HB2_CUDA(cudaStreamSynchronize(s->stream));
+    dev_free(d_f);
+    if (failed)
+        {
+        D.p2p = false;
+        return HB2_OK;
+        }
+    if (!D.d_peer_mail)
+        HB2_TRY(dev_alloc(&D.d_peer_mail, (size_t)P2P_MAX_RANKS));
+    HB2_CUDA(cudaMemcpy(D.d_peer_mail, D.peer_mail, sizeof(P2PBox*) * P2P_MAX_RANKS, cudaMemcpyHostToDevice));
+    D.p2p_epoch = 0;
+    D.p2p = true;
+    return HB2_OK;
+    }
+
+extern "C" int hb2_domain_p2p_active(const hb2_system* s)
+    {
+    return s && s->dom.p2p ? 1 : 0;
+    }
+
 extern "C" hb2_status hb2_comm_unique_id(void* out128)
     {
     if (!out128)

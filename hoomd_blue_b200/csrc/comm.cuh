@@ -58,6 +58,17 @@ HB2_HOSTDEVICE double domain_g(double f, uint32_t n, uint32_t coord)
     return g - (double)n;
     }
 
+// One-word collectives over NVLink peer memory (comm.cu: p2p_allreduce_kernel). Every rank owns a mailbox of
+// [2 epochs parity][P2P_MAX_RANKS] boxes in its HBM, mapped into every other process with CUDA IPC; a reduction
+// is ONE small kernel: store my value into slot [rank] of every peer's mailbox, wait until my own mailbox holds
+// this epoch's value of every rank, reduce in rank order (bit-identical on all ranks).
+constexpr int P2P_MAX_RANKS = 16;
+struct P2PBox
+    {
+    unsigned long long epoch;
+    double value;
+    };
+
 struct Domain
     {
     bool active = false;
@@ -89,6 +100,13 @@ struct Domain
     size_t cub_bytes = 0;
     uint32_t* d_inv = nullptr; // inverse of the cell-sort permutation
     uint32_t scratch_cap = 0;
+
+    // peer-memory mailboxes (null / false: the NCCL all-reduces serve)
+    bool p2p = false;
+    P2PBox* d_mail = nullptr;                       // this rank's mailbox
+    P2PBox* peer_mail[P2P_MAX_RANKS] = {};          // every rank's mailbox as mapped here (own included)
+    P2PBox** d_peer_mail = nullptr;                 // the same table on the device
+    unsigned long long p2p_epoch = 0;
     };
 
 // host entry points (comm.cu)

@@ -281,6 +281,12 @@ class State:
             raw = _comm.broadcast_object(bytes(uid))
             uid = (C.c_uint8 * 128).from_buffer_copy(raw)
             check(L.hb2_system_set_domain(h, grid, comm.rank, comm.num_ranks, uid))
+            # peer-memory mailboxes for the one-word reductions of every step (CUDA IPC handles travel like
+            # the NCCL id; the engine falls back to NCCL collectively when a peer cannot be mapped)
+            ipc = (C.c_uint8 * 64)()
+            check(L.hb2_domain_ipc_handle(h, ipc))
+            handles = b"".join(_comm.all_gather_arrays(bytes(ipc)))
+            check(L.hb2_domain_set_peers(h, handles, comm.num_ranks))
             self._grid = tuple(int(g) for g in grid)
         if local is not None:
             self._set_tagged(*local)

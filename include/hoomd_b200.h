@@ -222,6 +222,14 @@ uint32_t hb2_system_n(const hb2_system* sys); /* owned particles on this rank */
 hb2_status hb2_comm_unique_id(void* out128);
 hb2_status hb2_system_set_domain(hb2_system* sys, const uint32_t grid[3], uint32_t rank,
                                  uint32_t nranks, const void* nccl_unique_id);
+/* Optional, after hb2_system_set_domain: one-word reductions of every step (the rebuild vote of
+ * hoomd/md/NeighborList.cc:1271-1285 — MPI_Allreduce there — and the thermostat's kinetic energy) over NVLink
+ * peer memory instead of NCCL launches. Every rank exports a 64-byte CUDA IPC handle of its mailbox, the caller
+ * gathers the nranks handles in rank order (any side channel) and hands them to every rank; the switch is
+ * collective (one rank that cannot map a peer, or HB2_P2P=0, keeps NCCL everywhere). */
+hb2_status hb2_domain_ipc_handle(hb2_system* sys, void* out64);
+hb2_status hb2_domain_set_peers(hb2_system* sys, const void* handles, uint32_t nranks);
+int hb2_domain_p2p_active(const hb2_system* sys);
 /* hoomd/DomainDecomposition.cc:327-409 (findDecomposition): the grid with the least interface area. */
 hb2_status hb2_domain_find_decomposition(uint32_t nranks, double Lx, double Ly, double Lz,
                                          uint32_t grid[3]);

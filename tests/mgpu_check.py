@@ -214,7 +214,10 @@ def main():
     assert np.max(np.abs(nud - nu1)) <= 1e-5 * np.max(np.abs(nu1)), (nud, nu1)
     assert abs(ked - ke1) <= 2e-4 * abs(ke1), (ked, ke1)
     assert abs(int(bd_) - int(b1_)) <= 1
+    from hoomd_blue_b200 import _lib as _l
+    p2p = int(_l.lib().hb2_domain_p2p_active(sim.state._h))
     if rank == 0:
+        msg += f" p2p_mailboxes={p2p}"
         msg += f" npt_box_rel={np.max(np.abs(Ld / L1 - 1.0)):.1e} npt_nu_rel={np.max(np.abs(nud - nu1)) / np.max(np.abs(nu1)):.1e}"
         print(msg + f" bussi_KE_rel={abs(kb - kr) / abs(kr):.1e} dpd_force_err={derr:.1e}"
               f" langevin_KE_rel={abs(kl - km) / abs(km):.1e}"
