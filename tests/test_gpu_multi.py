@@ -26,3 +26,16 @@ def test_domain_decomposition(nproc):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mgpu ok" in r.stdout
+
+
+@pytest.mark.parametrize("nproc", [2, 8])
+def test_peer_memory_mailboxes(nproc):
+    """The per-step one-word reductions over NVLink peer memory (CUDA IPC mailboxes) with many ranks."""
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29520 + nproc),
+           os.path.join(ROOT, "tests", "p2p8_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "p2p8 ok" in r.stdout and "p2p_mailboxes=1" in r.stdout
