@@ -210,3 +210,31 @@ def test_two_rank_ghost_plan_over_gloo(grid):
         assert r[1] == "ok", r[1]
     assert sum(r[2] for r in res) == 12 ** 3
     assert all(r[3] > 0 for r in res)
+
+
+def test_fill_holes_plan():
+    """The in-place compaction of a migration stage (csrc/comm.cu fill_holes_kernel), restated: with the m
+    leaving indices in ascending order, the r-th stayer of the tail [N - m, N) moves into the r-th hole below
+    N - m. Afterwards [0, N - m) holds exactly the stayers, each once, and the plan is a pure function of the
+    leaver set."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for N, m in ((1, 0), (1, 1), (10, 3), (1000, 37), (1000, 999), (64, 64), (5000, 1)):
+        leave = np.sort(rng.choice(N, size=m, replace=False)).astype(np.int64)
+        is_leaver = np.zeros(N, dtype=bool)
+        is_leaver[leave] = True
+        data = np.arange(N) * 10 + 7  # a payload that names its original slot
+        out = data.copy()
+        n_stay = N - m
+        h = int(np.searchsorted(leave, n_stay, side="left"))  # holes below the new end
+        moved = 0
+        for k in range(m):  # one thread per tail slot, as the kernel
+            t = n_stay + k
+            if is_leaver[t]:
+                continue
+            r = k - (int(np.searchsorted(leave, t, side="left")) - h)
+            assert 0 <= r < h
+            out[leave[r]] = data[t]
+            moved += 1
+        assert moved == h
+        assert sorted(out[:n_stay].tolist()) == sorted(data[~is_leaver].tolist())
